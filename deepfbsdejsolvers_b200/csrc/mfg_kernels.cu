@@ -1,0 +1,325 @@
+// Fused kernels of the smart-grid mean-field game (coupled FBSDE with Cox-process jumps).
+//
+// Reference: coupledMFG/MFGModel.py:35-107 (state update, closed-form controls), coupledMFG/MFGSolvers.py
+// loss graphs Global :24-47, MultiStep :187-224, SumLocal :328-364, SumLocalReg :469-505, MultiStepReg :615-651.
+// States per path: (hQ, Q, R) exogenous, (hS, S) driven by the networks through the controls.  The
+// compensator is analytic (lam*dt), so a step is two small MLP rows plus ~60 flops.  One thread per path.
+#include "mfg.cuh"
+
+namespace fbsdej {
+
+struct Controls { float ah, al; };
+
+// calpha_hat / calpha, MFGModel.py:82-89
+__device__ __forceinline__ Controls controls(const MFGArgs& a, int i, float hQ, float Q, float R, float hY, float Y) {
+  Controls c;
+  const float ind = (R <= a.thetaR) ? 1.0f : 0.0f;
+  const float ce = a.coeffEqui;
+  const float kTheta = a.A + (1.0f - a.pi) * ce * a.p1 + a.K + ce * a.f1 * ind;
+  const float mq = a.meanhq[i];
+  const float atg = a.stochastic ? a.alphaTarget * mq : a.alphaTarget;
+  c.ah = -(1.0f / kTheta) * (a.p0 + a.pi * a.p1 * hQ + ((1.0f - a.pi) * ce * a.p1 + a.K) * hQ + hY +
+                             (a.f0 + ce * a.f1 * (hQ - mq - atg)) * ind);
+  c.al = -(1.0f / (a.A + a.K)) * (a.K * Q + a.p0 + a.pi * a.p1 * hQ + (1.0f - a.pi) * ce * a.p1 * (hQ + c.ah) + Y +
+                                  (a.f0 + ce * a.f1 * (hQ - mq + c.ah - atg)) * ind);
+  return c;
+}
+
+template <int HP>
+__global__ void __launch_bounds__(kThreads) mfg_forward(const MFGArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* swA = smem;
+  float* swB = swA + net_smem_floats(a.netA, HP, false);
+  float* red = swB + net_smem_floats(a.netB, HP, false);
+  float* tb = red + 8;
+  Tiles<HP> t;
+  t.carve(tb, false);
+  const NetView<HP> nvA = load_net<HP>(swA, a.theta, a.netA, false);
+  const NetView<HP> nvB = load_net<HP>(swB, a.theta, a.netB, false);
+  zero_tiles<HP>(tb, Tiles<HP>::fwd_floats());
+  const int row = threadIdx.x;
+  float* xt = t.xt + row;
+  const float* out = t.out + row;
+  const size_t sB = (size_t)a.B;
+  const int c0 = a.has_y ? 1 : 0;
+  float lh_sum = 0.0f, li_sum = 0.0f;
+  const int ntiles = (a.B + kThreads - 1) / kThreads;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int p0 = tile * kThreads + threadIdx.x;
+    const bool valid = p0 < a.B;
+    const int p = valid ? p0 : a.B - 1;
+    float hQ = a.q0, Q = a.q0, R = a.R0, hS = a.S0, S = a.S0;
+    float hY = 0.0f, Y = 0.0f;
+    if (a.scheme == SCH_GLOBAL) { hY = a.theta[a.y0_off]; Y = a.theta[a.y0_off + 1]; }
+    float Ch = 0.0f, Ci = 0.0f;                                                       // MultiStep
+    float hyp = 0.0f, ahp = 0.0f, yp = 0.0f, aip = 0.0f, llh = 0.0f, lli = 0.0f;      // SumLocal
+    for (int i = 0; i < a.N; ++i) {
+      const float tm = (float)i * a.dt;
+      const float dW0 = a.dW0[(size_t)i * sB + p], dW = a.dW[(size_t)i * sB + p], dN = a.dN[(size_t)i * sB + p];
+      xt[0] = tm; xt[RS] = hQ; xt[2 * RS] = hS; xt[3 * RS] = R;                       // getProjectedStates
+      mlp_fwd<HP, false>(nvA, t, row);
+      const float oh0 = out[0], oh1 = out[RS], oh2 = out[2 * RS];
+      xt[0] = tm; xt[RS] = Q; xt[2 * RS] = S; xt[3 * RS] = hQ; xt[4 * RS] = hS; xt[5 * RS] = R;   // getAllStates
+      mlp_fwd<HP, false>(nvB, t, row);
+      const float o0 = out[0], o1 = out[RS], o2 = out[2 * RS], o3 = out[3 * RS];
+      const float lamdt = (a.stochastic ? a.beta * (expf(a.alpha * hQ) - 1.0f) : a.jumpFactor) * a.dt;
+      const float dNc = dN - lamdt;
+      float a_h = -a.dt * (hS * a.C), a_i = -a.dt * (S * a.C);
+      if (a.has_z) {
+        const float hz0 = c0 ? oh1 : oh0, hgam = c0 ? oh2 : oh1;
+        const float z0 = c0 ? o1 : o0, gam = c0 ? o2 : o1, z = c0 ? o3 : o2;
+        a_h = a_h + hz0 * dW0 + hgam * dNc;                    // MFGSolvers.py:40 / :203
+        a_i = a_i + z0 * dW0 + gam * dNc + z * dW;             // :41 / :204
+      }
+      const float hYsel = (a.scheme == SCH_GLOBAL) ? hY : oh0;
+      const float Ysel = (a.scheme == SCH_GLOBAL) ? Y : o0;
+      if (valid) {
+        float* tx = a.traj + ((size_t)i * 5) * sB + p;
+        tx[0] = hQ; tx[sB] = Q; tx[2 * sB] = R; tx[3 * sB] = hS; tx[4 * sB] = S;
+        if (a.trajY) { a.trajY[((size_t)i * 2) * sB + p] = hYsel; a.trajY[((size_t)i * 2 + 1) * sB + p] = Ysel; }
+      }
+      if (a.scheme == SCH_GLOBAL) {
+        hY += a_h; Y += a_i;
+      } else if (a.scheme == SCH_MULTISTEP) {
+        if (valid) {
+          a.sch[((size_t)i * 2 + 0) * sB + p] = hYsel - Ch;
+          a.sch[((size_t)i * 2 + 1) * sB + p] = Ysel - Ci;
+        }
+        Ch += a_h; Ci += a_i;
+      } else {
+        if (i > 0) {
+          const float rh = hYsel - hyp - ahp, ri = Ysel - yp - aip;
+          llh = fmaf(rh, rh, llh); lli = fmaf(ri, ri, lli);
+          if (valid) { a.sch[((size_t)(i - 1) * 2 + 0) * sB + p] = rh; a.sch[((size_t)(i - 1) * 2 + 1) * sB + p] = ri; }
+        }
+        hyp = hYsel; ahp = a_h; yp = Ysel; aip = a_i;
+      }
+      // oneStepFrom, MFGModel.py:58-71 (controls use the states of step i)
+      const Controls c = controls(a, i, hQ, Q, R, hYsel, Ysel);
+      hS = hS + c.ah * a.dt;
+      S = S + c.al * a.dt;
+      R = R + a.dt - (dN > 0.0f ? R : 0.0f);
+      const float qn = a.qaver[i + 1];
+      hQ = hQ + a.coeffOU * (qn - hQ) * a.dt + a.sig0 * dW0;
+      Q = Q + a.coeffOU * (qn - Q) * a.dt + a.sig0 * dW0 + a.sig * dW;
+    }
+    const float gh = a.h1 + a.h2 * hS, gi = a.h1 + a.h2 * S;
+    float lh = 0.0f, li = 0.0f;
+    if (a.scheme == SCH_GLOBAL) {
+      const float eh = hY - gh, ei = Y - gi;
+      lh = eh * eh * a.inv_B; li = ei * ei * a.inv_B;
+      if (valid) { a.fin[p] = eh; a.fin[sB + p] = ei; }
+    } else if (a.scheme == SCH_MULTISTEP) {
+      if (valid) {
+        const float Dh = Ch - gh, Di = Ci - gi;
+        float seh = 0.0f, sei = 0.0f, s2h = 0.0f, s2i = 0.0f;
+        for (int k = 0; k < a.N; ++k) {
+          const float eh = a.sch[((size_t)k * 2 + 0) * sB + p] + Dh, ei = a.sch[((size_t)k * 2 + 1) * sB + p] + Di;
+          a.sch[((size_t)k * 2 + 0) * sB + p] = eh; a.sch[((size_t)k * 2 + 1) * sB + p] = ei;
+          seh += eh; sei += ei; s2h = fmaf(eh, eh, s2h); s2i = fmaf(ei, ei, s2i);
+        }
+        lh = s2h * (a.inv_B / (float)a.N); li = s2i * (a.inv_B / (float)a.N);
+        a.fin[p] = seh; a.fin[sB + p] = sei;
+      }
+    } else {
+      const float rh = gh - hyp - ahp, ri = gi - yp - aip;
+      llh = fmaf(rh, rh, llh); lli = fmaf(ri, ri, lli);
+      lh = llh * a.inv_B; li = lli * a.inv_B;
+      if (valid) { a.sch[((size_t)(a.N - 1) * 2 + 0) * sB + p] = rh; a.sch[((size_t)(a.N - 1) * 2 + 1) * sB + p] = ri; }
+    }
+    if (valid) {
+      float* tx = a.traj + ((size_t)a.N * 5) * sB + p;
+      tx[0] = hQ; tx[sB] = Q; tx[2 * sB] = R; tx[3 * sB] = hS; tx[4 * sB] = S;
+      if (a.trajY) {
+        a.trajY[((size_t)a.N * 2) * sB + p] = (a.scheme == SCH_GLOBAL) ? hY : gh;
+        a.trajY[((size_t)a.N * 2 + 1) * sB + p] = (a.scheme == SCH_GLOBAL) ? Y : gi;
+      }
+      lh_sum += lh; li_sum += li;
+    }
+  }
+  const float th = block_sum(lh_sum, red);
+  const float ti = block_sum(li_sum, red);
+  if (threadIdx.x == 0) {
+    a.lpart[blockIdx.x * 4 + 0] = a.w_hat * th + a.w_ind * ti;
+    a.lpart[blockIdx.x * 4 + 1] = th;
+    a.lpart[blockIdx.x * 4 + 2] = ti;
+    a.lpart[blockIdx.x * 4 + 3] = 0.0f;
+  }
+}
+
+template <int HP>
+__global__ void __launch_bounds__(kThreads) mfg_backward(const MFGArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* swA = smem;
+  float* swB = swA + net_smem_floats(a.netA, HP, true);
+  float* red = swB + net_smem_floats(a.netB, HP, true);
+  float* tb = red + 8;
+  Tiles<HP> t;
+  t.carve(tb, true);
+  const NetView<HP> nvA = load_net<HP>(swA, a.theta, a.netA, true);
+  const NetView<HP> nvB = load_net<HP>(swB, a.theta, a.netB, true);
+  zero_tiles<HP>(tb, Tiles<HP>::bwd_floats());
+  WGrad<HP> wgA, wgB;
+  wgA.init(nvA, t);
+  wgB.init(nvB, t);
+  const int row = threadIdx.x;
+  float* xt = t.xt + row;
+  float* dout = t.dout + row;
+  const size_t sB = (size_t)a.B;
+  const int c0 = a.has_y ? 1 : 0;
+  const float invB = a.inv_B, invBN = a.inv_B / (float)a.N;
+  const float wh = a.w_hat, wi = a.w_ind;
+  float y0h = 0.0f, y0i = 0.0f;
+  const int ntiles = (a.B + kThreads - 1) / kThreads;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int p0 = tile * kThreads + threadIdx.x;
+    const bool valid = p0 < a.B;
+    const int p = valid ? p0 : a.B - 1;
+    const float msk = valid ? 1.0f : 0.0f;
+    float Eh = 0.0f, Ei = 0.0f;
+    float ghbar, gibar, hYbar = 0.0f, Ybar = 0.0f;
+    if (a.scheme == SCH_GLOBAL) {
+      hYbar = 2.0f * a.fin[p] * invB * wh; Ybar = 2.0f * a.fin[sB + p] * invB * wi;
+      ghbar = -hYbar; gibar = -Ybar;
+    } else if (a.scheme == SCH_MULTISTEP) {
+      Eh = a.fin[p]; Ei = a.fin[sB + p];
+      ghbar = -2.0f * Eh * invBN * wh;
+      gibar = -2.0f * Ei * invBN * wi;
+    } else {
+      ghbar = 2.0f * a.sch[((size_t)(a.N - 1) * 2 + 0) * sB + p] * invB * wh;
+      gibar = 2.0f * a.sch[((size_t)(a.N - 1) * 2 + 1) * sB + p] * invB * wi;
+    }
+    float hSbar = ghbar * a.h2, Sbar = gibar * a.h2;
+    for (int i = a.N - 1; i >= 0; --i) {
+      const float tm = (float)i * a.dt;
+      const float* tx = a.traj + ((size_t)i * 5) * sB + p;
+      const float hQ = tx[0], Q = tx[sB], R = tx[2 * sB], hS = tx[3 * sB], S = tx[4 * sB];
+      const float dW0 = a.dW0[(size_t)i * sB + p], dW = a.dW[(size_t)i * sB + p], dN = a.dN[(size_t)i * sB + p];
+      const float lamdt = (a.stochastic ? a.beta * (expf(a.alpha * hQ) - 1.0f) : a.jumpFactor) * a.dt;
+      const float dNc = dN - lamdt;
+      // adjoint of the controlled states: hS' = hS + ah dt, S' = S + al dt
+      const float ind = (R <= a.thetaR) ? 1.0f : 0.0f;
+      const float ce = a.coeffEqui;
+      const float kTheta = a.A + (1.0f - a.pi) * ce * a.p1 + a.K + ce * a.f1 * ind;
+      const float albar = Sbar * a.dt;
+      const float dal_dah = -(1.0f / (a.A + a.K)) * ((1.0f - a.pi) * ce * a.p1 + ce * a.f1 * ind);
+      const float ahbar = hSbar * a.dt + albar * dal_dah;
+      const float cYi = albar * (-1.0f / (a.A + a.K));   // adjoint into the Y fed to oneStepFrom
+      const float cYh = ahbar * (-1.0f / kTheta);        // adjoint into hY
+      float abh, abi, hyb = 0.0f, yb = 0.0f;
+      if (a.scheme == SCH_GLOBAL) {
+        abh = hYbar; abi = Ybar;                 // hY_{i+1} = hY_i + a_h
+        hYbar += cYh; Ybar += cYi;               // OLD hY_i, Y_i feed the controls (MFGSolvers.py:43)
+      } else if (a.scheme == SCH_MULTISTEP) {
+        const float eh = a.sch[((size_t)i * 2 + 0) * sB + p], ei = a.sch[((size_t)i * 2 + 1) * sB + p];
+        abh = 2.0f * Eh * invBN * wh;
+        abi = 2.0f * Ei * invBN * wi;
+        hyb = 2.0f * eh * invBN * wh + cYh;
+        yb = 2.0f * ei * invBN * wi + cYi;
+        Eh -= eh; Ei -= ei;
+      } else {
+        const float rbh = 2.0f * a.sch[((size_t)i * 2 + 0) * sB + p] * invB * wh;
+        const float rbi = 2.0f * a.sch[((size_t)i * 2 + 1) * sB + p] * invB * wi;
+        float rbhm = 0.0f, rbim = 0.0f;
+        if (i > 0) {
+          rbhm = 2.0f * a.sch[((size_t)(i - 1) * 2 + 0) * sB + p] * invB * wh;
+          rbim = 2.0f * a.sch[((size_t)(i - 1) * 2 + 1) * sB + p] * invB * wi;
+        }
+        abh = -rbh; abi = -rbi;
+        hyb = rbhm - rbh + cYh;
+        yb = rbim - rbi + cYi;
+      }
+      // direct dependence of the increments on the states: a_h = -dt C hS + ..., a = -dt C S + ...
+      hSbar += -a.dt * a.C * abh;
+      Sbar += -a.dt * a.C * abi;
+      float dx[HP];
+      {
+        xt[0] = tm; xt[RS] = hQ; xt[2 * RS] = hS; xt[3 * RS] = R;
+        mlp_fwd<HP, true>(nvA, t, row);
+        for (int j = 0; j < nvA.nout; ++j) dout[j * RS] = 0.0f;
+        if (a.has_y) dout[0] = hyb * msk;
+        if (a.has_z) { dout[c0 * RS] = abh * dW0 * msk; dout[(c0 + 1) * RS] = abh * dNc * msk; }
+        mlp_delta<HP>(nvA, t, row, dx);
+        hSbar += dx[2];
+        __syncthreads();
+        wgA.accumulate(tb);
+        __syncthreads();
+      }
+      {
+        xt[0] = tm; xt[RS] = Q; xt[2 * RS] = S; xt[3 * RS] = hQ; xt[4 * RS] = hS; xt[5 * RS] = R;
+        mlp_fwd<HP, true>(nvB, t, row);
+        for (int j = 0; j < nvB.nout; ++j) dout[j * RS] = 0.0f;
+        if (a.has_y) dout[0] = yb * msk;
+        if (a.has_z) {
+          dout[c0 * RS] = abi * dW0 * msk; dout[(c0 + 1) * RS] = abi * dNc * msk; dout[(c0 + 2) * RS] = abi * dW * msk;
+        }
+        mlp_delta<HP>(nvB, t, row, dx);
+        Sbar += dx[2];
+        hSbar += dx[4];
+        __syncthreads();
+        wgB.accumulate(tb);
+        __syncthreads();
+      }
+    }
+    if (a.scheme == SCH_GLOBAL) { y0h += hYbar * msk; y0i += Ybar * msk; }
+  }
+  const float t0 = block_sum(y0h, red);
+  const float t1 = block_sum(y0i, red);
+  __syncthreads();
+  float* sg = tb;
+  for (int e = threadIdx.x; e < a.P; e += blockDim.x) sg[e] = 0.0f;
+  __syncthreads();
+  wgA.flush(nvA, sg, a.netA.ext_off);
+  wgB.flush(nvB, sg, a.netB.ext_off);
+  if (a.scheme == SCH_GLOBAL && threadIdx.x == 0) { sg[a.y0_off] = t0; sg[a.y0_off + 1] = t1; }
+  __syncthreads();
+  float* grow = a.gpart + (size_t)blockIdx.x * a.P;
+  for (int e = threadIdx.x; e < a.P; e += blockDim.x) grow[e] = sg[e];
+}
+
+template <int HP>
+static size_t mfg_smem(const MFGArgs& a, bool backward) {
+  const int w = net_smem_floats(a.netA, HP, backward) + net_smem_floats(a.netB, HP, backward);
+  const int tl = backward ? Tiles<HP>::bwd_floats() : Tiles<HP>::fwd_floats();
+  return sizeof(float) * (size_t)(w + 8 + tl);
+}
+size_t mfg_smem_bytes(int HP, const MFGArgs& a, bool backward) {
+  return HP == 24 ? mfg_smem<24>(a, backward) : mfg_smem<32>(a, backward);
+}
+
+int mfg_blocks_per_sm(int HP, const MFGArgs& a, bool backward) {
+  if (HP != 24) return 1;
+  const size_t smem = mfg_smem<24>(a, backward);
+  int nb = 0;
+  if (!backward) {
+    auto kern = mfg_forward<24>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem) != cudaSuccess) return 1;
+  } else {
+    auto kern = mfg_backward<24>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem) != cudaSuccess) return 1;
+  }
+  return nb < 1 ? 1 : nb;
+}
+
+int launch_mfg(int HP, const MFGArgs& a, int grid, bool backward, cudaStream_t st) {
+  if (HP != 24) {
+    set_error("mfg kernels: padded hidden width " + std::to_string(HP) + " not compiled (H <= 23)");
+    return -1;
+  }
+  const size_t smem = mfg_smem<24>(a, backward);
+  if (!backward) {
+    auto kern = mfg_forward<24>;
+    FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kThreads, smem, st>>>(a);
+  } else {
+    auto kern = mfg_backward<24>;
+    FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kThreads, smem, st>>>(a);
+  }
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace fbsdej

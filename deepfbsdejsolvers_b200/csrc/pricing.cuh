@@ -1,0 +1,149 @@
+// Argument block and model policies of the fused pricing-path kernels (Merton jump-diffusion,
+// d-asset geometric-basket extension, Variance Gamma).
+#pragma once
+#include "tile_mlp.cuh"
+
+namespace fbsdej {
+
+// loss-graph families (reference classes: SolversJumpDiff.py / SolversPureJump.py)
+enum { SCH_GLOBAL = 0, SCH_MULTISTEP = 1, SCH_SUMLOCAL = 2 };
+
+struct PricingArgs {
+  int B, N, G, M;             // local paths, time steps, threads per path, compensator sample count (mean denominator)
+  int scheme;                 // SCH_*
+  int one_net;                // jump rows are evaluated by netA (MultiStep1 / SumLocal1)
+  int has_jump;               // 0 for the *Reg solvers (no Z / Gam / compensator)
+  int use_netA;               // 0 only for VG Global (U network unused, SolversPureJump.py:22-41)
+  int has_y, zoff, has_z;     // netA output map: out[0] = Y if has_y; Z[k] = out[zoff + k] if has_z
+  int feat_mode;              // Merton two-net: 0 -> J (Global), 1 -> e^J
+  int stale_time;             // SumLocal*: time feature of step k >= 1 is k-1
+  float inv_B;                // 1 / GLOBAL batch (data-parallel ranks sum their partial means)
+  float dt, r, K, x0, aLin, sig, drift_dt;
+  NetRt netA, netB;
+  int y0_off, P;
+  const float* theta;
+  const float* dW;            // [N][D][B]
+  const float* J;             // [N][D][B]
+  const float* JMC;           // [N][D][Mcap]  non-zero samples first
+  const int* jmc_nnz;         // [N]
+  const int* jmc_n0;          // [N] multiplicity of the all-zero sample
+  int Mcap;
+  // Merton series tables (host float64 -> fp32): per (step, n): (c1, c2, sig_n*sqrt(tau), w_n), wK_n
+  const float4* tabA;
+  const float* tabK;
+  const int2* tab_range;      // [N] (nlo, nhi)
+  const float* qdisc;         // [N] e^{-q tau_i} (1 when d == 1)
+  int limit;
+  // VG spline tables: per (step, interval) cubic coefficients (c0..c3) around knot k0 + idx*h
+  const float4* vg_coef;
+  const float* vg_scale;      // [N] e^{-r tau_i} / pi
+  int vg_nint;
+  float vg_k0, vg_h, vg_inv_h;
+  // per path-step stores for the adjoint sweep
+  float* trajX;               // [N+1][D][B]
+  float* aux_s;               // [N][B]  aLin*dt*sign(Ysel - A_i)
+  float* aux_dA;              // [N][B]  dA/dX (d=1) or G*dA/dG/d (d>1)
+  float* sch1;                // [N][B]  MultiStep: e_k = F_k - g ; SumLocal: rho_i
+  float* fin;                 // [B]     Global: Y_N - g ; MultiStep: sum_k e_k
+  float* trajY;               // optional [N+1][B]
+  float* trajZ;               // optional [N][D][B]
+  float* lpart;               // [grid][4]
+  float* gpart;               // [grid][P]
+};
+
+template <int D_>
+struct MertonModel {
+  static constexpr int D = D_;
+  static constexpr bool kBrownian = true;
+
+  __device__ static __forceinline__ float basket(const float (&X)[D]) {
+    if (D == 1) return X[0];
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < D; ++k) s += logf(X[k]);
+    return expf(s * (1.0f / D));
+  }
+  // Closed-form price A(i, X) (pricingModels.py:33-49) and the stored derivative base.
+  __device__ static __forceinline__ void eval_A(const PricingArgs& a, int i, const float (&X)[D], float& A, float& dAb) {
+    const float G = basket(X);
+    const float Ge = (D == 1) ? G : G * a.qdisc[i];
+    const float k = logf(Ge / a.K);
+    const int2 rg = a.tab_range[i];
+    const float4* __restrict__ tA = a.tabA + (size_t)i * a.limit;
+    const float* __restrict__ tK = a.tabK + (size_t)i * a.limit;
+    float sD = 0.0f, sK = 0.0f;
+    for (int n = rg.x; n < rg.y; ++n) {
+      const float4 c = __ldg(tA + n);
+      const float d1 = fmaf(k, c.x, c.y);
+      const float d2 = d1 - c.z;
+      sD = fmaf(c.w, ncdf(d1), sD);
+      sK = fmaf(__ldg(tK + n), ncdf(d2), sK);
+    }
+    A = Ge * sD - sK;
+    dAb = (D == 1) ? sD : sD * Ge * (1.0f / D);
+  }
+  __device__ static __forceinline__ float dA_k(float dAb, float Xk) { return (D == 1) ? dAb : dAb / Xk; }
+  // jump-row inputs (SolversJumpDiff.py:37-39, 99-100, 173-175), written into this thread's row of the xt tile
+  __device__ static __forceinline__ void jump_input(const PricingArgs& a, float t, const float (&X)[D],
+                                                    const float (&Jv)[D], float* __restrict__ xt) {
+    xt[0] = t;
+    if (a.one_net) {
+#pragma unroll
+      for (int k = 0; k < D; ++k) xt[(1 + k) * RS] = X[k] * expf(Jv[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        xt[(1 + k) * RS] = X[k];
+        xt[(1 + D + k) * RS] = a.feat_mode == 0 ? Jv[k] : expf(Jv[k]);
+      }
+    }
+  }
+  template <int HP>
+  __device__ static __forceinline__ void jump_input_grad(const PricingArgs& a, const float (&Jv)[D], const float (&dx)[HP],
+                                                         float (&dX)[D]) {
+#pragma unroll
+    for (int k = 0; k < D; ++k) dX[k] += a.one_net ? dx[1 + k] * expf(Jv[k]) : dx[1 + k];
+  }
+};
+
+struct VGModel {
+  static constexpr int D = 1;
+  static constexpr bool kBrownian = false;
+
+  __device__ static __forceinline__ float basket(const float (&X)[1]) { return X[0]; }
+  // Lewis/FFT price through the per-step cubic table (pricingModels.py:156-179); the spline value is a
+  // constant for the gradient (tf.numpy_function), only the explicit X - sqrt(X K) factors are differentiated.
+  __device__ static __forceinline__ void eval_A(const PricingArgs& a, int i, const float (&X)[1], float& A, float& dAb) {
+    const float x = X[0];
+    const float k = logf(x / a.K);
+    int idx = (int)floorf((k - a.vg_k0) * a.vg_inv_h);
+    idx = idx < 0 ? 0 : (idx > a.vg_nint - 1 ? a.vg_nint - 1 : idx);
+    const float t = k - (a.vg_k0 + (float)idx * a.vg_h);
+    const float4 c = __ldg(a.vg_coef + (size_t)i * a.vg_nint + idx);
+    const float S = fmaf(fmaf(fmaf(c.w, t, c.z), t, c.y), t, c.x);
+    const float cs = a.vg_scale[i] * S;
+    const float sq = sqrtf(x * a.K);
+    A = x - sq * cs;
+    dAb = 1.0f - 0.5f * sq / x * cs;
+  }
+  __device__ static __forceinline__ float dA_k(float dAb, float) { return dAb; }
+  // jump-row inputs (SolversPureJump.py:34-36, 95-96)
+  __device__ static __forceinline__ void jump_input(const PricingArgs& a, float t, const float (&X)[1],
+                                                    const float (&Jv)[1], float* __restrict__ xt) {
+    xt[0] = t;
+    if (a.one_net) {
+      xt[RS] = X[0] + X[0] * Jv[0];
+    } else {
+      xt[RS] = X[0];
+      xt[2 * RS] = X[0] * Jv[0];
+    }
+  }
+  template <int HP>
+  __device__ static __forceinline__ void jump_input_grad(const PricingArgs& a, const float (&Jv)[1], const float (&dx)[HP],
+                                                         float (&dX)[1]) {
+    if (a.one_net) dX[0] += dx[1] * (1.0f + Jv[0]);
+    else dX[0] += dx[1] + dx[2] * Jv[0];
+  }
+};
+
+}  // namespace fbsdej

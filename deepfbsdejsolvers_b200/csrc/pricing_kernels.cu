@@ -1,0 +1,441 @@
+// Fused pricing-path kernels: one launch walks every path of the batch through all N Euler steps.
+//
+//   pricing_forward : per-step MLP evaluations (UZ/U net, jump net on the path's own jump, Monte-Carlo
+//                     compensator over the shared samples), BSDE update, closed-form coupling A(i,X),
+//                     coupled Euler step of X, loss terms; stores the O(1)-per-step state the adjoint needs.
+//   pricing_backward: reverse sweep with the hand-derived adjoint, recomputing activations into
+//                     shared-memory tiles, weight gradients accumulated in registers (tile_mlp.cuh).
+//
+// Row mapping: a CTA owns kThreads rows = (kThreads / G) paths x G rows; the G threads of a path share its
+// state and split the compensator samples (G = 1: one thread per path).
+//
+// Reference loss graphs: coupledPricing/SolversJumpDiff.py:22-44 (Global), :86-115/:162-190 (MultiStep1/2),
+// :236-269/:315-347 (SumLocal1/2), :391-415 (SumLocalReg), :461-481 (MultiStepReg); SolversPureJump.py same.
+#include "pricing.cuh"
+
+namespace fbsdej {
+
+__device__ __forceinline__ float group_allsum(float v, int G, float* red) {
+  if (G <= 32) return group_sum_shfl(v, G);
+  return block_sum(v, red);   // G == kThreads: one path per CTA
+}
+
+template <class Model, int HP>
+__global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a) {
+  constexpr int D = Model::D;
+  extern __shared__ __align__(16) float smem[];
+  float* swA = smem;
+  float* swB = swA + net_smem_floats(a.netA, HP, false);
+  float* red = swB + (a.one_net ? 0 : net_smem_floats(a.netB, HP, false));
+  float* tb = red + 8;
+  Tiles<HP> t;
+  t.carve(tb, false);
+  const NetView<HP> nvA = load_net<HP>(swA, a.theta, a.netA, false);
+  const NetView<HP> nvJ = a.one_net ? nvA : load_net<HP>(swB, a.theta, a.netB, false);
+  zero_tiles<HP>(tb, Tiles<HP>::fwd_floats());
+
+  const int row = threadIdx.x;
+  float* xt = t.xt + row;
+  const float* out = t.out + row;
+  const int G = a.G, ppb = kThreads / G, g = threadIdx.x % G;
+  const size_t sB = (size_t)a.B;
+  const float rdt = a.r * a.dt;
+  float lsum = 0.0f;
+  const int ntiles = (a.B + ppb - 1) / ppb;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int p0 = tile * ppb + threadIdx.x / G;
+    const bool valid = p0 < a.B;
+    const int p = valid ? p0 : a.B - 1;
+    const bool writer = valid && g == 0;
+    float X[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) X[k] = a.x0;
+    float Y = (a.scheme == SCH_GLOBAL) ? a.theta[a.y0_off] : 0.0f;
+    float Cpre = 0.0f;                               // MultiStep: sum_{j<i} toAdd_j
+    float yprev = 0.0f, aprev = 0.0f, lloc = 0.0f;   // SumLocal
+    for (int i = 0; i < a.N; ++i) {
+      const float tf = (a.scheme == SCH_SUMLOCAL && a.stale_time) ? (float)(i == 0 ? 0 : i - 1) : (float)i;
+      float dWv[D], Jv[D];
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        dWv[k] = Model::kBrownian ? a.dW[((size_t)i * D + k) * sB + p] : 0.0f;
+        Jv[k] = a.J[((size_t)i * D + k) * sB + p];
+      }
+      float y_net = 0.0f, zdw = 0.0f;
+      if (a.use_netA) {
+        xt[0] = tf;
+#pragma unroll
+        for (int k = 0; k < D; ++k) xt[(1 + k) * RS] = X[k];
+        mlp_fwd<HP, false>(nvA, t, row);
+        if (a.has_y) y_net = out[0];
+        if (a.has_z) {
+#pragma unroll
+          for (int k = 0; k < D; ++k) {
+            const float z = out[(a.zoff + k) * RS];
+            zdw = fmaf(z, dWv[k], zdw);
+            if (a.trajZ && writer) a.trajZ[((size_t)i * D + k) * sB + p] = z;
+          }
+        }
+      }
+      float gam = 0.0f, comp = 0.0f;
+      if (a.has_jump) {
+        Model::jump_input(a, tf, X, Jv, xt);
+        mlp_fwd<HP, false>(nvJ, t, row);
+        gam = out[0];
+        const int nnz = a.jmc_nnz[i], n0 = a.jmc_n0[i];
+        float csum = 0.0f;
+        for (int m = g; m <= nnz; m += G) {
+          float Jm[D];
+          float w = 1.0f;
+          if (m < nnz) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) Jm[k] = a.JMC[((size_t)i * D + k) * a.Mcap + m];
+          } else {
+            w = (float)n0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) Jm[k] = 0.0f;
+          }
+          if (w != 0.0f) {
+            Model::jump_input(a, tf, X, Jm, xt);
+            mlp_fwd<HP, false>(nvJ, t, row);
+            csum = fmaf(w, out[0], csum);
+          }
+        }
+        csum = group_allsum(csum, G, red);
+        comp = csum / (float)a.M;
+      }
+      // ---- loss-graph bookkeeping -----------------------------------------------------------
+      float Ysel;
+      if (a.scheme == SCH_GLOBAL) {
+        if (a.trajY && writer) a.trajY[(size_t)i * sB + p] = Y;
+        Y = Y - a.dt * (-a.r * Y) + zdw + gam - comp;        // SolversJumpDiff.py:41
+        Ysel = Y;                                            // the UPDATED Y feeds oneStepFrom (:43)
+      } else {
+        if (a.trajY && writer) a.trajY[(size_t)i * sB + p] = y_net;
+        const float ai = rdt * y_net + zdw + gam - comp;     // "toAdd" = -dt f(Y) + Z dW + Gam - mean(comp)
+        if (a.scheme == SCH_MULTISTEP) {
+          if (writer) a.sch1[(size_t)i * sB + p] = y_net - Cpre;   // u_i ; F_i - g = u_i + (sum_all toAdd - g)
+          Cpre += ai;
+        } else {
+          if (i > 0) {
+            const float rho = y_net - yprev - aprev;
+            lloc = fmaf(rho, rho, lloc);
+            if (writer) a.sch1[(size_t)(i - 1) * sB + p] = rho;
+          }
+          yprev = y_net; aprev = ai;
+        }
+        Ysel = y_net;
+      }
+      // ---- coupled Euler step (pricingModels.py:53-54 / :184-185) -----------------------------
+      float Ai, dAb;
+      Model::eval_A(a, i, X, Ai, dAb);
+      const float diff = Ysel - Ai;
+      const float coup = a.aLin * fabsf(diff) * a.dt;
+      if (writer) {
+        a.aux_s[(size_t)i * sB + p] = a.aLin * a.dt * (diff > 0.0f ? 1.0f : (diff < 0.0f ? -1.0f : 0.0f));
+        a.aux_dA[(size_t)i * sB + p] = dAb;
+#pragma unroll
+        for (int k = 0; k < D; ++k) a.trajX[((size_t)i * D + k) * sB + p] = X[k];
+      }
+#pragma unroll
+      for (int k = 0; k < D; ++k) X[k] = X[k] * expf(a.drift_dt + a.sig * dWv[k] + Jv[k]) + coup;
+    }
+    // ---- terminal condition ---------------------------------------------------------------------
+    const float gN = fmaxf(Model::basket(X) - a.K, 0.0f);
+    float lpath = 0.0f;
+    if (a.scheme == SCH_GLOBAL) {
+      const float e = Y - gN;
+      lpath = e * e * a.inv_B;
+      if (writer) { a.fin[p] = e; if (a.trajY) a.trajY[(size_t)a.N * sB + p] = Y; }
+    } else if (a.scheme == SCH_MULTISTEP) {
+      // second sweep over the stored u_k: e_k = F_k - g(X_N), loss = mean_k mean_b e_k^2 (SolversJumpDiff.py:115)
+      if (writer) {
+        const float Dv = Cpre - gN;
+        float se = 0.0f, s2 = 0.0f;
+        for (int k = 0; k < a.N; ++k) {
+          const float e = a.sch1[(size_t)k * sB + p] + Dv;
+          a.sch1[(size_t)k * sB + p] = e;
+          se += e;
+          s2 = fmaf(e, e, s2);
+        }
+        lpath = s2 * (a.inv_B / (float)a.N);
+        a.fin[p] = se;
+        if (a.trajY) a.trajY[(size_t)a.N * sB + p] = gN;
+      }
+    } else {
+      const float rho = gN - yprev - aprev;
+      lloc = fmaf(rho, rho, lloc);
+      lpath = lloc * a.inv_B;
+      if (writer) { a.sch1[(size_t)(a.N - 1) * sB + p] = rho; if (a.trajY) a.trajY[(size_t)a.N * sB + p] = gN; }
+    }
+    if (writer) {
+#pragma unroll
+      for (int k = 0; k < D; ++k) a.trajX[((size_t)a.N * D + k) * sB + p] = X[k];
+      lsum += lpath;
+    }
+  }
+  const float tot = block_sum(lsum, red);
+  if (threadIdx.x == 0) {
+    a.lpart[blockIdx.x * 4] = tot;
+    a.lpart[blockIdx.x * 4 + 1] = 0.0f; a.lpart[blockIdx.x * 4 + 2] = 0.0f; a.lpart[blockIdx.x * 4 + 3] = 0.0f;
+  }
+}
+
+template <class Model, int HP>
+__global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a) {
+  constexpr int D = Model::D;
+  extern __shared__ __align__(16) float smem[];
+  float* swA = smem;
+  float* swB = swA + net_smem_floats(a.netA, HP, true);
+  float* red = swB + (a.one_net ? 0 : net_smem_floats(a.netB, HP, true));
+  float* tb = red + 8;
+  Tiles<HP> t;
+  t.carve(tb, true);
+  const NetView<HP> nvA = load_net<HP>(swA, a.theta, a.netA, true);
+  const NetView<HP> nvJ = a.one_net ? nvA : load_net<HP>(swB, a.theta, a.netB, true);
+  zero_tiles<HP>(tb, Tiles<HP>::bwd_floats());
+  WGrad<HP> wgA, wgB;
+  wgA.init(nvA, t);
+  wgB.init(nvJ, t);
+
+  const int row = threadIdx.x;
+  float* xt = t.xt + row;
+  float* dout = t.dout + row;
+  const int G = a.G, ppb = kThreads / G, g = threadIdx.x % G;
+  const size_t sB = (size_t)a.B;
+  const float invB = a.inv_B, invBN = a.inv_B / (float)a.N, rdt = a.r * a.dt;
+  float y0g = 0.0f;
+  const int ntiles = (a.B + ppb - 1) / ppb;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int p0 = tile * ppb + threadIdx.x / G;
+    const bool valid = p0 < a.B;
+    const int p = valid ? p0 : a.B - 1;
+    const float msk = (valid && g == 0) ? 1.0f : 0.0f;   // rows that count for the main sites
+    const float vmsk = valid ? 1.0f : 0.0f;              // rows that count for the compensator
+    float X[D], Xbar[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) X[k] = a.trajX[((size_t)a.N * D + k) * sB + p];
+    float gbar, Ybar = 0.0f, Esum = 0.0f;
+    if (a.scheme == SCH_GLOBAL) {
+      Ybar = 2.0f * a.fin[p] * invB;
+      gbar = -Ybar;
+    } else if (a.scheme == SCH_MULTISTEP) {
+      Esum = a.fin[p];                                   // sum_k e_k ; d loss / d g = -2/(NB) sum_k e_k
+      gbar = -2.0f * Esum * invBN;
+    } else {
+      gbar = 2.0f * a.sch1[(size_t)(a.N - 1) * sB + p] * invB;
+    }
+    {
+      const float Gb = Model::basket(X);
+      const float ind = (Gb - a.K >= 0.0f) ? 1.0f : 0.0f;    // tf.maximum: gradient to the first argument on ties
+#pragma unroll
+      for (int k = 0; k < D; ++k) Xbar[k] = gbar * ind * ((D == 1) ? 1.0f : Gb / ((float)D * X[k]));
+    }
+    for (int i = a.N - 1; i >= 0; --i) {
+      const float tf = (a.scheme == SCH_SUMLOCAL && a.stale_time) ? (float)(i == 0 ? 0 : i - 1) : (float)i;
+      float dWv[D], Jv[D];
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        X[k] = a.trajX[((size_t)i * D + k) * sB + p];
+        dWv[k] = Model::kBrownian ? a.dW[((size_t)i * D + k) * sB + p] : 0.0f;
+        Jv[k] = a.J[((size_t)i * D + k) * sB + p];
+      }
+      const float s_i = a.aux_s[(size_t)i * sB + p], dAb = a.aux_dA[(size_t)i * sB + p];
+      // adjoint of the coupled Euler step X' = X e^{..} + aLin |Ysel - A(i,X)| dt
+      float sumXbar = 0.0f;
+#pragma unroll
+      for (int k = 0; k < D; ++k) sumXbar += Xbar[k];
+      const float cY = sumXbar * s_i;
+#pragma unroll
+      for (int k = 0; k < D; ++k)
+        Xbar[k] = Xbar[k] * expf(a.drift_dt + a.sig * dWv[k] + Jv[k]) - cY * Model::dA_k(dAb, X[k]);
+      // adjoints of the loss graph
+      float abar, ybar = 0.0f;
+      if (a.scheme == SCH_GLOBAL) {
+        Ybar += cY;
+        abar = Ybar;
+      } else if (a.scheme == SCH_MULTISTEP) {
+        const float e = a.sch1[(size_t)i * sB + p];
+        abar = 2.0f * Esum * invBN;                       // sum_{k<=i} Fbar_k
+        ybar = 2.0f * e * invBN + rdt * abar + cY;
+        Esum -= e;
+      } else {
+        const float rb = 2.0f * a.sch1[(size_t)i * sB + p] * invB;
+        const float rbm = (i > 0) ? 2.0f * a.sch1[(size_t)(i - 1) * sB + p] * invB : 0.0f;
+        abar = -rb;
+        ybar = rbm - rb + rdt * abar + cY;
+      }
+      float dXacc[D];
+#pragma unroll
+      for (int k = 0; k < D; ++k) dXacc[k] = 0.0f;
+      float dx[HP];
+      if (a.use_netA) {
+        xt[0] = tf;
+#pragma unroll
+        for (int k = 0; k < D; ++k) xt[(1 + k) * RS] = X[k];
+        mlp_fwd<HP, true>(nvA, t, row);
+        for (int j = 0; j < a.netA.nout; ++j) dout[j * RS] = 0.0f;
+        if (a.has_y) dout[0] = ybar * msk;
+        if (a.has_z && a.has_jump) {
+#pragma unroll
+          for (int k = 0; k < D; ++k) dout[(a.zoff + k) * RS] = abar * dWv[k] * msk;
+        }
+        mlp_delta<HP>(nvA, t, row, dx);
+#pragma unroll
+        for (int k = 0; k < D; ++k) dXacc[k] += dx[1 + k];
+        __syncthreads();
+        wgA.accumulate(tb);
+        __syncthreads();
+      }
+      if (a.has_jump) {
+        Model::jump_input(a, tf, X, Jv, xt);
+        mlp_fwd<HP, true>(nvJ, t, row);
+        for (int j = 0; j < nvJ.nout; ++j) dout[j * RS] = 0.0f;
+        dout[0] = abar * msk;
+        mlp_delta<HP>(nvJ, t, row, dx);
+        Model::template jump_input_grad<HP>(a, Jv, dx, dXacc);
+        __syncthreads();
+        if (a.one_net) wgA.accumulate(tb); else wgB.accumulate(tb);
+        __syncthreads();
+        const int nnz = a.jmc_nnz[i], n0 = a.jmc_n0[i];
+        const float cscale = -abar / (float)a.M * vmsk;
+        const int iters = (nnz + 1 + G - 1) / G;
+        for (int it = 0; it < iters; ++it) {
+          const int m = it * G + g;
+          float Jm[D];
+          float w = 0.0f;
+#pragma unroll
+          for (int k = 0; k < D; ++k) Jm[k] = 0.0f;
+          if (m < nnz) {
+            w = 1.0f;
+#pragma unroll
+            for (int k = 0; k < D; ++k) Jm[k] = a.JMC[((size_t)i * D + k) * a.Mcap + m];
+          } else if (m == nnz) {
+            w = (float)n0;
+          }
+          Model::jump_input(a, tf, X, Jm, xt);
+          mlp_fwd<HP, true>(nvJ, t, row);
+          dout[0] = cscale * w;
+          mlp_delta<HP>(nvJ, t, row, dx);
+          Model::template jump_input_grad<HP>(a, Jm, dx, dXacc);
+          __syncthreads();
+          if (a.one_net) wgA.accumulate(tb); else wgB.accumulate(tb);
+          __syncthreads();
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        const float s = (G == 1) ? dXacc[k] : group_allsum(dXacc[k], G, red);
+        Xbar[k] += s;
+      }
+      if (a.scheme == SCH_GLOBAL) Ybar *= (1.0f + rdt);
+    }
+    if (a.scheme == SCH_GLOBAL) y0g += Ybar * msk;
+  }
+  const float y0tot = block_sum(y0g, red);
+  // ---- flush: registers -> smem gradient vector (external layout) -> this CTA's row of gpart ----------
+  __syncthreads();
+  float* sg = tb;
+  for (int e = threadIdx.x; e < a.P; e += blockDim.x) sg[e] = 0.0f;
+  __syncthreads();
+  wgA.flush(nvA, sg, a.netA.ext_off);
+  if (!a.one_net) wgB.flush(nvJ, sg, a.netB.ext_off);
+  if (a.scheme == SCH_GLOBAL && threadIdx.x == 0) sg[a.y0_off] = y0tot;
+  __syncthreads();
+  float* grow = a.gpart + (size_t)blockIdx.x * a.P;
+  for (int e = threadIdx.x; e < a.P; e += blockDim.x) grow[e] = sg[e];
+}
+
+// ---- launch glue ---------------------------------------------------------------------------------
+template <int HP>
+static size_t pricing_smem(const PricingArgs& a, bool backward) {
+  const int w = net_smem_floats(a.netA, HP, backward) + (a.one_net ? 0 : net_smem_floats(a.netB, HP, backward));
+  const int tl = backward ? Tiles<HP>::bwd_floats() : Tiles<HP>::fwd_floats();
+  return sizeof(float) * (size_t)(w + 8 + tl);
+}
+
+template <class Model, int HP>
+static int launch_pair(const PricingArgs& a, int grid, bool backward, cudaStream_t st) {
+  const size_t smem = pricing_smem<HP>(a, backward);
+  if (smem > 227 * 1024) { set_error("pricing kernels: shared-memory footprint exceeds 227 KB"); return -1; }
+  if (!backward) {
+    auto kern = pricing_forward<Model, HP>;
+    FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kThreads, smem, st>>>(a);
+  } else {
+    auto kern = pricing_backward<Model, HP>;
+    FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kThreads, smem, st>>>(a);
+  }
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// A(iStep, X) for n states (component planes X[d][n]); the drop-in MertonJumpModel.A / VGmodel.A.
+template <class Model>
+__global__ void price_kernel(const PricingArgs a, int iStep, const float* __restrict__ Xin, int n, float* __restrict__ out) {
+  constexpr int D = Model::D;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+    float X[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) X[k] = Xin[(size_t)k * n + p];
+    float A, dAb;
+    if (iStep >= a.N) A = fmaxf(Model::basket(X) - a.K, 0.0f);   // pricingModels.py:49
+    else Model::eval_A(a, iStep, X, A, dAb);
+    out[p] = A;
+  }
+}
+
+int launch_price(int model, int D, const PricingArgs& a, int iStep, const float* X, int n, float* out, cudaStream_t st) {
+  int grid = (n + 127) / 128;
+  grid = grid < 1 ? 1 : (grid > 148 * 8 ? 148 * 8 : grid);
+  if (model == 0 && D == 1) price_kernel<MertonModel<1>><<<grid, 128, 0, st>>>(a, iStep, X, n, out);
+  else if (model == 0 && D == 10) price_kernel<MertonModel<10>><<<grid, 128, 0, st>>>(a, iStep, X, n, out);
+  else if (model == 1 && D == 1) price_kernel<VGModel><<<grid, 128, 0, st>>>(a, iStep, X, n, out);
+  else { set_error("price: unsupported (model, d)"); return -1; }
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <class Model, int HP>
+static int occ_pair(const PricingArgs& a, bool backward) {
+  const size_t smem = pricing_smem<HP>(a, backward);
+  int nb = 0;
+  if (!backward) {
+    auto kern = pricing_forward<Model, HP>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem) != cudaSuccess) return 1;
+  } else {
+    auto kern = pricing_backward<Model, HP>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem) != cudaSuccess) return 1;
+  }
+  return nb < 1 ? 1 : nb;
+}
+// resident CTAs per SM of the kernel that launch_pricing would run
+int pricing_blocks_per_sm(int model, int D, int HP, const PricingArgs& a, bool backward) {
+  if (HP == 24) {
+    if (model == 0 && D == 1) return occ_pair<MertonModel<1>, 24>(a, backward);
+    if (model == 0 && D == 10) return occ_pair<MertonModel<10>, 24>(a, backward);
+    if (model == 1 && D == 1) return occ_pair<VGModel, 24>(a, backward);
+  }
+  return 1;
+}
+
+size_t pricing_smem_bytes(int HP, const PricingArgs& a, bool backward) {
+  return HP == 24 ? pricing_smem<24>(a, backward) : pricing_smem<32>(a, backward);
+}
+
+// model: 0 = Merton, 1 = VG.  Returns -1 (with message) for shapes that were not compiled in.
+int launch_pricing(int model, int D, int HP, const PricingArgs& a, int grid, bool backward, cudaStream_t st) {
+  if (HP == 24) {
+    if (model == 0 && D == 1) return launch_pair<MertonModel<1>, 24>(a, grid, backward, st);
+    if (model == 0 && D == 10) return launch_pair<MertonModel<10>, 24>(a, grid, backward, st);
+    if (model == 1 && D == 1) return launch_pair<VGModel, 24>(a, grid, backward, st);
+  }
+  set_error("pricing kernels: unsupported (model, d, padded width) = (" + std::to_string(model) + ", " +
+            std::to_string(D) + ", " + std::to_string(HP) + "); compiled: Merton d in {1,10}, VG d=1, H<=23");
+  return -1;
+}
+
+}  // namespace fbsdej

@@ -1,0 +1,142 @@
+#include "util.cuh"
+
+namespace fbsdej {
+
+// out[0..3] = sum over CTAs of the loss partials; out[4+e] = sum over CTAs of gradient partials (fixed order:
+// deterministic for a given grid).  One thread per output element, coalesced over e.
+__global__ void reduce_partials_kernel(const float* __restrict__ lpart, int nparts_l, const float* __restrict__ gpart,
+                                       int nparts, int P, float* __restrict__ out, int with_grad) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < kHeader) {
+    float s = 0.0f;
+    for (int c = 0; c < nparts_l; ++c) s += lpart[c * 4 + e];
+    out[e] = s;
+  } else if (with_grad && e < kHeader + P) {
+    const int j = e - kHeader;
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    int c = 0;
+    for (; c + 3 < nparts; c += 4) {
+      s0 += gpart[(size_t)c * P + j]; s1 += gpart[(size_t)(c + 1) * P + j];
+      s2 += gpart[(size_t)(c + 2) * P + j]; s3 += gpart[(size_t)(c + 3) * P + j];
+    }
+    for (; c < nparts; ++c) s0 += gpart[(size_t)c * P + j];
+    out[e] = (s0 + s1) + (s2 + s3);
+  }
+}
+
+// Keras OptimizerV2 Adam (TF ResourceApplyAdam): see oracle/adam.py and SURVEY fact 9.
+__global__ void adam_kernel(float* __restrict__ theta, float* __restrict__ m, float* __restrict__ v,
+                            const float* __restrict__ grad, const float* __restrict__ mask, int n, float lr, float b1,
+                            float b2, float eps, const int* __restrict__ t_dev) {
+  const int t = *t_dev + 1;
+  const float b1p = powf(b1, (float)t), b2p = powf(b2, (float)t);
+  const float alpha = lr * sqrtf(1.0f - b2p) / (1.0f - b1p);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (mask && mask[i] == 0.0f) continue;
+    const float g = grad[i];
+    const float mi = m[i] + (g - m[i]) * (1.0f - b1);
+    const float vi = v[i] + (g * g - v[i]) * (1.0f - b2);
+    m[i] = mi; v[i] = vi;
+    theta[i] -= alpha * mi / (sqrtf(vi) + eps);
+  }
+}
+__global__ void bump_i32_kernel(int* p) { *p += 1; }
+__global__ void bump_u32_kernel(uint32_t* p) { *p += 1u; }
+__global__ void copy_loss_kernel(const float* out, float* dst, uint32_t* ctr) {
+  if (dst) dst[*ctr] = out[0];
+  *ctr += 1u;
+}
+
+// Generic row-wise MLP (runtime dims, H <= 64): Net.call of the reference for Y0 reports and drop-in __call__.
+__global__ void net_forward_kernel(const float* __restrict__ th, int nin, int H, int L, int nout, int act,
+                                   const float* __restrict__ x, int rows, float* __restrict__ y) {
+  extern __shared__ float sw[];
+  const int np = nin * H + H + (L - 1) * (H * H + H) + H * nout + nout;
+  for (int i = threadIdx.x; i < np; i += blockDim.x) sw[i] = th[i];
+  __syncthreads();
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
+    float h[64], h2[64];
+    const float* w = sw;
+    for (int j = 0; j < H; ++j) {
+      float acc = w[nin * H + j];
+      for (int k = 0; k < nin; ++k) acc = fmaf(x[(size_t)r * nin + k], w[k * H + j], acc);
+      h[j] = act == 0 ? tanhf(acc) : fmaxf(acc, 0.0f);
+    }
+    w += nin * H + H;
+    for (int l = 1; l < L; ++l) {
+      for (int j = 0; j < H; ++j) {
+        float acc = w[H * H + j];
+        for (int k = 0; k < H; ++k) acc = fmaf(h[k], w[k * H + j], acc);
+        h2[j] = act == 0 ? tanhf(acc) : fmaxf(acc, 0.0f);
+      }
+      for (int j = 0; j < H; ++j) h[j] = h2[j];
+      w += H * H + H;
+    }
+    for (int j = 0; j < nout; ++j) {
+      float acc = w[H * nout + j];
+      for (int k = 0; k < H; ++k) acc = fmaf(h[k], w[k * nout + j], acc);
+      y[(size_t)r * nout + j] = acc;
+    }
+  }
+}
+
+__global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int N, int B, int d, int to_ndb) {
+  const size_t total = (size_t)N * B * d;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    // t indexes the destination
+    if (to_ndb) {
+      const int b = (int)(t % B), k = (int)((t / B) % d), i = (int)(t / ((size_t)B * d));
+      dst[t] = src[((size_t)i * B + b) * d + k];
+    } else {
+      const int k = (int)(t % d), b = (int)((t / d) % B), i = (int)(t / ((size_t)B * d));
+      dst[t] = src[((size_t)i * d + k) * B + b];
+    }
+  }
+}
+
+int launch_reduce_partials(const float* lpart, int nparts_l, const float* gpart, int nparts_g, int P, float* out,
+                           bool with_grad, cudaStream_t st) {
+  const int n = kHeader + (with_grad ? P : 0);
+  reduce_partials_kernel<<<(n + 127) / 128, 128, 0, st>>>(lpart, nparts_l, gpart, nparts_g, P, out, with_grad ? 1 : 0);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_adam(float* theta, float* m, float* v, const float* grad, const float* mask, int n, float lr, float b1,
+                float b2, float eps, int* t_dev, cudaStream_t st) {
+  adam_kernel<<<(n + 255) / 256, 256, 0, st>>>(theta, m, v, grad, mask, n, lr, b1, b2, eps, t_dev);
+  bump_i32_kernel<<<1, 1, 0, st>>>(t_dev);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_bump_u32(uint32_t* p, cudaStream_t st) {
+  bump_u32_kernel<<<1, 1, 0, st>>>(p);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_copy_loss(const float* out, float* dst, uint32_t* ctr, cudaStream_t st) {
+  copy_loss_kernel<<<1, 1, 0, st>>>(out, dst, ctr);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_net_forward(const float* theta_net, int nin, int H, int L, int nout, int act, const float* x, int rows,
+                       float* y, cudaStream_t st) {
+  FB_REQUIRE(H <= 64 && L >= 1, "net_forward: H must be <= 64 and L >= 1");
+  const int np = nin * H + H + (L - 1) * (H * H + H) + H * nout + nout;
+  int grid = (rows + 127) / 128;
+  if (grid > 148 * 8) grid = 148 * 8;
+  if (grid < 1) grid = 1;
+  net_forward_kernel<<<grid, 128, np * sizeof(float), st>>>(theta_net, nin, H, L, nout, act, x, rows, y);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_transpose(const float* src, float* dst, int N, int B, int d, bool to_ndb, cudaStream_t st) {
+  const size_t total = (size_t)N * B * d;
+  size_t g = (total + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  if (g < 1) g = 1;
+  transpose_kernel<<<(int)g, 256, 0, st>>>(src, dst, N, B, d, to_ndb ? 1 : 0);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace fbsdej

@@ -1,0 +1,138 @@
+"""GPU parity: the fused sm_100a kernels (through the C-ABI) against the CPU oracle on identical injected noise.
+
+Bar (BASELINE.json north_star): losses, Y0 / Y and Z trajectories within 1e-5 relative in fp32.  Gradients are
+compared against the float64 oracle and must be as close to it as fp32 arithmetic allows (the fp32 oracle's own
+distance to float64 is the yardstick)."""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from oracle import MertonOracle, VGOracle, MFGOracle
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def _close(a, b, rtol=RTOL, atol=2e-6):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    err = np.abs(a - b)
+    tol = atol + rtol * np.abs(b)
+    assert np.all(err <= tol), f"max err {err.max():.3e} (rel {np.max(err / (np.abs(b) + 1e-30)):.3e})"
+
+
+def _grad_check(g_gpu, g64, g32):
+    scale = np.abs(g64).max() + 1e-30
+    e_gpu = np.abs(g_gpu - g64).max() / scale
+    e_32 = np.abs(g32 - g64).max() / scale
+    assert e_gpu <= max(2e-5, 4.0 * e_32), f"gradient error {e_gpu:.3e} vs fp32-oracle error {e_32:.3e}"
+
+
+@pytest.mark.parametrize("scheme", ["Global", "MultiStep1", "MultiStep2", "SumLocal1", "SumLocal2", "SumLocalReg", "MultiStepReg"])
+@pytest.mark.parametrize("B", [10, 37])
+def test_merton_d1(ctx, scheme, B):
+    M = 160
+    om = MertonOracle(aLin=H.ALIN, limit=30, d=1, **H.MERTON)
+    layout = H.pricing_layout("merton", scheme, 1)
+    theta = H.random_theta(layout, 1)
+    noise = H.merton_noise(om, B, M, seed=5, with_jmc=not scheme.endswith("Reg"))
+    l32, g32, aux = H.oracle_pricing(om, scheme, layout, theta, noise, B)
+    l64, g64, aux64 = H.oracle_pricing(om, scheme, layout, theta, noise, B, dtype=torch.float64)
+    s = H.native_pricing(ctx, "merton", H.MERTON, scheme, layout, d=1, M=0 if scheme.endswith("Reg") else M)
+    s.set_theta(theta)
+    s.set_noise(B, H.to_planes(noise["dW"]), H.to_planes(noise["J"]), H.to_planes(noise["JMC"]) if "JMC" in noise else None)
+    out, tx, ty, tz = s.loss(B, traj=True)
+    _close(out[0], l64)
+    _close(tx[:, 0, :], aux64["X"][:, :, 0])
+    _close(ty, aux64["Y"])
+    if "Z" in aux64:
+        _close(tz[:, 0, :], aux64["Z"][:, :, 0], atol=5e-6)
+    g = s.grad(B)
+    _close(g[0], l64)
+    _grad_check(g[4:], g64, g32)
+
+
+@pytest.mark.parametrize("scheme", ["Global", "MultiStep2", "SumLocal1", "SumLocalReg", "MultiStepReg"])
+def test_merton_d10(ctx, scheme):
+    B, M, d = 64, 96, 10
+    p = dict(H.MERTON, N=20)
+    om = MertonOracle(aLin=H.ALIN, limit=100, d=d, **p)
+    layout = H.pricing_layout("merton", scheme, d)
+    theta = H.random_theta(layout, 2)
+    noise = H.merton_noise(om, B, M, seed=6, with_jmc=not scheme.endswith("Reg"))
+    l32, g32, _ = H.oracle_pricing(om, scheme, layout, theta, noise, B)
+    l64, g64, aux64 = H.oracle_pricing(om, scheme, layout, theta, noise, B, dtype=torch.float64)
+    s = H.native_pricing(ctx, "merton", p, scheme, layout, d=d, M=0 if scheme.endswith("Reg") else M, limit=100)
+    s.set_theta(theta)
+    s.set_noise(B, H.to_planes(noise["dW"]), H.to_planes(noise["J"]), H.to_planes(noise["JMC"]) if "JMC" in noise else None)
+    out, tx, ty, tz = s.loss(B, traj=True)
+    _close(out[0], l64)
+    _close(tx, aux64["X"].transpose(0, 2, 1))
+    _close(ty, aux64["Y"])
+    g = s.grad(B)
+    _grad_check(g[4:], g64, g32)
+
+
+@pytest.mark.parametrize("scheme", ["Global", "MultiStep1", "MultiStep2", "SumLocal1", "SumLocal2", "SumLocalReg", "MultiStepReg"])
+def test_vg(ctx, scheme):
+    B, M = 24, 128
+    om = VGOracle(aLin=H.ALIN, **H.VG)
+    layout = H.pricing_layout("vg", scheme, 1)
+    theta = H.random_theta(layout, 3)
+    noise = H.vg_noise(om, B, M, seed=7, with_jmc=not scheme.endswith("Reg"))
+    l32, g32, _ = H.oracle_pricing(om, scheme, layout, theta, noise, B)
+    l64, g64, aux64 = H.oracle_pricing(om, scheme, layout, theta, noise, B, dtype=torch.float64)
+    s = H.native_pricing(ctx, "vg", H.VG, scheme, layout, M=0 if scheme.endswith("Reg") else M)
+    s.set_theta(theta)
+    s.set_noise(B, None, H.to_planes(noise["J"]), H.to_planes(noise["JMC"]) if "JMC" in noise else None)
+    out, tx, ty, _ = s.loss(B, traj=True)
+    _close(out[0], l64)
+    _close(tx[:, 0, :], aux64["X"][:, :, 0])
+    _close(ty, aux64["Y"])
+    g = s.grad(B)
+    _grad_check(g[4:], g64, g32)
+
+
+@pytest.mark.parametrize("scheme", ["Global", "MultiStep", "SumLocal", "SumLocalReg", "MultiStepReg"])
+@pytest.mark.parametrize("jumpModel", ["stochastic", "constant"])
+def test_mfg(ctx, scheme, jumpModel):
+    from oracle.mfg import sample_mfg_noise
+    B = 130
+    p = H.mfg_params(1, jumpModel)
+    om = MFGOracle(**p)
+    layout = H.mfg_layout(scheme)
+    theta = H.random_theta(layout, 4)
+    noise = sample_mfg_noise(om, B, torch.Generator().manual_seed(8))
+    (lh32, li32), g32, _ = H.oracle_mfg(om, scheme, layout, theta, noise, B)
+    (lh64, li64), g64, aux64 = H.oracle_mfg(om, scheme, layout, theta, noise, B, dtype=torch.float64)
+    s = H.native_mfg(ctx, p, scheme, layout)
+    s.set_theta(theta)
+    s.set_noise(B, noise["dW0"].numpy(), noise["dW"].numpy(), noise["dN"].numpy())
+    out, tx, ty, _ = s.loss(B, traj=True)
+    _close(out[1], lh64, rtol=2e-5)
+    _close(out[2], li64, rtol=2e-5)
+    _close(out[0], lh64 + li64, rtol=2e-5)
+    _close(tx[:, 0, :], aux64["hS"], atol=1e-5)
+    _close(tx[:, 1, :], aux64["S"], atol=1e-5)
+    _close(ty[:, 0, :], aux64["hY"], rtol=2e-5, atol=2e-4)
+    _close(ty[:, 1, :], aux64["Y"], rtol=2e-5, atol=2e-4)
+    g = s.grad(B)
+    _grad_check(g[4:], g64, g32)
+
+
+def test_adam_matches_keras_form(ctx):
+    from oracle import KerasAdam
+    om = MertonOracle(aLin=H.ALIN, limit=30, d=1, **H.MERTON)
+    layout = H.pricing_layout("merton", "SumLocalReg", 1)
+    theta = H.random_theta(layout, 9)
+    s = H.native_pricing(ctx, "merton", H.MERTON, "SumLocalReg", layout)
+    s.set_theta(theta)
+    rng = np.random.default_rng(0)
+    th = torch.tensor(theta.copy())
+    opt = KerasAdam(layout.total, 3e-4)
+    for _ in range(5):
+        g = rng.standard_normal(layout.total).astype(np.float32) * np.float32(1e-2)
+        opt.step(th, torch.tensor(g))
+        s.adam_step(3e-4, grad=ctx.to_device(g))
+    _close(s.get_theta(), th.numpy(), rtol=1e-6, atol=1e-8)
