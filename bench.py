@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""Benchmark of the deep-FBSDE-with-jumps training hot path (BASELINE.json metric: train iters/s & path-steps/s).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --gpus N --steps K ...  # reference-equivalent CPU path (torch restatement)
+
+A "step" = one training iteration of the workload: simulate increments -> forward -> adjoint -> reduce ->
+(all-reduce) -> Adam.  Workload (config.workload): Merton d=10 geometric basket, N=100 time steps, H=21 tanh nets,
+SolverGlobalSumLocalReg (B = 2^16 paths on one GPU; config 5: B = 2^20 paths sharded over N>1 GPUs).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+MERTON = dict(T=1.0, N=100, r=0.1, muJ=0.0, sigmaJ=0.2, sigma=0.3, lam=3.0, K=0.9, x0=1.0)
+D, H_WIDTH, LIMIT, ALIN, LR = 10, 21, 100, 0.1, 3e-4
+SOLVERS = {"SumLocalReg": 0, "MultiStepReg": 0, "Global": 256}     # name -> default compensator samples M
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--paths", type=int, default=0, help="global Monte-Carlo batch (default 2^16 on 1 GPU, 2^20 on N>1)")
+    ap.add_argument("--solver", default="SumLocalReg", choices=list(SOLVERS))
+    ap.add_argument("--M", type=int, default=-1, help="compensator samples for --solver Global (default 256)")
+    ap.add_argument("--cpu-paths", type=int, default=2048, help="paths of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(a, B, world):
+    M = SOLVERS[a.solver] if a.M < 0 else a.M
+    name = ("Merton d=10 geometric basket, N=100, H=21 tanh, Solver%s%s, B=%d paths (SURVEY 8d config %s)"
+            % ("Global" + a.solver if a.solver.endswith("Reg") else a.solver + "FBSDE", "" if M == 0 else " M=%d" % M, B,
+               "3" if world == 1 else "5"))
+    return M, {"workload": name, "paths": B, "time_steps": MERTON["N"], "d": D, "hidden": H_WIDTH, "solver": a.solver,
+               "compensator_M": M, "parallelism": "dp%d" % world, "l2_policy": "inputs exceed L2 (path tensors %.0f MB per rank)"
+               % (2 * MERTON["N"] * D * (B // world) * 4 / 1e6)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampling during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_iteration_factory(a, M, B_cpu):
+    """One training iteration of the reference-equivalent CPU restatement (oracle/, torch eager + autograd + Keras-form
+    Adam), noise drawn on the CPU the way the reference draws it."""
+    import torch
+    import helpers as H
+    from oracle import MertonOracle, KerasAdam, pricing_loss
+    from oracle.pricing import sample_pricing_noise
+    om = MertonOracle(aLin=ALIN, limit=LIMIT, d=D, **MERTON)
+    layout = H.pricing_layout("merton", a.solver, D, H_WIDTH)
+    theta = torch.tensor(H.random_theta(layout, 0), requires_grad=True)
+    opt = KerasAdam(layout.total, LR)
+    gen = torch.Generator().manual_seed(0)
+
+    def it():
+        noise = sample_pricing_noise(om, a.solver, B_cpu, max(M, 1), gen)
+        if theta.grad is not None:
+            theta.grad = None
+        loss = pricing_loss(om, a.solver, layout, theta, noise, B_cpu)
+        loss.backward()
+        opt.step(theta.data, theta.grad)
+        return float(loss)
+    return it
+
+
+def run_reference(a):
+    """--impl reference: TensorFlow (the reference's runtime) is not installable here, so the reference arm is the
+    CPU restatement of the same solver on all host threads, each step a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", str(a.gpus)))
+    B = a.paths or (2 ** 16 if world == 1 else 2 ** 20)
+    M, cfg = workload_config(a, B, world)
+    it = cpu_iteration_factory(a, M, a.cpu_paths)
+    for _ in range(max(1, min(a.warmup, 1))):
+        it()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        it()
+    dt = (time.perf_counter() - t0) / a.steps
+    val = a.cpu_paths * MERTON["N"] / dt
+    sample = "%d-path sample of the %d-path batch per step, all %d time steps, fwd+bwd+Adam" % (a.cpu_paths, B, MERTON["N"])
+    print(json.dumps({
+        "impl": "reference", "metric": "path-steps/s", "value": val, "unit": "path-steps/s", "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": dt * 1e3, "iters_per_s_equiv": val / (B * MERTON["N"]), "higher_is_better": True,
+        "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": val, "unit": "path-steps/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "path-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference-equivalent CPU restatement (torch eager), not TensorFlow"}))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_native(a):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from deepfbsdejsolvers_b200 import Context, set_seed
+    from deepfbsdejsolvers_b200 import coupledPricing as cp
+    from deepfbsdejsolvers_b200.solver_base import shard
+    import deepfbsdejsolvers_b200._lib as L
+
+    B = a.paths or (2 ** 16 if world == 1 else 2 ** 20)
+    M, cfg = workload_config(a, B, world)
+    off, Bl = shard(B, rank, world)
+    ctx = Context.default(local)
+    set_seed(0)
+    mm = cp.MertonJumpModel(MERTON["T"], MERTON["N"], MERTON["r"], MERTON["muJ"], MERTON["sigmaJ"], MERTON["sigma"], MERTON["lam"],
+                            MERTON["K"], MERTON["x0"], cp.AbsCoupling(ALIN), LIMIT, d=D)
+    layer = [H_WIDTH, H_WIDTH]
+    if a.solver == "Global":
+        solver = cp.SolverGlobalFBSDE(mm, cp.Net(1, D, layer, "tanh"), cp.Net(0, 1, layer, "tanh"), LR, M=M)
+    elif a.solver == "SumLocalReg":
+        solver = cp.SolverGlobalSumLocalReg(mm, cp.Net(0, 1, layer, "tanh"), cp.Net(0, 1, layer, "tanh"), LR)
+    else:
+        solver = cp.SolverGlobalMultiStepReg(mm, cp.Net(0, 1, layer, "tanh"), cp.Net(0, 1, layer, "tanh"), LR)
+    s = solver.build()
+    N = MERTON["N"]
+
+    def barrier():
+        ctx.sync()
+        if world > 1:
+            dist.barrier()
+        ctx.sync()
+
+    def step():
+        if world == 1:
+            s.train_steps(0, B, 1, LR)
+        else:
+            out = s.grad_step(0, Bl, B, off)
+            with torch.cuda.stream(ctx.stream):
+                dist.all_reduce(out)
+            s.adam_step(LR)
+            s.bump_iteration()
+
+    def timed(fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(ctx.stream)
+        for _ in range(n):
+            fn()
+        e1.record(ctx.stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=ctx.device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = ctx.launches
+    ms = timed(step, a.steps)
+    launches = ctx.launches - l0
+    clk = clocks.stop() if rank == 0 else None
+    ms_step = ms / a.steps
+    value = B * N / (ms_step * 1e-3)
+
+    # ---- end to end through the C-ABI with HOST buffers: H2D of the step's increments + step + D2H of the loss ----
+    e2e = None
+    if not a.no_e2e:
+        nfl = N * D * Bl
+        host = [[torch.randn(nfl, dtype=torch.float32).mul_(0.1).pin_memory() for _ in range(2)] for _ in range(2)]
+        dev = [ctx.empty(nfl), ctx.empty(nfl)]
+        loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        jmc = ctx.zeros(N * D * max(M, 1)) if M > 0 else None
+        k = [0]
+
+        def e2e_step():
+            hw, hj = host[k[0] & 1]
+            k[0] += 1
+            with torch.cuda.stream(ctx.stream):
+                dev[0].copy_(hw, non_blocking=True)
+                dev[1].copy_(hj, non_blocking=True)
+            L.check(L.lib.fbsdej_solver_set_noise(s.handle, Bl, dev[0].data_ptr(), dev[1].data_ptr(),
+                                                  jmc.data_ptr() if jmc is not None else None))
+            L.check(L.lib.fbsdej_solver_grad(s.handle, s.theta.data_ptr(), Bl, B, s.out.data_ptr()))
+            with torch.cuda.stream(ctx.stream):
+                if world > 1:
+                    dist.all_reduce(s.out)
+            s.adam_step(LR)
+            with torch.cuda.stream(ctx.stream):
+                loss_host.copy_(s.out[:1], non_blocking=True)
+            ctx.sync()
+
+        for _ in range(2):
+            e2e_step()
+        ms_e = timed(e2e_step, a.steps) / a.steps
+        e2e = {"value": B * N / (ms_e * 1e-3), "unit": "path-steps/s", "ms_per_step": ms_e,
+               "h2d_bytes_per_step": 2 * nfl * 4 * world, "d2h_bytes_per_step": 4 * world,
+               "what": "host (pinned) Brownian + jump increments of the step -> H2D -> fbsdej_solver_set_noise -> "
+                       "fbsdej_solver_grad -> fbsdej_adam_step -> loss D2H; the production path draws the increments on "
+                       "the device (Philox) and moves no per-step host data"}
+
+    # ---- per-kernel device times + roofline (rank 0) ----------------------------------------------------------------
+    roof, kernels = None, None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        prof = s.profile(0, Bl, reps=max(3, min(a.steps, 10)))
+        ps = Bl * N
+        jump = M > 0
+        # algorithmic bytes per path-step (SURVEY 8d / BASELINE.md section 5); Reg solvers have no Z / Gam / comp words
+        alg = {"sim_paths": 8 * D * ps,
+               "forward": 4 * ((5 * D + 4) if jump else (3 * D + 2 + D + 1)) * ps,
+               "backward": 4 * ((7 * D + 4) if jump else (5 * D + 2 + 2 * D + 2 - D)) * ps}
+        kernels = {}
+        for kname, b in alg.items():
+            t = prof[kname]
+            kernels[kname] = {"ms": t, "algorithmic_bytes": b, "achieved_GBps": b / (t * 1e-3) / 1e9 if t > 0 else None,
+                              "frac_of_measured_hbm": b / (t * 1e-3) / 1e9 / peak if t > 0 else None}
+        kernels["reduce"] = {"ms": prof["reduce"]}
+        if jump:
+            kernels["sim_compensator"] = {"ms": prof["sim_compensator"]}
+        dom = max(("sim_paths", "forward", "backward"), key=lambda n: prof[n])
+        roof = {"kernel": {"sim_paths": "sim_merton_kernel", "forward": "pricing_forward", "backward": "pricing_backward"}[dom],
+                "bound": "hbm", "achieved": kernels[dom]["achieved_GBps"], "peak": peak, "unit": "GB/s",
+                "frac": kernels[dom]["frac_of_measured_hbm"], "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                "share_of_step": prof[dom] / sum(prof.values()),
+                "note": "fused kernel: MLP evaluations, closed-form series and adjoint run inside the launch, so it is "
+                        "FMA/MUFU-bound; the fraction is algorithmic path-tensor bytes over the measured copy bandwidth"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        it = cpu_iteration_factory(a, M, a.cpu_paths)
+        it()
+        t0, n = time.perf_counter(), 0
+        while n < 2 or (time.perf_counter() - t0 < 10.0 and n < 50):
+            it(); n += 1
+        dt = (time.perf_counter() - t0) / n
+        cpu = {"value": a.cpu_paths * N / dt, "unit": "path-steps/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "%d iterations of a %d-path sample of the batch, all %d time steps, fwd+bwd+Adam (torch eager restatement "
+                         "of the reference solver, not TensorFlow)" % (n, a.cpu_paths, N), "ms_per_iteration": dt * 1e3}
+
+    if rank == 0:
+        line = {"metric": "path-steps/s", "value": value, "unit": "path-steps/s", "n_gpus": world, "steps": a.steps,
+                "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "iters_per_s": 1e3 / ms_step, "higher_is_better": True,
+                "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": cfg, "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "kernels": kernels,
+                "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)

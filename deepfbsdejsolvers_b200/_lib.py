@@ -42,7 +42,7 @@ class NetDesc(C.Structure):
 
 class SolverDesc(C.Structure):
     _fields_ = [("model", C.c_int), ("scheme", C.c_int), ("n_nets", C.c_int), ("nets", NetDesc * 2), ("n_y0", C.c_int),
-                ("M", C.c_int), ("stale_time", C.c_int), ("w_hat", C.c_float), ("w_ind", C.c_float)]
+                ("M", C.c_int), ("stale_time", C.c_int), ("w_hat", C.c_float), ("w_ind", C.c_float), ("price_table", C.c_int)]
 
 
 def _load():
@@ -77,6 +77,7 @@ def _load():
         "fbsdej_solver_grad_step": (i32, [vp, vp, u64, vp, u32, i32, i32, vp]),
         "fbsdej_bump_u32": (i32, [vp, vp]),
         "fbsdej_solver_train_steps": (i32, [vp, vp, vp, vp, vp, vp, vp, u64, i32, i32, f32, f32, f32, f32, vp]),
+        "fbsdej_solver_profile": (i32, [vp, vp, u64, i32, i32, C.POINTER(C.c_float)]),
         "fbsdej_solver_net_forward": (i32, [vp, vp, i32, vp, i32, vp]),
         "fbsdej_net_forward": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, i32, vp]),
         "fbsdej_solver_price": (i32, [vp, i32, vp, i32, vp]),

@@ -99,16 +99,20 @@ class MertonJumpModel(_PricingModel):
 
     kind = L.MODEL_MERTON
 
-    def __init__(self, T, N, r, muJ, sigmaJ, sigma, lam, K, x0, func, limit, d: int = 1):
+    def __init__(self, T, N, r, muJ, sigmaJ, sigma, lam, K, x0, func, limit, d: int = 1, price_table=None):
         self.T, self.r, self.sig, self.muJ, self.sigJ, self.lam = T, r, sigma, muJ, sigmaJ, lam
         self.K, self.N, self.dt, self.x0, self.func, self.limit, self.d = K, int(N), T / N, x0, func, int(limit), int(d)
         self.aLin = coupling_slope(func)
+        # d = 1 (the reference): sum the `limit` series terms at every path-step, as pricingModels.py:40-49 does.
+        # d > 1 needs limit ~ 100 terms: evaluate the same series through the library's per-step Hermite table.
+        self.price_table = (self.d > 1) if price_table is None else bool(price_table)
 
     def c_params(self) -> L.MertonParams:
         return L.MertonParams(self.T, self.r, self.muJ, self.sigJ, self.sig, self.lam, self.K, self.x0, self.aLin, self.N,
                               self.limit, self.d)
 
     def make_solver(self, scheme, nets, n_y0, M, ctx=None, **kw) -> NativeSolver:
+        kw.setdefault("price_table", self.price_table)
         s = NativeSolver(ctx or Context.default(), L.MODEL_MERTON, scheme, nets, n_y0, M, merton=self.c_params(), **kw)
         s.N, s.d = self.N, self.d
         return s

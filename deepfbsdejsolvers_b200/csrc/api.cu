@@ -152,6 +152,7 @@ struct fbsdej_solver {
   int sch = 0, one_net = 0, has_jump = 0, use_netA = 1, has_y = 0, zoff = 0, has_z = 0, feat_mode = 0;
   // tables
   float4* tabA = nullptr; float* tabK = nullptr; int2* tab_range = nullptr; float* qdisc = nullptr; int limit = 0;
+  float4* atab = nullptr; float4* atab_meta = nullptr; int* atab_off = nullptr; int use_atab = 0;
   float4* vg_coef = nullptr; float* vg_scale = nullptr; int vg_nint = 0; float vg_k0 = 0, vg_h = 1;
   uint32_t* pois_thr = nullptr; int npois = 0;
   float* qaver = nullptr; float* meanhq = nullptr;
@@ -239,6 +240,7 @@ void fill_pricing_args(const fbsdej_solver* s, const float* theta, int B, int B_
   a.dW = s->curA; a.J = s->curB;
   a.JMC = s->jmc; a.jmc_nnz = s->jmc_nnz; a.jmc_n0 = s->jmc_n0; a.Mcap = s->M > 0 ? s->M : 1;
   a.tabA = s->tabA; a.tabK = s->tabK; a.tab_range = s->tab_range; a.qdisc = s->qdisc; a.limit = s->limit;
+  a.atab = s->atab; a.atab_meta = s->atab_meta; a.atab_off = s->atab_off; a.use_atab = s->use_atab;
   a.vg_coef = s->vg_coef; a.vg_scale = s->vg_scale; a.vg_nint = s->vg_nint;
   a.vg_k0 = s->vg_k0; a.vg_h = s->vg_h; a.vg_inv_h = 1.0f / s->vg_h;
   a.trajX = s->trajX; a.aux_s = s->aux_s; a.aux_dA = s->aux_dA; a.sch1 = s->sch1; a.fin = s->fin;
@@ -266,7 +268,7 @@ void fill_mfg_args(const fbsdej_solver* s, const float* theta, int B, int B_glob
 
 // forward (+ backward) + partial reduction into out[0 .. 4 (+P)).  Returns the number of kernels launched.
 int run_pass(fbsdej_solver* s, const float* theta, int B, int B_global, float* out, bool with_grad, float* trajY,
-             float* trajZ) {
+             float* trajZ, cudaEvent_t* ev = nullptr) {
   FB_REQUIRE(B > 0 && B_global >= B, "B must be > 0 and B_global >= B");
   FB_REQUIRE(s->noiseB == B, "noise not set for this batch size: call fbsdej_solver_simulate / set_noise first");
   cudaStream_t st = s->ctx->stream;
@@ -280,7 +282,9 @@ int run_pass(fbsdej_solver* s, const float* theta, int B, int B_global, float* o
     if (ensure_grid(s, std::max(grid_f, grid_b))) return -2;
     a.lpart = s->lpart; a.gpart = s->gpart; a.trajY = trajY;
     if (launch_mfg(s->HP, a, grid_f, false, st)) return -1;
+    if (ev) cudaEventRecord(ev[0], st);
     if (with_grad && launch_mfg(s->HP, a, grid_b, true, st)) return -1;
+    if (ev) cudaEventRecord(ev[1], st);
   } else {
     PricingArgs a;
     fill_pricing_args(s, theta, B, B_global, a);
@@ -291,7 +295,9 @@ int run_pass(fbsdej_solver* s, const float* theta, int B, int B_global, float* o
     if (ensure_grid(s, std::max(grid_f, grid_b))) return -2;
     a.lpart = s->lpart; a.gpart = s->gpart; a.trajY = trajY; a.trajZ = trajZ;
     if (launch_pricing(s->model, s->D, s->HP, a, grid_f, false, st)) return -1;
+    if (ev) cudaEventRecord(ev[0], st);
     if (with_grad && launch_pricing(s->model, s->D, s->HP, a, grid_b, true, st)) return -1;
+    if (ev) cudaEventRecord(ev[1], st);
   }
   // loss partials come from the forward grid, gradient partials from the backward grid
   if (launch_reduce_partials(s->lpart, grid_f, s->gpart, grid_b, s->P, out, with_grad, st)) return -2;
@@ -300,7 +306,7 @@ int run_pass(fbsdej_solver* s, const float* theta, int B, int B_global, float* o
 }
 
 int do_simulate(fbsdej_solver* s, uint64_t seed, uint32_t iteration, const uint32_t* iter_ptr, uint32_t path_offset,
-                int B) {
+                int B, cudaEvent_t* ev = nullptr) {
   if (ensure_capacity(s, B)) return -2;
   cudaStream_t st = s->ctx->stream;
   const uint32_t lo = (uint32_t)seed, hi = (uint32_t)(seed >> 32);
@@ -311,6 +317,7 @@ int do_simulate(fbsdej_solver* s, uint64_t seed, uint32_t iteration, const uint3
     a.sqdt = (float)std::sqrt(s->mer.T / s->mer.N); a.muJ = (float)s->mer.muJ; a.sigJ = (float)s->mer.sigJ;
     a.pois_thr = s->pois_thr; a.npois = s->npois; a.dW = s->nA; a.J = s->nB;
     if (launch_sim_merton(a, st)) return -2;
+    if (ev) cudaEventRecord(*ev, st);
     s->ctx->launches += 1;
     if (s->has_jump) {
       SimMertonArgs c = a;
@@ -327,6 +334,7 @@ int do_simulate(fbsdej_solver* s, uint64_t seed, uint32_t iteration, const uint3
     a.shape = (float)((s->vg.T / s->vg.N) / s->vg.kappa); a.scale = (float)s->vg.kappa;
     a.theta = (float)s->vg.theta; a.sigJ = (float)s->vg.sigJ; a.J = s->nB;
     if (launch_sim_vg(a, st)) return -2;
+    if (ev) cudaEventRecord(*ev, st);
     s->ctx->launches += 1;
     if (s->has_jump) {
       SimVGArgs c = a;
@@ -345,6 +353,7 @@ int do_simulate(fbsdej_solver* s, uint64_t seed, uint32_t iteration, const uint3
     a.coeffOU = (float)s->mfg.coeffOU; a.sig0 = (float)s->mfg.sig0; a.stochastic = s->mfg.stochastic_jumps;
     a.qaver = s->qaver; a.dW0 = s->nA; a.dW = s->nB; a.dN = s->nC;
     if (launch_sim_mfg(a, st)) return -2;
+    if (ev) cudaEventRecord(*ev, st);
     s->ctx->launches += 1;
     s->curA = s->nA; s->curB = s->nB; s->curC = s->nC;
   }
@@ -389,6 +398,44 @@ int build_merton_tables(fbsdej_solver* s) {
       dev_upload(&s->qdisc, qd, st))
     return -2;
   s->limit = L;
+  if (s->desc.price_table) {
+    // Hermite table of sD(k) = sum_n w_n Phi(c1_n k + c2_n), sK(k) = sum_n wK_n Phi(c1_n k + c2_n - s_n) per step.
+    // Spacing from the cubic-Hermite bound  h^4/384 * max|f|,  |Phi(x/s)| <= 0.55/s^4  (target 2e-8 absolute).
+    const double kr = 1.6;
+    std::vector<float4> nodes, meta(N);
+    std::vector<int> offs(N);
+    for (int i = 0; i < N; ++i) {
+      const int2 r = rg[i];
+      double acc = 0.0;
+      for (int n = r.x; n < r.y; ++n) {
+        const float4 c = tA[(size_t)i * L + n];
+        acc += ((double)c.w + (double)tK[(size_t)i * L + n]) * std::pow((double)c.x, 4.0);   // w / s^4, c1 = 1/s
+      }
+      double h = std::pow(2e-8 * 384.0 / (0.55 * std::max(acc, 1e-30)), 0.25);
+      h = std::min(h, 0.05);
+      int nint = (int)std::ceil(2.0 * kr / h);
+      nint = std::max(16, std::min(nint, 1 << 16));
+      h = 2.0 * kr / nint;
+      offs[i] = (int)nodes.size();
+      meta[i] = make_float4((float)(-kr), (float)(1.0 / h), (float)h, (float)nint);
+      for (int j = 0; j <= nint; ++j) {
+        const double k = -kr + j * h;
+        double sD = 0, dD = 0, sK = 0, dK = 0;
+        for (int n = r.x; n < r.y; ++n) {
+          const float4 c = tA[(size_t)i * L + n];     // fp32-rounded coefficients: the table matches the fp32 series
+          const double wk = tK[(size_t)i * L + n];
+          const double d1 = (double)c.x * k + (double)c.y, d2 = d1 - (double)c.z;
+          sD += (double)c.w * 0.5 * std::erfc(-d1 * M_SQRT1_2);
+          sK += wk * 0.5 * std::erfc(-d2 * M_SQRT1_2);
+          dD += (double)c.w * (double)c.x * std::exp(-0.5 * d1 * d1) * 0.3989422804014327;
+          dK += wk * (double)c.x * std::exp(-0.5 * d2 * d2) * 0.3989422804014327;
+        }
+        nodes.push_back(make_float4((float)sD, (float)dD, (float)sK, (float)dK));
+      }
+    }
+    if (dev_upload(&s->atab, nodes, st) || dev_upload(&s->atab_meta, meta, st) || dev_upload(&s->atab_off, offs, st)) return -2;
+    s->use_atab = 1;
+  }
   // Poisson(lam dt) inversion table: thr[k] = floor(CDF(k) 2^32)
   const double mean = m.lam * dt;
   std::vector<uint32_t> thr;
@@ -503,6 +550,7 @@ int fbsdej_solver_destroy(fbsdej_solver* s) {
   if (s->graph) cudaGraphExecDestroy(s->graph);
   free_path_buffers(s);
   dev_free(s->tabA); dev_free(s->tabK); dev_free(s->tab_range); dev_free(s->qdisc);
+  dev_free(s->atab); dev_free(s->atab_meta); dev_free(s->atab_off);
   dev_free(s->vg_coef); dev_free(s->vg_scale); dev_free(s->pois_thr); dev_free(s->qaver); dev_free(s->meanhq);
   dev_free(s->jmc_raw); dev_free(s->jmc); dev_free(s->jmc_nnz); dev_free(s->jmc_n0);
   dev_free(s->lpart); dev_free(s->gpart); dev_free(s->out_dev); dev_free(s->step_ctr);
@@ -769,6 +817,34 @@ int fbsdej_solver_train_steps(fbsdej_solver* s, float* theta, float* m, float* v
     s->ctx->launches += s->launches_per_step;
   }
   return 0;
+}
+
+int fbsdej_solver_profile(fbsdej_solver* s, const float* theta, uint64_t seed, int B, int reps, float* ms_host) {
+  FB_REQUIRE(s && theta && ms_host && B > 0 && reps > 0, "profile: bad argument");
+  FB_CUDA(cudaSetDevice(s->ctx->device));
+  cudaStream_t st = s->ctx->stream;
+  cudaEvent_t ev[6];
+  for (auto& e : ev) FB_CUDA(cudaEventCreate(&e));
+  for (int k = 0; k < 5; ++k) ms_host[k] = 0.0f;
+  int rc = 0;
+  for (int r = -1; r < reps && !rc; ++r) {          // r == -1: untimed warm-up (also sizes the buffers)
+    FB_CUDA(cudaEventRecord(ev[0], st));
+    rc = do_simulate(s, seed, (uint32_t)(r + 1), nullptr, 0, B, &ev[1]);
+    if (rc) break;
+    FB_CUDA(cudaEventRecord(ev[2], st));
+    rc = run_pass(s, theta, B, B, s->out_dev, true, nullptr, nullptr, &ev[3]);
+    if (rc) break;
+    FB_CUDA(cudaEventRecord(ev[5], st));
+    FB_CUDA(cudaStreamSynchronize(st));
+    if (r < 0) continue;
+    for (int k = 0; k < 5; ++k) {
+      float ms = 0.0f;
+      FB_CUDA(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
+      ms_host[k] += ms / (float)reps;
+    }
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return rc;
 }
 
 int fbsdej_solver_net_forward(fbsdej_solver* s, const float* theta, int net_index, const float* x, int rows, float* y) {

@@ -34,6 +34,12 @@ struct PricingArgs {
   const int2* tab_range;      // [N] (nlo, nhi)
   const float* qdisc;         // [N] e^{-q tau_i} (1 when d == 1)
   int limit;
+  // optional tabulation of the series in k = log(G e^{-q tau} / K): per step a uniform grid of nodes
+  // (sD, dsD/dk, sK, dsK/dk), cubic Hermite between nodes; outside the grid the series is summed term by term
+  const float4* atab;         // all steps' nodes, concatenated
+  const float4* atab_meta;    // [N] (kmin, 1/h, h, number of intervals)
+  const int* atab_off;        // [N] first node of step i
+  int use_atab;
   // VG spline tables: per (step, interval) cubic coefficients (c0..c3) around knot k0 + idx*h
   const float4* vg_coef;
   const float* vg_scale;      // [N] e^{-r tau_i} / pi
@@ -68,16 +74,35 @@ struct MertonModel {
     const float G = basket(X);
     const float Ge = (D == 1) ? G : G * a.qdisc[i];
     const float k = logf(Ge / a.K);
-    const int2 rg = a.tab_range[i];
-    const float4* __restrict__ tA = a.tabA + (size_t)i * a.limit;
-    const float* __restrict__ tK = a.tabK + (size_t)i * a.limit;
     float sD = 0.0f, sK = 0.0f;
-    for (int n = rg.x; n < rg.y; ++n) {
-      const float4 c = __ldg(tA + n);
-      const float d1 = fmaf(k, c.x, c.y);
-      const float d2 = d1 - c.z;
-      sD = fmaf(c.w, ncdf(d1), sD);
-      sK = fmaf(__ldg(tK + n), ncdf(d2), sK);
+    bool done = false;
+    if (a.use_atab) {
+      const float4 m = __ldg(a.atab_meta + i);
+      const float u = (k - m.x) * m.y;
+      if (u >= 0.0f && u < m.w) {
+        const int j = (int)u;
+        const float t = u - (float)j;
+        const float4* __restrict__ nd = a.atab + a.atab_off[i] + j;
+        const float4 p0 = __ldg(nd), p1 = __ldg(nd + 1);
+        const float t2 = t * t, t3 = t2 * t;
+        const float h00 = 2.0f * t3 - 3.0f * t2 + 1.0f, h10 = (t3 - 2.0f * t2 + t) * m.z;
+        const float h01 = 3.0f * t2 - 2.0f * t3, h11 = (t3 - t2) * m.z;
+        sD = h00 * p0.x + h10 * p0.y + h01 * p1.x + h11 * p1.y;
+        sK = h00 * p0.z + h10 * p0.w + h01 * p1.z + h11 * p1.w;
+        done = true;
+      }
+    }
+    if (!done) {
+      const int2 rg = a.tab_range[i];
+      const float4* __restrict__ tA = a.tabA + (size_t)i * a.limit;
+      const float* __restrict__ tK = a.tabK + (size_t)i * a.limit;
+      for (int n = rg.x; n < rg.y; ++n) {
+        const float4 c = __ldg(tA + n);
+        const float d1 = fmaf(k, c.x, c.y);
+        const float d2 = d1 - c.z;
+        sD = fmaf(c.w, ncdf(d1), sD);
+        sK = fmaf(__ldg(tK + n), ncdf(d2), sK);
+      }
     }
     A = Ge * sD - sK;
     dAb = (D == 1) ? sD : sD * Ge * (1.0f / D);

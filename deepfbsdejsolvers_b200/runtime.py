@@ -99,11 +99,12 @@ class NativeSolver:
 
     def __init__(self, ctx: Context, model_kind: int, scheme: int, nets: Sequence[NetSpec], n_y0: int, M: int = 0,
                  merton: Optional[L.MertonParams] = None, vg: Optional[L.VGParams] = None,
-                 mfg: Optional[L.MFGParams] = None, stale_time: bool = True, w_hat: float = 1.0, w_ind: float = 1.0):
+                 mfg: Optional[L.MFGParams] = None, stale_time: bool = True, w_hat: float = 1.0, w_ind: float = 1.0,
+                 price_table: bool = False):
         self.ctx, self.model_kind, self.scheme, self.nets, self.n_y0, self.M = ctx, model_kind, scheme, list(nets), n_y0, M
         d = L.SolverDesc()
         d.model, d.scheme, d.n_nets, d.n_y0, d.M = model_kind, scheme, len(nets), n_y0, M
-        d.stale_time, d.w_hat, d.w_ind = int(stale_time), w_hat, w_ind
+        d.stale_time, d.w_hat, d.w_ind, d.price_table = int(stale_time), w_hat, w_ind, int(price_table)
         for k, n in enumerate(nets):
             d.nets[k] = L.NetDesc(n.nin, n.nout, n.H, n.L, L.ACT[n.activation])
         h = C.c_void_p()
@@ -205,6 +206,12 @@ class NativeSolver:
         check(lib.fbsdej_solver_grad_step(self.handle, _p(self.theta), seed, _p(self.iteration), path_offset, B, B_global,
                                           _p(self.out)))
         return self.out
+
+    def profile(self, seed: int, B: int, reps: int = 3) -> dict:
+        """Mean device milliseconds per kernel class of one iteration (CUDA events inside the library)."""
+        ms = (C.c_float * 5)()
+        check(lib.fbsdej_solver_profile(self.handle, _p(self.theta), seed, B, reps, ms))
+        return dict(zip(("sim_paths", "sim_compensator", "forward", "backward", "reduce"), [float(x) for x in ms]))
 
     def bump_iteration(self) -> None:
         check(lib.fbsdej_bump_u32(self.ctx.handle, _p(self.iteration)))

@@ -87,6 +87,9 @@ typedef struct {
   int M;                /* compensator samples (reference: 5000, SolversJumpDiff.py:34); 0 for *Reg / MFG */
   int stale_time;       /* 1 = reference behaviour of the SumLocal graphs */
   float w_hat, w_ind;   /* MFG objective = w_hat*loss_hat + w_ind*loss_ind (couplage ON: 1,1) */
+  int price_table;      /* Merton: 0 = sum the series of pricingModels.py:40-49 term by term at every path-step,
+                           1 = evaluate it through a per-step cubic-Hermite table in log-moneyness (abs. error < 5e-8,
+                           the same idea as the reference's own spline of the VG price, pricingModels.py:170-178) */
 } fbsdej_solver_desc;
 
 FBSDEJ_API const char* fbsdej_last_error(void);
@@ -151,6 +154,12 @@ FBSDEJ_API int fbsdej_bump_u32(fbsdej_ctx* ctx, uint32_t* p);
 FBSDEJ_API int fbsdej_solver_train_steps(fbsdej_solver* s, float* theta, float* m, float* v, const float* mask, int* t_dev,
                               uint32_t* iter_dev, uint64_t seed, int B, int n_steps, float lr, float beta1,
                               float beta2, float eps, float* loss_out);
+
+/* Per-kernel device times of one training iteration, measured with CUDA events on the ctx stream around each launch
+ * (bench.py's roofline numbers).  Runs `reps` iterations WITHOUT the Adam update (theta unchanged) and writes the mean
+ * milliseconds: ms[0] simulate paths, ms[1] simulate + compact compensator samples, ms[2] forward, ms[3] backward,
+ * ms[4] partial reduction. */
+FBSDEJ_API int fbsdej_solver_profile(fbsdej_solver* s, const float* theta, uint64_t seed, int B, int reps, float* ms_host);
 
 /* Generic row-wise network evaluation: Net.call (Networks.py:17-23).  x [rows][nin] row-major,
  * y [rows][nout] row-major.  net_index selects the net inside theta's flat layout. */

@@ -118,12 +118,12 @@ def oracle_mfg(model, scheme, layout, theta, noise, B, dtype=torch.float32, w=(1
 
 
 # ---- native side --------------------------------------------------------------------------------------------
-def native_pricing(ctx, kind, params, scheme, layout, d=1, M=0, limit=30, stale_time=True):
+def native_pricing(ctx, kind, params, scheme, layout, d=1, M=0, limit=30, stale_time=True, price_table=None):
     from deepfbsdejsolvers_b200 import NetSpec
     from deepfbsdejsolvers_b200.coupledPricing import MertonJumpModel, VGmodel, AbsCoupling
     if kind == "merton":
         mm = MertonJumpModel(params["T"], params["N"], params["r"], params["muJ"], params["sigmaJ"], params["sigma"],
-                             params["lam"], params["K"], params["x0"], AbsCoupling(ALIN), limit, d=d)
+                             params["lam"], params["K"], params["x0"], AbsCoupling(ALIN), limit, d=d, price_table=price_table)
     else:
         mm = VGmodel(params["T"], params["N"], params["r"], params["theta"], params["kappa"], params["sigmaJ"], params["K"],
                      params["x0"], AbsCoupling(ALIN))
