@@ -1,0 +1,252 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by EXECUTING THE REFERENCE'S OWN SOURCE FILES, unmodified, from /root/reference.
+
+TensorFlow is not installable in this image, so the files are imported against tests/golden/tfshim (a torch-backed
+stand-in for the TF API they use).  For every solver class one real `train(...)` call with one Adam step is run;
+the fixture stores the initial parameters (library flat layout), the random increments the reference drew (recorded at
+its `tf.random.*` / `mathModel.jumps` / `mathModel.dN` call sites), and what the reference computed: the loss, the
+tape gradients, the parameters after `optimizer.apply_gradients`, and the Y0 it reports.
+
+    python tests/golden/make_golden.py            # needs /root/reference; writes tests/golden/*.npz
+
+The oracle (tests/test_oracle_golden.py) and the CUDA path (tests/test_golden_gpu.py) are both checked against these.
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "tfshim"))
+REF = os.environ.get("FBSDEJ_REFERENCE", "/root/reference")
+
+import tensorflow as tf  # noqa: E402  (the shim)
+
+
+def load(name, rel):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+PM = load("ref_pricingModels", "coupledPricing/pricingModels.py")
+NETP = load("ref_Networks_pricing", "coupledPricing/Networks.py")
+SJD = load("ref_SolversJumpDiff", "coupledPricing/SolversJumpDiff.py")
+SPJ = load("ref_SolversPureJump", "coupledPricing/SolversPureJump.py")
+MFGM = load("ref_MFGModel", "coupledMFG/MFGModel.py")
+NETM = load("ref_Networks_mfg", "coupledMFG/Networks.py")
+MFGS = load("ref_MFGSolvers", "coupledMFG/MFGSolvers.py")
+
+ALIN = 0.1
+MCOMP = 5000   # hard-coded in the reference (SolversJumpDiff.py:34)
+
+
+def func(x):   # mainMerton.py:60-61
+    return ALIN * tf.math.abs(x)
+
+
+def build_net(net, example):
+    """Run the Keras-style lazy build, then give the biases non-zero values (a choice of parameter values)."""
+    net(example)
+    g = torch.Generator().manual_seed(99)
+    for lyr in net.ListOfDense:
+        lyr.bias.data = 0.1 * torch.randn(lyr.bias.shape, generator=g)
+
+
+def flat_net(net):
+    return np.concatenate([np.concatenate([l.kernel.detach().numpy().reshape(-1), l.bias.detach().numpy()]) for l in net.ListOfDense])
+
+
+def flat_grads(net, var_list, grads):
+    """Gradients of `net`'s Dense variables in library order (zeros where the tape returned None / net not trained)."""
+    lookup = {id(v): g for v, g in zip(var_list, grads)}
+    parts = []
+    for l in net.ListOfDense:
+        for v in (l.kernel, l.bias):
+            g = lookup.get(id(v))
+            parts.append(np.zeros(v.numel(), dtype=np.float32) if g is None else g.numpy().reshape(-1))
+    return np.concatenate(parts)
+
+
+class Recorder:
+    """Records the increments at the reference's own call sites."""
+
+    def __init__(self, model, B):
+        self.B, self.inside, self.J, self.JMC, self.gauss = B, False, [], [], []
+        orig_jumps, orig_normal, rec = model.jumps, tf.random.normal, self
+
+        def jumps(n):
+            rec.inside = True
+            out = orig_jumps(n)
+            rec.inside = False
+            (rec.J if n == rec.B else rec.JMC).append(out.detach().clone())
+            return out
+
+        def normal(shape, *a, **k):
+            x = orig_normal(shape, *a, **k)
+            if not rec.inside:
+                rec.gauss.append(x.detach().clone())
+            return x
+        model.jumps = jumps
+        tf.random.normal = normal
+        self._restore = lambda: setattr(tf.random, "normal", orig_normal)
+
+    def close(self):
+        self._restore()
+
+
+def pricing_case(kind, scheme):
+    torch.manual_seed(0)
+    tf.random.seed(1000 + hash((kind, scheme)) % 1000)
+    tf.keras.initializers.GEN.manual_seed(7 + len(scheme))
+    tf.GradientTape.LOG.clear()
+    merton = kind == "merton"
+    B = 6
+    if merton:
+        N = 6
+        par = dict(T=1.0, N=N, r=0.1, muJ=0.0, sigmaJ=0.2, sigma=0.3, lam=3.0, K=0.9, x0=1.0)
+        model = PM.MertonJumpModel(par["T"], N, par["r"], par["muJ"], par["sigmaJ"], par["sigma"], par["lam"], par["K"], par["x0"], func, 30)
+        S = SJD
+    else:
+        N = 4
+        par = dict(T=1.0, N=N, r=0.1, theta=-0.1, kappa=0.1, sigmaJ=0.2, K=1.0, x0=1.0)
+        model = PM.VGmodel(par["T"], N, par["r"], par["theta"], par["kappa"], par["sigmaJ"], par["K"], par["x0"], func)
+        S = SPJ
+    reg = scheme.endswith("Reg")
+    one = scheme.endswith("1")
+    y0_on = None
+    if scheme == "Global":
+        y0_on = "UZ" if merton else "Gam"
+    ndim = 1 if (scheme == "Global" or reg or not merton) else 2
+    layer = 21 * np.ones((2,), dtype=np.int32)
+    netA = NETP.Net(1 if y0_on == "UZ" else 0, ndim, layer, "tanh")
+    netB = None if one else NETP.Net(1 if y0_on == "Gam" else 0, 1, layer, "tanh")
+    build_net(netA, tf.zeros([1, 2]))
+    if netB is not None:
+        build_net(netB, tf.zeros([1, 3]))
+    lr = 3e-4
+    cls = {"Global": "SolverGlobalFBSDE", "MultiStep1": "SolverMultiStepFBSDE1", "MultiStep2": "SolverMultiStepFBSDE2",
+           "SumLocal1": "SolverSumLocalFBSDE1", "SumLocal2": "SolverSumLocalFBSDE2", "SumLocalReg": "SolverGlobalSumLocalReg",
+           "MultiStepReg": "SolverGlobalMultiStepReg"}[scheme]
+    solver = getattr(S, cls)(model, netA, lr) if one else getattr(S, cls)(model, netA, netB, lr)
+    theta0 = [flat_net(netA)] + ([flat_net(netB)] if netB is not None else [])
+    if y0_on:
+        theta0.append(np.array([(netA if y0_on == "UZ" else netB).Y0.detach().numpy()], dtype=np.float32))
+    theta0 = np.concatenate(theta0).astype(np.float32)
+    # the Reg solvers train on 1000*batchSize paths (SolversJumpDiff.py:435): batchSize=1 keeps the fixture small
+    bs = 1 if reg else B
+    Btrain = 1000 * bs if reg else bs
+    rec = Recorder(model, Btrain)
+    solver.train(bs, 1, 1, 1)     # one Adam step, then a 1-path (x100 for Reg) validation pass we do not record
+    rec.close()
+    loss, grads, trained = tf.GradientTape.LOG[0]     # the variable list the reference handed to tape.gradient
+    g = [flat_grads(netA, trained, grads)] + ([flat_grads(netB, trained, grads)] if netB is not None else [])
+    if y0_on:
+        holder = netA if y0_on == "UZ" else netB
+        lookup = {id(v): gg for v, gg in zip(trained, grads)}
+        g.append(np.array([lookup[id(holder.Y0)].numpy()], dtype=np.float32))
+    theta1 = [flat_net(netA)] + ([flat_net(netB)] if netB is not None else [])
+    if y0_on:
+        theta1.append(np.array([(netA if y0_on == "UZ" else netB).Y0.detach().numpy()], dtype=np.float32))
+    ncall = N + 1 if scheme.startswith("SumLocal") and not reg else N      # jumps() calls of the training pass
+    out = dict(kind=kind, scheme=scheme, B=Btrain, N=N, lr=lr, theta0=theta0, loss=np.float64(loss),
+               grad=np.concatenate(g).astype(np.float32), theta1=np.concatenate(theta1).astype(np.float32),
+               Y0_report=np.float32(solver.listY0[0]), J=torch.stack(rec.J[:ncall][:N], 0).numpy(),
+               **{k: np.float64(v) for k, v in par.items() if k != "N"})
+    if merton:
+        out["dW"] = (np.float32(np.sqrt(model.dt)) * torch.stack(rec.gauss[:N], 0)).numpy()
+    if not reg:
+        out["JMC"] = torch.stack(rec.JMC[:ncall][:N], 0).numpy()
+    return out
+
+
+def qaver_curve():
+    t = np.arange(48) / 48.0
+    return (0.35 + 0.2 * np.sin(2 * np.pi * (t - 0.3)) + 0.05 * np.sin(4 * np.pi * t))[:13]    # N = 12 steps
+
+
+def mfg_case(scheme, couplage="ON"):
+    tf.random.seed(2000 + len(scheme))
+    tf.keras.initializers.GEN.manual_seed(17 + len(scheme))
+    tf.GradientTape.LOG.clear()
+    Q = qaver_curve()
+    par = dict(T=0.25, R0=0.24, jumpFactor=8.0, alpha=30.0, beta=float(np.exp(-15.0)), coeffOU=5.0, A=150.0, K=50.0, pi=0.1,
+               p0=6.159423723, p1=87.4286117, f0=0.0, f1=1e4, theta=0.12, C=80.0, S0=0.0, h1=0.0, h2=600.0, sig0=0.1, sig=0.3,
+               alphaTarget=-0.2, coeffEqui=1.0)
+    Qt = torch.tensor(Q, dtype=torch.float32)
+    MFGM.QAver = Qt     # the reference reads a bare global `QAver` at MFGModel.py:67-68 (notebook namespace)
+    model = MFGM.ModelCoupledFBSDE(par["T"], Qt, par["R0"], par["jumpFactor"], par["alpha"], par["beta"], par["coeffOU"], par["A"],
+                                   par["K"], par["pi"], par["p0"], par["p1"], par["f0"], par["f1"], par["theta"], par["C"], par["S0"],
+                                   par["h1"], par["h2"], par["sig0"], par["sig"], par["alphaTarget"], "stochastic", par["coeffEqui"])
+    method = {"Global": "Global", "MultiStep": "SumMultiStep", "SumLocal": "SumLocal", "SumLocalReg": "SumLocalReg",
+              "MultiStepReg": "SumMultiStepReg"}[scheme]
+    reg = scheme.endswith("Reg")
+    wh, wi = (2, 3) if scheme == "Global" else ((1, 1) if reg else (3, 4))
+    km = NETM.kerasModels(NETM.Net_hat, NETM.Net, method, wh, wi, 20 * np.ones((2,), dtype=np.int32), 22 * np.ones((2,), dtype=np.int32),
+                          "tanh", "tanh")
+    model.init(1)
+    build_net(km.model_hat, model.getProjectedStates())
+    build_net(km.model, model.getAllStates())
+    B, lr = 16, 1e-3
+    cls = {"Global": "SolverGlobalFBSDE", "MultiStep": "SolverMultiStepFBSDE", "SumLocal": "SolverSumLocalFBSDE",
+           "SumLocalReg": "SolverGlobalSumLocalReg", "MultiStepReg": "SolverGlobalMultiStepReg"}[scheme]
+    solver = getattr(MFGS, cls)(model, km, lr, couplage)
+
+    def theta():
+        parts = [flat_net(km.model_hat), flat_net(km.model)]
+        if scheme == "Global":
+            parts.append(np.array([km.model_hat.Y0_hat.detach().numpy(), km.model.Y0.detach().numpy()], dtype=np.float32))
+        return np.concatenate(parts).astype(np.float32)
+    theta0 = theta()
+    gauss, dNs = [], []
+    orig_normal, orig_dN = tf.random.normal, model.dN
+
+    def normal(shape, *a, **k):
+        x = orig_normal(shape, *a, **k)
+        gauss.append(x.detach().clone())
+        return x
+
+    def dN():
+        n, c = orig_dN()
+        dNs.append(n.detach().clone())
+        return n, c
+    tf.random.normal, model.dN = normal, dN
+    solver.train(B, 1, 1, 1)
+    tf.random.normal = orig_normal
+    loss, grads, trained = tf.GradientTape.LOG[0]
+    lookup = {id(v): g for v, g in zip(trained, grads)}
+    g = [flat_grads(km.model_hat, trained, grads), flat_grads(km.model, trained, grads)]
+    if scheme == "Global":
+        g.append(np.array([lookup[id(km.model_hat.Y0_hat)].numpy(), lookup[id(km.model.Y0)].numpy()], dtype=np.float32))
+    N = model.N
+    sq = np.float32(np.sqrt(model.dt))
+    return dict(kind="mfg", scheme=scheme, B=B, N=N, lr=lr, QAver=Q, theta0=theta0, loss=np.float64(loss),
+                grad=np.concatenate(g).astype(np.float32), theta1=theta(),
+                Y0_hat_report=np.float32(solver.listY0_hat[0]), Y0_report=np.float32(solver.listY0[0]),
+                dW0=(sq * torch.stack(gauss[0:2 * N:2], 0)).numpy(), dW=(sq * torch.stack(gauss[1:2 * N:2], 0)).numpy(),
+                dN=torch.stack(dNs[:N], 0).numpy(), **{k: np.float64(v) for k, v in par.items()})
+
+
+def main():
+    import contextlib
+    import io
+    for kind in ("merton", "vg"):
+        for scheme in ("Global", "MultiStep1", "MultiStep2", "SumLocal1", "SumLocal2", "SumLocalReg", "MultiStepReg"):
+            with contextlib.redirect_stdout(io.StringIO()):
+                d = pricing_case(kind, scheme)
+            np.savez_compressed(os.path.join(HERE, f"{kind}_{scheme}.npz"), **d)
+            print(kind, scheme, "loss", float(d["loss"]), "Y0", float(d["Y0_report"]), "|grad|max", float(np.abs(d["grad"]).max()))
+    for scheme in ("Global", "MultiStep", "SumLocal", "SumLocalReg", "MultiStepReg"):
+        with contextlib.redirect_stdout(io.StringIO()):
+            d = mfg_case(scheme)
+        np.savez_compressed(os.path.join(HERE, f"mfg_{scheme}.npz"), **d)
+        print("mfg", scheme, "loss", float(d["loss"]), "Y0_hat", float(d["Y0_hat_report"]), "Y0", float(d["Y0_report"]))
+
+
+if __name__ == "__main__":
+    main()

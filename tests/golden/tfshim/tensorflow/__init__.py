@@ -127,7 +127,7 @@ def Variable(value, trainable=True, dtype=torch.float32, name=None):
 
 
 class GradientTape:
-    LOG = []          # (target value, [grad or None, ...]) per .gradient() call
+    LOG = []          # (target value, [grad or None, ...], [variable, ...]) per .gradient() call
 
     def __enter__(self):
         return self
@@ -138,5 +138,5 @@ class GradientTape:
     def gradient(self, target, variables):
         variables = list(variables)
         grads = torch.autograd.grad(target, variables, allow_unused=True)
-        GradientTape.LOG.append((float(target.detach()), [None if g is None else g.detach().clone() for g in grads]))
+        GradientTape.LOG.append((float(target.detach()), [None if g is None else g.detach().clone() for g in grads], variables))
         return list(grads)

@@ -1,0 +1,63 @@
+"""GPU: the CUDA path against the outputs of the reference's own source files (tests/golden/*.npz, produced by
+tests/golden/make_golden.py through the TensorFlow stand-in): one training step of every solver class - loss, tape
+gradient, parameters after the Keras-form Adam update, reported Y0 - on the increments the reference drew
+(compensator: the reference's hard-coded 5000 samples)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+from test_oracle_golden import load_case, CASES
+
+pytestmark = pytest.mark.gpu
+
+
+def planes(a):
+    """[N, n] (reference, d = 1) -> [N, 1, n]."""
+    return np.ascontiguousarray(a[:, None, :])
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
+def test_cuda_reproduces_reference_step(ctx, path):
+    c = load_case(path)
+    kind, scheme, B = str(c["kind"]), str(c["scheme"]), int(c["B"])
+    if kind == "mfg":
+        keys = ("T", "R0", "jumpFactor", "alpha", "beta", "coeffOU", "A", "K", "pi", "p0", "p1", "f0", "f1", "theta", "C", "S0", "h1",
+                "h2", "sig0", "sig", "alphaTarget", "coeffEqui")
+        layout = H.mfg_layout(scheme)
+        s = H.native_mfg(ctx, dict(QAver=c["QAver"], jumpModel="stochastic", **{k: c[k] for k in keys}), scheme, layout)
+        s.set_theta(c["theta0"])
+        s.set_noise(B, c["dW0"], c["dW"], c["dN"])
+    else:
+        layout = H.pricing_layout(kind, scheme, 1)
+        par = {k: c[k] for k in (("T", "r", "muJ", "sigmaJ", "sigma", "lam", "K", "x0") if kind == "merton" else
+                                 ("T", "r", "theta", "kappa", "sigmaJ", "K", "x0"))}
+        par["N"] = int(c["N"])
+        M = 0 if scheme.endswith("Reg") else c["JMC"].shape[1]
+        s = H.native_pricing(ctx, kind, par, scheme, layout, d=1, M=M)
+        s.set_theta(c["theta0"])
+        s.set_noise(B, planes(c["dW"]) if "dW" in c else None, planes(c["J"]), planes(c["JMC"]) if "JMC" in c else None)
+    out = s.grad(B)
+    assert abs(out[0] - c["loss"]) <= 2e-5 * abs(c["loss"]), (out[0], c["loss"])
+    g_ref = c["grad"].astype(np.float64)
+    err = np.abs(out[4:] - g_ref).max() / np.abs(g_ref).max()
+    assert err < 1e-4, f"gradient: rel-to-max error {err:.2e}"
+    s.adam_step(float(c["lr"]))
+    th = s.get_theta()
+    solid = np.abs(g_ref) > 1e-3 * np.abs(g_ref).max()
+    np.testing.assert_allclose(th[solid], c["theta1"][solid], rtol=0, atol=float(c["lr"]) * 2e-2)
+    # reported Y0 with the reference's post-update parameters
+    s.set_theta(c["theta1"])
+    if kind == "mfg":
+        if scheme == "Global":
+            y0h, y0 = c["theta1"][s.y0_offset], c["theta1"][s.y0_offset + 1]
+        else:
+            q0 = float(c["QAver"][0])
+            y0h = s.net_forward(0, np.array([[0.0, q0, c["S0"], c["R0"]]], dtype=np.float32))[0, 0]
+            y0 = s.net_forward(1, np.array([[0.0, q0, c["S0"], q0, c["S0"], c["R0"]]], dtype=np.float32))[0, 0]
+        assert abs(y0h - c["Y0_hat_report"]) < 2e-6 and abs(y0 - c["Y0_report"]) < 2e-6
+    elif scheme != "Global":
+        y0 = s.net_forward(0, np.array([[0.0, c["x0"]]], dtype=np.float32))[0, 0]
+        assert abs(y0 - c["Y0_report"]) < 2e-6

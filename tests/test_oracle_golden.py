@@ -1,0 +1,148 @@
+"""CPU: pins the oracle (oracle/) against
+  (a) tests/golden/*.npz - outputs of the reference's OWN source files executed unmodified through tests/golden/tfshim
+      (generator: tests/golden/make_golden.py): loss, tape gradients, post-Adam parameters and reported Y0 of one
+      training step of each of its 19 solver classes, on the increments the reference drew;
+  (b) the closed-form known answers embedded in the reference."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from oracle import KerasAdam, MertonOracle, VGOracle, MFGOracle, mlp_forward, pricing_loss, mfg_loss
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load_case(path):
+    z = np.load(path, allow_pickle=False)
+    return {k: (z[k].item() if z[k].shape == () else z[k]) for k in z.files}
+
+
+def oracle_of(case, dtype=torch.float32):
+    kind, scheme = str(case["kind"]), str(case["scheme"])
+    if kind == "merton":
+        om = MertonOracle(T=case["T"], N=int(case["N"]), r=case["r"], muJ=case["muJ"], sigmaJ=case["sigmaJ"], sigma=case["sigma"],
+                          lam=case["lam"], K=case["K"], x0=case["x0"], aLin=0.1, limit=30, d=1, dtype=dtype)
+        layout = H.pricing_layout("merton", scheme, 1)
+    elif kind == "vg":
+        om = VGOracle(T=case["T"], N=int(case["N"]), r=case["r"], theta=case["theta"], kappa=case["kappa"], sigmaJ=case["sigmaJ"],
+                      K=case["K"], x0=case["x0"], aLin=0.1, dtype=dtype)
+        layout = H.pricing_layout("vg", scheme, 1)
+    else:
+        keys = ("T", "R0", "jumpFactor", "alpha", "beta", "coeffOU", "A", "K", "pi", "p0", "p1", "f0", "f1", "theta", "C", "S0", "h1",
+                "h2", "sig0", "sig", "alphaTarget", "coeffEqui")
+        om = MFGOracle(QAver=case["QAver"], jumpModel="stochastic", dtype=dtype, **{k: case[k] for k in keys})
+        layout = H.mfg_layout(scheme)
+    return om, layout
+
+
+def noise_of(case, dtype=torch.float32):
+    t = lambda a: torch.tensor(a, dtype=dtype)
+    if str(case["kind"]) == "mfg":
+        return {"dW0": t(case["dW0"]), "dW": t(case["dW"]), "dN": t(case["dN"])}
+    nz = {"J": t(case["J"])[..., None]}
+    if "dW" in case:
+        nz["dW"] = t(case["dW"])[..., None]
+    if "JMC" in case:
+        nz["JMC"] = t(case["JMC"])[..., None]
+    return nz
+
+
+def eval_oracle(case, dtype=torch.float32):
+    om, layout = oracle_of(case, dtype)
+    th = torch.tensor(case["theta0"], dtype=dtype, requires_grad=True)
+    nz = noise_of(case, dtype)
+    B = int(case["B"])
+    if str(case["kind"]) == "mfg":
+        lh, li = mfg_loss(om, str(case["scheme"]), layout, th, nz, B)
+        loss = lh + li
+    else:
+        loss = pricing_loss(om, str(case["scheme"]), layout, th, nz, B)
+    loss.backward()
+    return om, layout, float(loss.detach()), th.grad.detach()
+
+
+CASES = sorted(glob.glob(os.path.join(GOLD, "*.npz")))
+
+
+def test_fixtures_present():
+    assert len(CASES) == 19, "run tests/golden/make_golden.py (needs /root/reference)"
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
+def test_oracle_reproduces_reference_step(path):
+    case = load_case(path)
+    om, layout, loss, grad = eval_oracle(case)
+    assert layout.total == case["theta0"].size
+    assert abs(loss - case["loss"]) <= 2e-5 * abs(case["loss"]), (loss, case["loss"])
+    g_ref = case["grad"].astype(np.float64)
+    err = np.abs(grad.numpy().astype(np.float64) - g_ref).max() / np.abs(g_ref).max()
+    assert err < 5e-5, f"gradient: rel-to-max error {err:.2e}"
+    # Keras-form Adam on the REFERENCE gradient must land on the reference's post-update parameters
+    th = torch.tensor(case["theta0"].copy())
+    KerasAdam(layout.total, float(case["lr"])).step(th, torch.tensor(case["grad"]))
+    np.testing.assert_allclose(th.numpy(), case["theta1"], rtol=0, atol=2e-7)
+    # ... and the oracle's own gradient gives the same step wherever the gradient is not rounding noise
+    th2 = torch.tensor(case["theta0"].copy())
+    KerasAdam(layout.total, float(case["lr"])).step(th2, grad)
+    solid = np.abs(g_ref) > 1e-3 * np.abs(g_ref).max()
+    np.testing.assert_allclose(th2.numpy()[solid], case["theta1"][solid], rtol=0, atol=float(case["lr"]) * 2e-2)
+    # reported Y0: trainable scalar (Global) or net(0, x0)[0] with the updated parameters
+    t1 = torch.tensor(case["theta1"])
+    scheme = str(case["scheme"])
+    if str(case["kind"]) == "mfg":
+        if scheme == "Global":
+            y0h, y0 = float(t1[layout.y0_offset]), float(t1[layout.y0_offset + 1])
+        else:
+            st = om.init(1)
+            y0h = float(mlp_forward(t1, layout, 0, om.proj_states(st))[0, 0])
+            y0 = float(mlp_forward(t1, layout, 1, om.all_states(st))[0, 0])
+        assert abs(y0h - case["Y0_hat_report"]) < 2e-6 and abs(y0 - case["Y0_report"]) < 2e-6
+    else:
+        if scheme == "Global":
+            y0 = float(t1[layout.y0_offset])
+        else:
+            y0 = float(mlp_forward(t1, layout, 0, torch.tensor([[0.0, float(case["x0"])]]))[0, 0])
+        assert abs(y0 - case["Y0_report"]) < 2e-6
+
+
+def test_merton_closed_form_known_answers():
+    om = MertonOracle(aLin=0.1, limit=30, d=1, dtype=torch.float64, **H.MERTON)
+    assert abs(float(om.A(0, om.init(1))[0]) - 0.2714569268) < 1e-9
+    x = torch.tensor([[0.8], [1.0], [1.2]], dtype=torch.float64)
+    np.testing.assert_allclose(om.A(25, x).numpy(), [0.07911842, 0.20222704, 0.36822489], atol=2e-8)
+    np.testing.assert_allclose(om.A(49, x).numpy(), [0.00217845, 0.10377461, 0.30217749], atol=2e-8)
+    om10 = MertonOracle(aLin=0.1, limit=100, d=10, dtype=torch.float64, **H.MERTON)
+    assert abs(float(om10.A(0, om10.init(1))[0]) - 0.1109224) < 2e-7
+    om32 = MertonOracle(aLin=0.1, limit=30, d=1, **H.MERTON)
+    assert abs(float(om32.A(0, om32.init(1))[0]) - 0.2714569268) < 2e-6
+
+
+def test_vg_fft_known_answers():
+    ov = VGOracle(aLin=0.1, dtype=torch.float64, **H.VG)
+    assert abs(ov.correction - (-0.0796816965)) < 1e-9
+    assert abs(float(ov.A(0, ov.init(1))[0]) - 0.1331402194) < 1e-8
+    x = torch.tensor([[0.9], [1.0], [1.1]], dtype=torch.float64)
+    np.testing.assert_allclose(ov.A(15, x).numpy(), [0.02925149, 0.08252713, 0.16135454], atol=2e-8)
+
+
+def test_exact_solution_makes_coupling_vanish():
+    """with Y == A the coupling term is zero, so X follows the uncoupled jump-diffusion."""
+    om = MertonOracle(aLin=0.1, limit=30, d=1, dtype=torch.float64, **H.MERTON)
+    X = torch.tensor([[0.95], [1.3]], dtype=torch.float64)
+    dW, J = torch.tensor([[0.02], [-0.1]], dtype=torch.float64), torch.tensor([[0.0], [0.15]], dtype=torch.float64)
+    X1 = om.one_step(7, X, dW, J, om.A(7, X))
+    np.testing.assert_allclose(X1.numpy(), (X * torch.exp(om.drift() * om.dt + om.sig * dW + J)).numpy(), rtol=1e-14)
+
+
+def test_keras_adam_differs_from_torch_adam():
+    th = torch.ones(4)
+    g = torch.tensor([1e-8, 1e-3, 0.5, -2.0])
+    opt = KerasAdam(4, 1e-3)
+    opt.step(th, g)
+    # first Keras step: lr*sqrt(1-b2)/(1-b1) * (1-b1) g / (sqrt((1-b2) g^2) + 1e-7)
+    expect = 1 - 1e-3 * np.sqrt(1 - 0.999) / (1 - 0.9) * (0.1 * g.numpy()) / (np.sqrt(0.001 * g.numpy() ** 2) + 1e-7)
+    np.testing.assert_allclose(th.numpy(), expect, rtol=1e-6)
