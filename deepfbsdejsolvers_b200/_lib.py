@@ -83,6 +83,7 @@ def _load():
         "fbsdej_solver_price": (i32, [vp, i32, vp, i32, vp]),
         "fbsdej_transpose_nbd_to_ndb": (i32, [vp, vp, vp, i32, i32, i32]),
         "fbsdej_transpose_ndb_to_nbd": (i32, [vp, vp, vp, i32, i32, i32]),
+        "fbsdej_selftest_tc": (i32, [vp, vp, vp, vp, vp, vp, vp]),
         "fbsdej_ctx_launch_count": (C.c_longlong, [vp]),
     }
     for name, (res, args) in sig.items():

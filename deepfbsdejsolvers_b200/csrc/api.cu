@@ -20,6 +20,9 @@ static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
 }  // namespace fbsdej
 
+namespace fbsdej {
+int launch_tc_selftest(const float*, const float*, const float*, const float*, float*, float*, cudaStream_t);
+}
 using namespace fbsdej;
 
 struct fbsdej_ctx {
@@ -874,6 +877,14 @@ int fbsdej_solver_price(fbsdej_solver* s, int iStep, const float* X, int n, floa
   fill_pricing_args(s, nullptr, 1, 1, a);
   if (launch_price(s->model, s->D, a, iStep, X, n, out, s->ctx->stream)) return -2;
   s->ctx->launches += 1;
+  return 0;
+}
+
+int fbsdej_selftest_tc(fbsdej_ctx* ctx, const float* A, const float* B, const float* P, const float* Q, float* out0, float* out1) {
+  FB_REQUIRE(ctx && A && B && P && Q && out0 && out1, "selftest_tc: NULL argument");
+  FB_CUDA(cudaSetDevice(ctx->device));
+  if (fbsdej::launch_tc_selftest(A, B, P, Q, out0, out1, ctx->stream)) return -2;
+  ctx->launches += 1;
   return 0;
 }
 

@@ -32,14 +32,13 @@ __global__ void __launch_bounds__(kThreads) mfg_forward(const MFGArgs a) {
   float* swB = swA + net_smem_floats(a.netA, HP, false);
   float* red = swB + net_smem_floats(a.netB, HP, false);
   float* tb = red + 8;
-  Tiles<HP> t;
+  using TL = Tiles<HP, 4>;
+  TL t;
   t.carve(tb, false);
   const NetView<HP> nvA = load_net<HP>(swA, a.theta, a.netA, false);
   const NetView<HP> nvB = load_net<HP>(swB, a.theta, a.netB, false);
-  zero_tiles<HP>(tb, Tiles<HP>::fwd_floats());
+  zero_tiles(tb, TL::fwd_floats());
   const int row = threadIdx.x;
-  float* xt = t.xt + row;
-  const float* out = t.out + row;
   const size_t sB = (size_t)a.B;
   const int c0 = a.has_y ? 1 : 0;
   float lh_sum = 0.0f, li_sum = 0.0f;
@@ -56,12 +55,16 @@ __global__ void __launch_bounds__(kThreads) mfg_forward(const MFGArgs a) {
     for (int i = 0; i < a.N; ++i) {
       const float tm = (float)i * a.dt;
       const float dW0 = a.dW0[(size_t)i * sB + p], dW = a.dW[(size_t)i * sB + p], dN = a.dN[(size_t)i * sB + p];
-      xt[0] = tm; xt[RS] = hQ; xt[2 * RS] = hS; xt[3 * RS] = R;                       // getProjectedStates
-      mlp_fwd<HP, false>(nvA, t, row);
-      const float oh0 = out[0], oh1 = out[RS], oh2 = out[2 * RS];
-      xt[0] = tm; xt[RS] = Q; xt[2 * RS] = S; xt[3 * RS] = hQ; xt[4 * RS] = hS; xt[5 * RS] = R;   // getAllStates
-      mlp_fwd<HP, false>(nvB, t, row);
-      const float o0 = out[0], o1 = out[RS], o2 = out[2 * RS], o3 = out[3 * RS];
+      st4(t.xt + 4 * row, make_float4(tm, hQ, hS, R));                               // getProjectedStates
+      st4(t.xt + 4 * (TR + row), make_float4(1.0f, 0.0f, 0.0f, 0.0f));
+      mlp_fwd<HP, false, TL>(nvA, t, row);
+      const float4 oh = ld4(t.out + 4 * row);
+      const float oh0 = oh.x, oh1 = oh.y, oh2 = oh.z;
+      st4(t.xt + 4 * row, make_float4(tm, Q, S, hQ));                                // getAllStates
+      st4(t.xt + 4 * (TR + row), make_float4(hS, R, 1.0f, 0.0f));
+      mlp_fwd<HP, false, TL>(nvB, t, row);
+      const float4 oi = ld4(t.out + 4 * row);
+      const float o0 = oi.x, o1 = oi.y, o2 = oi.z, o3 = oi.w;
       const float lamdt = (a.stochastic ? a.beta * (expf(a.alpha * hQ) - 1.0f) : a.jumpFactor) * a.dt;
       const float dNc = dN - lamdt;
       float a_h = -a.dt * (hS * a.C), a_i = -a.dt * (S * a.C);
@@ -154,17 +157,16 @@ __global__ void __launch_bounds__(kThreads) mfg_backward(const MFGArgs a) {
   float* swB = swA + net_smem_floats(a.netA, HP, true);
   float* red = swB + net_smem_floats(a.netB, HP, true);
   float* tb = red + 8;
-  Tiles<HP> t;
+  using TL = Tiles<HP, 4>;
+  TL t;
   t.carve(tb, true);
   const NetView<HP> nvA = load_net<HP>(swA, a.theta, a.netA, true);
   const NetView<HP> nvB = load_net<HP>(swB, a.theta, a.netB, true);
-  zero_tiles<HP>(tb, Tiles<HP>::bwd_floats());
+  zero_tiles(tb, TL::bwd_floats());
   WGrad<HP> wgA, wgB;
   wgA.init(nvA, t);
   wgB.init(nvB, t);
   const int row = threadIdx.x;
-  float* xt = t.xt + row;
-  float* dout = t.dout + row;
   const size_t sB = (size_t)a.B;
   const int c0 = a.has_y ? 1 : 0;
   const float invB = a.inv_B, invBN = a.inv_B / (float)a.N;
@@ -234,26 +236,34 @@ __global__ void __launch_bounds__(kThreads) mfg_backward(const MFGArgs a) {
       Sbar += -a.dt * a.C * abi;
       float dx[HP];
       {
-        xt[0] = tm; xt[RS] = hQ; xt[2 * RS] = hS; xt[3 * RS] = R;
-        mlp_fwd<HP, true>(nvA, t, row);
-        for (int j = 0; j < nvA.nout; ++j) dout[j * RS] = 0.0f;
-        if (a.has_y) dout[0] = hyb * msk;
-        if (a.has_z) { dout[c0 * RS] = abh * dW0 * msk; dout[(c0 + 1) * RS] = abh * dNc * msk; }
-        mlp_delta<HP>(nvA, t, row, dx);
+        st4(t.xt + 4 * row, make_float4(tm, hQ, hS, R));
+        st4(t.xt + 4 * (TR + row), make_float4(1.0f, 0.0f, 0.0f, 0.0f));
+        mlp_fwd<HP, true, TL>(nvA, t, row);
+        float dd[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (a.has_y) dd[0] = hyb * msk;
+        if (a.has_z) {
+          const float z0b = abh * dW0 * msk, gb = abh * dNc * msk;
+          if (c0) { dd[1] = z0b; dd[2] = gb; } else { dd[0] = z0b; dd[1] = gb; }
+        }
+        st4(t.dout + 4 * row, make_float4(dd[0], dd[1], dd[2], dd[3]));
+        mlp_delta<HP, TL>(nvA, t, row, dx);
         hSbar += dx[2];
         __syncthreads();
         wgA.accumulate(tb);
         __syncthreads();
       }
       {
-        xt[0] = tm; xt[RS] = Q; xt[2 * RS] = S; xt[3 * RS] = hQ; xt[4 * RS] = hS; xt[5 * RS] = R;
-        mlp_fwd<HP, true>(nvB, t, row);
-        for (int j = 0; j < nvB.nout; ++j) dout[j * RS] = 0.0f;
-        if (a.has_y) dout[0] = yb * msk;
+        st4(t.xt + 4 * row, make_float4(tm, Q, S, hQ));
+        st4(t.xt + 4 * (TR + row), make_float4(hS, R, 1.0f, 0.0f));
+        mlp_fwd<HP, true, TL>(nvB, t, row);
+        float dd[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (a.has_y) dd[0] = yb * msk;
         if (a.has_z) {
-          dout[c0 * RS] = abi * dW0 * msk; dout[(c0 + 1) * RS] = abi * dNc * msk; dout[(c0 + 2) * RS] = abi * dW * msk;
+          const float z0b = abi * dW0 * msk, gb = abi * dNc * msk, zb = abi * dW * msk;
+          if (c0) { dd[1] = z0b; dd[2] = gb; dd[3] = zb; } else { dd[0] = z0b; dd[1] = gb; dd[2] = zb; }
         }
-        mlp_delta<HP>(nvB, t, row, dx);
+        st4(t.dout + 4 * row, make_float4(dd[0], dd[1], dd[2], dd[3]));
+        mlp_delta<HP, TL>(nvB, t, row, dx);
         Sbar += dx[2];
         hSbar += dx[4];
         __syncthreads();
@@ -280,7 +290,7 @@ __global__ void __launch_bounds__(kThreads) mfg_backward(const MFGArgs a) {
 template <int HP>
 static size_t mfg_smem(const MFGArgs& a, bool backward) {
   const int w = net_smem_floats(a.netA, HP, backward) + net_smem_floats(a.netB, HP, backward);
-  const int tl = backward ? Tiles<HP>::bwd_floats() : Tiles<HP>::fwd_floats();
+  const int tl = backward ? Tiles<HP, 4>::bwd_floats() : Tiles<HP, 4>::fwd_floats();
   return sizeof(float) * (size_t)(w + 8 + tl);
 }
 size_t mfg_smem_bytes(int HP, const MFGArgs& a, bool backward) {

@@ -108,19 +108,24 @@ struct MertonModel {
     dAb = (D == 1) ? sD : sD * Ge * (1.0f / D);
   }
   __device__ static __forceinline__ float dA_k(float dAb, float Xk) { return (D == 1) ? dAb : dAb / Xk; }
-  // jump-row inputs (SolversJumpDiff.py:37-39, 99-100, 173-175), written into this thread's row of the xt tile
+  // jump-row inputs (SolversJumpDiff.py:37-39, 99-100, 173-175) incl. the constant-1 feature
+  template <int HP>
   __device__ static __forceinline__ void jump_input(const PricingArgs& a, float t, const float (&X)[D],
-                                                    const float (&Jv)[D], float* __restrict__ xt) {
-    xt[0] = t;
+                                                    const float (&Jv)[D], float (&in)[HP]) {
+#pragma unroll
+    for (int j = 0; j < HP; ++j) in[j] = 0.0f;
+    in[0] = t;
     if (a.one_net) {
 #pragma unroll
-      for (int k = 0; k < D; ++k) xt[(1 + k) * RS] = X[k] * expf(Jv[k]);
+      for (int k = 0; k < D; ++k) in[1 + k] = X[k] * expf(Jv[k]);
+      in[1 + D] = 1.0f;
     } else {
 #pragma unroll
       for (int k = 0; k < D; ++k) {
-        xt[(1 + k) * RS] = X[k];
-        xt[(1 + D + k) * RS] = a.feat_mode == 0 ? Jv[k] : expf(Jv[k]);
+        in[1 + k] = X[k];
+        in[1 + D + k] = a.feat_mode == 0 ? Jv[k] : expf(Jv[k]);
       }
+      in[1 + 2 * D] = 1.0f;
     }
   }
   template <int HP>
@@ -152,15 +157,20 @@ struct VGModel {
     dAb = 1.0f - 0.5f * sq / x * cs;
   }
   __device__ static __forceinline__ float dA_k(float dAb, float) { return dAb; }
-  // jump-row inputs (SolversPureJump.py:34-36, 95-96)
+  // jump-row inputs (SolversPureJump.py:34-36, 95-96) incl. the constant-1 feature
+  template <int HP>
   __device__ static __forceinline__ void jump_input(const PricingArgs& a, float t, const float (&X)[1],
-                                                    const float (&Jv)[1], float* __restrict__ xt) {
-    xt[0] = t;
+                                                    const float (&Jv)[1], float (&in)[HP]) {
+#pragma unroll
+    for (int j = 0; j < HP; ++j) in[j] = 0.0f;
+    in[0] = t;
     if (a.one_net) {
-      xt[RS] = X[0] + X[0] * Jv[0];
+      in[1] = X[0] + X[0] * Jv[0];
+      in[2] = 1.0f;
     } else {
-      xt[RS] = X[0];
-      xt[2 * RS] = X[0] * Jv[0];
+      in[1] = X[0];
+      in[2] = X[0] * Jv[0];
+      in[3] = 1.0f;
     }
   }
   template <int HP>

@@ -20,24 +20,24 @@ __device__ __forceinline__ float group_allsum(float v, int G, float* red) {
   return block_sum(v, red);   // G == kThreads: one path per CTA
 }
 
-template <class Model, int HP>
+template <class Model, int HP, bool JUMP>
 __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a) {
   constexpr int D = Model::D;
   extern __shared__ __align__(16) float smem[];
+  const bool two = JUMP && !a.one_net;
   float* swA = smem;
   float* swB = swA + net_smem_floats(a.netA, HP, false);
-  float* red = swB + (a.one_net ? 0 : net_smem_floats(a.netB, HP, false));
+  float* red = swB + (two ? net_smem_floats(a.netB, HP, false) : 0);
   float* tb = red + 8;
-  Tiles<HP> t;
+  using TL = Tiles<HP, JUMP ? NOP : 4>;
+  TL t;
   t.carve(tb, false);
   const NetView<HP> nvA = load_net<HP>(swA, a.theta, a.netA, false);
-  const NetView<HP> nvJ = a.one_net ? nvA : load_net<HP>(swB, a.theta, a.netB, false);
-  zero_tiles<HP>(tb, Tiles<HP>::fwd_floats());
+  const NetView<HP> nvJ = two ? load_net<HP>(swB, a.theta, a.netB, false) : nvA;
+  zero_tiles(tb, TL::fwd_floats());
 
   const int row = threadIdx.x;
-  float* xt = t.xt + row;
-  const float* out = t.out + row;
-  const int G = a.G, ppb = kThreads / G, g = threadIdx.x % G;
+  const int G = JUMP ? a.G : 1, ppb = kThreads / G, g = threadIdx.x % G;
   const size_t sB = (size_t)a.B;
   const float rdt = a.r * a.dt;
   float lsum = 0.0f;
@@ -63,25 +63,32 @@ __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a)
       }
       float y_net = 0.0f, zdw = 0.0f;
       if (a.use_netA) {
-        xt[0] = tf;
+        float in[HP];
 #pragma unroll
-        for (int k = 0; k < D; ++k) xt[(1 + k) * RS] = X[k];
-        mlp_fwd<HP, false>(nvA, t, row);
-        if (a.has_y) y_net = out[0];
-        if (a.has_z) {
+        for (int j = 0; j < HP; ++j) in[j] = 0.0f;
+        in[0] = tf;
+#pragma unroll
+        for (int k = 0; k < D; ++k) in[1 + k] = X[k];
+        in[1 + D] = 1.0f;
+        store_row<HP>(t.xt, row, in);
+        mlp_fwd<HP, false, TL>(nvA, t, row);
+        if (a.has_y) y_net = t.out[tix(0, row)];
+        if (JUMP && a.has_z) {
 #pragma unroll
           for (int k = 0; k < D; ++k) {
-            const float z = out[(a.zoff + k) * RS];
+            const float z = t.out[tix(a.zoff + k, row)];
             zdw = fmaf(z, dWv[k], zdw);
             if (a.trajZ && writer) a.trajZ[((size_t)i * D + k) * sB + p] = z;
           }
         }
       }
       float gam = 0.0f, comp = 0.0f;
-      if (a.has_jump) {
-        Model::jump_input(a, tf, X, Jv, xt);
-        mlp_fwd<HP, false>(nvJ, t, row);
-        gam = out[0];
+      if (JUMP) {
+        float in[HP];
+        Model::template jump_input<HP>(a, tf, X, Jv, in);
+        store_row<HP>(t.xt, row, in);
+        mlp_fwd<HP, false, TL>(nvJ, t, row);
+        gam = t.out[tix(0, row)];
         const int nnz = a.jmc_nnz[i], n0 = a.jmc_n0[i];
         float csum = 0.0f;
         for (int m = g; m <= nnz; m += G) {
@@ -96,9 +103,10 @@ __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a)
             for (int k = 0; k < D; ++k) Jm[k] = 0.0f;
           }
           if (w != 0.0f) {
-            Model::jump_input(a, tf, X, Jm, xt);
-            mlp_fwd<HP, false>(nvJ, t, row);
-            csum = fmaf(w, out[0], csum);
+            Model::template jump_input<HP>(a, tf, X, Jm, in);
+            store_row<HP>(t.xt, row, in);
+            mlp_fwd<HP, false, TL>(nvJ, t, row);
+            csum = fmaf(w, t.out[tix(0, row)], csum);
           }
         }
         csum = group_allsum(csum, G, red);
@@ -181,27 +189,28 @@ __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a)
   }
 }
 
-template <class Model, int HP>
+template <class Model, int HP, bool JUMP>
 __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a) {
   constexpr int D = Model::D;
   extern __shared__ __align__(16) float smem[];
+  const bool two = JUMP && !a.one_net;
   float* swA = smem;
   float* swB = swA + net_smem_floats(a.netA, HP, true);
-  float* red = swB + (a.one_net ? 0 : net_smem_floats(a.netB, HP, true));
+  float* red = swB + (two ? net_smem_floats(a.netB, HP, true) : 0);
   float* tb = red + 8;
-  Tiles<HP> t;
+  using TL = Tiles<HP, JUMP ? NOP : 4>;
+  TL t;
   t.carve(tb, true);
   const NetView<HP> nvA = load_net<HP>(swA, a.theta, a.netA, true);
-  const NetView<HP> nvJ = a.one_net ? nvA : load_net<HP>(swB, a.theta, a.netB, true);
-  zero_tiles<HP>(tb, Tiles<HP>::bwd_floats());
-  WGrad<HP> wgA, wgB;
+  const NetView<HP> nvJ = two ? load_net<HP>(swB, a.theta, a.netB, true) : nvA;
+  zero_tiles(tb, TL::bwd_floats());
+  WGrad<HP> wgA;
   wgA.init(nvA, t);
-  wgB.init(nvJ, t);
+  WGrad<HP> wgB;
+  if (JUMP) wgB.init(nvJ, t);
 
   const int row = threadIdx.x;
-  float* xt = t.xt + row;
-  float* dout = t.dout + row;
-  const int G = a.G, ppb = kThreads / G, g = threadIdx.x % G;
+  const int G = JUMP ? a.G : 1, ppb = kThreads / G, g = threadIdx.x % G;
   const size_t sB = (size_t)a.B;
   const float invB = a.inv_B, invBN = a.inv_B / (float)a.N, rdt = a.r * a.dt;
   float y0g = 0.0f;
@@ -233,22 +242,23 @@ __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a
     }
     for (int i = a.N - 1; i >= 0; --i) {
       const float tf = (a.scheme == SCH_SUMLOCAL && a.stale_time) ? (float)(i == 0 ? 0 : i - 1) : (float)i;
-      float dWv[D], Jv[D];
+      float Jv[D];
+      float cY;
+      {
+        // adjoint of the coupled Euler step X' = X e^{..} + aLin |Ysel - A(i,X)| dt
+        const float s_i = a.aux_s[(size_t)i * sB + p], dAb = a.aux_dA[(size_t)i * sB + p];
+        float sumXbar = 0.0f;
 #pragma unroll
-      for (int k = 0; k < D; ++k) {
-        X[k] = a.trajX[((size_t)i * D + k) * sB + p];
-        dWv[k] = Model::kBrownian ? a.dW[((size_t)i * D + k) * sB + p] : 0.0f;
-        Jv[k] = a.J[((size_t)i * D + k) * sB + p];
+        for (int k = 0; k < D; ++k) sumXbar += Xbar[k];
+        cY = sumXbar * s_i;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          X[k] = a.trajX[((size_t)i * D + k) * sB + p];
+          const float dWk = Model::kBrownian ? a.dW[((size_t)i * D + k) * sB + p] : 0.0f;
+          Jv[k] = a.J[((size_t)i * D + k) * sB + p];
+          Xbar[k] = Xbar[k] * expf(a.drift_dt + a.sig * dWk + Jv[k]) - cY * Model::dA_k(dAb, X[k]);
+        }
       }
-      const float s_i = a.aux_s[(size_t)i * sB + p], dAb = a.aux_dA[(size_t)i * sB + p];
-      // adjoint of the coupled Euler step X' = X e^{..} + aLin |Ysel - A(i,X)| dt
-      float sumXbar = 0.0f;
-#pragma unroll
-      for (int k = 0; k < D; ++k) sumXbar += Xbar[k];
-      const float cY = sumXbar * s_i;
-#pragma unroll
-      for (int k = 0; k < D; ++k)
-        Xbar[k] = Xbar[k] * expf(a.drift_dt + a.sig * dWv[k] + Jv[k]) - cY * Model::dA_k(dAb, X[k]);
       // adjoints of the loss graph
       float abar, ybar = 0.0f;
       if (a.scheme == SCH_GLOBAL) {
@@ -265,35 +275,46 @@ __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a
         abar = -rb;
         ybar = rbm - rb + rdt * abar + cY;
       }
-      float dXacc[D];
-#pragma unroll
-      for (int k = 0; k < D; ++k) dXacc[k] = 0.0f;
       float dx[HP];
+      float dXacc[JUMP ? D : 1];      // input-gradient sum over this thread's rows (reduced over the path's G threads below)
+      if (JUMP) {
+#pragma unroll
+        for (int k = 0; k < (JUMP ? D : 1); ++k) dXacc[k] = 0.0f;
+      }
       if (a.use_netA) {
-        xt[0] = tf;
 #pragma unroll
-        for (int k = 0; k < D; ++k) xt[(1 + k) * RS] = X[k];
-        mlp_fwd<HP, true>(nvA, t, row);
-        for (int j = 0; j < a.netA.nout; ++j) dout[j * RS] = 0.0f;
-        if (a.has_y) dout[0] = ybar * msk;
-        if (a.has_z && a.has_jump) {
+        for (int j = 0; j < HP; ++j) dx[j] = 0.0f;
+        dx[0] = tf;
 #pragma unroll
-          for (int k = 0; k < D; ++k) dout[(a.zoff + k) * RS] = abar * dWv[k] * msk;
+        for (int k = 0; k < D; ++k) dx[1 + k] = X[k];
+        dx[1 + D] = 1.0f;
+        store_row<HP>(t.xt, row, dx);
+        mlp_fwd<HP, true, TL>(nvA, t, row);
+        for (int j = 0; j < pad4(a.netA.nout); ++j) t.dout[tix(j, row)] = 0.0f;
+        if (a.has_y) t.dout[tix(0, row)] = ybar * msk;
+        if (JUMP && a.has_z) {
+#pragma unroll
+          for (int k = 0; k < D; ++k)
+            t.dout[tix(a.zoff + k, row)] = abar * (Model::kBrownian ? a.dW[((size_t)i * D + k) * sB + p] : 0.0f) * msk;
         }
-        mlp_delta<HP>(nvA, t, row, dx);
+        mlp_delta<HP, TL>(nvA, t, row, dx);
 #pragma unroll
-        for (int k = 0; k < D; ++k) dXacc[k] += dx[1 + k];
+        for (int k = 0; k < D; ++k) {
+          if (JUMP) dXacc[JUMP ? k : 0] += dx[1 + k]; else Xbar[k] += dx[1 + k];
+        }
         __syncthreads();
         wgA.accumulate(tb);
         __syncthreads();
       }
-      if (a.has_jump) {
-        Model::jump_input(a, tf, X, Jv, xt);
-        mlp_fwd<HP, true>(nvJ, t, row);
-        for (int j = 0; j < nvJ.nout; ++j) dout[j * RS] = 0.0f;
-        dout[0] = abar * msk;
-        mlp_delta<HP>(nvJ, t, row, dx);
-        Model::template jump_input_grad<HP>(a, Jv, dx, dXacc);
+      if (JUMP) {
+        float (&dXj)[D] = reinterpret_cast<float (&)[D]>(dXacc);
+        Model::template jump_input<HP>(a, tf, X, Jv, dx);
+        store_row<HP>(t.xt, row, dx);
+        mlp_fwd<HP, true, TL>(nvJ, t, row);
+        for (int j = 0; j < pad4(nvJ.nout); ++j) t.dout[tix(j, row)] = 0.0f;
+        t.dout[tix(0, row)] = abar * msk;
+        mlp_delta<HP, TL>(nvJ, t, row, dx);
+        Model::template jump_input_grad<HP>(a, Jv, dx, dXj);
         __syncthreads();
         if (a.one_net) wgA.accumulate(tb); else wgB.accumulate(tb);
         __syncthreads();
@@ -313,20 +334,18 @@ __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a
           } else if (m == nnz) {
             w = (float)n0;
           }
-          Model::jump_input(a, tf, X, Jm, xt);
-          mlp_fwd<HP, true>(nvJ, t, row);
-          dout[0] = cscale * w;
-          mlp_delta<HP>(nvJ, t, row, dx);
-          Model::template jump_input_grad<HP>(a, Jm, dx, dXacc);
+          Model::template jump_input<HP>(a, tf, X, Jm, dx);
+          store_row<HP>(t.xt, row, dx);
+          mlp_fwd<HP, true, TL>(nvJ, t, row);
+          t.dout[tix(0, row)] = cscale * w;
+          mlp_delta<HP, TL>(nvJ, t, row, dx);
+          Model::template jump_input_grad<HP>(a, Jm, dx, dXj);
           __syncthreads();
           if (a.one_net) wgA.accumulate(tb); else wgB.accumulate(tb);
           __syncthreads();
         }
-      }
 #pragma unroll
-      for (int k = 0; k < D; ++k) {
-        const float s = (G == 1) ? dXacc[k] : group_allsum(dXacc[k], G, red);
-        Xbar[k] += s;
+        for (int k = 0; k < D; ++k) Xbar[k] += (G == 1) ? dXj[k] : group_allsum(dXj[k], G, red);
       }
       if (a.scheme == SCH_GLOBAL) Ybar *= (1.0f + rdt);
     }
@@ -339,7 +358,7 @@ __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a
   for (int e = threadIdx.x; e < a.P; e += blockDim.x) sg[e] = 0.0f;
   __syncthreads();
   wgA.flush(nvA, sg, a.netA.ext_off);
-  if (!a.one_net) wgB.flush(nvJ, sg, a.netB.ext_off);
+  if (two) wgB.flush(nvJ, sg, a.netB.ext_off);
   if (a.scheme == SCH_GLOBAL && threadIdx.x == 0) sg[a.y0_off] = y0tot;
   __syncthreads();
   float* grow = a.gpart + (size_t)blockIdx.x * a.P;
@@ -349,26 +368,32 @@ __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a
 // ---- launch glue ---------------------------------------------------------------------------------
 template <int HP>
 static size_t pricing_smem(const PricingArgs& a, bool backward) {
-  const int w = net_smem_floats(a.netA, HP, backward) + (a.one_net ? 0 : net_smem_floats(a.netB, HP, backward));
-  const int tl = backward ? Tiles<HP>::bwd_floats() : Tiles<HP>::fwd_floats();
+  const bool two = a.has_jump && !a.one_net;
+  const int w = net_smem_floats(a.netA, HP, backward) + (two ? net_smem_floats(a.netB, HP, backward) : 0);
+  const int tl = a.has_jump ? (backward ? Tiles<HP, NOP>::bwd_floats() : Tiles<HP, NOP>::fwd_floats())
+                            : (backward ? Tiles<HP, 4>::bwd_floats() : Tiles<HP, 4>::fwd_floats());
   return sizeof(float) * (size_t)(w + 8 + tl);
 }
 
-template <class Model, int HP>
-static int launch_pair(const PricingArgs& a, int grid, bool backward, cudaStream_t st) {
+template <class Model, int HP, bool JUMP>
+static int launch_one(const PricingArgs& a, int grid, bool backward, cudaStream_t st) {
   const size_t smem = pricing_smem<HP>(a, backward);
   if (smem > 227 * 1024) { set_error("pricing kernels: shared-memory footprint exceeds 227 KB"); return -1; }
   if (!backward) {
-    auto kern = pricing_forward<Model, HP>;
+    auto kern = pricing_forward<Model, HP, JUMP>;
     FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kThreads, smem, st>>>(a);
   } else {
-    auto kern = pricing_backward<Model, HP>;
+    auto kern = pricing_backward<Model, HP, JUMP>;
     FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kThreads, smem, st>>>(a);
   }
   FB_CUDA(cudaGetLastError());
   return 0;
+}
+template <class Model, int HP>
+static int launch_pair(const PricingArgs& a, int grid, bool backward, cudaStream_t st) {
+  return a.has_jump ? launch_one<Model, HP, true>(a, grid, backward, st) : launch_one<Model, HP, false>(a, grid, backward, st);
 }
 
 // A(iStep, X) for n states (component planes X[d][n]); the drop-in MertonJumpModel.A / VGmodel.A.
@@ -397,20 +422,24 @@ int launch_price(int model, int D, const PricingArgs& a, int iStep, const float*
   return 0;
 }
 
-template <class Model, int HP>
-static int occ_pair(const PricingArgs& a, bool backward) {
+template <class Model, int HP, bool JUMP>
+static int occ_one(const PricingArgs& a, bool backward) {
   const size_t smem = pricing_smem<HP>(a, backward);
   int nb = 0;
   if (!backward) {
-    auto kern = pricing_forward<Model, HP>;
+    auto kern = pricing_forward<Model, HP, JUMP>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem) != cudaSuccess) return 1;
   } else {
-    auto kern = pricing_backward<Model, HP>;
+    auto kern = pricing_backward<Model, HP, JUMP>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem) != cudaSuccess) return 1;
   }
   return nb < 1 ? 1 : nb;
+}
+template <class Model, int HP>
+static int occ_pair(const PricingArgs& a, bool backward) {
+  return a.has_jump ? occ_one<Model, HP, true>(a, backward) : occ_one<Model, HP, false>(a, backward);
 }
 // resident CTAs per SM of the kernel that launch_pricing would run
 int pricing_blocks_per_sm(int model, int D, int HP, const PricingArgs& a, bool backward) {

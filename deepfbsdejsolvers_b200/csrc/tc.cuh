@@ -1,0 +1,143 @@
+// sm_100a tensor-core plumbing used by the tcgen05 variants of the fused kernels: mbarriers, TMEM allocation,
+// UMMA shared-memory / instruction descriptors (no-swizzle canonical layouts), tcgen05.mma kind::tf32, tcgen05.ld.
+//
+// Operand layouts (fp32 containers, TF32 math).  Every activation tile of tile_mlp.cuh is stored as float4 chunks
+// [feature/4][row][4]; that single byte layout is
+//   * a K-major canonical operand when features are the K dimension (forward / input-gradient GEMMs): 8-row x 16-byte
+//     core matrices, leading-byte-offset (next 16-byte chunk along K) = 2048 B, stride-byte-offset (next 8 rows) = 128 B;
+//   * an MN-major canonical operand when rows are the K dimension (weight-gradient GEMMs): the 8 rows of one K step
+//     are contiguous (128 B), the next 4-feature chunk along M/N is 2048 B away.
+// fp32 accuracy from TF32 tensor cores: operands are split x = hi + lo with hi = x with the 13 low mantissa bits
+// cleared (exactly representable in TF32) and lo = x - hi (exact in fp32); D += A_hi B_hi + A_lo B_hi + A_hi B_lo.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+
+namespace fbsdej {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
+// generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ---- TMEM -----------------------------------------------------------------------------------------------------
+// Called by ONE full warp.  ncols: power of two >= 32.
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// ---- descriptors ----------------------------------------------------------------------------------------------
+// 64-bit shared-memory matrix descriptor, SWIZZLE_NONE, descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  const uint32_t lo = ((addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+  const uint32_t hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14);
+  return ((uint64_t)hi << 32) | lo;
+}
+// 32-bit instruction descriptor, kind::tf32, fp32 accumulate.  a_mn / b_mn: operand is MN-major.
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
+// kind::f16 with BF16 operands, fp32 accumulate
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] * B[smem], issued by ONE thread.
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives once all tcgen05 operations issued so far by this thread have completed
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- TMEM -> registers: lane (= row) of this thread, 8 consecutive columns -------------------------------------
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// hi/lo split for 3xTF32
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  lo = x - hi;
+}
+// round-to-nearest TF32 (single-pass operands of the weight-gradient GEMMs)
+__device__ __forceinline__ float rn_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// bf16 hi/lo split (bf16x3: D += A_hi B_hi + A_lo B_hi + A_hi B_lo, ~2^-16 relative): returns the two bf16 bit patterns
+__device__ __forceinline__ void split_bf16(float x, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+  hi = (uint32_t)__bfloat16_as_ushort(h);
+  lo = (uint32_t)__bfloat16_as_ushort(l);
+}
+// Store 8 consecutive features of this thread's row as bf16 hi / lo chunks: tile layout [feature/8][row][8 bf16].
+__device__ __forceinline__ void store_bf16x8(uint4* __restrict__ hi_tile, uint4* __restrict__ lo_tile, int chunk, int row,
+                                             const float* v) {
+  uint32_t h[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) split_bf16(v[i], h[i], l[i]);
+  hi_tile[chunk * 128 + row] = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+  lo_tile[chunk * 128 + row] = make_uint4(l[0] | (l[1] << 16), l[2] | (l[3] << 16), l[4] | (l[5] << 16), l[6] | (l[7] << 16));
+}
+
+}  // namespace tc
+}  // namespace fbsdej

@@ -1,0 +1,208 @@
+// Self-test of the tcgen05 plumbing (tc.cuh): two tiny GEMMs on one CTA, results returned to the caller.
+//   test 0: D[128][32] = A[128][24] * B[24][32]          K-major operands  (forward / input-gradient GEMM shape)
+//   test 1: D[m][n]    = sum_r P[r][m] * Q[r][n], r<128  MN-major operands (weight-gradient GEMM shape), m,n < 24
+// Both with the 3xTF32 split.  Used by tests/test_tc_gpu.py before the fused kernels rely on the same descriptors.
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace fbsdej {
+
+constexpr int ST_TR = 128;
+
+__global__ void __launch_bounds__(128) tc_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                          const float* __restrict__ P, const float* __restrict__ Q,
+                                                          float* __restrict__ out0, float* __restrict__ out1) {
+  extern __shared__ __align__(1024) float sm[];
+  // tiles: [6 chunks][128 rows][4]; placed first so that the M = 128 MN-major reads (32 chunks x 2 KB) stay inside smem
+  float* a_hi = sm;                 // 3072 floats
+  float* a_lo = a_hi + 3072;
+  float* q_hi = a_lo + 3072;
+  float* q_lo = q_hi + 3072;
+  float* b_hi = q_lo + 3072;        // [6 chunks][32 n][4]
+  float* b_lo = b_hi + 768;
+  float* pad = b_lo + 768;          // >= 64 KB of slack follows (dynamic smem size chosen by the launcher)
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int r = threadIdx.x, warp = r >> 5;
+  (void)pad;
+  if (warp == 0) tc::tmem_alloc(&tmem_base, 64);
+  if (r == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tm = tmem_base;
+  uint32_t phase = 0;
+  for (int test = 0; test < 2; ++test) {
+    const float* src = test == 0 ? A : P;
+    for (int c = 0; c < 6; ++c) {
+      float hi[4], lo[4];
+      for (int i = 0; i < 4; ++i) tc::split_tf32(src[r * 24 + 4 * c + i], hi[i], lo[i]);
+      st4(a_hi + (c * ST_TR + r) * 4, make_float4(hi[0], hi[1], hi[2], hi[3]));
+      st4(a_lo + (c * ST_TR + r) * 4, make_float4(lo[0], lo[1], lo[2], lo[3]));
+      if (test == 1) {
+        for (int i = 0; i < 4; ++i) tc::split_tf32(Q[r * 24 + 4 * c + i], hi[i], lo[i]);
+        st4(q_hi + (c * ST_TR + r) * 4, make_float4(hi[0], hi[1], hi[2], hi[3]));
+        st4(q_lo + (c * ST_TR + r) * 4, make_float4(lo[0], lo[1], lo[2], lo[3]));
+      }
+    }
+    if (test == 0) {
+      for (int e = r; e < 24 * 32; e += 128) {
+        const int k = e / 32, n = e % 32;
+        float hi, lo;
+        tc::split_tf32(B[k * 32 + n], hi, lo);
+        b_hi[((k >> 2) * 32 + n) * 4 + (k & 3)] = hi;
+        b_lo[((k >> 2) * 32 + n) * 4 + (k & 3)] = lo;
+      }
+    }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    if (r == 0) {
+      tc::tc_fence_after();
+      if (test == 0) {
+        const uint32_t id = tc::idesc_tf32(128, 32, false, false);
+        uint32_t acc = 0;
+        for (int s = 0; s < 3; ++s) {       // K = 24 = 3 x 8
+          const uint64_t ah = tc::smem_desc(tc::smem_u32(a_hi) + s * 4096, 2048, 128);
+          const uint64_t al = tc::smem_desc(tc::smem_u32(a_lo) + s * 4096, 2048, 128);
+          const uint64_t bh = tc::smem_desc(tc::smem_u32(b_hi) + s * 1024, 512, 128);
+          const uint64_t bl = tc::smem_desc(tc::smem_u32(b_lo) + s * 1024, 512, 128);
+          tc::mma_tf32(tm, ah, bh, id, acc); acc = 1;
+          tc::mma_tf32(tm, al, bh, id, 1);
+          tc::mma_tf32(tm, ah, bl, id, 1);
+        }
+      } else {
+        const uint32_t id = tc::idesc_tf32(128, 32, true, true);
+        uint32_t acc = 0;
+        for (int s = 0; s < 16; ++s) {      // K = 128 rows = 16 x 8
+          const uint64_t ph = tc::smem_desc(tc::smem_u32(a_hi) + s * 128, 128, 2048);
+          const uint64_t pl = tc::smem_desc(tc::smem_u32(a_lo) + s * 128, 128, 2048);
+          const uint64_t qh = tc::smem_desc(tc::smem_u32(q_hi) + s * 128, 128, 2048);
+          const uint64_t ql = tc::smem_desc(tc::smem_u32(q_lo) + s * 128, 128, 2048);
+          tc::mma_tf32(tm + 32, ph, qh, id, acc); acc = 1;
+          tc::mma_tf32(tm + 32, pl, qh, id, 1);
+          tc::mma_tf32(tm + 32, ph, ql, id, 1);
+        }
+      }
+      tc::mma_commit(&bar);
+    }
+    tc::mbar_wait(&bar, phase);
+    phase ^= 1;
+    tc::tc_fence_after();
+    float* out = test == 0 ? out0 : out1;
+    for (int c8 = 0; c8 < 4; ++c8) {
+      float v[8];
+      tc::tmem_ld8(tm + ((uint32_t)(32 * warp) << 16) + (test == 0 ? 0 : 32) + 8 * c8, v);
+      tc::tmem_ld_wait();
+      for (int i = 0; i < 8; ++i) out[r * 32 + 8 * c8 + i] = v[i];
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+  }
+  if (warp == 0) tc::tmem_dealloc(tm, 64);
+}
+
+// bf16x3 variants: test 2: out2[128][32] = A[128][24(->32)] * B[24][32] (K-major); test 3: out3[m][n] = sum_r P[r][m] Q[r][n]
+// (MN-major).  Tiles [feature/8][row][8 bf16]: one byte layout serves both major-nesses.
+__global__ void __launch_bounds__(128) tc_selftest_bf16_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                               const float* __restrict__ P, const float* __restrict__ Q,
+                                                               float* __restrict__ out2, float* __restrict__ out3) {
+  extern __shared__ __align__(1024) float sm[];
+  uint4* a_hi = reinterpret_cast<uint4*>(sm);        // 4 chunks x 128 rows (chunk 3 zero)
+  uint4* a_lo = a_hi + 512;
+  uint4* q_hi = a_lo + 512;
+  uint4* q_lo = q_hi + 512;
+  uint4* b_hi = q_lo + 512;                          // [K/8 = 4][N = 32] uint4 (8 bf16 along K)
+  uint4* b_lo = b_hi + 128;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int r = threadIdx.x, warp = r >> 5;
+  if (warp == 0) tc::tmem_alloc(&tmem_base, 64);
+  if (r == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tm = tmem_base;
+  uint32_t phase = 0;
+  for (int test = 0; test < 2; ++test) {
+    const float* src = test == 0 ? A : P;
+    for (int c = 0; c < 4; ++c) {
+      float v[8];
+      for (int i = 0; i < 8; ++i) v[i] = (8 * c + i < 24) ? src[r * 24 + 8 * c + i] : 0.0f;
+      tc::store_bf16x8(a_hi, a_lo, c, r, v);
+      if (test == 1) {
+        for (int i = 0; i < 8; ++i) v[i] = (8 * c + i < 24) ? Q[r * 24 + 8 * c + i] : 0.0f;
+        tc::store_bf16x8(q_hi, q_lo, c, r, v);
+      }
+    }
+    if (test == 0) {
+      unsigned short* bh = reinterpret_cast<unsigned short*>(b_hi);
+      unsigned short* bl = reinterpret_cast<unsigned short*>(b_lo);
+      for (int e = r; e < 32 * 32; e += 128) {
+        const int k = e / 32, n = e % 32;
+        uint32_t hi, lo;
+        tc::split_bf16(k < 24 ? B[k * 32 + n] : 0.0f, hi, lo);
+        bh[((k >> 3) * 32 + n) * 8 + (k & 7)] = (unsigned short)hi;
+        bl[((k >> 3) * 32 + n) * 8 + (k & 7)] = (unsigned short)lo;
+      }
+    }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    if (r == 0) {
+      tc::tc_fence_after();
+      if (test == 0) {
+        const uint32_t id = tc::idesc_bf16(128, 32, false, false);
+        uint32_t acc = 0;
+        for (int s = 0; s < 2; ++s) {       // K = 32 = 2 x 16 (two 16-byte chunks per step)
+          const uint64_t ah = tc::smem_desc(tc::smem_u32(a_hi) + s * 4096, 2048, 128);
+          const uint64_t al = tc::smem_desc(tc::smem_u32(a_lo) + s * 4096, 2048, 128);
+          const uint64_t bh = tc::smem_desc(tc::smem_u32(b_hi) + s * 1024, 512, 128);
+          const uint64_t bl = tc::smem_desc(tc::smem_u32(b_lo) + s * 1024, 512, 128);
+          tc::mma_bf16(tm, ah, bh, id, acc); acc = 1;
+          tc::mma_bf16(tm, al, bh, id, 1);
+          tc::mma_bf16(tm, ah, bl, id, 1);
+        }
+      } else {
+        const uint32_t id = tc::idesc_bf16(128, 32, true, true);
+        uint32_t acc = 0;
+        for (int s = 0; s < 8; ++s) {       // K = 128 rows = 8 x 16 (two 8-row groups per step, 128 B apart)
+          const uint64_t ph = tc::smem_desc(tc::smem_u32(a_hi) + s * 256, 128, 2048);
+          const uint64_t pl = tc::smem_desc(tc::smem_u32(a_lo) + s * 256, 128, 2048);
+          const uint64_t qh = tc::smem_desc(tc::smem_u32(q_hi) + s * 256, 128, 2048);
+          const uint64_t ql = tc::smem_desc(tc::smem_u32(q_lo) + s * 256, 128, 2048);
+          tc::mma_bf16(tm + 32, ph, qh, id, acc); acc = 1;
+          tc::mma_bf16(tm + 32, pl, qh, id, 1);
+          tc::mma_bf16(tm + 32, ph, ql, id, 1);
+        }
+      }
+      tc::mma_commit(&bar);
+    }
+    tc::mbar_wait(&bar, phase);
+    phase ^= 1;
+    tc::tc_fence_after();
+    float* out = test == 0 ? out2 : out3;
+    for (int c8 = 0; c8 < 4; ++c8) {
+      float v[8];
+      tc::tmem_ld8(tm + ((uint32_t)(32 * warp) << 16) + (test == 0 ? 0 : 32) + 8 * c8, v);
+      tc::tmem_ld_wait();
+      for (int i = 0; i < 8; ++i) out[r * 32 + 8 * c8 + i] = v[i];
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+  }
+  if (warp == 0) tc::tmem_dealloc(tm, 64);
+}
+
+int launch_tc_selftest(const float* A, const float* B, const float* P, const float* Q, float* out0, float* out1, cudaStream_t st) {
+  const size_t smem = 160 * 1024;
+  FB_CUDA(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc_selftest_kernel<<<1, 128, smem, st>>>(A, B, P, Q, out0, out1);
+  FB_CUDA(cudaGetLastError());
+  FB_CUDA(cudaFuncSetAttribute(tc_selftest_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc_selftest_bf16_kernel<<<1, 128, smem, st>>>(A, B, P, Q, out0 + 128 * 32, out1 + 128 * 32);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace fbsdej

@@ -1,15 +1,17 @@
-// Tile MLP primitives: one CTA = kThreads rows; thread r owns row r.
+// Tile MLP primitives: one CTA = 128 rows; thread r owns row r.
 //
 // Replaces the Keras `Dense` stacks of the reference (coupledPricing/Networks.py:6-23,
 // coupledMFG/Networks.py:6-46: nin -> H (act) -> H (act) -> nout) and the tf.GradientTape pass through them
 // (SolversJumpDiff.py:47-53).
 //
 // Data layout (shared memory)
-//   * activation tiles are column-major  tile[col * RS + row]  (RS = 132): thread r only ever touches row r in
-//     the forward / delta passes, so the layers of one MLP evaluation need NO barrier; lanes hit consecutive banks.
+//   * activation tiles use the UMMA canonical K-major (no-swizzle) layout of sm_100: feature f of row r lives at
+//     float index ((f/4)*128 + r)*4 + f%4, i.e. float4 chunks [f/4][r].  Thread r reads/writes whole float4 chunks
+//     of its own row (conflict-free 128-bit accesses, no barrier between the layers of one evaluation), and the
+//     same bytes are directly a tcgen05.mma A operand (8-row x 16-byte core matrices, SBO = 128 B, LBO = 2048 B).
 //   * the constant-1 trick folds biases into the GEMVs: tile XT has a ones column at col nin, H1/H2 have a ones
 //     column at col H (< HP), and the weight blocks carry the bias as one more row / column.
-//   * per net, rows HP floats wide:
+//   * per net, rows HP floats wide, row counts padded to a multiple of 4 with zero rows:
 //       W1  [(nin+1)][HP]  row nin = b1         W2  [(H+1)][HP]  row H = b2        W3T [nout][HP]  col H = b3
 //       W2T [H][HP]  (W2T[j][k] = W2[k][j])     W1T [H][HP]  (W1T[j][i] = W1[i][j])      (backward only)
 //   * the weight gradient is an outer-product GEMM over the rows of the tile.  Every thread owns one fixed 4x4
@@ -20,7 +22,8 @@
 
 namespace fbsdej {
 
-constexpr int RS = 132;   // row stride (floats) of the column-major tiles
+constexpr int TR = 128;   // rows per tile (= kThreads)
+constexpr int NOP = 12;   // largest supported nout (width of the out / dout tiles of the jump-scheme kernels)
 
 enum { ACT_TANH = 0, ACT_RELU = 1 };
 
@@ -29,13 +32,17 @@ struct NetRt {     // runtime description of a network
   int ext_off;     // offset of this net in the external flat parameter vector
 };
 
+__host__ __device__ inline int pad4(int x) { return (x + 3) & ~3; }
 __host__ __device__ inline int net_ext_params(const NetRt& n) {
   return n.nin * n.H + n.H + n.H * n.H + n.H + n.H * n.nout + n.nout;
 }
 // smem floats of one net's weight block
 __host__ __device__ inline int net_smem_floats(const NetRt& n, int HP, bool bwd) {
-  return ((n.nin + 1) + (n.H + 1) + n.nout + (bwd ? 2 * n.H : 0)) * HP;
+  return (pad4(n.nin + 1) + pad4(n.H + 1) + n.nout + (bwd ? 2 * pad4(n.H) : 0)) * HP;
 }
+
+// float index of (feature f, row r) in a tile
+__device__ __forceinline__ int tix(int f, int r) { return (((f >> 2) * TR + r) << 2) | (f & 3); }
 
 template <int HP>
 struct NetView {   // smem views of one net
@@ -50,7 +57,7 @@ __device__ __forceinline__ float dact_fn(float h, int act) { return act == ACT_T
 template <int HP>
 __device__ __forceinline__ NetView<HP> load_net(float* sw, const float* __restrict__ theta, const NetRt& rt, bool bwd) {
   const int nin = rt.nin, H = rt.H, nout = rt.nout;
-  const int o1 = 0, o2 = (nin + 1) * HP, o3 = o2 + (H + 1) * HP, o2t = o3 + nout * HP, o1t = o2t + H * HP;
+  const int o1 = 0, o2 = pad4(nin + 1) * HP, o3 = o2 + pad4(H + 1) * HP, o2t = o3 + nout * HP, o1t = o2t + pad4(H) * HP;
   const int total = net_smem_floats(rt, HP, bwd);
   for (int i = threadIdx.x; i < total; i += blockDim.x) sw[i] = 0.0f;
   __syncthreads();
@@ -84,69 +91,74 @@ __device__ __forceinline__ NetView<HP> load_net(float* sw, const float* __restri
   return nv;
 }
 
-// a[j] = sum_{k<K} in[k*RS] * W[k*HP + j]   (in = this thread's row of a column-major tile)
+// one input value against one weight row: a[j] += x * W[j]
 template <int HP>
-__device__ __forceinline__ void gemv(float (&a)[HP], const float* __restrict__ W, int K, const float* __restrict__ in) {
+__device__ __forceinline__ void axpy_row(float (&a)[HP], float x, const float* __restrict__ W) {
 #pragma unroll
-  for (int j = 0; j < HP; ++j) a[j] = 0.0f;
-#pragma unroll 4
-  for (int k = 0; k < K; ++k) {
-    const float hk = in[k * RS];
-#pragma unroll
-    for (int j4 = 0; j4 < HP / 4; ++j4) {
-      const float4 w = ld4(W + k * HP + 4 * j4);
-      a[4 * j4] = fmaf(hk, w.x, a[4 * j4]);
-      a[4 * j4 + 1] = fmaf(hk, w.y, a[4 * j4 + 1]);
-      a[4 * j4 + 2] = fmaf(hk, w.z, a[4 * j4 + 2]);
-      a[4 * j4 + 3] = fmaf(hk, w.w, a[4 * j4 + 3]);
-    }
+  for (int j4 = 0; j4 < HP / 4; ++j4) {
+    const float4 w = ld4(W + 4 * j4);
+    a[4 * j4] = fmaf(x, w.x, a[4 * j4]);
+    a[4 * j4 + 1] = fmaf(x, w.y, a[4 * j4 + 1]);
+    a[4 * j4 + 2] = fmaf(x, w.z, a[4 * j4 + 2]);
+    a[4 * j4 + 3] = fmaf(x, w.w, a[4 * j4 + 3]);
   }
 }
 
-// Tiles of one CTA.  xt/h1/h2/d1/d2 are HP columns wide, dout/out are NOP columns wide (NOP = 12).
-constexpr int NOP = 12;
+// a[j] = sum_{k < 4*K4} in[k] * W[k*HP + j]   (in = this thread's row of a tile; W rows beyond the true K are zero)
 template <int HP>
+__device__ __forceinline__ void gemv(float (&a)[HP], const float* __restrict__ W, int K4, const float* __restrict__ tile, int row) {
+#pragma unroll
+  for (int j = 0; j < HP; ++j) a[j] = 0.0f;
+  const float* __restrict__ in = tile + 4 * row;
+#pragma unroll 2
+  for (int c = 0; c < K4; ++c) {
+    const float4 x = ld4(in + c * (4 * TR));
+    const float* __restrict__ w = W + 4 * c * HP;
+    axpy_row<HP>(a, x.x, w);
+    axpy_row<HP>(a, x.y, w + HP);
+    axpy_row<HP>(a, x.z, w + 2 * HP);
+    axpy_row<HP>(a, x.w, w + 3 * HP);
+  }
+}
+
+// store this thread's row of an HP-wide register vector into a tile
+template <int HP>
+__device__ __forceinline__ void store_row(float* __restrict__ tile, int row, const float (&v)[HP]) {
+#pragma unroll
+  for (int c = 0; c < HP / 4; ++c) st4(tile + (c * TR + row) * 4, make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+}
+
+// Tiles of one CTA.  xt/h1/h2/d1/d2 are HP features wide, dout/out are NW wide (NW = 4 or 12, >= nout).
+template <int HP, int NW>
 struct Tiles {
   float* xt; float* h1; float* h2; float* d1; float* d2; float* dout; float* out;
-  __host__ __device__ static constexpr int fwd_floats() { return (2 * HP + NOP) * RS; }           // xt, h1, out
-  __host__ __device__ static constexpr int bwd_floats() { return (5 * HP + 2 * NOP) * RS; }
+  __host__ __device__ static constexpr int fwd_floats() { return (2 * HP + NW) * TR; }           // xt, h1, out
+  __host__ __device__ static constexpr int bwd_floats() { return (5 * HP + 2 * NW) * TR; }
   __device__ void carve(float* base, bool bwd) {
-    xt = base; h1 = xt + HP * RS; out = h1 + HP * RS;
-    if (bwd) { h2 = out + NOP * RS; d1 = h2 + HP * RS; d2 = d1 + HP * RS; dout = d2 + HP * RS; }
+    xt = base; h1 = xt + HP * TR; out = h1 + HP * TR;
+    if (bwd) { h2 = out + NW * TR; d1 = h2 + HP * TR; d2 = d1 + HP * TR; dout = d2 + HP * TR; }
     else { h2 = d1 = d2 = dout = nullptr; }
   }
 };
 
-// Constant columns: zero everything, callers then keep cols < nin / < H up to date.  The ones columns are
-// (re)written by set_ones() whenever the net evaluated on the tile changes shape.
-template <int HP>
 __device__ __forceinline__ void zero_tiles(float* base, int nfloats) {
   for (int i = threadIdx.x; i < nfloats; i += blockDim.x) base[i] = 0.0f;
   __syncthreads();
 }
 
-// Forward of this thread's row.  Inputs: xt cols [0, nin) filled by the caller.  Outputs: t.out cols [0, nout).
-// KEEP_H2: also store the second hidden layer (needed by the backward sweep).
-template <int HP, bool KEEP_H2>
-__device__ __forceinline__ void mlp_fwd(const NetView<HP>& nv, const Tiles<HP>& t, int row) {
+// Forward of this thread's row.  Inputs: xt features [0, nin] written by the caller (feature nin = 1.0).
+// Outputs: t.out features [0, nout).  KEEP_H2: also store the second hidden layer (needed by the backward sweep).
+template <int HP, bool KEEP_H2, class TL>
+__device__ __forceinline__ void mlp_fwd(const NetView<HP>& nv, const TL& t, int row) {
   float a[HP];
-  float* xt = t.xt + row;
-  float* h1 = t.h1 + row;
-  xt[nv.nin * RS] = 1.0f;
-  gemv<HP>(a, nv.W1, nv.nin + 1, xt);
-#pragma unroll
-  for (int j = 0; j < HP; ++j)
-    if (j < nv.H) h1[j * RS] = act_fn(a[j], nv.act);
-  h1[nv.H * RS] = 1.0f;
-  gemv<HP>(a, nv.W2, nv.H + 1, h1);
+  gemv<HP>(a, nv.W1, (nv.nin + 4) >> 2, t.xt, row);
 #pragma unroll
   for (int j = 0; j < HP; ++j) a[j] = (j < nv.H) ? act_fn(a[j], nv.act) : ((j == nv.H) ? 1.0f : 0.0f);
-  if (KEEP_H2) {
-    float* h2 = t.h2 + row;
+  store_row<HP>(t.h1, row, a);
+  gemv<HP>(a, nv.W2, (nv.H + 4) >> 2, t.h1, row);
 #pragma unroll
-    for (int j = 0; j < HP; ++j) h2[j * RS] = a[j];
-  }
-  float* out = t.out + row;
+  for (int j = 0; j < HP; ++j) a[j] = (j < nv.H) ? act_fn(a[j], nv.act) : ((j == nv.H) ? 1.0f : 0.0f);
+  if (KEEP_H2) store_row<HP>(t.h2, row, a);
   for (int j = 0; j < nv.nout; ++j) {
     const float* __restrict__ w = nv.W3T + j * HP;
     float acc0 = 0.0f, acc1 = 0.0f;
@@ -156,39 +168,59 @@ __device__ __forceinline__ void mlp_fwd(const NetView<HP>& nv, const Tiles<HP>& 
       acc0 = fmaf(a[4 * k4], wv.x, acc0); acc1 = fmaf(a[4 * k4 + 1], wv.y, acc1);
       acc0 = fmaf(a[4 * k4 + 2], wv.z, acc0); acc1 = fmaf(a[4 * k4 + 3], wv.w, acc1);
     }
-    out[j * RS] = acc0 + acc1;
+    t.out[tix(j, row)] = acc0 + acc1;
   }
 }
 
-// Delta pass of this thread's row (after mlp_fwd<HP,true> on the same inputs).  Inputs: t.dout cols [0, nout).
-// Leaves d2/d1 in the tiles (for the weight gradient) and returns dx[i] = dL/dx_i in a[i], i < nin.
-template <int HP>
-__device__ __forceinline__ void mlp_delta(const NetView<HP>& nv, const Tiles<HP>& t, int row, float (&a)[HP]) {
-  float* d2 = t.d2 + row;
-  float* d1 = t.d1 + row;
-  const float* h1 = t.h1 + row;
-  const float* h2 = t.h2 + row;
-  gemv<HP>(a, nv.W3T, nv.nout, t.dout + row);
+// Delta pass of this thread's row (after mlp_fwd<HP,true> on the same inputs).  Inputs: t.dout features [0, nout)
+// (features up to the next multiple of 4 must be finite).  Leaves d2/d1 in the tiles (for the weight gradient) and
+// returns dx[i] = dL/dx_i in a[i], i < nin.
+template <int HP, class TL>
+__device__ __forceinline__ void mlp_delta(const NetView<HP>& nv, const TL& t, int row, float (&a)[HP]) {
+  // d2 = (W3 dout) .* act'(h2)   -- W3T rows beyond nout belong to the next weight block: mask the inputs instead
+  {
 #pragma unroll
-  for (int k = 0; k < HP; ++k) d2[k * RS] = (k < nv.H) ? a[k] * dact_fn(h2[k * RS], nv.act) : 0.0f;
-  gemv<HP>(a, nv.W2T, nv.H, d2);
+    for (int j = 0; j < HP; ++j) a[j] = 0.0f;
+    for (int j = 0; j < nv.nout; ++j) axpy_row<HP>(a, t.dout[tix(j, row)], nv.W3T + j * HP);
+  }
 #pragma unroll
-  for (int k = 0; k < HP; ++k) d1[k * RS] = (k < nv.H) ? a[k] * dact_fn(h1[k * RS], nv.act) : 0.0f;
-  gemv<HP>(a, nv.W1T, nv.H, d1);
+  for (int c = 0; c < HP / 4; ++c) {
+    const float4 h = ld4(t.h2 + (c * TR + row) * 4);
+    a[4 * c] = (4 * c < nv.H) ? a[4 * c] * dact_fn(h.x, nv.act) : 0.0f;
+    a[4 * c + 1] = (4 * c + 1 < nv.H) ? a[4 * c + 1] * dact_fn(h.y, nv.act) : 0.0f;
+    a[4 * c + 2] = (4 * c + 2 < nv.H) ? a[4 * c + 2] * dact_fn(h.z, nv.act) : 0.0f;
+    a[4 * c + 3] = (4 * c + 3 < nv.H) ? a[4 * c + 3] * dact_fn(h.w, nv.act) : 0.0f;
+  }
+  store_row<HP>(t.d2, row, a);
+  gemv<HP>(a, nv.W2T, (nv.H + 3) >> 2, t.d2, row);
+#pragma unroll
+  for (int c = 0; c < HP / 4; ++c) {
+    const float4 h = ld4(t.h1 + (c * TR + row) * 4);
+    a[4 * c] = (4 * c < nv.H) ? a[4 * c] * dact_fn(h.x, nv.act) : 0.0f;
+    a[4 * c + 1] = (4 * c + 1 < nv.H) ? a[4 * c + 1] * dact_fn(h.y, nv.act) : 0.0f;
+    a[4 * c + 2] = (4 * c + 2 < nv.H) ? a[4 * c + 2] * dact_fn(h.z, nv.act) : 0.0f;
+    a[4 * c + 3] = (4 * c + 3 < nv.H) ? a[4 * c + 3] * dact_fn(h.w, nv.act) : 0.0f;
+  }
+  store_row<HP>(t.d1, row, a);
+  gemv<HP>(a, nv.W1T, (nv.H + 3) >> 2, t.d1, row);
 }
 
 // ---- weight gradient ----------------------------------------------------------------------------------------
 // Thread u of the CTA owns block `blk = u % NB` and row chunk `u / NB` of the block list
 //   [ dW1: ceil((nin+1)/4) x HP/4 | dW2: HP/4 x HP/4 | dW3T: ceil(nout/4) x HP/4 ].
+// A block is (feature chunk ca of tile A) x (feature chunk cb of tile B): p[a][b] += sum_rows A[4ca+a][r] B[4cb+b][r];
+// one float4 per (chunk, row).  The 8 threads of a quarter-warp start at different rows (row rotation), so their
+// 128-bit loads fall into different banks although they walk the same row range.
 template <int HP>
 struct WGrad {
   float p[4][4];
-  int act_off, del_off;     // float offsets of the two 4-column groups from the tile base (xt)
-  int rq0, rq1;             // row-quad range of this thread's chunk
+  int a_off, b_off;         // float offsets of the two chunks from the tile base (xt), row 0
+  int r0, nr;               // first row and number of rows of this thread's chunk
   int type, k0, j0;         // 0: dW1[k][j]  1: dW2[k][j]  2: dW3T[j][k];  -1: idle
   int chunk, S;
 
-  __device__ void init(const NetView<HP>& nv, const Tiles<HP>& t) {
+  template <class TL>
+  __device__ void init(const NetView<HP>& nv, const TL& t) {
     constexpr int JB = HP / 4;
     const int nb1 = ((nv.nin + 1 + 3) / 4) * JB, nb2 = JB * JB, nb3 = ((nv.nout + 3) / 4) * JB;
     const int NB = nb1 + nb2 + nb3;
@@ -200,43 +232,45 @@ struct WGrad {
       for (int b = 0; b < 4; ++b) p[a][b] = 0.0f;
     const int u = threadIdx.x;
     chunk = u / NB;
-    type = -1; k0 = j0 = 0; act_off = del_off = 0; rq0 = rq1 = 0;
+    type = -1; k0 = j0 = 0; a_off = b_off = 0; r0 = nr = 0;
     if (chunk >= S) return;
     const int blk = u % NB;
-    rq0 = (chunk * (kThreads / 4)) / S;
-    rq1 = ((chunk + 1) * (kThreads / 4)) / S;
+    r0 = (chunk * TR) / S;
+    nr = ((chunk + 1) * TR) / S - r0;
+    int ta, tb;
     if (blk < nb1) {
       type = 0; k0 = 4 * (blk / JB); j0 = 4 * (blk % JB);
-      act_off = (int)(t.xt - t.xt) + k0 * RS; del_off = (int)(t.d1 - t.xt) + j0 * RS;
+      ta = (int)(t.xt - t.xt) + (k0 >> 2) * (4 * TR); tb = (int)(t.d1 - t.xt) + (j0 >> 2) * (4 * TR);
     } else if (blk < nb1 + nb2) {
       const int b2 = blk - nb1;
       type = 1; k0 = 4 * (b2 / JB); j0 = 4 * (b2 % JB);
-      act_off = (int)(t.h1 - t.xt) + k0 * RS; del_off = (int)(t.d2 - t.xt) + j0 * RS;
+      ta = (int)(t.h1 - t.xt) + (k0 >> 2) * (4 * TR); tb = (int)(t.d2 - t.xt) + (j0 >> 2) * (4 * TR);
     } else {
       const int b3 = blk - nb1 - nb2;
       type = 2; j0 = 4 * (b3 / JB); k0 = 4 * (b3 % JB);
-      act_off = (int)(t.dout - t.xt) + j0 * RS; del_off = (int)(t.h2 - t.xt) + k0 * RS;
+      ta = (int)(t.dout - t.xt) + (j0 >> 2) * (4 * TR); tb = (int)(t.h2 - t.xt) + (k0 >> 2) * (4 * TR);
     }
+    a_off = ta; b_off = tb;
   }
 
-  // p[a][b] += sum_rows A[(c+a)][r] * B[(c'+b)][r].  Call between two __syncthreads().
+  // Call between two __syncthreads().
   __device__ __forceinline__ void accumulate(const float* __restrict__ base) {
     if (type < 0) return;
-    const float* __restrict__ A = base + act_off;
-    const float* __restrict__ Bt = base + del_off;
-    for (int rq = rq0; rq < rq1; ++rq) {
-      float4 av[4], dv[4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) av[a] = ld4(A + a * RS + 4 * rq);
-#pragma unroll
-      for (int b = 0; b < 4; ++b) dv[b] = ld4(Bt + b * RS + 4 * rq);
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          p[a][b] = fmaf(av[a].x, dv[b].x, p[a][b]); p[a][b] = fmaf(av[a].y, dv[b].y, p[a][b]);
-          p[a][b] = fmaf(av[a].z, dv[b].z, p[a][b]); p[a][b] = fmaf(av[a].w, dv[b].w, p[a][b]);
-        }
+    const float* __restrict__ A = base + a_off + 4 * r0;
+    const float* __restrict__ Bt = base + b_off + 4 * r0;
+    const int rot = threadIdx.x & 7;
+    for (int i = 0; i < nr; ++i) {
+      int r = i + rot;
+      r = r >= nr ? r - nr : r;
+      const float4 av = ld4(A + 4 * r), bv = ld4(Bt + 4 * r);
+      p[0][0] = fmaf(av.x, bv.x, p[0][0]); p[0][1] = fmaf(av.x, bv.y, p[0][1]);
+      p[0][2] = fmaf(av.x, bv.z, p[0][2]); p[0][3] = fmaf(av.x, bv.w, p[0][3]);
+      p[1][0] = fmaf(av.y, bv.x, p[1][0]); p[1][1] = fmaf(av.y, bv.y, p[1][1]);
+      p[1][2] = fmaf(av.y, bv.z, p[1][2]); p[1][3] = fmaf(av.y, bv.w, p[1][3]);
+      p[2][0] = fmaf(av.z, bv.x, p[2][0]); p[2][1] = fmaf(av.z, bv.y, p[2][1]);
+      p[2][2] = fmaf(av.z, bv.z, p[2][2]); p[2][3] = fmaf(av.z, bv.w, p[2][3]);
+      p[3][0] = fmaf(av.w, bv.x, p[3][0]); p[3][1] = fmaf(av.w, bv.y, p[3][1]);
+      p[3][2] = fmaf(av.w, bv.z, p[3][2]); p[3][3] = fmaf(av.w, bv.w, p[3][3]);
     }
   }
 

@@ -174,6 +174,11 @@ FBSDEJ_API int fbsdej_solver_price(fbsdej_solver* s, int iStep, const float* X, 
 FBSDEJ_API int fbsdej_transpose_nbd_to_ndb(fbsdej_ctx* ctx, const float* src, float* dst, int N, int B, int d);
 FBSDEJ_API int fbsdej_transpose_ndb_to_nbd(fbsdej_ctx* ctx, const float* src, float* dst, int N, int B, int d);
 
+/* Self-test of the tcgen05 / TMEM plumbing: out0[128][32] = A[128][24] * B[24][32] (K-major operands),
+ * out1[m][n] = sum_r P[r][m] Q[r][n] for r < 128 (MN-major operands; rows m >= 24 and columns n >= 24 are unspecified).
+ * Device pointers; 3xTF32 split, fp32-grade results. */
+FBSDEJ_API int fbsdej_selftest_tc(fbsdej_ctx* ctx, const float* A, const float* B, const float* P, const float* Q, float* out0, float* out1);
+
 /* Number of kernels this library has launched on ctx since creation (bench.py's gpu_launches). */
 FBSDEJ_API long long fbsdej_ctx_launch_count(const fbsdej_ctx* ctx);
 
