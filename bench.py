@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--solver", default="SumLocalReg", choices=list(SOLVERS))
     ap.add_argument("--M", type=int, default=-1, help="compensator samples for --solver Global (default 256)")
     ap.add_argument("--cpu-paths", type=int, default=2048, help="paths of the bounded CPU sample")
+    ap.add_argument("--mma", default="ffma", choices=["ffma", "tcgen05"], help="layer arithmetic of the fused kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -51,7 +52,7 @@ def workload_config(a, B, world):
             % ("Global" + a.solver if a.solver.endswith("Reg") else a.solver + "FBSDE", "" if M == 0 else " M=%d" % M, B,
                "3" if world == 1 else "5"))
     return M, {"workload": name, "paths": B, "time_steps": MERTON["N"], "d": D, "hidden": H_WIDTH, "solver": a.solver,
-               "compensator_M": M, "parallelism": "dp%d" % world, "l2_policy": "inputs exceed L2 (path tensors %.0f MB per rank)"
+               "compensator_M": M, "mma": a.mma, "parallelism": "dp%d" % world, "l2_policy": "inputs exceed L2 (path tensors %.0f MB per rank)"
                % (2 * MERTON["N"] * D * (B // world) * 4 / 1e6)}
 
 
@@ -176,9 +177,11 @@ def run_native(a):
     if a.solver == "Global":
         solver = cp.SolverGlobalFBSDE(mm, cp.Net(1, D, layer, "tanh"), cp.Net(0, 1, layer, "tanh"), LR, M=M)
     elif a.solver == "SumLocalReg":
-        solver = cp.SolverGlobalSumLocalReg(mm, cp.Net(0, 1, layer, "tanh"), cp.Net(0, 1, layer, "tanh"), LR)
+        solver = cp.SolverGlobalSumLocalReg(mm, cp.Net(0, 1, layer, "tanh"), cp.Net(0, 1, layer, "tanh"), LR,
+                                            tensor_cores=a.mma == "tcgen05")
     else:
-        solver = cp.SolverGlobalMultiStepReg(mm, cp.Net(0, 1, layer, "tanh"), cp.Net(0, 1, layer, "tanh"), LR)
+        solver = cp.SolverGlobalMultiStepReg(mm, cp.Net(0, 1, layer, "tanh"), cp.Net(0, 1, layer, "tanh"), LR,
+                                             tensor_cores=a.mma == "tcgen05")
     s = solver.build()
     N = MERTON["N"]
 

@@ -42,7 +42,7 @@ class NetDesc(C.Structure):
 
 class SolverDesc(C.Structure):
     _fields_ = [("model", C.c_int), ("scheme", C.c_int), ("n_nets", C.c_int), ("nets", NetDesc * 2), ("n_y0", C.c_int),
-                ("M", C.c_int), ("stale_time", C.c_int), ("w_hat", C.c_float), ("w_ind", C.c_float), ("price_table", C.c_int)]
+                ("M", C.c_int), ("stale_time", C.c_int), ("w_hat", C.c_float), ("w_ind", C.c_float), ("price_table", C.c_int), ("mma_mode", C.c_int)]
 
 
 def _load():

@@ -229,6 +229,7 @@ void fill_pricing_args(const fbsdej_solver* s, const float* theta, int B, int B_
   a.scheme = s->sch; a.one_net = s->one_net; a.has_jump = s->has_jump; a.use_netA = s->use_netA;
   a.has_y = s->has_y; a.zoff = s->zoff; a.has_z = s->has_z; a.feat_mode = s->feat_mode;
   a.stale_time = s->desc.stale_time;
+  a.mma_mode = s->desc.mma_mode;
   a.inv_B = 1.0f / (float)B_global;
   if (s->model == FBSDEJ_MODEL_MERTON) {
     a.dt = (float)(s->mer.T / s->mer.N); a.r = (float)s->mer.r; a.K = (float)s->mer.K; a.x0 = (float)s->mer.x0;
@@ -636,6 +637,9 @@ int fbsdej_solver_create(fbsdej_ctx* ctx, const fbsdej_solver_desc* desc, const 
   s->P = off + ny0;
   s->M = s->has_jump ? desc->M : 0;
   FB_REQUIRE(!s->has_jump || desc->M >= 1, "this scheme needs M >= 1 compensator samples");
+  FB_REQUIRE(desc->mma_mode == 0 || desc->mma_mode == 1, "mma_mode must be 0 (FFMA) or 1 (tcgen05)");
+  FB_REQUIRE(desc->mma_mode == 0 || (reg && model != FBSDEJ_MODEL_MFG && HP == 24),
+             "mma_mode = 1 (tcgen05) is available for the SUMLOCALREG / MULTISTEPREG pricing solvers with H <= 23");
   cudaStream_t st = ctx->stream;
   if (model == FBSDEJ_MODEL_MERTON) {
     if (build_merton_tables(s.get())) return -2;

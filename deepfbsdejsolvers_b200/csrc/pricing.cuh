@@ -17,6 +17,7 @@ struct PricingArgs {
   int has_y, zoff, has_z;     // netA output map: out[0] = Y if has_y; Z[k] = out[zoff + k] if has_z
   int feat_mode;              // Merton two-net: 0 -> J (Global), 1 -> e^J
   int stale_time;             // SumLocal*: time feature of step k >= 1 is k-1
+  int mma_mode;               // 0 = fp32 FFMA layers, 1 = tcgen05 (compensator-free solvers only)
   float inv_B;                // 1 / GLOBAL batch (data-parallel ranks sum their partial means)
   float dt, r, K, x0, aLin, sig, drift_dt;
   NetRt netA, netB;

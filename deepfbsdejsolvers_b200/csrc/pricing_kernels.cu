@@ -12,6 +12,7 @@
 // Reference loss graphs: coupledPricing/SolversJumpDiff.py:22-44 (Global), :86-115/:162-190 (MultiStep1/2),
 // :236-269/:315-347 (SumLocal1/2), :391-415 (SumLocalReg), :461-481 (MultiStepReg); SolversPureJump.py same.
 #include "pricing.cuh"
+#include "tc_mlp.cuh"
 
 namespace fbsdej {
 
@@ -20,21 +21,29 @@ __device__ __forceinline__ float group_allsum(float v, int G, float* red) {
   return block_sum(v, red);   // G == kThreads: one path per CTA
 }
 
-template <class Model, int HP, bool JUMP>
+template <class Model, int HP, bool JUMP, bool TC>
 __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a) {
   constexpr int D = Model::D;
-  extern __shared__ __align__(16) float smem[];
+  static_assert(!(TC && JUMP), "the tcgen05 path covers the compensator-free solvers");
+  extern __shared__ __align__(1024) float smem[];
+  using TCF = TcForward<D + 2>;
   const bool two = JUMP && !a.one_net;
   float* swA = smem;
-  float* swB = swA + net_smem_floats(a.netA, HP, false);
+  float* swB = swA + (TC ? TCF::FLOATS : net_smem_floats(a.netA, HP, false));
   float* red = swB + (two ? net_smem_floats(a.netB, HP, false) : 0);
   float* tb = red + 8;
   using TL = Tiles<HP, JUMP ? NOP : 4>;
   TL t;
-  t.carve(tb, false);
-  const NetView<HP> nvA = load_net<HP>(swA, a.theta, a.netA, false);
-  const NetView<HP> nvJ = two ? load_net<HP>(swB, a.theta, a.netB, false) : nvA;
-  zero_tiles(tb, TL::fwd_floats());
+  NetView<HP> nvA, nvJ;
+  TCF tcf;
+  if constexpr (TC) {
+    tcf.init(smem, a.theta, a.netA);
+  } else {
+    t.carve(tb, false);
+    nvA = load_net<HP>(swA, a.theta, a.netA, false);
+    nvJ = two ? load_net<HP>(swB, a.theta, a.netB, false) : nvA;
+    zero_tiles(tb, TL::fwd_floats());
+  }
 
   const int row = threadIdx.x;
   const int G = JUMP ? a.G : 1, ppb = kThreads / G, g = threadIdx.x % G;
@@ -62,7 +71,16 @@ __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a)
         Jv[k] = a.J[((size_t)i * D + k) * sB + p];
       }
       float y_net = 0.0f, zdw = 0.0f;
-      if (a.use_netA) {
+      if constexpr (TC) {
+        float in[TCF::K1];
+#pragma unroll
+        for (int j = 0; j < TCF::K1; ++j) in[j] = 0.0f;
+        in[0] = tf;
+#pragma unroll
+        for (int k = 0; k < D; ++k) in[1 + k] = X[k];
+        in[1 + D] = 1.0f;
+        y_net = tcf.eval(in);
+      } else if (a.use_netA) {
         float in[HP];
 #pragma unroll
         for (int j = 0; j < HP; ++j) in[j] = 0.0f;
@@ -182,6 +200,7 @@ __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a)
       lsum += lpath;
     }
   }
+  if constexpr (TC) tcf.finish();
   const float tot = block_sum(lsum, red);
   if (threadIdx.x == 0) {
     a.lpart[blockIdx.x * 4] = tot;
@@ -189,25 +208,32 @@ __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a)
   }
 }
 
-template <class Model, int HP, bool JUMP>
+template <class Model, int HP, bool JUMP, bool TC>
 __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a) {
   constexpr int D = Model::D;
-  extern __shared__ __align__(16) float smem[];
+  static_assert(!(TC && JUMP), "the tcgen05 path covers the compensator-free solvers");
+  extern __shared__ __align__(1024) float smem[];
+  using TCB = TcBackward<D + 2>;
   const bool two = JUMP && !a.one_net;
   float* swA = smem;
-  float* swB = swA + net_smem_floats(a.netA, HP, true);
+  float* swB = swA + (TC ? TCB::FLOATS : net_smem_floats(a.netA, HP, true));
   float* red = swB + (two ? net_smem_floats(a.netB, HP, true) : 0);
-  float* tb = red + 8;
+  float* tb = TC ? smem : red + 8;                  // TC: the gradient staging vector reuses the (dead) operand tiles
   using TL = Tiles<HP, JUMP ? NOP : 4>;
   TL t;
-  t.carve(tb, true);
-  const NetView<HP> nvA = load_net<HP>(swA, a.theta, a.netA, true);
-  const NetView<HP> nvJ = two ? load_net<HP>(swB, a.theta, a.netB, true) : nvA;
-  zero_tiles(tb, TL::bwd_floats());
-  WGrad<HP> wgA;
-  wgA.init(nvA, t);
-  WGrad<HP> wgB;
-  if (JUMP) wgB.init(nvJ, t);
+  NetView<HP> nvA, nvJ;
+  WGrad<HP> wgA, wgB;
+  TCB tcb;
+  if constexpr (TC) {
+    tcb.init(smem, a.theta, a.netA);
+  } else {
+    t.carve(tb, true);
+    nvA = load_net<HP>(swA, a.theta, a.netA, true);
+    nvJ = two ? load_net<HP>(swB, a.theta, a.netB, true) : nvA;
+    zero_tiles(tb, TL::bwd_floats());
+    wgA.init(nvA, t);
+    if (JUMP) wgB.init(nvJ, t);
+  }
 
   const int row = threadIdx.x;
   const int G = JUMP ? a.G : 1, ppb = kThreads / G, g = threadIdx.x % G;
@@ -281,7 +307,18 @@ __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a
 #pragma unroll
         for (int k = 0; k < (JUMP ? D : 1); ++k) dXacc[k] = 0.0f;
       }
-      if (a.use_netA) {
+      if constexpr (TC) {
+        float in[TCB::K1], din[TCB::K1];
+#pragma unroll
+        for (int j = 0; j < TCB::K1; ++j) in[j] = 0.0f;
+        in[0] = tf;
+#pragma unroll
+        for (int k = 0; k < D; ++k) in[1 + k] = X[k];
+        in[1 + D] = 1.0f;
+        tcb.step(in, ybar * msk, din);
+#pragma unroll
+        for (int k = 0; k < D; ++k) Xbar[k] += din[1 + k];
+      } else if (a.use_netA) {
 #pragma unroll
         for (int j = 0; j < HP; ++j) dx[j] = 0.0f;
         dx[0] = tf;
@@ -355,10 +392,18 @@ __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a
   // ---- flush: registers -> smem gradient vector (external layout) -> this CTA's row of gpart ----------
   __syncthreads();
   float* sg = tb;
+  if constexpr (TC) {
+    if (tcb.pending_w) { tc::mbar_wait(tcb.bar_w, tcb.phase_w); tcb.phase_w ^= 1; tcb.pending_w = 0; }
+    __syncthreads();
+  }
   for (int e = threadIdx.x; e < a.P; e += blockDim.x) sg[e] = 0.0f;
   __syncthreads();
-  wgA.flush(nvA, sg, a.netA.ext_off);
-  if (two) wgB.flush(nvJ, sg, a.netB.ext_off);
+  if constexpr (TC) {
+    tcb.flush(sg, a.netA);
+  } else {
+    wgA.flush(nvA, sg, a.netA.ext_off);
+    if (two) wgB.flush(nvJ, sg, a.netB.ext_off);
+  }
   if (a.scheme == SCH_GLOBAL && threadIdx.x == 0) sg[a.y0_off] = y0tot;
   __syncthreads();
   float* grow = a.gpart + (size_t)blockIdx.x * a.P;
@@ -368,6 +413,11 @@ __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a
 // ---- launch glue ---------------------------------------------------------------------------------
 template <int HP>
 static size_t pricing_smem(const PricingArgs& a, bool backward) {
+  if (a.mma_mode == 1) {
+    const int k1 = (a.netA.nin + 1 + 3) & ~3;
+    const int fl = backward ? (4352 * 4 + k1 * 24 + 24 + 8) : (6144 + 1536 + k1 * 24 + 24 + 8);
+    return sizeof(float) * (size_t)(fl + 8);
+  }
   const bool two = a.has_jump && !a.one_net;
   const int w = net_smem_floats(a.netA, HP, backward) + (two ? net_smem_floats(a.netB, HP, backward) : 0);
   const int tl = a.has_jump ? (backward ? Tiles<HP, NOP>::bwd_floats() : Tiles<HP, NOP>::fwd_floats())
@@ -375,16 +425,16 @@ static size_t pricing_smem(const PricingArgs& a, bool backward) {
   return sizeof(float) * (size_t)(w + 8 + tl);
 }
 
-template <class Model, int HP, bool JUMP>
+template <class Model, int HP, bool JUMP, bool TC>
 static int launch_one(const PricingArgs& a, int grid, bool backward, cudaStream_t st) {
   const size_t smem = pricing_smem<HP>(a, backward);
   if (smem > 227 * 1024) { set_error("pricing kernels: shared-memory footprint exceeds 227 KB"); return -1; }
   if (!backward) {
-    auto kern = pricing_forward<Model, HP, JUMP>;
+    auto kern = pricing_forward<Model, HP, JUMP, TC>;
     FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kThreads, smem, st>>>(a);
   } else {
-    auto kern = pricing_backward<Model, HP, JUMP>;
+    auto kern = pricing_backward<Model, HP, JUMP, TC>;
     FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kThreads, smem, st>>>(a);
   }
@@ -393,7 +443,9 @@ static int launch_one(const PricingArgs& a, int grid, bool backward, cudaStream_
 }
 template <class Model, int HP>
 static int launch_pair(const PricingArgs& a, int grid, bool backward, cudaStream_t st) {
-  return a.has_jump ? launch_one<Model, HP, true>(a, grid, backward, st) : launch_one<Model, HP, false>(a, grid, backward, st);
+  if (a.has_jump) return launch_one<Model, HP, true, false>(a, grid, backward, st);
+  if (a.mma_mode == 1) return launch_one<Model, HP, false, true>(a, grid, backward, st);
+  return launch_one<Model, HP, false, false>(a, grid, backward, st);
 }
 
 // A(iStep, X) for n states (component planes X[d][n]); the drop-in MertonJumpModel.A / VGmodel.A.
@@ -422,24 +474,28 @@ int launch_price(int model, int D, const PricingArgs& a, int iStep, const float*
   return 0;
 }
 
-template <class Model, int HP, bool JUMP>
+template <class Model, int HP, bool JUMP, bool TC>
 static int occ_one(const PricingArgs& a, bool backward) {
   const size_t smem = pricing_smem<HP>(a, backward);
   int nb = 0;
   if (!backward) {
-    auto kern = pricing_forward<Model, HP, JUMP>;
+    auto kern = pricing_forward<Model, HP, JUMP, TC>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem) != cudaSuccess) return 1;
   } else {
-    auto kern = pricing_backward<Model, HP, JUMP>;
+    auto kern = pricing_backward<Model, HP, JUMP, TC>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem) != cudaSuccess) return 1;
   }
-  return nb < 1 ? 1 : nb;
+  nb = nb < 1 ? 1 : nb;
+  if (TC) nb = nb > (backward ? 4 : 16) ? (backward ? 4 : 16) : nb;    // TMEM: 512 columns / (128 | 32) per CTA
+  return nb;
 }
 template <class Model, int HP>
 static int occ_pair(const PricingArgs& a, bool backward) {
-  return a.has_jump ? occ_one<Model, HP, true>(a, backward) : occ_one<Model, HP, false>(a, backward);
+  if (a.has_jump) return occ_one<Model, HP, true, false>(a, backward);
+  if (a.mma_mode == 1) return occ_one<Model, HP, false, true>(a, backward);
+  return occ_one<Model, HP, false, false>(a, backward);
 }
 // resident CTAs per SM of the kernel that launch_pricing would run
 int pricing_blocks_per_sm(int model, int D, int HP, const PricingArgs& a, bool backward) {

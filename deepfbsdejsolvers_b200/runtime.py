@@ -100,11 +100,12 @@ class NativeSolver:
     def __init__(self, ctx: Context, model_kind: int, scheme: int, nets: Sequence[NetSpec], n_y0: int, M: int = 0,
                  merton: Optional[L.MertonParams] = None, vg: Optional[L.VGParams] = None,
                  mfg: Optional[L.MFGParams] = None, stale_time: bool = True, w_hat: float = 1.0, w_ind: float = 1.0,
-                 price_table: bool = False):
+                 price_table: bool = False, tensor_cores: bool = False):
         self.ctx, self.model_kind, self.scheme, self.nets, self.n_y0, self.M = ctx, model_kind, scheme, list(nets), n_y0, M
         d = L.SolverDesc()
         d.model, d.scheme, d.n_nets, d.n_y0, d.M = model_kind, scheme, len(nets), n_y0, M
         d.stale_time, d.w_hat, d.w_ind, d.price_table = int(stale_time), w_hat, w_ind, int(price_table)
+        d.mma_mode = int(tensor_cores)
         for k, n in enumerate(nets):
             d.nets[k] = L.NetDesc(n.nin, n.nout, n.H, n.L, L.ACT[n.activation])
         h = C.c_void_p()

@@ -79,10 +79,12 @@ class PricingSolverBase:
     M_DEFAULT = 5000       # compensator samples, hard-coded in the reference (SolversJumpDiff.py:34)
 
     def __init__(self, mathModel, netA: DenseNet, netB: Optional[DenseNet], lRate: float, M: Optional[int] = None,
-                 seed: int = 0, ctx: Optional[Context] = None, stale_time: bool = True):
+                 seed: int = 0, ctx: Optional[Context] = None, stale_time: bool = True, tensor_cores: Optional[bool] = None):
         self.mathModel, self.netA, self.netB, self.lRate = mathModel, netA, netB, lRate
         self.M = self.M_DEFAULT if M is None else int(M)
         self.seed, self.ctx, self.stale_time = seed, ctx, stale_time
+        # tcgen05 path (3xTF32 forward, bf16x3 adjoint): available for the compensator-free solvers; off unless asked for
+        self.tensor_cores = bool(tensor_cores) if tensor_cores is not None else False
         self.native: Optional[NativeSolver] = None
 
     # ------------------------------------------------------------------------------------------------------
@@ -109,7 +111,7 @@ class PricingSolverBase:
         n_y0 = 1 if self.SCHEME == L.GLOBAL else 0
         M = 0 if self.REG else self.M
         self.native = mm.make_solver(self.SCHEME, [n.spec() for n in nets], n_y0, M, ctx=self.ctx,
-                                     stale_time=self.stale_time)
+                                     stale_time=self.stale_time, tensor_cores=self.tensor_cores and self.REG)
         self.push_params()
         return self.native
 

@@ -118,7 +118,7 @@ def oracle_mfg(model, scheme, layout, theta, noise, B, dtype=torch.float32, w=(1
 
 
 # ---- native side --------------------------------------------------------------------------------------------
-def native_pricing(ctx, kind, params, scheme, layout, d=1, M=0, limit=30, stale_time=True, price_table=None):
+def native_pricing(ctx, kind, params, scheme, layout, d=1, M=0, limit=30, stale_time=True, price_table=None, tensor_cores=False):
     from deepfbsdejsolvers_b200 import NetSpec
     from deepfbsdejsolvers_b200.coupledPricing import MertonJumpModel, VGmodel, AbsCoupling
     if kind == "merton":
@@ -128,7 +128,7 @@ def native_pricing(ctx, kind, params, scheme, layout, d=1, M=0, limit=30, stale_
         mm = VGmodel(params["T"], params["N"], params["r"], params["theta"], params["kappa"], params["sigmaJ"], params["K"],
                      params["x0"], AbsCoupling(ALIN))
     nets = [NetSpec(n.nin, n.hidden[0], n.nout, n.activation) for n in layout.nets]
-    return mm.make_solver(PRICING_SCHEME_ID[scheme], nets, layout.n_y0, M, ctx=ctx, stale_time=stale_time)
+    return mm.make_solver(PRICING_SCHEME_ID[scheme], nets, layout.n_y0, M, ctx=ctx, stale_time=stale_time, tensor_cores=tensor_cores)
 
 
 def native_mfg(ctx, params, scheme, layout):

@@ -29,3 +29,53 @@ def test_tcgen05_selftest(ctx):
     print("tf32x3 K-major", e0, "bf16x3 K-major", e2, "bf16x3 MN-major", e3)
     assert e2 < 1e-4, f"bf16x3 K-major GEMM rel error {e2:.2e}"
     assert e3 < 1e-4, f"bf16x3 MN-major GEMM rel error {e3:.2e}"
+
+
+import helpers as H
+from oracle import MertonOracle, VGOracle
+
+
+def _check(s, B, l64, g64, g32, aux64, d):
+    out, tx, ty, _ = s.loss(B, traj=True)
+    assert abs(out[0] - l64) <= 2e-5 * abs(l64), (out[0], l64)
+    X = aux64["X"].transpose(0, 2, 1)
+    assert np.abs(tx - X).max() <= 2e-6 + 1e-5 * np.abs(X).max()
+    Y = aux64["Y"]
+    assert np.abs(ty[:Y.shape[0]] - Y).max() <= 4e-6 + 1e-5 * np.abs(Y).max()
+    g = s.grad(B)
+    assert abs(g[0] - l64) <= 2e-5 * abs(l64)
+    scale = np.abs(g64).max()
+    e_gpu, e_32 = np.abs(g[4:] - g64).max() / scale, np.abs(g32 - g64).max() / scale
+    print("loss rel", abs(out[0] - l64) / abs(l64), "grad rel-to-max", e_gpu, "(fp32 oracle", e_32, ")")
+    assert e_gpu <= 2e-4, f"gradient error {e_gpu:.3e}"
+
+
+@pytest.mark.parametrize("scheme", ["SumLocalReg", "MultiStepReg"])
+@pytest.mark.parametrize("d,B", [(1, 300), (10, 1000)])
+def test_tensor_core_path_matches_oracle(ctx, scheme, d, B):
+    """The tcgen05 kernels (3xTF32 forward, bf16x3 adjoint) against the float64 oracle on injected noise."""
+    p = dict(H.MERTON, N=12)
+    om = MertonOracle(aLin=H.ALIN, limit=30 if d == 1 else 100, d=d, **p)
+    layout = H.pricing_layout("merton", scheme, d)
+    theta = H.random_theta(layout, 21)
+    noise = H.merton_noise(om, B, 0, seed=22, with_jmc=False)
+    l32, g32, _ = H.oracle_pricing(om, scheme, layout, theta, noise, B)
+    l64, g64, aux64 = H.oracle_pricing(om, scheme, layout, theta, noise, B, dtype=torch.float64)
+    s = H.native_pricing(ctx, "merton", p, scheme, layout, d=d, limit=30 if d == 1 else 100, tensor_cores=True)
+    s.set_theta(theta)
+    s.set_noise(B, H.to_planes(noise["dW"]), H.to_planes(noise["J"]), None)
+    _check(s, B, l64, g64, g32, aux64, d)
+
+
+def test_tensor_core_path_vg(ctx):
+    B, scheme = 500, "SumLocalReg"
+    om = VGOracle(aLin=H.ALIN, **H.VG)
+    layout = H.pricing_layout("vg", scheme, 1)
+    theta = H.random_theta(layout, 23)
+    noise = H.vg_noise(om, B, 0, seed=24, with_jmc=False)
+    l32, g32, _ = H.oracle_pricing(om, scheme, layout, theta, noise, B)
+    l64, g64, aux64 = H.oracle_pricing(om, scheme, layout, theta, noise, B, dtype=torch.float64)
+    s = H.native_pricing(ctx, "vg", H.VG, scheme, layout, tensor_cores=True)
+    s.set_theta(theta)
+    s.set_noise(B, None, H.to_planes(noise["J"]), None)
+    _check(s, B, l64, g64, g32, aux64, 1)
