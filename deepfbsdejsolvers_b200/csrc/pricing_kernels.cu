@@ -478,17 +478,31 @@ template <class Model, int HP, bool JUMP, bool TC>
 static int occ_one(const PricingArgs& a, bool backward) {
   const size_t smem = pricing_smem<HP>(a, backward);
   int nb = 0;
+  cudaError_t e1, e2;
   if (!backward) {
     auto kern = pricing_forward<Model, HP, JUMP, TC>;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem) != cudaSuccess) return 1;
+    e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem);
   } else {
     auto kern = pricing_backward<Model, HP, JUMP, TC>;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem) != cudaSuccess) return 1;
+    e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem);
   }
-  nb = nb < 1 ? 1 : nb;
-  if (TC) nb = nb > (backward ? 4 : 16) ? (backward ? 4 : 16) : nb;    // TMEM: 512 columns / (128 | 32) per CTA
+  if (e1 != cudaSuccess || e2 != cudaSuccess || nb < 1) {
+    if (getenv("FBSDEJ_DEBUG"))
+      fprintf(stderr, "[fbsdej] occupancy query failed (%s / %s, nb=%d, smem=%zu)\n", cudaGetErrorString(e1), cudaGetErrorString(e2), nb, smem);
+    (void)cudaGetLastError();
+    nb = 1;
+  }
+  if (getenv("FBSDEJ_DEBUG")) fprintf(stderr, "[fbsdej] occupancy TC=%d bwd=%d nb=%d smem=%zu\n", (int)TC, (int)backward, nb, smem);
+  if (TC) {
+    // The occupancy calculator reports 1 CTA/SM for kernels that allocate TMEM (it cannot know the column count).
+    // Residency is bounded by registers (<= 168 -> 3, <= 128 -> 4), shared memory and TMEM (512 / 128 | 32 columns).
+    const int by_smem = (int)((227 * 1024) / (smem + 1024));
+    nb = backward ? 3 : 4;
+    nb = nb > by_smem ? by_smem : nb;
+    nb = nb < 1 ? 1 : nb;
+  }
   return nb;
 }
 template <class Model, int HP>

@@ -130,13 +130,20 @@ __device__ __forceinline__ void split_bf16(float x, uint32_t& hi, uint32_t& lo) 
   lo = (uint32_t)__bfloat16_as_ushort(l);
 }
 // Store 8 consecutive features of this thread's row as bf16 hi / lo chunks: tile layout [feature/8][row][8 bf16].
+// hi = the upper 16 bits of the fp32 value (truncation, exactly representable), lo = bf16_rn(x - hi): two values are
+// packed per PRMT / cvt.rn.bf16x2 instruction.
 __device__ __forceinline__ void store_bf16x8(uint4* __restrict__ hi_tile, uint4* __restrict__ lo_tile, int chunk, int row,
                                              const float* v) {
-  uint32_t h[8], l[8];
+  uint32_t h[4], l[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) split_bf16(v[i], h[i], l[i]);
-  hi_tile[chunk * 128 + row] = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
-  lo_tile[chunk * 128 + row] = make_uint4(l[0] | (l[1] << 16), l[2] | (l[3] << 16), l[4] | (l[5] << 16), l[6] | (l[7] << 16));
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t b0 = __float_as_uint(v[2 * i]), b1 = __float_as_uint(v[2 * i + 1]);
+    h[i] = __byte_perm(b0, b1, 0x7632);                                   // {hi16(b0), hi16(b1)}
+    const float r0 = v[2 * i] - __uint_as_float(b0 & 0xFFFF0000u), r1 = v[2 * i + 1] - __uint_as_float(b1 & 0xFFFF0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l[i]) : "f"(r1), "f"(r0));   // upper half <- first source
+  }
+  hi_tile[chunk * 128 + row] = make_uint4(h[0], h[1], h[2], h[3]);
+  lo_tile[chunk * 128 + row] = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 }  // namespace tc
