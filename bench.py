@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--solver", default="SumLocalReg", choices=list(SOLVERS))
     ap.add_argument("--M", type=int, default=-1, help="compensator samples for --solver Global (default 256)")
     ap.add_argument("--cpu-paths", type=int, default=2048, help="paths of the bounded CPU sample")
-    ap.add_argument("--mma", default="ffma", choices=["ffma", "tcgen05"], help="layer arithmetic of the fused kernels")
+    ap.add_argument("--mma", default="tcgen05", choices=["ffma", "tcgen05"], help="layer arithmetic of the fused kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()

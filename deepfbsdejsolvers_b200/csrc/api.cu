@@ -166,7 +166,7 @@ struct fbsdej_solver {
   const float *curA = nullptr, *curB = nullptr, *curC = nullptr;
   float* jmc_raw = nullptr; float* jmc = nullptr; int* jmc_nnz = nullptr; int* jmc_n0 = nullptr;
   // work buffers
-  float *trajX = nullptr, *aux_s = nullptr, *aux_dA = nullptr, *sch1 = nullptr, *fin = nullptr;
+  float *trajE = nullptr, *trajX = nullptr, *aux_s = nullptr, *aux_dA = nullptr, *sch1 = nullptr, *fin = nullptr;
   float *lpart = nullptr, *gpart = nullptr; int cap_grid = 0;
   float* out_dev = nullptr;       // [4 + P] scratch for train_steps
   uint32_t* step_ctr = nullptr;   // device step index inside train_steps
@@ -179,7 +179,7 @@ namespace {
 
 int free_path_buffers(fbsdej_solver* s) {
   dev_free(s->nA); dev_free(s->nB); dev_free(s->nC);
-  dev_free(s->trajX); dev_free(s->aux_s); dev_free(s->aux_dA); dev_free(s->sch1); dev_free(s->fin);
+  dev_free(s->trajE); dev_free(s->trajX); dev_free(s->aux_s); dev_free(s->aux_dA); dev_free(s->sch1); dev_free(s->fin);
   s->capB = 0;
   return 0;
 }
@@ -196,6 +196,7 @@ int ensure_capacity(fbsdej_solver* s, int B) {
   } else {
     if (s->model == FBSDEJ_MODEL_MERTON && dev_alloc(&s->nA, N * D * b)) return -2;
     if (dev_alloc(&s->nB, N * D * b)) return -2;
+    if (!s->has_jump && dev_alloc(&s->trajE, N * D * b)) return -2;
     if (dev_alloc(&s->trajX, (N + 1) * D * b) || dev_alloc(&s->aux_s, N * b) || dev_alloc(&s->aux_dA, N * b) ||
         dev_alloc(&s->sch1, N * b) || dev_alloc(&s->fin, b))
       return -2;
@@ -247,7 +248,7 @@ void fill_pricing_args(const fbsdej_solver* s, const float* theta, int B, int B_
   a.atab = s->atab; a.atab_meta = s->atab_meta; a.atab_off = s->atab_off; a.use_atab = s->use_atab;
   a.vg_coef = s->vg_coef; a.vg_scale = s->vg_scale; a.vg_nint = s->vg_nint;
   a.vg_k0 = s->vg_k0; a.vg_h = s->vg_h; a.vg_inv_h = 1.0f / s->vg_h;
-  a.trajX = s->trajX; a.aux_s = s->aux_s; a.aux_dA = s->aux_dA; a.sch1 = s->sch1; a.fin = s->fin;
+  a.trajE = s->trajE; a.trajX = s->trajX; a.aux_s = s->aux_s; a.aux_dA = s->aux_dA; a.sch1 = s->sch1; a.fin = s->fin;
   a.lpart = s->lpart; a.gpart = s->gpart;
 }
 

@@ -92,6 +92,8 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __host__ __device__ constexpr int round_up4(int x) { return (x + 3) & ~3; }
 
 // Standard normal CDF the way tfp does it: 0.5*erfc(-x/sqrt(2)).

@@ -48,6 +48,7 @@ struct PricingArgs {
   float vg_k0, vg_h, vg_inv_h;
   // per path-step stores for the adjoint sweep
   float* trajX;               // [N+1][D][B]
+  float* trajE;               // [N][D][B]  exp(drift dt + sig dW + J) (compensator-free solvers; saves the adjoint 2 loads + 1 exp)
   float* aux_s;               // [N][B]  aLin*dt*sign(Ysel - A_i)
   float* aux_dA;              // [N][B]  dA/dX (d=1) or G*dA/dG/d (d>1)
   float* sch1;                // [N][B]  MultiStep: e_k = F_k - g ; SumLocal: rho_i

@@ -70,6 +70,13 @@ __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a)
         dWv[k] = Model::kBrownian ? a.dW[((size_t)i * D + k) * sB + p] : 0.0f;
         Jv[k] = a.J[((size_t)i * D + k) * sB + p];
       }
+      if (i + 1 < a.N) {                             // next step's increments -> L2 while this step computes
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          if (Model::kBrownian) prefetch_l2(a.dW + ((size_t)(i + 1) * D + k) * sB + p);
+          prefetch_l2(a.J + ((size_t)(i + 1) * D + k) * sB + p);
+        }
+      }
       float y_net = 0.0f, zdw = 0.0f;
       if constexpr (TC) {
         float in[TCF::K1];
@@ -164,7 +171,11 @@ __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a)
         for (int k = 0; k < D; ++k) a.trajX[((size_t)i * D + k) * sB + p] = X[k];
       }
 #pragma unroll
-      for (int k = 0; k < D; ++k) X[k] = X[k] * expf(a.drift_dt + a.sig * dWv[k] + Jv[k]) + coup;
+      for (int k = 0; k < D; ++k) {
+        const float E = expf(a.drift_dt + a.sig * dWv[k] + Jv[k]);
+        if (!JUMP && writer) a.trajE[((size_t)i * D + k) * sB + p] = E;
+        X[k] = X[k] * E + coup;
+      }
     }
     // ---- terminal condition ---------------------------------------------------------------------
     const float gN = fmaxf(Model::basket(X) - a.K, 0.0f);
@@ -277,12 +288,31 @@ __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a
 #pragma unroll
         for (int k = 0; k < D; ++k) sumXbar += Xbar[k];
         cY = sumXbar * s_i;
+        float Ev[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {                 // all loads of the step first (independent, one latency)
+          X[k] = a.trajX[((size_t)i * D + k) * sB + p];
+          if (JUMP) {
+            Ev[k] = Model::kBrownian ? a.dW[((size_t)i * D + k) * sB + p] : 0.0f;
+            Jv[k] = a.J[((size_t)i * D + k) * sB + p];
+          } else {
+            Ev[k] = a.trajE[((size_t)i * D + k) * sB + p];
+            Jv[k] = 0.0f;
+          }
+        }
+        if (i > 0) {                                  // the next (earlier) step's state -> L2 while this step computes
+#pragma unroll
+          for (int k = 0; k < D; ++k) {
+            prefetch_l2(a.trajX + ((size_t)(i - 1) * D + k) * sB + p);
+            if (!JUMP) prefetch_l2(a.trajE + ((size_t)(i - 1) * D + k) * sB + p);
+          }
+          prefetch_l2(a.aux_s + (size_t)(i - 1) * sB + p);
+          prefetch_l2(a.aux_dA + (size_t)(i - 1) * sB + p);
+        }
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-          X[k] = a.trajX[((size_t)i * D + k) * sB + p];
-          const float dWk = Model::kBrownian ? a.dW[((size_t)i * D + k) * sB + p] : 0.0f;
-          Jv[k] = a.J[((size_t)i * D + k) * sB + p];
-          Xbar[k] = Xbar[k] * expf(a.drift_dt + a.sig * dWk + Jv[k]) - cY * Model::dA_k(dAb, X[k]);
+          const float E = JUMP ? expf(a.drift_dt + a.sig * Ev[k] + Jv[k]) : Ev[k];
+          Xbar[k] = Xbar[k] * E - cY * Model::dA_k(dAb, X[k]);
         }
       }
       // adjoints of the loss graph
