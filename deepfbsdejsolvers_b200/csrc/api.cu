@@ -167,6 +167,7 @@ struct fbsdej_solver {
   float* jmc_raw = nullptr; float* jmc = nullptr; int* jmc_nnz = nullptr; int* jmc_n0 = nullptr;
   // work buffers
   float *trajE = nullptr, *trajX = nullptr, *aux_s = nullptr, *aux_dA = nullptr, *sch1 = nullptr, *fin = nullptr;
+  float *rec = nullptr, *recN = nullptr;   // tcgen05 path: tile-major records (pricing.cuh: RecLayout)
   float *lpart = nullptr, *gpart = nullptr; int cap_grid = 0;
   float* out_dev = nullptr;       // [4 + P] scratch for train_steps
   uint32_t* step_ctr = nullptr;   // device step index inside train_steps
@@ -180,6 +181,7 @@ namespace {
 int free_path_buffers(fbsdej_solver* s) {
   dev_free(s->nA); dev_free(s->nB); dev_free(s->nC);
   dev_free(s->trajE); dev_free(s->trajX); dev_free(s->aux_s); dev_free(s->aux_dA); dev_free(s->sch1); dev_free(s->fin);
+  dev_free(s->rec); dev_free(s->recN);
   s->capB = 0;
   return 0;
 }
@@ -196,10 +198,15 @@ int ensure_capacity(fbsdej_solver* s, int B) {
   } else {
     if (s->model == FBSDEJ_MODEL_MERTON && dev_alloc(&s->nA, N * D * b)) return -2;
     if (dev_alloc(&s->nB, N * D * b)) return -2;
-    if (!s->has_jump && dev_alloc(&s->trajE, N * D * b)) return -2;
-    if (dev_alloc(&s->trajX, (N + 1) * D * b) || dev_alloc(&s->aux_s, N * b) || dev_alloc(&s->aux_dA, N * b) ||
-        dev_alloc(&s->sch1, N * b) || dev_alloc(&s->fin, b))
-      return -2;
+    if (s->desc.mma_mode == 1) {
+      const size_t nt = (b + kThreads - 1) / kThreads;
+      if (dev_alloc(&s->rec, nt * N * (2 * D + 3) * kThreads) || dev_alloc(&s->recN, nt * (D + 1) * kThreads)) return -2;
+    } else {
+      if (!s->has_jump && dev_alloc(&s->trajE, N * D * b)) return -2;
+      if (dev_alloc(&s->trajX, (N + 1) * D * b) || dev_alloc(&s->aux_s, N * b) || dev_alloc(&s->aux_dA, N * b) ||
+          dev_alloc(&s->sch1, N * b) || dev_alloc(&s->fin, b))
+        return -2;
+    }
   }
   s->capB = B;
   return 0;
@@ -249,6 +256,7 @@ void fill_pricing_args(const fbsdej_solver* s, const float* theta, int B, int B_
   a.vg_coef = s->vg_coef; a.vg_scale = s->vg_scale; a.vg_nint = s->vg_nint;
   a.vg_k0 = s->vg_k0; a.vg_h = s->vg_h; a.vg_inv_h = 1.0f / s->vg_h;
   a.trajE = s->trajE; a.trajX = s->trajX; a.aux_s = s->aux_s; a.aux_dA = s->aux_dA; a.sch1 = s->sch1; a.fin = s->fin;
+  a.rec = s->rec; a.recN = s->recN;
   a.lpart = s->lpart; a.gpart = s->gpart;
 }
 
@@ -735,6 +743,8 @@ int fbsdej_solver_loss(fbsdej_solver* s, const float* theta, int B, int B_global
       for (int i = 0; i <= s->N; ++i)
         FB_CUDA(cudaMemcpyAsync(trajX + (size_t)i * 2 * B, s->trajX + ((size_t)i * 5 + 3) * B, sizeof(float) * 2 * B,
                                 cudaMemcpyDeviceToDevice, s->ctx->stream));
+    } else if (s->desc.mma_mode == 1) {
+      if (launch_untile_traj(s->D, s->rec, s->recN, B, s->N, trajX, s->ctx->stream)) return -1;
     } else {
       FB_CUDA(cudaMemcpyAsync(trajX, s->trajX, sizeof(float) * (size_t)(s->N + 1) * s->D * B, cudaMemcpyDeviceToDevice,
                               s->ctx->stream));

@@ -53,10 +53,26 @@ struct PricingArgs {
   float* aux_dA;              // [N][B]  dA/dX (d=1) or G*dA/dG/d (d>1)
   float* sch1;                // [N][B]  MultiStep: e_k = F_k - g ; SumLocal: rho_i
   float* fin;                 // [B]     Global: Y_N - g ; MultiStep: sum_k e_k
+  // tcgen05 (compensator-free) path: tile-major per path-step records, one contiguous block per (tile, step):
+  //   rec  [ntiles][N][2D+3][128]   planes X[D], E[D], aLin*dt*sign, dA base, scheme residual  (RecLayout)
+  //   recN [ntiles][D+1][128]       planes X_N[D], fin
+  float* rec;
+  float* recN;
   float* trajY;               // optional [N+1][B]
   float* trajZ;               // optional [N][D][B]
   float* lpart;               // [grid][4]
   float* gpart;               // [grid][P]
+};
+
+// Record layout of the tcgen05 path: the adjoint sweep reads one (tile, step) block with immediate offsets from a
+// single base pointer (and one bulk L2 prefetch), the forward sweep writes it with 512-byte coalesced plane rows.
+template <int D>
+struct RecLayout {
+  static constexpr int P_X = 0, P_E = D, P_S = 2 * D, P_DA = 2 * D + 1, P_SCH = 2 * D + 2, NP = 2 * D + 3;
+  static constexpr int NPT = D + 1;
+  __host__ __device__ static size_t step_floats() { return (size_t)NP * TR; }
+  __host__ __device__ static size_t rec_floats(int ntiles, int N) { return (size_t)ntiles * N * NP * TR; }
+  __host__ __device__ static size_t recN_floats(int ntiles) { return (size_t)ntiles * NPT * TR; }
 };
 
 template <int D_>

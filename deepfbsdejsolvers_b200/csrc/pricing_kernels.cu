@@ -13,8 +13,12 @@
 // :236-269/:315-347 (SumLocal1/2), :391-415 (SumLocalReg), :461-481 (MultiStepReg); SolversPureJump.py same.
 #include "pricing.cuh"
 #include "tc_mlp.cuh"
+#include <type_traits>
 
 namespace fbsdej {
+
+int launch_reg_tc_backward(int model, int D, const PricingArgs& a, int grid, cudaStream_t st);   // reg_tc_kernels.cu
+size_t reg_tc_backward_smem();
 
 __device__ __forceinline__ float group_allsum(float v, int G, float* red) {
   if (G <= 32) return group_sum_shfl(v, G);
@@ -55,7 +59,9 @@ __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a)
     const int p0 = tile * ppb + threadIdx.x / G;
     const bool valid = p0 < a.B;
     const int p = valid ? p0 : a.B - 1;
-    const bool writer = valid && g == 0;
+    const bool writer = TC ? true : (valid && g == 0);   // TC: the padded rows of the last tile are written too (finite data)
+    using RL = RecLayout<D>;
+    float* const rec0 = TC ? a.rec + (size_t)tile * a.N * RL::NP * TR + row : nullptr;
     float X[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) X[k] = a.x0;
@@ -78,6 +84,7 @@ __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a)
         }
       }
       float y_net = 0.0f, zdw = 0.0f;
+      float* const rs = TC ? rec0 + (size_t)i * RL::NP * TR : nullptr;
       if constexpr (TC) {
         float in[TCF::K1];
 #pragma unroll
@@ -144,16 +151,18 @@ __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a)
         Y = Y - a.dt * (-a.r * Y) + zdw + gam - comp;        // SolversJumpDiff.py:41
         Ysel = Y;                                            // the UPDATED Y feeds oneStepFrom (:43)
       } else {
-        if (a.trajY && writer) a.trajY[(size_t)i * sB + p] = y_net;
+        if (a.trajY && valid && g == 0) a.trajY[(size_t)i * sB + p] = y_net;
         const float ai = rdt * y_net + zdw + gam - comp;     // "toAdd" = -dt f(Y) + Z dW + Gam - mean(comp)
         if (a.scheme == SCH_MULTISTEP) {
-          if (writer) a.sch1[(size_t)i * sB + p] = y_net - Cpre;   // u_i ; F_i - g = u_i + (sum_all toAdd - g)
+          if constexpr (TC) rs[RL::P_SCH * TR] = y_net - Cpre;
+          else if (writer) a.sch1[(size_t)i * sB + p] = y_net - Cpre;   // u_i ; F_i - g = u_i + (sum_all toAdd - g)
           Cpre += ai;
         } else {
           if (i > 0) {
             const float rho = y_net - yprev - aprev;
             lloc = fmaf(rho, rho, lloc);
-            if (writer) a.sch1[(size_t)(i - 1) * sB + p] = rho;
+            if constexpr (TC) (rs - RL::NP * TR)[RL::P_SCH * TR] = rho;
+            else if (writer) a.sch1[(size_t)(i - 1) * sB + p] = rho;
           }
           yprev = y_net; aprev = ai;
         }
@@ -164,8 +173,14 @@ __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a)
       Model::eval_A(a, i, X, Ai, dAb);
       const float diff = Ysel - Ai;
       const float coup = a.aLin * fabsf(diff) * a.dt;
-      if (writer) {
-        a.aux_s[(size_t)i * sB + p] = a.aLin * a.dt * (diff > 0.0f ? 1.0f : (diff < 0.0f ? -1.0f : 0.0f));
+      const float sgn = a.aLin * a.dt * (diff > 0.0f ? 1.0f : (diff < 0.0f ? -1.0f : 0.0f));
+      if constexpr (TC) {
+        rs[RL::P_S * TR] = sgn;
+        rs[RL::P_DA * TR] = dAb;
+#pragma unroll
+        for (int k = 0; k < D; ++k) rs[(RL::P_X + k) * TR] = X[k];
+      } else if (writer) {
+        a.aux_s[(size_t)i * sB + p] = sgn;
         a.aux_dA[(size_t)i * sB + p] = dAb;
 #pragma unroll
         for (int k = 0; k < D; ++k) a.trajX[((size_t)i * D + k) * sB + p] = X[k];
@@ -173,7 +188,8 @@ __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a)
 #pragma unroll
       for (int k = 0; k < D; ++k) {
         const float E = expf(a.drift_dt + a.sig * dWv[k] + Jv[k]);
-        if (!JUMP && writer) a.trajE[((size_t)i * D + k) * sB + p] = E;
+        if constexpr (TC) rs[(RL::P_E + k) * TR] = E;
+        else if (!JUMP && writer) a.trajE[((size_t)i * D + k) * sB + p] = E;
         X[k] = X[k] * E + coup;
       }
     }
@@ -190,25 +206,31 @@ __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a)
         const float Dv = Cpre - gN;
         float se = 0.0f, s2 = 0.0f;
         for (int k = 0; k < a.N; ++k) {
-          const float e = a.sch1[(size_t)k * sB + p] + Dv;
-          a.sch1[(size_t)k * sB + p] = e;
+          float* const q = TC ? rec0 + ((size_t)k * RL::NP + RL::P_SCH) * TR : a.sch1 + (size_t)k * sB + p;
+          const float e = *q + Dv;
+          *q = e;
           se += e;
           s2 = fmaf(e, e, s2);
         }
         lpath = s2 * (a.inv_B / (float)a.N);
-        a.fin[p] = se;
-        if (a.trajY) a.trajY[(size_t)a.N * sB + p] = gN;
+        if constexpr (TC) a.recN[((size_t)tile * RL::NPT + D) * TR + row] = se; else a.fin[p] = se;
+        if (a.trajY && valid) a.trajY[(size_t)a.N * sB + p] = gN;
       }
     } else {
       const float rho = gN - yprev - aprev;
       lloc = fmaf(rho, rho, lloc);
       lpath = lloc * a.inv_B;
-      if (writer) { a.sch1[(size_t)(a.N - 1) * sB + p] = rho; if (a.trajY) a.trajY[(size_t)a.N * sB + p] = gN; }
+      if constexpr (TC) rec0[((size_t)(a.N - 1) * RL::NP + RL::P_SCH) * TR] = rho;
+      else if (writer) a.sch1[(size_t)(a.N - 1) * sB + p] = rho;
+      if (writer && valid && a.trajY) a.trajY[(size_t)a.N * sB + p] = gN;
     }
     if (writer) {
 #pragma unroll
-      for (int k = 0; k < D; ++k) a.trajX[((size_t)a.N * D + k) * sB + p] = X[k];
-      lsum += lpath;
+      for (int k = 0; k < D; ++k) {
+        if constexpr (TC) a.recN[((size_t)tile * RL::NPT + k) * TR + row] = X[k];
+        else a.trajX[((size_t)a.N * D + k) * sB + p] = X[k];
+      }
+      if (valid) lsum += lpath;
     }
   }
   if constexpr (TC) tcf.finish();
@@ -444,9 +466,9 @@ __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a
 template <int HP>
 static size_t pricing_smem(const PricingArgs& a, bool backward) {
   if (a.mma_mode == 1) {
+    if (backward) return reg_tc_backward_smem();
     const int k1 = (a.netA.nin + 1 + 3) & ~3;
-    const int fl = backward ? (4352 * 4 + k1 * 24 + 24 + 8) : (6144 + 1536 + k1 * 24 + 24 + 8);
-    return sizeof(float) * (size_t)(fl + 8);
+    return sizeof(float) * (size_t)(6144 + 1536 + k1 * 24 + 24 + 8 + 8);
   }
   const bool two = a.has_jump && !a.one_net;
   const int w = net_smem_floats(a.netA, HP, backward) + (two ? net_smem_floats(a.netB, HP, backward) : 0);
@@ -463,7 +485,7 @@ static int launch_one(const PricingArgs& a, int grid, bool backward, cudaStream_
     auto kern = pricing_forward<Model, HP, JUMP, TC>;
     FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kThreads, smem, st>>>(a);
-  } else {
+  } else if constexpr (!TC) {
     auto kern = pricing_backward<Model, HP, JUMP, TC>;
     FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kThreads, smem, st>>>(a);
@@ -474,6 +496,7 @@ static int launch_one(const PricingArgs& a, int grid, bool backward, cudaStream_
 template <class Model, int HP>
 static int launch_pair(const PricingArgs& a, int grid, bool backward, cudaStream_t st) {
   if (a.has_jump) return launch_one<Model, HP, true, false>(a, grid, backward, st);
+  if (a.mma_mode == 1 && backward) return launch_reg_tc_backward(std::is_same<Model, VGModel>::value ? 1 : 0, Model::D, a, grid, st);
   if (a.mma_mode == 1) return launch_one<Model, HP, false, true>(a, grid, backward, st);
   return launch_one<Model, HP, false, false>(a, grid, backward, st);
 }
@@ -513,10 +536,12 @@ static int occ_one(const PricingArgs& a, bool backward) {
     auto kern = pricing_forward<Model, HP, JUMP, TC>;
     e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem);
-  } else {
+  } else if constexpr (!TC) {
     auto kern = pricing_backward<Model, HP, JUMP, TC>;
     e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem);
+  } else {
+    e1 = e2 = cudaSuccess; nb = 4;
   }
   if (e1 != cudaSuccess || e2 != cudaSuccess || nb < 1) {
     if (getenv("FBSDEJ_DEBUG"))
@@ -529,7 +554,7 @@ static int occ_one(const PricingArgs& a, bool backward) {
     // The occupancy calculator reports 1 CTA/SM for kernels that allocate TMEM (it cannot know the column count).
     // Residency is bounded by registers (<= 168 -> 3, <= 128 -> 4), shared memory and TMEM (512 / 128 | 32 columns).
     const int by_smem = (int)((227 * 1024) / (smem + 1024));
-    nb = backward ? 3 : 4;
+    nb = 4;
     nb = nb > by_smem ? by_smem : nb;
     nb = nb < 1 ? 1 : nb;
   }

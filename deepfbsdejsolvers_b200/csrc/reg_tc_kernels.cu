@@ -1,0 +1,413 @@
+// Adjoint sweep of the compensator-free (`Reg`) solvers with EVERY matrix product of the network on tcgen05:
+//
+//   SolverGlobalSumLocalReg  coupledPricing/SolversJumpDiff.py:391-415, SolversPureJump.py:361-384
+//   SolverGlobalMultiStepReg coupledPricing/SolversJumpDiff.py:461-481, SolversPureJump.py:430-450
+//   (their tf.GradientTape pass, SolversJumpDiff.py:421-427)
+//
+// One CTA = one tile of 128 paths, thread r = path r = TMEM lane r; the CTA walks the N time steps backwards.  Per step the
+// network u(t, X) (nin = 1 + D -> H -> H -> 1) is re-evaluated and differentiated with six GEMMs, all bf16x3
+// (x = hi + lo, D += A_hi B_hi + A_lo B_hi + A_hi B_lo, fp32 accumulation in TMEM, ~1e-5 relative):
+//
+//   L1   acc = X  W1          K = 16   (inputs incl. the constant-1 feature that carries b1)
+//   L2   acc = H1 W2          K = 32   (H1 incl. the constant-1 feature that carries b2)
+//   WG2  [dW2 | dW3] += [H1 | H2]^T D2          rows are K (MN-major operands); column 23 of D2 holds dL/dy
+//   BT   acc = D2 W2^T        K = 32
+//   DX   acc = D1 W1^T        K = 32   (input gradient, feeds the adjoint of X)
+//   WG1  dW1 += X^T D1
+//
+// Only the element-wise work stays on the CUDA cores (tanh, the deltas, the bf16 hi/lo split of the operand tiles and
+// the adjoint of the coupled Euler step).  The weight-gradient accumulators live in TMEM for the whole kernel (all
+// steps, all tiles of the CTA) and are read once at the end.  Each GEMM is issued by a different warp's lane 0, so
+// the descriptor arithmetic is spread over the four warps.
+//
+// Shared memory (54.9 KB -> 4 CTAs per SM; 128 TMEM columns each):
+//   operand tiles [feature / 8][128 rows][8 bf16] (16-byte chunks; one byte layout is K-major when features are K and
+//   MN-major when rows are K, tc.cuh), hi and lo copies:  X (16 features), H1, H2, D2 (24 features); D1 reuses H2's
+//   tile (its last reader, WG2, has completed when BT's commit is observed).
+//   B operands of the K-major GEMMs ([k / 8][n][8 bf16], 24 n-rows per chunk): W1, W2, W2^T, W1^T, hi and lo.
+//
+// Per path-step inputs come from the tile-major record written by the forward sweep (pricing.cuh: RecLayout): one base
+// pointer, immediate offsets, one bulk L2 prefetch per (tile, step).
+#include "pricing.cuh"
+#include "tc.cuh"
+
+namespace fbsdej {
+namespace rtc {
+
+constexpr int CH = 128;                       // uint4 per chunk (128 rows x 16 bytes)
+constexpr int XA_HI = 0, XA_LO = 2 * CH, H1_HI = 4 * CH, H2_HI = 7 * CH, H1_LO = 10 * CH, H2_LO = 13 * CH, D2_HI = 16 * CH,
+              D2_LO = 19 * CH, D1_HI = H2_HI, D1_LO = H2_LO, W_BASE = 22 * CH;
+constexpr int NB = 24;                        // n-rows stored per chunk of a B operand
+constexpr int W1B_HI = W_BASE, W1B_LO = W1B_HI + 2 * NB, W2B_HI = W1B_LO + 2 * NB, W2B_LO = W2B_HI + 4 * NB,
+              WTB_HI = W2B_LO + 4 * NB, WTB_LO = WTB_HI + 4 * NB, W1T_HI = WTB_LO + 4 * NB, W1T_LO = W1T_HI + 4 * 16,
+              U4_END = W1T_LO + 4 * 16;
+constexpr int OFF_W3 = U4_END * 4;            // float offsets after the uint4 region
+constexpr int OFF_BAR = OFF_W3 + 24;          // two mbarriers (8-byte aligned) + the TMEM base slot
+constexpr int SMEM_FLOATS = OFF_BAR + 8;
+static_assert((OFF_BAR % 2) == 0, "mbarrier alignment");
+constexpr uint32_t C_ACC = 0, C_W1 = 32, C_W2 = 64, NCOLS = 128;
+constexpr int COL_DOUT = 23;                  // spare column of D2 that carries dL/dy through WG2 (needs H <= 22)
+
+__device__ __forceinline__ void publish() {  // generic-proxy tile writes -> async proxy, then the CTA barrier
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+}
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// D[cols of ACC] = A (K-major, 128 rows x 16 KS) * B ([n][k], NBR n-rows per stored chunk), N = NN
+template <int KS, int NN, int NBR>
+__device__ __forceinline__ void gemm_k(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo) {
+  constexpr uint32_t id = tc::idesc_bf16(128, NN, false, false);
+#pragma unroll
+  for (int s = 0; s < KS; ++s) {
+    const uint64_t dah = tc::smem_desc(a_hi + s * 4096, 2048, 128), dal = tc::smem_desc(a_lo + s * 4096, 2048, 128);
+    const uint64_t dbh = tc::smem_desc(b_hi + s * (2 * NBR * 16), NBR * 16, 128), dbl = tc::smem_desc(b_lo + s * (2 * NBR * 16), NBR * 16, 128);
+    tc::mma_bf16(tmem_d, dah, dbh, id, s > 0 ? 1u : 0u);
+    tc::mma_bf16(tmem_d, dal, dbh, id, 1u);
+    tc::mma_bf16(tmem_d, dah, dbl, id, 1u);
+  }
+}
+// D[col0 ..] (+)= sum over the 128 rows of A^T B (both MN-major), N = 32
+__device__ __forceinline__ void gemm_rows(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t acc0) {
+  constexpr uint32_t id = tc::idesc_bf16(128, 32, true, true);
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {                     // 128 rows = 8 x 16
+    const uint64_t dah = tc::smem_desc(a_hi + s * 256, 128, 2048), dal = tc::smem_desc(a_lo + s * 256, 128, 2048);
+    const uint64_t dbh = tc::smem_desc(b_hi + s * 256, 128, 2048), dbl = tc::smem_desc(b_lo + s * 256, 128, 2048);
+    tc::mma_bf16(tmem_d, dah, dbh, id, (s > 0) ? 1u : acc0);
+    tc::mma_bf16(tmem_d, dal, dbh, id, 1u);
+    tc::mma_bf16(tmem_d, dah, dbl, id, 1u);
+  }
+}
+
+template <int ACT>
+__device__ __forceinline__ float actf(float x) { return ACT == ACT_TANH ? tanh_fast(x) : fmaxf(x, 0.0f); }
+template <int ACT>
+__device__ __forceinline__ float dactf(float h) { return ACT == ACT_TANH ? fmaf(-h, h, 1.0f) : (h > 0.0f ? 1.0f : 0.0f); }
+
+template <class Model, int ACT>
+__global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs a) {
+  constexpr int D = Model::D;
+  using RL = RecLayout<D>;
+  static_assert(D + 2 <= 16, "the X tile holds 16 features");
+  extern __shared__ __align__(1024) float smem[];
+  uint4* const u4 = reinterpret_cast<uint4*>(smem);
+  float* const w3s = smem + OFF_W3;
+  uint64_t* const bar_f = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* const bar_w = bar_f + 1;
+  uint32_t* const tslot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 4);
+  const int row = threadIdx.x, warp = row >> 5;
+  const bool issuer = (row & 31) == 0;
+  const int H = a.netA.H, nin = a.netA.nin;
+
+  // ---- one-time set-up: zero the tiles, stage the weights as bf16 hi/lo B operands, TMEM, barriers ---------------
+  for (int i = row; i < SMEM_FLOATS; i += kThreads) smem[i] = 0.0f;
+  __syncthreads();
+  {
+    const float* __restrict__ th = a.theta + a.netA.ext_off;
+    const int n1 = nin * H, n2 = n1 + H, n3 = n2 + H * H, n4 = n3 + H, n5 = n4 + H;
+    unsigned short* const w1h = reinterpret_cast<unsigned short*>(u4 + W1B_HI);
+    unsigned short* const w1l = reinterpret_cast<unsigned short*>(u4 + W1B_LO);
+    unsigned short* const w2h = reinterpret_cast<unsigned short*>(u4 + W2B_HI);
+    unsigned short* const w2l = reinterpret_cast<unsigned short*>(u4 + W2B_LO);
+    unsigned short* const wth = reinterpret_cast<unsigned short*>(u4 + WTB_HI);
+    unsigned short* const wtl = reinterpret_cast<unsigned short*>(u4 + WTB_LO);
+    unsigned short* const w1th = reinterpret_cast<unsigned short*>(u4 + W1T_HI);
+    unsigned short* const w1tl = reinterpret_cast<unsigned short*>(u4 + W1T_LO);
+    const float one_in = ACT == ACT_TANH ? 20.0f : 1.0f;   // act(one_in) == 1 exactly: the constant-1 unit of H1 / H2
+    for (int e = row; e < n5 + 2; e += kThreads) {
+      uint32_t hi, lo;
+      if (e < n2) {                                   // W1[i][j], b1[j] (i = nin): layer-1 B operand [n = j][k = i]
+        const int i = e < n1 ? e / H : nin, j = e < n1 ? e % H : e - n1;
+        tc::split_bf16(th[e], hi, lo);
+        w1h[((i >> 3) * NB + j) * 8 + (i & 7)] = (unsigned short)hi;
+        w1l[((i >> 3) * NB + j) * 8 + (i & 7)] = (unsigned short)lo;
+        if (i < nin) {                                // input-gradient B operand [n = i][k = j]
+          w1th[((j >> 3) * 16 + i) * 8 + (j & 7)] = (unsigned short)hi;
+          w1tl[((j >> 3) * 16 + i) * 8 + (j & 7)] = (unsigned short)lo;
+        }
+      } else if (e < n4) {                            // W2[k][j], b2[j] (k = H): layer-2 B operand [n = j][k]
+        const int k = e < n3 ? (e - n2) / H : H, j = e < n3 ? (e - n2) % H : e - n3;
+        tc::split_bf16(th[e], hi, lo);
+        w2h[((k >> 3) * NB + j) * 8 + (k & 7)] = (unsigned short)hi;
+        w2l[((k >> 3) * NB + j) * 8 + (k & 7)] = (unsigned short)lo;
+        if (k < H) {                                  // W2^T: B operand [n = k][k' = j]
+          wth[((j >> 3) * NB + k) * 8 + (j & 7)] = (unsigned short)hi;
+          wtl[((j >> 3) * NB + k) * 8 + (j & 7)] = (unsigned short)lo;
+        }
+      } else if (e < n5) {
+        w3s[e - n4] = th[e];                          // W3[k][0], k < H  (entries >= H stay 0: no delta for the constant unit)
+      } else if (e == n5) {                           // the constant-1 units: H1[H] = act(one_in * 1), H2[H] likewise
+        tc::split_bf16(one_in, hi, lo);
+        w1h[((nin >> 3) * NB + H) * 8 + (nin & 7)] = (unsigned short)hi;
+        w1l[((nin >> 3) * NB + H) * 8 + (nin & 7)] = (unsigned short)lo;
+      } else {
+        tc::split_bf16(one_in, hi, lo);
+        w2h[((H >> 3) * NB + H) * 8 + (H & 7)] = (unsigned short)hi;
+        w2l[((H >> 3) * NB + H) * 8 + (H & 7)] = (unsigned short)lo;
+      }
+    }
+  }
+  if (warp == 0) tc::tmem_alloc(tslot, NCOLS);
+  if (row == 0) { tc::mbar_init(bar_f, 1); tc::mbar_init(bar_w, 1); tc::fence_mbar_init(); }
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = *tslot;
+  const uint32_t lane_base = tmem + ((uint32_t)(row & ~31) << 16);
+  const uint32_t sbase = tc::smem_u32(u4);
+  auto sa = [&](int off_u4) { return sbase + (uint32_t)off_u4 * 16u; };
+  uint32_t phase_f = 0, phase_w = 0, pending_w = 0, started = 0;
+  auto wait_f = [&]() { tc::mbar_wait(bar_f, phase_f); phase_f ^= 1; tc::tc_fence_after(); };
+
+  const float invB = a.inv_B, invBN = a.inv_B / (float)a.N, rdt = a.r * a.dt;
+  const int ntiles = (a.B + TR - 1) / TR;
+  const uint32_t step_bytes = (uint32_t)(RL::NP * TR * sizeof(float));
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const float msk = (tile * TR + row < a.B) ? 1.0f : 0.0f;
+    const float* const rec0 = a.rec + (size_t)tile * a.N * RL::NP * TR + row;
+    const float* const recN = a.recN + (size_t)tile * RL::NPT * TR + row;
+    float Xbar[D];
+    float Esum = 0.0f, rb_next = 0.0f;                  // MultiStep: running sum of e_k;  SumLocal: 2 rho_i / B of the step above
+    {
+      float X[D];
+#pragma unroll
+      for (int k = 0; k < D; ++k) X[k] = recN[k * TR];
+      float gbar;
+      if (a.scheme == SCH_MULTISTEP) {
+        Esum = recN[D * TR];                            // sum_k e_k ; d loss / d g = -2/(NB) sum_k e_k
+        gbar = -2.0f * Esum * invBN;
+      } else {
+        rb_next = 2.0f * rec0[((size_t)(a.N - 1) * RL::NP + RL::P_SCH) * TR] * invB;
+        gbar = rb_next;
+      }
+      const float Gb = Model::basket(X);
+      const float ind = (Gb - a.K >= 0.0f) ? 1.0f : 0.0f;   // tf.maximum: gradient to the first argument on ties
+#pragma unroll
+      for (int k = 0; k < D; ++k) Xbar[k] = gbar * ind * ((D == 1) ? 1.0f : Gb / ((float)D * X[k]));
+    }
+    if (row == 0 && a.N >= 2) prefetch_l2_bulk(rec0 + (size_t)(a.N - 2) * RL::NP * TR, step_bytes);
+    for (int i = a.N - 1; i >= 0; --i) {
+      const float* const rs = rec0 + (size_t)i * RL::NP * TR;
+      // ---- loads of the step (one base pointer, immediate offsets) --------------------------------------------
+      float X[D], E[D];
+#pragma unroll
+      for (int k = 0; k < D; ++k) { X[k] = rs[(RL::P_X + k) * TR]; E[k] = rs[(RL::P_E + k) * TR]; }
+      const float s_i = rs[RL::P_S * TR], dAb = rs[RL::P_DA * TR];
+      float sch = 0.0f;
+      if (a.scheme == SCH_MULTISTEP) sch = rs[RL::P_SCH * TR];
+      else if (i > 0) sch = (rs - RL::NP * TR)[RL::P_SCH * TR];
+      if (row == 0 && i >= 2) prefetch_l2_bulk(rs - 2 * RL::NP * TR, step_bytes);
+      // ---- adjoint of the coupled Euler step X' = X E + aLin |y - A(i, X)| dt and of the loss graph -----------
+      float sumXbar = 0.0f;
+#pragma unroll
+      for (int k = 0; k < D; ++k) sumXbar += Xbar[k];
+      const float cY = sumXbar * s_i;
+      const float cA = cY * dAb;
+#pragma unroll
+      for (int k = 0; k < D; ++k) Xbar[k] = fmaf(Xbar[k], E[k], -((D == 1) ? cA : __fdividef(cA, X[k])));
+      float ybar;
+      if (a.scheme == SCH_MULTISTEP) {
+        const float abar = 2.0f * Esum * invBN;           // sum_{k<=i} Fbar_k
+        ybar = 2.0f * sch * invBN + rdt * abar + cY;
+        Esum -= sch;
+      } else {
+        const float rb = rb_next;
+        const float rbm = (i > 0) ? 2.0f * sch * invB : 0.0f;
+        ybar = rbm - rb - rdt * rb + cY;
+        rb_next = rbm;
+      }
+      const float dout = ybar * msk;
+      const float tf = (a.scheme == SCH_SUMLOCAL && a.stale_time) ? (float)(i == 0 ? 0 : i - 1) : (float)i;
+      // ---- X tile (inputs incl. the constant 1) -> L1 -------------------------------------------------------------
+      if (pending_w) { tc::mbar_wait(bar_w, phase_w); phase_w ^= 1; pending_w = 0; }   // WG1 of the step above read X
+      {
+        float xin[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) xin[k] = 0.0f;
+        xin[0] = tf;
+#pragma unroll
+        for (int k = 0; k < D; ++k) xin[1 + k] = X[k];
+        xin[1 + D] = 1.0f;
+        tc::store_bf16x8(u4 + XA_HI, u4 + XA_LO, 0, row, xin);
+        tc::store_bf16x8(u4 + XA_HI, u4 + XA_LO, 1, row, xin + 8);
+      }
+      publish();
+      if (warp == 0 && issuer) {
+        tc::tc_fence_after();
+        gemm_k<1, 32, NB>(tmem + C_ACC, sa(XA_HI), sa(XA_LO), sa(W1B_HI), sa(W1B_LO));
+        tc::mma_commit(bar_f);
+      }
+      wait_f();
+      // ---- h1 -> L2 ---------------------------------------------------------------------------------------------
+      float h1[24];
+#pragma unroll
+      for (int c8 = 0; c8 < 3; ++c8) {
+        float t8[8];
+        tc::tmem_ld8(lane_base + C_ACC + 8 * c8, t8);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) h1[8 * c8 + q] = actf<ACT>(t8[q]);
+        tc::store_bf16x8(u4 + H1_HI, u4 + H1_LO, c8, row, h1 + 8 * c8);
+      }
+      publish();
+      if (warp == 1 && issuer) {
+        tc::tc_fence_after();
+        gemm_k<2, 32, NB>(tmem + C_ACC, sa(H1_HI), sa(H1_LO), sa(W2B_HI), sa(W2B_LO));
+        tc::mma_commit(bar_f);
+      }
+      wait_f();
+      // ---- h2, delta 2 -> WG2, BT -------------------------------------------------------------------------------
+#pragma unroll
+      for (int c8 = 0; c8 < 3; ++c8) {
+        float t8[8], d2[8];
+        tc::tmem_ld8(lane_base + C_ACC + 8 * c8, t8);
+        tc::tmem_ld_wait();
+        const float4 wa = ld4(w3s + 8 * c8), wb = ld4(w3s + 8 * c8 + 4);
+        const float w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float h = actf<ACT>(t8[q]);
+          t8[q] = h;
+          d2[q] = dout * w8[q] * dactf<ACT>(h);
+        }
+        if (c8 == 2) d2[COL_DOUT - 16] = dout;
+        tc::store_bf16x8(u4 + H2_HI, u4 + H2_LO, c8, row, t8);
+        tc::store_bf16x8(u4 + D2_HI, u4 + D2_LO, c8, row, d2);
+      }
+      publish();
+      if (warp == 2 && issuer) {
+        tc::tc_fence_after();
+        gemm_rows(tmem + C_W2, sa(H1_HI), sa(H1_LO), sa(D2_HI), sa(D2_LO), started ? 1u : 0u);   // [dW2 | dW3]
+        gemm_k<2, 32, NB>(tmem + C_ACC, sa(D2_HI), sa(D2_LO), sa(WTB_HI), sa(WTB_LO));
+        tc::mma_commit(bar_f);
+      }
+      wait_f();
+      // ---- delta 1 -> DX, WG1 ---------------------------------------------------------------------------------
+#pragma unroll
+      for (int c8 = 0; c8 < 3; ++c8) {
+        float t8[8];
+        tc::tmem_ld8(lane_base + C_ACC + 8 * c8, t8);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t8[q] *= dactf<ACT>(h1[8 * c8 + q]);
+        tc::store_bf16x8(u4 + D1_HI, u4 + D1_LO, c8, row, t8);
+      }
+      publish();
+      if (warp == 3 && issuer) {
+        tc::tc_fence_after();
+        gemm_k<2, 16, 16>(tmem + C_ACC, sa(D1_HI), sa(D1_LO), sa(W1T_HI), sa(W1T_LO));
+        tc::mma_commit(bar_f);
+        gemm_rows(tmem + C_W1, sa(XA_HI), sa(XA_LO), sa(D1_HI), sa(D1_LO), started ? 1u : 0u);   // dW1
+        tc::mma_commit(bar_w);
+      }
+      started = 1;
+      pending_w = 1;
+      wait_f();
+      {
+        float t8[8];
+        tc::tmem_ld8(lane_base + C_ACC, t8);
+        float u8[8];
+        if (D > 7) tc::tmem_ld8(lane_base + C_ACC + 8, u8);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < D; ++k) Xbar[k] += (1 + k < 8) ? t8[(1 + k) & 7] : u8[(1 + k - 8) & 7];
+      }
+      tc::tc_fence_before();     // orders these TMEM reads before the next step's first MMA (via its publish barrier)
+    }
+  }
+  // ---- flush: TMEM weight gradients -> smem vector (external flat layout) -> this CTA's row of gpart ------------
+  if (pending_w) { tc::mbar_wait(bar_w, phase_w); phase_w ^= 1; pending_w = 0; }
+  tc::tc_fence_after();
+  __syncthreads();
+  float* const sg = smem;                              // the operand tiles are dead
+  for (int e = row; e < a.P; e += kThreads) sg[e] = 0.0f;
+  __syncthreads();
+  if (started && warp < 2) {
+    float* const g = sg + a.netA.ext_off;
+    const int o2 = nin * H + H, o3 = o2 + H * H + H;
+    float v[8];
+#pragma unroll
+    for (int c8 = 0; c8 < 3; ++c8) {
+      if (warp == 0) {
+        tc::tmem_ld8(lane_base + C_W1 + 8 * c8, v);
+        tc::tmem_ld_wait();
+        const int k = row;                             // lane = input feature (k = nin: b1)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int j = 8 * c8 + q;
+          if (k <= nin && j < H) g[k < nin ? k * H + j : nin * H + j] = v[q];
+        }
+      }
+      tc::tmem_ld8(lane_base + C_W2 + 8 * c8, v);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int j = 8 * c8 + q;
+        if (row <= H && j < H) g[row < H ? o2 + row * H + j : o2 + H * H + j] = v[q];       // lanes 0..H: dW2 rows, b2
+        if (j == COL_DOUT && row >= 24 && row - 24 <= H) g[o3 + (row - 24)] = v[q];         // lanes 24..24+H: dW3, b3
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  float* const grow = a.gpart + (size_t)blockIdx.x * a.P;
+  for (int e = row; e < a.P; e += kThreads) grow[e] = sg[e];
+  if (warp == 0) tc::tmem_dealloc(tmem, NCOLS);
+}
+
+// Tile-major record -> the plane layout of fbsdej_solver_loss' trajectory output: X [N+1][D][B].
+template <int D>
+__global__ void untile_traj_kernel(const float* __restrict__ rec, const float* __restrict__ recN, int B, int N, float* __restrict__ out) {
+  using RL = RecLayout<D>;
+  const size_t total = (size_t)(N + 1) * D * B;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int p = (int)(t % B), k = (int)((t / B) % D), i = (int)(t / ((size_t)B * D));
+    const int tile = p / TR, row = p % TR;
+    out[t] = i < N ? rec[(((size_t)tile * N + i) * RL::NP + RL::P_X + k) * TR + row] : recN[((size_t)tile * RL::NPT + k) * TR + row];
+  }
+}
+
+}  // namespace rtc
+
+size_t reg_tc_backward_smem() { return sizeof(float) * (size_t)rtc::SMEM_FLOATS; }
+
+template <class Model>
+static int launch_bwd(const PricingArgs& a, int grid, cudaStream_t st) {
+  const size_t smem = reg_tc_backward_smem();
+  if (a.netA.act == ACT_TANH) {
+    auto kern = rtc::reg_backward_tc<Model, ACT_TANH>;
+    FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kThreads, smem, st>>>(a);
+  } else {
+    auto kern = rtc::reg_backward_tc<Model, ACT_RELU>;
+    FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kThreads, smem, st>>>(a);
+  }
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_reg_tc_backward(int model, int D, const PricingArgs& a, int grid, cudaStream_t st) {
+  if (a.netA.H > 22 || a.netA.nout != 1) { set_error("tcgen05 adjoint: needs H <= 22 and a single network output"); return -1; }
+  if (model == 0 && D == 1) return launch_bwd<MertonModel<1>>(a, grid, st);
+  if (model == 0 && D == 10) return launch_bwd<MertonModel<10>>(a, grid, st);
+  if (model == 1 && D == 1) return launch_bwd<VGModel>(a, grid, st);
+  set_error("tcgen05 adjoint: unsupported (model, d)");
+  return -1;
+}
+
+int launch_untile_traj(int D, const float* rec, const float* recN, int B, int N, float* out, cudaStream_t st) {
+  const int grid = 148 * 4;
+  if (D == 1) rtc::untile_traj_kernel<1><<<grid, 256, 0, st>>>(rec, recN, B, N, out);
+  else if (D == 10) rtc::untile_traj_kernel<10><<<grid, 256, 0, st>>>(rec, recN, B, N, out);
+  else { set_error("untile: unsupported d"); return -1; }
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace fbsdej
