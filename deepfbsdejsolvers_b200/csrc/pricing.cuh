@@ -126,6 +126,55 @@ struct MertonModel {
     dAb = (D == 1) ? sD : sD * Ge * (1.0f / D);
   }
   __device__ static __forceinline__ float dA_k(float dAb, float Xk) { return (D == 1) ? dAb : dAb / Xk; }
+  // Same closed form for the tcgen05 kernels: the d logarithms of the geometric mean collapse into one per half of the
+  // product (d = 10: two MUFU.LG2 instead of ten library logf + one expf), table branch first.
+  __device__ static __forceinline__ void eval_A_fast(const PricingArgs& a, int i, const float (&X)[D], float& A, float& dAb) {
+    float k;
+    if (D == 1) {
+      k = __logf(X[0] / a.K);
+    } else {
+      constexpr int D2 = D / 2;
+      float p0 = 1.0f, p1 = 1.0f;
+#pragma unroll
+      for (int q = 0; q < D2; ++q) p0 *= X[q];
+#pragma unroll
+      for (int q = D2; q < D; ++q) p1 *= X[q];
+      k = (__logf(p0) + __logf(p1)) * (1.0f / D) + __logf(a.qdisc[i] / a.K);
+    }
+    const float Ge = (D == 1) ? X[0] : a.K * __expf(k);
+    float sD = 0.0f, sK = 0.0f;
+    bool done = false;
+    if (a.use_atab) {
+      const float4 m = __ldg(a.atab_meta + i);
+      const float u = (k - m.x) * m.y;
+      if (u >= 0.0f && u < m.w) {
+        const int j = (int)u;
+        const float t = u - (float)j;
+        const float4* __restrict__ nd = a.atab + a.atab_off[i] + j;
+        const float4 p0 = __ldg(nd), p1 = __ldg(nd + 1);
+        const float t2 = t * t, t3 = t2 * t;
+        const float h00 = 2.0f * t3 - 3.0f * t2 + 1.0f, h10 = (t3 - 2.0f * t2 + t) * m.z;
+        const float h01 = 3.0f * t2 - 2.0f * t3, h11 = (t3 - t2) * m.z;
+        sD = h00 * p0.x + h10 * p0.y + h01 * p1.x + h11 * p1.y;
+        sK = h00 * p0.z + h10 * p0.w + h01 * p1.z + h11 * p1.w;
+        done = true;
+      }
+    }
+    if (!done) {
+      const int2 rg = a.tab_range[i];
+      const float4* __restrict__ tA = a.tabA + (size_t)i * a.limit;
+      const float* __restrict__ tK = a.tabK + (size_t)i * a.limit;
+      for (int n = rg.x; n < rg.y; ++n) {
+        const float4 c = __ldg(tA + n);
+        const float d1 = fmaf(k, c.x, c.y);
+        const float d2 = d1 - c.z;
+        sD = fmaf(c.w, ncdf(d1), sD);
+        sK = fmaf(__ldg(tK + n), ncdf(d2), sK);
+      }
+    }
+    A = Ge * sD - sK;
+    dAb = (D == 1) ? sD : sD * Ge * (1.0f / D);
+  }
   // jump-row inputs (SolversJumpDiff.py:37-39, 99-100, 173-175) incl. the constant-1 feature
   template <int HP>
   __device__ static __forceinline__ void jump_input(const PricingArgs& a, float t, const float (&X)[D],
@@ -175,6 +224,9 @@ struct VGModel {
     dAb = 1.0f - 0.5f * sq / x * cs;
   }
   __device__ static __forceinline__ float dA_k(float dAb, float) { return dAb; }
+  __device__ static __forceinline__ void eval_A_fast(const PricingArgs& a, int i, const float (&X)[1], float& A, float& dAb) {
+    eval_A(a, i, X, A, dAb);
+  }
   // jump-row inputs (SolversPureJump.py:34-36, 95-96) incl. the constant-1 feature
   template <int HP>
   __device__ static __forceinline__ void jump_input(const PricingArgs& a, float t, const float (&X)[1],

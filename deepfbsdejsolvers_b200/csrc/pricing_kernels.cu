@@ -18,7 +18,9 @@
 namespace fbsdej {
 
 int launch_reg_tc_backward(int model, int D, const PricingArgs& a, int grid, cudaStream_t st);   // reg_tc_kernels.cu
+int launch_reg_tc_forward(int model, int D, const PricingArgs& a, int grid, cudaStream_t st);
 size_t reg_tc_backward_smem();
+size_t reg_tc_forward_smem();
 
 __device__ __forceinline__ float group_allsum(float v, int G, float* red) {
   if (G <= 32) return group_sum_shfl(v, G);
@@ -467,6 +469,7 @@ template <int HP>
 static size_t pricing_smem(const PricingArgs& a, bool backward) {
   if (a.mma_mode == 1) {
     if (backward) return reg_tc_backward_smem();
+    if (!getenv("FBSDEJ_OLD_TC_FWD")) return reg_tc_forward_smem();
     const int k1 = (a.netA.nin + 1 + 3) & ~3;
     return sizeof(float) * (size_t)(6144 + 1536 + k1 * 24 + 24 + 8 + 8);
   }
@@ -497,6 +500,7 @@ template <class Model, int HP>
 static int launch_pair(const PricingArgs& a, int grid, bool backward, cudaStream_t st) {
   if (a.has_jump) return launch_one<Model, HP, true, false>(a, grid, backward, st);
   if (a.mma_mode == 1 && backward) return launch_reg_tc_backward(std::is_same<Model, VGModel>::value ? 1 : 0, Model::D, a, grid, st);
+  if (a.mma_mode == 1 && !getenv("FBSDEJ_OLD_TC_FWD")) return launch_reg_tc_forward(std::is_same<Model, VGModel>::value ? 1 : 0, Model::D, a, grid, st);
   if (a.mma_mode == 1) return launch_one<Model, HP, false, true>(a, grid, backward, st);
   return launch_one<Model, HP, false, false>(a, grid, backward, st);
 }

@@ -34,10 +34,11 @@
 namespace fbsdej {
 namespace rtc {
 
+constexpr int NB = 24;                        // n-rows stored per chunk of a B operand
+namespace bwd {
 constexpr int CH = 128;                       // uint4 per chunk (128 rows x 16 bytes)
 constexpr int XA_HI = 0, XA_LO = 2 * CH, H1_HI = 4 * CH, H2_HI = 7 * CH, H1_LO = 10 * CH, H2_LO = 13 * CH, D2_HI = 16 * CH,
               D2_LO = 19 * CH, D1_HI = H2_HI, D1_LO = H2_LO, W_BASE = 22 * CH;
-constexpr int NB = 24;                        // n-rows stored per chunk of a B operand
 constexpr int W1B_HI = W_BASE, W1B_LO = W1B_HI + 2 * NB, W2B_HI = W1B_LO + 2 * NB, W2B_LO = W2B_HI + 4 * NB,
               WTB_HI = W2B_LO + 4 * NB, WTB_LO = WTB_HI + 4 * NB, W1T_HI = WTB_LO + 4 * NB, W1T_LO = W1T_HI + 4 * 16,
               U4_END = W1T_LO + 4 * 16;
@@ -47,6 +48,7 @@ constexpr int SMEM_FLOATS = OFF_BAR + 8;
 static_assert((OFF_BAR % 2) == 0, "mbarrier alignment");
 constexpr uint32_t C_ACC = 0, C_W1 = 32, C_W2 = 64, NCOLS = 128;
 constexpr int COL_DOUT = 23;                  // spare column of D2 that carries dL/dy through WG2 (needs H <= 22)
+}  // namespace bwd
 
 __device__ __forceinline__ void publish() {  // generic-proxy tile writes -> async proxy, then the CTA barrier
   tc::fence_async_smem();
@@ -92,6 +94,7 @@ template <class Model, int ACT>
 __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs a) {
   constexpr int D = Model::D;
   using RL = RecLayout<D>;
+  using namespace bwd;
   static_assert(D + 2 <= 16, "the X tile holds 16 features");
   extern __shared__ __align__(1024) float smem[];
   uint4* const u4 = reinterpret_cast<uint4*>(smem);
@@ -120,11 +123,13 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
     const float one_in = ACT == ACT_TANH ? 20.0f : 1.0f;   // act(one_in) == 1 exactly: the constant-1 unit of H1 / H2
     for (int e = row; e < n5 + 2; e += kThreads) {
       uint32_t hi, lo;
-      if (e < n2) {                                   // W1[i][j], b1[j] (i = nin): layer-1 B operand [n = j][k = i]
-        const int i = e < n1 ? e / H : nin, j = e < n1 ? e % H : e - n1;
+      if (e < n2) {                                   // W1[i][j]: layer-1 B operand [n = j][k = i]; the time row (i = 0) and
+        const int i = e < n1 ? e / H : nin, j = e < n1 ? e % H : e - n1;   // b1 (i = nin) live in the per-step effective bias
         tc::split_bf16(th[e], hi, lo);
-        w1h[((i >> 3) * NB + j) * 8 + (i & 7)] = (unsigned short)hi;
-        w1l[((i >> 3) * NB + j) * 8 + (i & 7)] = (unsigned short)lo;
+        if (i >= 1 && i < nin) {
+          w1h[((i >> 3) * NB + j) * 8 + (i & 7)] = (unsigned short)hi;
+          w1l[((i >> 3) * NB + j) * 8 + (i & 7)] = (unsigned short)lo;
+        }
         if (i < nin) {                                // input-gradient B operand [n = i][k = j]
           w1th[((j >> 3) * 16 + i) * 8 + (j & 7)] = (unsigned short)hi;
           w1tl[((j >> 3) * 16 + i) * 8 + (j & 7)] = (unsigned short)lo;
@@ -140,11 +145,8 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
         }
       } else if (e < n5) {
         w3s[e - n4] = th[e];                          // W3[k][0], k < H  (entries >= H stay 0: no delta for the constant unit)
-      } else if (e == n5) {                           // the constant-1 units: H1[H] = act(one_in * 1), H2[H] likewise
-        tc::split_bf16(one_in, hi, lo);
-        w1h[((nin >> 3) * NB + H) * 8 + (nin & 7)] = (unsigned short)hi;
-        w1l[((nin >> 3) * NB + H) * 8 + (nin & 7)] = (unsigned short)lo;
-      } else {
+      } else if (e == n5) {                           // (the constant-1 unit of H1 is written with the effective bias)
+      } else {                                        // the constant-1 unit of H2: act(one_in * 1) == 1
         tc::split_bf16(one_in, hi, lo);
         w2h[((H >> 3) * NB + H) * 8 + (H & 7)] = (unsigned short)hi;
         w2l[((H >> 3) * NB + H) * 8 + (H & 7)] = (unsigned short)lo;
@@ -159,6 +161,10 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
   tc::tc_fence_after();
   const uint32_t tmem = *tslot;
   const uint32_t lane_base = tmem + ((uint32_t)(row & ~31) << 16);
+  // thread j <= H owns the effective layer-1 bias of hidden unit j: c_j(t) = t W1[0][j] + b1[j] (fp32, then split)
+  float w0 = 0.0f, b1v = 0.0f;
+  if (row < H) { w0 = a.theta[a.netA.ext_off + row]; b1v = a.theta[a.netA.ext_off + nin * H + row]; }
+  const int bias_idx = ((nin >> 3) * NB + row) * 8 + (nin & 7);
   const uint32_t sbase = tc::smem_u32(u4);
   auto sa = [&](int off_u4) { return sbase + (uint32_t)off_u4 * 16u; };
   uint32_t phase_f = 0, phase_w = 0, pending_w = 0, started = 0;
@@ -235,6 +241,12 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
         xin[1 + D] = 1.0f;
         tc::store_bf16x8(u4 + XA_HI, u4 + XA_LO, 0, row, xin);
         tc::store_bf16x8(u4 + XA_HI, u4 + XA_LO, 1, row, xin + 8);
+        if (row <= H) {
+          uint32_t hi, lo;
+          tc::split_bf16(row < H ? fmaf(tf, w0, b1v) : (ACT == ACT_TANH ? 20.0f : 1.0f), hi, lo);
+          reinterpret_cast<unsigned short*>(u4 + W1B_HI)[bias_idx] = (unsigned short)hi;
+          reinterpret_cast<unsigned short*>(u4 + W1B_LO)[bias_idx] = (unsigned short)lo;
+        }
       }
       publish();
       if (warp == 0 && issuer) {
@@ -360,6 +372,250 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
   if (warp == 0) tc::tmem_dealloc(tmem, NCOLS);
 }
 
+// ---- forward sweep ---------------------------------------------------------------------------------------------
+// Loss graphs: SolverGlobalSumLocalReg.regressOptim (SolversJumpDiff.py:391-415), SolverGlobalMultiStepReg.regressOptim
+// (:461-481) and their VG twins; model step pricingModels.py:53-54 / :184-185.
+// Both layers run on tcgen05 with the 3xTF32 split (fp32-grade: the loss and the stored trajectories keep 1e-5 parity);
+// the time feature is folded into a per-step effective bias c_j = t W1[0][j] + b1[j] formed in fp32 (it is uniform over
+// the tile), so no operand of the split GEMMs is larger than O(1).  The closed-form coupling A(i, X), the exponentials of
+// the Euler step and the record stores are issued between an MMA's launch and the wait on its mbarrier.
+namespace fwd {
+constexpr int XA_HI = 0, XA_LO = 2048, H1_HI = 4096, H1_LO = 7168, W1B_HI = 10240, W1B_LO = W1B_HI + 4 * NB * 4,
+              W2B_HI = W1B_LO + 4 * NB * 4, W2B_LO = W2B_HI + 6 * NB * 4, OFF_W3 = W2B_LO + 6 * NB * 4, OFF_RED = OFF_W3 + 32,
+              OFF_BAR = OFF_RED + 8, SMEM_FLOATS = OFF_BAR + 8;
+static_assert((OFF_BAR % 2) == 0, "mbarrier alignment");
+
+// D[ACC] = A (K-major fp32 chunks [f/4][row][4], KS slices of 8) * B ([k/4][n][4], NB n-rows per chunk), N = 32, 3xTF32
+template <int KS>
+__device__ __forceinline__ void gemm_k_tf32(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo) {
+  constexpr uint32_t id = tc::idesc_tf32(128, 32, false, false);
+#pragma unroll
+  for (int s = 0; s < KS; ++s) {
+    const uint64_t dah = tc::smem_desc(a_hi + s * 4096, 2048, 128), dal = tc::smem_desc(a_lo + s * 4096, 2048, 128);
+    const uint64_t dbh = tc::smem_desc(b_hi + s * (2 * NB * 16), NB * 16, 128), dbl = tc::smem_desc(b_lo + s * (2 * NB * 16), NB * 16, 128);
+    tc::mma_tf32(tmem_d, dah, dbh, id, s > 0 ? 1u : 0u);
+    tc::mma_tf32(tmem_d, dal, dbh, id, 1u);
+    tc::mma_tf32(tmem_d, dah, dbl, id, 1u);
+  }
+}
+// store 4 consecutive features of this thread's row as TF32 hi / lo chunks
+__device__ __forceinline__ void store_tf32x4(float* __restrict__ hi_tile, float* __restrict__ lo_tile, int chunk, int row, const float* v) {
+  float h[4], l[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) tc::split_tf32(v[q], h[q], l[q]);
+  st4(hi_tile + (chunk * TR + row) * 4, make_float4(h[0], h[1], h[2], h[3]));
+  st4(lo_tile + (chunk * TR + row) * 4, make_float4(l[0], l[1], l[2], l[3]));
+}
+}  // namespace fwd
+
+template <class Model, int ACT>
+__global__ void __launch_bounds__(kThreads, 4) reg_forward_tc(const PricingArgs a) {
+  constexpr int D = Model::D;
+  using RL = RecLayout<D>;
+  using namespace fwd;
+  static_assert(D + 2 <= 16, "the X tile holds 16 features");
+  extern __shared__ __align__(1024) float smem[];
+  float* const w3s = smem + OFF_W3;
+  float* const red = smem + OFF_RED;
+  uint64_t* const bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint32_t* const tslot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 2);
+  const int row = threadIdx.x, warp = row >> 5;
+  const bool issuer = (row & 31) == 0;
+  const int H = a.netA.H, nin = a.netA.nin;
+  const float one_in = ACT == ACT_TANH ? 20.0f : 1.0f;
+
+  for (int i = row; i < SMEM_FLOATS; i += kThreads) smem[i] = 0.0f;
+  __syncthreads();
+  float w0 = 0.0f, b1v = 0.0f;                          // thread j <= H owns the effective bias of hidden unit j
+  {
+    const float* __restrict__ th = a.theta + a.netA.ext_off;
+    const int n1 = nin * H, n2 = n1 + H, n3 = n2 + H * H, n4 = n3 + H, n5 = n4 + H;
+    if (row < H) { w0 = th[row]; b1v = th[n1 + row]; }
+    for (int e = row; e <= n5 + 1; e += kThreads) {
+      float hi, lo;
+      if (e < n1) {                                     // W1[i][j], i >= 1 (the time row lives in the effective bias)
+        const int i = e / H, j = e % H;
+        if (i >= 1) {
+          tc::split_tf32(th[e], hi, lo);
+          smem[W1B_HI + ((i >> 2) * NB + j) * 4 + (i & 3)] = hi;
+          smem[W1B_LO + ((i >> 2) * NB + j) * 4 + (i & 3)] = lo;
+        }
+      } else if (e < n2) {
+      } else if (e < n4) {                              // W2[k][j], b2[j] (k = H)
+        const int k = e < n3 ? (e - n2) / H : H, j = e < n3 ? (e - n2) % H : e - n3;
+        tc::split_tf32(th[e], hi, lo);
+        smem[W2B_HI + ((k >> 2) * NB + j) * 4 + (k & 3)] = hi;
+        smem[W2B_LO + ((k >> 2) * NB + j) * 4 + (k & 3)] = lo;
+      } else if (e <= n5) {
+        w3s[e < n5 ? e - n4 : 24] = th[e];              // W3[k], k < H; b3 at index 24
+      } else {
+        tc::split_tf32(one_in, hi, lo);
+        smem[W2B_HI + ((H >> 2) * NB + H) * 4 + (H & 3)] = hi;
+        smem[W2B_LO + ((H >> 2) * NB + H) * 4 + (H & 3)] = lo;
+      }
+    }
+  }
+  if (warp == 0) tc::tmem_alloc(tslot, 32);
+  if (row == 0) { tc::mbar_init(bar, 1); tc::fence_mbar_init(); }
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = *tslot;
+  const uint32_t lane_base = tmem + ((uint32_t)(row & ~31) << 16);
+  const uint32_t sbase = tc::smem_u32(smem);
+  auto sa = [&](int off_f) { return sbase + (uint32_t)off_f * 4u; };
+  uint32_t phase = 0;
+  auto wait_mma = [&]() { tc::mbar_wait(bar, phase); phase ^= 1; tc::tc_fence_after(); };
+  const int bias_idx = ((nin >> 2) * NB + row) * 4 + (nin & 3);   // W1B[n = row][k = nin]
+
+  const size_t sB = (size_t)a.B;
+  const float rdt = a.r * a.dt;
+  float lsum = 0.0f;
+  const int ntiles = (a.B + TR - 1) / TR;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int p0 = tile * TR + row;
+    const bool valid = p0 < a.B;
+    const int p = valid ? p0 : a.B - 1;
+    float* const rec0 = a.rec + (size_t)tile * a.N * RL::NP * TR + row;
+    float X[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) X[k] = a.x0;
+    float Cpre = 0.0f;                               // MultiStep: sum_{j<i} toAdd_j
+    float yprev = 0.0f, aprev = 0.0f, lloc = 0.0f;   // SumLocal
+    for (int i = 0; i < a.N; ++i) {
+      const float tf = (a.scheme == SCH_SUMLOCAL && a.stale_time) ? (float)(i == 0 ? 0 : i - 1) : (float)i;
+      float* const rs = rec0 + (size_t)i * RL::NP * TR;
+      float E[D];
+      {
+        const float* __restrict__ pw = a.dW + (size_t)i * D * sB + p;
+        const float* __restrict__ pj = a.J + (size_t)i * D * sB + p;
+#pragma unroll
+        for (int k = 0; k < D; ++k) E[k] = a.drift_dt + (Model::kBrownian ? a.sig * pw[(size_t)k * sB] : 0.0f) + pj[(size_t)k * sB];
+      }
+      {
+        float xin[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) xin[k] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < D; ++k) xin[1 + k] = X[k];
+        xin[1 + D] = 1.0f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) store_tf32x4(smem + XA_HI, smem + XA_LO, c, row, xin + 4 * c);
+        if (row <= H) {
+          float hi, lo;
+          tc::split_tf32(row < H ? fmaf(tf, w0, b1v) : one_in, hi, lo);
+          smem[W1B_HI + bias_idx] = hi;
+          smem[W1B_LO + bias_idx] = lo;
+        }
+      }
+      publish();
+      if (warp == 0 && issuer) {
+        tc::tc_fence_after();
+        gemm_k_tf32<2>(tmem, sa(XA_HI), sa(XA_LO), sa(W1B_HI), sa(W1B_LO));
+        tc::mma_commit(bar);
+      }
+      // ---- independent of the network: closed-form coupling, exponentials, record stores -------------------------
+      float Ai, dAb;
+      Model::eval_A_fast(a, i, X, Ai, dAb);
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        rs[(RL::P_X + k) * TR] = X[k];
+        E[k] = __expf(E[k]);
+      }
+      rs[RL::P_DA * TR] = dAb;
+      wait_mma();
+      {
+        float h1[24];
+#pragma unroll
+        for (int c8 = 0; c8 < 3; ++c8) {
+          float t8[8];
+          tc::tmem_ld8(lane_base + 8 * c8, t8);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) h1[8 * c8 + q] = actf<ACT>(t8[q]);
+        }
+#pragma unroll
+        for (int c = 0; c < 6; ++c) store_tf32x4(smem + H1_HI, smem + H1_LO, c, row, h1 + 4 * c);
+      }
+      publish();
+      if (warp == 1 && issuer) {
+        tc::tc_fence_after();
+        gemm_k_tf32<3>(tmem, sa(H1_HI), sa(H1_LO), sa(W2B_HI), sa(W2B_LO));
+        tc::mma_commit(bar);
+      }
+#pragma unroll
+      for (int k = 0; k < D; ++k) rs[(RL::P_E + k) * TR] = E[k];
+      wait_mma();
+      float y_net = w3s[24];
+#pragma unroll
+      for (int c8 = 0; c8 < 3; ++c8) {
+        float t8[8];
+        tc::tmem_ld8(lane_base + 8 * c8, t8);
+        tc::tmem_ld_wait();
+        const float4 wa = ld4(w3s + 8 * c8), wb = ld4(w3s + 8 * c8 + 4);
+        const float w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) y_net = fmaf(actf<ACT>(t8[q]), w8[q], y_net);
+      }
+      tc::tc_fence_before();
+      // ---- loss-graph bookkeeping ---------------------------------------------------------------------------------
+      if (a.trajY && valid) a.trajY[(size_t)i * sB + p] = y_net;
+      const float ai = rdt * y_net;                        // "toAdd" = -dt f(Y)   (f = -r Y)
+      if (a.scheme == SCH_MULTISTEP) {
+        rs[RL::P_SCH * TR] = y_net - Cpre;                 // u_i ; F_i - g = u_i + (sum_all toAdd - g)
+        Cpre += ai;
+      } else {
+        if (i > 0) {
+          const float rho = y_net - yprev - aprev;
+          lloc = fmaf(rho, rho, lloc);
+          (rs - RL::NP * TR)[RL::P_SCH * TR] = rho;
+        }
+        yprev = y_net; aprev = ai;
+      }
+      // ---- coupled Euler step (pricingModels.py:53-54 / :184-185): the network's Y_i feeds the coupling ------------
+      const float diff = y_net - Ai;
+      const float coup = a.aLin * fabsf(diff) * a.dt;
+      rs[RL::P_S * TR] = a.aLin * a.dt * (diff > 0.0f ? 1.0f : (diff < 0.0f ? -1.0f : 0.0f));
+#pragma unroll
+      for (int k = 0; k < D; ++k) X[k] = fmaf(X[k], E[k], coup);
+    }
+    // ---- terminal condition -----------------------------------------------------------------------------------------
+    const float gN = fmaxf(Model::basket(X) - a.K, 0.0f);
+    float lpath;
+    if (a.scheme == SCH_MULTISTEP) {
+      // second sweep over the stored u_k: e_k = F_k - g(X_N), loss = mean_k mean_b e_k^2 (SolversJumpDiff.py:115)
+      const float Dv = Cpre - gN;
+      float se = 0.0f, s2 = 0.0f;
+      for (int k = 0; k < a.N; ++k) {
+        float* const q = rec0 + ((size_t)k * RL::NP + RL::P_SCH) * TR;
+        const float e = *q + Dv;
+        *q = e;
+        se += e;
+        s2 = fmaf(e, e, s2);
+      }
+      lpath = s2 * (a.inv_B / (float)a.N);
+      a.recN[((size_t)tile * RL::NPT + D) * TR + row] = se;
+    } else {
+      const float rho = gN - yprev - aprev;
+      lloc = fmaf(rho, rho, lloc);
+      lpath = lloc * a.inv_B;
+      rec0[((size_t)(a.N - 1) * RL::NP + RL::P_SCH) * TR] = rho;
+    }
+    if (a.trajY && valid) a.trajY[(size_t)a.N * sB + p] = gN;
+#pragma unroll
+    for (int k = 0; k < D; ++k) a.recN[((size_t)tile * RL::NPT + k) * TR + row] = X[k];
+    if (valid) lsum += lpath;
+  }
+  tc::tc_fence_before();
+  const float tot = block_sum(lsum, red);
+  if (row == 0) {
+    a.lpart[blockIdx.x * 4] = tot;
+    a.lpart[blockIdx.x * 4 + 1] = 0.0f; a.lpart[blockIdx.x * 4 + 2] = 0.0f; a.lpart[blockIdx.x * 4 + 3] = 0.0f;
+  }
+  if (warp == 0) tc::tmem_dealloc(tmem, 32);
+}
+
 // Tile-major record -> the plane layout of fbsdej_solver_loss' trajectory output: X [N+1][D][B].
 template <int D>
 __global__ void untile_traj_kernel(const float* __restrict__ rec, const float* __restrict__ recN, int B, int N, float* __restrict__ out) {
@@ -374,7 +630,33 @@ __global__ void untile_traj_kernel(const float* __restrict__ rec, const float* _
 
 }  // namespace rtc
 
-size_t reg_tc_backward_smem() { return sizeof(float) * (size_t)rtc::SMEM_FLOATS; }
+size_t reg_tc_backward_smem() { return sizeof(float) * (size_t)rtc::bwd::SMEM_FLOATS; }
+size_t reg_tc_forward_smem() { return sizeof(float) * (size_t)rtc::fwd::SMEM_FLOATS; }
+
+template <class Model>
+static int launch_fwd(const PricingArgs& a, int grid, cudaStream_t st) {
+  const size_t smem = reg_tc_forward_smem();
+  if (a.netA.act == ACT_TANH) {
+    auto kern = rtc::reg_forward_tc<Model, ACT_TANH>;
+    FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kThreads, smem, st>>>(a);
+  } else {
+    auto kern = rtc::reg_forward_tc<Model, ACT_RELU>;
+    FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kThreads, smem, st>>>(a);
+  }
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_reg_tc_forward(int model, int D, const PricingArgs& a, int grid, cudaStream_t st) {
+  if (a.netA.H > 22 || a.netA.nout != 1) { set_error("tcgen05 forward: needs H <= 22 and a single network output"); return -1; }
+  if (model == 0 && D == 1) return launch_fwd<MertonModel<1>>(a, grid, st);
+  if (model == 0 && D == 10) return launch_fwd<MertonModel<10>>(a, grid, st);
+  if (model == 1 && D == 1) return launch_fwd<VGModel>(a, grid, st);
+  set_error("tcgen05 forward: unsupported (model, d)");
+  return -1;
+}
 
 template <class Model>
 static int launch_bwd(const PricingArgs& a, int grid, cudaStream_t st) {
