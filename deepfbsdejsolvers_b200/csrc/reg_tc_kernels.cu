@@ -38,7 +38,7 @@ constexpr int NB = 24;                        // n-rows stored per chunk of a B 
 namespace bwd {
 constexpr int CH = 128;                       // uint4 per chunk (128 rows x 16 bytes)
 constexpr int XA_HI = 0, XA_LO = 2 * CH, H1_HI = 4 * CH, H2_HI = 7 * CH, H1_LO = 10 * CH, H2_LO = 13 * CH, D2_HI = 16 * CH,
-              D2_LO = 19 * CH, D1_HI = H2_HI, D1_LO = H2_LO, W_BASE = 22 * CH;
+              D2_LO = 19 * CH, D1_HI = H2_HI, D1_LO = H1_LO, W_BASE = 22 * CH;
 constexpr int W1B_HI = W_BASE, W1B_LO = W1B_HI + 2 * NB, W2B_HI = W1B_LO + 2 * NB, W2B_LO = W2B_HI + 4 * NB,
               WTB_HI = W2B_LO + 4 * NB, WTB_LO = WTB_HI + 4 * NB, W1T_HI = WTB_LO + 4 * NB, W1T_LO = W1T_HI + 4 * 16,
               U4_END = W1T_LO + 4 * 16;
@@ -46,7 +46,7 @@ constexpr int OFF_W3 = U4_END * 4;            // float offsets after the uint4 r
 constexpr int OFF_BAR = OFF_W3 + 24;          // two mbarriers (8-byte aligned) + the TMEM base slot
 constexpr int SMEM_FLOATS = OFF_BAR + 8;
 static_assert((OFF_BAR % 2) == 0, "mbarrier alignment");
-constexpr uint32_t C_ACC = 0, C_W1 = 32, C_W2 = 64, NCOLS = 128;
+constexpr uint32_t C_ACC = 0, C_W1 = 32, C_W2 = 80, NCOLS = 128;   // ACC 32 | WG1 48 | WG2 48 columns
 constexpr int COL_DOUT = 23;                  // spare column of D2 that carries dL/dy through WG2 (needs H <= 22)
 }  // namespace bwd
 
@@ -72,17 +72,15 @@ __device__ __forceinline__ void gemm_k(uint32_t tmem_d, uint32_t a_hi, uint32_t 
     tc::mma_bf16(tmem_d, dah, dbl, id, 1u);
   }
 }
-// D[col0 ..] (+)= sum over the 128 rows of A^T B (both MN-major), N = 32
-__device__ __forceinline__ void gemm_rows(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t acc0) {
-  constexpr uint32_t id = tc::idesc_bf16(128, 32, true, true);
+// Weight-gradient GEMM over the 128 rows of the tile (rows are K, both operands MN-major).  The hi and lo copies of A
+// are contiguous along M and those of B along N, so ONE MMA per 16-row slice forms all four hi/lo cross products in
+// separate accumulator blocks:  D[m][n], m in [A_hi features | A_lo features], n in [B_hi | B_lo] (24 columns each).
+// The three blocks that matter (hi.hi, hi.lo, lo.hi) are added when the accumulators are read at the end of the kernel.
+__device__ __forceinline__ void gemm_rows_stacked(uint32_t tmem_d, uint32_t a, uint32_t b, uint32_t acc0) {
+  constexpr uint32_t id = tc::idesc_bf16(128, 48, true, true);
 #pragma unroll
-  for (int s = 0; s < 8; ++s) {                     // 128 rows = 8 x 16
-    const uint64_t dah = tc::smem_desc(a_hi + s * 256, 128, 2048), dal = tc::smem_desc(a_lo + s * 256, 128, 2048);
-    const uint64_t dbh = tc::smem_desc(b_hi + s * 256, 128, 2048), dbl = tc::smem_desc(b_lo + s * 256, 128, 2048);
-    tc::mma_bf16(tmem_d, dah, dbh, id, (s > 0) ? 1u : acc0);
-    tc::mma_bf16(tmem_d, dal, dbh, id, 1u);
-    tc::mma_bf16(tmem_d, dah, dbl, id, 1u);
-  }
+  for (int s = 0; s < 8; ++s)                       // 128 rows = 8 x 16
+    tc::mma_bf16(tmem_d, tc::smem_desc(a + s * 256, 128, 2048), tc::smem_desc(b + s * 256, 128, 2048), id, (s > 0) ? 1u : acc0);
 }
 
 template <int ACT>
@@ -294,7 +292,7 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
       publish();
       if (warp == 2 && issuer) {
         tc::tc_fence_after();
-        gemm_rows(tmem + C_W2, sa(H1_HI), sa(H1_LO), sa(D2_HI), sa(D2_LO), started ? 1u : 0u);   // [dW2 | dW3]
+        gemm_rows_stacked(tmem + C_W2, sa(H1_HI), sa(D2_HI), started ? 1u : 0u);   // [H1 | H2 (hi) | H1 | H2 (lo)]^T [D2 hi | lo]
         gemm_k<2, 32, NB>(tmem + C_ACC, sa(D2_HI), sa(D2_LO), sa(WTB_HI), sa(WTB_LO));
         tc::mma_commit(bar_f);
       }
@@ -314,7 +312,7 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
         tc::tc_fence_after();
         gemm_k<2, 16, 16>(tmem + C_ACC, sa(D1_HI), sa(D1_LO), sa(W1T_HI), sa(W1T_LO));
         tc::mma_commit(bar_f);
-        gemm_rows(tmem + C_W1, sa(XA_HI), sa(XA_LO), sa(D1_HI), sa(D1_LO), started ? 1u : 0u);   // dW1
+        gemm_rows_stacked(tmem + C_W1, sa(XA_HI), sa(D1_HI), started ? 1u : 0u);   // [X hi | X lo]^T [D1 hi | lo]
         tc::mma_commit(bar_w);
       }
       started = 1;
@@ -336,33 +334,37 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
   if (pending_w) { tc::mbar_wait(bar_w, phase_w); phase_w ^= 1; pending_w = 0; }
   tc::tc_fence_after();
   __syncthreads();
-  float* const sg = smem;                              // the operand tiles are dead
+  float* const S = smem;                               // the operand tiles are dead: [128 lanes][49] scratch
+  float* const sg = smem + 8192;                       // gradient vector, external flat layout
+  constexpr int SW = 49;
   for (int e = row; e < a.P; e += kThreads) sg[e] = 0.0f;
-  __syncthreads();
-  if (started && warp < 2) {
-    float* const g = sg + a.netA.ext_off;
-    const int o2 = nin * H + H, o3 = o2 + H * H + H;
-    float v[8];
+  float* const g = sg + a.netA.ext_off;
+  const int o2 = nin * H + H, o3 = o2 + H * H + H;
+  for (int pass = 0; pass < 2; ++pass) {
+    __syncthreads();
+    if (started) {
 #pragma unroll
-    for (int c8 = 0; c8 < 3; ++c8) {
-      if (warp == 0) {
-        tc::tmem_ld8(lane_base + C_W1 + 8 * c8, v);
+      for (int c8 = 0; c8 < 6; ++c8) {
+        float v[8];
+        tc::tmem_ld8(lane_base + (pass == 0 ? C_W1 : C_W2) + 8 * c8, v);
         tc::tmem_ld_wait();
-        const int k = row;                             // lane = input feature (k = nin: b1)
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int j = 8 * c8 + q;
-          if (k <= nin && j < H) g[k < nin ? k * H + j : nin * H + j] = v[q];
-        }
+        for (int q = 0; q < 8; ++q) S[row * SW + 8 * c8 + q] = v[q];
       }
-      tc::tmem_ld8(lane_base + C_W2 + 8 * c8, v);
-      tc::tmem_ld_wait();
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int j = 8 * c8 + q;
-        if (row <= H && j < H) g[row < H ? o2 + row * H + j : o2 + H * H + j] = v[q];       // lanes 0..H: dW2 rows, b2
-        if (j == COL_DOUT && row >= 24 && row - 24 <= H) g[o3 + (row - 24)] = v[q];         // lanes 24..24+H: dW3, b3
+    }
+    __syncthreads();
+    if (started && pass == 0) {                        // lanes: X hi features 0..15, X lo features 16..31
+      for (int e = row; e < (nin + 1) * H; e += kThreads) {
+        const int i = e / H, j = e % H;                // i = nin: b1
+        g[e] = S[i * SW + j] + S[i * SW + 24 + j] + S[(16 + i) * SW + j];
       }
+    } else if (started) {                              // lanes: H1 hi 0..23, H2 hi 24..47, H1 lo 48..71, H2 lo 72..95
+      for (int e = row; e < (H + 1) * H; e += kThreads) {
+        const int k = e / H, j = e % H;                // k = H: b2
+        g[o2 + e] = S[k * SW + j] + S[k * SW + 24 + j] + S[(48 + k) * SW + j];
+      }
+      if (row <= H)                                    // dW3[k] (k = H: b3) rides in column COL_DOUT of D2
+        g[o3 + row] = S[(24 + row) * SW + COL_DOUT] + S[(24 + row) * SW + 24 + COL_DOUT] + S[(72 + row) * SW + COL_DOUT];
     }
   }
   tc::tc_fence_before();
