@@ -126,12 +126,14 @@ struct MertonModel {
     dAb = (D == 1) ? sD : sD * Ge * (1.0f / D);
   }
   __device__ static __forceinline__ float dA_k(float dAb, float Xk) { return (D == 1) ? dAb : dAb / Xk; }
-  // Same closed form for the tcgen05 kernels: the d logarithms of the geometric mean collapse into one per half of the
-  // product (d = 10: two MUFU.LG2 instead of ten library logf + one expf), table branch first.
-  __device__ static __forceinline__ void eval_A_fast(const PricingArgs& a, int i, const float (&X)[D], float& A, float& dAb) {
-    float k;
+  // Same closed form for the tcgen05 kernels, split in two so that the table loads are in flight while the caller does
+  // other work: the d logarithms of the geometric mean collapse into one per half of the product (d = 10: two MUFU.LG2
+  // instead of ten library logf + one expf).
+  struct AEval { float k, Ge, t; float4 m, p0, p1; bool tab; };
+  __device__ static __forceinline__ void eval_A_begin(const PricingArgs& a, int i, const float (&X)[D], AEval& e) {
     if (D == 1) {
-      k = __logf(X[0] / a.K);
+      e.k = __logf(X[0] / a.K);
+      e.Ge = X[0];
     } else {
       constexpr int D2 = D / 2;
       float p0 = 1.0f, p1 = 1.0f;
@@ -139,41 +141,44 @@ struct MertonModel {
       for (int q = 0; q < D2; ++q) p0 *= X[q];
 #pragma unroll
       for (int q = D2; q < D; ++q) p1 *= X[q];
-      k = (__logf(p0) + __logf(p1)) * (1.0f / D) + __logf(a.qdisc[i] / a.K);
+      e.k = (__logf(p0) + __logf(p1)) * (1.0f / D) + __logf(a.qdisc[i] / a.K);
+      e.Ge = a.K * __expf(e.k);
     }
-    const float Ge = (D == 1) ? X[0] : a.K * __expf(k);
-    float sD = 0.0f, sK = 0.0f;
-    bool done = false;
+    e.tab = false;
     if (a.use_atab) {
-      const float4 m = __ldg(a.atab_meta + i);
-      const float u = (k - m.x) * m.y;
-      if (u >= 0.0f && u < m.w) {
+      e.m = __ldg(a.atab_meta + i);
+      const float u = (e.k - e.m.x) * e.m.y;
+      if (u >= 0.0f && u < e.m.w) {
         const int j = (int)u;
-        const float t = u - (float)j;
+        e.t = u - (float)j;
         const float4* __restrict__ nd = a.atab + a.atab_off[i] + j;
-        const float4 p0 = __ldg(nd), p1 = __ldg(nd + 1);
-        const float t2 = t * t, t3 = t2 * t;
-        const float h00 = 2.0f * t3 - 3.0f * t2 + 1.0f, h10 = (t3 - 2.0f * t2 + t) * m.z;
-        const float h01 = 3.0f * t2 - 2.0f * t3, h11 = (t3 - t2) * m.z;
-        sD = h00 * p0.x + h10 * p0.y + h01 * p1.x + h11 * p1.y;
-        sK = h00 * p0.z + h10 * p0.w + h01 * p1.z + h11 * p1.w;
-        done = true;
+        e.p0 = __ldg(nd); e.p1 = __ldg(nd + 1);
+        e.tab = true;
       }
     }
-    if (!done) {
+  }
+  __device__ static __forceinline__ void eval_A_finish(const PricingArgs& a, int i, const AEval& e, float& A, float& dAb) {
+    float sD = 0.0f, sK = 0.0f;
+    if (e.tab) {
+      const float t = e.t, t2 = t * t, t3 = t2 * t;
+      const float h00 = 2.0f * t3 - 3.0f * t2 + 1.0f, h10 = (t3 - 2.0f * t2 + t) * e.m.z;
+      const float h01 = 3.0f * t2 - 2.0f * t3, h11 = (t3 - t2) * e.m.z;
+      sD = h00 * e.p0.x + h10 * e.p0.y + h01 * e.p1.x + h11 * e.p1.y;
+      sK = h00 * e.p0.z + h10 * e.p0.w + h01 * e.p1.z + h11 * e.p1.w;
+    } else {
       const int2 rg = a.tab_range[i];
       const float4* __restrict__ tA = a.tabA + (size_t)i * a.limit;
       const float* __restrict__ tK = a.tabK + (size_t)i * a.limit;
       for (int n = rg.x; n < rg.y; ++n) {
         const float4 c = __ldg(tA + n);
-        const float d1 = fmaf(k, c.x, c.y);
+        const float d1 = fmaf(e.k, c.x, c.y);
         const float d2 = d1 - c.z;
         sD = fmaf(c.w, ncdf(d1), sD);
         sK = fmaf(__ldg(tK + n), ncdf(d2), sK);
       }
     }
-    A = Ge * sD - sK;
-    dAb = (D == 1) ? sD : sD * Ge * (1.0f / D);
+    A = e.Ge * sD - sK;
+    dAb = (D == 1) ? sD : sD * e.Ge * (1.0f / D);
   }
   // jump-row inputs (SolversJumpDiff.py:37-39, 99-100, 173-175) incl. the constant-1 feature
   template <int HP>
@@ -224,8 +229,12 @@ struct VGModel {
     dAb = 1.0f - 0.5f * sq / x * cs;
   }
   __device__ static __forceinline__ float dA_k(float dAb, float) { return dAb; }
-  __device__ static __forceinline__ void eval_A_fast(const PricingArgs& a, int i, const float (&X)[1], float& A, float& dAb) {
-    eval_A(a, i, X, A, dAb);
+  struct AEval { float A, dAb; };
+  __device__ static __forceinline__ void eval_A_begin(const PricingArgs& a, int i, const float (&X)[1], AEval& e) {
+    eval_A(a, i, X, e.A, e.dAb);
+  }
+  __device__ static __forceinline__ void eval_A_finish(const PricingArgs&, int, const AEval& e, float& A, float& dAb) {
+    A = e.A; dAb = e.dAb;
   }
   // jump-row inputs (SolversPureJump.py:34-36, 95-96) incl. the constant-1 feature
   template <int HP>

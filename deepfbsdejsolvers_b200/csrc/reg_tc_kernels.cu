@@ -83,6 +83,11 @@ __device__ __forceinline__ void gemm_rows_stacked(uint32_t tmem_d, uint32_t a, u
     tc::mma_bf16(tmem_d, tc::smem_desc(a + s * 256, 128, 2048), tc::smem_desc(b + s * 256, 128, 2048), id, (s > 0) ? 1u : acc0);
 }
 
+__device__ __forceinline__ float rcp_fast(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 template <int ACT>
 __device__ __forceinline__ float actf(float x) { return ACT == ACT_TANH ? tanh_fast(x) : fmaxf(x, 0.0f); }
 template <int ACT>
@@ -195,17 +200,24 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
       for (int k = 0; k < D; ++k) Xbar[k] = gbar * ind * ((D == 1) ? 1.0f : Gb / ((float)D * X[k]));
     }
     if (row == 0 && a.N >= 2) prefetch_l2_bulk(rec0 + (size_t)(a.N - 2) * RL::NP * TR, step_bytes);
-    for (int i = a.N - 1; i >= 0; --i) {
+    // the record of step i is loaded one step ahead (during the last MMA wait of step i + 1): one base pointer,
+    // immediate offsets, DRAM / L2 latency off the critical chain
+    float Xn[D], En[D], s_n, dA_n, sch_n = 0.0f;
+    auto load_step = [&](int i) {
       const float* const rs = rec0 + (size_t)i * RL::NP * TR;
-      // ---- loads of the step (one base pointer, immediate offsets) --------------------------------------------
+#pragma unroll
+      for (int k = 0; k < D; ++k) { Xn[k] = rs[(RL::P_X + k) * TR]; En[k] = rs[(RL::P_E + k) * TR]; }
+      s_n = rs[RL::P_S * TR]; dA_n = rs[RL::P_DA * TR];
+      // MultiStep: e_i ; SumLocal: rho_{i-1} (the record of the step below; for i = 0 the value is unused)
+      sch_n = rs[(a.scheme == SCH_MULTISTEP || i == 0) ? RL::P_SCH * TR : (RL::P_SCH - RL::NP) * TR];
+      if (row == 0 && i >= 3) prefetch_l2_bulk(rs - 3 * RL::NP * TR, step_bytes);
+    };
+    load_step(a.N - 1);
+    for (int i = a.N - 1; i >= 0; --i) {
       float X[D], E[D];
 #pragma unroll
-      for (int k = 0; k < D; ++k) { X[k] = rs[(RL::P_X + k) * TR]; E[k] = rs[(RL::P_E + k) * TR]; }
-      const float s_i = rs[RL::P_S * TR], dAb = rs[RL::P_DA * TR];
-      float sch = 0.0f;
-      if (a.scheme == SCH_MULTISTEP) sch = rs[RL::P_SCH * TR];
-      else if (i > 0) sch = (rs - RL::NP * TR)[RL::P_SCH * TR];
-      if (row == 0 && i >= 2) prefetch_l2_bulk(rs - 2 * RL::NP * TR, step_bytes);
+      for (int k = 0; k < D; ++k) { X[k] = Xn[k]; E[k] = En[k]; }
+      const float s_i = s_n, dAb = dA_n, sch = sch_n;
       // ---- adjoint of the coupled Euler step X' = X E + aLin |y - A(i, X)| dt and of the loss graph -----------
       float sumXbar = 0.0f;
 #pragma unroll
@@ -213,7 +225,7 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
       const float cY = sumXbar * s_i;
       const float cA = cY * dAb;
 #pragma unroll
-      for (int k = 0; k < D; ++k) Xbar[k] = fmaf(Xbar[k], E[k], -((D == 1) ? cA : __fdividef(cA, X[k])));
+      for (int k = 0; k < D; ++k) Xbar[k] = fmaf(Xbar[k], E[k], -((D == 1) ? cA : cA * rcp_fast(X[k])));
       float ybar;
       if (a.scheme == SCH_MULTISTEP) {
         const float abar = 2.0f * Esum * invBN;           // sum_{k<=i} Fbar_k
@@ -317,6 +329,7 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
       }
       started = 1;
       pending_w = 1;
+      if (i > 0) load_step(i - 1);
       wait_f();
       {
         float t8[8];
@@ -485,16 +498,22 @@ __global__ void __launch_bounds__(kThreads, 4) reg_forward_tc(const PricingArgs 
     for (int k = 0; k < D; ++k) X[k] = a.x0;
     float Cpre = 0.0f;                               // MultiStep: sum_{j<i} toAdd_j
     float yprev = 0.0f, aprev = 0.0f, lloc = 0.0f;   // SumLocal
+    // the increments of step i are loaded one step ahead (right after the first MMA of step i - 1 is issued)
+    float Wn[Model::kBrownian ? D : 1], Jn[D];       // raw values: the combine happens where they are consumed
+    auto load_step = [&](int i) {
+      const float* __restrict__ pw = a.dW + (size_t)i * D * sB + p;
+      const float* __restrict__ pj = a.J + (size_t)i * D * sB + p;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        if (Model::kBrownian) Wn[Model::kBrownian ? k : 0] = pw[(size_t)k * sB];
+        Jn[k] = pj[(size_t)k * sB];
+      }
+    };
+    load_step(0);
     for (int i = 0; i < a.N; ++i) {
       const float tf = (a.scheme == SCH_SUMLOCAL && a.stale_time) ? (float)(i == 0 ? 0 : i - 1) : (float)i;
       float* const rs = rec0 + (size_t)i * RL::NP * TR;
       float E[D];
-      {
-        const float* __restrict__ pw = a.dW + (size_t)i * D * sB + p;
-        const float* __restrict__ pj = a.J + (size_t)i * D * sB + p;
-#pragma unroll
-        for (int k = 0; k < D; ++k) E[k] = a.drift_dt + (Model::kBrownian ? a.sig * pw[(size_t)k * sB] : 0.0f) + pj[(size_t)k * sB];
-      }
       {
         float xin[16];
 #pragma unroll
@@ -518,13 +537,15 @@ __global__ void __launch_bounds__(kThreads, 4) reg_forward_tc(const PricingArgs 
         tc::mma_commit(bar);
       }
       // ---- independent of the network: closed-form coupling, exponentials, record stores -------------------------
-      float Ai, dAb;
-      Model::eval_A_fast(a, i, X, Ai, dAb);
+      typename Model::AEval ae;
+      Model::eval_A_begin(a, i, X, ae);                  // table loads in flight ...
 #pragma unroll
-      for (int k = 0; k < D; ++k) {
+      for (int k = 0; k < D; ++k) {                      // ... while the exponentials and the stores issue
         rs[(RL::P_X + k) * TR] = X[k];
-        E[k] = __expf(E[k]);
+        E[k] = __expf(a.drift_dt + (Model::kBrownian ? a.sig * Wn[Model::kBrownian ? k : 0] : 0.0f) + Jn[k]);
       }
+      float Ai, dAb;
+      Model::eval_A_finish(a, i, ae, Ai, dAb);
       rs[RL::P_DA * TR] = dAb;
       wait_mma();
       {
@@ -548,6 +569,7 @@ __global__ void __launch_bounds__(kThreads, 4) reg_forward_tc(const PricingArgs 
       }
 #pragma unroll
       for (int k = 0; k < D; ++k) rs[(RL::P_E + k) * TR] = E[k];
+      if (i + 1 < a.N) load_step(i + 1);
       wait_mma();
       float y_net = w3s[24];
 #pragma unroll
