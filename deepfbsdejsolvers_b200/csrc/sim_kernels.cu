@@ -12,13 +12,31 @@
 namespace fbsdej {
 
 // Poisson(mean) by table inversion: thr[k] = floor(CDF(k) * 2^32); count = #{k : u >= thr[k]}.
-__device__ __forceinline__ float poisson_table(uint32_t u, const uint32_t* __restrict__ thr, int n) {
-  int c = 0;
-  for (int k = 0; k < n; ++k) {
+// One (path, asset pair, step) cell = ONE Philox call: words 0/1 -> the two Brownian normals (Box-Muller), words 2/3 ->
+// the two Poisson counts by table inversion.  A count of 1 (the only frequent non-zero case: P = lam dt e^{-lam dt})
+// takes its jump size from the SAME uniform: conditional on thr[0] <= u < thr[1], (u - thr[0]) / (thr[1] - thr[0]) is
+// uniform with ~28 bits, mapped through the inverse normal CDF.  Only counts >= 2 (P ~ (lam dt)^2 / 2) draw a second
+// Philox block (stream + 2), so warps almost never diverge into it.
+// Work split: blockIdx.y = step * KP + pair, blockIdx.x / threadIdx.x walk groups of 4 consecutive paths (128-bit
+// stores, no integer division anywhere).
+__device__ __forceinline__ float jump_size(uint32_t u, uint32_t t0, uint32_t t1, float inv_w1, const uint32_t* __restrict__ thr,
+                                           int n, float muJ, float sigJ, uint32_t gid, uint32_t c1, uint32_t iter, uint32_t stream,
+                                           uint32_t k0, uint32_t k1, int which) {
+  if (u < t0) return 0.0f;
+  if (u < t1) {                                          // exactly one jump: size ~ N(muJ, sigJ^2)
+    const float v = ((float)(u - t0) + 0.5f) * inv_w1;
+    return fmaf(sigJ, normcdfinvf(fminf(v, 0.99999994f)), muJ);
+  }
+  int c = 2;
+  for (int k = 2; k < n; ++k) {
     if (u < thr[k]) break;
     ++c;
   }
-  return (float)c;
+  const uint4 s = Philox::rand4(gid, c1, iter, stream + 2u, k0, k1);
+  float e0, e1;
+  box_muller(s.x, s.y, e0, e1);
+  const float dn = (float)c;
+  return dn * muJ + sigJ * sqrtf(dn) * (which ? e1 : e0);   // pricingModels.py:60 (sum of dn normals collapsed)
 }
 
 __global__ void __launch_bounds__(256) sim_merton_kernel(const SimMertonArgs a) {
@@ -27,47 +45,43 @@ __global__ void __launch_bounds__(256) sim_merton_kernel(const SimMertonArgs a) 
   __syncthreads();
   const int B4 = (a.B + 3) / 4, KP = (a.D + 1) / 2;
   const uint32_t iter = a.iter_ptr ? *a.iter_ptr : a.iteration;
-  const size_t total = (size_t)a.N * KP * B4;
-  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-    const int bq = (int)(t % B4);
-    const int kp = (int)((t / B4) % KP);
-    const int i = (int)(t / ((size_t)B4 * KP));
-    const int b0 = bq * 4, k0 = 2 * kp, k1 = 2 * kp + 1;
-    float w0[4], w1[4], j0[4], j1[4];
+  const uint32_t t0 = sthr[0], t1 = sthr[1];
+  const float inv_w1 = t1 > t0 ? 1.0f / (float)(t1 - t0) : 0.0f;
+  const bool vec = (a.B % 4 == 0);
+  for (int cell = blockIdx.y; cell < a.N * KP; cell += gridDim.y) {
+    const int i = cell / KP, kp = cell - i * KP;           // (uniform per block)
+    const int k0 = 2 * kp, k1 = 2 * kp + 1;
+    const uint32_t c1 = ((uint32_t)i << 8) | (uint32_t)kp;
+    const size_t o0 = ((size_t)i * a.D + k0) * a.B, o1 = ((size_t)i * a.D + k1) * a.B;
+    for (int bq = blockIdx.x * blockDim.x + threadIdx.x; bq < B4; bq += gridDim.x * blockDim.x) {
+      const int b0 = bq * 4;
+      float w0[4], w1[4], j0[4], j1[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const uint32_t gid = a.path_offset + (uint32_t)(b0 + q);
-      const uint32_t c1 = ((uint32_t)i << 8) | (uint32_t)kp;
-      const uint4 r = Philox::rand4(gid, c1, iter, a.stream, a.seed_lo, a.seed_hi);
-      float n0, n1;
-      box_muller(r.x, r.y, n0, n1);
-      w0[q] = a.sqdt * n0;
-      w1[q] = a.sqdt * n1;
-      const float dn0 = poisson_table(r.z, sthr, a.npois), dn1 = poisson_table(r.w, sthr, a.npois);
-      float e0 = 0.0f, e1 = 0.0f;
-      if (dn0 > 0.0f || dn1 > 0.0f) {   // jump sizes: drawn lazily, the counter makes skipping free
-        const uint4 s = Philox::rand4(gid, c1, iter, a.stream + 2u, a.seed_lo, a.seed_hi);
-        box_muller(s.x, s.y, e0, e1);
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t gid = a.path_offset + (uint32_t)(b0 + q);
+        const uint4 r = Philox::rand4(gid, c1, iter, a.stream, a.seed_lo, a.seed_hi);
+        float n0, n1;
+        box_muller(r.x, r.y, n0, n1);
+        w0[q] = a.sqdt * n0;
+        w1[q] = a.sqdt * n1;
+        j0[q] = jump_size(r.z, t0, t1, inv_w1, sthr, a.npois, a.muJ, a.sigJ, gid, c1, iter, a.stream, a.seed_lo, a.seed_hi, 0);
+        j1[q] = jump_size(r.w, t0, t1, inv_w1, sthr, a.npois, a.muJ, a.sigJ, gid, c1, iter, a.stream, a.seed_lo, a.seed_hi, 1);
       }
-      j0[q] = dn0 * a.muJ + a.sigJ * sqrtf(dn0) * e0;   // pricingModels.py:60
-      j1[q] = dn1 * a.muJ + a.sigJ * sqrtf(dn1) * e1;
-    }
-    const size_t o0 = ((size_t)i * a.D + k0) * a.B + b0, o1 = ((size_t)i * a.D + k1) * a.B + b0;
-    const bool vec = (a.B % 4 == 0);
-    if (vec) {
-      if (a.dW) st4(a.dW + o0, make_float4(w0[0], w0[1], w0[2], w0[3]));
-      st4(a.J + o0, make_float4(j0[0], j0[1], j0[2], j0[3]));
-      if (k1 < a.D) {
-        if (a.dW) st4(a.dW + o1, make_float4(w1[0], w1[1], w1[2], w1[3]));
-        st4(a.J + o1, make_float4(j1[0], j1[1], j1[2], j1[3]));
-      }
-    } else {
-      for (int q = 0; q < 4 && b0 + q < a.B; ++q) {
-        if (a.dW) a.dW[o0 + q] = w0[q];
-        a.J[o0 + q] = j0[q];
+      if (vec) {
+        if (a.dW) st4(a.dW + o0 + b0, make_float4(w0[0], w0[1], w0[2], w0[3]));
+        st4(a.J + o0 + b0, make_float4(j0[0], j0[1], j0[2], j0[3]));
         if (k1 < a.D) {
-          if (a.dW) a.dW[o1 + q] = w1[q];
-          a.J[o1 + q] = j1[q];
+          if (a.dW) st4(a.dW + o1 + b0, make_float4(w1[0], w1[1], w1[2], w1[3]));
+          st4(a.J + o1 + b0, make_float4(j1[0], j1[1], j1[2], j1[3]));
+        }
+      } else {
+        for (int q = 0; q < 4 && b0 + q < a.B; ++q) {
+          if (a.dW) a.dW[o0 + b0 + q] = w0[q];
+          a.J[o0 + b0 + q] = j0[q];
+          if (k1 < a.D) {
+            if (a.dW) a.dW[o1 + b0 + q] = w1[q];
+            a.J[o1 + b0 + q] = j1[q];
+          }
         }
       }
     }
@@ -204,8 +218,11 @@ static inline int sim_grid(size_t total, int threads) {
 }
 
 int launch_sim_merton(const SimMertonArgs& a, cudaStream_t st) {
-  const size_t total = (size_t)a.N * ((a.D + 1) / 2) * ((a.B + 3) / 4);
-  sim_merton_kernel<<<sim_grid(total, 256), 256, 0, st>>>(a);
+  const int cells = a.N * ((a.D + 1) / 2), B4 = (a.B + 3) / 4;
+  int gx = (B4 + 255) / 256;
+  gx = gx < 1 ? 1 : (gx > 148 * 8 ? 148 * 8 : gx);
+  const dim3 grid(gx, cells < 65535 ? cells : 65535);
+  sim_merton_kernel<<<grid, 256, 0, st>>>(a);
   FB_CUDA(cudaGetLastError());
   return 0;
 }
