@@ -194,6 +194,157 @@ __global__ void __launch_bounds__(128) tc_selftest_bf16_kernel(const float* __re
   if (warp == 0) tc::tmem_dealloc(tm, 64);
 }
 
+// A operand in TMEM (tcgen05.st by the row's own thread), B in shared memory; plus an M = 64 MN-major GEMM whose
+// accumulator is dumped from all 128 lanes so that the test can recover the row -> lane map.
+//   out_a[0] = A * B, 3xTF32, A from TMEM      out_a[1] = A * B, bf16x3, A from TMEM      out_m64 = all lanes x 32 columns
+__global__ void __launch_bounds__(128) tc_selftest_tmemA_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                                const float* __restrict__ P, const float* __restrict__ Q,
+                                                                float* __restrict__ out_a, float* __restrict__ out_m64) {
+  extern __shared__ __align__(1024) float sm[];
+  float* bt_hi = sm;                                   // tf32 B operand [6 chunks][32 n][4]
+  float* bt_lo = bt_hi + 768;
+  uint4* bb_hi = reinterpret_cast<uint4*>(bt_lo + 768);  // bf16 B operand [4 chunks][32 n] uint4
+  uint4* bb_lo = bb_hi + 128;
+  uint4* p_hi = bb_lo + 128;                           // bf16 tiles [4 chunks][128 rows] uint4
+  uint4* p_lo = p_hi + 512;
+  uint4* q_hi = p_lo + 512;
+  uint4* q_lo = q_hi + 512;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int r = threadIdx.x, warp = r >> 5;
+  for (int i = r; i < 2 * 768 + 4 * 256 + 4 * 4 * 512 + 8192; i += 128) sm[i] = 0.0f;
+  __syncthreads();
+  if (warp == 0) tc::tmem_alloc(&tmem_base, 128);
+  if (r == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
+  for (int e = r; e < 24 * 32; e += 128) {
+    const int k = e / 32, n = e % 32;
+    float hi, lo;
+    tc::split_tf32(B[k * 32 + n], hi, lo);
+    bt_hi[((k >> 2) * 32 + n) * 4 + (k & 3)] = hi;
+    bt_lo[((k >> 2) * 32 + n) * 4 + (k & 3)] = lo;
+    uint32_t h16, l16;
+    tc::split_bf16(B[k * 32 + n], h16, l16);
+    reinterpret_cast<unsigned short*>(bb_hi)[((k >> 3) * 32 + n) * 8 + (k & 7)] = (unsigned short)h16;
+    reinterpret_cast<unsigned short*>(bb_lo)[((k >> 3) * 32 + n) * 8 + (k & 7)] = (unsigned short)l16;
+  }
+  for (int c = 0; c < 4; ++c) {
+    float v[8];
+    for (int i = 0; i < 8; ++i) v[i] = (8 * c + i < 24) ? P[r * 24 + 8 * c + i] : 0.0f;
+    tc::store_bf16x8(p_hi, p_lo, c, r, v);
+    for (int i = 0; i < 8; ++i) v[i] = (8 * c + i < 24) ? Q[r * 24 + 8 * c + i] : 0.0f;
+    tc::store_bf16x8(q_hi, q_lo, c, r, v);
+  }
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tm = tmem_base, lane_base = tm + ((uint32_t)(32 * warp) << 16);
+  uint32_t phase = 0;
+  // ---- test 0: tf32, A hi at columns 32..55, A lo at 64..87 -----------------------------------------------------
+  for (int c8 = 0; c8 < 3; ++c8) {
+    uint32_t h[8], l[8];
+    for (int i = 0; i < 8; ++i) {
+      float hi, lo;
+      tc::split_tf32(A[r * 24 + 8 * c8 + i], hi, lo);
+      h[i] = __float_as_uint(hi); l[i] = __float_as_uint(lo);
+    }
+    tc::tmem_st8(lane_base + 32 + 8 * c8, h);
+    tc::tmem_st8(lane_base + 64 + 8 * c8, l);
+  }
+  tc::tmem_st_wait();
+  tc::tc_fence_before();
+  __syncthreads();
+  if (r == 0) {
+    tc::tc_fence_after();
+    const uint32_t id = tc::idesc_tf32(128, 32, false, false);
+    for (int s = 0; s < 3; ++s) {
+      const uint64_t bh = tc::smem_desc(tc::smem_u32(bt_hi) + s * 1024, 512, 128), bl = tc::smem_desc(tc::smem_u32(bt_lo) + s * 1024, 512, 128);
+      tc::mma_tf32_ts(tm, tm + 32 + 8 * s, bh, id, s > 0 ? 1u : 0u);
+      tc::mma_tf32_ts(tm, tm + 64 + 8 * s, bh, id, 1u);
+      tc::mma_tf32_ts(tm, tm + 32 + 8 * s, bl, id, 1u);
+    }
+    tc::mma_commit(&bar);
+  }
+  tc::mbar_wait(&bar, phase); phase ^= 1;
+  tc::tc_fence_after();
+  for (int c8 = 0; c8 < 4; ++c8) {
+    float v[8];
+    tc::tmem_ld8(lane_base + 8 * c8, v);
+    tc::tmem_ld_wait();
+    for (int i = 0; i < 8; ++i) out_a[r * 32 + 8 * c8 + i] = v[i];
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  // ---- test 1: bf16, K = 32 (24 real): A hi packed pairs at columns 32..47, A lo at 48..63 ----------------------------
+  for (int c8 = 0; c8 < 2; ++c8) {
+    uint32_t h[8], l[8];
+    for (int i = 0; i < 8; ++i) {
+      const int k0 = 16 * c8 + 2 * i;
+      uint32_t h0, l0, h1, l1;
+      tc::split_bf16(k0 < 24 ? A[r * 24 + k0] : 0.0f, h0, l0);
+      tc::split_bf16(k0 + 1 < 24 ? A[r * 24 + k0 + 1] : 0.0f, h1, l1);
+      h[i] = h0 | (h1 << 16); l[i] = l0 | (l1 << 16);
+    }
+    tc::tmem_st8(lane_base + 32 + 8 * c8, h);
+    tc::tmem_st8(lane_base + 48 + 8 * c8, l);
+  }
+  tc::tmem_st_wait();
+  tc::tc_fence_before();
+  __syncthreads();
+  if (r == 0) {
+    tc::tc_fence_after();
+    const uint32_t id = tc::idesc_bf16(128, 32, false, false);
+    for (int s = 0; s < 2; ++s) {
+      const uint64_t bh = tc::smem_desc(tc::smem_u32(bb_hi) + s * 1024, 512, 128), bl = tc::smem_desc(tc::smem_u32(bb_lo) + s * 1024, 512, 128);
+      tc::mma_bf16_ts(tm, tm + 32 + 8 * s, bh, id, s > 0 ? 1u : 0u);
+      tc::mma_bf16_ts(tm, tm + 48 + 8 * s, bh, id, 1u);
+      tc::mma_bf16_ts(tm, tm + 32 + 8 * s, bl, id, 1u);
+    }
+    tc::mma_commit(&bar);
+  }
+  tc::mbar_wait(&bar, phase); phase ^= 1;
+  tc::tc_fence_after();
+  for (int c8 = 0; c8 < 4; ++c8) {
+    float v[8];
+    tc::tmem_ld8(lane_base + 8 * c8, v);
+    tc::tmem_ld_wait();
+    for (int i = 0; i < 8; ++i) out_a[128 * 32 + r * 32 + 8 * c8 + i] = v[i];
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  // ---- test 2: M = 64, MN-major bf16x3: D[m][n] = sum_r P[r][m] Q[r][n]; first zero all lanes of the accumulator --------
+  {
+    uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int c8 = 0; c8 < 4; ++c8) tc::tmem_st8(lane_base + 96 + 8 * c8, z);
+    tc::tmem_st_wait();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (r == 0) {
+    tc::tc_fence_after();
+    const uint32_t id = tc::idesc_bf16(64, 32, true, true);
+    for (int s = 0; s < 8; ++s) {
+      const uint64_t ph = tc::smem_desc(tc::smem_u32(p_hi) + s * 256, 128, 2048), pl = tc::smem_desc(tc::smem_u32(p_lo) + s * 256, 128, 2048);
+      const uint64_t qh = tc::smem_desc(tc::smem_u32(q_hi) + s * 256, 128, 2048), ql = tc::smem_desc(tc::smem_u32(q_lo) + s * 256, 128, 2048);
+      tc::mma_bf16(tm + 96, ph, qh, id, 1u);
+      tc::mma_bf16(tm + 96, pl, qh, id, 1u);
+      tc::mma_bf16(tm + 96, ph, ql, id, 1u);
+    }
+    tc::mma_commit(&bar);
+  }
+  tc::mbar_wait(&bar, phase); phase ^= 1;
+  tc::tc_fence_after();
+  for (int c8 = 0; c8 < 4; ++c8) {
+    float v[8];
+    tc::tmem_ld8(lane_base + 96 + 8 * c8, v);
+    tc::tmem_ld_wait();
+    for (int i = 0; i < 8; ++i) out_m64[r * 32 + 8 * c8 + i] = v[i];
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tm, 128);
+}
+
 int launch_tc_selftest(const float* A, const float* B, const float* P, const float* Q, float* out0, float* out1, cudaStream_t st) {
   const size_t smem = 160 * 1024;
   FB_CUDA(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -201,6 +352,9 @@ int launch_tc_selftest(const float* A, const float* B, const float* P, const flo
   FB_CUDA(cudaGetLastError());
   FB_CUDA(cudaFuncSetAttribute(tc_selftest_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   tc_selftest_bf16_kernel<<<1, 128, smem, st>>>(A, B, P, Q, out0 + 128 * 32, out1 + 128 * 32);
+  FB_CUDA(cudaGetLastError());
+  FB_CUDA(cudaFuncSetAttribute(tc_selftest_tmemA_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc_selftest_tmemA_kernel<<<1, 128, smem, st>>>(A, B, P, Q, out0 + 2 * 128 * 32, out1 + 2 * 128 * 32);
   FB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -15,7 +15,7 @@ def test_tcgen05_selftest(ctx):
     A, B = rng.standard_normal((128, 24)).astype(np.float32), rng.standard_normal((24, 32)).astype(np.float32)
     P, Q = rng.standard_normal((128, 24)).astype(np.float32), rng.standard_normal((128, 24)).astype(np.float32)
     d = [ctx.to_device(x) for x in (A, B, P, Q)]
-    o0, o1 = ctx.zeros(2, 128, 32), ctx.zeros(2, 128, 32)
+    o0, o1 = ctx.zeros(4, 128, 32), ctx.zeros(4, 128, 32)
     L.check(L.lib.fbsdej_selftest_tc(ctx.handle, *[C.c_void_p(t.data_ptr()) for t in d], C.c_void_p(o0.data_ptr()),
                                      C.c_void_p(o1.data_ptr())))
     r0, r1 = ctx.to_host(o0).numpy(), ctx.to_host(o1).numpy()
@@ -29,6 +29,19 @@ def test_tcgen05_selftest(ctx):
     print("tf32x3 K-major", e0, "bf16x3 K-major", e2, "bf16x3 MN-major", e3)
     assert e2 < 1e-4, f"bf16x3 K-major GEMM rel error {e2:.2e}"
     assert e3 < 1e-4, f"bf16x3 MN-major GEMM rel error {e3:.2e}"
+    # A operand in tensor memory (tcgen05.st by the row's own thread), B in shared memory
+    e4 = np.abs(r0[2] - ref0).max() / np.abs(ref0).max()
+    e5 = np.abs(r0[3] - ref0).max() / np.abs(ref0).max()
+    print("A-in-TMEM tf32x3", e4, "bf16x3", e5)
+    # M = 64 accumulator: recover the row -> lane map from the dump of all 128 lanes
+    m64 = r1[2]
+    lanes = []
+    for m in range(24):
+        d = np.abs(m64[:, :24] - ref1[m][None, :]).max(axis=1) / np.abs(ref1).max()
+        lanes.append(int(np.argmin(d)) if d.min() < 1e-4 else -1)
+    print("M=64 row->lane", lanes)
+    assert e4 < 5e-6, f"A-in-TMEM tf32x3 rel error {e4:.2e}"
+    assert e5 < 1e-4, f"A-in-TMEM bf16x3 rel error {e5:.2e}"
 
 
 import helpers as H
