@@ -395,31 +395,45 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
 // the tile), so no operand of the split GEMMs is larger than O(1).  The closed-form coupling A(i, X), the exponentials of
 // the Euler step and the record stores are issued between an MMA's launch and the wait on its mbarrier.
 namespace fwd {
-constexpr int XA_HI = 0, XA_LO = 2048, H1_HI = 4096, H1_LO = 7168, W1B_HI = 10240, W1B_LO = W1B_HI + 4 * NB * 4,
-              W2B_HI = W1B_LO + 4 * NB * 4, W2B_LO = W2B_HI + 6 * NB * 4, OFF_W3 = W2B_LO + 6 * NB * 4, OFF_RED = OFF_W3 + 32,
+// shared memory: only the B operands (weights) - the activations go to tensor memory
+constexpr int W1B_HI = 0, W1B_LO = W1B_HI + 4 * NB * 4, W2B_HI = W1B_LO + 4 * NB * 4, W2B_LO = W2B_HI + 6 * NB * 4,
+              OFF_W3 = W2B_LO + 6 * NB * 4 + 32 /* N = 32 reads 8 n-rows past the last chunk */, OFF_RED = OFF_W3 + 32,
               OFF_BAR = OFF_RED + 8, SMEM_FLOATS = OFF_BAR + 8;
 static_assert((OFF_BAR % 2) == 0, "mbarrier alignment");
+// tensor memory columns: accumulator | A operand hi (X: 16, H1: 24 columns) | A operand lo
+constexpr uint32_t C_ACC = 0, C_AHI = 32, C_ALO = 64, NCOLS = 128;
 
-// D[ACC] = A (K-major fp32 chunks [f/4][row][4], KS slices of 8) * B ([k/4][n][4], NB n-rows per chunk), N = 32, 3xTF32
+// D[ACC] = A (tensor memory: lane = row, one TF32 element per column, KS slices of 8 columns; hi and lo copies)
+//          * B (shared memory [k/4][n][4], NB n-rows per chunk), N = 32, 3xTF32
 template <int KS>
-__device__ __forceinline__ void gemm_k_tf32(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo) {
+__device__ __forceinline__ void gemm_k_tf32(uint32_t tmem, uint32_t b_hi, uint32_t b_lo) {
   constexpr uint32_t id = tc::idesc_tf32(128, 32, false, false);
 #pragma unroll
   for (int s = 0; s < KS; ++s) {
-    const uint64_t dah = tc::smem_desc(a_hi + s * 4096, 2048, 128), dal = tc::smem_desc(a_lo + s * 4096, 2048, 128);
     const uint64_t dbh = tc::smem_desc(b_hi + s * (2 * NB * 16), NB * 16, 128), dbl = tc::smem_desc(b_lo + s * (2 * NB * 16), NB * 16, 128);
-    tc::mma_tf32(tmem_d, dah, dbh, id, s > 0 ? 1u : 0u);
-    tc::mma_tf32(tmem_d, dal, dbh, id, 1u);
-    tc::mma_tf32(tmem_d, dah, dbl, id, 1u);
+    tc::mma_tf32_ts(tmem + C_ACC, tmem + C_AHI + 8 * s, dbh, id, s > 0 ? 1u : 0u);
+    tc::mma_tf32_ts(tmem + C_ACC, tmem + C_ALO + 8 * s, dbh, id, 1u);
+    tc::mma_tf32_ts(tmem + C_ACC, tmem + C_AHI + 8 * s, dbl, id, 1u);
   }
 }
-// store 4 consecutive features of this thread's row as TF32 hi / lo chunks
-__device__ __forceinline__ void store_tf32x4(float* __restrict__ hi_tile, float* __restrict__ lo_tile, int chunk, int row, const float* v) {
-  float h[4], l[4];
+// 8 consecutive features of this thread's row -> TF32 hi / lo columns of the A operand in tensor memory
+__device__ __forceinline__ void store_tf32x8(uint32_t lane_base, int c8, const float* v) {
+  uint32_t h[8], l[8];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) tc::split_tf32(v[q], h[q], l[q]);
-  st4(hi_tile + (chunk * TR + row) * 4, make_float4(h[0], h[1], h[2], h[3]));
-  st4(lo_tile + (chunk * TR + row) * 4, make_float4(l[0], l[1], l[2], l[3]));
+  for (int q = 0; q < 8; ++q) {
+    float hi, lo;
+    tc::split_tf32(v[q], hi, lo);
+    h[q] = __float_as_uint(hi); l[q] = __float_as_uint(lo);
+  }
+  tc::tmem_st8(lane_base + C_AHI + 8 * c8, h);
+  tc::tmem_st8(lane_base + C_ALO + 8 * c8, l);
+}
+// TMEM operand writes (+ the bias row in shared memory) -> visible to the MMA issued after the CTA barrier
+__device__ __forceinline__ void publish_tmem() {
+  tc::tmem_st_wait();
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
 }
 }  // namespace fwd
 
@@ -470,7 +484,7 @@ __global__ void __launch_bounds__(kThreads, 4) reg_forward_tc(const PricingArgs 
       }
     }
   }
-  if (warp == 0) tc::tmem_alloc(tslot, 32);
+  if (warp == 0) tc::tmem_alloc(tslot, NCOLS);
   if (row == 0) { tc::mbar_init(bar, 1); tc::fence_mbar_init(); }
   tc::fence_async_smem();
   tc::tc_fence_before();
@@ -521,8 +535,8 @@ __global__ void __launch_bounds__(kThreads, 4) reg_forward_tc(const PricingArgs 
 #pragma unroll
         for (int k = 0; k < D; ++k) xin[1 + k] = X[k];
         xin[1 + D] = 1.0f;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) store_tf32x4(smem + XA_HI, smem + XA_LO, c, row, xin + 4 * c);
+        store_tf32x8(lane_base, 0, xin);
+        store_tf32x8(lane_base, 1, xin + 8);
         if (row <= H) {
           float hi, lo;
           tc::split_tf32(row < H ? fmaf(tf, w0, b1v) : one_in, hi, lo);
@@ -530,10 +544,10 @@ __global__ void __launch_bounds__(kThreads, 4) reg_forward_tc(const PricingArgs 
           smem[W1B_LO + bias_idx] = lo;
         }
       }
-      publish();
+      publish_tmem();
       if (warp == 0 && issuer) {
         tc::tc_fence_after();
-        gemm_k_tf32<2>(tmem, sa(XA_HI), sa(XA_LO), sa(W1B_HI), sa(W1B_LO));
+        gemm_k_tf32<2>(tmem, sa(W1B_HI), sa(W1B_LO));
         tc::mma_commit(bar);
       }
       // ---- independent of the network: closed-form coupling, exponentials, record stores -------------------------
@@ -548,23 +562,19 @@ __global__ void __launch_bounds__(kThreads, 4) reg_forward_tc(const PricingArgs 
       Model::eval_A_finish(a, i, ae, Ai, dAb);
       rs[RL::P_DA * TR] = dAb;
       wait_mma();
-      {
-        float h1[24];
 #pragma unroll
-        for (int c8 = 0; c8 < 3; ++c8) {
-          float t8[8];
-          tc::tmem_ld8(lane_base + 8 * c8, t8);
-          tc::tmem_ld_wait();
+      for (int c8 = 0; c8 < 3; ++c8) {
+        float t8[8];
+        tc::tmem_ld8(lane_base + C_ACC + 8 * c8, t8);
+        tc::tmem_ld_wait();
 #pragma unroll
-          for (int q = 0; q < 8; ++q) h1[8 * c8 + q] = actf<ACT>(t8[q]);
-        }
-#pragma unroll
-        for (int c = 0; c < 6; ++c) store_tf32x4(smem + H1_HI, smem + H1_LO, c, row, h1 + 4 * c);
+        for (int q = 0; q < 8; ++q) t8[q] = actf<ACT>(t8[q]);
+        store_tf32x8(lane_base, c8, t8);                 // (L1 has completed: the X columns are free)
       }
-      publish();
+      publish_tmem();
       if (warp == 1 && issuer) {
         tc::tc_fence_after();
-        gemm_k_tf32<3>(tmem, sa(H1_HI), sa(H1_LO), sa(W2B_HI), sa(W2B_LO));
+        gemm_k_tf32<3>(tmem, sa(W2B_HI), sa(W2B_LO));
         tc::mma_commit(bar);
       }
 #pragma unroll
@@ -575,7 +585,7 @@ __global__ void __launch_bounds__(kThreads, 4) reg_forward_tc(const PricingArgs 
 #pragma unroll
       for (int c8 = 0; c8 < 3; ++c8) {
         float t8[8];
-        tc::tmem_ld8(lane_base + 8 * c8, t8);
+        tc::tmem_ld8(lane_base + C_ACC + 8 * c8, t8);
         tc::tmem_ld_wait();
         const float4 wa = ld4(w3s + 8 * c8), wb = ld4(w3s + 8 * c8 + 4);
         const float w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
@@ -637,7 +647,7 @@ __global__ void __launch_bounds__(kThreads, 4) reg_forward_tc(const PricingArgs 
     a.lpart[blockIdx.x * 4] = tot;
     a.lpart[blockIdx.x * 4 + 1] = 0.0f; a.lpart[blockIdx.x * 4 + 2] = 0.0f; a.lpart[blockIdx.x * 4 + 3] = 0.0f;
   }
-  if (warp == 0) tc::tmem_dealloc(tmem, 32);
+  if (warp == 0) tc::tmem_dealloc(tmem, NCOLS);
 }
 
 // Tile-major record -> the plane layout of fbsdej_solver_loss' trajectory output: X [N+1][D][B].
