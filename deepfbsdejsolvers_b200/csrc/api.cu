@@ -170,7 +170,10 @@ struct fbsdej_solver {
   float *rec = nullptr, *recN = nullptr;   // tcgen05 path: tile-major records (pricing.cuh: RecLayout)
   float *lpart = nullptr, *gpart = nullptr; int cap_grid = 0;
   float* out_dev = nullptr;       // [4 + P] scratch for train_steps
-  uint32_t* step_ctr = nullptr;   // device step index inside train_steps
+  uint32_t* step_ctr = nullptr;   // device: [0] step index inside train_steps, [1] finished-block counter of the fused finish
+  struct Finish { float* theta; float* m; float* v; const float* mask; float lr, b1, b2, eps; int* t_dev; uint32_t* iter_dev;
+                  float* loss_dst; };
+  const Finish* finish = nullptr; // set by train_steps: run_pass fuses reduce + Adam + counters into one launch
   // cached training graph
   cudaGraphExec_t graph = nullptr;
   struct Key { const void *theta, *m, *v, *mask, *t, *it, *loss; uint64_t seed; int B; float lr, b1, b2, eps; } key;
@@ -313,7 +316,14 @@ int run_pass(fbsdej_solver* s, const float* theta, int B, int B_global, float* o
     if (ev) cudaEventRecord(ev[1], st);
   }
   // loss partials come from the forward grid, gradient partials from the backward grid
-  if (launch_reduce_partials(s->lpart, grid_f, s->gpart, grid_b, s->P, out, with_grad, st)) return -2;
+  if (s->finish && with_grad) {
+    const fbsdej_solver::Finish& f = *s->finish;
+    if (launch_reduce_adam(s->lpart, grid_f, s->gpart, grid_b, s->P, out, f.theta, f.m, f.v, f.mask, f.lr, f.b1, f.b2, f.eps,
+                           f.t_dev, f.iter_dev, f.loss_dst, s->step_ctr, s->step_ctr + 1, st))
+      return -2;
+  } else if (launch_reduce_partials(s->lpart, grid_f, s->gpart, grid_b, s->P, out, with_grad, st)) {
+    return -2;
+  }
   s->ctx->launches += with_grad ? 3 : 2;
   return 0;
 }
@@ -669,7 +679,8 @@ int fbsdej_solver_create(fbsdej_ctx* ctx, const fbsdej_solver_desc* desc, const 
     if (dev_alloc(&s->jmc_raw, n) || dev_alloc(&s->jmc, n) || dev_alloc(&s->jmc_nnz, (size_t)N) || dev_alloc(&s->jmc_n0, (size_t)N))
       return -2;
   }
-  if (dev_alloc(&s->out_dev, (size_t)(kHeader + s->P)) || dev_alloc(&s->step_ctr, (size_t)1)) return -2;
+  if (dev_alloc(&s->out_dev, (size_t)(kHeader + s->P)) || dev_alloc(&s->step_ctr, (size_t)2)) return -2;
+  FB_CUDA(cudaMemsetAsync(s->step_ctr, 0, 2 * sizeof(uint32_t), st));
   FB_CUDA(cudaStreamSynchronize(st));
   *out = s.release();
   return 0;
@@ -802,14 +813,13 @@ int fbsdej_solver_train_steps(fbsdej_solver* s, float* theta, float* m, float* v
   }
   FB_CUDA(cudaMemsetAsync(s->step_ctr, 0, sizeof(uint32_t), st));
   int done = 0;
-  auto one_step = [&]() -> int {
+  const fbsdej_solver::Finish fin{theta, m, v, mask, lr, beta1, beta2, eps, t_dev, iter_dev, loss_out};
+  auto one_step = [&]() -> int {       // simulate, forward, adjoint, [reduce + Adam + counters + loss record]: 4 launches
     if (do_simulate(s, seed, 0, iter_dev, 0, B)) return -2;
-    if (run_pass(s, theta, B, B, s->out_dev, true, nullptr, nullptr)) return -2;
-    if (launch_adam(theta, m, v, s->out_dev + kHeader, mask, s->P, lr, beta1, beta2, eps, t_dev, st)) return -2;
-    if (launch_bump_u32(iter_dev, st)) return -2;
-    if (launch_copy_loss(s->out_dev, loss_out, s->step_ctr, st)) return -2;
-    s->ctx->launches += 4;
-    return 0;
+    s->finish = &fin;
+    const int rc = run_pass(s, theta, B, B, s->out_dev, true, nullptr, nullptr);
+    s->finish = nullptr;
+    return rc ? -2 : 0;
   };
   if (!same && n_steps > 0) {
     if (one_step()) return -2;

@@ -6,6 +6,9 @@ namespace fbsdej {
 
 int launch_reduce_partials(const float* lpart, int nparts_l, const float* gpart, int nparts_g, int P, float* out,
                            bool with_grad, cudaStream_t st);
+int launch_reduce_adam(const float* lpart, int nparts_l, const float* gpart, int nparts_g, int P, float* out, float* theta,
+                       float* m, float* v, const float* mask, float lr, float b1, float b2, float eps, int* t_dev,
+                       uint32_t* iter_dev, float* loss_dst, uint32_t* step_ctr, unsigned int* done_ctr, cudaStream_t st);
 int launch_adam(float* theta, float* m, float* v, const float* grad, const float* mask, int n, float lr, float b1,
                 float b2, float eps, int* t_dev, cudaStream_t st);
 int launch_bump_u32(uint32_t* p, cudaStream_t st);

@@ -3,24 +3,71 @@
 namespace fbsdej {
 
 // out[0..3] = sum over CTAs of the loss partials; out[4+e] = sum over CTAs of gradient partials (fixed order:
-// deterministic for a given grid).  One thread per output element, coalesced over e.
-__global__ void reduce_partials_kernel(const float* __restrict__ lpart, int nparts_l, const float* __restrict__ gpart,
-                                       int nparts, int P, float* __restrict__ out, int with_grad) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+// deterministic for a given grid).  A block of 256 threads owns 32 consecutive output elements; its 8 warps split the
+// partial rows (row c goes to warp c mod 8, 8 independent loads in flight per thread), then one fixed-order sum over warps.
+// With theta != NULL the kernel also finishes the training step: Keras-form Adam on its elements and, in the block that
+// finishes last, the step / iteration counters and the loss record (replaces four more launches per step).
+struct FinishArgs {
+  float* theta; float* m; float* v; const float* mask;
+  float lr, b1, b2, eps;
+  int* t_dev; uint32_t* iter_dev; float* loss_dst; uint32_t* step_ctr; unsigned int* done_ctr;
+};
+
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ lpart, int nparts_l,
+                                                              const float* __restrict__ gpart, int nparts, int P,
+                                                              float* __restrict__ out, int with_grad, const FinishArgs f) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int e = blockIdx.x * 32 + tx;
+  const int n = kHeader + (with_grad ? P : 0);
+  float s = 0.0f;
   if (e < kHeader) {
-    float s = 0.0f;
-    for (int c = 0; c < nparts_l; ++c) s += lpart[c * 4 + e];
-    out[e] = s;
-  } else if (with_grad && e < kHeader + P) {
-    const int j = e - kHeader;
-    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
-    int c = 0;
-    for (; c + 3 < nparts; c += 4) {
-      s0 += gpart[(size_t)c * P + j]; s1 += gpart[(size_t)(c + 1) * P + j];
-      s2 += gpart[(size_t)(c + 2) * P + j]; s3 += gpart[(size_t)(c + 3) * P + j];
+    for (int c = ty; c < nparts_l; c += 8) s += lpart[c * 4 + e];
+  } else if (e < n) {
+    const float* __restrict__ g = gpart + (e - kHeader);
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f, a4 = 0.0f, a5 = 0.0f, a6 = 0.0f, a7 = 0.0f;
+    int c = ty;
+    for (; c + 56 < nparts; c += 64) {
+      a0 += g[(size_t)c * P]; a1 += g[(size_t)(c + 8) * P]; a2 += g[(size_t)(c + 16) * P]; a3 += g[(size_t)(c + 24) * P];
+      a4 += g[(size_t)(c + 32) * P]; a5 += g[(size_t)(c + 40) * P]; a6 += g[(size_t)(c + 48) * P]; a7 += g[(size_t)(c + 56) * P];
     }
-    for (; c < nparts; ++c) s0 += gpart[(size_t)c * P + j];
-    out[e] = (s0 + s1) + (s2 + s3);
+    for (; c < nparts; c += 8) a0 += g[(size_t)c * P];
+    s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  }
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && e < n) {
+    float t = red[0][tx];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) t += red[w][tx];
+    out[e] = t;
+    if (f.theta && e >= kHeader) {                    // oracle/adam.py, SURVEY fact 9
+      const int i = e - kHeader;
+      if (!(f.mask && f.mask[i] == 0.0f)) {
+        const int step = *f.t_dev + 1;
+        const float b1p = powf(f.b1, (float)step), b2p = powf(f.b2, (float)step);
+        const float alpha = f.lr * sqrtf(1.0f - b2p) / (1.0f - b1p);
+        const float mi = f.m[i] + (t - f.m[i]) * (1.0f - f.b1);
+        const float vi = f.v[i] + (t * t - f.v[i]) * (1.0f - f.b2);
+        f.m[i] = mi; f.v[i] = vi;
+        f.theta[i] -= alpha * mi / (sqrtf(vi) + f.eps);
+      }
+    }
+  }
+  if (f.theta) {                                      // the block that finishes last advances the counters
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int prev = atomicAdd(f.done_ctr, 1u);
+      if (prev == gridDim.x - 1) {
+        __threadfence();
+        *f.t_dev += 1;
+        *f.iter_dev += 1u;
+        if (f.loss_dst) f.loss_dst[*f.step_ctr] = __ldcg(out);
+        *f.step_ctr += 1u;
+        *f.done_ctr = 0u;
+      }
+    }
   }
 }
 
@@ -97,7 +144,18 @@ __global__ void transpose_kernel(const float* __restrict__ src, float* __restric
 int launch_reduce_partials(const float* lpart, int nparts_l, const float* gpart, int nparts_g, int P, float* out,
                            bool with_grad, cudaStream_t st) {
   const int n = kHeader + (with_grad ? P : 0);
-  reduce_partials_kernel<<<(n + 127) / 128, 128, 0, st>>>(lpart, nparts_l, gpart, nparts_g, P, out, with_grad ? 1 : 0);
+  FinishArgs f{};
+  reduce_partials_kernel<<<(n + 31) / 32, 256, 0, st>>>(lpart, nparts_l, gpart, nparts_g, P, out, with_grad ? 1 : 0, f);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+// reduce + Adam + counters + loss record in one launch (fbsdej_solver_train_steps)
+int launch_reduce_adam(const float* lpart, int nparts_l, const float* gpart, int nparts_g, int P, float* out, float* theta,
+                       float* m, float* v, const float* mask, float lr, float b1, float b2, float eps, int* t_dev,
+                       uint32_t* iter_dev, float* loss_dst, uint32_t* step_ctr, unsigned int* done_ctr, cudaStream_t st) {
+  const int n = kHeader + P;
+  FinishArgs f{theta, m, v, mask, lr, b1, b2, eps, t_dev, iter_dev, loss_dst, step_ctr, done_ctr};
+  reduce_partials_kernel<<<(n + 31) / 32, 256, 0, st>>>(lpart, nparts_l, gpart, nparts_g, P, out, 1, f);
   FB_CUDA(cudaGetLastError());
   return 0;
 }
