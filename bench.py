@@ -228,24 +228,36 @@ def run_native(a):
     value = B * N / (ms_step * 1e-3)
 
     # ---- end to end through the C-ABI with HOST buffers: H2D of the step's increments + step + D2H of the loss ----
-    e2e = None
+    # The step's Brownian / jump increments live in pinned host memory; a copy stream uploads step k+1 into the other
+    # device buffer while step k computes (both inside the timed region), the loss comes back to the host every step.
+    e2e, e2e_rng = None, None
     if not a.no_e2e:
         nfl = N * D * Bl
         host = [[torch.randn(nfl, dtype=torch.float32).mul_(0.1).pin_memory() for _ in range(2)] for _ in range(2)]
-        dev = [ctx.empty(nfl), ctx.empty(nfl)]
+        dev = [[ctx.empty(nfl), ctx.empty(nfl)] for _ in range(2)]
         loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
         jmc = ctx.zeros(N * D * max(M, 1)) if M > 0 else None
+        copy_stream = torch.cuda.Stream(ctx.device)
+        up = [torch.cuda.Event(), torch.cuda.Event()]        # upload of buffer b finished
+        free = [torch.cuda.Event(), torch.cuda.Event()]      # compute on buffer b finished
         k = [0]
 
+        def upload(b, src):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(free[b])
+                dev[b][0].copy_(host[src][0], non_blocking=True)
+                dev[b][1].copy_(host[src][1], non_blocking=True)
+                up[b].record(copy_stream)
+
         def e2e_step():
-            hw, hj = host[k[0] & 1]
+            b = k[0] & 1
             k[0] += 1
-            with torch.cuda.stream(ctx.stream):
-                dev[0].copy_(hw, non_blocking=True)
-                dev[1].copy_(hj, non_blocking=True)
-            L.check(L.lib.fbsdej_solver_set_noise(s.handle, Bl, dev[0].data_ptr(), dev[1].data_ptr(),
+            upload(b ^ 1, k[0] & 1)                          # next step's increments -> the other buffer
+            ctx.stream.wait_event(up[b])
+            L.check(L.lib.fbsdej_solver_set_noise(s.handle, Bl, dev[b][0].data_ptr(), dev[b][1].data_ptr(),
                                                   jmc.data_ptr() if jmc is not None else None))
             L.check(L.lib.fbsdej_solver_grad(s.handle, s.theta.data_ptr(), Bl, B, s.out.data_ptr()))
+            free[b].record(ctx.stream)
             with torch.cuda.stream(ctx.stream):
                 if world > 1:
                     dist.all_reduce(s.out)
@@ -254,14 +266,37 @@ def run_native(a):
                 loss_host.copy_(s.out[:1], non_blocking=True)
             ctx.sync()
 
+        for b in range(2):
+            free[b].record(ctx.stream)
+        upload(0, 0)
         for _ in range(2):
             e2e_step()
         ms_e = timed(e2e_step, a.steps) / a.steps
+        copy_stream.synchronize()
         e2e = {"value": B * N / (ms_e * 1e-3), "unit": "path-steps/s", "ms_per_step": ms_e,
                "h2d_bytes_per_step": 2 * nfl * 4 * world, "d2h_bytes_per_step": 4 * world,
-               "what": "host (pinned) Brownian + jump increments of the step -> H2D -> fbsdej_solver_set_noise -> "
-                       "fbsdej_solver_grad -> fbsdej_adam_step -> loss D2H; the production path draws the increments on "
-                       "the device (Philox) and moves no per-step host data"}
+               "what": "host (pinned) Brownian + jump increments of the step -> H2D (double-buffered on a copy stream) -> "
+                       "fbsdej_solver_set_noise -> fbsdej_solver_grad -> fbsdej_adam_step -> loss D2H + sync every step; "
+                       "bounded by the PCIe upload of 8*d bytes per path-step"}
+        del host, dev
+
+        # the production call: Solver.train_steps draws the increments on the device (Philox), so its per-step host input is
+        # (seed, step count, learning rate) and its per-step host output the loss
+        loss_dev = ctx.zeros(1)
+
+        def rng_step():
+            s.train_steps(0, B, 1, LR, loss_out=loss_dev)
+            with torch.cuda.stream(ctx.stream):
+                loss_host.copy_(loss_dev, non_blocking=True)
+            ctx.sync()
+
+        if world == 1:
+            for _ in range(2):
+                rng_step()
+            ms_r = timed(rng_step, a.steps) / a.steps
+            e2e_rng = {"value": B * N / (ms_r * 1e-3), "unit": "path-steps/s", "ms_per_step": ms_r, "h2d_bytes_per_step": 0,
+                       "d2h_bytes_per_step": 4, "what": "fbsdej_solver_train_steps(n_steps=1) + loss D2H + host sync every step; "
+                       "increments drawn on the device, as the reference draws them inside its graph"}
 
     # ---- per-kernel device times + roofline (rank 0) ----------------------------------------------------------------
     roof, kernels = None, None
@@ -288,13 +323,25 @@ def run_native(a):
         if jump:
             kernels["sim_compensator"] = {"ms": prof["sim_compensator"]}
         dom = max(("sim_paths", "forward", "backward"), key=lambda n: prof[n])
-        roof = {"kernel": {"sim_paths": "sim_merton_kernel", "forward": "pricing_forward", "backward": "pricing_backward"}[dom],
+        tc = a.mma == "tcgen05" and not jump
+        kname = {"sim_paths": "sim_merton_kernel", "forward": "reg_forward_tc" if tc else "pricing_forward",
+                 "backward": "reg_backward_tc" if tc else "pricing_backward"}[dom]
+        traffic = None
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (config 3)
+            prof_js = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            if Bl == prof_js["paths"] and N == prof_js["time_steps"]:
+                traffic = prof_js["kernels"][kname]["dram_bytes"]
+        except Exception:
+            pass
+        roof = {"kernel": kname,
                 "bound": "hbm", "achieved": kernels[dom]["achieved_GBps"], "peak": peak, "unit": "GB/s",
-                "frac": kernels[dom]["frac_of_measured_hbm"], "traffic": None,
+                "frac": kernels[dom]["frac_of_measured_hbm"], "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "share_of_step": prof[dom] / sum(prof.values()),
-                "note": "fused kernel: MLP evaluations, closed-form series and adjoint run inside the launch, so it is "
-                        "FMA/MUFU-bound; the fraction is algorithmic path-tensor bytes over the measured copy bandwidth"}
+                "algorithmic_bytes": kernels[dom]["algorithmic_bytes"],
+                "note": "fused kernel: the network GEMMs (tcgen05), tanh, the closed-form coupling and the adjoint run inside "
+                        "the launch, so it is bound by the tensor / MUFU pipes and the per-step MMA round trips, not by HBM; "
+                        "frac = algorithmic path-tensor bytes (SURVEY 8d) / launch time / measured copy bandwidth"}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -312,8 +359,8 @@ def run_native(a):
         line = {"metric": "path-steps/s", "value": value, "unit": "path-steps/s", "n_gpus": world, "steps": a.steps,
                 "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "iters_per_s": 1e3 / ms_step, "higher_is_better": True,
                 "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": cfg, "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "kernels": kernels,
-                "cpu_baseline": cpu}
+                "config": cfg, "clocks": clk, "e2e": e2e, "e2e_device_rng": e2e_rng, "gpu_launches": int(launches), "roofline": roof,
+                "kernels": kernels, "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
