@@ -15,17 +15,19 @@ namespace fbsdej {
 // One (path, asset pair, step) cell = ONE Philox call: words 0/1 -> the two Brownian normals (Box-Muller), words 2/3 ->
 // the two Poisson counts by table inversion.  A count of 1 (the only frequent non-zero case: P = lam dt e^{-lam dt})
 // takes its jump size from the SAME uniform: conditional on thr[0] <= u < thr[1], (u - thr[0]) / (thr[1] - thr[0]) is
-// uniform with ~28 bits, mapped through the inverse normal CDF.  Only counts >= 2 (P ~ (lam dt)^2 / 2) draw a second
-// Philox block (stream + 2), so warps almost never diverge into it.
-// Work split: blockIdx.y = step * KP + pair, blockIdx.x / threadIdx.x walk groups of 4 consecutive paths (128-bit
-// stores, no integer division anywhere).
-__device__ __forceinline__ float jump_size(uint32_t u, uint32_t t0, uint32_t t1, float inv_w1, const uint32_t* __restrict__ thr,
-                                           int n, float muJ, float sigJ, uint32_t gid, uint32_t c1, uint32_t iter, uint32_t stream,
-                                           uint32_t k0, uint32_t k1, int which) {
-  if (u < t0) return 0.0f;
-  if (u < t1) {                                          // exactly one jump: size ~ N(muJ, sigJ^2)
+// uniform with ~28 bits, mapped through the inverse normal CDF (branch-free polynomial, evaluated for every draw).
+// Only counts >= 2 (P ~ (lam dt)^2 / 2) and far-tail sizes go through jump_size_rare (a second Philox block, stream + 2).
+// Work split: a work unit = (step, asset pair, chunk of 256 groups of 4 consecutive paths); a persistent grid (4 CTAs per
+// SM) strides over the units, so the per-CTA set-up is paid once and the only integer divisions are per unit and uniform.
+// 128-bit stores.
+// Rare cases of a Poisson draw (count >= 2, or a single jump whose uniform falls in the far tail of the normal): exact
+// table walk, library inverse CDF, second Philox block for the collapsed sum of count normals (pricingModels.py:60).
+__device__ __noinline__ float jump_size_rare(uint32_t u, uint32_t t0, uint32_t t1, float inv_w1, const uint32_t* __restrict__ thr,
+                                             int n, float muJ, float sigJ, uint32_t gid, uint32_t c1, uint32_t iter, uint32_t stream,
+                                             uint32_t k0, uint32_t k1, int which) {
+  if (u < t1) {
     const float v = ((float)(u - t0) + 0.5f) * inv_w1;
-    return fmaf(sigJ, normcdfinvf(fminf(v, 0.99999994f)), muJ);
+    return fmaf(sigJ, normcdfinvf(fminf(fmaxf(v, 1.0e-9f), 0.99999994f)), muJ);
   }
   int c = 2;
   for (int k = 2; k < n; ++k) {
@@ -36,10 +38,46 @@ __device__ __forceinline__ float jump_size(uint32_t u, uint32_t t0, uint32_t t1,
   float e0, e1;
   box_muller(s.x, s.y, e0, e1);
   const float dn = (float)c;
-  return dn * muJ + sigJ * sqrtf(dn) * (which ? e1 : e0);   // pricingModels.py:60 (sum of dn normals collapsed)
+  return dn * muJ + sigJ * sqrtf(dn) * (which ? e1 : e0);
 }
 
-__global__ void __launch_bounds__(256) sim_merton_kernel(const SimMertonArgs a) {
+// Branch-free common case.  count = 0: J = 0.  count = 1 (thr[0] <= u < thr[1]): v = (u - thr[0] + 1/2) / (thr[1] - thr[0])
+// is uniform on (0, 1) with ~28 bits; z = Phi^{-1}(v) = sqrt(2) erfinv(2v - 1) by Giles' single-precision polynomial in
+// w = -ln(4 v (1 - v)) (central branch w < 5, |error| ~ 3e-7); J = muJ + sigJ z.  `rare` flags what the polynomial does not
+// cover.
+__device__ __forceinline__ float jump_size_fast(uint32_t u, uint32_t t0, uint32_t t1, float inv_w1, float muJ, float sigJ, bool& rare) {
+  const float v = ((float)(u - t0) + 0.5f) * inv_w1;
+  const float x = fmaf(2.0f, v, -1.0f);
+  float w = -0.6931471805599453f * __log2f(fmaf(-x, x, 1.0f));
+  const bool one = (u >= t0) && (u < t1);
+  rare = (u >= t1) || (one && !(w < 5.0f));
+  w -= 2.5f;
+  float p = 2.81022636e-08f;
+  p = fmaf(p, w, 3.43273939e-07f);
+  p = fmaf(p, w, -3.5233877e-06f);
+  p = fmaf(p, w, -4.39150654e-06f);
+  p = fmaf(p, w, 0.00021858087f);
+  p = fmaf(p, w, -0.00125372503f);
+  p = fmaf(p, w, -0.00417768164f);
+  p = fmaf(p, w, 0.246640727f);
+  p = fmaf(p, w, 1.50140941f);
+  const float z = 1.4142135623730951f * p * x;
+  return one ? fmaf(sigJ, z, muJ) : 0.0f;
+}
+
+// two N(0,1) from two 32-bit words: Box-Muller with the MUFU approximations (lg2, sqrt, sin, cos)
+__device__ __forceinline__ void box_muller_fast(uint32_t a, uint32_t b, float scale, float& n0, float& n1) {
+  const float u = fmaf(__uint2float_rz(a), 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // (0, 1)
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * __log2f(u)));           // sqrt(-2 ln u)
+  r *= scale;
+  float sn, cs;
+  __sincosf(__uint2float_rz(b) * 1.4629180792671596e-09f, &sn, &cs);                               // 2 pi b / 2^32
+  n0 = r * cs;
+  n1 = r * sn;
+}
+
+__global__ void __launch_bounds__(256, 4) sim_merton_kernel(const SimMertonArgs a) {
   __shared__ uint32_t sthr[64];
   if (threadIdx.x < 64) sthr[threadIdx.x] = threadIdx.x < a.npois ? a.pois_thr[threadIdx.x] : 0xffffffffu;
   __syncthreads();
@@ -48,24 +86,39 @@ __global__ void __launch_bounds__(256) sim_merton_kernel(const SimMertonArgs a) 
   const uint32_t t0 = sthr[0], t1 = sthr[1];
   const float inv_w1 = t1 > t0 ? 1.0f / (float)(t1 - t0) : 0.0f;
   const bool vec = (a.B % 4 == 0);
-  for (int cell = blockIdx.y; cell < a.N * KP; cell += gridDim.y) {
-    const int i = cell / KP, kp = cell - i * KP;           // (uniform per block)
+  const int nchunk = (B4 + 255) / 256;
+  const long long nunits = (long long)a.N * KP * nchunk;
+  for (long long unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+    const int cell = (int)(unit / nchunk), chunk = (int)(unit - (long long)cell * nchunk);   // (uniform per block)
+    const int i = cell / KP, kp = cell - i * KP;
     const int k0 = 2 * kp, k1 = 2 * kp + 1;
     const uint32_t c1 = ((uint32_t)i << 8) | (uint32_t)kp;
     const size_t o0 = ((size_t)i * a.D + k0) * a.B, o1 = ((size_t)i * a.D + k1) * a.B;
-    for (int bq = blockIdx.x * blockDim.x + threadIdx.x; bq < B4; bq += gridDim.x * blockDim.x) {
+    const int bq = chunk * 256 + threadIdx.x;
+    if (bq < B4) {
       const int b0 = bq * 4;
       float w0[4], w1[4], j0[4], j1[4];
+      uint32_t rare = 0;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < 4; ++q) {                        // branch-free: the four Philox chains interleave
         const uint32_t gid = a.path_offset + (uint32_t)(b0 + q);
         const uint4 r = Philox::rand4(gid, c1, iter, a.stream, a.seed_lo, a.seed_hi);
-        float n0, n1;
-        box_muller(r.x, r.y, n0, n1);
-        w0[q] = a.sqdt * n0;
-        w1[q] = a.sqdt * n1;
-        j0[q] = jump_size(r.z, t0, t1, inv_w1, sthr, a.npois, a.muJ, a.sigJ, gid, c1, iter, a.stream, a.seed_lo, a.seed_hi, 0);
-        j1[q] = jump_size(r.w, t0, t1, inv_w1, sthr, a.npois, a.muJ, a.sigJ, gid, c1, iter, a.stream, a.seed_lo, a.seed_hi, 1);
+        box_muller_fast(r.x, r.y, a.sqdt, w0[q], w1[q]);
+        bool rare0, rare1;
+        j0[q] = jump_size_fast(r.z, t0, t1, inv_w1, a.muJ, a.sigJ, rare0);
+        j1[q] = jump_size_fast(r.w, t0, t1, inv_w1, a.muJ, a.sigJ, rare1);
+        rare |= (rare0 ? 1u : 0u) << (2 * q) | (rare1 ? 1u : 0u) << (2 * q + 1);
+      }
+      if (rare) {                                          // ~0.4 % of the cells: redo the block, exact path
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if ((rare >> (2 * q)) & 3u) {
+            const uint32_t gid = a.path_offset + (uint32_t)(b0 + q);
+            const uint4 r = Philox::rand4(gid, c1, iter, a.stream, a.seed_lo, a.seed_hi);
+            if ((rare >> (2 * q)) & 1u) j0[q] = jump_size_rare(r.z, t0, t1, inv_w1, sthr, a.npois, a.muJ, a.sigJ, gid, c1, iter, a.stream, a.seed_lo, a.seed_hi, 0);
+            if ((rare >> (2 * q)) & 2u) j1[q] = jump_size_rare(r.w, t0, t1, inv_w1, sthr, a.npois, a.muJ, a.sigJ, gid, c1, iter, a.stream, a.seed_lo, a.seed_hi, 1);
+          }
+        }
       }
       if (vec) {
         if (a.dW) st4(a.dW + o0 + b0, make_float4(w0[0], w0[1], w0[2], w0[3]));
@@ -218,10 +271,8 @@ static inline int sim_grid(size_t total, int threads) {
 }
 
 int launch_sim_merton(const SimMertonArgs& a, cudaStream_t st) {
-  const int cells = a.N * ((a.D + 1) / 2), B4 = (a.B + 3) / 4;
-  int gx = (B4 + 255) / 256;
-  gx = gx < 1 ? 1 : (gx > 148 * 8 ? 148 * 8 : gx);
-  const dim3 grid(gx, cells < 65535 ? cells : 65535);
+  const long long nunits = (long long)a.N * ((a.D + 1) / 2) * (((a.B + 3) / 4 + 255) / 256);
+  const int grid = (int)(nunits < 148 * 4 ? (nunits < 1 ? 1 : nunits) : 148 * 4);
   sim_merton_kernel<<<grid, 256, 0, st>>>(a);
   FB_CUDA(cudaGetLastError());
   return 0;
