@@ -83,8 +83,9 @@ class PricingSolverBase:
         self.mathModel, self.netA, self.netB, self.lRate = mathModel, netA, netB, lRate
         self.M = self.M_DEFAULT if M is None else int(M)
         self.seed, self.ctx, self.stale_time = seed, ctx, stale_time
-        # tcgen05 path (3xTF32 forward, bf16x3 adjoint): available for the compensator-free solvers; off unless asked for
-        self.tensor_cores = bool(tensor_cores) if tensor_cores is not None else False
+        # tcgen05 path (3xTF32 forward, bf16x3 adjoint; tests/test_tc_gpu.py): the compensator-free solvers use it unless
+        # told otherwise (None = automatic: on when the kernels cover the network shape)
+        self.tensor_cores = tensor_cores
         self.native: Optional[NativeSolver] = None
 
     # ------------------------------------------------------------------------------------------------------
@@ -110,8 +111,11 @@ class PricingSolverBase:
             raise ValueError("the jump network must have ndimOut=1")
         n_y0 = 1 if self.SCHEME == L.GLOBAL else 0
         M = 0 if self.REG else self.M
+        spec = self.netA.spec()
+        tc_ok = self.REG and spec.H <= 22 and spec.L == 2 and spec.nout == 1 and d in (1, 10)
+        use_tc = tc_ok if self.tensor_cores is None else (bool(self.tensor_cores) and self.REG)
         self.native = mm.make_solver(self.SCHEME, [n.spec() for n in nets], n_y0, M, ctx=self.ctx,
-                                     stale_time=self.stale_time, tensor_cores=self.tensor_cores and self.REG)
+                                     stale_time=self.stale_time, tensor_cores=use_tc)
         self.push_params()
         return self.native
 

@@ -1,0 +1,53 @@
+"""GPU: the training call itself.  (1) fbsdej_solver_train_steps (CUDA graph: simulate -> forward -> adjoint -> fused
+reduce + Adam + counters) must land on the same parameters as the same steps driven one C-ABI call at a time
+(fbsdej_solver_grad_step -> fbsdej_adam_step -> fbsdej_bump_u32), for the fp32 FFMA kernels and for the tcgen05 kernels;
+(2) the drop-in SolverGlobalSumLocalReg trains the Merton price towards the closed-form known answer 0.2714569
+(pricingModels.py:40-49 at the mainMerton.py:57 parameters)."""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("scheme,d,M,tc", [("SumLocalReg", 10, 0, True), ("MultiStepReg", 1, 0, True), ("SumLocalReg", 1, 0, False),
+                                            ("Global", 1, 48, False)])
+def test_graph_replay_equals_stepwise_calls(ctx, scheme, d, M, tc):
+    B, n, lr, seed = 300, 4, 3e-4, 99
+    p = dict(H.MERTON, N=8)
+    layout = H.pricing_layout("merton", scheme, d)
+    theta = H.random_theta(layout, 3)
+    a = H.native_pricing(ctx, "merton", p, scheme, layout, d=d, M=M, limit=30 if d == 1 else 100, tensor_cores=tc)
+    b = H.native_pricing(ctx, "merton", p, scheme, layout, d=d, M=M, limit=30 if d == 1 else 100, tensor_cores=tc)
+    a.set_theta(theta); b.set_theta(theta)
+    a.reset_optimizer(); b.reset_optimizer()
+    losses = ctx.zeros(n)
+    a.train_steps(seed, B, n, lr, loss_out=losses)
+    step_loss = []
+    for _ in range(n):
+        out = b.grad_step(seed, B, B, 0)
+        step_loss.append(float(ctx.to_host(out[:1]).numpy()[0]))
+        b.adam_step(lr)
+        b.bump_iteration()
+    ctx.sync()
+    ta, tb = a.get_theta(), b.get_theta()
+    assert np.isfinite(ta).all() and np.abs(ta - theta).max() > 0
+    assert np.abs(ta - tb).max() <= 1e-7 * max(1.0, np.abs(tb).max()), np.abs(ta - tb).max()
+    la = ctx.to_host(losses).numpy()
+    assert np.allclose(la, np.array(step_loss), rtol=1e-6, atol=0)
+    assert int(ctx.to_host(a.t).numpy()[0]) == n and int(ctx.to_host(a.iteration).numpy()[0]) == int(ctx.to_host(b.iteration).numpy()[0])
+
+
+def test_reg_solver_trains_to_closed_form(ctx):
+    from deepfbsdejsolvers_b200 import coupledPricing as cp, set_seed
+    set_seed(5)
+    M = H.MERTON
+    mm = cp.MertonJumpModel(M["T"], 20, M["r"], M["muJ"], M["sigmaJ"], M["sigma"], M["lam"], M["K"], M["x0"], cp.AbsCoupling(H.ALIN), 30)
+    solver = cp.SolverGlobalSumLocalReg(mm, cp.Net(0, 1, [21, 21], "tanh"), cp.Net(0, 1, [21, 21], "tanh"), 2e-3, ctx=ctx)
+    listY0, _ = solver.train(4, 10, 250, 16)         # train batch 1000 * 4 (SolversJumpDiff.py:435), val 100 * 10
+    closed = float(mm.A(0, mm.init(1)).numpy()[0])
+    assert abs(closed - 0.2714569) < 2e-5
+    assert solver.lossList[-1] < solver.lossList[0]
+    assert abs(float(listY0[-1]) - closed) < 0.02, (listY0, closed)
