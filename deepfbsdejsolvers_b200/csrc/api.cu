@@ -234,9 +234,22 @@ int pick_G(const fbsdej_solver* s, int B) {
   return G;
 }
 
+// CTAs per path (thread-block cluster) for the jump schemes at small batch: as many as fill the GPU (portable limit 8),
+// but no more than the expected evaluated compensator rows per step give one row per thread.
+int pick_C(const fbsdej_solver* s, int B, int G) {
+  if (!s->has_jump || G != kThreads || getenv("FBSDEJ_NO_CLUSTER")) return 1;
+  double rows = s->M;
+  if (s->model == FBSDEJ_MODEL_MERTON)   // zero-jump samples are deduplicated: expected non-zero ones + 1
+    rows = s->M * (1.0 - std::exp(-s->mer.lam * (s->mer.T / s->mer.N) * s->D)) + 1.0;
+  int C = std::min(8, s->ctx->sms / std::max(B, 1));
+  C = std::min(C, (int)std::ceil(rows / kThreads));
+  return std::max(C, 1);
+}
+
 void fill_pricing_args(const fbsdej_solver* s, const float* theta, int B, int B_global, PricingArgs& a) {
   std::memset(&a, 0, sizeof(a));
   a.B = B; a.N = s->N; a.G = pick_G(s, B); a.M = s->M > 0 ? s->M : 1;
+  a.C = pick_C(s, B, a.G);
   a.scheme = s->sch; a.one_net = s->one_net; a.has_jump = s->has_jump; a.use_netA = s->use_netA;
   a.has_y = s->has_y; a.zoff = s->zoff; a.has_z = s->has_z; a.feat_mode = s->feat_mode;
   a.stale_time = s->desc.stale_time;
@@ -306,8 +319,10 @@ int run_pass(fbsdej_solver* s, const float* theta, int B, int B_global, float* o
     fill_pricing_args(s, theta, B, B_global, a);
     const int ppb = kThreads / a.G;
     const int ntiles = (B + ppb - 1) / ppb;
-    grid_f = std::min(ntiles, s->ctx->sms * pricing_blocks_per_sm(s->model, s->D, s->HP, a, false));
-    if (with_grad) grid_b = std::min(ntiles, s->ctx->sms * pricing_blocks_per_sm(s->model, s->D, s->HP, a, true));
+    // a.C CTAs (one cluster) per tile when the batch is small
+    grid_f = a.C * std::min(ntiles, std::max(1, s->ctx->sms * pricing_blocks_per_sm(s->model, s->D, s->HP, a, false) / a.C));
+    if (with_grad)
+      grid_b = a.C * std::min(ntiles, std::max(1, s->ctx->sms * pricing_blocks_per_sm(s->model, s->D, s->HP, a, true) / a.C));
     if (ensure_grid(s, std::max(grid_f, grid_b))) return -2;
     a.lpart = s->lpart; a.gpart = s->gpart; a.trajY = trajY; a.trajZ = trajZ;
     if (launch_pricing(s->model, s->D, s->HP, a, grid_f, false, st)) return -1;

@@ -10,6 +10,7 @@ enum { SCH_GLOBAL = 0, SCH_MULTISTEP = 1, SCH_SUMLOCAL = 2 };
 
 struct PricingArgs {
   int B, N, G, M;             // local paths, time steps, threads per path, compensator sample count (mean denominator)
+  int C;                      // CTAs per path: a thread-block cluster splits the compensator samples (small batches; else 1)
   int scheme;                 // SCH_*
   int one_net;                // jump rows are evaluated by netA (MultiStep1 / SumLocal1)
   int has_jump;               // 0 for the *Reg solvers (no Z / Gam / compensator)

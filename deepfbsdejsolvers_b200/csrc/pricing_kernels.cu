@@ -12,8 +12,8 @@
 // Reference loss graphs: coupledPricing/SolversJumpDiff.py:22-44 (Global), :86-115/:162-190 (MultiStep1/2),
 // :236-269/:315-347 (SumLocal1/2), :391-415 (SumLocalReg), :461-481 (MultiStepReg); SolversPureJump.py same.
 #include "pricing.cuh"
-#include "tc_mlp.cuh"
 #include <type_traits>
+#include <cooperative_groups.h>
 
 namespace fbsdej {
 
@@ -27,43 +27,67 @@ __device__ __forceinline__ float group_allsum(float v, int G, float* red) {
   return block_sum(v, red);   // G == kThreads: one path per CTA
 }
 
-template <class Model, int HP, bool JUMP, bool TC>
+// Small batches (the reference's B = 10): a thread-block CLUSTER of C CTAs shares one path and splits its compensator
+// samples; the per-step partial sums are exchanged through distributed shared memory.  v[] is CTA-uniform on entry
+// (after block_sum); every CTA of the cluster leaves with the same sum, added in rank order.  Two slots alternate so
+// that one cluster barrier per call suffices (a slot is rewritten only after the next call's barrier).
+constexpr int kRedFloats = 8 + 2 * 16;
+template <int NV>
+__device__ __forceinline__ void cluster_allsum(float (&v)[NV], float* red, int& parity, int C) {
+  static_assert(NV <= 16, "slot width");
+  namespace cg = cooperative_groups;
+  cg::cluster_group cl = cg::this_cluster();
+  float* slot = red + 8 + 16 * parity;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) slot[k] = v[k];
+  }
+  cl.sync();
+  float s[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) s[k] = 0.0f;
+  for (int r = 0; r < C; ++r) {
+    const float* __restrict__ rs = cl.map_shared_rank(slot, r);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) s[k] += rs[k];
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = s[k];
+  parity ^= 1;
+}
+__device__ __forceinline__ unsigned cluster_rank() { return cooperative_groups::this_cluster().block_rank(); }
+
+template <class Model, int HP, bool JUMP>
 __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a) {
   constexpr int D = Model::D;
-  static_assert(!(TC && JUMP), "the tcgen05 path covers the compensator-free solvers");
   extern __shared__ __align__(1024) float smem[];
-  using TCF = TcForward<D + 2>;
   const bool two = JUMP && !a.one_net;
   float* swA = smem;
-  float* swB = swA + (TC ? TCF::FLOATS : net_smem_floats(a.netA, HP, false));
+  float* swB = swA + net_smem_floats(a.netA, HP, false);
   float* red = swB + (two ? net_smem_floats(a.netB, HP, false) : 0);
-  float* tb = red + 8;
+  float* tb = red + kRedFloats;
   using TL = Tiles<HP, JUMP ? NOP : 4>;
   TL t;
   NetView<HP> nvA, nvJ;
-  TCF tcf;
-  if constexpr (TC) {
-    tcf.init(smem, a.theta, a.netA);
-  } else {
-    t.carve(tb, false);
-    nvA = load_net<HP>(swA, a.theta, a.netA, false);
-    nvJ = two ? load_net<HP>(swB, a.theta, a.netB, false) : nvA;
-    zero_tiles(tb, TL::fwd_floats());
-  }
+  t.carve(tb, false);
+  nvA = load_net<HP>(swA, a.theta, a.netA, false);
+  nvJ = two ? load_net<HP>(swB, a.theta, a.netB, false) : nvA;
+  zero_tiles(tb, TL::fwd_floats());
 
   const int row = threadIdx.x;
   const int G = JUMP ? a.G : 1, ppb = kThreads / G, g = threadIdx.x % G;
+  const int C = JUMP ? a.C : 1;                             // CTAs per path (cluster size); C > 1 implies G == kThreads
+  const int crank = (JUMP && C > 1) ? (int)cluster_rank() : 0;
+  int cpar = 0;
   const size_t sB = (size_t)a.B;
   const float rdt = a.r * a.dt;
   float lsum = 0.0f;
   const int ntiles = (a.B + ppb - 1) / ppb;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (int tile = blockIdx.x / C; tile < ntiles; tile += gridDim.x / C) {
     const int p0 = tile * ppb + threadIdx.x / G;
     const bool valid = p0 < a.B;
     const int p = valid ? p0 : a.B - 1;
-    const bool writer = TC ? true : (valid && g == 0);   // TC: the padded rows of the last tile are written too (finite data)
-    using RL = RecLayout<D>;
-    float* const rec0 = TC ? a.rec + (size_t)tile * a.N * RL::NP * TR + row : nullptr;
+    const bool writer = valid && g == 0 && crank == 0;
     float X[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) X[k] = a.x0;
@@ -86,17 +110,7 @@ __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a)
         }
       }
       float y_net = 0.0f, zdw = 0.0f;
-      float* const rs = TC ? rec0 + (size_t)i * RL::NP * TR : nullptr;
-      if constexpr (TC) {
-        float in[TCF::K1];
-#pragma unroll
-        for (int j = 0; j < TCF::K1; ++j) in[j] = 0.0f;
-        in[0] = tf;
-#pragma unroll
-        for (int k = 0; k < D; ++k) in[1 + k] = X[k];
-        in[1 + D] = 1.0f;
-        y_net = tcf.eval(in);
-      } else if (a.use_netA) {
+      if (a.use_netA) {
         float in[HP];
 #pragma unroll
         for (int j = 0; j < HP; ++j) in[j] = 0.0f;
@@ -125,7 +139,7 @@ __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a)
         gam = t.out[tix(0, row)];
         const int nnz = a.jmc_nnz[i], n0 = a.jmc_n0[i];
         float csum = 0.0f;
-        for (int m = g; m <= nnz; m += G) {
+        for (int m = crank * G + g; m <= nnz; m += G * C) {
           float Jm[D];
           float w = 1.0f;
           if (m < nnz) {
@@ -144,6 +158,11 @@ __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a)
           }
         }
         csum = group_allsum(csum, G, red);
+        if (C > 1) {
+          float cs[1] = {csum};
+          cluster_allsum<1>(cs, red, cpar, C);
+          csum = cs[0];
+        }
         comp = csum / (float)a.M;
       }
       // ---- loss-graph bookkeeping -----------------------------------------------------------
@@ -153,18 +172,16 @@ __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a)
         Y = Y - a.dt * (-a.r * Y) + zdw + gam - comp;        // SolversJumpDiff.py:41
         Ysel = Y;                                            // the UPDATED Y feeds oneStepFrom (:43)
       } else {
-        if (a.trajY && valid && g == 0) a.trajY[(size_t)i * sB + p] = y_net;
+        if (a.trajY && writer) a.trajY[(size_t)i * sB + p] = y_net;
         const float ai = rdt * y_net + zdw + gam - comp;     // "toAdd" = -dt f(Y) + Z dW + Gam - mean(comp)
         if (a.scheme == SCH_MULTISTEP) {
-          if constexpr (TC) rs[RL::P_SCH * TR] = y_net - Cpre;
-          else if (writer) a.sch1[(size_t)i * sB + p] = y_net - Cpre;   // u_i ; F_i - g = u_i + (sum_all toAdd - g)
+          if (writer) a.sch1[(size_t)i * sB + p] = y_net - Cpre;   // u_i ; F_i - g = u_i + (sum_all toAdd - g)
           Cpre += ai;
         } else {
           if (i > 0) {
             const float rho = y_net - yprev - aprev;
             lloc = fmaf(rho, rho, lloc);
-            if constexpr (TC) (rs - RL::NP * TR)[RL::P_SCH * TR] = rho;
-            else if (writer) a.sch1[(size_t)(i - 1) * sB + p] = rho;
+            if (writer) a.sch1[(size_t)(i - 1) * sB + p] = rho;
           }
           yprev = y_net; aprev = ai;
         }
@@ -176,12 +193,7 @@ __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a)
       const float diff = Ysel - Ai;
       const float coup = a.aLin * fabsf(diff) * a.dt;
       const float sgn = a.aLin * a.dt * (diff > 0.0f ? 1.0f : (diff < 0.0f ? -1.0f : 0.0f));
-      if constexpr (TC) {
-        rs[RL::P_S * TR] = sgn;
-        rs[RL::P_DA * TR] = dAb;
-#pragma unroll
-        for (int k = 0; k < D; ++k) rs[(RL::P_X + k) * TR] = X[k];
-      } else if (writer) {
+      if (writer) {
         a.aux_s[(size_t)i * sB + p] = sgn;
         a.aux_dA[(size_t)i * sB + p] = dAb;
 #pragma unroll
@@ -190,8 +202,7 @@ __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a)
 #pragma unroll
       for (int k = 0; k < D; ++k) {
         const float E = expf(a.drift_dt + a.sig * dWv[k] + Jv[k]);
-        if constexpr (TC) rs[(RL::P_E + k) * TR] = E;
-        else if (!JUMP && writer) a.trajE[((size_t)i * D + k) * sB + p] = E;
+        if (!JUMP && writer) a.trajE[((size_t)i * D + k) * sB + p] = E;
         X[k] = X[k] * E + coup;
       }
     }
@@ -208,79 +219,70 @@ __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a)
         const float Dv = Cpre - gN;
         float se = 0.0f, s2 = 0.0f;
         for (int k = 0; k < a.N; ++k) {
-          float* const q = TC ? rec0 + ((size_t)k * RL::NP + RL::P_SCH) * TR : a.sch1 + (size_t)k * sB + p;
+          float* const q = a.sch1 + (size_t)k * sB + p;
           const float e = *q + Dv;
           *q = e;
           se += e;
           s2 = fmaf(e, e, s2);
         }
         lpath = s2 * (a.inv_B / (float)a.N);
-        if constexpr (TC) a.recN[((size_t)tile * RL::NPT + D) * TR + row] = se; else a.fin[p] = se;
-        if (a.trajY && valid) a.trajY[(size_t)a.N * sB + p] = gN;
+        a.fin[p] = se;
+        if (a.trajY) a.trajY[(size_t)a.N * sB + p] = gN;
       }
     } else {
       const float rho = gN - yprev - aprev;
       lloc = fmaf(rho, rho, lloc);
       lpath = lloc * a.inv_B;
-      if constexpr (TC) rec0[((size_t)(a.N - 1) * RL::NP + RL::P_SCH) * TR] = rho;
-      else if (writer) a.sch1[(size_t)(a.N - 1) * sB + p] = rho;
-      if (writer && valid && a.trajY) a.trajY[(size_t)a.N * sB + p] = gN;
+      if (writer) { a.sch1[(size_t)(a.N - 1) * sB + p] = rho; if (a.trajY) a.trajY[(size_t)a.N * sB + p] = gN; }
     }
     if (writer) {
 #pragma unroll
-      for (int k = 0; k < D; ++k) {
-        if constexpr (TC) a.recN[((size_t)tile * RL::NPT + k) * TR + row] = X[k];
-        else a.trajX[((size_t)a.N * D + k) * sB + p] = X[k];
-      }
-      if (valid) lsum += lpath;
+      for (int k = 0; k < D; ++k) a.trajX[((size_t)a.N * D + k) * sB + p] = X[k];
+      lsum += lpath;
     }
   }
-  if constexpr (TC) tcf.finish();
   const float tot = block_sum(lsum, red);
   if (threadIdx.x == 0) {
     a.lpart[blockIdx.x * 4] = tot;
     a.lpart[blockIdx.x * 4 + 1] = 0.0f; a.lpart[blockIdx.x * 4 + 2] = 0.0f; a.lpart[blockIdx.x * 4 + 3] = 0.0f;
   }
+  if (JUMP && C > 1) cooperative_groups::this_cluster().sync();   // no CTA leaves while a peer may still read its slots
 }
 
-template <class Model, int HP, bool JUMP, bool TC>
+template <class Model, int HP, bool JUMP>
 __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a) {
   constexpr int D = Model::D;
-  static_assert(!(TC && JUMP), "the tcgen05 path covers the compensator-free solvers");
   extern __shared__ __align__(1024) float smem[];
-  using TCB = TcBackward<D + 2>;
   const bool two = JUMP && !a.one_net;
   float* swA = smem;
-  float* swB = swA + (TC ? TCB::FLOATS : net_smem_floats(a.netA, HP, true));
+  float* swB = swA + net_smem_floats(a.netA, HP, true);
   float* red = swB + (two ? net_smem_floats(a.netB, HP, true) : 0);
-  float* tb = TC ? smem : red + 8;                  // TC: the gradient staging vector reuses the (dead) operand tiles
+  float* tb = red + kRedFloats;
   using TL = Tiles<HP, JUMP ? NOP : 4>;
   TL t;
   NetView<HP> nvA, nvJ;
   WGrad<HP> wgA, wgB;
-  TCB tcb;
-  if constexpr (TC) {
-    tcb.init(smem, a.theta, a.netA);
-  } else {
-    t.carve(tb, true);
-    nvA = load_net<HP>(swA, a.theta, a.netA, true);
-    nvJ = two ? load_net<HP>(swB, a.theta, a.netB, true) : nvA;
-    zero_tiles(tb, TL::bwd_floats());
-    wgA.init(nvA, t);
-    if (JUMP) wgB.init(nvJ, t);
-  }
+  t.carve(tb, true);
+  nvA = load_net<HP>(swA, a.theta, a.netA, true);
+  nvJ = two ? load_net<HP>(swB, a.theta, a.netB, true) : nvA;
+  zero_tiles(tb, TL::bwd_floats());
+  wgA.init(nvA, t);
+  if (JUMP) wgB.init(nvJ, t);
 
   const int row = threadIdx.x;
   const int G = JUMP ? a.G : 1, ppb = kThreads / G, g = threadIdx.x % G;
+  const int C = JUMP ? a.C : 1;
+  const int crank = (JUMP && C > 1) ? (int)cluster_rank() : 0;
+  int cpar = 0;
   const size_t sB = (size_t)a.B;
   const float invB = a.inv_B, invBN = a.inv_B / (float)a.N, rdt = a.r * a.dt;
   float y0g = 0.0f;
   const int ntiles = (a.B + ppb - 1) / ppb;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (int tile = blockIdx.x / C; tile < ntiles; tile += gridDim.x / C) {
     const int p0 = tile * ppb + threadIdx.x / G;
     const bool valid = p0 < a.B;
     const int p = valid ? p0 : a.B - 1;
-    const float msk = (valid && g == 0) ? 1.0f : 0.0f;   // rows that count for the main sites
+    const float msk = (valid && g == 0 && crank == 0) ? 1.0f : 0.0f;   // rows that count for the main sites
     const float vmsk = valid ? 1.0f : 0.0f;              // rows that count for the compensator
     float X[D], Xbar[D];
 #pragma unroll
@@ -361,18 +363,7 @@ __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a
 #pragma unroll
         for (int k = 0; k < (JUMP ? D : 1); ++k) dXacc[k] = 0.0f;
       }
-      if constexpr (TC) {
-        float in[TCB::K1], din[TCB::K1];
-#pragma unroll
-        for (int j = 0; j < TCB::K1; ++j) in[j] = 0.0f;
-        in[0] = tf;
-#pragma unroll
-        for (int k = 0; k < D; ++k) in[1 + k] = X[k];
-        in[1 + D] = 1.0f;
-        tcb.step(in, ybar * msk, din);
-#pragma unroll
-        for (int k = 0; k < D; ++k) Xbar[k] += din[1 + k];
-      } else if (a.use_netA) {
+      if (a.use_netA) {
 #pragma unroll
         for (int j = 0; j < HP; ++j) dx[j] = 0.0f;
         dx[0] = tf;
@@ -411,9 +402,9 @@ __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a
         __syncthreads();
         const int nnz = a.jmc_nnz[i], n0 = a.jmc_n0[i];
         const float cscale = -abar / (float)a.M * vmsk;
-        const int iters = (nnz + 1 + G - 1) / G;
+        const int iters = (nnz + 1 + G * C - 1) / (G * C);
         for (int it = 0; it < iters; ++it) {
-          const int m = it * G + g;
+          const int m = (it * C + crank) * G + g;
           float Jm[D];
           float w = 0.0f;
 #pragma unroll
@@ -436,7 +427,10 @@ __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a
           __syncthreads();
         }
 #pragma unroll
-        for (int k = 0; k < D; ++k) Xbar[k] += (G == 1) ? dXj[k] : group_allsum(dXj[k], G, red);
+        for (int k = 0; k < D; ++k) dXj[k] = (G == 1) ? dXj[k] : group_allsum(dXj[k], G, red);
+        if (C > 1) cluster_allsum<D>(dXj, red, cpar, C);
+#pragma unroll
+        for (int k = 0; k < D; ++k) Xbar[k] += dXj[k];
       }
       if (a.scheme == SCH_GLOBAL) Ybar *= (1.0f + rdt);
     }
@@ -446,63 +440,61 @@ __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a
   // ---- flush: registers -> smem gradient vector (external layout) -> this CTA's row of gpart ----------
   __syncthreads();
   float* sg = tb;
-  if constexpr (TC) {
-    if (tcb.pending_w) { tc::mbar_wait(tcb.bar_w, tcb.phase_w); tcb.phase_w ^= 1; tcb.pending_w = 0; }
-    __syncthreads();
-  }
   for (int e = threadIdx.x; e < a.P; e += blockDim.x) sg[e] = 0.0f;
   __syncthreads();
-  if constexpr (TC) {
-    tcb.flush(sg, a.netA);
-  } else {
-    wgA.flush(nvA, sg, a.netA.ext_off);
-    if (two) wgB.flush(nvJ, sg, a.netB.ext_off);
-  }
+  wgA.flush(nvA, sg, a.netA.ext_off);
+  if (two) wgB.flush(nvJ, sg, a.netB.ext_off);
   if (a.scheme == SCH_GLOBAL && threadIdx.x == 0) sg[a.y0_off] = y0tot;
   __syncthreads();
   float* grow = a.gpart + (size_t)blockIdx.x * a.P;
   for (int e = threadIdx.x; e < a.P; e += blockDim.x) grow[e] = sg[e];
+  if (JUMP && C > 1) cooperative_groups::this_cluster().sync();
 }
 
 // ---- launch glue ---------------------------------------------------------------------------------
 template <int HP>
 static size_t pricing_smem(const PricingArgs& a, bool backward) {
-  if (a.mma_mode == 1) {
-    if (backward) return reg_tc_backward_smem();
-    if (!getenv("FBSDEJ_OLD_TC_FWD")) return reg_tc_forward_smem();
-    const int k1 = (a.netA.nin + 1 + 3) & ~3;
-    return sizeof(float) * (size_t)(6144 + 1536 + k1 * 24 + 24 + 8 + 8);
-  }
+  if (a.mma_mode == 1) return backward ? reg_tc_backward_smem() : reg_tc_forward_smem();
   const bool two = a.has_jump && !a.one_net;
   const int w = net_smem_floats(a.netA, HP, backward) + (two ? net_smem_floats(a.netB, HP, backward) : 0);
   const int tl = a.has_jump ? (backward ? Tiles<HP, NOP>::bwd_floats() : Tiles<HP, NOP>::fwd_floats())
                             : (backward ? Tiles<HP, 4>::bwd_floats() : Tiles<HP, 4>::fwd_floats());
-  return sizeof(float) * (size_t)(w + 8 + tl);
+  return sizeof(float) * (size_t)(w + kRedFloats + tl);
 }
 
-template <class Model, int HP, bool JUMP, bool TC>
+template <class Model, int HP, bool JUMP>
 static int launch_one(const PricingArgs& a, int grid, bool backward, cudaStream_t st) {
   const size_t smem = pricing_smem<HP>(a, backward);
   if (smem > 227 * 1024) { set_error("pricing kernels: shared-memory footprint exceeds 227 KB"); return -1; }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  const int C = JUMP ? a.C : 1;
+  if (C > 1) {                                        // the CTAs of one path form a thread-block cluster
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  }
   if (!backward) {
-    auto kern = pricing_forward<Model, HP, JUMP, TC>;
+    auto kern = pricing_forward<Model, HP, JUMP>;
     FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kThreads, smem, st>>>(a);
-  } else if constexpr (!TC) {
-    auto kern = pricing_backward<Model, HP, JUMP, TC>;
+    FB_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+  } else {
+    auto kern = pricing_backward<Model, HP, JUMP>;
     FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kThreads, smem, st>>>(a);
+    FB_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
   }
   FB_CUDA(cudaGetLastError());
   return 0;
 }
 template <class Model, int HP>
 static int launch_pair(const PricingArgs& a, int grid, bool backward, cudaStream_t st) {
-  if (a.has_jump) return launch_one<Model, HP, true, false>(a, grid, backward, st);
-  if (a.mma_mode == 1 && backward) return launch_reg_tc_backward(std::is_same<Model, VGModel>::value ? 1 : 0, Model::D, a, grid, st);
-  if (a.mma_mode == 1 && !getenv("FBSDEJ_OLD_TC_FWD")) return launch_reg_tc_forward(std::is_same<Model, VGModel>::value ? 1 : 0, Model::D, a, grid, st);
-  if (a.mma_mode == 1) return launch_one<Model, HP, false, true>(a, grid, backward, st);
-  return launch_one<Model, HP, false, false>(a, grid, backward, st);
+  if (a.has_jump) return launch_one<Model, HP, true>(a, grid, backward, st);
+  if (a.mma_mode == 1) {   // compensator-free solvers on tcgen05 (reg_tc_kernels.cu)
+    const int model = std::is_same<Model, VGModel>::value ? 1 : 0;
+    return backward ? launch_reg_tc_backward(model, Model::D, a, grid, st) : launch_reg_tc_forward(model, Model::D, a, grid, st);
+  }
+  return launch_one<Model, HP, false>(a, grid, backward, st);
 }
 
 // A(iStep, X) for n states (component planes X[d][n]); the drop-in MertonJumpModel.A / VGmodel.A.
@@ -531,21 +523,19 @@ int launch_price(int model, int D, const PricingArgs& a, int iStep, const float*
   return 0;
 }
 
-template <class Model, int HP, bool JUMP, bool TC>
+template <class Model, int HP, bool JUMP>
 static int occ_one(const PricingArgs& a, bool backward) {
   const size_t smem = pricing_smem<HP>(a, backward);
   int nb = 0;
   cudaError_t e1, e2;
   if (!backward) {
-    auto kern = pricing_forward<Model, HP, JUMP, TC>;
-    e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem);
-  } else if constexpr (!TC) {
-    auto kern = pricing_backward<Model, HP, JUMP, TC>;
+    auto kern = pricing_forward<Model, HP, JUMP>;
     e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem);
   } else {
-    e1 = e2 = cudaSuccess; nb = 4;
+    auto kern = pricing_backward<Model, HP, JUMP>;
+    e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem);
   }
   if (e1 != cudaSuccess || e2 != cudaSuccess || nb < 1) {
     if (getenv("FBSDEJ_DEBUG"))
@@ -553,22 +543,15 @@ static int occ_one(const PricingArgs& a, bool backward) {
     (void)cudaGetLastError();
     nb = 1;
   }
-  if (getenv("FBSDEJ_DEBUG")) fprintf(stderr, "[fbsdej] occupancy TC=%d bwd=%d nb=%d smem=%zu\n", (int)TC, (int)backward, nb, smem);
-  if (TC) {
-    // The occupancy calculator reports 1 CTA/SM for kernels that allocate TMEM (it cannot know the column count).
-    // Residency is bounded by registers (<= 168 -> 3, <= 128 -> 4), shared memory and TMEM (512 / 128 | 32 columns).
-    const int by_smem = (int)((227 * 1024) / (smem + 1024));
-    nb = 4;
-    nb = nb > by_smem ? by_smem : nb;
-    nb = nb < 1 ? 1 : nb;
-  }
   return nb;
 }
 template <class Model, int HP>
 static int occ_pair(const PricingArgs& a, bool backward) {
-  if (a.has_jump) return occ_one<Model, HP, true, false>(a, backward);
-  if (a.mma_mode == 1) return occ_one<Model, HP, false, true>(a, backward);
-  return occ_one<Model, HP, false, false>(a, backward);
+  // tcgen05 kernels: 4 CTAs per SM by construction (<= 128 registers, <= 56 KB shared memory, 128 TMEM columns); the
+  // occupancy calculator does not know about TMEM
+  if (a.mma_mode == 1 && !a.has_jump) return 4;
+  if (a.has_jump) return occ_one<Model, HP, true>(a, backward);
+  return occ_one<Model, HP, false>(a, backward);
 }
 // resident CTAs per SM of the kernel that launch_pricing would run
 int pricing_blocks_per_sm(int model, int D, int HP, const PricingArgs& a, bool backward) {
