@@ -151,6 +151,37 @@ class NativeSolver:
         with torch.cuda.stream(self.ctx.stream):
             self.m.zero_(); self.v.zero_(); self.t.zero_()
 
+    # ---- checkpoint (params | m | v | t | iteration; the reference keeps nothing on disk) ---------------
+    def state_dict(self) -> dict:
+        """Everything a bit-exact resume needs: the Philox draws depend only on (seed, iteration, path id)."""
+        h = self.ctx.to_host
+        return {"theta": h(self.theta).numpy().copy(), "m": h(self.m).numpy().copy(), "v": h(self.v).numpy().copy(),
+                "t": h(self.t).numpy().copy(), "iteration": h(self.iteration).numpy().copy(),
+                "layout": np.array([self.model_kind, self.scheme, self.P, self.n_y0, self.M], dtype=np.int64)}
+
+    def load_state_dict(self, sd: dict) -> None:
+        lay = np.asarray(sd["layout"]).astype(np.int64)
+        mine = np.array([self.model_kind, self.scheme, self.P, self.n_y0, self.M], dtype=np.int64)
+        if not np.array_equal(lay, mine):
+            raise FbsdejError(f"checkpoint layout {lay.tolist()} does not match this solver {mine.tolist()} "
+                              "(model, scheme, parameter count, Y0 count, compensator samples)")
+        with torch.cuda.stream(self.ctx.stream):
+            self.theta.copy_(torch.from_numpy(np.asarray(sd["theta"], dtype=np.float32)))
+            self.m.copy_(torch.from_numpy(np.asarray(sd["m"], dtype=np.float32)))
+            self.v.copy_(torch.from_numpy(np.asarray(sd["v"], dtype=np.float32)))
+            self.t.copy_(torch.from_numpy(np.asarray(sd["t"], dtype=np.int32)))
+            self.iteration.copy_(torch.from_numpy(np.asarray(sd["iteration"], dtype=np.int32)))
+        self.ctx.sync()
+
+    def save_checkpoint(self, path: str, **extra) -> None:
+        np.savez(path, **self.state_dict(), **{k: np.asarray(v) for k, v in extra.items()})
+
+    def load_checkpoint(self, path: str) -> dict:
+        with np.load(path) as z:
+            sd = {k: z[k] for k in z.files}
+        self.load_state_dict(sd)
+        return sd
+
     def set_weights(self, w_hat: float, w_ind: float) -> None:
         check(lib.fbsdej_solver_set_weights(self.handle, w_hat, w_ind))
 

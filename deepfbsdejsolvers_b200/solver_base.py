@@ -173,5 +173,16 @@ class PricingSolverBase:
         self.pull_params()
         return self._result()
 
+    # checkpoint / resume
+    def save(self, path: str) -> None:
+        self.build().save_checkpoint(path, seed=self.seed, listY0=getattr(self, "listY0", []), lossList=getattr(self, "lossList", []))
+
+    def load(self, path: str) -> None:
+        sd = self.build().load_checkpoint(path)
+        self.seed = int(sd.get("seed", self.seed))
+        self.listY0 = [np.float32(x) for x in sd.get("listY0", [])]
+        self.lossList = [float(x) for x in sd.get("lossList", [])]
+        self.pull_params()
+
     def _result(self):
         return self.listY0, self.duration

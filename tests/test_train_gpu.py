@@ -51,3 +51,41 @@ def test_reg_solver_trains_to_closed_form(ctx):
     assert abs(closed - 0.2714569) < 2e-5
     assert solver.lossList[-1] < solver.lossList[0]
     assert abs(float(listY0[-1]) - closed) < 0.02, (listY0, closed)
+
+
+def test_checkpoint_resume_is_bit_exact(ctx, tmp_path):
+    """params | m | v | t | iteration on disk; counter-based increments make the resumed run identical to the uninterrupted one."""
+    B, lr, seed = 300, 3e-4, 7
+    p = dict(H.MERTON, N=8)
+    layout = H.pricing_layout("merton", "SumLocalReg", 10)
+    theta = H.random_theta(layout, 4)
+    a = H.native_pricing(ctx, "merton", p, "SumLocalReg", layout, d=10, limit=100, tensor_cores=True)
+    a.set_theta(theta); a.reset_optimizer()
+    a.train_steps(seed, B, 3, lr)
+    ctx.sync()
+    ck = str(tmp_path / "ck.npz")
+    a.save_checkpoint(ck)
+    a.train_steps(seed, B, 2, lr)
+    ctx.sync()
+    b = H.native_pricing(ctx, "merton", p, "SumLocalReg", layout, d=10, limit=100, tensor_cores=True)
+    b.load_checkpoint(ck)
+    b.train_steps(seed, B, 2, lr)
+    ctx.sync()
+    assert np.array_equal(a.get_theta(), b.get_theta())
+    c = H.native_pricing(ctx, "merton", p, "MultiStepReg", layout, d=10, limit=100, tensor_cores=True)
+    with pytest.raises(Exception):
+        c.load_checkpoint(ck)
+
+
+def test_driver_scripts_run(ctx, tmp_path, monkeypatch):
+    """The mainMerton / mainVG / mainMFGComparison command lines on a tiny budget."""
+    monkeypatch.chdir(tmp_path)
+    from deepfbsdejsolvers_b200.coupledPricing import mainMerton, mainVG
+    from deepfbsdejsolvers_b200.coupledMFG import mainMFGComparison
+    cols = mainMerton.main(["--nEpochExt", "2", "--nEpoch", "3", "--batchSize", "4", "--methods", "Global,SumLocal1,SumMultiStepReg"])
+    assert abs(cols["Y0_closed_formula"][0] - 0.2714569) < 2e-5 and len(cols["Y0_Global"]) == 2
+    cols = mainVG.main(["--nEpochExt", "2", "--nEpoch", "3", "--batchSize", "4", "--methods", "Global,SumLocalReg"])
+    assert abs(cols["Y0_closed_formula"][0] - 0.1331402) < 2e-5 and np.isfinite(cols["loss_Global"]).all()
+    hY0, Y0 = mainMFGComparison.main(["--nEpochExt", "2", "--nEpoch", "3", "--batchSize", "16", "--methods", "Global,SumLocalReg"])
+    assert len(hY0) == 2 and len(Y0[0]) == 2 and np.isfinite(np.array(Y0)).all()
+    assert (tmp_path / "merton_Y0.csv").exists() and (tmp_path / "Y0List.csv").exists()
