@@ -68,6 +68,35 @@ class SolverBase:
         yi = s.net_forward(1, np.array([[0.0, q0, mm.S0, q0, mm.S0, mm.R0]], dtype=np.float32))[0, 0]
         return float(yh), float(yi)
 
+    # ---- diagnostics (MFGSolvers.py:118-178, 296-318, 436-459, 581-602, 727-748): forward-only replays of the trained
+    # networks on fresh increments; the sweep itself is the forward kernel with its trajectory dump -----------------------
+    SEED_DIAG = 0x64696167
+
+    def _replay(self, nbSimul: int):
+        s = self.build()
+        self._ndiag = getattr(self, "_ndiag", 0) + 1
+        s.simulate(self.seed ^ self.SEED_DIAG, self._ndiag, nbSimul)
+        out, tx, ty, _ = s.loss(nbSimul, traj=True)          # tx: (hS, S) [N+1, 2, B]; ty: (hY, Y) [N+1, 2, B]
+        return s, out, tx.astype(np.float64), ty.astype(np.float64)
+
+    def simulateGlobalErr(self, nbSimul):
+        """(mean cost of the projected player, mean cost of the individual player, terminal mismatch): cost =
+        sum_i dt f(S_i) + g(S_N) with f(U) = C U, g(X) = h1 + h2 X (MFGModel.py:92-98)."""
+        s, out, tx, ty = self._replay(nbSimul)
+        mm = self.mathModel
+        N, dt = s.N, float(mm.T) / s.N
+        run = dt * float(mm.C) * tx[:N].sum(axis=0)                                   # [2, B]
+        gN = float(mm.h1) + float(mm.h2) * tx[N]                                      # [2, B]
+        cost = (run + gN).mean(axis=1)
+        last = ty[N] if self.SCHEME == L.GLOBAL else ty[N - 1]                       # others compare the LAST net output (:318)
+        mismatch = float(((last - gN) ** 2).mean(axis=1).sum())
+        return float(cost[0]), float(cost[1]), mismatch
+
+    def followS(self, nbSimul):
+        """Mean and (population) standard deviation of hS and S at every time step (MFGSolvers.py:148-178)."""
+        _, _, tx, _ = self._replay(nbSimul)
+        return (list(tx[:, 0].mean(axis=1)), list(tx[:, 0].std(axis=1)), list(tx[:, 1].mean(axis=1)), list(tx[:, 1].std(axis=1)))
+
     def _mask(self, which: str) -> torch.Tensor:
         s = self.native
         m = np.zeros(s.P, dtype=np.float32)

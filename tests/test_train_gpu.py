@@ -89,3 +89,28 @@ def test_driver_scripts_run(ctx, tmp_path, monkeypatch):
     hY0, Y0 = mainMFGComparison.main(["--nEpochExt", "2", "--nEpoch", "3", "--batchSize", "16", "--methods", "Global,SumLocalReg"])
     assert len(hY0) == 2 and len(Y0[0]) == 2 and np.isfinite(np.array(Y0)).all()
     assert (tmp_path / "merton_Y0.csv").exists() and (tmp_path / "Y0List.csv").exists()
+
+
+@pytest.mark.parametrize("name", ["SolverGlobalFBSDE", "SolverSumLocalFBSDE"])
+def test_mfg_diagnostics(ctx, name):
+    """simulateGlobalErr / followS (MFGSolvers.py:118-178) are reductions of the forward kernel's trajectory
+    dump (itself parity-tested in test_parity_gpu.py::test_mfg): shapes, the initial state, and the identity
+    cost = dt C sum_i mean(S_i) + h1 + h2 mean(S_N) between the two diagnostics (independent draws, Monte-Carlo tolerance)."""
+    from deepfbsdejsolvers_b200 import coupledMFG as cm, set_seed
+    set_seed(2)
+    P = H.mfg_params(1)
+    mm = cm.ModelCoupledFBSDE(**P)
+    wh, wi, method = ((2, 3, "Global") if name == "SolverGlobalFBSDE" else (3, 4, "SumLocal"))
+    km = cm.kerasModels(cm.Net_hat, cm.Net, method, wh, wi, [20, 20], [22, 22], "tanh", "tanh")
+    solver = getattr(cm, name)(mm, km, 1e-3, "ON", ctx=ctx)
+    solver.train(64, 128, 5, 1)
+    nb = 40000
+    c_hat, c_ind, mismatch = solver.simulateGlobalErr(nb)
+    ah, sh, ai, si = solver.followS(nb)
+    N = solver.native.N
+    assert len(ah) == N + 1 and len(si) == N + 1 and np.isfinite([c_hat, c_ind, mismatch]).all() and mismatch >= 0
+    assert abs(ah[0] - P["S0"]) < 1e-7 and sh[0] < 1e-7
+    dt = P["T"] / N
+    for cost, aver in ((c_hat, ah), (c_ind, ai)):
+        ident = dt * P["C"] * float(np.sum(aver[:N])) + P["h1"] + P["h2"] * float(aver[N])
+        assert abs(cost - ident) <= 0.02 * max(1.0, abs(ident)), (cost, ident)
