@@ -39,14 +39,14 @@ namespace bwd {
 constexpr int CH = 128;                       // uint4 per chunk (128 rows x 16 bytes)
 constexpr int XA_HI = 0, XA_LO = 2 * CH, H1_HI = 4 * CH, H2_HI = 7 * CH, H1_LO = 10 * CH, H2_LO = 13 * CH, D2_HI = 16 * CH,
               D2_LO = 19 * CH, D1_HI = H2_HI, D1_LO = H1_LO, W_BASE = 22 * CH;
-constexpr int W1B_HI = W_BASE, W1B_LO = W1B_HI + 2 * NB, W2B_HI = W1B_LO + 2 * NB, W2B_LO = W2B_HI + 4 * NB,
-              WTB_HI = W2B_LO + 4 * NB, WTB_LO = WTB_HI + 4 * NB, W1T_HI = WTB_LO + 4 * NB, W1T_LO = W1T_HI + 4 * 16,
-              U4_END = W1T_LO + 4 * 16;
+// B operands of the layer GEMMs, hi and lo copies STACKED ALONG N inside every K chunk: [k / 8][n' ][8 bf16] with
+// n' = n (hi) for n' < NH and n' - NH (lo) above; NH = 24 (W1, W2, W2^T) or 16 (W1^T)
+constexpr int W1B = W_BASE, W2B = W1B + 2 * 2 * NB, WTB = W2B + 4 * 2 * NB, W1T = WTB + 4 * 2 * NB, U4_END = W1T + 4 * 2 * 16;
 constexpr int OFF_W3 = U4_END * 4;            // float offsets after the uint4 region
 constexpr int OFF_BAR = OFF_W3 + 24;          // two mbarriers (8-byte aligned) + the TMEM base slot
 constexpr int SMEM_FLOATS = OFF_BAR + 8;
 static_assert((OFF_BAR % 2) == 0, "mbarrier alignment");
-constexpr uint32_t C_ACC = 0, C_W1 = 32, C_W2 = 80, NCOLS = 128;   // ACC 32 | WG1 48 | WG2 48 columns
+constexpr uint32_t C_ACC = 0, C_W1 = 48, C_W2 = 80, NCOLS = 128;   // ACC 48 | WG1 32 | WG2 48 columns
 constexpr int COL_DOUT = 23;                  // spare column of D2 that carries dL/dy through WG2 (needs H <= 22)
 }  // namespace bwd
 
@@ -59,25 +59,41 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) 
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
-// D[cols of ACC] = A (K-major, 128 rows x 16 KS) * B ([n][k], NBR n-rows per stored chunk), N = NN
-template <int KS, int NN, int NBR>
-__device__ __forceinline__ void gemm_k(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo) {
-  constexpr uint32_t id = tc::idesc_bf16(128, NN, false, false);
+// Layer GEMM, bf16x3 in TWO MMAs per 16-wide K slice: D[:, 0 .. 2 NH) = A_hi [B_hi | B_lo] (N = 2 NH), then
+// D[:, 0 .. N2) += A_lo [B_hi | ..] (N2 = NH rounded up to 16; the columns beyond NH pick up lo.lo terms, which belong to
+// the exact product).  The caller adds the column blocks [0, NH) and [NH, 2 NH) when it reads the accumulator.
+// A: K-major tile (128 rows); B: [k / 8][2 NH n-rows][8 bf16].
+template <int KS, int NH>
+__device__ __forceinline__ void gemm_k(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b) {
+  constexpr uint32_t id1 = tc::idesc_bf16(128, 2 * NH, false, false), id2 = tc::idesc_bf16(128, (NH + 15) / 16 * 16, false, false);
+  constexpr uint32_t chunk = 2 * NH * 16;
 #pragma unroll
   for (int s = 0; s < KS; ++s) {
-    const uint64_t dah = tc::smem_desc(a_hi + s * 4096, 2048, 128), dal = tc::smem_desc(a_lo + s * 4096, 2048, 128);
-    const uint64_t dbh = tc::smem_desc(b_hi + s * (2 * NBR * 16), NBR * 16, 128), dbl = tc::smem_desc(b_lo + s * (2 * NBR * 16), NBR * 16, 128);
-    tc::mma_bf16(tmem_d, dah, dbh, id, s > 0 ? 1u : 0u);
-    tc::mma_bf16(tmem_d, dal, dbh, id, 1u);
-    tc::mma_bf16(tmem_d, dah, dbl, id, 1u);
+    const uint64_t db = tc::smem_desc(b + s * 2 * chunk, chunk, 128);
+    tc::mma_bf16(tmem_d, tc::smem_desc(a_hi + s * 4096, 2048, 128), db, id1, s > 0 ? 1u : 0u);
+    tc::mma_bf16(tmem_d, tc::smem_desc(a_lo + s * 4096, 2048, 128), db, id2, 1u);
+  }
+}
+// this thread's row of a layer GEMM result: v[j] = D[j] + D[NH + j], j < NJ (NJ a multiple of 8)
+template <int NH, int NJ>
+__device__ __forceinline__ void load_acc(uint32_t lane_base, float (&v)[NJ]) {
+#pragma unroll
+  for (int c8 = 0; c8 < NJ / 8; ++c8) {
+    float p8[8], q8[8];
+    tc::tmem_ld8(lane_base + 8 * c8, p8);
+    tc::tmem_ld8(lane_base + NH + 8 * c8, q8);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[8 * c8 + q] = p8[q] + q8[q];
   }
 }
 // Weight-gradient GEMM over the 128 rows of the tile (rows are K, both operands MN-major).  The hi and lo copies of A
 // are contiguous along M and those of B along N, so ONE MMA per 16-row slice forms all four hi/lo cross products in
 // separate accumulator blocks:  D[m][n], m in [A_hi features | A_lo features], n in [B_hi | B_lo] (24 columns each).
 // The three blocks that matter (hi.hi, hi.lo, lo.hi) are added when the accumulators are read at the end of the kernel.
+template <int NN>
 __device__ __forceinline__ void gemm_rows_stacked(uint32_t tmem_d, uint32_t a, uint32_t b, uint32_t acc0) {
-  constexpr uint32_t id = tc::idesc_bf16(128, 48, true, true);
+  constexpr uint32_t id = tc::idesc_bf16(128, NN, true, true);
 #pragma unroll
   for (int s = 0; s < 8; ++s)                       // 128 rows = 8 x 16
     tc::mma_bf16(tmem_d, tc::smem_desc(a + s * 256, 128, 2048), tc::smem_desc(b + s * 256, 128, 2048), id, (s > 0) ? 1u : acc0);
@@ -115,44 +131,34 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
   {
     const float* __restrict__ th = a.theta + a.netA.ext_off;
     const int n1 = nin * H, n2 = n1 + H, n3 = n2 + H * H, n4 = n3 + H, n5 = n4 + H;
-    unsigned short* const w1h = reinterpret_cast<unsigned short*>(u4 + W1B_HI);
-    unsigned short* const w1l = reinterpret_cast<unsigned short*>(u4 + W1B_LO);
-    unsigned short* const w2h = reinterpret_cast<unsigned short*>(u4 + W2B_HI);
-    unsigned short* const w2l = reinterpret_cast<unsigned short*>(u4 + W2B_LO);
-    unsigned short* const wth = reinterpret_cast<unsigned short*>(u4 + WTB_HI);
-    unsigned short* const wtl = reinterpret_cast<unsigned short*>(u4 + WTB_LO);
-    unsigned short* const w1th = reinterpret_cast<unsigned short*>(u4 + W1T_HI);
-    unsigned short* const w1tl = reinterpret_cast<unsigned short*>(u4 + W1T_LO);
+    unsigned short* const w1 = reinterpret_cast<unsigned short*>(u4 + W1B);
+    unsigned short* const w2 = reinterpret_cast<unsigned short*>(u4 + W2B);
+    unsigned short* const wt = reinterpret_cast<unsigned short*>(u4 + WTB);
+    unsigned short* const w1t = reinterpret_cast<unsigned short*>(u4 + W1T);
+    // element (n, k) of a stacked B operand with NH n-rows per copy: hi at n, lo at NH + n
+    auto put = [](unsigned short* w, int NH, int n, int k, uint32_t hi, uint32_t lo) {
+      w[((k >> 3) * 2 * NH + n) * 8 + (k & 7)] = (unsigned short)hi;
+      w[((k >> 3) * 2 * NH + NH + n) * 8 + (k & 7)] = (unsigned short)lo;
+    };
     const float one_in = ACT == ACT_TANH ? 20.0f : 1.0f;   // act(one_in) == 1 exactly: the constant-1 unit of H1 / H2
     for (int e = row; e < n5 + 2; e += kThreads) {
       uint32_t hi, lo;
       if (e < n2) {                                   // W1[i][j]: layer-1 B operand [n = j][k = i]; the time row (i = 0) and
         const int i = e < n1 ? e / H : nin, j = e < n1 ? e % H : e - n1;   // b1 (i = nin) live in the per-step effective bias
         tc::split_bf16(th[e], hi, lo);
-        if (i >= 1 && i < nin) {
-          w1h[((i >> 3) * NB + j) * 8 + (i & 7)] = (unsigned short)hi;
-          w1l[((i >> 3) * NB + j) * 8 + (i & 7)] = (unsigned short)lo;
-        }
-        if (i < nin) {                                // input-gradient B operand [n = i][k = j]
-          w1th[((j >> 3) * 16 + i) * 8 + (j & 7)] = (unsigned short)hi;
-          w1tl[((j >> 3) * 16 + i) * 8 + (j & 7)] = (unsigned short)lo;
-        }
+        if (i >= 1 && i < nin) put(w1, NB, j, i, hi, lo);
+        if (i < nin) put(w1t, 16, i, j, hi, lo);      // input-gradient B operand [n = i][k = j]
       } else if (e < n4) {                            // W2[k][j], b2[j] (k = H): layer-2 B operand [n = j][k]
         const int k = e < n3 ? (e - n2) / H : H, j = e < n3 ? (e - n2) % H : e - n3;
         tc::split_bf16(th[e], hi, lo);
-        w2h[((k >> 3) * NB + j) * 8 + (k & 7)] = (unsigned short)hi;
-        w2l[((k >> 3) * NB + j) * 8 + (k & 7)] = (unsigned short)lo;
-        if (k < H) {                                  // W2^T: B operand [n = k][k' = j]
-          wth[((j >> 3) * NB + k) * 8 + (j & 7)] = (unsigned short)hi;
-          wtl[((j >> 3) * NB + k) * 8 + (j & 7)] = (unsigned short)lo;
-        }
+        put(w2, NB, j, k, hi, lo);
+        if (k < H) put(wt, NB, k, j, hi, lo);         // W2^T: B operand [n = k][k' = j]
       } else if (e < n5) {
         w3s[e - n4] = th[e];                          // W3[k][0], k < H  (entries >= H stay 0: no delta for the constant unit)
       } else if (e == n5) {                           // (the constant-1 unit of H1 is written with the effective bias)
       } else {                                        // the constant-1 unit of H2: act(one_in * 1) == 1
         tc::split_bf16(one_in, hi, lo);
-        w2h[((H >> 3) * NB + H) * 8 + (H & 7)] = (unsigned short)hi;
-        w2l[((H >> 3) * NB + H) * 8 + (H & 7)] = (unsigned short)lo;
+        put(w2, NB, H, H, hi, lo);
       }
     }
   }
@@ -167,7 +173,7 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
   // thread j <= H owns the effective layer-1 bias of hidden unit j: c_j(t) = t W1[0][j] + b1[j] (fp32, then split)
   float w0 = 0.0f, b1v = 0.0f;
   if (row < H) { w0 = a.theta[a.netA.ext_off + row]; b1v = a.theta[a.netA.ext_off + nin * H + row]; }
-  const int bias_idx = ((nin >> 3) * NB + row) * 8 + (nin & 7);
+  const int bias_idx = ((nin >> 3) * 2 * NB + row) * 8 + (nin & 7);   // hi copy; the lo copy is NB n-rows further
   const uint32_t sbase = tc::smem_u32(u4);
   auto sa = [&](int off_u4) { return sbase + (uint32_t)off_u4 * 16u; };
   uint32_t phase_f = 0, phase_w = 0, pending_w = 0, started = 0;
@@ -254,32 +260,30 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
         if (row <= H) {
           uint32_t hi, lo;
           tc::split_bf16(row < H ? fmaf(tf, w0, b1v) : (ACT == ACT_TANH ? 20.0f : 1.0f), hi, lo);
-          reinterpret_cast<unsigned short*>(u4 + W1B_HI)[bias_idx] = (unsigned short)hi;
-          reinterpret_cast<unsigned short*>(u4 + W1B_LO)[bias_idx] = (unsigned short)lo;
+          reinterpret_cast<unsigned short*>(u4 + W1B)[bias_idx] = (unsigned short)hi;
+          reinterpret_cast<unsigned short*>(u4 + W1B)[bias_idx + NB * 8] = (unsigned short)lo;
         }
       }
       publish();
       if (warp == 0 && issuer) {
         tc::tc_fence_after();
-        gemm_k<1, 32, NB>(tmem + C_ACC, sa(XA_HI), sa(XA_LO), sa(W1B_HI), sa(W1B_LO));
+        gemm_k<1, NB>(tmem + C_ACC, sa(XA_HI), sa(XA_LO), sa(W1B));
         tc::mma_commit(bar_f);
       }
       wait_f();
       // ---- h1 -> L2 ---------------------------------------------------------------------------------------------
       float h1[24];
+      load_acc<NB, 24>(lane_base + C_ACC, h1);
 #pragma unroll
       for (int c8 = 0; c8 < 3; ++c8) {
-        float t8[8];
-        tc::tmem_ld8(lane_base + C_ACC + 8 * c8, t8);
-        tc::tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 8; ++q) h1[8 * c8 + q] = actf<ACT>(t8[q]);
+        for (int q = 0; q < 8; ++q) h1[8 * c8 + q] = actf<ACT>(h1[8 * c8 + q]);
         tc::store_bf16x8(u4 + H1_HI, u4 + H1_LO, c8, row, h1 + 8 * c8);
       }
       publish();
       if (warp == 1 && issuer) {
         tc::tc_fence_after();
-        gemm_k<2, 32, NB>(tmem + C_ACC, sa(H1_HI), sa(H1_LO), sa(W2B_HI), sa(W2B_LO));
+        gemm_k<2, NB>(tmem + C_ACC, sa(H1_HI), sa(H1_LO), sa(W2B));
         tc::mma_commit(bar_f);
       }
       wait_f();
@@ -287,8 +291,14 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
 #pragma unroll
       for (int c8 = 0; c8 < 3; ++c8) {
         float t8[8], d2[8];
-        tc::tmem_ld8(lane_base + C_ACC + 8 * c8, t8);
-        tc::tmem_ld_wait();
+        {
+          float q8[8];
+          tc::tmem_ld8(lane_base + C_ACC + 8 * c8, t8);
+          tc::tmem_ld8(lane_base + C_ACC + NB + 8 * c8, q8);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) t8[q] += q8[q];
+        }
         const float4 wa = ld4(w3s + 8 * c8), wb = ld4(w3s + 8 * c8 + 4);
         const float w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
@@ -304,27 +314,28 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
       publish();
       if (warp == 2 && issuer) {
         tc::tc_fence_after();
-        gemm_rows_stacked(tmem + C_W2, sa(H1_HI), sa(D2_HI), started ? 1u : 0u);   // [H1 | H2 (hi) | H1 | H2 (lo)]^T [D2 hi | lo]
-        gemm_k<2, 32, NB>(tmem + C_ACC, sa(D2_HI), sa(D2_LO), sa(WTB_HI), sa(WTB_LO));
+        gemm_rows_stacked<48>(tmem + C_W2, sa(H1_HI), sa(D2_HI), started ? 1u : 0u);   // [H1 | H2 (hi) | H1 | H2 (lo)]^T [D2 hi | lo]
+        gemm_k<2, NB>(tmem + C_ACC, sa(D2_HI), sa(D2_LO), sa(WTB));
         tc::mma_commit(bar_f);
       }
       wait_f();
       // ---- delta 1 -> DX, WG1 ---------------------------------------------------------------------------------
 #pragma unroll
       for (int c8 = 0; c8 < 3; ++c8) {
-        float t8[8];
+        float t8[8], q8[8];
         tc::tmem_ld8(lane_base + C_ACC + 8 * c8, t8);
+        tc::tmem_ld8(lane_base + C_ACC + NB + 8 * c8, q8);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 8; ++q) t8[q] *= dactf<ACT>(h1[8 * c8 + q]);
+        for (int q = 0; q < 8; ++q) t8[q] = (t8[q] + q8[q]) * dactf<ACT>(h1[8 * c8 + q]);
         tc::store_bf16x8(u4 + D1_HI, u4 + D1_LO, c8, row, t8);
       }
       publish();
       if (warp == 3 && issuer) {
         tc::tc_fence_after();
-        gemm_k<2, 16, 16>(tmem + C_ACC, sa(D1_HI), sa(D1_LO), sa(W1T_HI), sa(W1T_LO));
+        gemm_k<2, 16>(tmem + C_ACC, sa(D1_HI), sa(D1_LO), sa(W1T));
         tc::mma_commit(bar_f);
-        gemm_rows_stacked(tmem + C_W1, sa(XA_HI), sa(D1_HI), started ? 1u : 0u);   // [X hi | X lo]^T [D1 hi | lo]
+        gemm_rows_stacked<32>(tmem + C_W1, sa(D1_HI), sa(XA_HI), started ? 1u : 0u);   // [D1 hi | D1 lo]^T [X hi | X lo] = dW1^T
         tc::mma_commit(bar_w);
       }
       started = 1;
@@ -332,13 +343,10 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
       if (i > 0) load_step(i - 1);
       wait_f();
       {
-        float t8[8];
-        tc::tmem_ld8(lane_base + C_ACC, t8);
-        float u8[8];
-        if (D > 7) tc::tmem_ld8(lane_base + C_ACC + 8, u8);
-        tc::tmem_ld_wait();
+        float dx[16];
+        load_acc<16, (D > 7 ? 16 : 8)>(lane_base + C_ACC, reinterpret_cast<float (&)[D > 7 ? 16 : 8]>(dx));
 #pragma unroll
-        for (int k = 0; k < D; ++k) Xbar[k] += (1 + k < 8) ? t8[(1 + k) & 7] : u8[(1 + k - 8) & 7];
+        for (int k = 0; k < D; ++k) Xbar[k] += dx[1 + k];
       }
       tc::tc_fence_before();     // orders these TMEM reads before the next step's first MMA (via its publish barrier)
     }
@@ -357,7 +365,7 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
     __syncthreads();
     if (started) {
 #pragma unroll
-      for (int c8 = 0; c8 < 6; ++c8) {
+      for (int c8 = 0; c8 < (pass == 0 ? 4 : 6); ++c8) {
         float v[8];
         tc::tmem_ld8(lane_base + (pass == 0 ? C_W1 : C_W2) + 8 * c8, v);
         tc::tmem_ld_wait();
@@ -366,10 +374,10 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
       }
     }
     __syncthreads();
-    if (started && pass == 0) {                        // lanes: X hi features 0..15, X lo features 16..31
+    if (started && pass == 0) {                        // lanes: D1 hi j, D1 lo 24 + j; columns: X hi i, X lo 16 + i
       for (int e = row; e < (nin + 1) * H; e += kThreads) {
         const int i = e / H, j = e % H;                // i = nin: b1
-        g[e] = S[i * SW + j] + S[i * SW + 24 + j] + S[(16 + i) * SW + j];
+        g[e] = S[j * SW + i] + S[j * SW + 16 + i] + S[(24 + j) * SW + i];
       }
     } else if (started) {                              // lanes: H1 hi 0..23, H2 hi 24..47, H1 lo 48..71, H2 lo 72..95
       for (int e = row; e < (H + 1) * H; e += kThreads) {
