@@ -92,3 +92,21 @@ def test_tensor_core_path_vg(ctx):
     s.set_theta(theta)
     s.set_noise(B, None, H.to_planes(noise["J"]), None)
     _check(s, B, l64, g64, g32, aux64, 1)
+
+
+@pytest.mark.parametrize("act,B,Hn", [("relu", 37, 21), ("tanh", 129, 16), ("relu", 260, 22)])
+def test_tensor_core_path_shapes_and_relu(ctx, act, B, Hn):
+    """Edge shapes of the tcgen05 kernels: fewer paths than one 128-row tile, one path into the second tile, the widest and a
+    narrow hidden layer, ReLU (whose constant-1 unit and masks take the other branch of the kernels)."""
+    d, scheme = 10, "SumLocalReg"
+    p = dict(H.MERTON, N=6)
+    om = MertonOracle(aLin=H.ALIN, limit=100, d=d, **p)
+    layout = H.pricing_layout("merton", scheme, d, H=Hn, act=act)
+    theta = H.random_theta(layout, 31)
+    noise = H.merton_noise(om, B, 0, seed=32, with_jmc=False)
+    l32, g32, _ = H.oracle_pricing(om, scheme, layout, theta, noise, B)
+    l64, g64, aux64 = H.oracle_pricing(om, scheme, layout, theta, noise, B, dtype=torch.float64)
+    s = H.native_pricing(ctx, "merton", p, scheme, layout, d=d, limit=100, tensor_cores=True)
+    s.set_theta(theta)
+    s.set_noise(B, H.to_planes(noise["dW"]), H.to_planes(noise["J"]), None)
+    _check(s, B, l64, g64, g32, aux64, d)
