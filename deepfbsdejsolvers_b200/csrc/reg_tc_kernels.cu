@@ -543,14 +543,16 @@ __global__ void __launch_bounds__(kThreads, 4) reg_forward_tc(const PricingArgs 
 #pragma unroll
         for (int k = 0; k < D; ++k) xin[1 + k] = X[k];
         xin[1 + D] = 1.0f;
-        store_tf32x8(lane_base, 0, xin);
-        store_tf32x8(lane_base, 1, xin + 8);
         if (row <= H) {
           float hi, lo;
           tc::split_tf32(row < H ? fmaf(tf, w0, b1v) : one_in, hi, lo);
           smem[W1B_HI + bias_idx] = hi;
           smem[W1B_LO + bias_idx] = lo;
         }
+        // the TMEM stores go last, right before the wait::st of publish_tmem(): tcgen05.st reads its source registers
+        // asynchronously, so any instruction that reuses one of them would stall until the store has drained
+        store_tf32x8(lane_base, 0, xin);
+        store_tf32x8(lane_base, 1, xin + 8);
       }
       publish_tmem();
       if (warp == 0 && issuer) {
