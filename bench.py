@@ -119,7 +119,7 @@ def cpu_iteration_factory(a, M, B_cpu):
         loss = pricing_loss(om, a.solver, layout, theta, noise, B_cpu)
         loss.backward()
         opt.step(theta.data, theta.grad)
-        return float(loss)
+        return float(loss.detach())
     return it
 
 

@@ -102,7 +102,7 @@ def oracle_pricing(model, scheme, layout, theta, noise, B, dtype=torch.float32, 
     loss = pricing_loss(model, scheme, layout, th, nz, B, stale_time=stale_time, aux=aux)
     loss.backward()
     model.dtype = old
-    return float(loss), th.grad.double().numpy(), {k: v.double().numpy() for k, v in aux.items()}
+    return float(loss.detach()), th.grad.double().numpy(), {k: v.double().numpy() for k, v in aux.items()}
 
 
 def oracle_mfg(model, scheme, layout, theta, noise, B, dtype=torch.float32, w=(1.0, 1.0)):
@@ -114,7 +114,7 @@ def oracle_mfg(model, scheme, layout, theta, noise, B, dtype=torch.float32, w=(1
     lh, li = mfg_loss(model, scheme, layout, th, nz, B, aux=aux)
     (w[0] * lh + w[1] * li).backward()
     model.dtype = old
-    return (float(lh), float(li)), th.grad.double().numpy(), {k: v.double().numpy() for k, v in aux.items()}
+    return (float(lh.detach()), float(li.detach())), th.grad.double().numpy(), {k: v.double().numpy() for k, v in aux.items()}
 
 
 # ---- native side --------------------------------------------------------------------------------------------
