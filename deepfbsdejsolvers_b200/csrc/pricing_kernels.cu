@@ -21,6 +21,7 @@ int launch_reg_tc_backward(int model, int D, const PricingArgs& a, int grid, cud
 int launch_reg_tc_forward(int model, int D, const PricingArgs& a, int grid, cudaStream_t st);
 size_t reg_tc_backward_smem();
 size_t reg_tc_forward_smem();
+int reg_tc_forward_occupancy(int B, int sms);
 
 __device__ __forceinline__ float group_allsum(float v, int G, float* red) {
   if (G <= 32) return group_sum_shfl(v, G);
@@ -547,9 +548,14 @@ static int occ_one(const PricingArgs& a, bool backward) {
 }
 template <class Model, int HP>
 static int occ_pair(const PricingArgs& a, bool backward) {
-  // tcgen05 kernels: 4 CTAs per SM by construction (<= 128 registers, <= 56 KB shared memory, 128 TMEM columns); the
-  // occupancy calculator does not know about TMEM
-  if (a.mma_mode == 1 && !a.has_jump) return 4;
+  // tcgen05 kernels, by construction: adjoint 4 CTAs per SM (<= 128 registers, 54.9 KB shared memory, 128 TMEM columns),
+  // forward 5 (<= 102 registers, 8 KB, 96 columns); the occupancy calculator does not know about TMEM
+  if (a.mma_mode == 1 && !a.has_jump) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return backward ? 4 : reg_tc_forward_occupancy(a.B, sms);
+  }
   if (a.has_jump) return occ_one<Model, HP, true>(a, backward);
   return occ_one<Model, HP, false>(a, backward);
 }

@@ -408,24 +408,25 @@ constexpr int W1B_HI = 0, W1B_LO = W1B_HI + 4 * NB * 4, W2B_HI = W1B_LO + 4 * NB
               OFF_W3 = W2B_LO + 6 * NB * 4 + 32 /* N = 32 reads 8 n-rows past the last chunk */, OFF_RED = OFF_W3 + 32,
               OFF_BAR = OFF_RED + 8, SMEM_FLOATS = OFF_BAR + 8;
 static_assert((OFF_BAR % 2) == 0, "mbarrier alignment");
-// tensor memory columns: accumulator | A operand hi (X: 16, H1: 24 columns) | A operand lo
-constexpr uint32_t C_ACC = 0, C_AHI = 32, C_ALO = 64, NCOLS = 128;
+// tensor memory: two allocations (32 + 64 = 96 columns, so that five CTAs fit the 512 columns of an SM): the accumulator,
+// and the A operand hi (X: 16, H1: 24 columns) | lo
+constexpr uint32_t NCOLS_ACC = 32, NCOLS_A = 64, C_AHI = 0, C_ALO = 32;
 
 // D[ACC] = A (tensor memory: lane = row, one TF32 element per column, KS slices of 8 columns; hi and lo copies)
 //          * B (shared memory [k/4][n][4], NB n-rows per chunk), N = 32, 3xTF32
 template <int KS>
-__device__ __forceinline__ void gemm_k_tf32(uint32_t tmem, uint32_t b_hi, uint32_t b_lo) {
+__device__ __forceinline__ void gemm_k_tf32(uint32_t tmem_acc, uint32_t tmem_a, uint32_t b_hi, uint32_t b_lo) {
   constexpr uint32_t id = tc::idesc_tf32(128, 32, false, false);
 #pragma unroll
   for (int s = 0; s < KS; ++s) {
     const uint64_t dbh = tc::smem_desc(b_hi + s * (2 * NB * 16), NB * 16, 128), dbl = tc::smem_desc(b_lo + s * (2 * NB * 16), NB * 16, 128);
-    tc::mma_tf32_ts(tmem + C_ACC, tmem + C_AHI + 8 * s, dbh, id, s > 0 ? 1u : 0u);
-    tc::mma_tf32_ts(tmem + C_ACC, tmem + C_ALO + 8 * s, dbh, id, 1u);
-    tc::mma_tf32_ts(tmem + C_ACC, tmem + C_AHI + 8 * s, dbl, id, 1u);
+    tc::mma_tf32_ts(tmem_acc, tmem_a + C_AHI + 8 * s, dbh, id, s > 0 ? 1u : 0u);
+    tc::mma_tf32_ts(tmem_acc, tmem_a + C_ALO + 8 * s, dbh, id, 1u);
+    tc::mma_tf32_ts(tmem_acc, tmem_a + C_AHI + 8 * s, dbl, id, 1u);
   }
 }
 // 8 consecutive features of this thread's row -> TF32 hi / lo columns of the A operand in tensor memory
-__device__ __forceinline__ void store_tf32x8(uint32_t lane_base, int c8, const float* v) {
+__device__ __forceinline__ void store_tf32x8(uint32_t lane_base /* of the A allocation */, int c8, const float* v) {
   uint32_t h[8], l[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
@@ -445,8 +446,10 @@ __device__ __forceinline__ void publish_tmem() {
 }
 }  // namespace fwd
 
-template <class Model, int ACT>
-__global__ void __launch_bounds__(kThreads, 4) reg_forward_tc(const PricingArgs a) {
+// OCC = resident CTAs per SM the kernel is compiled for: 5 (<= 102 registers) pays off when every SM gets at least five
+// tiles; with fewer tiles (B = 2^16: 3.5 per SM) the 4-CTA build with its larger register budget is faster.
+template <class Model, int ACT, int OCC>
+__global__ void __launch_bounds__(kThreads, OCC) reg_forward_tc(const PricingArgs a) {
   constexpr int D = Model::D;
   using RL = RecLayout<D>;
   using namespace fwd;
@@ -492,14 +495,14 @@ __global__ void __launch_bounds__(kThreads, 4) reg_forward_tc(const PricingArgs 
       }
     }
   }
-  if (warp == 0) tc::tmem_alloc(tslot, NCOLS);
+  if (warp == 0) { tc::tmem_alloc(tslot, NCOLS_ACC, false); tc::tmem_alloc(tslot + 1, NCOLS_A); }
   if (row == 0) { tc::mbar_init(bar, 1); tc::fence_mbar_init(); }
   tc::fence_async_smem();
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tmem = *tslot;
-  const uint32_t lane_base = tmem + ((uint32_t)(row & ~31) << 16);
+  const uint32_t tmem = tslot[0], tmem_a = tslot[1];
+  const uint32_t lane_base = tmem + ((uint32_t)(row & ~31) << 16), lane_a = tmem_a + ((uint32_t)(row & ~31) << 16);
   const uint32_t sbase = tc::smem_u32(smem);
   auto sa = [&](int off_f) { return sbase + (uint32_t)off_f * 4u; };
   uint32_t phase = 0;
@@ -551,13 +554,13 @@ __global__ void __launch_bounds__(kThreads, 4) reg_forward_tc(const PricingArgs 
         }
         // the TMEM stores go last, right before the wait::st of publish_tmem(): tcgen05.st reads its source registers
         // asynchronously, so any instruction that reuses one of them would stall until the store has drained
-        store_tf32x8(lane_base, 0, xin);
-        store_tf32x8(lane_base, 1, xin + 8);
+        store_tf32x8(lane_a, 0, xin);
+        store_tf32x8(lane_a, 1, xin + 8);
       }
       publish_tmem();
       if (warp == 0 && issuer) {
         tc::tc_fence_after();
-        gemm_k_tf32<2>(tmem, sa(W1B_HI), sa(W1B_LO));
+        gemm_k_tf32<2>(tmem, tmem_a, sa(W1B_HI), sa(W1B_LO));
         tc::mma_commit(bar);
       }
       // ---- independent of the network: closed-form coupling, exponentials, record stores -------------------------
@@ -575,16 +578,16 @@ __global__ void __launch_bounds__(kThreads, 4) reg_forward_tc(const PricingArgs 
 #pragma unroll
       for (int c8 = 0; c8 < 3; ++c8) {
         float t8[8];
-        tc::tmem_ld8(lane_base + C_ACC + 8 * c8, t8);
+        tc::tmem_ld8(lane_base + 8 * c8, t8);
         tc::tmem_ld_wait();
 #pragma unroll
         for (int q = 0; q < 8; ++q) t8[q] = actf<ACT>(t8[q]);
-        store_tf32x8(lane_base, c8, t8);                 // (L1 has completed: the X columns are free)
+        store_tf32x8(lane_a, c8, t8);                    // (L1 has completed: the X columns are free)
       }
       publish_tmem();
       if (warp == 1 && issuer) {
         tc::tc_fence_after();
-        gemm_k_tf32<3>(tmem, sa(W2B_HI), sa(W2B_LO));
+        gemm_k_tf32<3>(tmem, tmem_a, sa(W2B_HI), sa(W2B_LO));
         tc::mma_commit(bar);
       }
 #pragma unroll
@@ -595,7 +598,7 @@ __global__ void __launch_bounds__(kThreads, 4) reg_forward_tc(const PricingArgs 
 #pragma unroll
       for (int c8 = 0; c8 < 3; ++c8) {
         float t8[8];
-        tc::tmem_ld8(lane_base + C_ACC + 8 * c8, t8);
+        tc::tmem_ld8(lane_base + 8 * c8, t8);
         tc::tmem_ld_wait();
         const float4 wa = ld4(w3s + 8 * c8), wb = ld4(w3s + 8 * c8 + 4);
         const float w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
@@ -657,7 +660,7 @@ __global__ void __launch_bounds__(kThreads, 4) reg_forward_tc(const PricingArgs 
     a.lpart[blockIdx.x * 4] = tot;
     a.lpart[blockIdx.x * 4 + 1] = 0.0f; a.lpart[blockIdx.x * 4 + 2] = 0.0f; a.lpart[blockIdx.x * 4 + 3] = 0.0f;
   }
-  if (warp == 0) tc::tmem_dealloc(tmem, NCOLS);
+  if (warp == 0) { tc::tmem_dealloc(tmem, NCOLS_ACC); tc::tmem_dealloc(tmem_a, NCOLS_A); }
 }
 
 // Tile-major record -> the plane layout of fbsdej_solver_loss' trajectory output: X [N+1][D][B].
@@ -677,20 +680,25 @@ __global__ void untile_traj_kernel(const float* __restrict__ rec, const float* _
 size_t reg_tc_backward_smem() { return sizeof(float) * (size_t)rtc::bwd::SMEM_FLOATS; }
 size_t reg_tc_forward_smem() { return sizeof(float) * (size_t)rtc::fwd::SMEM_FLOATS; }
 
-template <class Model>
-static int launch_fwd(const PricingArgs& a, int grid, cudaStream_t st) {
+template <class Model, int ACT, int OCC>
+static int launch_fwd_one(const PricingArgs& a, int grid, cudaStream_t st) {
   const size_t smem = reg_tc_forward_smem();
-  if (a.netA.act == ACT_TANH) {
-    auto kern = rtc::reg_forward_tc<Model, ACT_TANH>;
-    FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kThreads, smem, st>>>(a);
-  } else {
-    auto kern = rtc::reg_forward_tc<Model, ACT_RELU>;
-    FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kThreads, smem, st>>>(a);
-  }
+  auto kern = rtc::reg_forward_tc<Model, ACT, OCC>;
+  FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, kThreads, smem, st>>>(a);
   FB_CUDA(cudaGetLastError());
   return 0;
+}
+int reg_tc_forward_occupancy(int B, int sms) { return (B + TR - 1) / TR >= 5 * sms ? 5 : 4; }
+template <class Model>
+static int launch_fwd(const PricingArgs& a, int grid, cudaStream_t st) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const bool five = reg_tc_forward_occupancy(a.B, sms) == 5;
+  if (a.netA.act == ACT_TANH)
+    return five ? launch_fwd_one<Model, ACT_TANH, 5>(a, grid, st) : launch_fwd_one<Model, ACT_TANH, 4>(a, grid, st);
+  return five ? launch_fwd_one<Model, ACT_RELU, 5>(a, grid, st) : launch_fwd_one<Model, ACT_RELU, 4>(a, grid, st);
 }
 
 int launch_reg_tc_forward(int model, int D, const PricingArgs& a, int grid, cudaStream_t st) {

@@ -41,16 +41,20 @@ __device__ __noinline__ float jump_size_rare(uint32_t u, uint32_t t0, uint32_t t
   return dn * muJ + sigJ * sqrtf(dn) * (which ? e1 : e0);
 }
 
-// Branch-free common case.  count = 0: J = 0.  count = 1 (thr[0] <= u < thr[1]): v = (u - thr[0] + 1/2) / (thr[1] - thr[0])
-// is uniform on (0, 1) with ~28 bits; z = Phi^{-1}(v) = sqrt(2) erfinv(2v - 1) by Giles' single-precision polynomial in
-// w = -ln(4 v (1 - v)) (central branch w < 5, |error| ~ 3e-7); J = muJ + sigJ z.  `rare` flags what the polynomial does not
-// cover.
-__device__ __forceinline__ float jump_size_fast(uint32_t u, uint32_t t0, uint32_t t1, float inv_w1, float muJ, float sigJ, bool& rare) {
+// Branch-free common case for the two Poisson draws (u0, u1) of one Philox block.  count = 0: J = 0.  count = 1
+// (thr[0] <= u < thr[1]): v = (u - thr[0] + 1/2) / (thr[1] - thr[0]) is uniform on (0, 1) with ~28 bits;
+// z = Phi^{-1}(v) = sqrt(2) erfinv(2v - 1) by Giles' single-precision polynomial in w = -ln(4 v (1 - v)) (central branch
+// w < 5, |error| ~ 3e-7); J = muJ + sigJ z.  The polynomial is evaluated ONCE, on whichever of the two draws has the single
+// jump; `rare` flags everything else (a count >= 2, both draws jumping, a far-tail size) for the exact path.
+__device__ __forceinline__ void jump_sizes_fast(uint32_t u0, uint32_t u1, uint32_t t0, uint32_t t1, float inv_w1, float muJ,
+                                                float sigJ, float& j0, float& j1, uint32_t& rare) {
+  const bool one0 = (u0 >= t0) && (u0 < t1), one1 = (u1 >= t0) && (u1 < t1);
+  const uint32_t u = one1 ? u1 : u0;
   const float v = ((float)(u - t0) + 0.5f) * inv_w1;
   const float x = fmaf(2.0f, v, -1.0f);
   float w = -0.6931471805599453f * __log2f(fmaf(-x, x, 1.0f));
-  const bool one = (u >= t0) && (u < t1);
-  rare = (u >= t1) || (one && !(w < 5.0f));
+  const bool tail = (one0 || one1) && !(w < 5.0f);
+  rare = ((u0 >= t1) || (one0 && (one1 || tail)) ? 1u : 0u) | ((u1 >= t1) || (one1 && (one0 || tail)) ? 2u : 0u);
   w -= 2.5f;
   float p = 2.81022636e-08f;
   p = fmaf(p, w, 3.43273939e-07f);
@@ -61,8 +65,9 @@ __device__ __forceinline__ float jump_size_fast(uint32_t u, uint32_t t0, uint32_
   p = fmaf(p, w, -0.00417768164f);
   p = fmaf(p, w, 0.246640727f);
   p = fmaf(p, w, 1.50140941f);
-  const float z = 1.4142135623730951f * p * x;
-  return one ? fmaf(sigJ, z, muJ) : 0.0f;
+  const float jump = fmaf(sigJ, 1.4142135623730951f * p * x, muJ);
+  j0 = one0 ? jump : 0.0f;
+  j1 = one1 ? jump : 0.0f;
 }
 
 // two N(0,1) from two 32-bit words: Box-Muller with the MUFU approximations (lg2, sqrt, sin, cos)
@@ -104,10 +109,9 @@ __global__ void __launch_bounds__(256, 4) sim_merton_kernel(const SimMertonArgs 
         const uint32_t gid = a.path_offset + (uint32_t)(b0 + q);
         const uint4 r = Philox::rand4(gid, c1, iter, a.stream, a.seed_lo, a.seed_hi);
         box_muller_fast(r.x, r.y, a.sqdt, w0[q], w1[q]);
-        bool rare0, rare1;
-        j0[q] = jump_size_fast(r.z, t0, t1, inv_w1, a.muJ, a.sigJ, rare0);
-        j1[q] = jump_size_fast(r.w, t0, t1, inv_w1, a.muJ, a.sigJ, rare1);
-        rare |= (rare0 ? 1u : 0u) << (2 * q) | (rare1 ? 1u : 0u) << (2 * q + 1);
+        uint32_t rq;
+        jump_sizes_fast(r.z, r.w, t0, t1, inv_w1, a.muJ, a.sigJ, j0[q], j1[q], rq);
+        rare |= rq << (2 * q);
       }
       if (rare) {                                          // ~0.4 % of the cells: redo the block, exact path
 #pragma unroll

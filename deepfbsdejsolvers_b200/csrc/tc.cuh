@@ -47,10 +47,10 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 
 // ---- TMEM -----------------------------------------------------------------------------------------------------
 // Called by ONE full warp.  ncols: power of two >= 32.
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols, bool last = true) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
                : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (last) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");   // after the CTA's last allocation
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
