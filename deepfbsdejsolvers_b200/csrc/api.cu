@@ -672,8 +672,8 @@ int fbsdej_solver_create(fbsdej_ctx* ctx, const fbsdej_solver_desc* desc, const 
   s->M = s->has_jump ? desc->M : 0;
   FB_REQUIRE(!s->has_jump || desc->M >= 1, "this scheme needs M >= 1 compensator samples");
   FB_REQUIRE(desc->mma_mode == 0 || desc->mma_mode == 1, "mma_mode must be 0 (FFMA) or 1 (tcgen05)");
-  FB_REQUIRE(desc->mma_mode == 0 || (reg && model != FBSDEJ_MODEL_MFG && HP == 24),
-             "mma_mode = 1 (tcgen05) is available for the SUMLOCALREG / MULTISTEPREG pricing solvers with H <= 23");
+  FB_REQUIRE(desc->mma_mode == 0 || (reg && model != FBSDEJ_MODEL_MFG && HP == 24 && desc->nets[0].H <= 22),
+             "mma_mode = 1 (tcgen05) is available for the SUMLOCALREG / MULTISTEPREG pricing solvers with H <= 22");
   cudaStream_t st = ctx->stream;
   if (model == FBSDEJ_MODEL_MERTON) {
     if (build_merton_tables(s.get())) return -2;

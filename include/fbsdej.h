@@ -90,9 +90,10 @@ typedef struct {
   int price_table;      /* Merton: 0 = sum the series of pricingModels.py:40-49 term by term at every path-step,
                            1 = evaluate it through a per-step cubic-Hermite table in log-moneyness (abs. error < 5e-8,
                            the same idea as the reference's own spline of the VG price, pricingModels.py:170-178) */
-  int mma_mode;         /* 0 = every layer in fp32 FFMA; 1 = tcgen05 tensor cores for the H x H layer, its transpose and the
-                           weight-gradient GEMMs (3xTF32 forward, bf16x3 adjoint; accumulators in TMEM).  Available for the
-                           compensator-free solvers (SUMLOCALREG / MULTISTEPREG) of the pricing models, H <= 23. */
+  int mma_mode;         /* 0 = every layer in fp32 FFMA; 1 = every matrix product of the network on tcgen05 tensor cores
+                           (forward: both layers 3xTF32 with the A operands in TMEM; adjoint: six bf16x3 GEMMs per step,
+                           weight-gradient accumulators resident in TMEM).  Available for the compensator-free solvers
+                           (SUMLOCALREG / MULTISTEPREG) of the pricing models, H <= 22, one network output. */
 } fbsdej_solver_desc;
 
 FBSDEJ_API const char* fbsdej_last_error(void);
