@@ -310,11 +310,18 @@ def run_native(a):
         prof = s.profile(0, Bl, reps=max(3, min(a.steps, 10)))
         ps = Bl * N
         jump = M > 0
+        # the tcgen05 Merton solvers draw the increments inside the forward sweep: no simulation kernel, and the fused
+        # kernel is charged with the simulation's algorithmic bytes as well ("fused kernel" paragraph)
+        fused_sim = a.mma == "tcgen05" and not jump and os.environ.get("FBSDEJ_NO_FUSED_RNG") is None
         # algorithmic bytes per path-step (SURVEY 8d / BASELINE.md section 5); Reg solvers have no Z / Gam / comp words
         alg = {"sim_paths": 8 * D * ps,
                "forward": 4 * ((5 * D + 4) if jump else (3 * D + 2 + D + 1)) * ps,
                "backward": 4 * ((7 * D + 4) if jump else (5 * D + 2 + 2 * D + 2 - D)) * ps}
+        if fused_sim:
+            alg["forward"] += alg.pop("sim_paths")
         kernels = {}
+        if fused_sim:
+            kernels["sim_paths"] = {"ms": 0.0, "fused_into": "forward (reg_forward_tc draws the increments in registers)"}
         for kname, b in alg.items():
             t = prof[kname]
             kernels[kname] = {"ms": t, "algorithmic_bytes": b, "achieved_GBps": b / (t * 1e-3) / 1e9 if t > 0 else None,
@@ -322,7 +329,7 @@ def run_native(a):
         kernels["reduce"] = {"ms": prof["reduce"]}
         if jump:
             kernels["sim_compensator"] = {"ms": prof["sim_compensator"]}
-        dom = max(("sim_paths", "forward", "backward"), key=lambda n: prof[n])
+        dom = max(alg, key=lambda n: prof[n])
         tc = a.mma == "tcgen05" and not jump
         kname = {"sim_paths": "sim_merton_kernel", "forward": "reg_forward_tc" if tc else "pricing_forward",
                  "backward": "reg_backward_tc" if tc else "pricing_backward"}[dom]

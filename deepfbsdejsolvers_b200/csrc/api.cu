@@ -174,6 +174,9 @@ struct fbsdej_solver {
   struct Finish { float* theta; float* m; float* v; const float* mask; float lr, b1, b2, eps; int* t_dev; uint32_t* iter_dev;
                   float* loss_dst; };
   const Finish* finish = nullptr; // set by train_steps: run_pass fuses reduce + Adam + counters into one launch
+  // set by step_pass: the tcgen05 forward draws the Merton increments itself (sim_device.cuh), nothing is materialised
+  struct Rng { uint64_t seed; uint32_t iteration; const uint32_t* iter_ptr; uint32_t path_offset; };
+  const Rng* rng = nullptr;
   // cached training graph
   cudaGraphExec_t graph = nullptr;
   struct Key { const void *theta, *m, *v, *mask, *t, *it, *loss; uint64_t seed; int B; float lr, b1, b2, eps; } key;
@@ -299,7 +302,7 @@ void fill_mfg_args(const fbsdej_solver* s, const float* theta, int B, int B_glob
 int run_pass(fbsdej_solver* s, const float* theta, int B, int B_global, float* out, bool with_grad, float* trajY,
              float* trajZ, cudaEvent_t* ev = nullptr) {
   FB_REQUIRE(B > 0 && B_global >= B, "B must be > 0 and B_global >= B");
-  FB_REQUIRE(s->noiseB == B, "noise not set for this batch size: call fbsdej_solver_simulate / set_noise first");
+  FB_REQUIRE(s->rng || s->noiseB == B, "noise not set for this batch size: call fbsdej_solver_simulate / set_noise first");
   cudaStream_t st = s->ctx->stream;
   int grid_f, grid_b = 0;
   if (s->model == FBSDEJ_MODEL_MFG) {
@@ -325,6 +328,12 @@ int run_pass(fbsdej_solver* s, const float* theta, int B, int B_global, float* o
       grid_b = a.C * std::min(ntiles, std::max(1, s->ctx->sms * pricing_blocks_per_sm(s->model, s->D, s->HP, a, true) / a.C));
     if (ensure_grid(s, std::max(grid_f, grid_b))) return -2;
     a.lpart = s->lpart; a.gpart = s->gpart; a.trajY = trajY; a.trajZ = trajZ;
+    if (s->rng) {
+      a.rng = 1; a.seed_lo = (uint32_t)s->rng->seed; a.seed_hi = (uint32_t)(s->rng->seed >> 32);
+      a.iteration = s->rng->iteration; a.iter_ptr = s->rng->iter_ptr; a.path_offset = s->rng->path_offset;
+      a.pois_thr = s->pois_thr; a.npois = s->npois;
+      a.sqdt = (float)std::sqrt(s->mer.T / s->mer.N); a.muJ = (float)s->mer.muJ; a.sigJ = (float)s->mer.sigJ;
+    }
     if (launch_pricing(s->model, s->D, s->HP, a, grid_f, false, st)) return -1;
     if (ev) cudaEventRecord(ev[0], st);
     if (with_grad && launch_pricing(s->model, s->D, s->HP, a, grid_b, true, st)) return -1;
@@ -397,6 +406,28 @@ int do_simulate(fbsdej_solver* s, uint64_t seed, uint32_t iteration, const uint3
   }
   s->noiseB = B;
   return 0;
+}
+
+// One training-path pass on fresh increments: simulate -> forward -> adjoint -> reduce.  The tcgen05 Merton solvers skip the
+// simulation kernel: their forward sweep draws the same Philox increments in registers (bit-identical to do_simulate).
+bool fused_rng(const fbsdej_solver* s) {
+  return s->desc.mma_mode == 1 && s->model == FBSDEJ_MODEL_MERTON && !s->has_jump && !getenv("FBSDEJ_NO_FUSED_RNG");
+}
+int step_pass(fbsdej_solver* s, const float* theta, uint64_t seed, uint32_t iteration, const uint32_t* iter_ptr,
+              uint32_t path_offset, int B, int B_global, float* out, cudaEvent_t* ev = nullptr) {
+  if (!fused_rng(s)) {
+    if (do_simulate(s, seed, iteration, iter_ptr, path_offset, B, ev ? &ev[1] : nullptr)) return -2;
+    if (ev) cudaEventRecord(ev[2], s->ctx->stream);
+    return run_pass(s, theta, B, B_global, out, true, nullptr, nullptr, ev ? &ev[3] : nullptr);
+  }
+  if (ensure_capacity(s, B)) return -2;
+  if (ev) { cudaEventRecord(ev[1], s->ctx->stream); cudaEventRecord(ev[2], s->ctx->stream); }
+  const fbsdej_solver::Rng rng{seed, iteration, iter_ptr, path_offset};
+  s->rng = &rng;
+  const int rc = run_pass(s, theta, B, B_global, out, true, nullptr, nullptr, ev ? &ev[3] : nullptr);
+  s->rng = nullptr;
+  s->noiseB = 0;                       // no increments were materialised
+  return rc;
 }
 
 int build_merton_tables(fbsdej_solver* s) {
@@ -798,8 +829,7 @@ int fbsdej_solver_grad_step(fbsdej_solver* s, const float* theta, uint64_t seed,
                             uint32_t path_offset, int B, int B_global, float* out) {
   FB_REQUIRE(s && theta && out && iter_dev, "grad_step: NULL argument");
   FB_CUDA(cudaSetDevice(s->ctx->device));
-  if (do_simulate(s, seed, 0, iter_dev, path_offset, B)) return -2;
-  return run_pass(s, theta, B, B_global, out, true, nullptr, nullptr);
+  return step_pass(s, theta, seed, 0, iter_dev, path_offset, B, B_global, out);
 }
 
 int fbsdej_bump_u32(fbsdej_ctx* ctx, uint32_t* p) {
@@ -830,9 +860,8 @@ int fbsdej_solver_train_steps(fbsdej_solver* s, float* theta, float* m, float* v
   int done = 0;
   const fbsdej_solver::Finish fin{theta, m, v, mask, lr, beta1, beta2, eps, t_dev, iter_dev, loss_out};
   auto one_step = [&]() -> int {       // simulate, forward, adjoint, [reduce + Adam + counters + loss record]: 4 launches
-    if (do_simulate(s, seed, 0, iter_dev, 0, B)) return -2;
     s->finish = &fin;
-    const int rc = run_pass(s, theta, B, B, s->out_dev, true, nullptr, nullptr);
+    const int rc = step_pass(s, theta, seed, 0, iter_dev, 0, B, B, s->out_dev);
     s->finish = nullptr;
     return rc ? -2 : 0;
   };
@@ -872,10 +901,7 @@ int fbsdej_solver_profile(fbsdej_solver* s, const float* theta, uint64_t seed, i
   int rc = 0;
   for (int r = -1; r < reps && !rc; ++r) {          // r == -1: untimed warm-up (also sizes the buffers)
     FB_CUDA(cudaEventRecord(ev[0], st));
-    rc = do_simulate(s, seed, (uint32_t)(r + 1), nullptr, 0, B, &ev[1]);
-    if (rc) break;
-    FB_CUDA(cudaEventRecord(ev[2], st));
-    rc = run_pass(s, theta, B, B, s->out_dev, true, nullptr, nullptr, &ev[3]);
+    rc = step_pass(s, theta, seed, (uint32_t)(r + 1), nullptr, 0, B, B, s->out_dev, ev);
     if (rc) break;
     FB_CUDA(cudaEventRecord(ev[5], st));
     FB_CUDA(cudaStreamSynchronize(st));

@@ -23,6 +23,13 @@ struct PricingArgs {
   float dt, r, K, x0, aLin, sig, drift_dt;
   NetRt netA, netB;
   int y0_off, P;
+  // rng = 1 (tcgen05 forward, Merton): the sweep draws its own increments (sim_device.cuh: same counters and arithmetic
+  // as sim_merton_kernel) instead of reading dW / J
+  int rng, npois;
+  uint32_t seed_lo, seed_hi, iteration, path_offset;
+  const uint32_t* iter_ptr;   // device iteration counter (CUDA-graph replay); NULL -> `iteration`
+  const uint32_t* pois_thr;
+  float sqdt, muJ, sigJ;
   const float* theta;
   const float* dW;            // [N][D][B]
   const float* J;             // [N][D][B]

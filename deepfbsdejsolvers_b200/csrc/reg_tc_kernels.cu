@@ -29,6 +29,7 @@
 // Per path-step inputs come from the tile-major record written by the forward sweep (pricing.cuh: RecLayout): one base
 // pointer, immediate offsets, one bulk L2 prefetch per (tile, step).
 #include "pricing.cuh"
+#include "sim_device.cuh"
 #include "tc.cuh"
 
 namespace fbsdej {
@@ -406,7 +407,7 @@ namespace fwd {
 // shared memory: only the B operands (weights) - the activations go to tensor memory
 constexpr int W1B_HI = 0, W1B_LO = W1B_HI + 4 * NB * 4, W2B_HI = W1B_LO + 4 * NB * 4, W2B_LO = W2B_HI + 6 * NB * 4,
               OFF_W3 = W2B_LO + 6 * NB * 4 + 32 /* N = 32 reads 8 n-rows past the last chunk */, OFF_RED = OFF_W3 + 32,
-              OFF_BAR = OFF_RED + 8, SMEM_FLOATS = OFF_BAR + 8;
+              OFF_BAR = OFF_RED + 8, OFF_THR = OFF_BAR + 8 /* 64 Poisson thresholds (fused RNG) */, SMEM_FLOATS = OFF_THR + 64;
 static_assert((OFF_BAR % 2) == 0, "mbarrier alignment");
 // tensor memory: two allocations (32 + 64 = 96 columns, so that five CTAs fit the 512 columns of an SM): the accumulator,
 // and the A operand hi (X: 16, H1: 24 columns) | lo
@@ -448,7 +449,9 @@ __device__ __forceinline__ void publish_tmem() {
 
 // OCC = resident CTAs per SM the kernel is compiled for: 5 (<= 102 registers) pays off when every SM gets at least five
 // tiles; with fewer tiles (B = 2^16: 3.5 per SM) the 4-CTA build with its larger register budget is faster.
-template <class Model, int ACT, int OCC>
+// RNG: the sweep draws the Merton increments itself (one Philox block per asset pair, in the shadow of the first MMA) - the
+// simulation kernel, its 8 d bytes per path-step of stores and this kernel's loads of them disappear from the step.
+template <class Model, int ACT, int OCC, bool RNG>
 __global__ void __launch_bounds__(kThreads, OCC) reg_forward_tc(const PricingArgs a) {
   constexpr int D = Model::D;
   using RL = RecLayout<D>;
@@ -495,6 +498,8 @@ __global__ void __launch_bounds__(kThreads, OCC) reg_forward_tc(const PricingArg
       }
     }
   }
+  uint32_t* const sthr = reinterpret_cast<uint32_t*>(smem + OFF_THR);
+  if (RNG && row < 64) sthr[row] = row < a.npois ? a.pois_thr[row] : 0xffffffffu;
   if (warp == 0) { tc::tmem_alloc(tslot, NCOLS_ACC, false); tc::tmem_alloc(tslot + 1, NCOLS_A); }
   if (row == 0) { tc::mbar_init(bar, 1); tc::fence_mbar_init(); }
   tc::fence_async_smem();
@@ -512,11 +517,15 @@ __global__ void __launch_bounds__(kThreads, OCC) reg_forward_tc(const PricingArg
   const size_t sB = (size_t)a.B;
   const float rdt = a.r * a.dt;
   float lsum = 0.0f;
+  const uint32_t rng_iter = RNG ? (a.iter_ptr ? *a.iter_ptr : a.iteration) : 0u;
+  const uint32_t t0 = RNG ? sthr[0] : 0u, t1 = RNG ? sthr[1] : 0u;
+  const float inv_w1 = t1 > t0 ? 1.0f / (float)(t1 - t0) : 0.0f;
   const int ntiles = (a.B + TR - 1) / TR;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int p0 = tile * TR + row;
     const bool valid = p0 < a.B;
     const int p = valid ? p0 : a.B - 1;
+    const uint32_t gid = a.path_offset + (uint32_t)p;
     float* const rec0 = a.rec + (size_t)tile * a.N * RL::NP * TR + row;
     float X[D];
 #pragma unroll
@@ -526,6 +535,7 @@ __global__ void __launch_bounds__(kThreads, OCC) reg_forward_tc(const PricingArg
     // the increments of step i are loaded one step ahead (right after the first MMA of step i - 1 is issued)
     float Wn[Model::kBrownian ? D : 1], Jn[D];       // raw values: the combine happens where they are consumed
     auto load_step = [&](int i) {
+      if (RNG) return;
       const float* __restrict__ pw = a.dW + (size_t)i * D * sB + p;
       const float* __restrict__ pj = a.J + (size_t)i * D * sB + p;
 #pragma unroll
@@ -535,6 +545,21 @@ __global__ void __launch_bounds__(kThreads, OCC) reg_forward_tc(const PricingArg
       }
     };
     load_step(0);
+    // RNG: the exponentials e^{drift dt + sig dW + J} of step i + 1 are drawn during step i, two asset pairs in the shadow
+    // of the first MMA and the rest in the shadow of the second one
+    float En[RNG ? D : 1];
+    auto draw = [&](int i, int kp_lo, int kp_hi) {
+#pragma unroll
+      for (int kp = 0; kp < (D + 1) / 2; ++kp) {
+        if (kp < kp_lo || kp >= kp_hi) continue;
+        const MertonCell c = merton_cell(gid, ((uint32_t)i << 8) | (uint32_t)kp, rng_iter, STREAM_PATH, a.seed_lo, a.seed_hi, t0, t1,
+                                         inv_w1, a.sqdt, a.muJ, a.sigJ, sthr, a.npois);
+        En[RNG ? 2 * kp : 0] = __expf(a.drift_dt + a.sig * c.w0 + c.j0);
+        if (2 * kp + 1 < D) En[RNG ? 2 * kp + 1 : 0] = __expf(a.drift_dt + a.sig * c.w1 + c.j1);
+      }
+    };
+    constexpr int KP = (D + 1) / 2, KP1 = KP < 2 ? KP : 2;
+    if constexpr (RNG) draw(0, 0, KP);
     for (int i = 0; i < a.N; ++i) {
       const float tf = (a.scheme == SCH_SUMLOCAL && a.stale_time) ? (float)(i == 0 ? 0 : i - 1) : (float)i;
       float* const rs = rec0 + (size_t)i * RL::NP * TR;
@@ -566,10 +591,19 @@ __global__ void __launch_bounds__(kThreads, OCC) reg_forward_tc(const PricingArg
       // ---- independent of the network: closed-form coupling, exponentials, record stores -------------------------
       typename Model::AEval ae;
       Model::eval_A_begin(a, i, X, ae);                  // table loads in flight ...
+      if constexpr (RNG) {                               // ... while the stores issue and next step's increments are drawn
 #pragma unroll
-      for (int k = 0; k < D; ++k) {                      // ... while the exponentials and the stores issue
-        rs[(RL::P_X + k) * TR] = X[k];
-        E[k] = __expf(a.drift_dt + (Model::kBrownian ? a.sig * Wn[Model::kBrownian ? k : 0] : 0.0f) + Jn[k]);
+        for (int k = 0; k < D; ++k) {
+          rs[(RL::P_X + k) * TR] = X[k];
+          E[k] = En[RNG ? k : 0];
+        }
+        if (i + 1 < a.N) draw(i + 1, 0, KP1);
+      } else {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {                    // ... while the exponentials and the stores issue
+          rs[(RL::P_X + k) * TR] = X[k];
+          E[k] = __expf(a.drift_dt + (Model::kBrownian ? a.sig * Wn[Model::kBrownian ? k : 0] : 0.0f) + Jn[k]);
+        }
       }
       float Ai, dAb;
       Model::eval_A_finish(a, i, ae, Ai, dAb);
@@ -592,7 +626,9 @@ __global__ void __launch_bounds__(kThreads, OCC) reg_forward_tc(const PricingArg
       }
 #pragma unroll
       for (int k = 0; k < D; ++k) rs[(RL::P_E + k) * TR] = E[k];
-      if (i + 1 < a.N) load_step(i + 1);
+      if (i + 1 < a.N) {
+        if constexpr (RNG) draw(i + 1, KP1, KP); else load_step(i + 1);
+      }
       wait_mma();
       float y_net = w3s[24];
 #pragma unroll
@@ -680,10 +716,10 @@ __global__ void untile_traj_kernel(const float* __restrict__ rec, const float* _
 size_t reg_tc_backward_smem() { return sizeof(float) * (size_t)rtc::bwd::SMEM_FLOATS; }
 size_t reg_tc_forward_smem() { return sizeof(float) * (size_t)rtc::fwd::SMEM_FLOATS; }
 
-template <class Model, int ACT, int OCC>
+template <class Model, int ACT, int OCC, bool RNG>
 static int launch_fwd_one(const PricingArgs& a, int grid, cudaStream_t st) {
   const size_t smem = reg_tc_forward_smem();
-  auto kern = rtc::reg_forward_tc<Model, ACT, OCC>;
+  auto kern = rtc::reg_forward_tc<Model, ACT, OCC, RNG>;
   FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, kThreads, smem, st>>>(a);
   FB_CUDA(cudaGetLastError());
@@ -696,9 +732,17 @@ static int launch_fwd(const PricingArgs& a, int grid, cudaStream_t st) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const bool five = reg_tc_forward_occupancy(a.B, sms) == 5;
+  if constexpr (Model::kBrownian) {
+    if (a.rng) {
+      if (a.netA.act == ACT_TANH)
+        return five ? launch_fwd_one<Model, ACT_TANH, 5, true>(a, grid, st) : launch_fwd_one<Model, ACT_TANH, 4, true>(a, grid, st);
+      return five ? launch_fwd_one<Model, ACT_RELU, 5, true>(a, grid, st) : launch_fwd_one<Model, ACT_RELU, 4, true>(a, grid, st);
+    }
+  }
+  if (a.rng) { set_error("tcgen05 forward: in-kernel increments exist for the Merton model only"); return -1; }
   if (a.netA.act == ACT_TANH)
-    return five ? launch_fwd_one<Model, ACT_TANH, 5>(a, grid, st) : launch_fwd_one<Model, ACT_TANH, 4>(a, grid, st);
-  return five ? launch_fwd_one<Model, ACT_RELU, 5>(a, grid, st) : launch_fwd_one<Model, ACT_RELU, 4>(a, grid, st);
+    return five ? launch_fwd_one<Model, ACT_TANH, 5, false>(a, grid, st) : launch_fwd_one<Model, ACT_TANH, 4, false>(a, grid, st);
+  return five ? launch_fwd_one<Model, ACT_RELU, 5, false>(a, grid, st) : launch_fwd_one<Model, ACT_RELU, 4, false>(a, grid, st);
 }
 
 int launch_reg_tc_forward(int model, int D, const PricingArgs& a, int grid, cudaStream_t st) {

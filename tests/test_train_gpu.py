@@ -114,3 +114,25 @@ def test_mfg_diagnostics(ctx, name):
     for cost, aver in ((c_hat, ah), (c_ind, ai)):
         ident = dt * P["C"] * float(np.sum(aver[:N])) + P["h1"] + P["h2"] * float(aver[N])
         assert abs(cost - ident) <= 0.02 * max(1.0, abs(ident)), (cost, ident)
+
+
+@pytest.mark.parametrize("scheme", ["SumLocalReg", "MultiStepReg"])
+def test_in_kernel_increments_equal_simulated_ones(ctx, scheme):
+    """The tcgen05 Merton solvers draw their increments inside the forward sweep (no simulation kernel, nothing in HBM).
+    Same Philox counters and arithmetic as fbsdej_solver_simulate, so the step on fused increments must reproduce
+    simulate(seed, iteration) -> grad, for a shard with a path offset as well."""
+    d, B, seed, it = 10, 333, 4242, 5
+    p = dict(H.MERTON, N=7)
+    layout = H.pricing_layout("merton", scheme, d)
+    theta = H.random_theta(layout, 8)
+    a = H.native_pricing(ctx, "merton", p, scheme, layout, d=d, limit=100, tensor_cores=True)
+    b = H.native_pricing(ctx, "merton", p, scheme, layout, d=d, limit=100, tensor_cores=True)
+    a.set_theta(theta); b.set_theta(theta)
+    for _ in range(it):
+        b.bump_iteration()
+    for off, cnt in ((0, B), (100, 200)):
+        a.simulate(seed, it, cnt, path_offset=off)
+        ref = a.grad(cnt, B_global=B)
+        out = ctx.to_host(b.grad_step(seed, cnt, B, off)).numpy()
+        assert abs(out[0] - ref[0]) <= 1e-6 * abs(ref[0]), (out[0], ref[0])
+        assert np.abs(out[4:] - ref[4:]).max() <= 1e-6 * np.abs(ref[4:]).max()
