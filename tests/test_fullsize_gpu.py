@@ -1,0 +1,67 @@
+"""GPU: BASELINE.json's full size (config 3: Merton d = 10, B = 2^16 paths x N = 100 steps, SolverGlobalSumLocalReg on the tcgen05
+kernels), checked through size-independent properties - the oracle cannot run this size in seconds:
+  * determinism: the same (seed, iteration) gives bit-identical losses, gradients and post-Adam parameters;
+  * the batch mean is shard-additive: two virtual shards (path offsets 0 and B/2, weights 1/B) sum to the full-batch loss and
+    gradient up to fp32 summation order - the data-parallel invariant at full size;
+  * increments drawn inside the forward sweep == increments materialised by the simulation kernel;
+  * the tcgen05 kernels agree with the fp32 FFMA kernels on the same increments (1e-5 loss, 2e-4 of the largest gradient);
+  * a few hundred training steps reduce the validation loss."""
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+B, D, SEED = 1 << 16, 10, 2026
+P = dict(H.MERTON, N=100)
+
+
+def _solver(ctx, theta, tc=True):
+    layout = H.pricing_layout("merton", "SumLocalReg", D)
+    s = H.native_pricing(ctx, "merton", P, "SumLocalReg", layout, d=D, limit=100, tensor_cores=tc)
+    s.set_theta(theta)
+    s.reset_optimizer()
+    return s
+
+
+@pytest.fixture(scope="module")
+def theta():
+    return H.random_theta(H.pricing_layout("merton", "SumLocalReg", D), 77)
+
+
+def test_determinism_and_shard_additivity(ctx, theta):
+    a, b = _solver(ctx, theta), _solver(ctx, theta)
+    full = ctx.to_host(a.grad_step(SEED, B, B, 0)).numpy().copy()
+    again = ctx.to_host(b.grad_step(SEED, B, B, 0)).numpy().copy()
+    assert np.array_equal(full, again)
+    acc = np.zeros_like(full, dtype=np.float64)
+    for off in (0, B // 2):
+        acc += ctx.to_host(b.grad_step(SEED, B // 2, B, off)).numpy()
+    assert abs(acc[0] - full[0]) <= 2e-6 * abs(full[0])
+    assert np.abs(acc[4:] - full[4:]).max() <= 2e-5 * np.abs(full[4:]).max()
+    a.train_steps(SEED, B, 3, 3e-4); b.train_steps(SEED, B, 3, 3e-4)
+    ctx.sync()
+    assert np.array_equal(a.get_theta(), b.get_theta())
+
+
+def test_fused_increments_and_ffma_agreement(ctx, theta):
+    tc, ff = _solver(ctx, theta), _solver(ctx, theta, tc=False)
+    fused = ctx.to_host(tc.grad_step(SEED, B, B, 0)).numpy().copy()      # increments drawn inside the forward sweep
+    tc.simulate(SEED, 0, B)
+    mat = tc.grad(B)                                                     # same counters, materialised by sim_merton_kernel
+    assert abs(fused[0] - mat[0]) <= 1e-6 * abs(mat[0]) and np.abs(fused[4:] - mat[4:]).max() <= 1e-6 * np.abs(mat[4:]).max()
+    ff.simulate(SEED, 0, B)
+    ref = ff.grad(B)                                                     # fp32 FFMA kernels on the same increments
+    assert abs(mat[0] - ref[0]) <= 1e-5 * abs(ref[0]), (mat[0], ref[0])
+    assert np.abs(mat[4:] - ref[4:]).max() <= 2e-4 * np.abs(ref[4:]).max()
+
+
+def test_training_reduces_the_validation_loss(ctx, theta):
+    s = _solver(ctx, theta)
+    s.simulate(SEED ^ 0x55, 0, B)
+    before = float(s.loss(B)[0])
+    s.train_steps(SEED, B, 300, 1e-3)
+    s.simulate(SEED ^ 0x55, 0, B)
+    after = float(s.loss(B)[0])
+    assert np.isfinite(after) and after < 0.7 * before, (before, after)
