@@ -72,6 +72,7 @@ def _load():
         "fbsdej_solver_set_noise": (i32, [vp, i32, vp, vp, vp]),
         "fbsdej_solver_get_noise": (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
         "fbsdej_solver_loss": (i32, [vp, vp, i32, i32, vp, vp, vp, vp]),
+        "fbsdej_solver_mfg_states": (i32, [vp, i32, vp]),
         "fbsdej_solver_grad": (i32, [vp, vp, i32, i32, vp]),
         "fbsdej_adam_step": (i32, [vp, vp, vp, vp, vp, vp, i32, f32, f32, f32, f32, vp]),
         "fbsdej_solver_grad_step": (i32, [vp, vp, u64, vp, u32, i32, i32, vp]),

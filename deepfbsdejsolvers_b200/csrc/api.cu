@@ -810,6 +810,15 @@ int fbsdej_solver_loss(fbsdej_solver* s, const float* theta, int B, int B_global
   return 0;
 }
 
+int fbsdej_solver_mfg_states(fbsdej_solver* s, int B, float* out) {
+  FB_REQUIRE(s && out && B > 0, "mfg_states: bad argument");
+  FB_REQUIRE(s->model == FBSDEJ_MODEL_MFG, "mfg_states: not an MFG solver");
+  FB_REQUIRE(s->trajX && B <= s->capB, "mfg_states: run fbsdej_solver_loss / fbsdej_solver_grad with this batch size first");
+  FB_CUDA(cudaSetDevice(s->ctx->device));
+  FB_CUDA(cudaMemcpyAsync(out, s->trajX, sizeof(float) * (size_t)(s->N + 1) * 5 * B, cudaMemcpyDeviceToDevice, s->ctx->stream));
+  return 0;
+}
+
 int fbsdej_solver_grad(fbsdej_solver* s, const float* theta, int B, int B_global, float* out) {
   FB_REQUIRE(s && theta && out, "grad: NULL argument");
   FB_CUDA(cudaSetDevice(s->ctx->device));

@@ -216,6 +216,12 @@ class NativeSolver:
             return o, self.ctx.to_host(tx).numpy(), self.ctx.to_host(ty).numpy(), (None if tz is None else self.ctx.to_host(tz).numpy())
         return o
 
+    def mfg_states(self, B: int) -> np.ndarray:
+        """(hQ, Q, R, hS, S) of the last loss / grad call: [N+1, 5, B]."""
+        out = self.ctx.zeros(self.N + 1, 5, B)
+        check(lib.fbsdej_solver_mfg_states(self.handle, B, _p(out)))
+        return self.ctx.to_host(out).numpy()
+
     def grad(self, B: int, B_global: Optional[int] = None) -> np.ndarray:
         Bg = B if B_global is None else B_global
         check(lib.fbsdej_solver_grad(self.handle, _p(self.theta), B, Bg, _p(self.out)))

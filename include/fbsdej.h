@@ -135,6 +135,11 @@ FBSDEJ_API int fbsdej_solver_get_noise(fbsdej_solver* s, const float** a, const 
  * MFG: X = (hS,S) [N+1][2][B], Y = (hY,Y) [N+1][2][B], Z ignored. out: >= 4 floats. */
 FBSDEJ_API int fbsdej_solver_loss(fbsdej_solver* s, const float* theta, int B, int B_global, float* out, float* trajX,
                        float* trajY, float* trajZ);
+
+/* MFG: the full state dump of the last fbsdej_solver_loss / fbsdej_solver_grad call, out [N+1][5][B] with planes
+ * (hQ, Q, R, hS, S) - what MFGSolutionsFixedTrajectory.simulateAllProcesses records step by step on pre-drawn increments
+ * (coupledMFG/MFGSolutions.py:23-57, getAllStates MFGModel.py:106-107). */
+FBSDEJ_API int fbsdej_solver_mfg_states(fbsdej_solver* s, int B, float* out);
 /* Forward + hand-derived adjoint: trainOpt's tape.gradient (SolversJumpDiff.py:47-53, MFGSolvers.py:50-73).
  * out: 4 + P floats. */
 FBSDEJ_API int fbsdej_solver_grad(fbsdej_solver* s, const float* theta, int B, int B_global, float* out);

@@ -136,3 +136,48 @@ def test_in_kernel_increments_equal_simulated_ones(ctx, scheme):
         out = ctx.to_host(b.grad_step(seed, cnt, B, off)).numpy()
         assert abs(out[0] - ref[0]) <= 1e-6 * abs(ref[0]), (out[0], ref[0])
         assert np.abs(out[4:] - ref[4:]).max() <= 1e-6 * np.abs(ref[4:]).max()
+
+
+def test_fixed_trajectory_replay_matches_host_recursion(ctx):
+    """MFGSolutionsFixedTrajectory on pre-drawn [nbSimul, N+1] increments.  The fused kernel's replay (states,
+    controls) against the reference recursion stepped on the host (ModelCoupledFBSDE.oneStepFrom / calpha / calpha_hat,
+    MFGModel.py:58-89) with the same networks."""
+    import torch
+    from deepfbsdejsolvers_b200 import coupledMFG as cm, set_seed
+    set_seed(3)
+    P = H.mfg_params(1)
+    mm = cm.ModelCoupledFBSDE(**P)
+    km = cm.kerasModels(cm.Net_hat, cm.Net, "SumLocalReg", 1, 1, [20, 20], [22, 22], "tanh", "tanh")
+    solver = cm.SolverGlobalSumLocalReg(mm, km, 1e-3, "ON", ctx=ctx)
+    solver.train(64, 128, 5, 1)
+    nb, N = 48, mm.N
+    rng = np.random.default_rng(0)
+    dW0 = (np.sqrt(mm.dt) * rng.standard_normal((nb, N + 1))).astype(np.float32)
+    dW = (np.sqrt(mm.dt) * rng.standard_normal((nb, N + 1))).astype(np.float32)
+    dN = rng.poisson(0.3, (nb, N + 1)).astype(np.float32)
+    sol = cm.MFGSolutionsFixedTrajectory(mm, km, "SumLocalReg", dW0, dW, dN, ctx=ctx)
+    sol.simulateAllProcesses(nb)
+    assert sol.hS.shape == (nb, N + 1) and sol.alpha.shape == (nb, N + 1) and sol.meanhQ.shape == (N + 1,)
+    # host recursion with the same (trained) networks
+    s = solver.native
+    mm.init(nb)
+    for i in range(N + 1):
+        t = np.full(nb, i * mm.dt, dtype=np.float32)
+        hY = s.net_forward(0, np.stack([t, mm.hQ.numpy(), mm.hS.numpy(), mm.R.numpy()], 1))[:, 0]
+        Y = s.net_forward(1, np.stack([t, mm.Q.numpy(), mm.S.numpy(), mm.hQ.numpy(), mm.hS.numpy(), mm.R.numpy()], 1))[:, 0]
+        hYt, Yt = torch.from_numpy(hY), torch.from_numpy(Y)
+        for name, ref in (("hQ", mm.hQ), ("Q", mm.Q), ("R", mm.R), ("hS", mm.hS), ("S", mm.S)):
+            got = getattr(sol, name)[:, i]
+            assert np.abs(got - ref.numpy()).max() <= 2e-4 * max(1.0, np.abs(ref.numpy()).max()), (name, i)
+        assert np.abs(sol.alpha_hat[:, i] - mm.calpha_hat(hYt).numpy()).max() <= 5e-4 * max(1.0, np.abs(sol.alpha_hat[:, i]).max())
+        assert np.abs(sol.alpha[:, i] - mm.calpha(hYt, Yt).numpy()).max() <= 5e-4 * max(1.0, np.abs(sol.alpha[:, i]).max())
+        if i < N:
+            mm.oneStepFrom(torch.from_numpy(dW0[:, i]), torch.from_numpy(dW[:, i]), torch.from_numpy(dN[:, i]), hYt, Yt)
+    mean_cost, std_cost = sol.objectiveFunction()
+    assert np.isfinite([mean_cost, std_cost]).all() and sol.price(mm.pi, sol.alpha_hat).shape == (nb, N + 1)
+    # the Global replay (BSDE-propagated Y) runs through the same path
+    kg = cm.kerasModels(cm.Net_hat, cm.Net, "Global", 2, 3, [20, 20], [22, 22], "tanh", "tanh")
+    cm.SolverGlobalFBSDE(mm, kg, 1e-3, "ON", ctx=ctx).train(32, 64, 2, 1)
+    solg = cm.MFGSolutionsFixedTrajectory(mm, kg, "Global", dW0, dW, dN, ctx=ctx)
+    solg.simulateAllProcesses(nb)
+    assert np.isfinite(solg.objectiveFunction()).all()
