@@ -158,3 +158,31 @@ class VGmodel(_PricingModel):
         x, y = _as_cpu(X), _as_cpu(Y)
         coup = self.aLin * torch.abs(y - self.A(iStep, x)) * self.dt
         return x * torch.exp((self.r - self.correction) * self.dt + _as_cpu(gaussJ)) + coup
+
+
+class VGmodelinvfourier(VGmodel):
+    """VGmodelinvfourier(T, N, r, theta, kappa, sigmaJ, K, x0, func)  (pricingModels.py:73-126): the same Variance-Gamma model
+    with the call price by DIRECT Fourier inversion, `X Q1 - K e^{-r tau} Q2` with `Q_j = 1/2 + (1/pi) int Re(...) du` on a
+    1000-point trapezoid over u in [1e-15, 5000] (:99-107).  It is the independent cross-check of the Lewis/FFT table that
+    `VGmodel.A` and the kernels use (0.1331406 vs 0.1331402 at the mainVG.py:54 parameters).
+
+    The reference class cannot be used with any solver (its `jumps()` takes no batch size, :115); here it
+    inherits the solver plumbing of VGmodel, so only `A` differs: evaluated on the host in float64 exactly as written."""
+
+    def characteristicfunc(self, iStep, u):
+        tau = self.T - iStep * self.dt
+        return np.exp(tau * (1j * (self.r - self.correction) * u
+                             - np.log(1 - 1j * self.theta * self.kappa * u + 0.5 * self.kappa * self.sigJ * self.sigJ * u * u) / self.kappa))
+
+    def A(self, iStep, X):
+        x = np.asarray(_as_cpu(X).numpy(), dtype=np.float64).reshape(-1)
+        k = np.log(self.K / x)[None, :]                                   # [1, B]
+        u = np.linspace(1e-15, 5000.0, 10 ** 3)[:, None]                  # [1000, 1]
+        base = np.exp(-1j * u * k) / (1j * u)
+        i1 = np.real(base * self.characteristicfunc(iStep, u - 1j) / self.characteristicfunc(iStep, -1.0000000000001j))
+        i2 = np.real(base * self.characteristicfunc(iStep, u + 0j))
+        trapz = getattr(np, "trapezoid", None) or np.trapz
+        Q1 = 0.5 + trapz(i1, u[:, 0], axis=0) / np.pi
+        Q2 = 0.5 + trapz(i2, u[:, 0], axis=0) / np.pi
+        price = x * Q1 - self.K * np.exp(-self.r * (self.T - iStep * self.dt)) * Q2
+        return torch.from_numpy(price.astype(np.float32)).reshape(_as_cpu(X).shape)

@@ -129,6 +129,19 @@ def test_vg_fft_known_answers():
     np.testing.assert_allclose(ov.A(15, x).numpy(), [0.02925149, 0.08252713, 0.16135454], atol=2e-8)
 
 
+def test_vg_direct_fourier_inversion_cross_checks_the_fft_price():
+    """pricingModels.py:73-126 (VGmodelinvfourier.A, 1000-point trapezoid of the two Fourier integrals) against the Lewis/FFT
+    price of pricingModels.py:156-179 (the oracle's VG.A): two independent pricers of the same model."""
+    from deepfbsdejsolvers_b200.coupledPricing import VGmodelinvfourier, AbsCoupling
+    ov = VGOracle(aLin=0.1, dtype=torch.float64, **H.VG)
+    mv = VGmodelinvfourier(H.VG["T"], H.VG["N"], H.VG["r"], H.VG["theta"], H.VG["kappa"], H.VG["sigmaJ"], H.VG["K"], H.VG["x0"],
+                           AbsCoupling(0.1))
+    assert abs(float(mv.A(0, torch.ones(1))[0]) - 0.1331406) < 2e-7
+    for i in (0, 7, 15, 29):
+        x = torch.tensor([0.8, 0.9, 1.0, 1.1, 1.25], dtype=torch.float64)
+        np.testing.assert_allclose(mv.A(i, x).numpy(), ov.A(i, x.reshape(-1, 1)).numpy().reshape(-1), atol=5e-5)   # du = 5 trapezoid
+
+
 def test_exact_solution_makes_coupling_vanish():
     """with Y == A the coupling term is zero, so X follows the uncoupled jump-diffusion."""
     om = MertonOracle(aLin=0.1, limit=30, d=1, dtype=torch.float64, **H.MERTON)
