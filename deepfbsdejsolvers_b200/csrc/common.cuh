@@ -8,7 +8,6 @@
 namespace fbsdej {
 
 constexpr int kThreads = 128;        // threads per CTA of the fused path kernels (= rows of one MLP tile)
-constexpr int kRowStride = 132;      // staging column stride (128 rows + 4: shifts banks by 4 per column)
 constexpr int kHeader = 4;           // out vector header: [loss, loss_a, loss_b, aux]
 
 // ---- error plumbing (C-ABI returns codes; message kept thread-local) -------------------------

@@ -143,13 +143,6 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
   lo = x - hi;
 }
-// round-to-nearest TF32 (single-pass operands of the weight-gradient GEMMs)
-__device__ __forceinline__ float rn_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
-
 // bf16 hi/lo split (bf16x3: D += A_hi B_hi + A_lo B_hi + A_hi B_lo, ~2^-16 relative): returns the two bf16 bit patterns
 __device__ __forceinline__ void split_bf16(float x, uint32_t& hi, uint32_t& lo) {
   const __nv_bfloat16 h = __float2bfloat16_rn(x);
