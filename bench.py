@@ -233,7 +233,8 @@ def run_native(a):
     e2e, e2e_rng = None, None
     if not a.no_e2e:
         nfl = N * D * Bl
-        host = [[torch.randn(nfl, dtype=torch.float32).mul_(0.1).pin_memory() for _ in range(2)] for _ in range(2)]
+        one = [torch.randn(nfl, dtype=torch.float32).mul_(0.1).pin_memory() for _ in range(2)]   # (dW, J) of a step, pinned
+        host = [one, one]                      # synthetic data: the same host block is uploaded for every step
         dev = [[ctx.empty(nfl), ctx.empty(nfl)] for _ in range(2)]
         loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
         jmc = ctx.zeros(N * D * max(M, 1)) if M > 0 else None
