@@ -25,27 +25,45 @@ __device__ __forceinline__ Controls controls(const MFGArgs& a, int i, float hQ, 
   return c;
 }
 
+// Both kernels run TWO roles side by side in a CTA of 2 x 128 threads: threads [0, 128) evaluate / differentiate the
+// projected player's network (hat), threads [128, 256) the individual player's, each on its own tile set and for the same
+// 128 paths; the network outputs (forward) and the state adjoints (backward) are exchanged through shared memory.  Every
+// thread carries the path's scalar state redundantly.  The reference's default batch is ONE tile (B = 128) walking 95 serial
+// steps, so the latency of a step - not throughput - is what counts, and the two networks of a step are independent.
+constexpr int kMfgThreads = 2 * kThreads;
+
+__device__ __forceinline__ float block_sum2(float v, float* red) {   // sum over the kMfgThreads threads, valid in every thread
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
+}
+
 template <int HP>
-__global__ void __launch_bounds__(kThreads) mfg_forward(const MFGArgs a) {
+__global__ void __launch_bounds__(kMfgThreads) mfg_forward(const MFGArgs a) {
   extern __shared__ __align__(16) float smem[];
+  using TL = Tiles<HP, 4>;
   float* swA = smem;
   float* swB = swA + net_smem_floats(a.netA, HP, false);
   float* red = swB + net_smem_floats(a.netB, HP, false);
-  float* tb = red + 8;
-  using TL = Tiles<HP, 4>;
+  float* outx = red + 8;                       // network outputs, [parity][role][4][128 rows]
+  float* tb = outx + 2 * 2 * 4 * TR;
+  const int role = threadIdx.x >> 7, row = threadIdx.x & (TR - 1);
   TL t;
-  t.carve(tb, false);
+  t.carve(tb + role * TL::fwd_floats(), false);
   const NetView<HP> nvA = load_net<HP>(swA, a.theta, a.netA, false);
   const NetView<HP> nvB = load_net<HP>(swB, a.theta, a.netB, false);
-  zero_tiles(tb, TL::fwd_floats());
-  const int row = threadIdx.x;
+  const NetView<HP>& nv = role == 0 ? nvA : nvB;
+  zero_tiles(tb, 2 * TL::fwd_floats());
   const size_t sB = (size_t)a.B;
   const int c0 = a.has_y ? 1 : 0;
   float lh_sum = 0.0f, li_sum = 0.0f;
-  const int ntiles = (a.B + kThreads - 1) / kThreads;
+  const int ntiles = (a.B + TR - 1) / TR;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int p0 = tile * kThreads + threadIdx.x;
+    const int p0 = tile * TR + row;
     const bool valid = p0 < a.B;
+    const bool writer = valid && role == 0;
     const int p = valid ? p0 : a.B - 1;
     float hQ = a.q0, Q = a.q0, R = a.R0, hS = a.S0, S = a.S0;
     float hY = 0.0f, Y = 0.0f;
@@ -55,15 +73,19 @@ __global__ void __launch_bounds__(kThreads) mfg_forward(const MFGArgs a) {
     for (int i = 0; i < a.N; ++i) {
       const float tm = (float)i * a.dt;
       const float dW0 = a.dW0[(size_t)i * sB + p], dW = a.dW[(size_t)i * sB + p], dN = a.dN[(size_t)i * sB + p];
-      st4(t.xt + 4 * row, make_float4(tm, hQ, hS, R));                               // getProjectedStates
-      st4(t.xt + 4 * (TR + row), make_float4(1.0f, 0.0f, 0.0f, 0.0f));
-      mlp_fwd<HP, false, TL>(nvA, t, row);
-      const float4 oh = ld4(t.out + 4 * row);
+      float* const ox = outx + (i & 1) * (2 * 4 * TR);
+      t.out = ox + role * (4 * TR);
+      if (role == 0) {
+        st4(t.xt + 4 * row, make_float4(tm, hQ, hS, R));                             // getProjectedStates
+        st4(t.xt + 4 * (TR + row), make_float4(1.0f, 0.0f, 0.0f, 0.0f));
+      } else {
+        st4(t.xt + 4 * row, make_float4(tm, Q, S, hQ));                              // getAllStates
+        st4(t.xt + 4 * (TR + row), make_float4(hS, R, 1.0f, 0.0f));
+      }
+      mlp_fwd<HP, false, TL>(nv, t, row);
+      __syncthreads();                                                               // both networks' outputs of step i
+      const float4 oh = ld4(ox + 4 * row), oi = ld4(ox + 4 * TR + 4 * row);
       const float oh0 = oh.x, oh1 = oh.y, oh2 = oh.z;
-      st4(t.xt + 4 * row, make_float4(tm, Q, S, hQ));                                // getAllStates
-      st4(t.xt + 4 * (TR + row), make_float4(hS, R, 1.0f, 0.0f));
-      mlp_fwd<HP, false, TL>(nvB, t, row);
-      const float4 oi = ld4(t.out + 4 * row);
       const float o0 = oi.x, o1 = oi.y, o2 = oi.z, o3 = oi.w;
       const float lamdt = (a.stochastic ? a.beta * (expf(a.alpha * hQ) - 1.0f) : a.jumpFactor) * a.dt;
       const float dNc = dN - lamdt;
@@ -76,7 +98,7 @@ __global__ void __launch_bounds__(kThreads) mfg_forward(const MFGArgs a) {
       }
       const float hYsel = (a.scheme == SCH_GLOBAL) ? hY : oh0;
       const float Ysel = (a.scheme == SCH_GLOBAL) ? Y : o0;
-      if (valid) {
+      if (writer) {
         float* tx = a.traj + ((size_t)i * 5) * sB + p;
         tx[0] = hQ; tx[sB] = Q; tx[2 * sB] = R; tx[3 * sB] = hS; tx[4 * sB] = S;
         if (a.trajY) { a.trajY[((size_t)i * 2) * sB + p] = hYsel; a.trajY[((size_t)i * 2 + 1) * sB + p] = Ysel; }
@@ -84,7 +106,7 @@ __global__ void __launch_bounds__(kThreads) mfg_forward(const MFGArgs a) {
       if (a.scheme == SCH_GLOBAL) {
         hY += a_h; Y += a_i;
       } else if (a.scheme == SCH_MULTISTEP) {
-        if (valid) {
+        if (writer) {
           a.sch[((size_t)i * 2 + 0) * sB + p] = hYsel - Ch;
           a.sch[((size_t)i * 2 + 1) * sB + p] = Ysel - Ci;
         }
@@ -93,7 +115,7 @@ __global__ void __launch_bounds__(kThreads) mfg_forward(const MFGArgs a) {
         if (i > 0) {
           const float rh = hYsel - hyp - ahp, ri = Ysel - yp - aip;
           llh = fmaf(rh, rh, llh); lli = fmaf(ri, ri, lli);
-          if (valid) { a.sch[((size_t)(i - 1) * 2 + 0) * sB + p] = rh; a.sch[((size_t)(i - 1) * 2 + 1) * sB + p] = ri; }
+          if (writer) { a.sch[((size_t)(i - 1) * 2 + 0) * sB + p] = rh; a.sch[((size_t)(i - 1) * 2 + 1) * sB + p] = ri; }
         }
         hyp = hYsel; ahp = a_h; yp = Ysel; aip = a_i;
       }
@@ -111,9 +133,9 @@ __global__ void __launch_bounds__(kThreads) mfg_forward(const MFGArgs a) {
     if (a.scheme == SCH_GLOBAL) {
       const float eh = hY - gh, ei = Y - gi;
       lh = eh * eh * a.inv_B; li = ei * ei * a.inv_B;
-      if (valid) { a.fin[p] = eh; a.fin[sB + p] = ei; }
+      if (writer) { a.fin[p] = eh; a.fin[sB + p] = ei; }
     } else if (a.scheme == SCH_MULTISTEP) {
-      if (valid) {
+      if (writer) {
         const float Dh = Ch - gh, Di = Ci - gi;
         float seh = 0.0f, sei = 0.0f, s2h = 0.0f, s2i = 0.0f;
         for (int k = 0; k < a.N; ++k) {
@@ -128,9 +150,9 @@ __global__ void __launch_bounds__(kThreads) mfg_forward(const MFGArgs a) {
       const float rh = gh - hyp - ahp, ri = gi - yp - aip;
       llh = fmaf(rh, rh, llh); lli = fmaf(ri, ri, lli);
       lh = llh * a.inv_B; li = lli * a.inv_B;
-      if (valid) { a.sch[((size_t)(a.N - 1) * 2 + 0) * sB + p] = rh; a.sch[((size_t)(a.N - 1) * 2 + 1) * sB + p] = ri; }
+      if (writer) { a.sch[((size_t)(a.N - 1) * 2 + 0) * sB + p] = rh; a.sch[((size_t)(a.N - 1) * 2 + 1) * sB + p] = ri; }
     }
-    if (valid) {
+    if (writer) {
       float* tx = a.traj + ((size_t)a.N * 5) * sB + p;
       tx[0] = hQ; tx[sB] = Q; tx[2 * sB] = R; tx[3 * sB] = hS; tx[4 * sB] = S;
       if (a.trajY) {
@@ -140,8 +162,8 @@ __global__ void __launch_bounds__(kThreads) mfg_forward(const MFGArgs a) {
       lh_sum += lh; li_sum += li;
     }
   }
-  const float th = block_sum(lh_sum, red);
-  const float ti = block_sum(li_sum, red);
+  const float th = block_sum2(lh_sum, red);
+  const float ti = block_sum2(li_sum, red);
   if (threadIdx.x == 0) {
     a.lpart[blockIdx.x * 4 + 0] = a.w_hat * th + a.w_ind * ti;
     a.lpart[blockIdx.x * 4 + 1] = th;
@@ -151,30 +173,32 @@ __global__ void __launch_bounds__(kThreads) mfg_forward(const MFGArgs a) {
 }
 
 template <int HP>
-__global__ void __launch_bounds__(kThreads) mfg_backward(const MFGArgs a) {
+__global__ void __launch_bounds__(kMfgThreads) mfg_backward(const MFGArgs a) {
   extern __shared__ __align__(16) float smem[];
+  using TL = Tiles<HP, 4>;
   float* swA = smem;
   float* swB = swA + net_smem_floats(a.netA, HP, true);
   float* red = swB + net_smem_floats(a.netB, HP, true);
-  float* tb = red + 8;
-  using TL = Tiles<HP, 4>;
+  float* dxx = red + 8;                        // state adjoints out of the two delta passes, [parity][3][128 rows]
+  float* tb = dxx + 2 * 3 * TR;
+  const int role = threadIdx.x >> 7, row = threadIdx.x & (TR - 1);
   TL t;
-  t.carve(tb, true);
+  float* const tbr = tb + role * TL::bwd_floats();
+  t.carve(tbr, true);
   const NetView<HP> nvA = load_net<HP>(swA, a.theta, a.netA, true);
   const NetView<HP> nvB = load_net<HP>(swB, a.theta, a.netB, true);
-  zero_tiles(tb, TL::bwd_floats());
-  WGrad<HP> wgA, wgB;
-  wgA.init(nvA, t);
-  wgB.init(nvB, t);
-  const int row = threadIdx.x;
+  const NetView<HP>& nv = role == 0 ? nvA : nvB;
+  zero_tiles(tb, 2 * TL::bwd_floats());
+  WGrad<HP> wg;
+  wg.init(nv, t, row);
   const size_t sB = (size_t)a.B;
   const int c0 = a.has_y ? 1 : 0;
   const float invB = a.inv_B, invBN = a.inv_B / (float)a.N;
   const float wh = a.w_hat, wi = a.w_ind;
   float y0h = 0.0f, y0i = 0.0f;
-  const int ntiles = (a.B + kThreads - 1) / kThreads;
+  const int ntiles = (a.B + TR - 1) / TR;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int p0 = tile * kThreads + threadIdx.x;
+    const int p0 = tile * TR + row;
     const bool valid = p0 < a.B;
     const int p = valid ? p0 : a.B - 1;
     const float msk = valid ? 1.0f : 0.0f;
@@ -235,10 +259,11 @@ __global__ void __launch_bounds__(kThreads) mfg_backward(const MFGArgs a) {
       hSbar += -a.dt * a.C * abh;
       Sbar += -a.dt * a.C * abi;
       float dx[HP];
-      {
+      float* const dxs = dxx + (i & 1) * (3 * TR);
+      if (role == 0) {
         st4(t.xt + 4 * row, make_float4(tm, hQ, hS, R));
         st4(t.xt + 4 * (TR + row), make_float4(1.0f, 0.0f, 0.0f, 0.0f));
-        mlp_fwd<HP, true, TL>(nvA, t, row);
+        mlp_fwd<HP, true, TL>(nv, t, row);
         float dd[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         if (a.has_y) dd[0] = hyb * msk;
         if (a.has_z) {
@@ -246,16 +271,12 @@ __global__ void __launch_bounds__(kThreads) mfg_backward(const MFGArgs a) {
           if (c0) { dd[1] = z0b; dd[2] = gb; } else { dd[0] = z0b; dd[1] = gb; }
         }
         st4(t.dout + 4 * row, make_float4(dd[0], dd[1], dd[2], dd[3]));
-        mlp_delta<HP, TL>(nvA, t, row, dx);
-        hSbar += dx[2];
-        __syncthreads();
-        wgA.accumulate(tb);
-        __syncthreads();
-      }
-      {
+        mlp_delta<HP, TL>(nv, t, row, dx);
+        dxs[row] = dx[2];                            // d / d hS through the projected player's network
+      } else {
         st4(t.xt + 4 * row, make_float4(tm, Q, S, hQ));
         st4(t.xt + 4 * (TR + row), make_float4(hS, R, 1.0f, 0.0f));
-        mlp_fwd<HP, true, TL>(nvB, t, row);
+        mlp_fwd<HP, true, TL>(nv, t, row);
         float dd[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         if (a.has_y) dd[0] = yb * msk;
         if (a.has_z) {
@@ -263,24 +284,25 @@ __global__ void __launch_bounds__(kThreads) mfg_backward(const MFGArgs a) {
           if (c0) { dd[1] = z0b; dd[2] = gb; dd[3] = zb; } else { dd[0] = z0b; dd[1] = gb; dd[2] = zb; }
         }
         st4(t.dout + 4 * row, make_float4(dd[0], dd[1], dd[2], dd[3]));
-        mlp_delta<HP, TL>(nvB, t, row, dx);
-        Sbar += dx[2];
-        hSbar += dx[4];
-        __syncthreads();
-        wgB.accumulate(tb);
-        __syncthreads();
+        mlp_delta<HP, TL>(nv, t, row, dx);
+        dxs[TR + row] = dx[2];                       // d / d S
+        dxs[2 * TR + row] = dx[4];                   // d / d hS through the individual player's network
       }
+      __syncthreads();                               // tiles complete (weight gradient) + adjoints exchanged
+      wg.accumulate(tbr);
+      hSbar += dxs[row] + dxs[2 * TR + row];
+      Sbar += dxs[TR + row];
+      __syncthreads();                               // before the tiles are overwritten
     }
-    if (a.scheme == SCH_GLOBAL) { y0h += hYbar * msk; y0i += Ybar * msk; }
+    if (a.scheme == SCH_GLOBAL && role == 0) { y0h += hYbar * msk; y0i += Ybar * msk; }
   }
-  const float t0 = block_sum(y0h, red);
-  const float t1 = block_sum(y0i, red);
+  const float t0 = block_sum2(y0h, red);
+  const float t1 = block_sum2(y0i, red);
   __syncthreads();
   float* sg = tb;
   for (int e = threadIdx.x; e < a.P; e += blockDim.x) sg[e] = 0.0f;
   __syncthreads();
-  wgA.flush(nvA, sg, a.netA.ext_off);
-  wgB.flush(nvB, sg, a.netB.ext_off);
+  wg.flush(nv, sg, role == 0 ? a.netA.ext_off : a.netB.ext_off);
   if (a.scheme == SCH_GLOBAL && threadIdx.x == 0) { sg[a.y0_off] = t0; sg[a.y0_off + 1] = t1; }
   __syncthreads();
   float* grow = a.gpart + (size_t)blockIdx.x * a.P;
@@ -290,7 +312,7 @@ __global__ void __launch_bounds__(kThreads) mfg_backward(const MFGArgs a) {
 template <int HP>
 static size_t mfg_smem(const MFGArgs& a, bool backward) {
   const int w = net_smem_floats(a.netA, HP, backward) + net_smem_floats(a.netB, HP, backward);
-  const int tl = backward ? Tiles<HP, 4>::bwd_floats() : Tiles<HP, 4>::fwd_floats();
+  const int tl = backward ? 2 * Tiles<HP, 4>::bwd_floats() + 2 * 3 * TR : 2 * Tiles<HP, 4>::fwd_floats() + 2 * 2 * 4 * TR;
   return sizeof(float) * (size_t)(w + 8 + tl);
 }
 size_t mfg_smem_bytes(int HP, const MFGArgs& a, bool backward) {
@@ -304,11 +326,11 @@ int mfg_blocks_per_sm(int HP, const MFGArgs& a, bool backward) {
   if (!backward) {
     auto kern = mfg_forward<24>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem) != cudaSuccess) return 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kMfgThreads, smem) != cudaSuccess) return 1;
   } else {
     auto kern = mfg_backward<24>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem) != cudaSuccess) return 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kMfgThreads, smem) != cudaSuccess) return 1;
   }
   return nb < 1 ? 1 : nb;
 }
@@ -322,11 +344,11 @@ int launch_mfg(int HP, const MFGArgs& a, int grid, bool backward, cudaStream_t s
   if (!backward) {
     auto kern = mfg_forward<24>;
     FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kThreads, smem, st>>>(a);
+    kern<<<grid, kMfgThreads, smem, st>>>(a);
   } else {
     auto kern = mfg_backward<24>;
     FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kThreads, smem, st>>>(a);
+    kern<<<grid, kMfgThreads, smem, st>>>(a);
   }
   FB_CUDA(cudaGetLastError());
   return 0;

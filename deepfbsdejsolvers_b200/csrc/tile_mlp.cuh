@@ -227,8 +227,10 @@ struct WGrad {
   int type, k0, j0;         // 0: dW1[k][j]  1: dW2[k][j]  2: dW3T[j][k];  -1: idle
   int chunk, S;
 
+  // u: index of the calling thread among the kThreads threads that share the tile set (threadIdx.x unless a CTA hosts
+  // several tile sets, mfg_kernels.cu)
   template <class TL>
-  __device__ void init(const NetView<HP>& nv, const TL& t) {
+  __device__ void init(const NetView<HP>& nv, const TL& t, int u = -1) {
     constexpr int JB = HP / 4;
     const int nb1 = ((nv.nin + 1 + 3) / 4) * JB, nb2 = JB * JB, nb3 = ((nv.nout + 3) / 4) * JB;
     const int NB = nb1 + nb2 + nb3;
@@ -238,7 +240,7 @@ struct WGrad {
     for (int a = 0; a < 4; ++a)
 #pragma unroll
       for (int b = 0; b < 4; ++b) p[a][b] = 0.0f;
-    const int u = threadIdx.x;
+    if (u < 0) u = threadIdx.x;
     chunk = u / NB;
     type = -1; k0 = j0 = 0; a_off = b_off = 0; r0 = nr = 0;
     if (chunk >= S) return;
