@@ -39,7 +39,10 @@ def parse():
     ap.add_argument("--paths", type=int, default=0, help="global Monte-Carlo batch (default 2^16 on 1 GPU, 2^20 on N>1)")
     ap.add_argument("--solver", default="SumLocalReg", choices=list(SOLVERS))
     ap.add_argument("--M", type=int, default=-1, help="compensator samples for --solver Global (default 256)")
-    ap.add_argument("--cpu-paths", type=int, default=2048, help="paths of the bounded CPU sample")
+    ap.add_argument("--cpu-paths", type=int, default=0,
+                    help="paths of the bounded CPU sample per step (0 = automatic: 16384 for the cpu_baseline leg; for --impl "
+                         "reference the largest power of two <= the batch that keeps the run near two minutes - the CPU "
+                         "restatement is more efficient on larger samples)")
     ap.add_argument("--mma", default="tcgen05", choices=["ffma", "tcgen05"], help="layer arithmetic of the fused kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -133,15 +136,25 @@ def run_reference(a):
     world = int(os.environ.get("WORLD_SIZE", str(a.gpus)))
     B = a.paths or (2 ** 16 if world == 1 else 2 ** 20)
     M, cfg = workload_config(a, B, world)
-    it = cpu_iteration_factory(a, M, a.cpu_paths)
+    cpu_paths = a.cpu_paths
+    if cpu_paths <= 0:                       # size the sample from one probe iteration: ~120 s for warm-up + K steps
+        probe = cpu_iteration_factory(a, M, 2048)
+        probe()
+        t0 = time.perf_counter()
+        probe()
+        t_probe = time.perf_counter() - t0
+        cpu_paths = 2048
+        while cpu_paths * 2 <= min(B, 65536) and (a.steps + 1) * t_probe * (cpu_paths * 2 / 2048) <= 120.0:
+            cpu_paths *= 2
+    it = cpu_iteration_factory(a, M, cpu_paths)
     for _ in range(max(1, min(a.warmup, 1))):
         it()
     t0 = time.perf_counter()
     for _ in range(a.steps):
         it()
     dt = (time.perf_counter() - t0) / a.steps
-    val = a.cpu_paths * MERTON["N"] / dt
-    sample = "%d-path sample of the %d-path batch per step, all %d time steps, fwd+bwd+Adam" % (a.cpu_paths, B, MERTON["N"])
+    val = cpu_paths * MERTON["N"] / dt
+    sample = "%d-path sample of the %d-path batch per step, all %d time steps, fwd+bwd+Adam" % (cpu_paths, B, MERTON["N"])
     print(json.dumps({
         "impl": "reference", "metric": "path-steps/s", "value": val, "unit": "path-steps/s", "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": dt * 1e3, "iters_per_s_equiv": val / (B * MERTON["N"]), "higher_is_better": True,
@@ -353,15 +366,16 @@ def run_native(a):
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        it = cpu_iteration_factory(a, M, a.cpu_paths)
+        cpu_paths = a.cpu_paths if a.cpu_paths > 0 else min(B, 16384)
+        it = cpu_iteration_factory(a, M, cpu_paths)
         it()
         t0, n = time.perf_counter(), 0
-        while n < 2 or (time.perf_counter() - t0 < 10.0 and n < 50):
+        while n < 2 or (time.perf_counter() - t0 < 15.0 and n < 50):
             it(); n += 1
         dt = (time.perf_counter() - t0) / n
-        cpu = {"value": a.cpu_paths * N / dt, "unit": "path-steps/s", "cores": torch.get_num_threads(), "kind": "port",
+        cpu = {"value": cpu_paths * N / dt, "unit": "path-steps/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": "%d iterations of a %d-path sample of the batch, all %d time steps, fwd+bwd+Adam (torch eager restatement "
-                         "of the reference solver, not TensorFlow)" % (n, a.cpu_paths, N), "ms_per_iteration": dt * 1e3}
+                         "of the reference solver, not TensorFlow)" % (n, cpu_paths, N), "ms_per_iteration": dt * 1e3}
 
     if rank == 0:
         line = {"metric": "path-steps/s", "value": value, "unit": "path-steps/s", "n_gpus": world, "steps": a.steps,
