@@ -181,3 +181,24 @@ def test_fixed_trajectory_replay_matches_host_recursion(ctx):
     solg = cm.MFGSolutionsFixedTrajectory(mm, kg, "Global", dW0, dW, dN, ctx=ctx)
     solg.simulateAllProcesses(nb)
     assert np.isfinite(solg.objectiveFunction()).all()
+
+
+def test_mfg_graph_replay_equals_stepwise_calls(ctx):
+    """The MFG training call (CUDA graph: Cox-count simulation -> two-network forward -> adjoint -> fused reduce + Adam)
+    against the same steps driven call by call."""
+    B, n, lr, seed = 200, 3, 1e-3, 17
+    P = H.mfg_params(1)
+    layout = H.mfg_layout("Global")
+    theta = H.random_theta(layout, 6)
+    a, b = H.native_mfg(ctx, P, "Global", layout), H.native_mfg(ctx, P, "Global", layout)
+    a.set_theta(theta); b.set_theta(theta)
+    a.reset_optimizer(); b.reset_optimizer()
+    a.train_steps(seed, B, n, lr)
+    for _ in range(n):
+        b.grad_step(seed, B, B, 0)
+        b.adam_step(lr)
+        b.bump_iteration()
+    ctx.sync()
+    ta, tb = a.get_theta(), b.get_theta()
+    assert np.isfinite(ta).all() and np.abs(ta - theta).max() > 0
+    assert np.abs(ta - tb).max() <= 1e-7 * max(1.0, np.abs(tb).max())
