@@ -284,6 +284,7 @@ void fill_mfg_args(const fbsdej_solver* s, const float* theta, int B, int B_glob
   const fbsdej_mfg_params& m = s->mfg;
   a.B = B; a.N = s->N; a.scheme = s->sch; a.has_y = s->has_y; a.has_z = s->has_z;
   a.stochastic = m.stochastic_jumps;
+  a.mma_mode = s->desc.mma_mode;
   a.inv_B = 1.0f / (float)B_global; a.w_hat = s->desc.w_hat; a.w_ind = s->desc.w_ind;
   a.dt = (float)(m.T / s->N); a.q0 = (float)s->q0; a.R0 = (float)m.R0; a.S0 = (float)m.S0;
   a.alpha = (float)m.alpha; a.beta = (float)m.beta; a.jumpFactor = (float)m.jumpFactor; a.coeffOU = (float)m.coeffOU;
@@ -309,13 +310,14 @@ int run_pass(fbsdej_solver* s, const float* theta, int B, int B_global, float* o
     MFGArgs a;
     fill_mfg_args(s, theta, B, B_global, a);
     const int ntiles = (B + kThreads - 1) / kThreads;
-    grid_f = std::min(ntiles, s->ctx->sms * mfg_blocks_per_sm(s->HP, a, false));
-    if (with_grad) grid_b = std::min(ntiles, s->ctx->sms * mfg_blocks_per_sm(s->HP, a, true));
+    const bool tc = a.mma_mode == 1;       // tcgen05 kernels: one CTA (two roles x 128 threads) per SM
+    grid_f = std::min(ntiles, s->ctx->sms * (tc ? 1 : mfg_blocks_per_sm(s->HP, a, false)));
+    if (with_grad) grid_b = std::min(ntiles, s->ctx->sms * (tc ? 1 : mfg_blocks_per_sm(s->HP, a, true)));
     if (ensure_grid(s, std::max(grid_f, grid_b))) return -2;
     a.lpart = s->lpart; a.gpart = s->gpart; a.trajY = trajY;
-    if (launch_mfg(s->HP, a, grid_f, false, st)) return -1;
+    if (tc ? launch_mfg_tc(a, grid_f, false, st) : launch_mfg(s->HP, a, grid_f, false, st)) return -1;
     if (ev) cudaEventRecord(ev[0], st);
-    if (with_grad && launch_mfg(s->HP, a, grid_b, true, st)) return -1;
+    if (with_grad && (tc ? launch_mfg_tc(a, grid_b, true, st) : launch_mfg(s->HP, a, grid_b, true, st))) return -1;
     if (ev) cudaEventRecord(ev[1], st);
   } else {
     PricingArgs a;
@@ -703,8 +705,11 @@ int fbsdej_solver_create(fbsdej_ctx* ctx, const fbsdej_solver_desc* desc, const 
   s->M = s->has_jump ? desc->M : 0;
   FB_REQUIRE(!s->has_jump || desc->M >= 1, "this scheme needs M >= 1 compensator samples");
   FB_REQUIRE(desc->mma_mode == 0 || desc->mma_mode == 1, "mma_mode must be 0 (FFMA) or 1 (tcgen05)");
-  FB_REQUIRE(desc->mma_mode == 0 || (reg && model != FBSDEJ_MODEL_MFG && HP == 24 && desc->nets[0].H <= 22),
-             "mma_mode = 1 (tcgen05) is available for the SUMLOCALREG / MULTISTEPREG pricing solvers with H <= 22");
+  FB_REQUIRE(desc->mma_mode == 0 ||
+                 (model == FBSDEJ_MODEL_MFG ? (desc->nets[0].H <= 22 && desc->nets[1].H <= 22 && desc->nets[0].act == desc->nets[1].act)
+                                            : (reg && HP == 24 && desc->nets[0].H <= 22)),
+             "mma_mode = 1 (tcgen05) is available for the SUMLOCALREG / MULTISTEPREG pricing solvers and for the MFG solvers, "
+             "hidden width <= 22");
   cudaStream_t st = ctx->stream;
   if (model == FBSDEJ_MODEL_MERTON) {
     if (build_merton_tables(s.get())) return -2;

@@ -8,6 +8,7 @@ struct MFGArgs {
   int B, N, scheme;          // SCH_*
   int has_y, has_z;          // nets output Y first (MultiStep/SumLocal/Reg); Z0/Gam(/Z) present (not Reg)
   int stochastic;            // jumpModel == 'stochastic'
+  int mma_mode;              // 0 = fp32 FFMA kernels (mfg_kernels.cu), 1 = tcgen05 kernels (mfg_tc_kernels.cu)
   float inv_B, w_hat, w_ind;
   float dt, q0, R0, S0;
   float alpha, beta, jumpFactor, coeffOU, A, K, pi, p0, p1, f0, f1, thetaR, C, h1, h2, sig0, sig, alphaTarget, coeffEqui;
@@ -26,6 +27,7 @@ struct MFGArgs {
 };
 
 int launch_mfg(int HP, const MFGArgs& a, int grid, bool backward, cudaStream_t st);
+int launch_mfg_tc(const MFGArgs& a, int grid, bool backward, cudaStream_t st);
 int launch_pricing(int model, int D, int HP, const PricingArgs& a, int grid, bool backward, cudaStream_t st);
 size_t pricing_smem_bytes(int HP, const PricingArgs& a, bool backward);
 size_t mfg_smem_bytes(int HP, const MFGArgs& a, bool backward);

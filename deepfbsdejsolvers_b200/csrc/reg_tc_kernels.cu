@@ -31,11 +31,11 @@
 #include "pricing.cuh"
 #include "sim_device.cuh"
 #include "tc.cuh"
+#include "tc_net.cuh"
 
 namespace fbsdej {
 namespace rtc {
 
-constexpr int NB = 24;                        // n-rows stored per chunk of a B operand
 namespace bwd {
 constexpr int CH = 128;                       // uint4 per chunk (128 rows x 16 bytes)
 constexpr int XA_HI = 0, XA_LO = 2 * CH, H1_HI = 4 * CH, H2_HI = 7 * CH, H1_LO = 10 * CH, H2_LO = 13 * CH, D2_HI = 16 * CH,
@@ -50,65 +50,6 @@ static_assert((OFF_BAR % 2) == 0, "mbarrier alignment");
 constexpr uint32_t C_ACC = 0, C_W1 = 48, C_W2 = 80, NCOLS = 128;   // ACC 48 | WG1 32 | WG2 48 columns
 constexpr int COL_DOUT = 23;                  // spare column of D2 that carries dL/dy through WG2 (needs H <= 22)
 }  // namespace bwd
-
-__device__ __forceinline__ void publish() {  // generic-proxy tile writes -> async proxy, then the CTA barrier
-  tc::fence_async_smem();
-  tc::tc_fence_before();
-  __syncthreads();
-}
-__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-
-// Layer GEMM, bf16x3 in TWO MMAs per 16-wide K slice: D[:, 0 .. 2 NH) = A_hi [B_hi | B_lo] (N = 2 NH), then
-// D[:, 0 .. N2) += A_lo [B_hi | ..] (N2 = NH rounded up to 16; the columns beyond NH pick up lo.lo terms, which belong to
-// the exact product).  The caller adds the column blocks [0, NH) and [NH, 2 NH) when it reads the accumulator.
-// A: K-major tile (128 rows); B: [k / 8][2 NH n-rows][8 bf16].
-template <int KS, int NH>
-__device__ __forceinline__ void gemm_k(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b) {
-  constexpr uint32_t id1 = tc::idesc_bf16(128, 2 * NH, false, false), id2 = tc::idesc_bf16(128, (NH + 15) / 16 * 16, false, false);
-  constexpr uint32_t chunk = 2 * NH * 16;
-#pragma unroll
-  for (int s = 0; s < KS; ++s) {
-    const uint64_t db = tc::smem_desc(b + s * 2 * chunk, chunk, 128);
-    tc::mma_bf16(tmem_d, tc::smem_desc(a_hi + s * 4096, 2048, 128), db, id1, s > 0 ? 1u : 0u);
-    tc::mma_bf16(tmem_d, tc::smem_desc(a_lo + s * 4096, 2048, 128), db, id2, 1u);
-  }
-}
-// this thread's row of a layer GEMM result: v[j] = D[j] + D[NH + j], j < NJ (NJ a multiple of 8)
-template <int NH, int NJ>
-__device__ __forceinline__ void load_acc(uint32_t lane_base, float (&v)[NJ]) {
-#pragma unroll
-  for (int c8 = 0; c8 < NJ / 8; ++c8) {
-    float p8[8], q8[8];
-    tc::tmem_ld8(lane_base + 8 * c8, p8);
-    tc::tmem_ld8(lane_base + NH + 8 * c8, q8);
-    tc::tmem_ld_wait();
-#pragma unroll
-    for (int q = 0; q < 8; ++q) v[8 * c8 + q] = p8[q] + q8[q];
-  }
-}
-// Weight-gradient GEMM over the 128 rows of the tile (rows are K, both operands MN-major).  The hi and lo copies of A
-// are contiguous along M and those of B along N, so ONE MMA per 16-row slice forms all four hi/lo cross products in
-// separate accumulator blocks:  D[m][n], m in [A_hi features | A_lo features], n in [B_hi | B_lo] (24 columns each).
-// The three blocks that matter (hi.hi, hi.lo, lo.hi) are added when the accumulators are read at the end of the kernel.
-template <int NN>
-__device__ __forceinline__ void gemm_rows_stacked(uint32_t tmem_d, uint32_t a, uint32_t b, uint32_t acc0) {
-  constexpr uint32_t id = tc::idesc_bf16(128, NN, true, true);
-#pragma unroll
-  for (int s = 0; s < 8; ++s)                       // 128 rows = 8 x 16
-    tc::mma_bf16(tmem_d, tc::smem_desc(a + s * 256, 128, 2048), tc::smem_desc(b + s * 256, 128, 2048), id, (s > 0) ? 1u : acc0);
-}
-
-__device__ __forceinline__ float rcp_fast(float x) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-template <int ACT>
-__device__ __forceinline__ float actf(float x) { return ACT == ACT_TANH ? tanh_fast(x) : fmaxf(x, 0.0f); }
-template <int ACT>
-__device__ __forceinline__ float dactf(float h) { return ACT == ACT_TANH ? fmaf(-h, h, 1.0f) : (h > 0.0f ? 1.0f : 0.0f); }
 
 template <class Model, int ACT>
 __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs a) {
@@ -411,40 +352,8 @@ constexpr int W1B_HI = 0, W1B_LO = W1B_HI + 4 * NB * 4, W2B_HI = W1B_LO + 4 * NB
 static_assert((OFF_BAR % 2) == 0, "mbarrier alignment");
 // tensor memory: two allocations (32 + 64 = 96 columns, so that five CTAs fit the 512 columns of an SM): the accumulator,
 // and the A operand hi (X: 16, H1: 24 columns) | lo
-constexpr uint32_t NCOLS_ACC = 32, NCOLS_A = 64, C_AHI = 0, C_ALO = 32;
+constexpr uint32_t NCOLS_ACC = 32, NCOLS_A = 64;
 
-// D[ACC] = A (tensor memory: lane = row, one TF32 element per column, KS slices of 8 columns; hi and lo copies)
-//          * B (shared memory [k/4][n][4], NB n-rows per chunk), N = 32, 3xTF32
-template <int KS>
-__device__ __forceinline__ void gemm_k_tf32(uint32_t tmem_acc, uint32_t tmem_a, uint32_t b_hi, uint32_t b_lo) {
-  constexpr uint32_t id = tc::idesc_tf32(128, 32, false, false);
-#pragma unroll
-  for (int s = 0; s < KS; ++s) {
-    const uint64_t dbh = tc::smem_desc(b_hi + s * (2 * NB * 16), NB * 16, 128), dbl = tc::smem_desc(b_lo + s * (2 * NB * 16), NB * 16, 128);
-    tc::mma_tf32_ts(tmem_acc, tmem_a + C_AHI + 8 * s, dbh, id, s > 0 ? 1u : 0u);
-    tc::mma_tf32_ts(tmem_acc, tmem_a + C_ALO + 8 * s, dbh, id, 1u);
-    tc::mma_tf32_ts(tmem_acc, tmem_a + C_AHI + 8 * s, dbl, id, 1u);
-  }
-}
-// 8 consecutive features of this thread's row -> TF32 hi / lo columns of the A operand in tensor memory
-__device__ __forceinline__ void store_tf32x8(uint32_t lane_base /* of the A allocation */, int c8, const float* v) {
-  uint32_t h[8], l[8];
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    float hi, lo;
-    tc::split_tf32(v[q], hi, lo);
-    h[q] = __float_as_uint(hi); l[q] = __float_as_uint(lo);
-  }
-  tc::tmem_st8(lane_base + C_AHI + 8 * c8, h);
-  tc::tmem_st8(lane_base + C_ALO + 8 * c8, l);
-}
-// TMEM operand writes (+ the bias row in shared memory) -> visible to the MMA issued after the CTA barrier
-__device__ __forceinline__ void publish_tmem() {
-  tc::tmem_st_wait();
-  tc::fence_async_smem();
-  tc::tc_fence_before();
-  __syncthreads();
-}
 }  // namespace fwd
 
 // OCC = resident CTAs per SM the kernel is compiled for: 5 (<= 102 registers) pays off when every SM gets at least five

@@ -93,7 +93,7 @@ typedef struct {
   int mma_mode;         /* 0 = every layer in fp32 FFMA; 1 = every matrix product of the network on tcgen05 tensor cores
                            (forward: both layers 3xTF32 with the A operands in TMEM; adjoint: six bf16x3 GEMMs per step,
                            weight-gradient accumulators resident in TMEM).  Available for the compensator-free solvers
-                           (SUMLOCALREG / MULTISTEPREG) of the pricing models, H <= 22, one network output. */
+                           (SUMLOCALREG / MULTISTEPREG) of the pricing models and for all five MFG solvers, H <= 22. */
 } fbsdej_solver_desc;
 
 FBSDEJ_API const char* fbsdej_last_error(void);

@@ -131,9 +131,9 @@ def native_pricing(ctx, kind, params, scheme, layout, d=1, M=0, limit=30, stale_
     return mm.make_solver(PRICING_SCHEME_ID[scheme], nets, layout.n_y0, M, ctx=ctx, stale_time=stale_time, tensor_cores=tensor_cores)
 
 
-def native_mfg(ctx, params, scheme, layout):
+def native_mfg(ctx, params, scheme, layout, tensor_cores=False):
     from deepfbsdejsolvers_b200 import NetSpec
     from deepfbsdejsolvers_b200.coupledMFG import ModelCoupledFBSDE
     mm = ModelCoupledFBSDE(**params)
     nets = [NetSpec(n.nin, n.hidden[0], n.nout, n.activation) for n in layout.nets]
-    return mm.make_solver(MFG_SCHEME_ID[scheme], nets, layout.n_y0, ctx=ctx)
+    return mm.make_solver(MFG_SCHEME_ID[scheme], nets, layout.n_y0, ctx=ctx, tensor_cores=tensor_cores)

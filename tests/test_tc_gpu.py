@@ -110,3 +110,31 @@ def test_tensor_core_path_shapes_and_relu(ctx, act, B, Hn):
     s.set_theta(theta)
     s.set_noise(B, H.to_planes(noise["dW"]), H.to_planes(noise["J"]), None)
     _check(s, B, l64, g64, g32, aux64, d)
+
+
+from oracle import MFGOracle
+
+
+@pytest.mark.parametrize("scheme", ["Global", "MultiStep", "SumLocal", "SumLocalReg", "MultiStepReg"])
+@pytest.mark.parametrize("jumpModel,B", [("stochastic", 130), ("constant", 64)])
+def test_mfg_tensor_core_path_matches_oracle(ctx, scheme, jumpModel, B):
+    """The tcgen05 MFG kernels (two networks side by side, nout up to 4) against the float64 oracle on injected increments."""
+    from oracle.mfg import sample_mfg_noise
+    p = H.mfg_params(1, jumpModel)
+    om = MFGOracle(**p)
+    layout = H.mfg_layout(scheme)
+    theta = H.random_theta(layout, 4)
+    noise = sample_mfg_noise(om, B, torch.Generator().manual_seed(8))
+    (lh32, li32), g32, _ = H.oracle_mfg(om, scheme, layout, theta, noise, B)
+    (lh64, li64), g64, aux64 = H.oracle_mfg(om, scheme, layout, theta, noise, B, dtype=torch.float64)
+    s = H.native_mfg(ctx, p, scheme, layout, tensor_cores=True)
+    s.set_theta(theta)
+    s.set_noise(B, noise["dW0"].numpy(), noise["dW"].numpy(), noise["dN"].numpy())
+    out, tx, ty, _ = s.loss(B, traj=True)
+    assert abs(out[1] - lh64) <= 3e-5 * abs(lh64) and abs(out[2] - li64) <= 3e-5 * abs(li64), (out, lh64, li64)
+    assert np.abs(tx[:, 0, :] - aux64["hS"]).max() <= 2e-5 and np.abs(tx[:, 1, :] - aux64["S"]).max() <= 2e-5
+    g = s.grad(B)
+    scale = np.abs(g64).max()
+    e_gpu, e_32 = np.abs(g[4:] - g64).max() / scale, np.abs(g32 - g64).max() / scale
+    print(scheme, jumpModel, "loss rel", abs(out[0] - lh64 - li64) / abs(lh64 + li64), "grad rel-to-max", e_gpu, "(fp32 oracle", e_32, ")")
+    assert e_gpu <= 3e-4, f"gradient error {e_gpu:.3e}"
