@@ -22,9 +22,11 @@ class SolverBase:
     SCHEME = L.GLOBAL
     REG = False
 
-    def __init__(self, mathModel, modelKeras, lRate, couplage, seed: int = 0, ctx=None):
+    def __init__(self, mathModel, modelKeras, lRate, couplage, seed: int = 0, ctx=None, tensor_cores=None):
         self.mathModel, self.modelKeras, self.lRate, self.couplage = mathModel, modelKeras, lRate, couplage
         self.seed, self.ctx, self.native = seed, ctx, None
+        # tcgen05 kernels (csrc/mfg_tc_kernels.cu; tests/test_tc_gpu.py): None = automatic, on when both networks fit them
+        self.tensor_cores = tensor_cores
 
     # expected output widths (mainMFGComparison.py:119-124)
     def _widths(self):
@@ -42,7 +44,10 @@ class SolverBase:
         if (hat.ndimOut, ind.ndimOut) != (wh, wi):
             raise ValueError(f"{type(self).__name__}: networks must have ndimOut ({wh}, {wi}), got ({hat.ndimOut}, {ind.ndimOut})")
         n_y0 = 2 if self.SCHEME == L.GLOBAL else 0
-        self.native = self.mathModel.make_solver(self.SCHEME, [hat.spec(), ind.spec()], n_y0, ctx=self.ctx)
+        sh, si = hat.spec(), ind.spec()
+        tc_ok = sh.H <= 22 and si.H <= 22 and sh.L == 2 and si.L == 2 and sh.activation == si.activation
+        use_tc = tc_ok if self.tensor_cores is None else bool(self.tensor_cores)
+        self.native = self.mathModel.make_solver(self.SCHEME, [sh, si], n_y0, ctx=self.ctx, tensor_cores=use_tc)
         parts = [hat.params, ind.params]
         if n_y0:
             parts.append(np.array([hat.Y0_hat.numpy(), ind.Y0.numpy()], dtype=np.float32))
