@@ -87,6 +87,64 @@ def main():
         ms = time_solver(solver, B, a.iters, ctx)
         out.append({"config": "4 mainMFGComparison.py", "solver": name, "paths": B, "time_steps": mm.N, "M": 0,
                     "ms_per_iter": ms, "iters_per_s": 1e3 / ms, "path_steps_per_s": B * mm.N * 1e3 / ms})
+    if a.cpu:
+        # the reference-equivalent CPU restatement (oracle/: torch eager + autograd + Keras-form Adam) on the same shapes, noise
+        # drawn on the CPU the way the reference draws it; median of 3 iterations after one warm-up
+        import torch
+        from oracle import MertonOracle, VGOracle, MFGOracle, KerasAdam, pricing_loss, mfg_loss
+        from oracle.pricing import sample_pricing_noise
+        from oracle.mfg import sample_mfg_noise
+        gen = torch.Generator().manual_seed(0)
+
+        def cpu_ms(make_it):
+            it = make_it()
+            it()
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter(); it(); ts.append(time.perf_counter() - t0)
+            return 1e3 * float(np.median(ts))
+
+        def pricing_it(kind, model, scheme, B, Mc):
+            layout = H.pricing_layout(kind, scheme, 1)
+            theta = torch.tensor(H.random_theta(layout, 0), requires_grad=True)
+            opt = KerasAdam(layout.total, 3e-4)
+
+            def it():
+                noise = sample_pricing_noise(model, scheme, B, max(Mc, 1), gen)
+                theta.grad = None
+                loss = pricing_loss(model, scheme, layout, theta, noise, B)
+                loss.backward()
+                opt.step(theta.data, theta.grad)
+            return it
+
+        def mfg_it(model, scheme, B):
+            layout = H.mfg_layout(scheme)
+            theta = torch.tensor(H.random_theta(layout, 0), requires_grad=True)
+            opt = KerasAdam(layout.total, 1e-3)
+
+            def it():
+                noise = sample_mfg_noise(model, B, gen)
+                theta.grad = None
+                lh, li = mfg_loss(model, scheme, layout, theta, noise, B)
+                (lh + li).backward()
+                opt.step(theta.data, theta.grad)
+            return it
+
+        scheme_of = {"SolverGlobalFBSDE": "Global", "SolverMultiStepFBSDE1": "MultiStep1", "SolverMultiStepFBSDE2": "MultiStep2",
+                     "SolverSumLocalFBSDE1": "SumLocal1", "SolverSumLocalFBSDE2": "SumLocal2", "SolverGlobalSumLocalReg": "SumLocalReg",
+                     "SolverGlobalMultiStepReg": "MultiStepReg", "SolverMultiStepFBSDE": "MultiStep", "SolverSumLocalFBSDE": "SumLocal"}
+        om = MertonOracle(aLin=0.1, limit=30, d=1, **H.MERTON)
+        ov = VGOracle(aLin=0.1, **H.VG)
+        og = MFGOracle(**P)
+        for o in out:
+            sch = scheme_of[o["solver"]]
+            if o["config"].startswith("1"):
+                ms = cpu_ms(lambda: pricing_it("merton", om, sch, o["paths"], o["M"]))
+            elif o["config"].startswith("2"):
+                ms = cpu_ms(lambda: pricing_it("vg", ov, sch, o["paths"], o["M"]))
+            else:
+                ms = cpu_ms(lambda: mfg_it(og, sch, o["paths"]))
+            o["cpu_ms_per_iter"], o["cpu_threads"], o["speedup_vs_cpu"] = ms, torch.get_num_threads(), ms / o["ms_per_iter"]
     for o in out:
         print(json.dumps(o))
 
