@@ -55,8 +55,10 @@ def workload_config(a, B, world):
             % ("Global" + a.solver if a.solver.endswith("Reg") else a.solver + "FBSDE", "" if M == 0 else " M=%d" % M, B,
                "3" if world == 1 else "5"))
     return M, {"workload": name, "paths": B, "time_steps": MERTON["N"], "d": D, "hidden": H_WIDTH, "solver": a.solver,
-               "compensator_M": M, "mma": a.mma, "parallelism": "dp%d" % world, "l2_policy": "inputs exceed L2 (path tensors %.0f MB per rank)"
-               % (2 * MERTON["N"] * D * (B // world) * 4 / 1e6)}
+               "compensator_M": M, "mma": a.mma, "parallelism": "dp%d" % world,
+               "l2_policy": "working set exceeds L2: %.0f MB of per-path-step records per rank are written by the forward sweep and "
+                            "read back by the adjoint every step (126 MB L2); no flush needed"
+               % ((2 * D + 3) * MERTON["N"] * (B // world) * 4 / 1e6)}
 
 
 # ---------------------------------------------------------------------------------------------------------------
