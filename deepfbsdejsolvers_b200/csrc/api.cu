@@ -204,7 +204,7 @@ int ensure_capacity(fbsdej_solver* s, int B) {
   } else {
     if (s->model == FBSDEJ_MODEL_MERTON && dev_alloc(&s->nA, N * D * b)) return -2;
     if (dev_alloc(&s->nB, N * D * b)) return -2;
-    if (s->desc.mma_mode == 1) {
+    if (s->desc.mma_mode == 1 && !s->has_jump) {
       const size_t nt = (b + kThreads - 1) / kThreads;
       if (dev_alloc(&s->rec, nt * N * (2 * D + 3) * kThreads) || dev_alloc(&s->recN, nt * (D + 1) * kThreads)) return -2;
     } else {
@@ -705,11 +705,15 @@ int fbsdej_solver_create(fbsdej_ctx* ctx, const fbsdej_solver_desc* desc, const 
   s->M = s->has_jump ? desc->M : 0;
   FB_REQUIRE(!s->has_jump || desc->M >= 1, "this scheme needs M >= 1 compensator samples");
   FB_REQUIRE(desc->mma_mode == 0 || desc->mma_mode == 1, "mma_mode must be 0 (FFMA) or 1 (tcgen05)");
+  // tcgen05 coverage: the compensator-free pricing solvers, the MFG solvers, and the jump network of the two-network jump
+  // schemes at d = 1 (one output, tanh)
+  const bool jtc_ok = s->has_jump && !one_net && s->D == 1 && HP == 24 && desc->nets[1].H <= 22 && desc->nets[1].nout == 1 &&
+                      desc->nets[1].act == FBSDEJ_ACT_TANH;
   FB_REQUIRE(desc->mma_mode == 0 ||
                  (model == FBSDEJ_MODEL_MFG ? (desc->nets[0].H <= 22 && desc->nets[1].H <= 22 && desc->nets[0].act == desc->nets[1].act)
-                                            : (reg && HP == 24 && desc->nets[0].H <= 22)),
-             "mma_mode = 1 (tcgen05) is available for the SUMLOCALREG / MULTISTEPREG pricing solvers and for the MFG solvers, "
-             "hidden width <= 22");
+                                            : ((reg && HP == 24 && desc->nets[0].H <= 22) || jtc_ok)),
+             "mma_mode = 1 (tcgen05) is available for the SUMLOCALREG / MULTISTEPREG pricing solvers, for the MFG solvers and for "
+             "the two-network jump schemes at d = 1 with a tanh jump network; hidden width <= 22");
   cudaStream_t st = ctx->stream;
   if (model == FBSDEJ_MODEL_MERTON) {
     if (build_merton_tables(s.get())) return -2;
@@ -805,7 +809,7 @@ int fbsdej_solver_loss(fbsdej_solver* s, const float* theta, int B, int B_global
       for (int i = 0; i <= s->N; ++i)
         FB_CUDA(cudaMemcpyAsync(trajX + (size_t)i * 2 * B, s->trajX + ((size_t)i * 5 + 3) * B, sizeof(float) * 2 * B,
                                 cudaMemcpyDeviceToDevice, s->ctx->stream));
-    } else if (s->desc.mma_mode == 1) {
+    } else if (s->desc.mma_mode == 1 && !s->has_jump) {
       if (launch_untile_traj(s->D, s->rec, s->recN, B, s->N, trajX, s->ctx->stream)) return -1;
     } else {
       FB_CUDA(cudaMemcpyAsync(trajX, s->trajX, sizeof(float) * (size_t)(s->N + 1) * s->D * B, cudaMemcpyDeviceToDevice,

@@ -1,0 +1,343 @@
+// The jump network on tensor cores inside the jump-scheme kernels (pricing_kernels.cu, template flag JTC): the rows of one
+// path-step - the path's own jump and the Monte-Carlo compensator samples (SolversJumpDiff.py:37-41, SolversPureJump.py:34-38)
+// - are evaluated 128 at a time as one tcgen05 tile: row r of the tile = sample r, thread r = TMEM lane r.
+//
+//   JumpTcFwd::eval  : y = W3 . act(W2 . act(W1 x))   both layers 3xTF32, A operands in TMEM (as reg_forward_tc)
+//   JumpTcBwd::step  : recompute, delta pass, dL/dx, weight gradients accumulated in TMEM over every tile, step and path of
+//                      the CTA, six bf16x3 GEMMs (as reg_backward_tc); read once at kernel end (flush)
+//
+// The network has one output and nin <= 14 inputs (two-network schemes, d = 1: nin = 3).  The time feature is folded
+// into a per-step effective bias (set_time).  Building blocks: tc_net.cuh.
+#pragma once
+#include "tc_net.cuh"
+
+namespace fbsdej {
+
+template <int ACT>
+struct JumpTcFwd {
+  // shared memory (floats): B operands of the two layers (TF32 hi / lo), W3 + b3, the mbarrier, the TMEM slots
+  static constexpr int NBR = rtc::NB;
+  static constexpr int W1B_HI = 0, W1B_LO = W1B_HI + 4 * NBR * 4, W2B_HI = W1B_LO + 4 * NBR * 4, W2B_LO = W2B_HI + 6 * NBR * 4,
+                       OFF_W3 = W2B_LO + 6 * NBR * 4 + 32, OFF_BAR = OFF_W3 + 32, FLOATS = OFF_BAR + 8;
+  float* sm;
+  uint64_t* bar;
+  uint32_t tmem, tmem_a, lane_base, lane_a, phase, sbase;
+  float w0, b1v;
+  int H, nin, bias_idx;
+
+  __device__ void init(float* smem, const float* __restrict__ theta, const NetRt& rt) {   // all threads; ends with a barrier
+    sm = smem; H = rt.H; nin = rt.nin; phase = 0;
+    bar = reinterpret_cast<uint64_t*>(sm + OFF_BAR);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(sm + OFF_BAR + 2);
+    const int row = threadIdx.x;
+    for (int i = row; i < FLOATS; i += kThreads) sm[i] = 0.0f;
+    __syncthreads();
+    const float* __restrict__ th = theta + rt.ext_off;
+    const int n1 = nin * H, n2 = n1 + H, n3 = n2 + H * H, n4 = n3 + H, n5 = n4 + H;
+    w0 = 0.0f; b1v = 0.0f;
+    if (row < H) { w0 = th[row]; b1v = th[n1 + row]; }
+    for (int e = row; e <= n5; e += kThreads) {
+      float hi, lo;
+      if (e < n1) {
+        const int i = e / H, j = e % H;
+        if (i >= 1) {
+          tc::split_tf32(th[e], hi, lo);
+          sm[W1B_HI + ((i >> 2) * NBR + j) * 4 + (i & 3)] = hi;
+          sm[W1B_LO + ((i >> 2) * NBR + j) * 4 + (i & 3)] = lo;
+        }
+      } else if (e < n2) {
+      } else if (e < n4) {
+        const int k = e < n3 ? (e - n2) / H : H, j = e < n3 ? (e - n2) % H : e - n3;
+        tc::split_tf32(th[e], hi, lo);
+        sm[W2B_HI + ((k >> 2) * NBR + j) * 4 + (k & 3)] = hi;
+        sm[W2B_LO + ((k >> 2) * NBR + j) * 4 + (k & 3)] = lo;
+      } else {
+        sm[OFF_W3 + (e < n5 ? e - n4 : 24)] = th[e];      // W3[k], k < H; b3 at index 24
+      }
+    }
+    if (row < 32) { tc::tmem_alloc(tslot, 32, false); tc::tmem_alloc(tslot + 1, 64); }
+    if (row == 0) { tc::mbar_init(bar, 1); tc::fence_mbar_init(); }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    tmem = tslot[0]; tmem_a = tslot[1];
+    lane_base = tmem + ((uint32_t)(row & ~31) << 16);
+    lane_a = tmem_a + ((uint32_t)(row & ~31) << 16);
+    sbase = tc::smem_u32(sm);
+    bias_idx = ((nin >> 2) * NBR + row) * 4 + (nin & 3);
+  }
+  // effective layer-1 bias c_j = t W1[0][j] + b1[j]; visible to the MMA after the next eval's first barrier
+  __device__ __forceinline__ void set_time(float t) {
+    const int row = threadIdx.x;
+    if (row <= H) {
+      float hi, lo;
+      tc::split_tf32(row < H ? fmaf(t, w0, b1v) : (ACT == ACT_TANH ? 20.0f : 1.0f), hi, lo);
+      sm[W1B_HI + bias_idx] = hi;
+      sm[W1B_LO + bias_idx] = lo;
+    }
+  }
+  // xin: this row's inputs, xin[0] = 0 (time), xin[nin] = 1.  Every thread of the CTA calls (barriers inside).
+  __device__ __forceinline__ float eval(const float (&xin)[16]) {
+    using namespace rtc;
+    const int row = threadIdx.x, warp = row >> 5;
+    fwd::store_tf32x8(lane_a, 0, xin);
+    fwd::store_tf32x8(lane_a, 1, xin + 8);
+    fwd::publish_tmem();
+    if (row == 0) {
+      tc::tc_fence_after();
+      fwd::gemm_k_tf32<2>(tmem, tmem_a, sbase + W1B_HI * 4, sbase + W1B_LO * 4);
+      tc::mma_commit(bar);
+    }
+    tc::mbar_wait(bar, phase); phase ^= 1; tc::tc_fence_after();
+#pragma unroll
+    for (int c8 = 0; c8 < 3; ++c8) {
+      float t8[8];
+      tc::tmem_ld8(lane_base + 8 * c8, t8);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t8[q] = actf<ACT>(t8[q]);
+      fwd::store_tf32x8(lane_a, c8, t8);
+    }
+    fwd::publish_tmem();
+    if (warp == 1 && (row & 31) == 0) {
+      tc::tc_fence_after();
+      fwd::gemm_k_tf32<3>(tmem, tmem_a, sbase + W2B_HI * 4, sbase + W2B_LO * 4);
+      tc::mma_commit(bar);
+    }
+    tc::mbar_wait(bar, phase); phase ^= 1; tc::tc_fence_after();
+    float y = sm[OFF_W3 + 24];
+#pragma unroll
+    for (int c8 = 0; c8 < 3; ++c8) {
+      float t8[8];
+      tc::tmem_ld8(lane_base + 8 * c8, t8);
+      tc::tmem_ld_wait();
+      const float4 wa = ld4(sm + OFF_W3 + 8 * c8), wb = ld4(sm + OFF_W3 + 8 * c8 + 4);
+      const float w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+      for (int q = 0; q < 8; ++q) y = fmaf(actf<ACT>(t8[q]), w8[q], y);
+    }
+    tc::tc_fence_before();
+    return y;
+  }
+  __device__ void finish() {
+    tc::tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) { tc::tmem_dealloc(tmem, 32); tc::tmem_dealloc(tmem_a, 64); }
+  }
+};
+
+template <int ACT>
+struct JumpTcBwd {
+  static constexpr int CH = 128, NBR = rtc::NB;
+  // uint4 offsets: operand tiles, then the stacked B operands (as reg_backward_tc)
+  static constexpr int XA_HI = 0, XA_LO = 2 * CH, H1_HI = 4 * CH, H2_HI = 7 * CH, H1_LO = 10 * CH, H2_LO = 13 * CH, D2_HI = 16 * CH,
+                       D2_LO = 19 * CH, D1_HI = H2_HI, D1_LO = H1_LO, W_BASE = 22 * CH;
+  static constexpr int W1B = W_BASE, W2B = W1B + 2 * 2 * NBR, WTB = W2B + 4 * 2 * NBR, W1T = WTB + 4 * 2 * NBR, U4_END = W1T + 4 * 2 * 16;
+  static constexpr int OFF_W3 = U4_END * 4, OFF_BAR = OFF_W3 + 24, FLOATS = OFF_BAR + 8;
+  static constexpr uint32_t C_ACC = 0, C_W1 = 48, C_W2 = 80, NCOLS = 128;
+  static constexpr int COL_DOUT = 23, SW = 49;
+  float* sm;
+  uint4* u4;
+  uint64_t* bar_f;
+  uint64_t* bar_w;
+  uint32_t tmem, lane_base, sbase, phase_f, phase_w, pending_w, started;
+  float w0, b1v;
+  int H, nin, bias_idx;
+
+  __device__ void init(float* smem, const float* __restrict__ theta, const NetRt& rt) {
+    sm = smem; u4 = reinterpret_cast<uint4*>(smem); H = rt.H; nin = rt.nin;
+    phase_f = phase_w = pending_w = started = 0;
+    bar_f = reinterpret_cast<uint64_t*>(sm + OFF_BAR);
+    bar_w = bar_f + 1;
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(sm + OFF_BAR + 4);
+    const int row = threadIdx.x;
+    for (int i = row; i < FLOATS; i += kThreads) sm[i] = 0.0f;
+    __syncthreads();
+    const float* __restrict__ th = theta + rt.ext_off;
+    const int n1 = nin * H, n2 = n1 + H, n3 = n2 + H * H, n4 = n3 + H, n5 = n4 + H;
+    unsigned short* const w1 = reinterpret_cast<unsigned short*>(u4 + W1B);
+    unsigned short* const w2 = reinterpret_cast<unsigned short*>(u4 + W2B);
+    unsigned short* const wt = reinterpret_cast<unsigned short*>(u4 + WTB);
+    unsigned short* const w1t = reinterpret_cast<unsigned short*>(u4 + W1T);
+    auto put = [](unsigned short* w, int NH, int n, int k, uint32_t hi, uint32_t lo) {
+      w[((k >> 3) * 2 * NH + n) * 8 + (k & 7)] = (unsigned short)hi;
+      w[((k >> 3) * 2 * NH + NH + n) * 8 + (k & 7)] = (unsigned short)lo;
+    };
+    for (int e = row; e < n5 + 1; e += kThreads) {
+      uint32_t hi, lo;
+      if (e < n2) {
+        const int i = e < n1 ? e / H : nin, j = e < n1 ? e % H : e - n1;
+        tc::split_bf16(th[e], hi, lo);
+        if (i >= 1 && i < nin) put(w1, NBR, j, i, hi, lo);
+        if (i < nin) put(w1t, 16, i, j, hi, lo);
+      } else if (e < n4) {
+        const int k = e < n3 ? (e - n2) / H : H, j = e < n3 ? (e - n2) % H : e - n3;
+        tc::split_bf16(th[e], hi, lo);
+        put(w2, NBR, j, k, hi, lo);
+        if (k < H) put(wt, NBR, k, j, hi, lo);
+      } else if (e < n5) {
+        sm[OFF_W3 + (e - n4)] = th[e];
+      } else {
+        tc::split_bf16(ACT == ACT_TANH ? 20.0f : 1.0f, hi, lo);
+        put(w2, NBR, H, H, hi, lo);
+      }
+    }
+    w0 = 0.0f; b1v = 0.0f;
+    if (row < H) { w0 = th[row]; b1v = th[n1 + row]; }
+    if (row < 32) tc::tmem_alloc(tslot, NCOLS);
+    if (row == 0) { tc::mbar_init(bar_f, 1); tc::mbar_init(bar_w, 1); tc::fence_mbar_init(); }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    tmem = *tslot;
+    lane_base = tmem + ((uint32_t)(row & ~31) << 16);
+    sbase = tc::smem_u32(u4);
+    bias_idx = ((nin >> 3) * 2 * NBR + row) * 8 + (nin & 7);
+  }
+  __device__ __forceinline__ uint32_t sa(int off_u4) const { return sbase + (uint32_t)off_u4 * 16u; }
+  __device__ __forceinline__ void wait_f() { tc::mbar_wait(bar_f, phase_f); phase_f ^= 1; tc::tc_fence_after(); }
+  __device__ __forceinline__ void drain_w() {
+    if (pending_w) { tc::mbar_wait(bar_w, phase_w); phase_w ^= 1; pending_w = 0; }
+  }
+  // effective layer-1 bias of the step; the previous tile's GEMMs that read the bias row have completed (their results were
+  // waited for), so the row can be rewritten right away; the next step()'s first barrier publishes it
+  __device__ __forceinline__ void set_time(float t) {
+    const int row = threadIdx.x;
+    if (row <= H) {
+      uint32_t hi, lo;
+      tc::split_bf16(row < H ? fmaf(t, w0, b1v) : (ACT == ACT_TANH ? 20.0f : 1.0f), hi, lo);
+      reinterpret_cast<unsigned short*>(u4 + W1B)[bias_idx] = (unsigned short)hi;
+      reinterpret_cast<unsigned short*>(u4 + W1B)[bias_idx + NBR * 8] = (unsigned short)lo;
+    }
+  }
+  // One tile: xin = this row's inputs (xin[0] = time for dW1, xin[nin] = 1), dout = adjoint of the row's output (0 for rows
+  // that do not count).  dx[i] = dL/d xin[i], i < 8.  Every thread of the CTA calls.
+  __device__ __forceinline__ void step(const float (&xin)[16], float dout, float (&dx)[8]) {
+    using namespace rtc;
+    const int row = threadIdx.x, warp = row >> 5;
+    const bool issuer = (row & 31) == 0;
+    drain_w();                                         // WG1 of the previous tile read X, D1
+    tc::store_bf16x8(u4 + XA_HI, u4 + XA_LO, 0, row, xin);
+    tc::store_bf16x8(u4 + XA_HI, u4 + XA_LO, 1, row, xin + 8);
+    publish();
+    if (warp == 0 && issuer) {
+      tc::tc_fence_after();
+      gemm_k<1, NBR>(tmem + C_ACC, sa(XA_HI), sa(XA_LO), sa(W1B));
+      tc::mma_commit(bar_f);
+    }
+    wait_f();
+    float h1[24];
+    load_acc<NBR, 24>(lane_base + C_ACC, h1);
+#pragma unroll
+    for (int c8 = 0; c8 < 3; ++c8) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) h1[8 * c8 + q] = actf<ACT>(h1[8 * c8 + q]);
+      tc::store_bf16x8(u4 + H1_HI, u4 + H1_LO, c8, row, h1 + 8 * c8);
+    }
+    publish();
+    if (warp == 1 && issuer) {
+      tc::tc_fence_after();
+      gemm_k<2, NBR>(tmem + C_ACC, sa(H1_HI), sa(H1_LO), sa(W2B));
+      tc::mma_commit(bar_f);
+    }
+    wait_f();
+#pragma unroll
+    for (int c8 = 0; c8 < 3; ++c8) {
+      float t8[8], d2[8];
+      {
+        float q8[8];
+        tc::tmem_ld8(lane_base + C_ACC + 8 * c8, t8);
+        tc::tmem_ld8(lane_base + C_ACC + NBR + 8 * c8, q8);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t8[q] += q8[q];
+      }
+      const float4 wa = ld4(sm + OFF_W3 + 8 * c8), wb = ld4(sm + OFF_W3 + 8 * c8 + 4);
+      const float w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float h = actf<ACT>(t8[q]);
+        t8[q] = h;
+        d2[q] = dout * w8[q] * dactf<ACT>(h);
+      }
+      if (c8 == 2) d2[COL_DOUT - 16] = dout;
+      tc::store_bf16x8(u4 + H2_HI, u4 + H2_LO, c8, row, t8);
+      tc::store_bf16x8(u4 + D2_HI, u4 + D2_LO, c8, row, d2);
+    }
+    publish();
+    if (warp == 2 && issuer) {
+      tc::tc_fence_after();
+      gemm_rows_stacked<48>(tmem + C_W2, sa(H1_HI), sa(D2_HI), started ? 1u : 0u);
+      gemm_k<2, NBR>(tmem + C_ACC, sa(D2_HI), sa(D2_LO), sa(WTB));
+      tc::mma_commit(bar_f);
+    }
+    wait_f();
+#pragma unroll
+    for (int c8 = 0; c8 < 3; ++c8) {
+      float t8[8], q8[8];
+      tc::tmem_ld8(lane_base + C_ACC + 8 * c8, t8);
+      tc::tmem_ld8(lane_base + C_ACC + NBR + 8 * c8, q8);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t8[q] = (t8[q] + q8[q]) * dactf<ACT>(h1[8 * c8 + q]);
+      tc::store_bf16x8(u4 + D1_HI, u4 + D1_LO, c8, row, t8);
+    }
+    publish();
+    if (warp == 3 && issuer) {
+      tc::tc_fence_after();
+      gemm_k<2, 16>(tmem + C_ACC, sa(D1_HI), sa(D1_LO), sa(W1T));
+      tc::mma_commit(bar_f);
+      gemm_rows_stacked<32>(tmem + C_W1, sa(D1_HI), sa(XA_HI), started ? 1u : 0u);
+      tc::mma_commit(bar_w);
+    }
+    started = 1;
+    pending_w = 1;
+    wait_f();
+    load_acc<16, 8>(lane_base + C_ACC, dx);
+    tc::tc_fence_before();
+  }
+  // TMEM weight gradients -> g[...] (external flat layout of this network, zeroed by the caller).  All threads call; the
+  // operand tiles are dead and serve as scratch.
+  __device__ void flush(float* __restrict__ g) {
+    const int row = threadIdx.x;
+    drain_w();
+    tc::tc_fence_after();
+    __syncthreads();
+    float* const S = sm;
+    const int o2 = nin * H + H, o3 = o2 + H * H + H;
+    for (int pass = 0; pass < 2; ++pass) {
+      __syncthreads();
+      if (started) {
+#pragma unroll
+        for (int c8 = 0; c8 < 6; ++c8) {
+          if (pass == 0 && c8 >= 4) break;
+          float v[8];
+          tc::tmem_ld8(lane_base + (pass == 0 ? C_W1 : C_W2) + 8 * c8, v);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) S[row * SW + 8 * c8 + q] = v[q];
+        }
+      }
+      __syncthreads();
+      if (started && pass == 0) {
+        for (int e = row; e < (nin + 1) * H; e += kThreads) {
+          const int i = e / H, j = e % H;
+          g[e] = S[j * SW + i] + S[j * SW + 16 + i] + S[(24 + j) * SW + i];
+        }
+      } else if (started) {
+        for (int e = row; e < (H + 1) * H; e += kThreads) {
+          const int k = e / H, j = e % H;
+          g[o2 + e] = S[k * SW + j] + S[k * SW + 24 + j] + S[(48 + k) * SW + j];
+        }
+        if (row <= H) g[o3 + row] = S[(24 + row) * SW + COL_DOUT] + S[(24 + row) * SW + 24 + COL_DOUT] + S[(72 + row) * SW + COL_DOUT];
+      }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (row < 32) tc::tmem_dealloc(tmem, NCOLS);
+  }
+};
+
+}  // namespace fbsdej

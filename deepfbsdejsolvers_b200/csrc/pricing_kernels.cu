@@ -13,9 +13,13 @@
 // :236-269/:315-347 (SumLocal1/2), :391-415 (SumLocalReg), :461-481 (MultiStepReg); SolversPureJump.py same.
 #include "pricing.cuh"
 #include <type_traits>
-#include <cooperative_groups.h>
+#include "cluster.cuh"
+#include "jump_tc.cuh"
 
 namespace fbsdej {
+
+// JTC kernels: the tensor-core block of the jump network sits at the start of shared memory (1024-byte aligned)
+constexpr int kJtcFwdFloats = (JumpTcFwd<ACT_TANH>::FLOATS + 31) & ~31, kJtcBwdFloats = (JumpTcBwd<ACT_TANH>::FLOATS + 31) & ~31;
 
 int launch_reg_tc_backward(int model, int D, const PricingArgs& a, int grid, cudaStream_t st);   // reg_tc_kernels.cu
 int launch_reg_tc_forward(int model, int D, const PricingArgs& a, int grid, cudaStream_t st);
@@ -23,57 +27,27 @@ size_t reg_tc_backward_smem();
 size_t reg_tc_forward_smem();
 int reg_tc_forward_occupancy(int B, int sms);
 
-__device__ __forceinline__ float group_allsum(float v, int G, float* red) {
-  if (G <= 32) return group_sum_shfl(v, G);
-  return block_sum(v, red);   // G == kThreads: one path per CTA
-}
-
-// Small batches (the reference's B = 10): a thread-block CLUSTER of C CTAs shares one path and splits its compensator
-// samples; the per-step partial sums are exchanged through distributed shared memory.  v[] is CTA-uniform on entry
-// (after block_sum); every CTA of the cluster leaves with the same sum, added in rank order.  Two slots alternate so
-// that one cluster barrier per call suffices (a slot is rewritten only after the next call's barrier).
-constexpr int kRedFloats = 8 + 2 * 16;
-template <int NV>
-__device__ __forceinline__ void cluster_allsum(float (&v)[NV], float* red, int& parity, int C) {
-  static_assert(NV <= 16, "slot width");
-  namespace cg = cooperative_groups;
-  cg::cluster_group cl = cg::this_cluster();
-  float* slot = red + 8 + 16 * parity;
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int k = 0; k < NV; ++k) slot[k] = v[k];
-  }
-  cl.sync();
-  float s[NV];
-#pragma unroll
-  for (int k = 0; k < NV; ++k) s[k] = 0.0f;
-  for (int r = 0; r < C; ++r) {
-    const float* __restrict__ rs = cl.map_shared_rank(slot, r);
-#pragma unroll
-    for (int k = 0; k < NV; ++k) s[k] += rs[k];
-  }
-#pragma unroll
-  for (int k = 0; k < NV; ++k) v[k] = s[k];
-  parity ^= 1;
-}
-__device__ __forceinline__ unsigned cluster_rank() { return cooperative_groups::this_cluster().block_rank(); }
-
-template <class Model, int HP, bool JUMP>
+// JTC: the jump network (two-network schemes, one output, at most 14 inputs, tanh) runs on tcgen05 (jump_tc.cuh): the
+// path's own jump and its compensator samples are the rows of 128-row tiles.
+template <class Model, int HP, bool JUMP, bool JTC>
 __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a) {
   constexpr int D = Model::D;
+  static_assert(!JTC || (JUMP && 1 + 2 * D <= 7), "JTC: jump schemes, input gradients in one 8-column read");
   extern __shared__ __align__(1024) float smem[];
   const bool two = JUMP && !a.one_net;
-  float* swA = smem;
+  float* swA = smem + (JTC ? kJtcFwdFloats : 0);
   float* swB = swA + net_smem_floats(a.netA, HP, false);
-  float* red = swB + (two ? net_smem_floats(a.netB, HP, false) : 0);
+  float* red = swB + ((two && !JTC) ? net_smem_floats(a.netB, HP, false) : 0);
   float* tb = red + kRedFloats;
   using TL = Tiles<HP, JUMP ? NOP : 4>;
   TL t;
   NetView<HP> nvA, nvJ;
   t.carve(tb, false);
   nvA = load_net<HP>(swA, a.theta, a.netA, false);
-  nvJ = two ? load_net<HP>(swB, a.theta, a.netB, false) : nvA;
+  nvJ = (two && !JTC) ? load_net<HP>(swB, a.theta, a.netB, false) : nvA;
   zero_tiles(tb, TL::fwd_floats());
+  JumpTcFwd<ACT_TANH> jf;
+  if constexpr (JTC) jf.init(smem, a.theta, a.netB);
 
   const int row = threadIdx.x;
   const int G = JUMP ? a.G : 1, ppb = kThreads / G, g = threadIdx.x % G;
@@ -132,7 +106,40 @@ __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a)
         }
       }
       float gam = 0.0f, comp = 0.0f;
-      if (JUMP) {
+      if constexpr (JTC) {
+        // rows of the step: compensator samples 0 .. nnz-1, the zero sample (weight n0), the path's own jump
+        const int nnz = a.jmc_nnz[i], n0 = a.jmc_n0[i];
+        const int iters = (nnz + 2 + G * C - 1) / (G * C);
+        float gc[2] = {0.0f, 0.0f};
+        jf.set_time(tf);
+        for (int it = 0; it < iters; ++it) {
+          const int m = (it * C + crank) * G + g;
+          float Jm[D];
+          float w = 0.0f;
+#pragma unroll
+          for (int k = 0; k < D; ++k) Jm[k] = 0.0f;
+          if (m < nnz) {
+            w = 1.0f;
+#pragma unroll
+            for (int k = 0; k < D; ++k) Jm[k] = a.JMC[((size_t)i * D + k) * a.Mcap + m];
+          } else if (m == nnz) {
+            w = (float)n0;
+          } else if (m == nnz + 1) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) Jm[k] = Jv[k];
+          }
+          float in[HP];
+          Model::template jump_input<HP>(a, tf, X, Jm, in);
+          const float y = jf.eval(reinterpret_cast<const float (&)[16]>(in));
+          gc[1] = fmaf(w, y, gc[1]);
+          if (m == nnz + 1) gc[0] = y;
+        }
+        gc[0] = group_allsum(gc[0], G, red);
+        gc[1] = group_allsum(gc[1], G, red);
+        if (C > 1) cluster_allsum<2>(gc, red, cpar, C);
+        gam = gc[0];
+        comp = gc[1] / (float)a.M;
+      } else if (JUMP) {
         float in[HP];
         Model::template jump_input<HP>(a, tf, X, Jv, in);
         store_row<HP>(t.xt, row, in);
@@ -247,17 +254,18 @@ __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a)
     a.lpart[blockIdx.x * 4] = tot;
     a.lpart[blockIdx.x * 4 + 1] = 0.0f; a.lpart[blockIdx.x * 4 + 2] = 0.0f; a.lpart[blockIdx.x * 4 + 3] = 0.0f;
   }
+  if constexpr (JTC) jf.finish();
   if (JUMP && C > 1) cooperative_groups::this_cluster().sync();   // no CTA leaves while a peer may still read its slots
 }
 
-template <class Model, int HP, bool JUMP>
+template <class Model, int HP, bool JUMP, bool JTC>
 __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a) {
   constexpr int D = Model::D;
   extern __shared__ __align__(1024) float smem[];
   const bool two = JUMP && !a.one_net;
-  float* swA = smem;
+  float* swA = smem + (JTC ? kJtcBwdFloats : 0);
   float* swB = swA + net_smem_floats(a.netA, HP, true);
-  float* red = swB + (two ? net_smem_floats(a.netB, HP, true) : 0);
+  float* red = swB + ((two && !JTC) ? net_smem_floats(a.netB, HP, true) : 0);
   float* tb = red + kRedFloats;
   using TL = Tiles<HP, JUMP ? NOP : 4>;
   TL t;
@@ -265,10 +273,12 @@ __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a
   WGrad<HP> wgA, wgB;
   t.carve(tb, true);
   nvA = load_net<HP>(swA, a.theta, a.netA, true);
-  nvJ = two ? load_net<HP>(swB, a.theta, a.netB, true) : nvA;
+  nvJ = (two && !JTC) ? load_net<HP>(swB, a.theta, a.netB, true) : nvA;
   zero_tiles(tb, TL::bwd_floats());
   wgA.init(nvA, t);
-  if (JUMP) wgB.init(nvJ, t);
+  if (JUMP && !JTC) wgB.init(nvJ, t);
+  JumpTcBwd<ACT_TANH> jb;
+  if constexpr (JTC) jb.init(smem, a.theta, a.netB);
 
   const int row = threadIdx.x;
   const int G = JUMP ? a.G : 1, ppb = kThreads / G, g = threadIdx.x % G;
@@ -389,7 +399,42 @@ __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a
         wgA.accumulate(tb);
         __syncthreads();
       }
-      if (JUMP) {
+      if constexpr (JTC) {
+        float (&dXj)[D] = reinterpret_cast<float (&)[D]>(dXacc);
+        const int nnz = a.jmc_nnz[i], n0 = a.jmc_n0[i];
+        const float cscale = -abar / (float)a.M * vmsk;
+        const int iters = (nnz + 2 + G * C - 1) / (G * C);
+        jb.set_time(tf);
+        for (int it = 0; it < iters; ++it) {
+          const int m = (it * C + crank) * G + g;
+          float Jm[D];
+          float dout = 0.0f;
+#pragma unroll
+          for (int k = 0; k < D; ++k) Jm[k] = 0.0f;
+          if (m < nnz) {
+            dout = cscale;
+#pragma unroll
+            for (int k = 0; k < D; ++k) Jm[k] = a.JMC[((size_t)i * D + k) * a.Mcap + m];
+          } else if (m == nnz) {
+            dout = cscale * (float)n0;
+          } else if (m == nnz + 1) {                       // the path's own jump
+            dout = abar * vmsk;
+#pragma unroll
+            for (int k = 0; k < D; ++k) Jm[k] = Jv[k];
+          }
+          Model::template jump_input<HP>(a, tf, X, Jm, dx);
+          float d8[8];
+          jb.step(reinterpret_cast<const float (&)[16]>(dx), dout, d8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dx[j] = d8[j];
+          Model::template jump_input_grad<HP>(a, Jm, dx, dXj);
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) dXj[k] = (G == 1) ? dXj[k] : group_allsum(dXj[k], G, red);
+        if (C > 1) cluster_allsum<D>(dXj, red, cpar, C);
+#pragma unroll
+        for (int k = 0; k < D; ++k) Xbar[k] += dXj[k];
+      } else if (JUMP) {
         float (&dXj)[D] = reinterpret_cast<float (&)[D]>(dXacc);
         Model::template jump_input<HP>(a, tf, X, Jv, dx);
         store_row<HP>(t.xt, row, dx);
@@ -444,7 +489,8 @@ __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a
   for (int e = threadIdx.x; e < a.P; e += blockDim.x) sg[e] = 0.0f;
   __syncthreads();
   wgA.flush(nvA, sg, a.netA.ext_off);
-  if (two) wgB.flush(nvJ, sg, a.netB.ext_off);
+  if (two && !JTC) wgB.flush(nvJ, sg, a.netB.ext_off);
+  if constexpr (JTC) jb.flush(sg + a.netB.ext_off);
   if (a.scheme == SCH_GLOBAL && threadIdx.x == 0) sg[a.y0_off] = y0tot;
   __syncthreads();
   float* grow = a.gpart + (size_t)blockIdx.x * a.P;
@@ -455,15 +501,17 @@ __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a
 // ---- launch glue ---------------------------------------------------------------------------------
 template <int HP>
 static size_t pricing_smem(const PricingArgs& a, bool backward) {
-  if (a.mma_mode == 1) return backward ? reg_tc_backward_smem() : reg_tc_forward_smem();
+  if (a.mma_mode == 1 && !a.has_jump) return backward ? reg_tc_backward_smem() : reg_tc_forward_smem();
   const bool two = a.has_jump && !a.one_net;
-  const int w = net_smem_floats(a.netA, HP, backward) + (two ? net_smem_floats(a.netB, HP, backward) : 0);
+  const bool jtc = a.mma_mode == 1 && a.has_jump;
+  const int w = net_smem_floats(a.netA, HP, backward) +
+                (jtc ? (backward ? kJtcBwdFloats : kJtcFwdFloats) : two ? net_smem_floats(a.netB, HP, backward) : 0);
   const int tl = a.has_jump ? (backward ? Tiles<HP, NOP>::bwd_floats() : Tiles<HP, NOP>::fwd_floats())
                             : (backward ? Tiles<HP, 4>::bwd_floats() : Tiles<HP, 4>::fwd_floats());
   return sizeof(float) * (size_t)(w + kRedFloats + tl);
 }
 
-template <class Model, int HP, bool JUMP>
+template <class Model, int HP, bool JUMP, bool JTC = false>
 static int launch_one(const PricingArgs& a, int grid, bool backward, cudaStream_t st) {
   const size_t smem = pricing_smem<HP>(a, backward);
   if (smem > 227 * 1024) { set_error("pricing kernels: shared-memory footprint exceeds 227 KB"); return -1; }
@@ -477,11 +525,11 @@ static int launch_one(const PricingArgs& a, int grid, bool backward, cudaStream_
     cfg.attrs = attr; cfg.numAttrs = 1;
   }
   if (!backward) {
-    auto kern = pricing_forward<Model, HP, JUMP>;
+    auto kern = pricing_forward<Model, HP, JUMP, JTC>;
     FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     FB_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
   } else {
-    auto kern = pricing_backward<Model, HP, JUMP>;
+    auto kern = pricing_backward<Model, HP, JUMP, JTC>;
     FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     FB_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
   }
@@ -490,6 +538,11 @@ static int launch_one(const PricingArgs& a, int grid, bool backward, cudaStream_
 }
 template <class Model, int HP>
 static int launch_pair(const PricingArgs& a, int grid, bool backward, cudaStream_t st) {
+  if (a.has_jump && a.mma_mode == 1) {   // jump network on tcgen05 (jump_tc.cuh): two-network schemes, d = 1
+    if constexpr (Model::D == 1) return launch_one<Model, HP, true, true>(a, grid, backward, st);
+    set_error("pricing kernels: the tcgen05 jump path is compiled for d = 1");
+    return -1;
+  }
   if (a.has_jump) return launch_one<Model, HP, true>(a, grid, backward, st);
   if (a.mma_mode == 1) {   // compensator-free solvers on tcgen05 (reg_tc_kernels.cu)
     const int model = std::is_same<Model, VGModel>::value ? 1 : 0;
@@ -524,17 +577,17 @@ int launch_price(int model, int D, const PricingArgs& a, int iStep, const float*
   return 0;
 }
 
-template <class Model, int HP, bool JUMP>
+template <class Model, int HP, bool JUMP, bool JTC = false>
 static int occ_one(const PricingArgs& a, bool backward) {
   const size_t smem = pricing_smem<HP>(a, backward);
   int nb = 0;
   cudaError_t e1, e2;
   if (!backward) {
-    auto kern = pricing_forward<Model, HP, JUMP>;
+    auto kern = pricing_forward<Model, HP, JUMP, JTC>;
     e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem);
   } else {
-    auto kern = pricing_backward<Model, HP, JUMP>;
+    auto kern = pricing_backward<Model, HP, JUMP, JTC>;
     e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem);
   }
@@ -555,6 +608,10 @@ static int occ_pair(const PricingArgs& a, bool backward) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     return backward ? 4 : reg_tc_forward_occupancy(a.B, sms);
+  }
+  if (a.has_jump && a.mma_mode == 1) {   // the occupancy calculator does not know about TMEM: 128 / 96 of 512 columns per CTA
+    if constexpr (Model::D == 1) return std::min(occ_one<Model, HP, true, true>(a, backward), backward ? 4 : 5);
+    return 1;
   }
   if (a.has_jump) return occ_one<Model, HP, true>(a, backward);
   return occ_one<Model, HP, false>(a, backward);

@@ -8,6 +8,7 @@ grad_step -> all_reduce([loss | grads], NCCL) -> Adam, identical on every rank (
 """
 from __future__ import annotations
 
+import os
 import time
 from typing import List, Optional
 
@@ -113,7 +114,13 @@ class PricingSolverBase:
         M = 0 if self.REG else self.M
         spec = self.netA.spec()
         tc_ok = self.REG and spec.H <= 22 and spec.L == 2 and spec.nout == 1 and d in (1, 10)
-        use_tc = tc_ok if self.tensor_cores is None else (bool(self.tensor_cores) and self.REG)
+        # two-network jump schemes at d = 1: the jump network (own jump + compensator rows) on tcgen05
+        jtc_ok = False
+        if not self.REG and self.TWO_NET and d == 1:
+            sb = self.netB.spec()
+            jtc_ok = sb.H <= 22 and spec.H <= 23 and sb.L == 2 and sb.nout == 1 and sb.activation == "tanh"
+        auto = tc_ok or (jtc_ok and os.environ.get("FBSDEJ_JUMP_TC", "0") == "1")
+        use_tc = auto if self.tensor_cores is None else (bool(self.tensor_cores) and (tc_ok or jtc_ok))
         self.native = mm.make_solver(self.SCHEME, [n.spec() for n in nets], n_y0, M, ctx=self.ctx,
                                      stale_time=self.stale_time, tensor_cores=use_tc)
         self.push_params()

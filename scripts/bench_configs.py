@@ -31,6 +31,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--cpu", action="store_true")
+    ap.add_argument("--only", default="", help="comma-separated config numbers (default: 1,2,4)")
     a = ap.parse_args()
     import helpers as H
     from deepfbsdejsolvers_b200 import Context, set_seed
@@ -53,7 +54,8 @@ def main():
               ("SolverSumLocalFBSDE2", lambda m: cp.SolverSumLocalFBSDE2(m, net(0, 2), net(0, 1), 3e-4), 10),
               ("SolverGlobalSumLocalReg", lambda m: cp.SolverGlobalSumLocalReg(m, net(0, 1), net(0, 1), 3e-4), 10000),
               ("SolverGlobalMultiStepReg", lambda m: cp.SolverGlobalMultiStepReg(m, net(0, 1), net(0, 1), 3e-4), 10000)]
-    for name, mk, B in cases1:
+    only = set(a.only.split(",")) if a.only else {"1", "2", "4"}
+    for name, mk, B in (cases1 if "1" in only else []):
         ms = time_solver(mk(merton()), B, a.iters, ctx)
         out.append({"config": "1 mainMerton.py", "solver": name, "paths": B, "time_steps": M["N"], "M": 0 if "Reg" in name else 5000,
                     "ms_per_iter": ms, "iters_per_s": 1e3 / ms, "path_steps_per_s": B * M["N"] * 1e3 / ms})
@@ -69,7 +71,7 @@ def main():
               ("SolverSumLocalFBSDE2", lambda m: pj.SolverSumLocalFBSDE2(m, net(0, 1), net(0, 1), 3e-4), 10),
               ("SolverGlobalSumLocalReg", lambda m: pj.SolverGlobalSumLocalReg(m, net(0, 1), net(0, 1), 1.5e-4), 10000),
               ("SolverGlobalMultiStepReg", lambda m: pj.SolverGlobalMultiStepReg(m, net(0, 1), net(0, 1), 1.5e-4), 10000)]
-    for name, mk, B in cases2:
+    for name, mk, B in (cases2 if "2" in only else []):
         ms = time_solver(mk(vg()), B, a.iters, ctx)
         out.append({"config": "2 mainVG.py", "solver": name, "paths": B, "time_steps": V["N"], "M": 0 if "Reg" in name else 5000,
                     "ms_per_iter": ms, "iters_per_s": 1e3 / ms, "path_steps_per_s": B * V["N"] * 1e3 / ms})
@@ -77,7 +79,7 @@ def main():
     P = H.mfg_params()
     widths = {"SolverGlobalFBSDE": (2, 3), "SolverMultiStepFBSDE": (3, 4), "SolverSumLocalFBSDE": (3, 4),
               "SolverGlobalSumLocalReg": (1, 1), "SolverGlobalMultiStepReg": (1, 1)}
-    for name, (wh, wi) in widths.items():
+    for name, (wh, wi) in (widths.items() if "4" in only else []):
         mm = cm.ModelCoupledFBSDE(**P)
         method = {"SolverGlobalFBSDE": "Global", "SolverMultiStepFBSDE": "SumMultiStep", "SolverSumLocalFBSDE": "SumLocal",
                   "SolverGlobalSumLocalReg": "SumLocalReg", "SolverGlobalMultiStepReg": "SumMultiStepReg"}[name]

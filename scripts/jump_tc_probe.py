@@ -1,0 +1,39 @@
+#!/usr/bin/env python
+"""ms per training iteration of the two-network jump schemes with the jump network on FFMA tiles vs tcgen05 (jump_tc.cuh),
+mainMerton.py / mainVG.py shapes (M = 5000) at several batch sizes."""
+import json, os, sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "scripts"))
+
+
+def main():
+    import helpers as H
+    from bench_configs import time_solver
+    from deepfbsdejsolvers_b200 import Context, set_seed
+    from deepfbsdejsolvers_b200 import coupledPricing as cp
+    from deepfbsdejsolvers_b200.coupledPricing import SolversPureJump as pj
+    ctx = Context.default(0)
+    set_seed(0)
+    M, V = H.MERTON, H.VG
+    net = lambda bY0, nout: cp.Net(bY0, nout, [21, 21], "tanh")
+    merton = lambda: cp.MertonJumpModel(M["T"], M["N"], M["r"], M["muJ"], M["sigmaJ"], M["sigma"], M["lam"], M["K"], M["x0"], cp.AbsCoupling(0.1), 30)
+    vg = lambda: cp.VGmodel(V["T"], V["N"], V["r"], V["theta"], V["kappa"], V["sigmaJ"], V["K"], V["x0"], cp.AbsCoupling(0.1))
+    cases = [("merton Global", lambda tc: cp.SolverGlobalFBSDE(merton(), net(1, 1), net(0, 1), 4e-4, tensor_cores=tc)),
+             ("merton SumLocal2", lambda tc: cp.SolverSumLocalFBSDE2(merton(), net(0, 2), net(0, 1), 3e-4, tensor_cores=tc)),
+             ("vg Global", lambda tc: pj.SolverGlobalFBSDE(vg(), net(0, 1), net(1, 1), 5e-4, tensor_cores=tc)),
+             ("vg MultiStep2", lambda tc: pj.SolverMultiStepFBSDE2(vg(), net(0, 1), net(0, 1), 3e-4, tensor_cores=tc))]
+    for name, mk in cases:
+        for B in (10, 100, 1000):
+            iters = 100 if B <= 100 else 20
+            r = {"case": name, "paths": B}
+            for tc in (False, True):
+                r["tcgen05_ms" if tc else "ffma_ms"] = time_solver(mk(tc), B, iters, ctx)
+            r["speedup"] = r["ffma_ms"] / r["tcgen05_ms"]
+            print(json.dumps(r), flush=True)
+
+
+if __name__ == "__main__":
+    main()

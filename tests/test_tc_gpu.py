@@ -138,3 +138,50 @@ def test_mfg_tensor_core_path_matches_oracle(ctx, scheme, jumpModel, B):
     e_gpu, e_32 = np.abs(g[4:] - g64).max() / scale, np.abs(g32 - g64).max() / scale
     print(scheme, jumpModel, "loss rel", abs(out[0] - lh64 - li64) / abs(lh64 + li64), "grad rel-to-max", e_gpu, "(fp32 oracle", e_32, ")")
     assert e_gpu <= 3e-4, f"gradient error {e_gpu:.3e}"
+
+
+def _check_jump(s, B, l64, g64, g32, aux64, has_z):
+    out, tx, ty, tz = s.loss(B, traj=True)
+    assert abs(out[0] - l64) <= 2e-5 * abs(l64), (out[0], l64)
+    X = aux64["X"][:, :, 0]
+    assert np.abs(tx[:, 0, :] - X).max() <= 2e-6 + 1e-5 * np.abs(X).max()
+    Y = aux64["Y"]
+    assert np.abs(ty[:Y.shape[0]] - Y).max() <= 4e-6 + 1e-5 * np.abs(Y).max()
+    g = s.grad(B)
+    assert abs(g[0] - l64) <= 2e-5 * abs(l64)
+    scale = np.abs(g64).max()
+    e_gpu, e_32 = np.abs(g[4:] - g64).max() / scale, np.abs(g32 - g64).max() / scale
+    print("loss rel", abs(out[0] - l64) / abs(l64), "grad rel-to-max", e_gpu, "(fp32 oracle", e_32, ")")
+    assert e_gpu <= 3e-4, f"gradient error {e_gpu:.3e}"
+
+
+@pytest.mark.parametrize("scheme", ["Global", "MultiStep2", "SumLocal2"])
+@pytest.mark.parametrize("B,M", [(10, 700), (37, 160), (1500, 40)])
+def test_jump_network_on_tensor_cores_merton(ctx, scheme, B, M):
+    """Two-network jump schemes with the jump network (own jump + Monte-Carlo compensator rows) on tcgen05: a cluster of CTAs
+    per path (B = 10), one CTA per path, and several paths per 128-row tile (B = 1500)."""
+    om = MertonOracle(aLin=H.ALIN, limit=30, d=1, **H.MERTON)
+    layout = H.pricing_layout("merton", scheme, 1)
+    theta = H.random_theta(layout, 41)
+    noise = H.merton_noise(om, B, M, seed=42, with_jmc=True)
+    l32, g32, _ = H.oracle_pricing(om, scheme, layout, theta, noise, B)
+    l64, g64, aux64 = H.oracle_pricing(om, scheme, layout, theta, noise, B, dtype=torch.float64)
+    s = H.native_pricing(ctx, "merton", H.MERTON, scheme, layout, d=1, M=M, tensor_cores=True)
+    s.set_theta(theta)
+    s.set_noise(B, H.to_planes(noise["dW"]), H.to_planes(noise["J"]), H.to_planes(noise["JMC"]))
+    _check_jump(s, B, l64, g64, g32, aux64, True)
+
+
+@pytest.mark.parametrize("scheme", ["Global", "MultiStep2", "SumLocal2"])
+def test_jump_network_on_tensor_cores_vg(ctx, scheme):
+    B, M = 24, 300
+    om = VGOracle(aLin=H.ALIN, **H.VG)
+    layout = H.pricing_layout("vg", scheme, 1)
+    theta = H.random_theta(layout, 43)
+    noise = H.vg_noise(om, B, M, seed=44, with_jmc=True)
+    l32, g32, _ = H.oracle_pricing(om, scheme, layout, theta, noise, B)
+    l64, g64, aux64 = H.oracle_pricing(om, scheme, layout, theta, noise, B, dtype=torch.float64)
+    s = H.native_pricing(ctx, "vg", H.VG, scheme, layout, M=M, tensor_cores=True)
+    s.set_theta(theta)
+    s.set_noise(B, None, H.to_planes(noise["J"]), H.to_planes(noise["JMC"]))
+    _check_jump(s, B, l64, g64, g32, aux64, False)
