@@ -6,8 +6,9 @@
 //   JumpTcBwd::step  : recompute, delta pass, dL/dx, weight gradients accumulated in TMEM over every tile, step and path of
 //                      the CTA, six bf16x3 GEMMs (as reg_backward_tc); read once at kernel end (flush)
 //
-// The network has one output and nin <= 14 inputs (two-network schemes, d = 1: nin = 3).  The time feature is folded
-// into a per-step effective bias (set_time).  Building blocks: tc_net.cuh.
+// Only the first output of the network is evaluated (two-network schemes: the jump network's single output; one-network
+// schemes: U of the (U, Z) network at the jumped state) and nin <= 14.  The time feature is folded into a per-step effective
+// bias (set_time).  Building blocks: tc_net.cuh.
 #pragma once
 #include "tc_net.cuh"
 
@@ -33,10 +34,11 @@ struct JumpTcFwd {
     for (int i = row; i < FLOATS; i += kThreads) sm[i] = 0.0f;
     __syncthreads();
     const float* __restrict__ th = theta + rt.ext_off;
-    const int n1 = nin * H, n2 = n1 + H, n3 = n2 + H * H, n4 = n3 + H, n5 = n4 + H;
+    const int n1 = nin * H, n2 = n1 + H, n3 = n2 + H * H, n4 = n3 + H, nout = rt.nout;
     w0 = 0.0f; b1v = 0.0f;
     if (row < H) { w0 = th[row]; b1v = th[n1 + row]; }
-    for (int e = row; e <= n5; e += kThreads) {
+    if (row <= H) sm[OFF_W3 + (row < H ? row : 24)] = th[n4 + row * nout];   // W3[k][0], k < H; b3[0] at index 24
+    for (int e = row; e < n4; e += kThreads) {
       float hi, lo;
       if (e < n1) {
         const int i = e / H, j = e % H;
@@ -46,13 +48,11 @@ struct JumpTcFwd {
           sm[W1B_LO + ((i >> 2) * NBR + j) * 4 + (i & 3)] = lo;
         }
       } else if (e < n2) {
-      } else if (e < n4) {
+      } else {
         const int k = e < n3 ? (e - n2) / H : H, j = e < n3 ? (e - n2) % H : e - n3;
         tc::split_tf32(th[e], hi, lo);
         sm[W2B_HI + ((k >> 2) * NBR + j) * 4 + (k & 3)] = hi;
         sm[W2B_LO + ((k >> 2) * NBR + j) * 4 + (k & 3)] = lo;
-      } else {
-        sm[OFF_W3 + (e < n5 ? e - n4 : 24)] = th[e];      // W3[k], k < H; b3 at index 24
       }
     }
     if (row < 32) { tc::tmem_alloc(tslot, 32, false); tc::tmem_alloc(tslot + 1, 64); }
@@ -143,7 +143,7 @@ struct JumpTcBwd {
   uint64_t* bar_w;
   uint32_t tmem, lane_base, sbase, phase_f, phase_w, pending_w, started;
   float w0, b1v;
-  int H, nin, bias_idx;
+  int H, nin, nout, bias_idx;
 
   __device__ void init(float* smem, const float* __restrict__ theta, const NetRt& rt) {
     sm = smem; u4 = reinterpret_cast<uint4*>(smem); H = rt.H; nin = rt.nin;
@@ -155,7 +155,9 @@ struct JumpTcBwd {
     for (int i = row; i < FLOATS; i += kThreads) sm[i] = 0.0f;
     __syncthreads();
     const float* __restrict__ th = theta + rt.ext_off;
-    const int n1 = nin * H, n2 = n1 + H, n3 = n2 + H * H, n4 = n3 + H, n5 = n4 + H;
+    const int n1 = nin * H, n2 = n1 + H, n3 = n2 + H * H, n4 = n3 + H;
+    nout = rt.nout;
+    if (row < H) sm[OFF_W3 + row] = th[n4 + row * nout];    // W3[k][0]
     unsigned short* const w1 = reinterpret_cast<unsigned short*>(u4 + W1B);
     unsigned short* const w2 = reinterpret_cast<unsigned short*>(u4 + W2B);
     unsigned short* const wt = reinterpret_cast<unsigned short*>(u4 + WTB);
@@ -164,7 +166,7 @@ struct JumpTcBwd {
       w[((k >> 3) * 2 * NH + n) * 8 + (k & 7)] = (unsigned short)hi;
       w[((k >> 3) * 2 * NH + NH + n) * 8 + (k & 7)] = (unsigned short)lo;
     };
-    for (int e = row; e < n5 + 1; e += kThreads) {
+    for (int e = row; e < n4 + 1; e += kThreads) {
       uint32_t hi, lo;
       if (e < n2) {
         const int i = e < n1 ? e / H : nin, j = e < n1 ? e % H : e - n1;
@@ -176,8 +178,6 @@ struct JumpTcBwd {
         tc::split_bf16(th[e], hi, lo);
         put(w2, NBR, j, k, hi, lo);
         if (k < H) put(wt, NBR, k, j, hi, lo);
-      } else if (e < n5) {
-        sm[OFF_W3 + (e - n4)] = th[e];
       } else {
         tc::split_bf16(ACT == ACT_TANH ? 20.0f : 1.0f, hi, lo);
         put(w2, NBR, H, H, hi, lo);
@@ -298,7 +298,7 @@ struct JumpTcBwd {
     load_acc<16, 8>(lane_base + C_ACC, dx);
     tc::tc_fence_before();
   }
-  // TMEM weight gradients -> g[...] (external flat layout of this network, zeroed by the caller).  All threads call; the
+  // TMEM weight gradients, added to g[...] (external flat layout of this network; first output column of W3 / b3).  All threads call; the
   // operand tiles are dead and serve as scratch.
   __device__ void flush(float* __restrict__ g) {
     const int row = threadIdx.x;
@@ -324,14 +324,14 @@ struct JumpTcBwd {
       if (started && pass == 0) {
         for (int e = row; e < (nin + 1) * H; e += kThreads) {
           const int i = e / H, j = e % H;
-          g[e] = S[j * SW + i] + S[j * SW + 16 + i] + S[(24 + j) * SW + i];
+          g[e] += S[j * SW + i] + S[j * SW + 16 + i] + S[(24 + j) * SW + i];
         }
       } else if (started) {
         for (int e = row; e < (H + 1) * H; e += kThreads) {
           const int k = e / H, j = e % H;
-          g[o2 + e] = S[k * SW + j] + S[k * SW + 24 + j] + S[(48 + k) * SW + j];
+          g[o2 + e] += S[k * SW + j] + S[k * SW + 24 + j] + S[(48 + k) * SW + j];
         }
-        if (row <= H) g[o3 + row] = S[(24 + row) * SW + COL_DOUT] + S[(24 + row) * SW + 24 + COL_DOUT] + S[(72 + row) * SW + COL_DOUT];
+        if (row <= H) g[o3 + row * nout] += S[(24 + row) * SW + COL_DOUT] + S[(24 + row) * SW + 24 + COL_DOUT] + S[(72 + row) * SW + COL_DOUT];
       }
     }
     tc::tc_fence_before();

@@ -84,8 +84,9 @@ class PricingSolverBase:
         self.mathModel, self.netA, self.netB, self.lRate = mathModel, netA, netB, lRate
         self.M = self.M_DEFAULT if M is None else int(M)
         self.seed, self.ctx, self.stale_time = seed, ctx, stale_time
-        # tcgen05 path (3xTF32 forward, bf16x3 adjoint; tests/test_tc_gpu.py): the compensator-free solvers use it unless
-        # told otherwise (None = automatic: on when the kernels cover the network shape)
+        # tcgen05 path (3xTF32 forward, bf16x3 adjoint; tests/test_tc_gpu.py): used unless told otherwise (None = automatic:
+        # on when the kernels cover the scheme and the network shape - the compensator-free solvers at d in {1, 10}, the jump
+        # schemes at d = 1)
         self.tensor_cores = tensor_cores
         self.native: Optional[NativeSolver] = None
 
@@ -114,12 +115,12 @@ class PricingSolverBase:
         M = 0 if self.REG else self.M
         spec = self.netA.spec()
         tc_ok = self.REG and spec.H <= 22 and spec.L == 2 and spec.nout == 1 and d in (1, 10)
-        # two-network jump schemes at d = 1: the jump network (own jump + compensator rows) on tcgen05
+        # jump schemes at d = 1: the jump evaluations (own jump + compensator rows) on tcgen05
         jtc_ok = False
-        if not self.REG and self.TWO_NET and d == 1:
-            sb = self.netB.spec()
-            jtc_ok = sb.H <= 22 and spec.H <= 23 and sb.L == 2 and sb.nout == 1 and sb.activation == "tanh"
-        auto = tc_ok or (jtc_ok and os.environ.get("FBSDEJ_JUMP_TC", "0") == "1")
+        if not self.REG and d == 1:
+            sb = self.netB.spec() if self.TWO_NET else spec
+            jtc_ok = sb.H <= 22 and spec.H <= 23 and sb.L == 2 and sb.activation == "tanh"
+        auto = tc_ok or jtc_ok
         use_tc = auto if self.tensor_cores is None else (bool(self.tensor_cores) and (tc_ok or jtc_ok))
         self.native = mm.make_solver(self.SCHEME, [n.spec() for n in nets], n_y0, M, ctx=self.ctx,
                                      stale_time=self.stale_time, tensor_cores=use_tc)

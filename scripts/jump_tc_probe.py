@@ -23,6 +23,8 @@ def main():
     vg = lambda: cp.VGmodel(V["T"], V["N"], V["r"], V["theta"], V["kappa"], V["sigmaJ"], V["K"], V["x0"], cp.AbsCoupling(0.1))
     cases = [("merton Global", lambda tc: cp.SolverGlobalFBSDE(merton(), net(1, 1), net(0, 1), 4e-4, tensor_cores=tc)),
              ("merton SumLocal2", lambda tc: cp.SolverSumLocalFBSDE2(merton(), net(0, 2), net(0, 1), 3e-4, tensor_cores=tc)),
+             ("merton MultiStep1", lambda tc: cp.SolverMultiStepFBSDE1(merton(), net(0, 2), 3e-4, tensor_cores=tc)),
+             ("vg SumLocal1", lambda tc: pj.SolverSumLocalFBSDE1(vg(), net(0, 1), 3e-4, tensor_cores=tc)),
              ("vg Global", lambda tc: pj.SolverGlobalFBSDE(vg(), net(0, 1), net(1, 1), 5e-4, tensor_cores=tc)),
              ("vg MultiStep2", lambda tc: pj.SolverMultiStepFBSDE2(vg(), net(0, 1), net(0, 1), 3e-4, tensor_cores=tc))]
     for name, mk in cases:

@@ -155,10 +155,10 @@ def _check_jump(s, B, l64, g64, g32, aux64, has_z):
     assert e_gpu <= 3e-4, f"gradient error {e_gpu:.3e}"
 
 
-@pytest.mark.parametrize("scheme", ["Global", "MultiStep2", "SumLocal2"])
+@pytest.mark.parametrize("scheme", ["Global", "MultiStep1", "MultiStep2", "SumLocal1", "SumLocal2"])
 @pytest.mark.parametrize("B,M", [(10, 700), (37, 160), (1500, 40)])
 def test_jump_network_on_tensor_cores_merton(ctx, scheme, B, M):
-    """Two-network jump schemes with the jump network (own jump + Monte-Carlo compensator rows) on tcgen05: a cluster of CTAs
+    """Jump schemes with the jump evaluations (own jump + Monte-Carlo compensator rows) on tcgen05: a cluster of CTAs
     per path (B = 10), one CTA per path, and several paths per 128-row tile (B = 1500)."""
     om = MertonOracle(aLin=H.ALIN, limit=30, d=1, **H.MERTON)
     layout = H.pricing_layout("merton", scheme, 1)
@@ -172,7 +172,7 @@ def test_jump_network_on_tensor_cores_merton(ctx, scheme, B, M):
     _check_jump(s, B, l64, g64, g32, aux64, True)
 
 
-@pytest.mark.parametrize("scheme", ["Global", "MultiStep2", "SumLocal2"])
+@pytest.mark.parametrize("scheme", ["Global", "MultiStep1", "MultiStep2", "SumLocal1", "SumLocal2"])
 def test_jump_network_on_tensor_cores_vg(ctx, scheme):
     B, M = 24, 300
     om = VGOracle(aLin=H.ALIN, **H.VG)
