@@ -244,7 +244,9 @@ int pick_C(const fbsdej_solver* s, int B, int G) {
   double rows = s->M;
   if (s->model == FBSDEJ_MODEL_MERTON)   // zero-jump samples are deduplicated: expected non-zero ones + 1
     rows = s->M * (1.0 - std::exp(-s->mer.lam * (s->mer.T / s->mer.N) * s->D)) + 1.0;
-  int C = std::min(8, s->ctx->sms / std::max(B, 1));
+  // (the tcgen05 jump kernels keep two CTAs per SM resident in the adjoint sweep, four in the forward one)
+  const int per_sm = s->desc.mma_mode == 1 ? 2 : 1;
+  int C = std::min(8, s->ctx->sms * per_sm / std::max(B, 1));
   C = std::min(C, (int)std::ceil(rows / kThreads));
   return std::max(C, 1);
 }
@@ -708,7 +710,7 @@ int fbsdej_solver_create(fbsdej_ctx* ctx, const fbsdej_solver_desc* desc, const 
   // tcgen05 coverage: the compensator-free pricing solvers, the MFG solvers, and the jump evaluations (own jump + Monte-Carlo
   // compensator) of the jump schemes at d = 1 with a tanh network
   const fbsdej_net_desc& jn = desc->nets[one_net ? 0 : 1];
-  const bool jtc_ok = s->has_jump && s->D == 1 && HP == 24 && jn.H <= 22 && jn.act == FBSDEJ_ACT_TANH;
+  const bool jtc_ok = s->has_jump && s->D == 1 && HP == 24 && jn.H <= 22 && jn.act == FBSDEJ_ACT_TANH && s->P <= 24 * kThreads;
   FB_REQUIRE(desc->mma_mode == 0 ||
                  (model == FBSDEJ_MODEL_MFG ? (desc->nets[0].H <= 22 && desc->nets[1].H <= 22 && desc->nets[0].act == desc->nets[1].act)
                                             : ((reg && HP == 24 && desc->nets[0].H <= 22) || jtc_ok)),

@@ -130,23 +130,29 @@ struct JumpTcFwd {
 template <int ACT>
 struct JumpTcBwd {
   static constexpr int CH = 128, NBR = rtc::NB;
-  // uint4 offsets: operand tiles, then the stacked B operands (as reg_backward_tc)
-  static constexpr int XA_HI = 0, XA_LO = 2 * CH, H1_HI = 4 * CH, H2_HI = 7 * CH, H1_LO = 10 * CH, H2_LO = 13 * CH, D2_HI = 16 * CH,
-                       D2_LO = 19 * CH, D1_HI = H2_HI, D1_LO = H1_LO, W_BASE = 22 * CH;
-  static constexpr int W1B = W_BASE, W2B = W1B + 2 * 2 * NBR, WTB = W2B + 4 * 2 * NBR, W1T = WTB + 4 * 2 * NBR, U4_END = W1T + 4 * 2 * 16;
+  // operand tiles (uint4 offsets from `tiles`; they may alias memory the caller uses between the steps' tile loops)
+  // Order matters: a layer GEMM with K = 32 reads one chunk past a 24-feature operand (the weights' rows there are zero, so
+  // the chunk only has to hold finite bf16 values): H1_HI -> H2_HI[0], H1_LO -> H2_LO[0] (zeroed by set_time: the caller may
+  // have left anything there), D2_HI -> D2_LO[0], D2_LO -> XA_HI[0], D1_HI -> D1_LO[0], D1_LO -> H2_LO[0].
+  static constexpr int H1_HI = 0, H2_HI = 3 * CH, H1_LO = 6 * CH, H2_LO = 9 * CH, D2_HI = 12 * CH, D2_LO = 15 * CH, XA_HI = 18 * CH,
+                       XA_LO = 20 * CH, D1_HI = H2_HI, D1_LO = H1_LO, TILE_U4 = 22 * CH, TILE_FLOATS = TILE_U4 * 4;
+  // weights block (uint4 offsets from `wts`): the stacked B operands (as reg_backward_tc), then W3, the mbarriers, the TMEM slot
+  static constexpr int W1B = 0, W2B = W1B + 2 * 2 * NBR, WTB = W2B + 4 * 2 * NBR, W1T = WTB + 4 * 2 * NBR, U4_END = W1T + 4 * 2 * 16;
   static constexpr int OFF_W3 = U4_END * 4, OFF_BAR = OFF_W3 + 24, FLOATS = OFF_BAR + 8;
   static constexpr uint32_t C_ACC = 0, C_W1 = 48, C_W2 = 80, NCOLS = 128;
   static constexpr int COL_DOUT = 23, SW = 49;
-  float* sm;
-  uint4* u4;
+  float* sm;        // weights block
+  uint4* u4;        // operand tiles
+  uint4* w4;
   uint64_t* bar_f;
   uint64_t* bar_w;
-  uint32_t tmem, lane_base, sbase, phase_f, phase_w, pending_w, started;
+  uint32_t tmem, lane_base, sbase, wbase, phase_f, phase_w, pending_w, started;
   float w0, b1v;
   int H, nin, nout, bias_idx;
 
-  __device__ void init(float* smem, const float* __restrict__ theta, const NetRt& rt) {
-    sm = smem; u4 = reinterpret_cast<uint4*>(smem); H = rt.H; nin = rt.nin;
+  // wts: FLOATS floats; tiles: TILE_FLOATS floats; both 16-byte aligned
+  __device__ void init(float* wts, float* tiles, const float* __restrict__ theta, const NetRt& rt) {
+    sm = wts; w4 = reinterpret_cast<uint4*>(wts); u4 = reinterpret_cast<uint4*>(tiles); H = rt.H; nin = rt.nin;
     phase_f = phase_w = pending_w = started = 0;
     bar_f = reinterpret_cast<uint64_t*>(sm + OFF_BAR);
     bar_w = bar_f + 1;
@@ -158,10 +164,10 @@ struct JumpTcBwd {
     const int n1 = nin * H, n2 = n1 + H, n3 = n2 + H * H, n4 = n3 + H;
     nout = rt.nout;
     if (row < H) sm[OFF_W3 + row] = th[n4 + row * nout];    // W3[k][0]
-    unsigned short* const w1 = reinterpret_cast<unsigned short*>(u4 + W1B);
-    unsigned short* const w2 = reinterpret_cast<unsigned short*>(u4 + W2B);
-    unsigned short* const wt = reinterpret_cast<unsigned short*>(u4 + WTB);
-    unsigned short* const w1t = reinterpret_cast<unsigned short*>(u4 + W1T);
+    unsigned short* const w1 = reinterpret_cast<unsigned short*>(w4 + W1B);
+    unsigned short* const w2 = reinterpret_cast<unsigned short*>(w4 + W2B);
+    unsigned short* const wt = reinterpret_cast<unsigned short*>(w4 + WTB);
+    unsigned short* const w1t = reinterpret_cast<unsigned short*>(w4 + W1T);
     auto put = [](unsigned short* w, int NH, int n, int k, uint32_t hi, uint32_t lo) {
       w[((k >> 3) * 2 * NH + n) * 8 + (k & 7)] = (unsigned short)hi;
       w[((k >> 3) * 2 * NH + NH + n) * 8 + (k & 7)] = (unsigned short)lo;
@@ -194,9 +200,11 @@ struct JumpTcBwd {
     tmem = *tslot;
     lane_base = tmem + ((uint32_t)(row & ~31) << 16);
     sbase = tc::smem_u32(u4);
+    wbase = tc::smem_u32(w4);
     bias_idx = ((nin >> 3) * 2 * NBR + row) * 8 + (nin & 7);
   }
   __device__ __forceinline__ uint32_t sa(int off_u4) const { return sbase + (uint32_t)off_u4 * 16u; }
+  __device__ __forceinline__ uint32_t sw(int off_u4) const { return wbase + (uint32_t)off_u4 * 16u; }
   __device__ __forceinline__ void wait_f() { tc::mbar_wait(bar_f, phase_f); phase_f ^= 1; tc::tc_fence_after(); }
   __device__ __forceinline__ void drain_w() {
     if (pending_w) { tc::mbar_wait(bar_w, phase_w); phase_w ^= 1; pending_w = 0; }
@@ -208,9 +216,11 @@ struct JumpTcBwd {
     if (row <= H) {
       uint32_t hi, lo;
       tc::split_bf16(row < H ? fmaf(t, w0, b1v) : (ACT == ACT_TANH ? 20.0f : 1.0f), hi, lo);
-      reinterpret_cast<unsigned short*>(u4 + W1B)[bias_idx] = (unsigned short)hi;
-      reinterpret_cast<unsigned short*>(u4 + W1B)[bias_idx + NBR * 8] = (unsigned short)lo;
+      reinterpret_cast<unsigned short*>(w4 + W1B)[bias_idx] = (unsigned short)hi;
+      reinterpret_cast<unsigned short*>(w4 + W1B)[bias_idx + NBR * 8] = (unsigned short)lo;
     }
+    u4[H2_HI + row] = make_uint4(0u, 0u, 0u, 0u);       // K padding of the first tile's layer-2 GEMM
+    u4[H2_LO + row] = make_uint4(0u, 0u, 0u, 0u);
   }
   // One tile: xin = this row's inputs (xin[0] = time for dW1, xin[nin] = 1), dout = adjoint of the row's output (0 for rows
   // that do not count).  dx[i] = dL/d xin[i], i < 8.  Every thread of the CTA calls.
@@ -224,7 +234,7 @@ struct JumpTcBwd {
     publish();
     if (warp == 0 && issuer) {
       tc::tc_fence_after();
-      gemm_k<1, NBR>(tmem + C_ACC, sa(XA_HI), sa(XA_LO), sa(W1B));
+      gemm_k<1, NBR>(tmem + C_ACC, sa(XA_HI), sa(XA_LO), sw(W1B));
       tc::mma_commit(bar_f);
     }
     wait_f();
@@ -239,7 +249,7 @@ struct JumpTcBwd {
     publish();
     if (warp == 1 && issuer) {
       tc::tc_fence_after();
-      gemm_k<2, NBR>(tmem + C_ACC, sa(H1_HI), sa(H1_LO), sa(W2B));
+      gemm_k<2, NBR>(tmem + C_ACC, sa(H1_HI), sa(H1_LO), sw(W2B));
       tc::mma_commit(bar_f);
     }
     wait_f();
@@ -270,7 +280,7 @@ struct JumpTcBwd {
     if (warp == 2 && issuer) {
       tc::tc_fence_after();
       gemm_rows_stacked<48>(tmem + C_W2, sa(H1_HI), sa(D2_HI), started ? 1u : 0u);
-      gemm_k<2, NBR>(tmem + C_ACC, sa(D2_HI), sa(D2_LO), sa(WTB));
+      gemm_k<2, NBR>(tmem + C_ACC, sa(D2_HI), sa(D2_LO), sw(WTB));
       tc::mma_commit(bar_f);
     }
     wait_f();
@@ -287,7 +297,7 @@ struct JumpTcBwd {
     publish();
     if (warp == 3 && issuer) {
       tc::tc_fence_after();
-      gemm_k<2, 16>(tmem + C_ACC, sa(D1_HI), sa(D1_LO), sa(W1T));
+      gemm_k<2, 16>(tmem + C_ACC, sa(D1_HI), sa(D1_LO), sw(W1T));
       tc::mma_commit(bar_f);
       gemm_rows_stacked<32>(tmem + C_W1, sa(D1_HI), sa(XA_HI), started ? 1u : 0u);
       tc::mma_commit(bar_w);
@@ -298,14 +308,14 @@ struct JumpTcBwd {
     load_acc<16, 8>(lane_base + C_ACC, dx);
     tc::tc_fence_before();
   }
-  // TMEM weight gradients, added to g[...] (external flat layout of this network; first output column of W3 / b3).  All threads call; the
-  // operand tiles are dead and serve as scratch.
+  // TMEM weight gradients, added to g[...] (external flat layout of this network; first output column of W3 / b3).  All
+  // threads call; the operand tiles are dead and serve as scratch (128 x SW floats).
   __device__ void flush(float* __restrict__ g) {
     const int row = threadIdx.x;
     drain_w();
     tc::tc_fence_after();
     __syncthreads();
-    float* const S = sm;
+    float* const S = reinterpret_cast<float*>(u4);
     const int o2 = nin * H + H, o3 = o2 + H * H + H;
     for (int pass = 0; pass < 2; ++pass) {
       __syncthreads();

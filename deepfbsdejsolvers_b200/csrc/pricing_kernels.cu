@@ -277,8 +277,11 @@ __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a
   zero_tiles(tb, TL::bwd_floats());
   wgA.init(nvA, t);
   if (JUMP && !JTC) wgB.init(nvJ, t);
+  // JTC: the operand tiles of the tensor-core block live in the h1 .. d2 tiles of the FFMA network (every tile is rewritten
+  // in full by whichever phase uses it next; the phases are separated by drain_w / the MMA waits)
+  static_assert(JumpTcBwd<ACT_TANH>::TILE_FLOATS <= TL::bwd_floats() - (HP + (JUMP ? NOP : 4)) * TR, "operand tiles fit between the input and dout tiles");
   JumpTcBwd<ACT_TANH> jb;
-  if constexpr (JTC) jb.init(smem, a.theta, a.netB);
+  if constexpr (JTC) jb.init(smem, t.h1, a.theta, a.netB);
 
   const int row = threadIdx.x;
   const int G = JUMP ? a.G : 1, ppb = kThreads / G, g = threadIdx.x % G;
@@ -374,6 +377,7 @@ __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a
 #pragma unroll
         for (int k = 0; k < (JUMP ? D : 1); ++k) dXacc[k] = 0.0f;
       }
+      if constexpr (JTC) jb.drain_w();   // the last weight-gradient GEMM of the step above still reads the shared tiles
       if (a.use_netA) {
 #pragma unroll
         for (int j = 0; j < HP; ++j) dx[j] = 0.0f;
@@ -591,12 +595,25 @@ static int occ_one(const PricingArgs& a, bool backward) {
     e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem);
   }
+  if (JTC && e1 == cudaSuccess && e2 == cudaSuccess) {
+    // the occupancy calculator answers 1 for kernels that allocate tensor memory; the hardware co-schedules CTAs as long as
+    // registers, shared memory and the 512 TMEM columns (128 backward / 96 forward per CTA) allow
+    cudaFuncAttributes fa{};
+    const cudaError_t e3 = backward ? cudaFuncGetAttributes(&fa, pricing_backward<Model, HP, JUMP, JTC>)
+                                    : cudaFuncGetAttributes(&fa, pricing_forward<Model, HP, JUMP, JTC>);
+    if (e3 == cudaSuccess && fa.numRegs > 0) {
+      const int by_regs = 65536 / (((fa.numRegs + 7) & ~7) * kThreads);
+      const int by_smem = (int)((228 * 1024) / (smem + fa.sharedSizeBytes + 1024));
+      nb = std::max(1, std::min(std::min(by_regs, by_smem), backward ? 4 : 5));
+    }
+  }
   if (e1 != cudaSuccess || e2 != cudaSuccess || nb < 1) {
     if (getenv("FBSDEJ_DEBUG"))
       fprintf(stderr, "[fbsdej] occupancy query failed (%s / %s, nb=%d, smem=%zu)\n", cudaGetErrorString(e1), cudaGetErrorString(e2), nb, smem);
     (void)cudaGetLastError();
     nb = 1;
   }
+  if (getenv("FBSDEJ_DEBUG")) fprintf(stderr, "[fbsdej] occupancy(%s, jtc=%d): %d CTAs/SM, smem %zu\n", backward ? "backward" : "forward", (int)JTC, nb, smem);
   return nb;
 }
 template <class Model, int HP>
@@ -610,7 +627,7 @@ static int occ_pair(const PricingArgs& a, bool backward) {
     return backward ? 4 : reg_tc_forward_occupancy(a.B, sms);
   }
   if (a.has_jump && a.mma_mode == 1) {   // the occupancy calculator does not know about TMEM: 128 / 96 of 512 columns per CTA
-    if constexpr (Model::D == 1) return std::min(occ_one<Model, HP, true, true>(a, backward), backward ? 4 : 5);
+    if constexpr (Model::D == 1) return occ_one<Model, HP, true, true>(a, backward);
     return 1;
   }
   if (a.has_jump) return occ_one<Model, HP, true>(a, backward);

@@ -10,6 +10,12 @@ sys.path.insert(0, os.path.join(ROOT, "scripts"))
 
 
 def main():
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--case", default="", help="run one case only (for ncu), e.g. 'vg Global'")
+    ap.add_argument("--paths", type=int, default=1000)
+    ap.add_argument("--iters", type=int, default=0)
+    a = ap.parse_args()
     import helpers as H
     from bench_configs import time_solver
     from deepfbsdejsolvers_b200 import Context, set_seed
@@ -27,6 +33,9 @@ def main():
              ("vg SumLocal1", lambda tc: pj.SolverSumLocalFBSDE1(vg(), net(0, 1), 3e-4, tensor_cores=tc)),
              ("vg Global", lambda tc: pj.SolverGlobalFBSDE(vg(), net(0, 1), net(1, 1), 5e-4, tensor_cores=tc)),
              ("vg MultiStep2", lambda tc: pj.SolverMultiStepFBSDE2(vg(), net(0, 1), net(0, 1), 3e-4, tensor_cores=tc))]
+    if a.case:
+        print(json.dumps({"case": a.case, "paths": a.paths, "tcgen05_ms": time_solver(dict(cases)[a.case](True), a.paths, a.iters or 3, ctx)}))
+        return
     for name, mk in cases:
         for B in (10, 100, 1000):
             iters = 100 if B <= 100 else 20
