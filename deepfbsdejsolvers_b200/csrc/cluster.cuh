@@ -11,6 +11,17 @@ __device__ __forceinline__ float group_allsum(float v, int G, float* red) {
   return block_sum(v, red);   // G == kThreads: one path per CTA
 }
 
+// two sums at once (one barrier pair for G == kThreads); red[0 .. 7]
+__device__ __forceinline__ void group_allsum2(float& u, float& v, int G, float* red) {
+  if (G <= 32) { u = group_sum_shfl(u, G); v = group_sum_shfl(v, G); return; }
+  u = warp_sum(u); v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = u; red[4 + (threadIdx.x >> 5)] = v; }
+  __syncthreads();
+  u = (red[0] + red[1]) + (red[2] + red[3]);
+  v = (red[4] + red[5]) + (red[6] + red[7]);
+}
+
 // Small batches (the reference's B = 10): a thread-block CLUSTER of C CTAs shares one path and splits its compensator
 // samples; the per-step partial sums are exchanged through distributed shared memory.  v[] is CTA-uniform on entry
 // (after block_sum); every CTA of the cluster leaves with the same sum, added in rank order.  Two slots alternate so

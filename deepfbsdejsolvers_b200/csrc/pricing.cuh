@@ -134,6 +134,30 @@ struct MertonModel {
     dAb = (D == 1) ? sD : sD * Ge * (1.0f / D);
   }
   __device__ static __forceinline__ float dA_k(float dAb, float Xk) { return (D == 1) ? dAb : dAb / Xk; }
+  // The same closed form when the G threads of a group hold the same state (jump-scheme kernels, one path per group): the
+  // terms of the Poisson series are dealt out over the group and the two partial sums reduced by `allsum2` - the serial chain
+  // of up to `limit` normal CDF pairs per step becomes one or two.
+  template <class AllSum2>
+  __device__ static __forceinline__ void eval_A_group(const PricingArgs& a, int i, const float (&X)[D], float& A, float& dAb, int G, int g,
+                                                      AllSum2 allsum2) {
+    const float Gm = basket(X);
+    const float Ge = (D == 1) ? Gm : Gm * a.qdisc[i];
+    const float k = logf(Ge / a.K);
+    const int2 rg = a.tab_range[i];
+    const float4* __restrict__ tA = a.tabA + (size_t)i * a.limit;
+    const float* __restrict__ tK = a.tabK + (size_t)i * a.limit;
+    float sD = 0.0f, sK = 0.0f;
+    for (int n = rg.x + g; n < rg.y; n += G) {
+      const float4 c = __ldg(tA + n);
+      const float d1 = fmaf(k, c.x, c.y);
+      const float d2 = d1 - c.z;
+      sD = fmaf(c.w, ncdf(d1), sD);
+      sK = fmaf(__ldg(tK + n), ncdf(d2), sK);
+    }
+    allsum2(sD, sK);
+    A = Ge * sD - sK;
+    dAb = (D == 1) ? sD : sD * Ge * (1.0f / D);
+  }
   // Same closed form for the tcgen05 kernels, split in two so that the table loads are in flight while the caller does
   // other work: the d logarithms of the geometric mean collapse into one per half of the product (d = 10: two MUFU.LG2
   // instead of ten library logf + one expf).

@@ -38,7 +38,8 @@ __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a)
   float* swA = smem + (JTC ? kJtcFwdFloats : 0);
   float* swB = swA + net_smem_floats(a.netA, HP, false);
   float* red = swB + ((two && !JTC) ? net_smem_floats(a.netB, HP, false) : 0);
-  float* tb = red + kRedFloats;
+  float* rv = red + kRedFloats;                        // single-row block of the (U, Z) network (jump schemes, G == kThreads)
+  float* tb = rv + (JUMP ? row_floats<HP>() : 0);
   using TL = Tiles<HP, JUMP ? NOP : 4>;
   TL t;
   NetView<HP> nvA, nvJ;
@@ -53,6 +54,7 @@ __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a)
   const int G = JUMP ? a.G : 1, ppb = kThreads / G, g = threadIdx.x % G;
   const int C = JUMP ? a.C : 1;                             // CTAs per path (cluster size); C > 1 implies G == kThreads
   const int crank = (JUMP && C > 1) ? (int)cluster_rank() : 0;
+  const bool rowmode = JUMP && G == kThreads;               // one path per CTA: the (U, Z) network has a single row
   int cpar = 0;
   const size_t sB = (size_t)a.B;
   const float rdt = a.r * a.dt;
@@ -93,13 +95,18 @@ __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a)
 #pragma unroll
         for (int k = 0; k < D; ++k) in[1 + k] = X[k];
         in[1 + D] = 1.0f;
-        store_row<HP>(t.xt, row, in);
-        mlp_fwd<HP, false, TL>(nvA, t, row);
-        if (a.has_y) y_net = t.out[tix(0, row)];
+        if (rowmode) {
+          row_fwd<HP>(nvA, rv, in);
+        } else {
+          store_row<HP>(t.xt, row, in);
+          mlp_fwd<HP, false, TL>(nvA, t, row);
+        }
+        auto outA = [&](int j) { return rowmode ? rv[6 * HP + j] : t.out[tix(j, row)]; };
+        if (a.has_y) y_net = outA(0);
         if (JUMP && a.has_z) {
 #pragma unroll
           for (int k = 0; k < D; ++k) {
-            const float z = t.out[tix(a.zoff + k, row)];
+            const float z = outA(a.zoff + k);
             zdw = fmaf(z, dWv[k], zdw);
             if (a.trajZ && writer) a.trajZ[((size_t)i * D + k) * sB + p] = z;
           }
@@ -134,8 +141,7 @@ __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a)
           gc[1] = fmaf(w, y, gc[1]);
           if (m == nnz + 1) gc[0] = y;
         }
-        gc[0] = group_allsum(gc[0], G, red);
-        gc[1] = group_allsum(gc[1], G, red);
+        group_allsum2(gc[0], gc[1], G, red);
         if (C > 1) cluster_allsum<2>(gc, red, cpar, C);
         gam = gc[0];
         comp = gc[1] / (float)a.M;
@@ -197,7 +203,12 @@ __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a)
       }
       // ---- coupled Euler step (pricingModels.py:53-54 / :184-185) -----------------------------
       float Ai, dAb;
-      Model::eval_A(a, i, X, Ai, dAb);
+      if constexpr (JUMP && Model::kBrownian) {
+        if (G > 1 && !a.use_atab) Model::eval_A_group(a, i, X, Ai, dAb, G, g, [&](float& u, float& v) { group_allsum2(u, v, G, red); });
+        else Model::eval_A(a, i, X, Ai, dAb);
+      } else {
+        Model::eval_A(a, i, X, Ai, dAb);
+      }
       const float diff = Ysel - Ai;
       const float coup = a.aLin * fabsf(diff) * a.dt;
       const float sgn = a.aLin * a.dt * (diff > 0.0f ? 1.0f : (diff < 0.0f ? -1.0f : 0.0f));
@@ -266,7 +277,8 @@ __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a
   float* swA = smem + (JTC ? kJtcBwdFloats : 0);
   float* swB = swA + net_smem_floats(a.netA, HP, true);
   float* red = swB + ((two && !JTC) ? net_smem_floats(a.netB, HP, true) : 0);
-  float* tb = red + kRedFloats;
+  float* rv = red + kRedFloats;
+  float* tb = rv + (JUMP ? row_floats<HP>() : 0);
   using TL = Tiles<HP, JUMP ? NOP : 4>;
   TL t;
   NetView<HP> nvA, nvJ;
@@ -287,6 +299,7 @@ __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a
   const int G = JUMP ? a.G : 1, ppb = kThreads / G, g = threadIdx.x % G;
   const int C = JUMP ? a.C : 1;
   const int crank = (JUMP && C > 1) ? (int)cluster_rank() : 0;
+  const bool rowmode = JUMP && G == kThreads;
   int cpar = 0;
   const size_t sB = (size_t)a.B;
   const float invB = a.inv_B, invBN = a.inv_B / (float)a.N, rdt = a.r * a.dt;
@@ -385,23 +398,42 @@ __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a
 #pragma unroll
         for (int k = 0; k < D; ++k) dx[1 + k] = X[k];
         dx[1 + D] = 1.0f;
-        store_row<HP>(t.xt, row, dx);
-        mlp_fwd<HP, true, TL>(nvA, t, row);
-        for (int j = 0; j < pad4(a.netA.nout); ++j) t.dout[tix(j, row)] = 0.0f;
-        if (a.has_y) t.dout[tix(0, row)] = ybar * msk;
-        if (JUMP && a.has_z) {
+        if (rowmode) {
+          // thread j holds entry j of dL/dout; only the first CTA of the path's cluster counts (the others see zeros)
+          const float mrow = (valid && crank == 0) ? 1.0f : 0.0f;
+          float dj = (a.has_y && row == 0) ? ybar * mrow : 0.0f;
+          if (a.has_z) {
 #pragma unroll
-          for (int k = 0; k < D; ++k)
-            t.dout[tix(a.zoff + k, row)] = abar * (Model::kBrownian ? a.dW[((size_t)i * D + k) * sB + p] : 0.0f) * msk;
-        }
-        mlp_delta<HP, TL>(nvA, t, row, dx);
+            for (int k = 0; k < D; ++k)
+              if (row == a.zoff + k) dj = abar * (Model::kBrownian ? a.dW[((size_t)i * D + k) * sB + p] : 0.0f) * mrow;
+          }
+          row_fwd<HP>(nvA, rv, dx);
+          float dxr[1 + D];
+          row_delta<HP, 1 + D>(nvA, rv, dj, dxr);
+          if (row == 0) {
 #pragma unroll
-        for (int k = 0; k < D; ++k) {
-          if (JUMP) dXacc[JUMP ? k : 0] += dx[1 + k]; else Xbar[k] += dx[1 + k];
+            for (int k = 0; k < D; ++k) dXacc[JUMP ? k : 0] += dxr[1 + k];
+          }
+          wgA.accumulate_row(rv);
+        } else {
+          store_row<HP>(t.xt, row, dx);
+          mlp_fwd<HP, true, TL>(nvA, t, row);
+          for (int j = 0; j < pad4(a.netA.nout); ++j) t.dout[tix(j, row)] = 0.0f;
+          if (a.has_y) t.dout[tix(0, row)] = ybar * msk;
+          if (JUMP && a.has_z) {
+#pragma unroll
+            for (int k = 0; k < D; ++k)
+              t.dout[tix(a.zoff + k, row)] = abar * (Model::kBrownian ? a.dW[((size_t)i * D + k) * sB + p] : 0.0f) * msk;
+          }
+          mlp_delta<HP, TL>(nvA, t, row, dx);
+#pragma unroll
+          for (int k = 0; k < D; ++k) {
+            if (JUMP) dXacc[JUMP ? k : 0] += dx[1 + k]; else Xbar[k] += dx[1 + k];
+          }
+          __syncthreads();
+          wgA.accumulate(tb);
+          __syncthreads();
         }
-        __syncthreads();
-        wgA.accumulate(tb);
-        __syncthreads();
       }
       if constexpr (JTC) {
         float (&dXj)[D] = reinterpret_cast<float (&)[D]>(dXacc);
@@ -512,7 +544,7 @@ static size_t pricing_smem(const PricingArgs& a, bool backward) {
                 (jtc ? (backward ? kJtcBwdFloats : kJtcFwdFloats) : two ? net_smem_floats(a.netB, HP, backward) : 0);
   const int tl = a.has_jump ? (backward ? Tiles<HP, NOP>::bwd_floats() : Tiles<HP, NOP>::fwd_floats())
                             : (backward ? Tiles<HP, 4>::bwd_floats() : Tiles<HP, 4>::fwd_floats());
-  return sizeof(float) * (size_t)(w + kRedFloats + tl);
+  return sizeof(float) * (size_t)(w + kRedFloats + (a.has_jump ? row_floats<HP>() : 0) + tl);
 }
 
 template <class Model, int HP, bool JUMP, bool JTC = false>

@@ -213,6 +213,77 @@ __device__ __forceinline__ void mlp_delta(const NetView<HP>& nv, const TL& t, in
   gemv<HP>(a, nv.W1T, (nv.H + 3) >> 2, t.d1, row);
 }
 
+// ---- one row shared by the whole CTA ------------------------------------------------------------------------------
+// Jump schemes at small batch: the CTA (G == kThreads) works on ONE path, so the network at the path's state has a single
+// row.  Thread j owns hidden unit j; the layer vectors live in a small shared-memory block
+//   rv: xs[HP] | h1s[HP] | h2s[HP] | d2s[HP] | d1s[HP] | dos[HP] | outs[16]
+// Two barriers per forward, two more per delta pass - instead of every thread walking the same row through the tile MLP.
+template <int HP>
+__host__ __device__ constexpr int row_floats() { return 6 * HP + 16; }
+
+// x: CTA-uniform inputs (x[nin] = 1).  Outputs in rv[6 HP + o], o < nout, valid after the call.
+template <int HP>
+__device__ __forceinline__ void row_fwd(const NetView<HP>& nv, float* __restrict__ rv, const float (&x)[HP]) {
+  const int j = threadIdx.x;
+  __syncthreads();                                  // readers of the previous row are done
+  if (j == 32) {                                    // the inputs, for the weight gradient (a warp with no other work here)
+#pragma unroll
+    for (int c = 0; c < HP / 4; ++c) st4(rv + 4 * c, make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]));
+  }
+  if (j < HP) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int i = 0; i < HP; ++i)
+      if (i <= nv.nin) acc = fmaf(x[i], nv.W1[i * HP + j], acc);
+    rv[HP + j] = (j < nv.H) ? act_fn(acc, nv.act) : ((j == nv.H) ? 1.0f : 0.0f);
+  }
+  __syncthreads();
+  if (j < HP) {
+    float acc = 0.0f;
+#pragma unroll 8
+    for (int k = 0; k <= nv.H; ++k) acc = fmaf(rv[HP + k], nv.W2[k * HP + j], acc);
+    rv[2 * HP + j] = (j < nv.H) ? act_fn(acc, nv.act) : ((j == nv.H) ? 1.0f : 0.0f);
+  }
+  __syncthreads();
+  if (j < nv.nout) {
+    const float* __restrict__ w = nv.W3T + j * HP;
+    float acc = 0.0f;
+#pragma unroll 8
+    for (int k = 0; k <= nv.H; ++k) acc = fmaf(rv[2 * HP + k], w[k], acc);
+    rv[6 * HP + j] = acc;
+  }
+  __syncthreads();
+}
+// dout_j: this thread's entry of dL/dout (thread j < nout; anything elsewhere).  Leaves d2s / d1s / dos for the weight
+// gradient and returns dx[i] = dL/dx_i for i < NDX in every thread.
+template <int HP, int NDX>
+__device__ __forceinline__ void row_delta(const NetView<HP>& nv, float* __restrict__ rv, float dout_j, float (&dx)[NDX]) {
+  const int j = threadIdx.x;
+  if (j < HP) rv[5 * HP + j] = (j < nv.nout) ? dout_j : 0.0f;
+  __syncthreads();
+  if (j < HP) {
+    float acc = 0.0f;
+    for (int o = 0; o < nv.nout; ++o) acc = fmaf(rv[5 * HP + o], nv.W3T[o * HP + j], acc);
+    rv[3 * HP + j] = (j < nv.H) ? acc * dact_fn(rv[2 * HP + j], nv.act) : 0.0f;
+  }
+  __syncthreads();
+  if (j < HP) {
+    float acc = 0.0f;
+#pragma unroll 8
+    for (int k = 0; k < nv.H; ++k) acc = fmaf(rv[3 * HP + k], nv.W2T[k * HP + j], acc);
+    rv[4 * HP + j] = (j < nv.H) ? acc * dact_fn(rv[HP + j], nv.act) : 0.0f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NDX; ++i) dx[i] = 0.0f;
+#pragma unroll 8
+  for (int k = 0; k < nv.H; ++k) {
+    const float d = rv[4 * HP + k];
+#pragma unroll
+    for (int i = 0; i < NDX; ++i) dx[i] = fmaf(d, nv.W1T[k * HP + i], dx[i]);
+  }
+}
+
 // ---- weight gradient ----------------------------------------------------------------------------------------
 // Thread u of the CTA owns block `blk = u % NB` and row chunk `u / NB` of the block list
 //   [ dW1: ceil((nin+1)/4) x HP/4 | dW2: HP/4 x HP/4 | dW3T: ceil(nout/4) x HP/4 ].
@@ -282,6 +353,21 @@ struct WGrad {
       p[3][0] = fmaf(av.w, bv.x, p[3][0]); p[3][1] = fmaf(av.w, bv.y, p[3][1]);
       p[3][2] = fmaf(av.w, bv.z, p[3][2]); p[3][3] = fmaf(av.w, bv.w, p[3][3]);
     }
+  }
+
+  // single-row variant (row_fwd / row_delta above): only the first row chunk's owner of a block accumulates
+  __device__ __forceinline__ void accumulate_row(const float* __restrict__ rv) {
+    if (type < 0 || chunk != 0) return;
+    const float4 av = ld4(rv + (type == 0 ? k0 : type == 1 ? HP + k0 : 5 * HP + j0));
+    const float4 bv = ld4(rv + (type == 0 ? 4 * HP + j0 : type == 1 ? 3 * HP + j0 : 2 * HP + k0));
+    p[0][0] = fmaf(av.x, bv.x, p[0][0]); p[0][1] = fmaf(av.x, bv.y, p[0][1]);
+    p[0][2] = fmaf(av.x, bv.z, p[0][2]); p[0][3] = fmaf(av.x, bv.w, p[0][3]);
+    p[1][0] = fmaf(av.y, bv.x, p[1][0]); p[1][1] = fmaf(av.y, bv.y, p[1][1]);
+    p[1][2] = fmaf(av.y, bv.z, p[1][2]); p[1][3] = fmaf(av.y, bv.w, p[1][3]);
+    p[2][0] = fmaf(av.z, bv.x, p[2][0]); p[2][1] = fmaf(av.z, bv.y, p[2][1]);
+    p[2][2] = fmaf(av.z, bv.z, p[2][2]); p[2][3] = fmaf(av.z, bv.w, p[2][3]);
+    p[3][0] = fmaf(av.w, bv.x, p[3][0]); p[3][1] = fmaf(av.w, bv.y, p[3][1]);
+    p[3][2] = fmaf(av.w, bv.z, p[3][2]); p[3][3] = fmaf(av.w, bv.w, p[3][3]);
   }
 
   // external flat index (relative to the net) of p[a][b], or -1
