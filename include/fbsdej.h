@@ -93,7 +93,9 @@ typedef struct {
   int mma_mode;         /* 0 = every layer in fp32 FFMA; 1 = every matrix product of the network on tcgen05 tensor cores
                            (forward: both layers 3xTF32 with the A operands in TMEM; adjoint: six bf16x3 GEMMs per step,
                            weight-gradient accumulators resident in TMEM).  Available for the compensator-free solvers
-                           (SUMLOCALREG / MULTISTEPREG) of the pricing models and for all five MFG solvers, H <= 22. */
+                           (SUMLOCALREG / MULTISTEPREG) of the pricing models and for all five MFG solvers, H <= 22; for the
+                           jump schemes at d = 1 (tanh) it moves the jump evaluations - the path's own jump and the
+                           Monte-Carlo compensator rows - onto tcgen05 (the (U, Z) network stays fp32 FFMA). */
 } fbsdej_solver_desc;
 
 FBSDEJ_API const char* fbsdej_last_error(void);
