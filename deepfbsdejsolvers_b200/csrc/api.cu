@@ -708,14 +708,14 @@ int fbsdej_solver_create(fbsdej_ctx* ctx, const fbsdej_solver_desc* desc, const 
   FB_REQUIRE(!s->has_jump || desc->M >= 1, "this scheme needs M >= 1 compensator samples");
   FB_REQUIRE(desc->mma_mode == 0 || desc->mma_mode == 1, "mma_mode must be 0 (FFMA) or 1 (tcgen05)");
   // tcgen05 coverage: the compensator-free pricing solvers, the MFG solvers, and the jump evaluations (own jump + Monte-Carlo
-  // compensator) of the jump schemes at d = 1 with a tanh network
+  // compensator) of the jump schemes with a tanh network
   const fbsdej_net_desc& jn = desc->nets[one_net ? 0 : 1];
-  const bool jtc_ok = s->has_jump && s->D == 1 && HP == 24 && jn.H <= 22 && jn.act == FBSDEJ_ACT_TANH && s->P <= 24 * kThreads;
+  const bool jtc_ok = s->has_jump && (s->D == 1 || s->D == 10) && HP == 24 && jn.H <= 22 && jn.act == FBSDEJ_ACT_TANH && s->P <= 24 * kThreads;
   FB_REQUIRE(desc->mma_mode == 0 ||
                  (model == FBSDEJ_MODEL_MFG ? (desc->nets[0].H <= 22 && desc->nets[1].H <= 22 && desc->nets[0].act == desc->nets[1].act)
                                             : ((reg && HP == 24 && desc->nets[0].H <= 22) || jtc_ok)),
              "mma_mode = 1 (tcgen05) is available for the SUMLOCALREG / MULTISTEPREG pricing solvers, for the MFG solvers and for "
-             "the jump schemes at d = 1 with a tanh jump network; hidden width <= 22");
+             "the jump schemes with a tanh jump network; hidden width <= 22");
   cudaStream_t st = ctx->stream;
   if (model == FBSDEJ_MODEL_MERTON) {
     if (build_merton_tables(s.get())) return -2;

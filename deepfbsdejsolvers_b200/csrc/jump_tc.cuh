@@ -14,11 +14,13 @@
 
 namespace fbsdej {
 
-template <int ACT>
+// NXC: 8-feature chunks of the input row (2: up to 15 inputs + the constant 1, d = 1; 3: up to 23, d = 10)
+template <int ACT, int NXC>
 struct JumpTcFwd {
+  static_assert(NXC == 2 || NXC == 3, "input row of 16 or 24 features");
   // shared memory (floats): B operands of the two layers (TF32 hi / lo), W3 + b3, the mbarrier, the TMEM slots
-  static constexpr int NBR = rtc::NB;
-  static constexpr int W1B_HI = 0, W1B_LO = W1B_HI + 4 * NBR * 4, W2B_HI = W1B_LO + 4 * NBR * 4, W2B_LO = W2B_HI + 6 * NBR * 4,
+  static constexpr int NBR = rtc::NB, NI = 8 * NXC;
+  static constexpr int W1B_HI = 0, W1B_LO = W1B_HI + 2 * NXC * NBR * 4, W2B_HI = W1B_LO + 2 * NXC * NBR * 4, W2B_LO = W2B_HI + 6 * NBR * 4,
                        OFF_W3 = W2B_LO + 6 * NBR * 4 + 32, OFF_BAR = OFF_W3 + 32, FLOATS = OFF_BAR + 8;
   float* sm;
   uint64_t* bar;
@@ -78,15 +80,15 @@ struct JumpTcFwd {
     }
   }
   // xin: this row's inputs, xin[0] = 0 (time), xin[nin] = 1.  Every thread of the CTA calls (barriers inside).
-  __device__ __forceinline__ float eval(const float (&xin)[16]) {
+  __device__ __forceinline__ float eval(const float (&xin)[NI]) {
     using namespace rtc;
     const int row = threadIdx.x, warp = row >> 5;
-    fwd::store_tf32x8(lane_a, 0, xin);
-    fwd::store_tf32x8(lane_a, 1, xin + 8);
+#pragma unroll
+    for (int c8 = 0; c8 < NXC; ++c8) fwd::store_tf32x8(lane_a, c8, xin + 8 * c8);
     fwd::publish_tmem();
     if (row == 0) {
       tc::tc_fence_after();
-      fwd::gemm_k_tf32<2>(tmem, tmem_a, sbase + W1B_HI * 4, sbase + W1B_LO * 4);
+      fwd::gemm_k_tf32<NXC>(tmem, tmem_a, sbase + W1B_HI * 4, sbase + W1B_LO * 4);
       tc::mma_commit(bar);
     }
     tc::mbar_wait(bar, phase); phase ^= 1; tc::tc_fence_after();
@@ -127,19 +129,23 @@ struct JumpTcFwd {
   }
 };
 
-template <int ACT>
+template <int ACT, int NXC>
 struct JumpTcBwd {
-  static constexpr int CH = 128, NBR = rtc::NB;
+  static_assert(NXC == 2 || NXC == 3, "input row of 16 or 24 features");
+  static constexpr int CH = 128, NBR = rtc::NB, NI = 8 * NXC, KS1 = NXC == 2 ? 1 : 2, NDX = NXC == 2 ? 8 : 16;
   // operand tiles (uint4 offsets from `tiles`; they may alias memory the caller uses between the steps' tile loops)
   // Order matters: a layer GEMM with K = 32 reads one chunk past a 24-feature operand (the weights' rows there are zero, so
   // the chunk only has to hold finite bf16 values): H1_HI -> H2_HI[0], H1_LO -> H2_LO[0] (zeroed by set_time: the caller may
-  // have left anything there), D2_HI -> D2_LO[0], D2_LO -> XA_HI[0], D1_HI -> D1_LO[0], D1_LO -> H2_LO[0].
+  // have left anything there), D2_HI -> D2_LO[0], D2_LO -> XA_HI[0], D1_HI -> D1_LO[0], D1_LO -> H2_LO[0]; with 24 input
+  // features XA_HI -> XA_LO[0], XA_LO -> a pad chunk (zeroed by set_time).
   static constexpr int H1_HI = 0, H2_HI = 3 * CH, H1_LO = 6 * CH, H2_LO = 9 * CH, D2_HI = 12 * CH, D2_LO = 15 * CH, XA_HI = 18 * CH,
-                       XA_LO = 20 * CH, D1_HI = H2_HI, D1_LO = H1_LO, TILE_U4 = 22 * CH, TILE_FLOATS = TILE_U4 * 4;
+                       XA_LO = XA_HI + NXC * CH, XA_PAD = XA_LO + NXC * CH, D1_HI = H2_HI, D1_LO = H1_LO,
+                       TILE_U4 = XA_PAD + (NXC == 3 ? CH : 0), TILE_FLOATS = TILE_U4 * 4;
   // weights block (uint4 offsets from `wts`): the stacked B operands (as reg_backward_tc), then W3, the mbarriers, the TMEM slot
-  static constexpr int W1B = 0, W2B = W1B + 2 * 2 * NBR, WTB = W2B + 4 * 2 * NBR, W1T = WTB + 4 * 2 * NBR, U4_END = W1T + 4 * 2 * 16;
+  static constexpr int W1B = 0, W2B = W1B + 2 * KS1 * 2 * NBR, WTB = W2B + 4 * 2 * NBR, W1T = WTB + 4 * 2 * NBR, U4_END = W1T + 4 * 2 * NI;
   static constexpr int OFF_W3 = U4_END * 4, OFF_BAR = OFF_W3 + 24, FLOATS = OFF_BAR + 8;
-  static constexpr uint32_t C_ACC = 0, C_W1 = 48, C_W2 = 80, NCOLS = 128;
+  // tensor memory: layer accumulator (48) | dW1^T (2 NI) | [dW2 | dW3] (48)
+  static constexpr uint32_t C_ACC = 0, C_W1 = 48, C_W2 = 48 + 2 * NI, NCOLS = NXC == 2 ? 128 : 256;
   static constexpr int COL_DOUT = 23, SW = 49;
   float* sm;        // weights block
   uint4* u4;        // operand tiles
@@ -178,7 +184,7 @@ struct JumpTcBwd {
         const int i = e < n1 ? e / H : nin, j = e < n1 ? e % H : e - n1;
         tc::split_bf16(th[e], hi, lo);
         if (i >= 1 && i < nin) put(w1, NBR, j, i, hi, lo);
-        if (i < nin) put(w1t, 16, i, j, hi, lo);
+        if (i < nin) put(w1t, NI, i, j, hi, lo);
       } else if (e < n4) {
         const int k = e < n3 ? (e - n2) / H : H, j = e < n3 ? (e - n2) % H : e - n3;
         tc::split_bf16(th[e], hi, lo);
@@ -221,20 +227,21 @@ struct JumpTcBwd {
     }
     u4[H2_HI + row] = make_uint4(0u, 0u, 0u, 0u);       // K padding of the first tile's layer-2 GEMM
     u4[H2_LO + row] = make_uint4(0u, 0u, 0u, 0u);
+    if (NXC == 3) u4[XA_PAD + row] = make_uint4(0u, 0u, 0u, 0u);
   }
   // One tile: xin = this row's inputs (xin[0] = time for dW1, xin[nin] = 1), dout = adjoint of the row's output (0 for rows
   // that do not count).  dx[i] = dL/d xin[i], i < 8.  Every thread of the CTA calls.
-  __device__ __forceinline__ void step(const float (&xin)[16], float dout, float (&dx)[8]) {
+  __device__ __forceinline__ void step(const float (&xin)[NI], float dout, float (&dx)[NDX]) {
     using namespace rtc;
     const int row = threadIdx.x, warp = row >> 5;
     const bool issuer = (row & 31) == 0;
     drain_w();                                         // WG1 of the previous tile read X, D1
-    tc::store_bf16x8(u4 + XA_HI, u4 + XA_LO, 0, row, xin);
-    tc::store_bf16x8(u4 + XA_HI, u4 + XA_LO, 1, row, xin + 8);
+#pragma unroll
+    for (int c8 = 0; c8 < NXC; ++c8) tc::store_bf16x8(u4 + XA_HI, u4 + XA_LO, c8, row, xin + 8 * c8);
     publish();
     if (warp == 0 && issuer) {
       tc::tc_fence_after();
-      gemm_k<1, NBR>(tmem + C_ACC, sa(XA_HI), sa(XA_LO), sw(W1B));
+      gemm_k<KS1, NBR>(tmem + C_ACC, sa(XA_HI), sa(XA_LO), sw(W1B));
       tc::mma_commit(bar_f);
     }
     wait_f();
@@ -297,15 +304,15 @@ struct JumpTcBwd {
     publish();
     if (warp == 3 && issuer) {
       tc::tc_fence_after();
-      gemm_k<2, 16>(tmem + C_ACC, sa(D1_HI), sa(D1_LO), sw(W1T));
+      gemm_k<2, NI>(tmem + C_ACC, sa(D1_HI), sa(D1_LO), sw(W1T));
       tc::mma_commit(bar_f);
-      gemm_rows_stacked<32>(tmem + C_W1, sa(D1_HI), sa(XA_HI), started ? 1u : 0u);
+      gemm_rows_stacked<2 * NI>(tmem + C_W1, sa(D1_HI), sa(XA_HI), started ? 1u : 0u);
       tc::mma_commit(bar_w);
     }
     started = 1;
     pending_w = 1;
     wait_f();
-    load_acc<16, 8>(lane_base + C_ACC, dx);
+    load_acc<NI, NDX>(lane_base + C_ACC, dx);
     tc::tc_fence_before();
   }
   // TMEM weight gradients, added to g[...] (external flat layout of this network; first output column of W3 / b3).  All
@@ -322,7 +329,7 @@ struct JumpTcBwd {
       if (started) {
 #pragma unroll
         for (int c8 = 0; c8 < 6; ++c8) {
-          if (pass == 0 && c8 >= 4) break;
+          if (pass == 0 && c8 >= 2 * NI / 8) break;
           float v[8];
           tc::tmem_ld8(lane_base + (pass == 0 ? C_W1 : C_W2) + 8 * c8, v);
           tc::tmem_ld_wait();
@@ -334,7 +341,7 @@ struct JumpTcBwd {
       if (started && pass == 0) {
         for (int e = row; e < (nin + 1) * H; e += kThreads) {
           const int i = e / H, j = e % H;
-          g[e] += S[j * SW + i] + S[j * SW + 16 + i] + S[(24 + j) * SW + i];
+          g[e] += S[j * SW + i] + S[j * SW + NI + i] + S[(24 + j) * SW + i];
         }
       } else if (started) {
         for (int e = row; e < (H + 1) * H; e += kThreads) {

@@ -19,7 +19,10 @@
 namespace fbsdej {
 
 // JTC kernels: the tensor-core block of the jump network sits at the start of shared memory (1024-byte aligned)
-constexpr int kJtcFwdFloats = (JumpTcFwd<ACT_TANH>::FLOATS + 31) & ~31, kJtcBwdFloats = (JumpTcBwd<ACT_TANH>::FLOATS + 31) & ~31;
+// (sized for the wider of the two compiled input rows, so that the launch code need not know d)
+constexpr int kJtcFwdFloats = (JumpTcFwd<ACT_TANH, 3>::FLOATS + 31) & ~31, kJtcBwdFloats = (JumpTcBwd<ACT_TANH, 3>::FLOATS + 31) & ~31;
+template <int D>
+__host__ __device__ constexpr int jtc_nxc() { return 2 + 2 * D <= 16 ? 2 : 3; }   // inputs [t, X, jump features, 1] in 16 or 24 features
 
 int launch_reg_tc_backward(int model, int D, const PricingArgs& a, int grid, cudaStream_t st);   // reg_tc_kernels.cu
 int launch_reg_tc_forward(int model, int D, const PricingArgs& a, int grid, cudaStream_t st);
@@ -32,7 +35,8 @@ int reg_tc_forward_occupancy(int B, int sms);
 template <class Model, int HP, bool JUMP, bool JTC>
 __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a) {
   constexpr int D = Model::D;
-  static_assert(!JTC || (JUMP && 1 + 2 * D <= 7), "JTC: jump schemes, input gradients in one 8-column read");
+  static_assert(!JTC || (JUMP && 2 + 2 * D <= 24), "JTC: jump schemes, inputs in at most 24 features");
+  constexpr int NXC = jtc_nxc<D>();
   extern __shared__ __align__(1024) float smem[];
   const bool two = JUMP && !a.one_net;
   float* swA = smem + (JTC ? kJtcFwdFloats : 0);
@@ -47,7 +51,7 @@ __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a)
   nvA = load_net<HP>(swA, a.theta, a.netA, false);
   nvJ = (two && !JTC) ? load_net<HP>(swB, a.theta, a.netB, false) : nvA;
   zero_tiles(tb, TL::fwd_floats());
-  JumpTcFwd<ACT_TANH> jf;
+  JumpTcFwd<ACT_TANH, NXC> jf;
   if constexpr (JTC) jf.init(smem, a.theta, a.netB);
 
   const int row = threadIdx.x;
@@ -137,7 +141,7 @@ __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a)
           }
           float in[HP];
           Model::template jump_input<HP>(a, tf, X, Jm, in);
-          const float y = jf.eval(reinterpret_cast<const float (&)[16]>(in));
+          const float y = jf.eval(reinterpret_cast<const float (&)[8 * NXC]>(in));
           gc[1] = fmaf(w, y, gc[1]);
           if (m == nnz + 1) gc[0] = y;
         }
@@ -291,8 +295,11 @@ __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a
   if (JUMP && !JTC) wgB.init(nvJ, t);
   // JTC: the operand tiles of the tensor-core block live in the h1 .. d2 tiles of the FFMA network (every tile is rewritten
   // in full by whichever phase uses it next; the phases are separated by drain_w / the MMA waits)
-  static_assert(JumpTcBwd<ACT_TANH>::TILE_FLOATS <= TL::bwd_floats() - (HP + (JUMP ? NOP : 4)) * TR, "operand tiles fit between the input and dout tiles");
-  JumpTcBwd<ACT_TANH> jb;
+  constexpr int NXC = jtc_nxc<D>();
+  using JB = JumpTcBwd<ACT_TANH, NXC>;
+  static_assert(JB::TILE_FLOATS <= TL::bwd_floats() - (HP + (JUMP ? NOP : 4)) * TR, "operand tiles fit between the input and dout tiles");
+  static_assert(!JTC || 1 + D <= JB::NDX, "input gradients of the state come back in one read");
+  JB jb;
   if constexpr (JTC) jb.init(smem, t.h1, a.theta, a.netB);
 
   const int row = threadIdx.x;
@@ -459,10 +466,10 @@ __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a
             for (int k = 0; k < D; ++k) Jm[k] = Jv[k];
           }
           Model::template jump_input<HP>(a, tf, X, Jm, dx);
-          float d8[8];
-          jb.step(reinterpret_cast<const float (&)[16]>(dx), dout, d8);
+          float dn[JB::NDX];
+          jb.step(reinterpret_cast<const float (&)[8 * NXC]>(dx), dout, dn);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) dx[j] = d8[j];
+          for (int j = 0; j < JB::NDX; ++j) dx[j] = dn[j];
           Model::template jump_input_grad<HP>(a, Jm, dx, dXj);
         }
 #pragma unroll
@@ -575,9 +582,7 @@ static int launch_one(const PricingArgs& a, int grid, bool backward, cudaStream_
 template <class Model, int HP>
 static int launch_pair(const PricingArgs& a, int grid, bool backward, cudaStream_t st) {
   if (a.has_jump && a.mma_mode == 1) {   // jump network on tcgen05 (jump_tc.cuh): two-network schemes, d = 1
-    if constexpr (Model::D == 1) return launch_one<Model, HP, true, true>(a, grid, backward, st);
-    set_error("pricing kernels: the tcgen05 jump path is compiled for d = 1");
-    return -1;
+    return launch_one<Model, HP, true, true>(a, grid, backward, st);
   }
   if (a.has_jump) return launch_one<Model, HP, true>(a, grid, backward, st);
   if (a.mma_mode == 1) {   // compensator-free solvers on tcgen05 (reg_tc_kernels.cu)
@@ -636,7 +641,8 @@ static int occ_one(const PricingArgs& a, bool backward) {
     if (e3 == cudaSuccess && fa.numRegs > 0) {
       const int by_regs = 65536 / (((fa.numRegs + 7) & ~7) * kThreads);
       const int by_smem = (int)((228 * 1024) / (smem + fa.sharedSizeBytes + 1024));
-      nb = std::max(1, std::min(std::min(by_regs, by_smem), backward ? 4 : 5));
+      const int by_tmem = backward ? 512 / (int)JumpTcBwd<ACT_TANH, jtc_nxc<Model::D>()>::NCOLS : 5;
+      nb = std::max(1, std::min(std::min(by_regs, by_smem), by_tmem));
     }
   }
   if (e1 != cudaSuccess || e2 != cudaSuccess || nb < 1) {
@@ -659,8 +665,7 @@ static int occ_pair(const PricingArgs& a, bool backward) {
     return backward ? 4 : reg_tc_forward_occupancy(a.B, sms);
   }
   if (a.has_jump && a.mma_mode == 1) {   // the occupancy calculator does not know about TMEM: 128 / 96 of 512 columns per CTA
-    if constexpr (Model::D == 1) return occ_one<Model, HP, true, true>(a, backward);
-    return 1;
+    return occ_one<Model, HP, true, true>(a, backward);
   }
   if (a.has_jump) return occ_one<Model, HP, true>(a, backward);
   return occ_one<Model, HP, false>(a, backward);

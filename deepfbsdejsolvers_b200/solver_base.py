@@ -85,8 +85,8 @@ class PricingSolverBase:
         self.M = self.M_DEFAULT if M is None else int(M)
         self.seed, self.ctx, self.stale_time = seed, ctx, stale_time
         # tcgen05 path (3xTF32 forward, bf16x3 adjoint; tests/test_tc_gpu.py): used unless told otherwise (None = automatic:
-        # on when the kernels cover the scheme and the network shape - the compensator-free solvers at d in {1, 10}, the jump
-        # schemes at d = 1)
+        # on when the kernels cover the scheme and the network shape - the compensator-free solvers and the jump evaluations of
+        # the jump schemes at d in {1, 10})
         self.tensor_cores = tensor_cores
         self.native: Optional[NativeSolver] = None
 
@@ -115,9 +115,9 @@ class PricingSolverBase:
         M = 0 if self.REG else self.M
         spec = self.netA.spec()
         tc_ok = self.REG and spec.H <= 22 and spec.L == 2 and spec.nout == 1 and d in (1, 10)
-        # jump schemes at d = 1: the jump evaluations (own jump + compensator rows) on tcgen05
+        # jump schemes: the jump evaluations (own jump + compensator rows) on tcgen05
         jtc_ok = False
-        if not self.REG and d == 1:
+        if not self.REG and d in (1, 10):
             sb = self.netB.spec() if self.TWO_NET else spec
             jtc_ok = sb.H <= 22 and spec.H <= 23 and sb.L == 2 and sb.activation == "tanh"
         auto = tc_ok or jtc_ok

@@ -94,7 +94,7 @@ typedef struct {
                            (forward: both layers 3xTF32 with the A operands in TMEM; adjoint: six bf16x3 GEMMs per step,
                            weight-gradient accumulators resident in TMEM).  Available for the compensator-free solvers
                            (SUMLOCALREG / MULTISTEPREG) of the pricing models and for all five MFG solvers, H <= 22; for the
-                           jump schemes at d = 1 (tanh) it moves the jump evaluations - the path's own jump and the
+                           jump schemes (tanh) it moves the jump evaluations - the path's own jump and the
                            Monte-Carlo compensator rows - onto tcgen05 (the (U, Z) network stays fp32 FFMA). */
 } fbsdej_solver_desc;
 

@@ -15,6 +15,7 @@ def main():
     ap.add_argument("--case", default="", help="run one case only (for ncu), e.g. 'vg Global'")
     ap.add_argument("--paths", type=int, default=1000)
     ap.add_argument("--iters", type=int, default=0)
+    ap.add_argument("--ffma", action="store_true", help="with --case: time the fp32 FFMA tile kernels instead")
     a = ap.parse_args()
     import helpers as H
     from bench_configs import time_solver
@@ -27,16 +28,21 @@ def main():
     net = lambda bY0, nout: cp.Net(bY0, nout, [21, 21], "tanh")
     merton = lambda: cp.MertonJumpModel(M["T"], M["N"], M["r"], M["muJ"], M["sigmaJ"], M["sigma"], M["lam"], M["K"], M["x0"], cp.AbsCoupling(0.1), 30)
     vg = lambda: cp.VGmodel(V["T"], V["N"], V["r"], V["theta"], V["kappa"], V["sigmaJ"], V["K"], V["x0"], cp.AbsCoupling(0.1))
-    cases = [("merton Global", lambda tc: cp.SolverGlobalFBSDE(merton(), net(1, 1), net(0, 1), 4e-4, tensor_cores=tc)),
+    merton10 = lambda: cp.MertonJumpModel(M["T"], 100, M["r"], M["muJ"], M["sigmaJ"], M["sigma"], M["lam"], M["K"], M["x0"], cp.AbsCoupling(0.1), 100, d=10)
+    cases = [("merton10 Global", lambda tc: cp.SolverGlobalFBSDE(merton10(), net(1, 10), net(0, 1), 4e-4, M=256, tensor_cores=tc)),
+             ("merton Global", lambda tc: cp.SolverGlobalFBSDE(merton(), net(1, 1), net(0, 1), 4e-4, tensor_cores=tc)),
              ("merton SumLocal2", lambda tc: cp.SolverSumLocalFBSDE2(merton(), net(0, 2), net(0, 1), 3e-4, tensor_cores=tc)),
              ("merton MultiStep1", lambda tc: cp.SolverMultiStepFBSDE1(merton(), net(0, 2), 3e-4, tensor_cores=tc)),
              ("vg SumLocal1", lambda tc: pj.SolverSumLocalFBSDE1(vg(), net(0, 1), 3e-4, tensor_cores=tc)),
              ("vg Global", lambda tc: pj.SolverGlobalFBSDE(vg(), net(0, 1), net(1, 1), 5e-4, tensor_cores=tc)),
              ("vg MultiStep2", lambda tc: pj.SolverMultiStepFBSDE2(vg(), net(0, 1), net(0, 1), 3e-4, tensor_cores=tc))]
     if a.case:
-        print(json.dumps({"case": a.case, "paths": a.paths, "tcgen05_ms": time_solver(dict(cases)[a.case](True), a.paths, a.iters or 3, ctx)}))
+        print(json.dumps({"case": a.case, "paths": a.paths,
+                          "ffma_ms" if a.ffma else "tcgen05_ms": time_solver(dict(cases)[a.case](not a.ffma), a.paths, a.iters or 3, ctx)}))
         return
     for name, mk in cases:
+        if name.startswith("merton10"):
+            continue                              # d = 10: run with --case (B = 2^16 takes a while on the FFMA tiles)
         for B in (10, 100, 1000):
             iters = 100 if B <= 100 else 20
             r = {"case": name, "paths": B}

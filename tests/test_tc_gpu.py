@@ -185,3 +185,30 @@ def test_jump_network_on_tensor_cores_vg(ctx, scheme):
     s.set_theta(theta)
     s.set_noise(B, None, H.to_planes(noise["J"]), H.to_planes(noise["JMC"]))
     _check_jump(s, B, l64, g64, g32, aux64, False)
+
+
+@pytest.mark.parametrize("scheme", ["Global", "MultiStep2", "SumLocal1"])
+@pytest.mark.parametrize("B,M", [(64, 400), (1500, 96)])
+def test_jump_network_on_tensor_cores_merton_d10(ctx, scheme, B, M):
+    """d = 10: the jump rows have 22 input features (three 8-feature chunks of the operand tile); one path per CTA with a
+    cluster (B = 64) and several paths per tile (B = 1500)."""
+    d = 10
+    p = dict(H.MERTON, N=12)
+    om = MertonOracle(aLin=H.ALIN, limit=100, d=d, **p)
+    layout = H.pricing_layout("merton", scheme, d)
+    theta = H.random_theta(layout, 51)
+    noise = H.merton_noise(om, B, M, seed=52, with_jmc=True)
+    l32, g32, _ = H.oracle_pricing(om, scheme, layout, theta, noise, B)
+    l64, g64, aux64 = H.oracle_pricing(om, scheme, layout, theta, noise, B, dtype=torch.float64)
+    s = H.native_pricing(ctx, "merton", p, scheme, layout, d=d, M=M, limit=100, tensor_cores=True)
+    s.set_theta(theta)
+    s.set_noise(B, H.to_planes(noise["dW"]), H.to_planes(noise["J"]), H.to_planes(noise["JMC"]))
+    out, tx, ty, tz = s.loss(B, traj=True)
+    assert abs(out[0] - l64) <= 2e-5 * abs(l64), (out[0], l64)
+    X = aux64["X"].transpose(0, 2, 1)
+    assert np.abs(tx - X).max() <= 2e-6 + 1e-5 * np.abs(X).max()
+    g = s.grad(B)
+    scale = np.abs(g64).max()
+    e_gpu, e_32 = np.abs(g[4:] - g64).max() / scale, np.abs(g32 - g64).max() / scale
+    print("loss rel", abs(out[0] - l64) / abs(l64), "grad rel-to-max", e_gpu, "(fp32 oracle", e_32, ")")
+    assert e_gpu <= 3e-4, f"gradient error {e_gpu:.3e}"
