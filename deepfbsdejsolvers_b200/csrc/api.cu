@@ -237,7 +237,7 @@ int pick_G(const fbsdej_solver* s, int B) {
   return G;
 }
 
-// CTAs per path (thread-block cluster) for the jump schemes at small batch: as many as fill the GPU (portable limit 8),
+// CTAs per path (thread-block cluster) for the jump schemes at small batch: as many as fill the GPU (at most 16),
 // but no more than the expected evaluated compensator rows per step give one row per thread.
 int pick_C(const fbsdej_solver* s, int B, int G) {
   if (!s->has_jump || G != kThreads || getenv("FBSDEJ_NO_CLUSTER")) return 1;
@@ -246,7 +246,11 @@ int pick_C(const fbsdej_solver* s, int B, int G) {
     rows = s->M * (1.0 - std::exp(-s->mer.lam * (s->mer.T / s->mer.N) * s->D)) + 1.0;
   // (the tcgen05 jump kernels keep two CTAs per SM resident in the adjoint sweep, four in the forward one)
   const int per_sm = s->desc.mma_mode == 1 ? 2 : 1;
-  int C = std::min(8, s->ctx->sms * per_sm / std::max(B, 1));
+  // 16 CTAs per cluster is sm_100's non-portable maximum (the launch sets cudaFuncAttributeNonPortableClusterSizeAllowed);
+  // FBSDEJ_MAX_CLUSTER=8 restores the portable limit
+  const char* mc = getenv("FBSDEJ_MAX_CLUSTER");
+  const int maxC = mc ? std::max(1, std::min(16, atoi(mc))) : 16;
+  int C = std::min(maxC, s->ctx->sms * per_sm / std::max(B, 1));
   C = std::min(C, (int)std::ceil(rows / kThreads));
   return std::max(C, 1);
 }

@@ -570,10 +570,12 @@ static int launch_one(const PricingArgs& a, int grid, bool backward, cudaStream_
   if (!backward) {
     auto kern = pricing_forward<Model, HP, JUMP, JTC>;
     FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (C > 8) FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     FB_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
   } else {
     auto kern = pricing_backward<Model, HP, JUMP, JTC>;
     FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (C > 8) FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     FB_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
   }
   FB_CUDA(cudaGetLastError());
