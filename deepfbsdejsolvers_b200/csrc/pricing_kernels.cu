@@ -33,10 +33,11 @@ int reg_tc_forward_occupancy(int B, int sms);
 // JTC: the jump network (two-network schemes, one output, at most 14 inputs, tanh) runs on tcgen05 (jump_tc.cuh): the
 // path's own jump and its compensator samples are the rows of 128-row tiles.
 template <class Model, int HP, bool JUMP, bool JTC>
-__global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a) {
+__global__ void __launch_bounds__(kThreads, JTC ? 4 : 0) pricing_forward(const PricingArgs a) {
   constexpr int D = Model::D;
   static_assert(!JTC || (JUMP && 2 + 2 * D <= 24), "JTC: jump schemes, inputs in at most 24 features");
   constexpr int NXC = jtc_nxc<D>();
+  constexpr bool PF = JTC && D == 1;     // compensator samples requested one tile ahead (d = 10: the registers are worth more)
   extern __shared__ __align__(1024) float smem[];
   const bool two = JUMP && !a.one_net;
   float* swA = smem + (JTC ? kJtcFwdFloats : 0);
@@ -90,6 +91,19 @@ __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a)
           prefetch_l2(a.J + ((size_t)(i + 1) * D + k) * sB + p);
         }
       }
+      // JTC: the step's sample counts and this thread's first compensator sample are requested before the (U, Z) network runs;
+      // inside the tile loop the next sample is always in flight while the current tile is evaluated
+      int nnz = 0, n0 = 0;
+      float Jn[D];
+      auto jmc_load = [&](int m) {
+        const int mc = m < a.Mcap ? m : a.Mcap - 1;
+#pragma unroll
+        for (int k = 0; k < D; ++k) Jn[k] = a.JMC[((size_t)i * D + k) * a.Mcap + mc];
+      };
+      if constexpr (JTC) {
+        nnz = a.jmc_nnz[i]; n0 = a.jmc_n0[i];
+        if constexpr (PF) jmc_load(crank * G + g);
+      }
       float y_net = 0.0f, zdw = 0.0f;
       if (a.use_netA) {
         float in[HP];
@@ -119,7 +133,6 @@ __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a)
       float gam = 0.0f, comp = 0.0f;
       if constexpr (JTC) {
         // rows of the step: compensator samples 0 .. nnz-1, the zero sample (weight n0), the path's own jump
-        const int nnz = a.jmc_nnz[i], n0 = a.jmc_n0[i];
         const int iters = (nnz + 2 + G * C - 1) / (G * C);
         float gc[2] = {0.0f, 0.0f};
         jf.set_time(tf);
@@ -132,13 +145,14 @@ __global__ void __launch_bounds__(kThreads) pricing_forward(const PricingArgs a)
           if (m < nnz) {
             w = 1.0f;
 #pragma unroll
-            for (int k = 0; k < D; ++k) Jm[k] = a.JMC[((size_t)i * D + k) * a.Mcap + m];
+            for (int k = 0; k < D; ++k) Jm[k] = PF ? Jn[k] : a.JMC[((size_t)i * D + k) * a.Mcap + m];
           } else if (m == nnz) {
             w = (float)n0;
           } else if (m == nnz + 1) {
 #pragma unroll
             for (int k = 0; k < D; ++k) Jm[k] = Jv[k];
           }
+          if (PF && it + 1 < iters) jmc_load(m + G * C);
           float in[HP];
           Model::template jump_input<HP>(a, tf, X, Jm, in);
           const float y = jf.eval(reinterpret_cast<const float (&)[8 * NXC]>(in));
@@ -296,6 +310,7 @@ __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a
   // JTC: the operand tiles of the tensor-core block live in the h1 .. d2 tiles of the FFMA network (every tile is rewritten
   // in full by whichever phase uses it next; the phases are separated by drain_w / the MMA waits)
   constexpr int NXC = jtc_nxc<D>();
+  constexpr bool PF = JTC && D == 1;
   using JB = JumpTcBwd<ACT_TANH, NXC>;
   static_assert(JB::TILE_FLOATS <= TL::bwd_floats() - (HP + (JUMP ? NOP : 4)) * TR, "operand tiles fit between the input and dout tiles");
   static_assert(!JTC || 1 + D <= JB::NDX, "input gradients of the state come back in one read");
@@ -397,6 +412,17 @@ __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a
 #pragma unroll
         for (int k = 0; k < (JUMP ? D : 1); ++k) dXacc[k] = 0.0f;
       }
+      int nnz = 0, n0 = 0;
+      float Jn[D];
+      auto jmc_load = [&](int m) {
+        const int mc = m < a.Mcap ? m : a.Mcap - 1;
+#pragma unroll
+        for (int k = 0; k < D; ++k) Jn[k] = a.JMC[((size_t)i * D + k) * a.Mcap + mc];
+      };
+      if constexpr (JTC) {
+        nnz = a.jmc_nnz[i]; n0 = a.jmc_n0[i];
+        if constexpr (PF) jmc_load(crank * G + g);
+      }
       if constexpr (JTC) jb.drain_w();   // the last weight-gradient GEMM of the step above still reads the shared tiles
       if (a.use_netA) {
 #pragma unroll
@@ -444,7 +470,6 @@ __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a
       }
       if constexpr (JTC) {
         float (&dXj)[D] = reinterpret_cast<float (&)[D]>(dXacc);
-        const int nnz = a.jmc_nnz[i], n0 = a.jmc_n0[i];
         const float cscale = -abar / (float)a.M * vmsk;
         const int iters = (nnz + 2 + G * C - 1) / (G * C);
         jb.set_time(tf);
@@ -457,7 +482,7 @@ __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a
           if (m < nnz) {
             dout = cscale;
 #pragma unroll
-            for (int k = 0; k < D; ++k) Jm[k] = a.JMC[((size_t)i * D + k) * a.Mcap + m];
+            for (int k = 0; k < D; ++k) Jm[k] = PF ? Jn[k] : a.JMC[((size_t)i * D + k) * a.Mcap + m];
           } else if (m == nnz) {
             dout = cscale * (float)n0;
           } else if (m == nnz + 1) {                       // the path's own jump
@@ -465,6 +490,7 @@ __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a
 #pragma unroll
             for (int k = 0; k < D; ++k) Jm[k] = Jv[k];
           }
+          if (PF && it + 1 < iters) jmc_load(m + G * C);
           Model::template jump_input<HP>(a, tf, X, Jm, dx);
           float dn[JB::NDX];
           jb.step(reinterpret_cast<const float (&)[8 * NXC]>(dx), dout, dn);
