@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(kThreads, JTC ? 4 : 0) pricing_forward(const P
 }
 
 template <class Model, int HP, bool JUMP, bool JTC>
-__global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a) {
+__global__ void __launch_bounds__(kThreads, JTC ? 2 : 0) pricing_backward(const PricingArgs a) {
   constexpr int D = Model::D;
   extern __shared__ __align__(1024) float smem[];
   const bool two = JUMP && !a.one_net;
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(kThreads) pricing_backward(const PricingArgs a
   // JTC: the operand tiles of the tensor-core block live in the h1 .. d2 tiles of the FFMA network (every tile is rewritten
   // in full by whichever phase uses it next; the phases are separated by drain_w / the MMA waits)
   constexpr int NXC = jtc_nxc<D>();
-  constexpr bool PF = JTC && D == 1;
+  constexpr bool PF = JTC;               // (two CTAs per SM whatever the register count: always prefetch)
   using JB = JumpTcBwd<ACT_TANH, NXC>;
   static_assert(JB::TILE_FLOATS <= TL::bwd_floats() - (HP + (JUMP ? NOP : 4)) * TR, "operand tiles fit between the input and dout tiles");
   static_assert(!JTC || 1 + D <= JB::NDX, "input gradients of the state come back in one read");
