@@ -7,8 +7,9 @@
 //                      the CTA, six bf16x3 GEMMs (as reg_backward_tc); read once at kernel end (flush)
 //
 // Only the first output of the network is evaluated (two-network schemes: the jump network's single output; one-network
-// schemes: U of the (U, Z) network at the jumped state) and nin <= 14.  The time feature is folded into a per-step effective
-// bias (set_time).  Building blocks: tc_net.cuh.
+// schemes: U of the (U, Z) network at the jumped state); the input row [t, state, jump features, 1] has 16 (d = 1) or 24
+// (d = 10) features (template parameter NXC).  The time feature is folded into a per-step effective bias (set_time).
+// Building blocks: tc_net.cuh.
 #pragma once
 #include "tc_net.cuh"
 
