@@ -212,3 +212,19 @@ def test_jump_network_on_tensor_cores_merton_d10(ctx, scheme, B, M):
     e_gpu, e_32 = np.abs(g[4:] - g64).max() / scale, np.abs(g32 - g64).max() / scale
     print("loss rel", abs(out[0] - l64) / abs(l64), "grad rel-to-max", e_gpu, "(fp32 oracle", e_32, ")")
     assert e_gpu <= 3e-4, f"gradient error {e_gpu:.3e}"
+
+
+def test_jump_network_on_tensor_cores_one_path_per_thread(ctx):
+    """Large batch: pick_G gives every thread its own path (G = 1), a tile is 128 paths on the same compensator sample."""
+    B, M, scheme = 40000, 24, "Global"
+    p = dict(H.MERTON, N=6)
+    om = MertonOracle(aLin=H.ALIN, limit=30, d=1, **p)
+    layout = H.pricing_layout("merton", scheme, 1)
+    theta = H.random_theta(layout, 61)
+    noise = H.merton_noise(om, B, M, seed=62, with_jmc=True)
+    l32, g32, _ = H.oracle_pricing(om, scheme, layout, theta, noise, B)
+    l64, g64, aux64 = H.oracle_pricing(om, scheme, layout, theta, noise, B, dtype=torch.float64)
+    s = H.native_pricing(ctx, "merton", p, scheme, layout, d=1, M=M, tensor_cores=True)
+    s.set_theta(theta)
+    s.set_noise(B, H.to_planes(noise["dW"]), H.to_planes(noise["J"]), H.to_planes(noise["JMC"]))
+    _check_jump(s, B, l64, g64, g32, aux64, True)
