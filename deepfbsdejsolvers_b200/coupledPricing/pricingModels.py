@@ -103,9 +103,10 @@ class MertonJumpModel(_PricingModel):
         self.T, self.r, self.sig, self.muJ, self.sigJ, self.lam = T, r, sigma, muJ, sigmaJ, lam
         self.K, self.N, self.dt, self.x0, self.func, self.limit, self.d = K, int(N), T / N, x0, func, int(limit), int(d)
         self.aLin = coupling_slope(func)
-        # d = 1 (the reference): sum the `limit` series terms at every path-step, as pricingModels.py:40-49 does.
-        # d > 1 needs limit ~ 100 terms: evaluate the same series through the library's per-step Hermite table.
-        self.price_table = (self.d > 1) if price_table is None else bool(price_table)
+        # The series of pricingModels.py:40-49 (`limit` terms, two normal CDFs each) is evaluated through the library's per-step
+        # cubic-Hermite table in log-moneyness (absolute error < 5e-8; exact series outside the grid) unless price_table=False,
+        # which sums the terms at every path-step the way the reference does.
+        self.price_table = True if price_table is None else bool(price_table)
 
     def c_params(self) -> L.MertonParams:
         return L.MertonParams(self.T, self.r, self.muJ, self.sigJ, self.sig, self.lam, self.K, self.x0, self.aLin, self.N,

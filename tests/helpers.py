@@ -118,7 +118,7 @@ def oracle_mfg(model, scheme, layout, theta, noise, B, dtype=torch.float32, w=(1
 
 
 # ---- native side --------------------------------------------------------------------------------------------
-def native_pricing(ctx, kind, params, scheme, layout, d=1, M=0, limit=30, stale_time=True, price_table=None, tensor_cores=False):
+def native_pricing(ctx, kind, params, scheme, layout, d=1, M=0, limit=30, stale_time=True, price_table=False, tensor_cores=False):
     from deepfbsdejsolvers_b200 import NetSpec
     from deepfbsdejsolvers_b200.coupledPricing import MertonJumpModel, VGmodel, AbsCoupling
     if kind == "merton":

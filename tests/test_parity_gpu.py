@@ -55,6 +55,31 @@ def test_merton_d1(ctx, scheme, B):
     _grad_check(g[4:], g64, g32)
 
 
+@pytest.mark.parametrize("scheme", ["Global", "SumLocal1", "SumLocalReg"])
+@pytest.mark.parametrize("tensor_cores", [False, True])
+def test_merton_d1_price_table(ctx, scheme, tensor_cores):
+    """d = 1 with the closed form A(i, X) read from the per-step Hermite table (the model class's default) instead of the
+    30-term series: same parity bar."""
+    B, M = 300, 160
+    om = MertonOracle(aLin=H.ALIN, limit=30, d=1, **H.MERTON)
+    layout = H.pricing_layout("merton", scheme, 1)
+    theta = H.random_theta(layout, 11)
+    reg = scheme.endswith("Reg")
+    noise = H.merton_noise(om, B, M, seed=12, with_jmc=not reg)
+    l32, g32, _ = H.oracle_pricing(om, scheme, layout, theta, noise, B)
+    l64, g64, aux64 = H.oracle_pricing(om, scheme, layout, theta, noise, B, dtype=torch.float64)
+    s = H.native_pricing(ctx, "merton", H.MERTON, scheme, layout, d=1, M=0 if reg else M, price_table=True, tensor_cores=tensor_cores)
+    s.set_theta(theta)
+    s.set_noise(B, H.to_planes(noise["dW"]), H.to_planes(noise["J"]), H.to_planes(noise["JMC"]) if "JMC" in noise else None)
+    out, tx, ty, tz = s.loss(B, traj=True)
+    _close(out[0], l64, rtol=2e-5 if tensor_cores else RTOL)
+    _close(tx[:, 0, :], aux64["X"][:, :, 0])
+    g = s.grad(B)
+    scale = np.abs(g64).max() + 1e-30
+    e_gpu = np.abs(g[4:] - g64).max() / scale
+    assert e_gpu <= (3e-4 if tensor_cores else 1e-4), f"gradient error {e_gpu:.3e}"
+
+
 @pytest.mark.parametrize("scheme", ["Global", "MultiStep2", "SumLocal1", "SumLocalReg", "MultiStepReg"])
 @pytest.mark.parametrize("price_table", [False, True])
 def test_merton_d10(ctx, scheme, price_table):

@@ -74,7 +74,8 @@ def test_tensor_core_path_matches_oracle(ctx, scheme, d, B):
     noise = H.merton_noise(om, B, 0, seed=22, with_jmc=False)
     l32, g32, _ = H.oracle_pricing(om, scheme, layout, theta, noise, B)
     l64, g64, aux64 = H.oracle_pricing(om, scheme, layout, theta, noise, B, dtype=torch.float64)
-    s = H.native_pricing(ctx, "merton", p, scheme, layout, d=d, limit=30 if d == 1 else 100, tensor_cores=True)
+    # d = 10 through the per-step Hermite table of the closed form (the default of the model class), d = 1 through the series
+    s = H.native_pricing(ctx, "merton", p, scheme, layout, d=d, limit=30 if d == 1 else 100, tensor_cores=True, price_table=d > 1)
     s.set_theta(theta)
     s.set_noise(B, H.to_planes(noise["dW"]), H.to_planes(noise["J"]), None)
     _check(s, B, l64, g64, g32, aux64, d)
