@@ -78,6 +78,10 @@ def _load():
         "fbsdej_solver_grad_step": (i32, [vp, vp, u64, vp, u32, i32, i32, vp]),
         "fbsdej_bump_u32": (i32, [vp, vp]),
         "fbsdej_solver_train_steps": (i32, [vp, vp, vp, vp, vp, vp, vp, u64, i32, i32, f32, f32, f32, f32, vp]),
+        "fbsdej_solver_dp_init": (i32, [vp, i32, i32, vp]),
+        "fbsdej_solver_dp_buffer": (i32, [vp, vp]),
+        "fbsdej_solver_dp_connect": (i32, [vp, vp, vp]),
+        "fbsdej_solver_train_steps_dp": (i32, [vp, vp, vp, vp, vp, vp, vp, u64, i32, i32, u32, i32, f32, f32, f32, f32, vp]),
         "fbsdej_solver_profile": (i32, [vp, vp, u64, i32, i32, C.POINTER(C.c_float)]),
         "fbsdej_solver_net_forward": (i32, [vp, vp, i32, vp, i32, vp]),
         "fbsdej_net_forward": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, i32, vp]),

@@ -179,7 +179,18 @@ struct fbsdej_solver {
   const Rng* rng = nullptr;
   // cached training graph
   cudaGraphExec_t graph = nullptr;
-  struct Key { const void *theta, *m, *v, *mask, *t, *it, *loss; uint64_t seed; int B; float lr, b1, b2, eps; } key;
+  struct Key { const void *theta, *m, *v, *mask, *t, *it, *loss; uint64_t seed; int B; float lr, b1, b2, eps;
+               int B_global; uint32_t path_offset; int dp; } key;
+  // data-parallel exchange inside the finishing kernel (fbsdej_solver_dp_*, util.cuh: XchgArgs)
+  struct Dp {
+    int rank = 0, world = 1;
+    unsigned char* buf = nullptr;              // this rank's exchange buffer
+    std::vector<void*> peers;                  // [world] buffers of every rank as seen from this process
+    std::vector<char> opened;                  // peers[r] came from cudaIpcOpenMemHandle
+    float** d_data = nullptr; uint32_t** d_flags = nullptr;   // device pointer tables
+    bool connected = false;
+  } dp;
+  bool dp_step = false;                        // set by train_steps_dp around the step
 };
 
 namespace {
@@ -350,8 +361,15 @@ int run_pass(fbsdej_solver* s, const float* theta, int B, int B_global, float* o
   // loss partials come from the forward grid, gradient partials from the backward grid
   if (s->finish && with_grad) {
     const fbsdej_solver::Finish& f = *s->finish;
+    XchgArgs x{};
+    if (s->dp_step) {
+      const size_t data_bytes = sizeof(float) * 2 * (size_t)s->dp.world * xchg_nstride(s->P);
+      x.peer_data = s->dp.d_data; x.peer_flags = s->dp.d_flags;
+      x.xctr = reinterpret_cast<uint32_t*>(s->dp.buf + data_bytes) + (size_t)s->dp.world * xchg_nblk(s->P);
+      x.rank = s->dp.rank; x.world = s->dp.world; x.nstride = xchg_nstride(s->P); x.nblk = xchg_nblk(s->P);
+    }
     if (launch_reduce_adam(s->lpart, grid_f, s->gpart, grid_b, s->P, out, f.theta, f.m, f.v, f.mask, f.lr, f.b1, f.b2, f.eps,
-                           f.t_dev, f.iter_dev, f.loss_dst, s->step_ctr, s->step_ctr + 1, st))
+                           f.t_dev, f.iter_dev, f.loss_dst, s->step_ctr, s->step_ctr + 1, st, s->dp_step ? &x : nullptr))
       return -2;
   } else if (launch_reduce_partials(s->lpart, grid_f, s->gpart, grid_b, s->P, out, with_grad, st)) {
     return -2;
@@ -631,6 +649,9 @@ int fbsdej_solver_destroy(fbsdej_solver* s) {
   dev_free(s->vg_coef); dev_free(s->vg_scale); dev_free(s->pois_thr); dev_free(s->qaver); dev_free(s->meanhq);
   dev_free(s->jmc_raw); dev_free(s->jmc); dev_free(s->jmc_nnz); dev_free(s->jmc_n0);
   dev_free(s->lpart); dev_free(s->gpart); dev_free(s->out_dev); dev_free(s->step_ctr);
+  for (size_t r = 0; r < s->dp.peers.size(); ++r)
+    if (s->dp.opened[r] && s->dp.peers[r]) cudaIpcCloseMemHandle(s->dp.peers[r]);
+  dev_free(s->dp.buf); dev_free(s->dp.d_data); dev_free(s->dp.d_flags);
   delete s;
   return 0;
 }
@@ -863,9 +884,10 @@ int fbsdej_bump_u32(fbsdej_ctx* ctx, uint32_t* p) {
   return 0;
 }
 
-int fbsdej_solver_train_steps(fbsdej_solver* s, float* theta, float* m, float* v, const float* mask, int* t_dev,
-                              uint32_t* iter_dev, uint64_t seed, int B, int n_steps, float lr, float beta1,
-                              float beta2, float eps, float* loss_out) {
+namespace {
+int train_steps_impl(fbsdej_solver* s, float* theta, float* m, float* v, const float* mask, int* t_dev, uint32_t* iter_dev,
+                     uint64_t seed, int B, int B_global, uint32_t path_offset, bool dp, int n_steps, float lr, float beta1,
+                     float beta2, float eps, float* loss_out) {
   FB_REQUIRE(s && theta && m && v && t_dev && iter_dev && B > 0 && n_steps >= 0, "train_steps: bad argument");
   FB_CUDA(cudaSetDevice(s->ctx->device));
   cudaStream_t st = s->ctx->stream;
@@ -874,6 +896,7 @@ int fbsdej_solver_train_steps(fbsdej_solver* s, float* theta, float* m, float* v
   std::memset(&k, 0, sizeof(k));
   k.theta = theta; k.m = m; k.v = v; k.mask = mask; k.t = t_dev; k.it = iter_dev; k.loss = loss_out;
   k.seed = seed; k.B = B; k.lr = lr; k.b1 = beta1; k.b2 = beta2; k.eps = eps;
+  k.B_global = B_global; k.path_offset = path_offset; k.dp = dp ? 1 : 0;
   const bool same = s->graph && std::memcmp(&k, &s->key, sizeof(k)) == 0;
   if (!same) {
     if (s->graph) { cudaGraphExecDestroy(s->graph); s->graph = nullptr; }
@@ -885,8 +908,10 @@ int fbsdej_solver_train_steps(fbsdej_solver* s, float* theta, float* m, float* v
   const fbsdej_solver::Finish fin{theta, m, v, mask, lr, beta1, beta2, eps, t_dev, iter_dev, loss_out};
   auto one_step = [&]() -> int {       // simulate, forward, adjoint, [reduce + Adam + counters + loss record]: 4 launches
     s->finish = &fin;
-    const int rc = step_pass(s, theta, seed, 0, iter_dev, 0, B, B, s->out_dev);
+    s->dp_step = dp;
+    const int rc = step_pass(s, theta, seed, 0, iter_dev, path_offset, B, B_global, s->out_dev);
     s->finish = nullptr;
+    s->dp_step = false;
     return rc ? -2 : 0;
   };
   if (!same && n_steps > 0) {
@@ -913,6 +938,76 @@ int fbsdej_solver_train_steps(fbsdej_solver* s, float* theta, float* m, float* v
     s->ctx->launches += s->launches_per_step;
   }
   return 0;
+}
+}  // namespace
+
+int fbsdej_solver_train_steps(fbsdej_solver* s, float* theta, float* m, float* v, const float* mask, int* t_dev,
+                              uint32_t* iter_dev, uint64_t seed, int B, int n_steps, float lr, float beta1,
+                              float beta2, float eps, float* loss_out) {
+  return train_steps_impl(s, theta, m, v, mask, t_dev, iter_dev, seed, B, B, 0u, false, n_steps, lr, beta1, beta2, eps, loss_out);
+}
+
+// ---- data-parallel training steps without a host-driven collective --------------------------------------------------
+// Every rank (one process per GPU, or several solvers of one process in the tests) owns an exchange buffer; dp_init
+// allocates it and returns its CUDA IPC handle, the caller gathers the handles of all ranks (torch.distributed, MPI, ...)
+// and hands them to dp_connect, which maps the peers' buffers (NVLink peer access) - or takes raw device pointers for
+// ranks that live in the same process.  train_steps_dp is train_steps on this rank's shard [path_offset, path_offset + B)
+// of a global batch: the finishing kernel exchanges the [loss | gradient] vector through the peers' buffers and every
+// rank applies the same Adam update - one CUDA graph per step, no NCCL call, no host synchronisation between the ranks.
+int fbsdej_solver_dp_init(fbsdej_solver* s, int rank, int world, unsigned char* handle64) {
+  FB_REQUIRE(s && handle64 && world >= 1 && world <= 32 && rank >= 0 && rank < world, "dp_init: bad argument");
+  FB_REQUIRE(!s->dp.buf, "dp_init: already initialised");
+  FB_CUDA(cudaSetDevice(s->ctx->device));
+  const size_t bytes = xchg_bytes(s->P, world);
+  if (dev_alloc(&s->dp.buf, bytes)) return -2;
+  FB_CUDA(cudaMemset(s->dp.buf, 0, bytes));
+  s->dp.rank = rank; s->dp.world = world;
+  cudaIpcMemHandle_t h;
+  static_assert(sizeof(h) == 64, "CUDA IPC handle size");
+  FB_CUDA(cudaIpcGetMemHandle(&h, s->dp.buf));
+  std::memcpy(handle64, &h, 64);
+  return 0;
+}
+int fbsdej_solver_dp_buffer(fbsdej_solver* s, void** ptr) {
+  FB_REQUIRE(s && ptr && s->dp.buf, "dp_buffer: dp_init first");
+  *ptr = s->dp.buf;
+  return 0;
+}
+int fbsdej_solver_dp_connect(fbsdej_solver* s, const unsigned char* handles, void* const* raw_ptrs) {
+  FB_REQUIRE(s && s->dp.buf && (handles || raw_ptrs), "dp_connect: dp_init first; handles or raw pointers needed");
+  FB_REQUIRE(!s->dp.connected, "dp_connect: already connected");
+  FB_CUDA(cudaSetDevice(s->ctx->device));
+  const int W = s->dp.world;
+  s->dp.peers.assign(W, nullptr); s->dp.opened.assign(W, 0);
+  for (int r = 0; r < W; ++r) {
+    if (r == s->dp.rank) { s->dp.peers[r] = s->dp.buf; continue; }
+    if (raw_ptrs && raw_ptrs[r]) { s->dp.peers[r] = raw_ptrs[r]; continue; }
+    FB_REQUIRE(handles != nullptr, "dp_connect: no handle for rank " + std::to_string(r));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handles + (size_t)r * 64, 64);
+    void* p = nullptr;
+    FB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    s->dp.peers[r] = p; s->dp.opened[r] = 1;
+  }
+  const size_t data_bytes = sizeof(float) * 2 * (size_t)W * xchg_nstride(s->P);
+  std::vector<float*> hd(W); std::vector<uint32_t*> hf(W);
+  for (int r = 0; r < W; ++r) {
+    hd[r] = reinterpret_cast<float*>(s->dp.peers[r]);
+    hf[r] = reinterpret_cast<uint32_t*>(static_cast<unsigned char*>(s->dp.peers[r]) + data_bytes);
+  }
+  if (dev_alloc(&s->dp.d_data, (size_t)W) || dev_alloc(&s->dp.d_flags, (size_t)W)) return -2;
+  FB_CUDA(cudaMemcpy(s->dp.d_data, hd.data(), sizeof(float*) * W, cudaMemcpyHostToDevice));
+  FB_CUDA(cudaMemcpy(s->dp.d_flags, hf.data(), sizeof(uint32_t*) * W, cudaMemcpyHostToDevice));
+  s->dp.connected = true;
+  return 0;
+}
+int fbsdej_solver_train_steps_dp(fbsdej_solver* s, float* theta, float* m, float* v, const float* mask, int* t_dev,
+                                 uint32_t* iter_dev, uint64_t seed, int B, int B_global, uint32_t path_offset, int n_steps,
+                                 float lr, float beta1, float beta2, float eps, float* loss_out) {
+  FB_REQUIRE(s && s->dp.connected, "train_steps_dp: fbsdej_solver_dp_init / dp_connect first");
+  FB_REQUIRE(B_global >= B, "train_steps_dp: B_global must be >= B");
+  return train_steps_impl(s, theta, m, v, mask, t_dev, iter_dev, seed, B, B_global, path_offset, true, n_steps, lr, beta1, beta2,
+                          eps, loss_out);
 }
 
 int fbsdej_solver_profile(fbsdej_solver* s, const float* theta, uint64_t seed, int B, int reps, float* ms_host) {

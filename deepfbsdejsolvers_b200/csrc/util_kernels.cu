@@ -11,7 +11,17 @@ struct FinishArgs {
   float* theta; float* m; float* v; const float* mask;
   float lr, b1, b2, eps;
   int* t_dev; uint32_t* iter_dev; float* loss_dst; uint32_t* step_ctr; unsigned int* done_ctr;
+  XchgArgs x;                    // x.world > 1: sum the vector over the ranks before the update
 };
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ lpart, int nparts_l,
                                                               const float* __restrict__ gpart, int nparts, int P,
@@ -36,10 +46,34 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
   }
   red[ty][tx] = s;
   __syncthreads();
-  if (ty == 0 && e < n) {
-    float t = red[0][tx];
+  float t = 0.0f;
+  if (ty == 0) {
+    t = red[0][tx];
 #pragma unroll
     for (int w = 1; w < 8; ++w) t += red[w][tx];
+    if (f.x.world > 1) {
+      // Data-parallel step: this block's 32 elements go to every rank's slot of this rank (peer memory over NVLink, or the
+      // same device in the single-process tests), the block's flag on every rank is raised to the step stamp, and once the
+      // W flags of this block have arrived here the W rows are added in rank order - the same order, hence the same bits,
+      // on every rank.  Two data slots alternate: a peer can be at most one step ahead (it needs this rank's next stamp).
+      const XchgArgs& x = f.x;
+      const uint32_t stamp = *x.xctr + 1u;
+      const size_t slot = (size_t)(stamp & 1u) * x.world;
+      for (int r = 0; r < x.world; ++r) x.peer_data[r][(slot + x.rank) * x.nstride + e] = t;
+      __threadfence_system();
+      __syncwarp();
+      if (tx < x.world) st_release_sys(x.peer_flags[tx] + (size_t)x.rank * x.nblk + blockIdx.x, stamp);
+      if (tx < x.world) {
+        const uint32_t* fl = x.peer_flags[x.rank] + (size_t)tx * x.nblk + blockIdx.x;
+        while ((int32_t)(ld_acquire_sys(fl) - stamp) < 0) {}
+      }
+      __syncwarp();
+      const float* mine = x.peer_data[x.rank];
+      t = 0.0f;
+      for (int r = 0; r < x.world; ++r) t += __ldcv(mine + (slot + r) * x.nstride + e);
+    }
+  }
+  if (ty == 0 && e < n) {
     out[e] = t;
     if (f.theta && e >= kHeader) {                    // oracle/adam.py, SURVEY fact 9
       const int i = e - kHeader;
@@ -65,6 +99,7 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
         *f.iter_dev += 1u;
         if (f.loss_dst) f.loss_dst[*f.step_ctr] = __ldcg(out);
         *f.step_ctr += 1u;
+        if (f.x.world > 1) *f.x.xctr += 1u;
         *f.done_ctr = 0u;
       }
     }
@@ -152,9 +187,11 @@ int launch_reduce_partials(const float* lpart, int nparts_l, const float* gpart,
 // reduce + Adam + counters + loss record in one launch (fbsdej_solver_train_steps)
 int launch_reduce_adam(const float* lpart, int nparts_l, const float* gpart, int nparts_g, int P, float* out, float* theta,
                        float* m, float* v, const float* mask, float lr, float b1, float b2, float eps, int* t_dev,
-                       uint32_t* iter_dev, float* loss_dst, uint32_t* step_ctr, unsigned int* done_ctr, cudaStream_t st) {
+                       uint32_t* iter_dev, float* loss_dst, uint32_t* step_ctr, unsigned int* done_ctr, cudaStream_t st,
+                       const XchgArgs* x) {
   const int n = kHeader + P;
-  FinishArgs f{theta, m, v, mask, lr, b1, b2, eps, t_dev, iter_dev, loss_dst, step_ctr, done_ctr};
+  FinishArgs f{theta, m, v, mask, lr, b1, b2, eps, t_dev, iter_dev, loss_dst, step_ctr, done_ctr, XchgArgs{}};
+  if (x) f.x = *x;
   reduce_partials_kernel<<<(n + 31) / 32, 256, 0, st>>>(lpart, nparts_l, gpart, nparts_g, P, out, 1, f);
   FB_CUDA(cudaGetLastError());
   return 0;

@@ -239,6 +239,32 @@ class NativeSolver:
         check(lib.fbsdej_solver_train_steps(self.handle, _p(self.theta), _p(self.m), _p(self.v), _p(mask), _p(self.t),
                                             _p(self.iteration), seed, B, n_steps, lr, beta1, beta2, eps, _p(loss_out)))
 
+    dp_connected = False
+
+    # ---- data-parallel steps with the exchange inside the finishing kernel (include/fbsdej.h: fbsdej_solver_dp_*) ----------
+    def dp_init(self, rank: int, world: int) -> bytes:
+        h = (C.c_ubyte * 64)()
+        check(lib.fbsdej_solver_dp_init(self.handle, rank, world, h))
+        return bytes(h)
+
+    def dp_buffer(self) -> int:
+        p = C.c_void_p()
+        check(lib.fbsdej_solver_dp_buffer(self.handle, C.byref(p)))
+        return int(p.value)
+
+    def dp_connect(self, handles: Optional[bytes] = None, raw_ptrs: Optional[list] = None) -> None:
+        hb = (C.c_ubyte * len(handles)).from_buffer_copy(handles) if handles else None
+        rp = (C.c_void_p * len(raw_ptrs))(*[C.c_void_p(p) if p else None for p in raw_ptrs]) if raw_ptrs else None
+        check(lib.fbsdej_solver_dp_connect(self.handle, hb, rp))
+        self.dp_connected = True
+
+    def train_steps_dp(self, seed: int, B: int, B_global: int, path_offset: int, n_steps: int, lr: float,
+                       mask: Optional[torch.Tensor] = None, loss_out: Optional[torch.Tensor] = None, beta1: float = 0.9,
+                       beta2: float = 0.999, eps: float = 1e-7) -> None:
+        check(lib.fbsdej_solver_train_steps_dp(self.handle, _p(self.theta), _p(self.m), _p(self.v), _p(mask), _p(self.t),
+                                               _p(self.iteration), seed, B, B_global, path_offset, n_steps, lr, beta1, beta2,
+                                               eps, _p(loss_out)))
+
     def grad_step(self, seed: int, B: int, B_global: int, path_offset: int) -> torch.Tensor:
         """simulate + forward + backward of this rank's shard; returns the device vector [4 + P] to all-reduce."""
         check(lib.fbsdej_solver_grad_step(self.handle, _p(self.theta), seed, _p(self.iteration), path_offset, B, B_global,

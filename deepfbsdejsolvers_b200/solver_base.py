@@ -37,6 +37,18 @@ def shard(B: int, rank: int, world: int):
     return off, cnt
 
 
+def attach_peers(s: NativeSolver, dist, rank: int, world: int) -> None:
+    """Exchange the CUDA IPC handles of the ranks' exchange buffers (one all_gather, once per solver)."""
+    if s.dp_connected:
+        return
+    h = s.dp_init(rank, world)
+    mine = torch.tensor(list(h), dtype=torch.uint8, device=s.ctx.device)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    s.dp_connect(handles=b"".join(bytes(x.cpu().tolist()) for x in parts))
+    dist.barrier()
+
+
 class TrainLoop:
     """Steps a NativeSolver; hides single-GPU graph replay vs. data-parallel stepping."""
 
@@ -52,6 +64,13 @@ class TrainLoop:
             off, cnt = shard(B, rank, world)
             if cnt == 0:
                 raise ValueError(f"batch {B} is smaller than the number of ranks {world}")
+            if dist.get_backend() == "nccl" and os.environ.get("FBSDEJ_DP", "p2p") != "nccl":
+                # the step's [loss | gradient] exchange runs inside the finishing kernel over peer memory: one CUDA graph
+                # per step on every rank, no collective call (FBSDEJ_DP=nccl keeps the all_reduce loop below)
+                attach_peers(s, dist, rank, world)
+                s.train_steps_dp(self.seed, cnt, B, off, n, self.lr, mask=mask)
+                s.ctx.sync()
+                return
             for _ in range(n):
                 out = s.grad_step(self.seed, cnt, B, off)
                 with torch.cuda.stream(s.ctx.stream):

@@ -166,6 +166,24 @@ FBSDEJ_API int fbsdej_solver_train_steps(fbsdej_solver* s, float* theta, float* 
                               uint32_t* iter_dev, uint64_t seed, int B, int n_steps, float lr, float beta1,
                               float beta2, float eps, float* loss_out);
 
+/* Data-parallel training without a host-driven collective (replaces "grad_step -> NCCL all_reduce -> adam_step" of the
+ * reference-side loop; the reference itself is single-device).  One rank per GPU (one process each), or several
+ * solvers of one process.
+ *   dp_init     allocates this rank's exchange buffer and returns its 64-byte CUDA IPC handle;
+ *   dp_buffer   the same buffer as a raw device pointer (for ranks that share a process);
+ *   dp_connect  handles: world x 64 bytes gathered from all ranks (may be NULL if raw_ptrs covers every peer);
+ *               raw_ptrs: world entries, non-NULL for peers of this process (may be NULL);
+ *   train_steps_dp  n_steps training steps on the shard [path_offset, path_offset + B) of a global batch of B_global paths:
+ *               the kernel that finishes a step writes its [loss | gradient] vector into every peer's buffer (NVLink peer
+ *               stores), waits for the peers' vectors, adds them in rank order and applies the same Adam update on every
+ *               rank.  Same CUDA graph replay as train_steps; all ranks must call it with the same n_steps. */
+FBSDEJ_API int fbsdej_solver_dp_init(fbsdej_solver* s, int rank, int world, unsigned char* handle64);
+FBSDEJ_API int fbsdej_solver_dp_buffer(fbsdej_solver* s, void** ptr);
+FBSDEJ_API int fbsdej_solver_dp_connect(fbsdej_solver* s, const unsigned char* handles, void* const* raw_ptrs);
+FBSDEJ_API int fbsdej_solver_train_steps_dp(fbsdej_solver* s, float* theta, float* m, float* v, const float* mask, int* t_dev,
+                                 uint32_t* iter_dev, uint64_t seed, int B, int B_global, uint32_t path_offset, int n_steps,
+                                 float lr, float beta1, float beta2, float eps, float* loss_out);
+
 /* Per-kernel device times of one training iteration, measured with CUDA events on the ctx stream around each launch
  * (bench.py's roofline numbers).  Runs `reps` iterations WITHOUT the Adam update (theta unchanged) and writes the mean
  * milliseconds: ms[0] simulate paths, ms[1] simulate + compact compensator samples, ms[2] forward, ms[3] backward,

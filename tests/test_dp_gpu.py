@@ -61,3 +61,66 @@ def test_simulated_increment_statistics(ctx):
     assert abs(J.var() - lam * dt * sj ** 2) < 0.02 * lam * dt * sj ** 2        # Var = E[dN] sigJ^2 (muJ = 0)
     s.simulate(7, 1, B)
     assert not np.array_equal(s.read_device(pa, 1000), dW[:1000].astype(np.float32))   # new iteration, new draws
+
+
+@pytest.mark.parametrize("scheme,M,d", [("SumLocalReg", 0, 10), ("Global", 64, 1)])
+def test_exchange_inside_the_finishing_kernel(ctx, scheme, M, d):
+    """Two ranks of one process on one device (two streams): fbsdej_solver_train_steps_dp exchanges the [loss | gradient]
+    vector through the peers' buffers inside the finishing kernel.  Both ranks must end with bit-identical parameters, equal to
+    single-rank training on the whole batch up to the fp32 summation order of the gradient."""
+    import threading
+    import torch
+    from deepfbsdejsolvers_b200 import Context
+    B, seed, steps, lr, world = 1000, 99, 6, 1e-3, 2
+    p = dict(H.MERTON, N=10)
+    layout = H.pricing_layout("merton", scheme, d)
+    theta = H.random_theta(layout, 5)
+    kw = dict(d=d, M=M, limit=30 if d == 1 else 100, tensor_cores=True, price_table=d > 1)
+    full = H.native_pricing(ctx, "merton", p, scheme, layout, **kw)
+    full.set_theta(theta)
+    loss_full = ctx.zeros(steps)
+    full.train_steps(seed, B, steps, lr, loss_out=loss_full)
+    ctx.sync()
+    ranks, losses = [], []
+    for r in range(world):
+        c = Context(ctx.index)
+        s = H.native_pricing(c, "merton", p, scheme, layout, **kw)
+        s.set_theta(theta)
+        off, cnt = shard(B, r, world)
+        s.grad_step(seed, cnt, B, off)                   # sizes every buffer: no allocation while a peer's kernel waits
+        c.sync()
+        ranks.append((c, s, off, cnt))
+        losses.append(c.zeros(steps))
+    bufs = []
+    for r, (c, s, off, cnt) in enumerate(ranks):
+        s.dp_init(r, world)
+        bufs.append(s.dp_buffer())
+    for c, s, off, cnt in ranks:
+        s.dp_connect(raw_ptrs=bufs)
+    errs = []
+
+    def run(r):
+        c, s, off, cnt = ranks[r]
+        try:
+            s.train_steps_dp(seed, cnt, B, off, steps, lr, loss_out=losses[r])
+            c.sync()
+        except Exception as e:   # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=120)
+    assert not errs and not any(t.is_alive() for t in th), errs
+    t0 = ranks[0][0].to_host(ranks[0][1].theta).numpy()
+    t1 = ranks[1][0].to_host(ranks[1][1].theta).numpy()
+    assert np.array_equal(t0, t1)
+    l0, l1 = ranks[0][0].to_host(losses[0]).numpy(), ranks[1][0].to_host(losses[1]).numpy()
+    assert np.array_equal(l0, l1)
+    lf, tf = ctx.to_host(loss_full).numpy(), ctx.to_host(full.theta).numpy()
+    assert np.abs(l0 - lf).max() <= 2e-5 * np.abs(lf).max(), (l0, lf)
+    # (the output bias of the jump network has an exactly-zero gradient in exact arithmetic: Adam turns its fp32 summation
+    # noise into +-lr steps, so that one entry follows the summation order)
+    far = np.abs(t0 - tf) > 2e-4 * np.abs(tf - theta).max() + 1e-7
+    assert far.sum() <= (0 if M == 0 else 1), (far.sum(), np.abs(t0 - tf).max())
