@@ -178,7 +178,7 @@ def run_native(a):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from deepfbsdejsolvers_b200 import Context, set_seed
     from deepfbsdejsolvers_b200 import coupledPricing as cp
-    from deepfbsdejsolvers_b200.solver_base import shard
+    from deepfbsdejsolvers_b200.solver_base import shard, attach_peers
     import deepfbsdejsolvers_b200._lib as L
 
     B = a.paths or (2 ** 16 if world == 1 else 2 ** 20)
@@ -206,9 +206,21 @@ def run_native(a):
             dist.barrier()
         ctx.sync()
 
+    # N > 1: the step's [loss | gradient] exchange runs inside the finishing kernel over NVLink peer memory
+    # (fbsdej_solver_train_steps_dp: one CUDA graph per step, no collective call); FBSDEJ_DP=nccl selects the
+    # grad_step -> NCCL all_reduce -> adam_step loop instead
+    p2p = world > 1 and os.environ.get("FBSDEJ_DP", "p2p") != "nccl"
+    if p2p:
+        attach_peers(s, dist, rank, world)
+    if world > 1:
+        cfg["dp_exchange"] = ("inside the finishing kernel over NVLink peer memory (CUDA IPC buffers), no collective call" if p2p
+                              else "NCCL all_reduce of [loss | gradient] per step")
+
     def step():
         if world == 1:
             s.train_steps(0, B, 1, LR)
+        elif p2p:
+            s.train_steps_dp(0, Bl, B, off, 1, LR)
         else:
             out = s.grad_step(0, Bl, B, off)
             with torch.cuda.stream(ctx.stream):
@@ -379,6 +391,16 @@ def run_native(a):
                "sample": "%d iterations of a %d-path sample of the batch, all %d time steps, fwd+bwd+Adam (torch eager restatement "
                          "of the reference solver, not TensorFlow)" % (n, cpu_paths, N), "ms_per_iteration": dt * 1e3}
 
+    in_sync = None
+    if world > 1:        # every rank applied the same updates: the parameter vectors must agree bit for bit
+        with torch.cuda.stream(ctx.stream):
+            chk = torch.stack([s.theta.double().sum(), s.theta.double().abs().sum()])
+            lo, hi = chk.clone(), chk.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        ctx.sync()
+        in_sync = bool(torch.equal(lo, hi))
+        cfg["ranks_in_sync"] = in_sync
     if rank == 0:
         line = {"metric": "path-steps/s", "value": value, "unit": "path-steps/s", "n_gpus": world, "steps": a.steps,
                 "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "iters_per_s": 1e3 / ms_step, "higher_is_better": True,
