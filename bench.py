@@ -211,7 +211,7 @@ def run_native(a):
     # grad_step -> NCCL all_reduce -> adam_step loop instead
     p2p = world > 1 and os.environ.get("FBSDEJ_DP", "p2p") != "nccl"
     if p2p:
-        attach_peers(s, dist, rank, world)
+        p2p = attach_peers(s, dist, rank, world)
     if world > 1:
         cfg["dp_exchange"] = ("inside the finishing kernel over NVLink peer memory (CUDA IPC buffers), no collective call" if p2p
                               else "NCCL all_reduce of [loss | gradient] per step")

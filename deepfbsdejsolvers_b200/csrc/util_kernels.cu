@@ -17,6 +17,11 @@ struct FinishArgs {
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -63,13 +68,19 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
       __threadfence_system();
       __syncwarp();
       if (tx < x.world) st_release_sys(x.peer_flags[tx] + (size_t)x.rank * x.nblk + blockIdx.x, stamp);
+      bool late = false;
       if (tx < x.world) {
+        // a peer that never arrives (a rank died, or the ranks disagree on the number of steps) must not hang the device:
+        // after 30 s the step is poisoned with NaN instead
         const uint32_t* fl = x.peer_flags[x.rank] + (size_t)tx * x.nblk + blockIdx.x;
-        while ((int32_t)(ld_acquire_sys(fl) - stamp) < 0) {}
+        const unsigned long long t0 = globaltimer_ns();
+        while ((int32_t)(ld_acquire_sys(fl) - stamp) < 0) {
+          if (globaltimer_ns() - t0 > 30000000000ull) { late = true; break; }
+        }
       }
-      __syncwarp();
+      late = __any_sync(0xffffffffu, late);
       const float* mine = x.peer_data[x.rank];
-      t = 0.0f;
+      t = late ? __int_as_float(0x7fc00000) : 0.0f;
       for (int r = 0; r < x.world; ++r) t += __ldcv(mine + (slot + r) * x.nstride + e);
     }
   }

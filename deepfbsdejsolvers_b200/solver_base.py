@@ -37,16 +37,33 @@ def shard(B: int, rank: int, world: int):
     return off, cnt
 
 
-def attach_peers(s: NativeSolver, dist, rank: int, world: int) -> None:
-    """Exchange the CUDA IPC handles of the ranks' exchange buffers (one all_gather, once per solver)."""
+def attach_peers(s: NativeSolver, dist, rank: int, world: int) -> bool:
+    """Exchange the CUDA IPC handles of the ranks' exchange buffers (one all_gather, once per solver).  Returns False - on
+    every rank - if any rank could not map its peers (no peer access between the devices): the caller then keeps the NCCL
+    all-reduce loop."""
     if s.dp_connected:
-        return
-    h = s.dp_init(rank, world)
+        return True
+    if getattr(s, "dp_unavailable", False):
+        return False
+    ok = 1
+    try:
+        h = s.dp_init(rank, world)
+    except Exception:   # noqa: BLE001
+        h, ok = bytes(64), 0
     mine = torch.tensor(list(h), dtype=torch.uint8, device=s.ctx.device)
     parts = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(parts, mine)
-    s.dp_connect(handles=b"".join(bytes(x.cpu().tolist()) for x in parts))
-    dist.barrier()
+    if ok:
+        try:
+            s.dp_connect(handles=b"".join(bytes(x.cpu().tolist()) for x in parts))
+        except Exception:   # noqa: BLE001
+            ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device=s.ctx.device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        s.dp_connected, s.dp_unavailable = False, True
+        return False
+    return True
 
 
 class TrainLoop:
@@ -64,10 +81,10 @@ class TrainLoop:
             off, cnt = shard(B, rank, world)
             if cnt == 0:
                 raise ValueError(f"batch {B} is smaller than the number of ranks {world}")
-            if dist.get_backend() == "nccl" and os.environ.get("FBSDEJ_DP", "p2p") != "nccl":
+            if (dist.get_backend() == "nccl" and os.environ.get("FBSDEJ_DP", "p2p") != "nccl"
+                    and attach_peers(s, dist, rank, world)):
                 # the step's [loss | gradient] exchange runs inside the finishing kernel over peer memory: one CUDA graph
                 # per step on every rank, no collective call (FBSDEJ_DP=nccl keeps the all_reduce loop below)
-                attach_peers(s, dist, rank, world)
                 s.train_steps_dp(self.seed, cnt, B, off, n, self.lr, mask=mask)
                 s.ctx.sync()
                 return
