@@ -7,7 +7,11 @@
 //                     shared-memory tiles, weight gradients accumulated in registers (tile_mlp.cuh).
 //
 // Row mapping: a CTA owns kThreads rows = (kThreads / G) paths x G rows; the G threads of a path share its
-// state and split the compensator samples (G = 1: one thread per path).
+// state and split the compensator samples (G = 1: one thread per path).  With one path per CTA (G == kThreads) the
+// (U, Z) network has a single row and is evaluated with thread j = hidden unit j (tile_mlp.cuh: row_fwd / row_delta).
+//
+// Template flag JTC (mma_mode = 1): the jump evaluations - the path's own jump and the compensator samples - run on
+// tcgen05 as rows of 128-row tiles (jump_tc.cuh); everything else in these kernels is unchanged.
 //
 // Reference loss graphs: coupledPricing/SolversJumpDiff.py:22-44 (Global), :86-115/:162-190 (MultiStep1/2),
 // :236-269/:315-347 (SumLocal1/2), :391-415 (SumLocalReg), :461-481 (MultiStepReg); SolversPureJump.py same.
@@ -30,8 +34,6 @@ size_t reg_tc_backward_smem();
 size_t reg_tc_forward_smem();
 int reg_tc_forward_occupancy(int B, int sms);
 
-// JTC: the jump network (two-network schemes, one output, at most 14 inputs, tanh) runs on tcgen05 (jump_tc.cuh): the
-// path's own jump and its compensator samples are the rows of 128-row tiles.
 template <class Model, int HP, bool JUMP, bool JTC>
 __global__ void __launch_bounds__(kThreads, JTC ? 4 : 0) pricing_forward(const PricingArgs a) {
   constexpr int D = Model::D;
