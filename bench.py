@@ -12,6 +12,7 @@ Prints ONE JSON line on rank 0.
 from __future__ import annotations
 
 import argparse
+import math
 import json
 import os
 import subprocess
@@ -260,9 +261,17 @@ def run_native(a):
     e2e, e2e_rng = None, None
     if not a.no_e2e:
         nfl = N * D * Bl
-        one = [torch.randn(nfl, dtype=torch.float32).mul_(0.1).pin_memory() for _ in range(2)]   # (dW, J) of a step, pinned
-        host = [one, one]                      # synthetic data: the same host block is uploaded for every step
-        dev = [[ctx.empty(nfl), ctx.empty(nfl)] for _ in range(2)]
+        # one step's increments in pinned host memory (synthetic; the same block is uploaded for every step): Brownian planes
+        # dense, compound-Poisson jump planes as their non-zero entries - exactly 0 wherever no jump fell into the step
+        dt = MERTON["T"] / N
+        gen = torch.Generator().manual_seed(1234 + rank)
+        dW_h = torch.randn(nfl, dtype=torch.float32, generator=gen).mul_(dt ** 0.5).pin_memory()
+        hit = torch.rand(nfl, generator=gen) < (1.0 - math.exp(-MERTON["lam"] * dt))
+        jidx_h = torch.nonzero(hit).flatten().to(torch.int32).pin_memory()      # < 2^31 entries per rank
+        nnz = int(jidx_h.numel())
+        jval_h = (torch.randn(nnz, dtype=torch.float32, generator=gen) * MERTON["sigmaJ"] + MERTON["muJ"]).pin_memory()
+        del hit
+        dev = [[ctx.empty(nfl), ctx.empty(max(nnz, 1), dtype=torch.int32), ctx.empty(max(nnz, 1))] for _ in range(2)]
         loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
         jmc = ctx.zeros(N * D * max(M, 1)) if M > 0 else None
         copy_stream = torch.cuda.Stream(ctx.device)
@@ -270,20 +279,22 @@ def run_native(a):
         free = [torch.cuda.Event(), torch.cuda.Event()]      # compute on buffer b finished
         k = [0]
 
-        def upload(b, src):
+        def upload(b):
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(free[b])
-                dev[b][0].copy_(host[src][0], non_blocking=True)
-                dev[b][1].copy_(host[src][1], non_blocking=True)
+                dev[b][0].copy_(dW_h, non_blocking=True)
+                dev[b][1][:nnz].copy_(jidx_h, non_blocking=True)
+                dev[b][2][:nnz].copy_(jval_h, non_blocking=True)
                 up[b].record(copy_stream)
 
         def e2e_step():
             b = k[0] & 1
             k[0] += 1
-            upload(b ^ 1, k[0] & 1)                          # next step's increments -> the other buffer
+            upload(b ^ 1)                                    # next step's increments -> the other buffer
             ctx.stream.wait_event(up[b])
-            L.check(L.lib.fbsdej_solver_set_noise(s.handle, Bl, dev[b][0].data_ptr(), dev[b][1].data_ptr(),
-                                                  jmc.data_ptr() if jmc is not None else None))
+            L.check(L.lib.fbsdej_solver_set_noise_sparse_jumps(s.handle, Bl, dev[b][0].data_ptr(), dev[b][1].data_ptr(),
+                                                               dev[b][2].data_ptr(), nnz,
+                                                               jmc.data_ptr() if jmc is not None else None))
             L.check(L.lib.fbsdej_solver_grad(s.handle, s.theta.data_ptr(), Bl, B, s.out.data_ptr()))
             free[b].record(ctx.stream)
             with torch.cuda.stream(ctx.stream):
@@ -296,17 +307,18 @@ def run_native(a):
 
         for b in range(2):
             free[b].record(ctx.stream)
-        upload(0, 0)
+        upload(0)
         for _ in range(2):
             e2e_step()
         ms_e = timed(e2e_step, a.steps) / a.steps
         copy_stream.synchronize()
         e2e = {"value": B * N / (ms_e * 1e-3), "unit": "path-steps/s", "ms_per_step": ms_e,
-               "h2d_bytes_per_step": 2 * nfl * 4 * world, "d2h_bytes_per_step": 4 * world,
-               "what": "host (pinned) Brownian + jump increments of the step -> H2D (double-buffered on a copy stream) -> "
-                       "fbsdej_solver_set_noise -> fbsdej_solver_grad -> fbsdej_adam_step -> loss D2H + sync every step; "
-                       "bounded by the PCIe upload of 8*d bytes per path-step"}
-        del host, dev
+               "h2d_bytes_per_step": (nfl * 4 + nnz * 8) * world, "d2h_bytes_per_step": 4 * world,
+               "what": "host (pinned) increments of the step - Brownian planes dense, compound-Poisson jump planes as (index, "
+                       "value) of their non-zero entries - -> H2D (double-buffered on a copy stream) -> "
+                       "fbsdej_solver_set_noise_sparse_jumps -> fbsdej_solver_grad -> fbsdej_adam_step -> loss D2H + sync "
+                       "every step; bounded by the PCIe upload of 4*d bytes per path-step"}
+        del dev
 
         # the production call: Solver.train_steps draws the increments on the device (Philox), so its per-step host input is
         # (seed, step count, learning rate) and its per-step host output the loss

@@ -70,6 +70,7 @@ def _load():
         "fbsdej_solver_set_vg_table_host": (i32, [vp, C.POINTER(C.c_double), i32, C.c_double, C.c_double]),
         "fbsdej_solver_simulate": (i32, [vp, u64, u32, u32, i32]),
         "fbsdej_solver_set_noise": (i32, [vp, i32, vp, vp, vp]),
+        "fbsdej_solver_set_noise_sparse_jumps": (i32, [vp, i32, vp, vp, vp, i32, vp]),
         "fbsdej_solver_get_noise": (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
         "fbsdej_solver_loss": (i32, [vp, vp, i32, i32, vp, vp, vp, vp]),
         "fbsdej_solver_mfg_states": (i32, [vp, i32, vp]),

@@ -813,6 +813,26 @@ int fbsdej_solver_set_noise(fbsdej_solver* s, int B, const float* a, const float
   return 0;
 }
 
+int fbsdej_solver_set_noise_sparse_jumps(fbsdej_solver* s, int B, const float* dW, const uint32_t* jidx, const float* jval, int nnz,
+                                         const float* jmc) {
+  FB_REQUIRE(s && B > 0 && nnz >= 0 && (nnz == 0 || (jidx && jval)), "set_noise_sparse_jumps: bad argument");
+  FB_REQUIRE(s->model != FBSDEJ_MODEL_MFG, "set_noise_sparse_jumps: pricing models only");
+  FB_REQUIRE((s->model == FBSDEJ_MODEL_MERTON) == (dW != nullptr), "set_noise_sparse_jumps: dW is required for Merton and must be NULL for VG");
+  FB_REQUIRE(!s->has_jump || jmc, "set_noise_sparse_jumps: JMC is required for schemes with a compensator");
+  FB_CUDA(cudaSetDevice(s->ctx->device));
+  if (ensure_capacity(s, B)) return -2;
+  // the dense jump planes are rebuilt in the solver's own increment buffer (the one fbsdej_solver_simulate fills)
+  if (launch_scatter(s->nB, (size_t)s->N * s->D * B, jidx, jval, nnz, s->ctx->stream)) return -2;
+  s->ctx->launches += 1;
+  s->curA = dW; s->curB = s->nB; s->curC = nullptr;
+  if (s->has_jump) {
+    if (launch_compact_jmc(jmc, s->jmc, s->jmc_nnz, s->jmc_n0, s->N, s->D, s->M, 1, s->ctx->stream)) return -2;
+    s->ctx->launches += 1;
+  }
+  s->noiseB = B;
+  return 0;
+}
+
 int fbsdej_solver_get_noise(fbsdej_solver* s, const float** a, const float** b, const float** c, const int** jmc_nnz,
                             const int** jmc_n0) {
   FB_REQUIRE(s, "get_noise: solver is NULL");

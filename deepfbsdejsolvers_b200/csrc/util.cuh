@@ -32,6 +32,7 @@ int launch_bump_u32(uint32_t* p, cudaStream_t st);
 int launch_copy_loss(const float* out, float* dst, uint32_t* ctr, cudaStream_t st);
 int launch_net_forward(const float* theta_net, int nin, int H, int L, int nout, int act, const float* x, int rows,
                        float* y, cudaStream_t st);
+int launch_scatter(float* dst, size_t n, const uint32_t* idx, const float* val, int nnz, cudaStream_t st);
 int launch_transpose(const float* src, float* dst, int N, int B, int d, bool to_ndb, cudaStream_t st);
 
 }  // namespace fbsdej

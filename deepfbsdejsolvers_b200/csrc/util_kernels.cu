@@ -187,6 +187,25 @@ __global__ void transpose_kernel(const float* __restrict__ src, float* __restric
   }
 }
 
+__global__ void scatter_kernel(float* __restrict__ dst, const uint32_t* __restrict__ idx, const float* __restrict__ val, int nnz,
+                               size_t n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += gridDim.x * blockDim.x) {
+    const uint32_t k = idx[i];
+    if (k < n) dst[k] = val[i];
+  }
+}
+// dst[0 .. n) = 0, then dst[idx[i]] = val[i]
+int launch_scatter(float* dst, size_t n, const uint32_t* idx, const float* val, int nnz, cudaStream_t st) {
+  FB_CUDA(cudaMemsetAsync(dst, 0, n * sizeof(float), st));
+  if (nnz > 0) {
+    int grid = (nnz + 255) / 256;
+    if (grid > 148 * 8) grid = 148 * 8;
+    scatter_kernel<<<grid, 256, 0, st>>>(dst, idx, val, nnz, n);
+  }
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int launch_reduce_partials(const float* lpart, int nparts_l, const float* gpart, int nparts_g, int P, float* out,
                            bool with_grad, cudaStream_t st) {
   const int n = kHeader + (with_grad ? P : 0);

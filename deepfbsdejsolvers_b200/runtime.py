@@ -200,6 +200,15 @@ class NativeSolver:
         self._keep = ts
         check(lib.fbsdej_solver_set_noise(self.handle, B, _p(ts[0]), _p(ts[1]), _p(ts[2])))
 
+    def set_noise_sparse_jumps(self, B: int, dW, J, jmc=None) -> None:
+        """set_noise with the jump planes J [N,d,B] shipped as their non-zero entries (index, value)."""
+        Jf = np.ascontiguousarray(np.asarray(J, dtype=np.float32)).reshape(-1)
+        idx = np.flatnonzero(Jf).astype(np.uint32)
+        ts = [None if dW is None else self.ctx.to_device(dW), self.ctx.to_device(idx.view(np.int32), dtype=torch.int32),
+              self.ctx.to_device(Jf[idx]), None if jmc is None else self.ctx.to_device(jmc)]
+        self._keep = ts
+        check(lib.fbsdej_solver_set_noise_sparse_jumps(self.handle, B, _p(ts[0]), _p(ts[1]), _p(ts[2]), int(idx.size), _p(ts[3])))
+
     # ---- evaluation ------------------------------------------------------------------------------------------
     def loss(self, B: int, B_global: Optional[int] = None, traj: bool = False):
         Bg = B if B_global is None else B_global

@@ -128,6 +128,12 @@ FBSDEJ_API int fbsdej_solver_set_vg_table_host(fbsdej_solver* s, const double* c
  *   pricing: dW [N][d][B] (Merton), J [N][d][B], JMC [N][d][M];  MFG: a = dW0, b = dW, c = dN, all [N][B]. */
 FBSDEJ_API int fbsdej_solver_simulate(fbsdej_solver* s, uint64_t seed, uint32_t iteration, uint32_t path_offset, int B);
 FBSDEJ_API int fbsdej_solver_set_noise(fbsdej_solver* s, int B, const float* a, const float* b, const float* c);
+/* The same for the pricing models with the jump planes given as their non-zero entries (a compound-Poisson increment is
+ * exactly 0 wherever no jump fell into the step - 97 % of the entries at lam dt = 0.03): J[jidx[i]] = jval[i], jidx = flat
+ * index into [N][d][B], everything else 0.  Lossless; halves the host-to-device bytes of an injected step.  dW / jmc as in
+ * set_noise (device pointers). */
+FBSDEJ_API int fbsdej_solver_set_noise_sparse_jumps(fbsdej_solver* s, int B, const float* dW, const uint32_t* jidx, const float* jval,
+                                         int nnz, const float* jmc);
 /* Device pointers of the solver's current noise tensors (for dumps / statistics tests). */
 FBSDEJ_API int fbsdej_solver_get_noise(fbsdej_solver* s, const float** a, const float** b, const float** c, const int** jmc_nnz,
                             const int** jmc_n0);
