@@ -191,3 +191,26 @@ def test_adam_matches_keras_form(ctx):
         opt.step(th, torch.tensor(g))
         s.adam_step(3e-4, grad=ctx.to_device(g))
     _close(s.get_theta(), th.numpy(), rtol=1e-6, atol=1e-8)
+
+
+def test_sparse_jump_injection_equals_dense(ctx):
+    """fbsdej_solver_set_noise_sparse_jumps (jump planes as their non-zero entries) reproduces set_noise bit for bit."""
+    d, B, scheme = 10, 500, "SumLocalReg"
+    p = dict(H.MERTON, N=8)
+    om = MertonOracle(aLin=H.ALIN, limit=100, d=d, **p)
+    layout = H.pricing_layout("merton", scheme, d)
+    theta = H.random_theta(layout, 3)
+    noise = H.merton_noise(om, B, 0, seed=4, with_jmc=False)
+    dW, J = H.to_planes(noise["dW"]), H.to_planes(noise["J"])
+    assert 0 < np.count_nonzero(J) < 0.5 * J.size
+    outs = []
+    for sparse in (False, True):
+        for tc in (False, True):
+            s = H.native_pricing(ctx, "merton", p, scheme, layout, d=d, limit=100, tensor_cores=tc)
+            s.set_theta(theta)
+            if sparse:
+                s.set_noise_sparse_jumps(B, dW, J)
+            else:
+                s.set_noise(B, dW, J, None)
+            outs.append(s.grad(B).copy())
+    assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[1], outs[3])
