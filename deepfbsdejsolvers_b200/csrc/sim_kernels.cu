@@ -175,17 +175,19 @@ __global__ void __launch_bounds__(256) sim_mfg_kernel(const SimMFGArgs a) {
 
 // Stable compaction of the compensator samples of each step: non-zero samples first, count of all-zero ones.
 // (Merton: ~94 % of the 5000 samples are exactly 0 at lam*dt = 0.06; their mean contribution is n0*G(i,X,0)/M.)
-__global__ void __launch_bounds__(256) compact_jmc_kernel(const float* __restrict__ src, float* __restrict__ dst,
-                                                          int* __restrict__ nnz, int* __restrict__ n0, int D, int M,
-                                                          int dedup) {
-  __shared__ int swarp[8];
+constexpr int kCompactThreads = 1024;   // one block per step: fewer (barrier-separated) rounds over the M samples
+__global__ void __launch_bounds__(kCompactThreads) compact_jmc_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                                     int* __restrict__ nnz, int* __restrict__ n0, int D, int M,
+                                                                     int dedup) {
+  constexpr int NW = kCompactThreads / 32;
+  __shared__ int swarp[NW];
   __shared__ int sbase;
   const int i = blockIdx.x;
   const float* s = src + (size_t)i * D * M;
   float* d = dst + (size_t)i * D * M;
   if (threadIdx.x == 0) sbase = 0;
   __syncthreads();
-  for (int m0 = 0; m0 < M; m0 += 256) {
+  for (int m0 = 0; m0 < M; m0 += kCompactThreads) {
     const int m = m0 + threadIdx.x;
     bool nz = false;
     if (m < M) {
@@ -201,7 +203,7 @@ __global__ void __launch_bounds__(256) compact_jmc_kernel(const float* __restric
     off += __popc(bal & ((1u << lane) - 1u));
     if (nz) for (int k = 0; k < D; ++k) d[(size_t)k * M + off] = s[(size_t)k * M + m];
     __syncthreads();
-    if (threadIdx.x == 0) { int tot = 0; for (int w = 0; w < 8; ++w) tot += swarp[w]; sbase += tot; }
+    if (threadIdx.x == 0) { int tot = 0; for (int w = 0; w < NW; ++w) tot += swarp[w]; sbase += tot; }
     __syncthreads();
   }
   if (threadIdx.x == 0) { nnz[i] = sbase; n0[i] = M - sbase; }
@@ -231,7 +233,7 @@ int launch_sim_mfg(const SimMFGArgs& a, cudaStream_t st) {
   return 0;
 }
 int launch_compact_jmc(const float* src, float* dst, int* nnz, int* n0, int N, int D, int M, int dedup, cudaStream_t st) {
-  compact_jmc_kernel<<<N, 256, 0, st>>>(src, dst, nnz, n0, D, M, dedup);
+  compact_jmc_kernel<<<N, kCompactThreads, 0, st>>>(src, dst, nnz, n0, D, M, dedup);
   FB_CUDA(cudaGetLastError());
   return 0;
 }
