@@ -216,7 +216,7 @@ int ensure_capacity(fbsdej_solver* s, int B) {
     if (s->model == FBSDEJ_MODEL_MERTON && dev_alloc(&s->nA, N * D * b)) return -2;
     if (dev_alloc(&s->nB, N * D * b)) return -2;
     if (s->desc.mma_mode == 1 && !s->has_jump) {
-      const size_t nt = (b + kThreads - 1) / kThreads;
+      const size_t nt = (size_t)make_tile_map(B, 4 * s->ctx->sms).ntiles;
       if (dev_alloc(&s->rec, nt * N * (2 * D + 3) * kThreads) || dev_alloc(&s->recN, nt * (D + 1) * kThreads)) return -2;
     } else {
       if (!s->has_jump && dev_alloc(&s->trajE, N * D * b)) return -2;
@@ -345,6 +345,11 @@ int run_pass(fbsdej_solver* s, const float* theta, int B, int B_global, float* o
     grid_f = a.C * std::min(ntiles, std::max(1, s->ctx->sms * pricing_blocks_per_sm(s->model, s->D, s->HP, a, false) / a.C));
     if (with_grad)
       grid_b = a.C * std::min(ntiles, std::max(1, s->ctx->sms * pricing_blocks_per_sm(s->model, s->D, s->HP, a, true) / a.C));
+    if (a.mma_mode == 1 && !a.has_jump) {   // tcgen05 compensator-free kernels: four CTAs per SM, tiles of 4 or 3 warps
+      a.tmap = make_tile_map(B, 4 * s->ctx->sms);
+      grid_f = std::min(a.tmap.ntiles, 4 * s->ctx->sms);
+      if (with_grad) grid_b = grid_f;
+    }
     if (ensure_grid(s, std::max(grid_f, grid_b))) return -2;
     a.lpart = s->lpart; a.gpart = s->gpart; a.trajY = trajY; a.trajZ = trajZ;
     if (s->rng) {
@@ -857,7 +862,7 @@ int fbsdej_solver_loss(fbsdej_solver* s, const float* theta, int B, int B_global
         FB_CUDA(cudaMemcpyAsync(trajX + (size_t)i * 2 * B, s->trajX + ((size_t)i * 5 + 3) * B, sizeof(float) * 2 * B,
                                 cudaMemcpyDeviceToDevice, s->ctx->stream));
     } else if (s->desc.mma_mode == 1 && !s->has_jump) {
-      if (launch_untile_traj(s->D, s->rec, s->recN, B, s->N, trajX, s->ctx->stream)) return -1;
+      if (launch_untile_traj(s->D, s->rec, s->recN, make_tile_map(B, 4 * s->ctx->sms), B, s->N, trajX, s->ctx->stream)) return -1;
     } else {
       FB_CUDA(cudaMemcpyAsync(trajX, s->trajX, sizeof(float) * (size_t)(s->N + 1) * s->D * B, cudaMemcpyDeviceToDevice,
                               s->ctx->stream));

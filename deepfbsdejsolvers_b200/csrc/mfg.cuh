@@ -34,6 +34,6 @@ size_t mfg_smem_bytes(int HP, const MFGArgs& a, bool backward);
 int pricing_blocks_per_sm(int model, int D, int HP, const PricingArgs& a, bool backward);
 int mfg_blocks_per_sm(int HP, const MFGArgs& a, bool backward);
 int launch_price(int model, int D, const PricingArgs& a, int iStep, const float* X, int n, float* out, cudaStream_t st);
-int launch_untile_traj(int D, const float* rec, const float* recN, int B, int N, float* out, cudaStream_t st);
+int launch_untile_traj(int D, const float* rec, const float* recN, TileMap map, int B, int N, float* out, cudaStream_t st);
 
 }  // namespace fbsdej

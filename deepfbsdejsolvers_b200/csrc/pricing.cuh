@@ -8,6 +8,27 @@ namespace fbsdej {
 // loss-graph families (reference classes: SolversJumpDiff.py / SolversPureJump.py)
 enum { SCH_GLOBAL = 0, SCH_MULTISTEP = 1, SCH_SUMLOCAL = 2 };
 
+// Tiles of the tcgen05 compensator-free kernels (reg_tc_kernels.cu).  Tile t holds the paths [tile_base(t), + tile_height(t)):
+// 128 rows (four warps) when (t % period) < tall, else 96 rows (three warps); period = the grid size, so a CTA's tiles all
+// have its own height.  The sweeps are bound by instruction issue, and 2^16 paths are 13.8 warps per SM: with 128-row tiles
+// only, 68 SMs carry 16 warps while 80 carry 12; the mixed heights give every SM 14 (make_tile_map, api.cu).
+// Uniform 128-row tiles: period = tall = 1.
+struct TileMap { int ntiles, period, tall; };
+__host__ __device__ inline int tile_height(const TileMap& m, int t) { return (t % m.period) < m.tall ? 128 : 96; }
+__host__ __device__ inline int tile_base(const TileMap& m, int t) {
+  const int w = t / m.period, c = t % m.period;
+  return w * (m.tall * 128 + (m.period - m.tall) * 96) + (c < m.tall ? c * 128 : m.tall * 128 + (c - m.tall) * 96);
+}
+inline TileMap make_tile_map(int B, int slots) {
+  const long long W = (B + 31) / 32;                          // warps of paths
+  const long long waves = (W + 4LL * slots - 1) / (4LL * slots);
+  if (W >= 3LL * slots * waves) {                             // every CTA slot gets a tile of 3 or 4 warps in every wave
+    const int tall = (int)((W - 3LL * slots * waves + waves - 1) / waves);
+    return TileMap{(int)(waves * slots), slots, tall};
+  }
+  return TileMap{(B + 127) / 128, 1, 1};
+}
+
 struct PricingArgs {
   int B, N, G, M;             // local paths, time steps, threads per path, compensator sample count (mean denominator)
   int C;                      // CTAs per path: a thread-block cluster splits the compensator samples (small batches; else 1)
@@ -66,6 +87,7 @@ struct PricingArgs {
   //   recN [ntiles][D+1][128]       planes X_N[D], fin
   float* rec;
   float* recN;
+  TileMap tmap;
   float* trajY;               // optional [N+1][B]
   float* trajZ;               // optional [N][D][B]
   float* lpart;               // [grid][4]

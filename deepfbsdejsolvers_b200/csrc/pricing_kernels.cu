@@ -31,8 +31,7 @@ __host__ __device__ constexpr int jtc_nxc() { return 2 + 2 * D <= 16 ? 2 : 3; } 
 int launch_reg_tc_backward(int model, int D, const PricingArgs& a, int grid, cudaStream_t st);   // reg_tc_kernels.cu
 int launch_reg_tc_forward(int model, int D, const PricingArgs& a, int grid, cudaStream_t st);
 size_t reg_tc_backward_smem();
-size_t reg_tc_forward_smem();
-int reg_tc_forward_occupancy(int B, int sms);
+size_t reg_tc_forward_smem(int D);
 
 template <class Model, int HP, bool JUMP, bool JTC>
 __global__ void __launch_bounds__(kThreads, JTC ? 4 : 0) pricing_forward(const PricingArgs a) {
@@ -572,7 +571,7 @@ __global__ void __launch_bounds__(kThreads, JTC ? 2 : 0) pricing_backward(const 
 // ---- launch glue ---------------------------------------------------------------------------------
 template <int HP>
 static size_t pricing_smem(const PricingArgs& a, bool backward) {
-  if (a.mma_mode == 1 && !a.has_jump) return backward ? reg_tc_backward_smem() : reg_tc_forward_smem();
+  if (a.mma_mode == 1 && !a.has_jump) return backward ? reg_tc_backward_smem() : reg_tc_forward_smem(10);
   const bool two = a.has_jump && !a.one_net;
   const bool jtc = a.mma_mode == 1 && a.has_jump;
   const int w = net_smem_floats(a.netA, HP, backward) +
@@ -692,7 +691,7 @@ static int occ_pair(const PricingArgs& a, bool backward) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return backward ? 4 : reg_tc_forward_occupancy(a.B, sms);
+    return 4;
   }
   if (a.has_jump && a.mma_mode == 1) {   // the occupancy calculator does not know about TMEM: 128 / 96 of 512 columns per CTA
     return occ_one<Model, HP, true, true>(a, backward);

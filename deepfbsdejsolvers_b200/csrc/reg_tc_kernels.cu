@@ -122,10 +122,12 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
   auto wait_f = [&]() { tc::mbar_wait(bar_f, phase_f); phase_f ^= 1; tc::tc_fence_after(); };
 
   const float invB = a.inv_B, invBN = a.inv_B / (float)a.N, rdt = a.r * a.dt;
-  const int ntiles = (a.B + TR - 1) / TR;
+  const int ntiles = a.tmap.ntiles;
   const uint32_t step_bytes = (uint32_t)(RL::NP * TR * sizeof(float));
+  // rows beyond the tile's height (96-row tiles) were never written by the forward sweep: they run on benign constants
+  const bool live = row < tile_height(a.tmap, blockIdx.x);
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const float msk = (tile * TR + row < a.B) ? 1.0f : 0.0f;
+    const float msk = (live && tile_base(a.tmap, tile) + row < a.B) ? 1.0f : 0.0f;
     const float* const rec0 = a.rec + (size_t)tile * a.N * RL::NP * TR + row;
     const float* const recN = a.recN + (size_t)tile * RL::NPT * TR + row;
     float Xbar[D];
@@ -133,13 +135,13 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
     {
       float X[D];
 #pragma unroll
-      for (int k = 0; k < D; ++k) X[k] = recN[k * TR];
+      for (int k = 0; k < D; ++k) X[k] = live ? recN[k * TR] : 1.0f;
       float gbar;
       if (a.scheme == SCH_MULTISTEP) {
-        Esum = recN[D * TR];                            // sum_k e_k ; d loss / d g = -2/(NB) sum_k e_k
+        Esum = live ? recN[D * TR] : 0.0f;              // sum_k e_k ; d loss / d g = -2/(NB) sum_k e_k
         gbar = -2.0f * Esum * invBN;
       } else {
-        rb_next = 2.0f * rec0[((size_t)(a.N - 1) * RL::NP + RL::P_SCH) * TR] * invB;
+        rb_next = live ? 2.0f * rec0[((size_t)(a.N - 1) * RL::NP + RL::P_SCH) * TR] * invB : 0.0f;
         gbar = rb_next;
       }
       const float Gb = Model::basket(X);
@@ -150,14 +152,18 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
     if (row == 0 && a.N >= 2) prefetch_l2_bulk(rec0 + (size_t)(a.N - 2) * RL::NP * TR, step_bytes);
     // the record of step i is loaded one step ahead (during the last MMA wait of step i + 1): one base pointer,
     // immediate offsets, DRAM / L2 latency off the critical chain
-    float Xn[D], En[D], s_n, dA_n, sch_n = 0.0f;
+    float Xn[D], En[D], s_n = 0.0f, dA_n = 0.0f, sch_n = 0.0f;
+#pragma unroll
+    for (int k = 0; k < D; ++k) { Xn[k] = 1.0f; En[k] = 1.0f; }
     auto load_step = [&](int i) {
       const float* const rs = rec0 + (size_t)i * RL::NP * TR;
+      if (live) {
 #pragma unroll
-      for (int k = 0; k < D; ++k) { Xn[k] = rs[(RL::P_X + k) * TR]; En[k] = rs[(RL::P_E + k) * TR]; }
-      s_n = rs[RL::P_S * TR]; dA_n = rs[RL::P_DA * TR];
-      // MultiStep: e_i ; SumLocal: rho_{i-1} (the record of the step below; for i = 0 the value is unused)
-      sch_n = rs[(a.scheme == SCH_MULTISTEP || i == 0) ? RL::P_SCH * TR : (RL::P_SCH - RL::NP) * TR];
+        for (int k = 0; k < D; ++k) { Xn[k] = rs[(RL::P_X + k) * TR]; En[k] = rs[(RL::P_E + k) * TR]; }
+        s_n = rs[RL::P_S * TR]; dA_n = rs[RL::P_DA * TR];
+        // MultiStep: e_i ; SumLocal: rho_{i-1} (the record of the step below; for i = 0 the value is unused)
+        sch_n = rs[(a.scheme == SCH_MULTISTEP || i == 0) ? RL::P_SCH * TR : (RL::P_SCH - RL::NP) * TR];
+      }
       if (row == 0 && i >= 3) prefetch_l2_bulk(rs - 3 * RL::NP * TR, step_bytes);
     };
     load_step(a.N - 1);
@@ -342,26 +348,42 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
 // (:461-481) and their VG twins; model step pricingModels.py:53-54 / :184-185.
 // Both layers run on tcgen05 with the 3xTF32 split (fp32-grade: the loss and the stored trajectories keep 1e-5 parity);
 // the time feature is folded into a per-step effective bias c_j = t W1[0][j] + b1[j] formed in fp32 (it is uniform over
-// the tile), so no operand of the split GEMMs is larger than O(1).  The closed-form coupling A(i, X), the exponentials of
-// the Euler step and the record stores are issued between an MMA's launch and the wait on its mbarrier.
+// the tile), so no operand of the split GEMMs is larger than O(1).
+//
+// One CTA = one tile of 128 paths = TWO warpgroups with different jobs (an SM holds 4 such CTAs = 32 warps; with one thread per
+// path and 443 paths per SM at 2^16 paths there were 14, and the sweep was latency-bound):
+//   warpgroup 0 ("network"): thread r = path r = TMEM lane r.  Operand writes to tensor memory, the two MMA round trips, tanh,
+//                the closed-form coupling A(i, X), the loss-graph bookkeeping, the coupled Euler step and the record stores.
+//   warpgroup 1 ("increments"): thread r produces path r's exponentials E = e^{drift dt + sig dW + J} one to two steps ahead -
+//                drawn from Philox counters (RNG; sim_device.cuh) or read from the materialised dW / J planes - into a
+//                two-stage shared-memory ring (mbarrier full / empty pairs, one arrival per warp) and into the record.
+// The increments do not depend on the state, so the two chains only meet at the ring; setmaxnreg moves registers from the
+// producer to the network warpgroup.
 namespace fwd {
-// shared memory: only the B operands (weights) - the activations go to tensor memory
+constexpr int NST = 2;                        // ring stages
+// shared memory: the B operands (weights) - the activations go to tensor memory - and the increment ring
 constexpr int W1B_HI = 0, W1B_LO = W1B_HI + 4 * NB * 4, W2B_HI = W1B_LO + 4 * NB * 4, W2B_LO = W2B_HI + 6 * NB * 4,
               OFF_W3 = W2B_LO + 6 * NB * 4 + 32 /* N = 32 reads 8 n-rows past the last chunk */, OFF_RED = OFF_W3 + 32,
-              OFF_BAR = OFF_RED + 8, OFF_THR = OFF_BAR + 8 /* 64 Poisson thresholds (fused RNG) */, SMEM_FLOATS = OFF_THR + 64;
-static_assert((OFF_BAR % 2) == 0, "mbarrier alignment");
-// tensor memory: two allocations (32 + 64 = 96 columns, so that five CTAs fit the 512 columns of an SM): the accumulator,
-// and the A operand hi (X: 16, H1: 24 columns) | lo
+              OFF_BAR = OFF_RED + 8 /* mbarriers: mma, full[NST], empty[NST] */, OFF_TS = OFF_BAR + 2 * (1 + 2 * NST),
+              OFF_THR = OFF_TS + 2 /* 64 Poisson thresholds (fused RNG) */, OFF_RING = OFF_THR + 64;
+static_assert((OFF_BAR % 2) == 0 && (OFF_RING % 4) == 0, "mbarrier / ring alignment");
+template <int D> constexpr int smem_floats() { return OFF_RING + NST * D * TR; }
+// tensor memory: two allocations (32 + 64 = 96 columns): the accumulator, and the A operand hi (X: 16, H1: 24 columns) | lo
 constexpr uint32_t NCOLS_ACC = 32, NCOLS_A = 64;
+constexpr int REGS_NET = 80, REGS_INC = 48;   // (80 + 48) * 128 threads = 64 * 256: four CTAs per SM
 
+__device__ __forceinline__ void net_barrier(int nthr) { asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory"); }   // warpgroup 0 only
+// TMEM operand writes (+ the bias row in shared memory) -> visible to the MMA issued after the warpgroup barrier
+__device__ __forceinline__ void publish_net(int nthr) {
+  tc::tmem_st_wait();
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  net_barrier(nthr);
+}
 }  // namespace fwd
 
-// OCC = resident CTAs per SM the kernel is compiled for: 5 (<= 102 registers) pays off when every SM gets at least five
-// tiles; with fewer tiles (B = 2^16: 3.5 per SM) the 4-CTA build with its larger register budget is faster.
-// RNG: the sweep draws the Merton increments itself (one Philox block per asset pair, in the shadow of the first MMA) - the
-// simulation kernel, its 8 d bytes per path-step of stores and this kernel's loads of them disappear from the step.
-template <class Model, int ACT, int OCC, bool RNG>
-__global__ void __launch_bounds__(kThreads, OCC) reg_forward_tc(const PricingArgs a) {
+template <class Model, int ACT, bool RNG>
+__global__ void __launch_bounds__(2 * kThreads, 4) reg_forward_tc(const PricingArgs a) {
   constexpr int D = Model::D;
   using RL = RecLayout<D>;
   using namespace fwd;
@@ -369,21 +391,19 @@ __global__ void __launch_bounds__(kThreads, OCC) reg_forward_tc(const PricingArg
   extern __shared__ __align__(1024) float smem[];
   float* const w3s = smem + OFF_W3;
   float* const red = smem + OFF_RED;
-  uint64_t* const bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint32_t* const tslot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 2);
-  const int row = threadIdx.x, warp = row >> 5;
-  const bool issuer = (row & 31) == 0;
+  uint64_t* const bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);   // [0] MMA, [1 + s] full, [1 + NST + s] empty
+  uint32_t* const tslot = reinterpret_cast<uint32_t*>(smem + OFF_TS);
+  float* const ring = smem + OFF_RING;                                 // [NST][D][128]
+  const int tid = threadIdx.x, row = tid & (kThreads - 1), wg = tid >> 7, warp = (tid >> 5) & 3, lane = tid & 31;
   const int H = a.netA.H, nin = a.netA.nin;
   const float one_in = ACT == ACT_TANH ? 20.0f : 1.0f;
 
-  for (int i = row; i < SMEM_FLOATS; i += kThreads) smem[i] = 0.0f;
+  for (int i = tid; i < OFF_RING; i += 2 * kThreads) smem[i] = 0.0f;
   __syncthreads();
-  float w0 = 0.0f, b1v = 0.0f;                          // thread j <= H owns the effective bias of hidden unit j
   {
     const float* __restrict__ th = a.theta + a.netA.ext_off;
     const int n1 = nin * H, n2 = n1 + H, n3 = n2 + H * H, n4 = n3 + H, n5 = n4 + H;
-    if (row < H) { w0 = th[row]; b1v = th[n1 + row]; }
-    for (int e = row; e <= n5 + 1; e += kThreads) {
+    for (int e = tid; e <= n5 + 1; e += 2 * kThreads) {
       float hi, lo;
       if (e < n1) {                                     // W1[i][j], i >= 1 (the time row lives in the effective bias)
         const int i = e / H, j = e % H;
@@ -408,13 +428,94 @@ __global__ void __launch_bounds__(kThreads, OCC) reg_forward_tc(const PricingArg
     }
   }
   uint32_t* const sthr = reinterpret_cast<uint32_t*>(smem + OFF_THR);
-  if (RNG && row < 64) sthr[row] = row < a.npois ? a.pois_thr[row] : 0xffffffffu;
-  if (warp == 0) { tc::tmem_alloc(tslot, NCOLS_ACC, false); tc::tmem_alloc(tslot + 1, NCOLS_A); }
-  if (row == 0) { tc::mbar_init(bar, 1); tc::fence_mbar_init(); }
+  if (RNG && tid < 64) sthr[tid] = tid < a.npois ? a.pois_thr[tid] : 0xffffffffu;
+  if (tid < 32) { tc::tmem_alloc(tslot, NCOLS_ACC, false); tc::tmem_alloc(tslot + 1, NCOLS_A); }
+  const int hrows = tile_height(a.tmap, blockIdx.x);    // rows (= threads per warpgroup) of this CTA's tiles: 128 or 96
+  if (tid == 0) {
+    tc::mbar_init(bar, 1);
+    for (int s = 0; s < NST; ++s) { tc::mbar_init(bar + 1 + s, hrows / 32); tc::mbar_init(bar + 1 + NST + s, hrows / 32); }
+    tc::fence_mbar_init();
+  }
   tc::fence_async_smem();
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
+
+  const size_t sB = (size_t)a.B;
+  const int ntiles = a.tmap.ntiles;
+  uint32_t it = 0;                                      // ring position: steps of all tiles of this CTA, in order
+  if (row >= hrows) return;                             // 96-row tiles: the fourth warp of either warpgroup has no paths
+
+  if (wg == 1) {
+    // ================================ increments: producer of the E ring ================================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_INC));
+    const uint32_t rng_iter = RNG ? (a.iter_ptr ? *a.iter_ptr : a.iteration) : 0u;
+    const uint32_t t0 = RNG ? sthr[0] : 0u, t1 = RNG ? sthr[1] : 0u;
+    const float inv_w1 = t1 > t0 ? 1.0f / (float)(t1 - t0) : 0.0f;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int p0 = tile_base(a.tmap, tile) + row;
+      const int p = p0 < a.B ? p0 : a.B - 1;
+      const uint32_t gid = a.path_offset + (uint32_t)p;
+      float* const rec0 = a.rec + (size_t)tile * a.N * RL::NP * TR + row;
+      for (int i = 0; i < a.N; ++i, ++it) {
+        const uint32_t s = it % NST;
+        float E[D];
+        if constexpr (RNG) {
+          // one Philox block per asset pair; the rare cells (a count >= 2, both draws jumping, a far-tail size: ~0.4 %) are
+          // redone on the exact path after the branch-free common case of every pair, so that the pairs interleave
+          constexpr int KP = (D + 1) / 2;
+          float jj[2 * KP];
+          uint32_t rare_any = 0;
+#pragma unroll
+          for (int kp = 0; kp < KP; ++kp) {
+            const uint4 r = Philox::rand4(gid, ((uint32_t)i << 8) | (uint32_t)kp, rng_iter, STREAM_PATH, a.seed_lo, a.seed_hi);
+            float w0, w1;
+            box_muller_fast(r.x, r.y, a.sqdt, w0, w1);
+            uint32_t rare;
+            jump_sizes_fast(r.z, r.w, t0, t1, inv_w1, a.muJ, a.sigJ, jj[2 * kp], jj[2 * kp + 1], rare);
+            rare_any |= rare << (2 * kp);
+            E[2 * kp] = fmaf(a.sig, w0, a.drift_dt);
+            if (2 * kp + 1 < D) E[2 * kp + 1] = fmaf(a.sig, w1, a.drift_dt);
+          }
+          if (rare_any) {
+#pragma unroll
+            for (int kp = 0; kp < KP; ++kp) {
+              if ((rare_any >> (2 * kp)) & 3u) {
+                const uint32_t c1 = ((uint32_t)i << 8) | (uint32_t)kp;
+                const uint4 r = Philox::rand4(gid, c1, rng_iter, STREAM_PATH, a.seed_lo, a.seed_hi);
+                if ((rare_any >> (2 * kp)) & 1u)
+                  jj[2 * kp] = jump_size_rare(r.z, t0, t1, inv_w1, sthr, a.npois, a.muJ, a.sigJ, gid, c1, rng_iter, STREAM_PATH, a.seed_lo, a.seed_hi, 0);
+                if ((rare_any >> (2 * kp)) & 2u)
+                  jj[2 * kp + 1] = jump_size_rare(r.w, t0, t1, inv_w1, sthr, a.npois, a.muJ, a.sigJ, gid, c1, rng_iter, STREAM_PATH, a.seed_lo, a.seed_hi, 1);
+              }
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < D; ++k) E[k] = __expf(E[k] + jj[k]);
+        } else {
+          const float* __restrict__ pw = a.dW + (size_t)i * D * sB + p;
+          const float* __restrict__ pj = a.J + (size_t)i * D * sB + p;
+#pragma unroll
+          for (int k = 0; k < D; ++k)
+            E[k] = __expf(a.drift_dt + (Model::kBrownian ? a.sig * pw[(size_t)k * sB] : 0.0f) + pj[(size_t)k * sB]);
+        }
+        if (it >= NST) tc::mbar_wait(bar + 1 + NST + s, ((it / NST) - 1) & 1);   // the network has read this stage
+        float* const rg = ring + (size_t)s * D * TR + row;
+        float* const rs = rec0 + (size_t)i * RL::NP * TR;
+#pragma unroll
+        for (int k = 0; k < D; ++k) { rg[k * TR] = E[k]; rs[(RL::P_E + k) * TR] = E[k]; }
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(bar + 1 + s);
+      }
+    }
+    return;
+  }
+
+  // ==================================== network: consumer of the ring ==================================================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_NET));
+  const bool issuer = lane == 0;
+  float w0 = 0.0f, b1v = 0.0f;                          // thread j <= H owns the effective bias of hidden unit j
+  if (row < H) { w0 = a.theta[a.netA.ext_off + row]; b1v = a.theta[a.netA.ext_off + nin * H + row]; }
   const uint32_t tmem = tslot[0], tmem_a = tslot[1];
   const uint32_t lane_base = tmem + ((uint32_t)(row & ~31) << 16), lane_a = tmem_a + ((uint32_t)(row & ~31) << 16);
   const uint32_t sbase = tc::smem_u32(smem);
@@ -422,57 +523,21 @@ __global__ void __launch_bounds__(kThreads, OCC) reg_forward_tc(const PricingArg
   uint32_t phase = 0;
   auto wait_mma = [&]() { tc::mbar_wait(bar, phase); phase ^= 1; tc::tc_fence_after(); };
   const int bias_idx = ((nin >> 2) * NB + row) * 4 + (nin & 3);   // W1B[n = row][k = nin]
-
-  const size_t sB = (size_t)a.B;
   const float rdt = a.r * a.dt;
   float lsum = 0.0f;
-  const uint32_t rng_iter = RNG ? (a.iter_ptr ? *a.iter_ptr : a.iteration) : 0u;
-  const uint32_t t0 = RNG ? sthr[0] : 0u, t1 = RNG ? sthr[1] : 0u;
-  const float inv_w1 = t1 > t0 ? 1.0f / (float)(t1 - t0) : 0.0f;
-  const int ntiles = (a.B + TR - 1) / TR;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int p0 = tile * TR + row;
+    const int p0 = tile_base(a.tmap, tile) + row;
     const bool valid = p0 < a.B;
     const int p = valid ? p0 : a.B - 1;
-    const uint32_t gid = a.path_offset + (uint32_t)p;
     float* const rec0 = a.rec + (size_t)tile * a.N * RL::NP * TR + row;
     float X[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) X[k] = a.x0;
     float Cpre = 0.0f;                               // MultiStep: sum_{j<i} toAdd_j
     float yprev = 0.0f, aprev = 0.0f, lloc = 0.0f;   // SumLocal
-    // the increments of step i are loaded one step ahead (right after the first MMA of step i - 1 is issued)
-    float Wn[Model::kBrownian ? D : 1], Jn[D];       // raw values: the combine happens where they are consumed
-    auto load_step = [&](int i) {
-      if (RNG) return;
-      const float* __restrict__ pw = a.dW + (size_t)i * D * sB + p;
-      const float* __restrict__ pj = a.J + (size_t)i * D * sB + p;
-#pragma unroll
-      for (int k = 0; k < D; ++k) {
-        if (Model::kBrownian) Wn[Model::kBrownian ? k : 0] = pw[(size_t)k * sB];
-        Jn[k] = pj[(size_t)k * sB];
-      }
-    };
-    load_step(0);
-    // RNG: the exponentials e^{drift dt + sig dW + J} of step i + 1 are drawn during step i, two asset pairs in the shadow
-    // of the first MMA and the rest in the shadow of the second one
-    float En[RNG ? D : 1];
-    auto draw = [&](int i, int kp_lo, int kp_hi) {
-#pragma unroll
-      for (int kp = 0; kp < (D + 1) / 2; ++kp) {
-        if (kp < kp_lo || kp >= kp_hi) continue;
-        const MertonCell c = merton_cell(gid, ((uint32_t)i << 8) | (uint32_t)kp, rng_iter, STREAM_PATH, a.seed_lo, a.seed_hi, t0, t1,
-                                         inv_w1, a.sqdt, a.muJ, a.sigJ, sthr, a.npois);
-        En[RNG ? 2 * kp : 0] = __expf(a.drift_dt + a.sig * c.w0 + c.j0);
-        if (2 * kp + 1 < D) En[RNG ? 2 * kp + 1 : 0] = __expf(a.drift_dt + a.sig * c.w1 + c.j1);
-      }
-    };
-    constexpr int KP = (D + 1) / 2, KP1 = KP < 2 ? KP : 2;
-    if constexpr (RNG) draw(0, 0, KP);
-    for (int i = 0; i < a.N; ++i) {
+    for (int i = 0; i < a.N; ++i, ++it) {
       const float tf = (a.scheme == SCH_SUMLOCAL && a.stale_time) ? (float)(i == 0 ? 0 : i - 1) : (float)i;
       float* const rs = rec0 + (size_t)i * RL::NP * TR;
-      float E[D];
       {
         float xin[16];
 #pragma unroll
@@ -486,69 +551,71 @@ __global__ void __launch_bounds__(kThreads, OCC) reg_forward_tc(const PricingArg
           smem[W1B_HI + bias_idx] = hi;
           smem[W1B_LO + bias_idx] = lo;
         }
-        // the TMEM stores go last, right before the wait::st of publish_tmem(): tcgen05.st reads its source registers
+        // the TMEM stores go last, right before the wait::st of publish_net(): tcgen05.st reads its source registers
         // asynchronously, so any instruction that reuses one of them would stall until the store has drained
         store_tf32x8(lane_a, 0, xin);
         store_tf32x8(lane_a, 1, xin + 8);
       }
-      publish_tmem();
+      publish_net(hrows);
       if (warp == 0 && issuer) {
         tc::tc_fence_after();
         gemm_k_tf32<2>(tmem, tmem_a, sa(W1B_HI), sa(W1B_LO));
         tc::mma_commit(bar);
       }
-      // ---- independent of the network: closed-form coupling, exponentials, record stores -------------------------
+      // ---- independent of the network: closed-form coupling, record stores (in the shadow of the first MMA) ------------
       typename Model::AEval ae;
-      Model::eval_A_begin(a, i, X, ae);                  // table loads in flight ...
-      if constexpr (RNG) {                               // ... while the stores issue and next step's increments are drawn
+      Model::eval_A_begin(a, i, X, ae);                  // table loads in flight while the stores issue
 #pragma unroll
-        for (int k = 0; k < D; ++k) {
-          rs[(RL::P_X + k) * TR] = X[k];
-          E[k] = En[RNG ? k : 0];
-        }
-        if (i + 1 < a.N) draw(i + 1, 0, KP1);
-      } else {
-#pragma unroll
-        for (int k = 0; k < D; ++k) {                    // ... while the exponentials and the stores issue
-          rs[(RL::P_X + k) * TR] = X[k];
-          E[k] = __expf(a.drift_dt + (Model::kBrownian ? a.sig * Wn[Model::kBrownian ? k : 0] : 0.0f) + Jn[k]);
-        }
-      }
+      for (int k = 0; k < D; ++k) rs[(RL::P_X + k) * TR] = X[k];
       float Ai, dAb;
       Model::eval_A_finish(a, i, ae, Ai, dAb);
       rs[RL::P_DA * TR] = dAb;
       wait_mma();
+      {
+        float t24[24];
+        tc::tmem_ld8(lane_base, reinterpret_cast<float (&)[8]>(t24[0]));
+        tc::tmem_ld8(lane_base + 8, reinterpret_cast<float (&)[8]>(t24[8]));
+        tc::tmem_ld8(lane_base + 16, reinterpret_cast<float (&)[8]>(t24[16]));
+        tc::tmem_ld_wait();                              // one drain for the three loads
 #pragma unroll
-      for (int c8 = 0; c8 < 3; ++c8) {
-        float t8[8];
-        tc::tmem_ld8(lane_base + 8 * c8, t8);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int q = 0; q < 8; ++q) t8[q] = actf<ACT>(t8[q]);
-        store_tf32x8(lane_a, c8, t8);                    // (L1 has completed: the X columns are free)
+        for (int q = 0; q < 24; ++q) t24[q] = actf<ACT>(t24[q]);
+        store_tf32x8(lane_a, 0, t24);                    // (L1 has completed: the X columns are free)
+        store_tf32x8(lane_a, 1, t24 + 8);
+        store_tf32x8(lane_a, 2, t24 + 16);
       }
-      publish_tmem();
+      publish_net(hrows);
       if (warp == 1 && issuer) {
         tc::tc_fence_after();
         gemm_k_tf32<3>(tmem, tmem_a, sa(W2B_HI), sa(W2B_LO));
         tc::mma_commit(bar);
       }
+      // ---- this step's exponentials from the ring (in the shadow of the second MMA) -------------------------------------
+      float E[D];
+      {
+        const uint32_t s = it % NST;
+        tc::mbar_wait(bar + 1 + s, (it / NST) & 1);
+        const float* const rg = ring + (size_t)s * D * TR + row;
 #pragma unroll
-      for (int k = 0; k < D; ++k) rs[(RL::P_E + k) * TR] = E[k];
-      if (i + 1 < a.N) {
-        if constexpr (RNG) draw(i + 1, KP1, KP); else load_step(i + 1);
+        for (int k = 0; k < D; ++k) E[k] = rg[k * TR];
+        __syncwarp();
+        if (issuer) tc::mbar_arrive(bar + 1 + NST + s);
       }
       wait_mma();
       float y_net = w3s[24];
-#pragma unroll
-      for (int c8 = 0; c8 < 3; ++c8) {
-        float t8[8];
-        tc::tmem_ld8(lane_base + 8 * c8, t8);
+      {
+        float t24[24];
+        tc::tmem_ld8(lane_base, reinterpret_cast<float (&)[8]>(t24[0]));
+        tc::tmem_ld8(lane_base + 8, reinterpret_cast<float (&)[8]>(t24[8]));
+        tc::tmem_ld8(lane_base + 16, reinterpret_cast<float (&)[8]>(t24[16]));
         tc::tmem_ld_wait();
-        const float4 wa = ld4(w3s + 8 * c8), wb = ld4(w3s + 8 * c8 + 4);
-        const float w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
-        for (int q = 0; q < 8; ++q) y_net = fmaf(actf<ACT>(t8[q]), w8[q], y_net);
+        for (int c4 = 0; c4 < 6; ++c4) {
+          const float4 w = ld4(w3s + 4 * c4);
+          y_net = fmaf(actf<ACT>(t24[4 * c4]), w.x, y_net);
+          y_net = fmaf(actf<ACT>(t24[4 * c4 + 1]), w.y, y_net);
+          y_net = fmaf(actf<ACT>(t24[4 * c4 + 2]), w.z, y_net);
+          y_net = fmaf(actf<ACT>(t24[4 * c4 + 3]), w.w, y_net);
+        }
       }
       tc::tc_fence_before();
       // ---- loss-graph bookkeeping ---------------------------------------------------------------------------------
@@ -600,9 +667,11 @@ __global__ void __launch_bounds__(kThreads, OCC) reg_forward_tc(const PricingArg
     if (valid) lsum += lpath;
   }
   tc::tc_fence_before();
-  const float tot = block_sum(lsum, red);
+  lsum = warp_sum(lsum);
+  if (lane == 0) red[warp] = lsum;
+  net_barrier(hrows);
   if (row == 0) {
-    a.lpart[blockIdx.x * 4] = tot;
+    a.lpart[blockIdx.x * 4] = red[0] + red[1] + red[2] + red[3];   // (red[3] stays 0 in a 96-row CTA)
     a.lpart[blockIdx.x * 4 + 1] = 0.0f; a.lpart[blockIdx.x * 4 + 2] = 0.0f; a.lpart[blockIdx.x * 4 + 3] = 0.0f;
   }
   if (warp == 0) { tc::tmem_dealloc(tmem, NCOLS_ACC); tc::tmem_dealloc(tmem_a, NCOLS_A); }
@@ -610,48 +679,42 @@ __global__ void __launch_bounds__(kThreads, OCC) reg_forward_tc(const PricingArg
 
 // Tile-major record -> the plane layout of fbsdej_solver_loss' trajectory output: X [N+1][D][B].
 template <int D>
-__global__ void untile_traj_kernel(const float* __restrict__ rec, const float* __restrict__ recN, int B, int N, float* __restrict__ out) {
+__global__ void untile_traj_kernel(const float* __restrict__ rec, const float* __restrict__ recN, TileMap map, int B, int N,
+                                   float* __restrict__ out) {
   using RL = RecLayout<D>;
-  const size_t total = (size_t)(N + 1) * D * B;
+  const size_t total = (size_t)(N + 1) * D * map.ntiles * TR;
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-    const int p = (int)(t % B), k = (int)((t / B) % D), i = (int)(t / ((size_t)B * D));
-    const int tile = p / TR, row = p % TR;
-    out[t] = i < N ? rec[(((size_t)tile * N + i) * RL::NP + RL::P_X + k) * TR + row] : recN[((size_t)tile * RL::NPT + k) * TR + row];
+    const int row = (int)(t % TR), tile = (int)((t / TR) % map.ntiles), k = (int)((t / ((size_t)TR * map.ntiles)) % D),
+              i = (int)(t / ((size_t)TR * map.ntiles * D));
+    const int p = tile_base(map, tile) + row;
+    if (row >= tile_height(map, tile) || p >= B) continue;
+    out[((size_t)i * D + k) * B + p] =
+        i < N ? rec[(((size_t)tile * N + i) * RL::NP + RL::P_X + k) * TR + row] : recN[((size_t)tile * RL::NPT + k) * TR + row];
   }
 }
 
 }  // namespace rtc
 
 size_t reg_tc_backward_smem() { return sizeof(float) * (size_t)rtc::bwd::SMEM_FLOATS; }
-size_t reg_tc_forward_smem() { return sizeof(float) * (size_t)rtc::fwd::SMEM_FLOATS; }
+size_t reg_tc_forward_smem(int D) { return sizeof(float) * (size_t)(D == 10 ? rtc::fwd::smem_floats<10>() : rtc::fwd::smem_floats<1>()); }
 
-template <class Model, int ACT, int OCC, bool RNG>
+template <class Model, int ACT, bool RNG>
 static int launch_fwd_one(const PricingArgs& a, int grid, cudaStream_t st) {
-  const size_t smem = reg_tc_forward_smem();
-  auto kern = rtc::reg_forward_tc<Model, ACT, OCC, RNG>;
+  const size_t smem = sizeof(float) * (size_t)rtc::fwd::smem_floats<Model::D>();
+  auto kern = rtc::reg_forward_tc<Model, ACT, RNG>;
   FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, kThreads, smem, st>>>(a);
+  kern<<<grid, 2 * kThreads, smem, st>>>(a);
   FB_CUDA(cudaGetLastError());
   return 0;
 }
-int reg_tc_forward_occupancy(int B, int sms) { return (B + TR - 1) / TR >= 5 * sms ? 5 : 4; }
 template <class Model>
 static int launch_fwd(const PricingArgs& a, int grid, cudaStream_t st) {
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const bool five = reg_tc_forward_occupancy(a.B, sms) == 5;
   if constexpr (Model::kBrownian) {
-    if (a.rng) {
-      if (a.netA.act == ACT_TANH)
-        return five ? launch_fwd_one<Model, ACT_TANH, 5, true>(a, grid, st) : launch_fwd_one<Model, ACT_TANH, 4, true>(a, grid, st);
-      return five ? launch_fwd_one<Model, ACT_RELU, 5, true>(a, grid, st) : launch_fwd_one<Model, ACT_RELU, 4, true>(a, grid, st);
-    }
+    if (a.rng)
+      return a.netA.act == ACT_TANH ? launch_fwd_one<Model, ACT_TANH, true>(a, grid, st) : launch_fwd_one<Model, ACT_RELU, true>(a, grid, st);
   }
   if (a.rng) { set_error("tcgen05 forward: in-kernel increments exist for the Merton model only"); return -1; }
-  if (a.netA.act == ACT_TANH)
-    return five ? launch_fwd_one<Model, ACT_TANH, 5, false>(a, grid, st) : launch_fwd_one<Model, ACT_TANH, 4, false>(a, grid, st);
-  return five ? launch_fwd_one<Model, ACT_RELU, 5, false>(a, grid, st) : launch_fwd_one<Model, ACT_RELU, 4, false>(a, grid, st);
+  return a.netA.act == ACT_TANH ? launch_fwd_one<Model, ACT_TANH, false>(a, grid, st) : launch_fwd_one<Model, ACT_RELU, false>(a, grid, st);
 }
 
 int launch_reg_tc_forward(int model, int D, const PricingArgs& a, int grid, cudaStream_t st) {
@@ -688,10 +751,10 @@ int launch_reg_tc_backward(int model, int D, const PricingArgs& a, int grid, cud
   return -1;
 }
 
-int launch_untile_traj(int D, const float* rec, const float* recN, int B, int N, float* out, cudaStream_t st) {
+int launch_untile_traj(int D, const float* rec, const float* recN, TileMap map, int B, int N, float* out, cudaStream_t st) {
   const int grid = 148 * 4;
-  if (D == 1) rtc::untile_traj_kernel<1><<<grid, 256, 0, st>>>(rec, recN, B, N, out);
-  else if (D == 10) rtc::untile_traj_kernel<10><<<grid, 256, 0, st>>>(rec, recN, B, N, out);
+  if (D == 1) rtc::untile_traj_kernel<1><<<grid, 256, 0, st>>>(rec, recN, map, B, N, out);
+  else if (D == 10) rtc::untile_traj_kernel<10><<<grid, 256, 0, st>>>(rec, recN, map, B, N, out);
   else { set_error("untile: unsupported d"); return -1; }
   FB_CUDA(cudaGetLastError());
   return 0;
