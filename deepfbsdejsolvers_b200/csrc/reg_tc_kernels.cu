@@ -372,6 +372,15 @@ template <int D> constexpr int smem_floats() { return OFF_RING + NST * D * TR; }
 constexpr uint32_t NCOLS_ACC = 32, NCOLS_A = 64;
 constexpr int REGS_NET = 80, REGS_INC = 48;   // (80 + 48) * 128 threads = 64 * 256: four CTAs per SM
 
+// hidden unit in r form (tanh: r = 1 / (2^x' + 1), h = 1 - 2 r is never formed) or ReLU
+template <int ACT>
+__device__ __forceinline__ float hidf(float x) {
+  if (ACT != ACT_TANH) return fmaxf(x, 0.0f);
+  float t, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + 1.0f));
+  return r;
+}
 __device__ __forceinline__ void net_barrier(int nthr) { asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory"); }   // warpgroup 0 only
 // TMEM operand writes (+ the bias row in shared memory) -> visible to the MMA issued after the warpgroup barrier
 __device__ __forceinline__ void publish_net(int nthr) {
@@ -396,35 +405,50 @@ __global__ void __launch_bounds__(2 * kThreads, 4) reg_forward_tc(const PricingA
   float* const ring = smem + OFF_RING;                                 // [NST][D][128]
   const int tid = threadIdx.x, row = tid & (kThreads - 1), wg = tid >> 7, warp = (tid >> 5) & 3, lane = tid & 31;
   const int H = a.netA.H, nin = a.netA.nin;
-  const float one_in = ACT == ACT_TANH ? 20.0f : 1.0f;
+  constexpr float CS = ACT == ACT_TANH ? 2.885390081777927f : 1.0f;        // pre-activation scale 2 log2(e)
+  constexpr float W2S = ACT == ACT_TANH ? -2.0f * CS : 1.0f, W3S = ACT == ACT_TANH ? -2.0f : 1.0f;
+  constexpr float one_in = ACT == ACT_TANH ? -200.0f : 1.0f;               // constant-1 unit: r(-200) = 1, relu(1) = 1
 
   for (int i = tid; i < OFF_RING; i += 2 * kThreads) smem[i] = 0.0f;
   __syncthreads();
   {
+    // tanh layers run in "r form": the MMA delivers x' = 2 log2(e) x (scale folded into the weights), the thread forms
+    // r = 1 / (2^x' + 1) (two MUFU + one add) and hands r - not h = 1 - 2 r - to the next layer, whose weights carry the
+    // factor -2 and whose bias row carries b + sum_k W[k][.]; the constant-1 unit is r = 1 exactly (2^-200 flushes to 0).
     const float* __restrict__ th = a.theta + a.netA.ext_off;
     const int n1 = nin * H, n2 = n1 + H, n3 = n2 + H * H, n4 = n3 + H, n5 = n4 + H;
-    for (int e = tid; e <= n5 + 1; e += 2 * kThreads) {
+    for (int e = tid; e < n5; e += 2 * kThreads) {
       float hi, lo;
       if (e < n1) {                                     // W1[i][j], i >= 1 (the time row lives in the effective bias)
         const int i = e / H, j = e % H;
         if (i >= 1) {
-          tc::split_tf32(th[e], hi, lo);
+          tc::split_tf32(CS * th[e], hi, lo);
           smem[W1B_HI + ((i >> 2) * NB + j) * 4 + (i & 3)] = hi;
           smem[W1B_LO + ((i >> 2) * NB + j) * 4 + (i & 3)] = lo;
         }
       } else if (e < n2) {
-      } else if (e < n4) {                              // W2[k][j], b2[j] (k = H)
-        const int k = e < n3 ? (e - n2) / H : H, j = e < n3 ? (e - n2) % H : e - n3;
-        tc::split_tf32(th[e], hi, lo);
+      } else if (e < n3) {                              // W2[k][j]
+        const int k = (e - n2) / H, j = (e - n2) % H;
+        tc::split_tf32(W2S * th[e], hi, lo);
         smem[W2B_HI + ((k >> 2) * NB + j) * 4 + (k & 3)] = hi;
         smem[W2B_LO + ((k >> 2) * NB + j) * 4 + (k & 3)] = lo;
-      } else if (e <= n5) {
-        w3s[e < n5 ? e - n4 : 24] = th[e];              // W3[k], k < H; b3 at index 24
+      } else if (e < n4) {
       } else {
-        tc::split_tf32(one_in, hi, lo);
-        smem[W2B_HI + ((H >> 2) * NB + H) * 4 + (H & 3)] = hi;
-        smem[W2B_LO + ((H >> 2) * NB + H) * 4 + (H & 3)] = lo;
+        w3s[e - n4] = W3S * th[e];                      // W3[k], k < H
       }
+    }
+    if (tid < H) {                                      // bias row of layer 2 (k = H)
+      float b = th[n3 + tid];
+      if (ACT == ACT_TANH) for (int k = 0; k < H; ++k) b += th[n2 + k * H + tid];
+      float hi, lo;
+      tc::split_tf32(CS * b, hi, lo);
+      smem[W2B_HI + ((H >> 2) * NB + tid) * 4 + (H & 3)] = hi;
+      smem[W2B_LO + ((H >> 2) * NB + tid) * 4 + (H & 3)] = lo;
+    }
+    if (tid == 2 * kThreads - 1) {                      // output bias at index 24
+      float b = th[n5];
+      if (ACT == ACT_TANH) for (int k = 0; k < H; ++k) b += th[n4 + k];
+      w3s[24] = b;
     }
   }
   uint32_t* const sthr = reinterpret_cast<uint32_t*>(smem + OFF_THR);
@@ -452,6 +476,9 @@ __global__ void __launch_bounds__(2 * kThreads, 4) reg_forward_tc(const PricingA
     const uint32_t rng_iter = RNG ? (a.iter_ptr ? *a.iter_ptr : a.iteration) : 0u;
     const uint32_t t0 = RNG ? sthr[0] : 0u, t1 = RNG ? sthr[1] : 0u;
     const float inv_w1 = t1 > t0 ? 1.0f / (float)(t1 - t0) : 0.0f;
+    // E = 2^(log2(e) (drift dt + sig dW + J)): log2(e) rides in the constants (jump sizes are linear in muJ, sigJ)
+    constexpr float L2E = 1.4426950408889634f;
+    const float driftL = L2E * a.drift_dt, sigL = L2E * a.sig, muJL = L2E * a.muJ, sigJL = L2E * a.sigJ;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int p0 = tile_base(a.tmap, tile) + row;
       const int p = p0 < a.B ? p0 : a.B - 1;
@@ -472,10 +499,10 @@ __global__ void __launch_bounds__(2 * kThreads, 4) reg_forward_tc(const PricingA
             float w0, w1;
             box_muller_fast(r.x, r.y, a.sqdt, w0, w1);
             uint32_t rare;
-            jump_sizes_fast(r.z, r.w, t0, t1, inv_w1, a.muJ, a.sigJ, jj[2 * kp], jj[2 * kp + 1], rare);
+            jump_sizes_fast(r.z, r.w, t0, t1, inv_w1, muJL, sigJL, jj[2 * kp], jj[2 * kp + 1], rare);
             rare_any |= rare << (2 * kp);
-            E[2 * kp] = fmaf(a.sig, w0, a.drift_dt);
-            if (2 * kp + 1 < D) E[2 * kp + 1] = fmaf(a.sig, w1, a.drift_dt);
+            E[2 * kp] = fmaf(sigL, w0, driftL);
+            if (2 * kp + 1 < D) E[2 * kp + 1] = fmaf(sigL, w1, driftL);
           }
           if (rare_any) {
 #pragma unroll
@@ -484,14 +511,14 @@ __global__ void __launch_bounds__(2 * kThreads, 4) reg_forward_tc(const PricingA
                 const uint32_t c1 = ((uint32_t)i << 8) | (uint32_t)kp;
                 const uint4 r = Philox::rand4(gid, c1, rng_iter, STREAM_PATH, a.seed_lo, a.seed_hi);
                 if ((rare_any >> (2 * kp)) & 1u)
-                  jj[2 * kp] = jump_size_rare(r.z, t0, t1, inv_w1, sthr, a.npois, a.muJ, a.sigJ, gid, c1, rng_iter, STREAM_PATH, a.seed_lo, a.seed_hi, 0);
+                  jj[2 * kp] = jump_size_rare(r.z, t0, t1, inv_w1, sthr, a.npois, muJL, sigJL, gid, c1, rng_iter, STREAM_PATH, a.seed_lo, a.seed_hi, 0);
                 if ((rare_any >> (2 * kp)) & 2u)
-                  jj[2 * kp + 1] = jump_size_rare(r.w, t0, t1, inv_w1, sthr, a.npois, a.muJ, a.sigJ, gid, c1, rng_iter, STREAM_PATH, a.seed_lo, a.seed_hi, 1);
+                  jj[2 * kp + 1] = jump_size_rare(r.w, t0, t1, inv_w1, sthr, a.npois, muJL, sigJL, gid, c1, rng_iter, STREAM_PATH, a.seed_lo, a.seed_hi, 1);
               }
             }
           }
 #pragma unroll
-          for (int k = 0; k < D; ++k) E[k] = __expf(E[k] + jj[k]);
+          for (int k = 0; k < D; ++k) E[k] = ex2_raw(E[k] + jj[k]);
         } else {
           const float* __restrict__ pw = a.dW + (size_t)i * D * sB + p;
           const float* __restrict__ pj = a.J + (size_t)i * D * sB + p;
@@ -515,7 +542,7 @@ __global__ void __launch_bounds__(2 * kThreads, 4) reg_forward_tc(const PricingA
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_NET));
   const bool issuer = lane == 0;
   float w0 = 0.0f, b1v = 0.0f;                          // thread j <= H owns the effective bias of hidden unit j
-  if (row < H) { w0 = a.theta[a.netA.ext_off + row]; b1v = a.theta[a.netA.ext_off + nin * H + row]; }
+  if (row < H) { w0 = CS * a.theta[a.netA.ext_off + row]; b1v = CS * a.theta[a.netA.ext_off + nin * H + row]; }
   const uint32_t tmem = tslot[0], tmem_a = tslot[1];
   const uint32_t lane_base = tmem + ((uint32_t)(row & ~31) << 16), lane_a = tmem_a + ((uint32_t)(row & ~31) << 16);
   const uint32_t sbase = tc::smem_u32(smem);
@@ -578,7 +605,7 @@ __global__ void __launch_bounds__(2 * kThreads, 4) reg_forward_tc(const PricingA
         tc::tmem_ld8(lane_base + 16, reinterpret_cast<float (&)[8]>(t24[16]));
         tc::tmem_ld_wait();                              // one drain for the three loads
 #pragma unroll
-        for (int q = 0; q < 24; ++q) t24[q] = actf<ACT>(t24[q]);
+        for (int q = 0; q < 24; ++q) t24[q] = hidf<ACT>(t24[q]);
         store_tf32x8(lane_a, 0, t24);                    // (L1 has completed: the X columns are free)
         store_tf32x8(lane_a, 1, t24 + 8);
         store_tf32x8(lane_a, 2, t24 + 16);
@@ -611,10 +638,10 @@ __global__ void __launch_bounds__(2 * kThreads, 4) reg_forward_tc(const PricingA
 #pragma unroll
         for (int c4 = 0; c4 < 6; ++c4) {
           const float4 w = ld4(w3s + 4 * c4);
-          y_net = fmaf(actf<ACT>(t24[4 * c4]), w.x, y_net);
-          y_net = fmaf(actf<ACT>(t24[4 * c4 + 1]), w.y, y_net);
-          y_net = fmaf(actf<ACT>(t24[4 * c4 + 2]), w.z, y_net);
-          y_net = fmaf(actf<ACT>(t24[4 * c4 + 3]), w.w, y_net);
+          y_net = fmaf(hidf<ACT>(t24[4 * c4]), w.x, y_net);
+          y_net = fmaf(hidf<ACT>(t24[4 * c4 + 1]), w.y, y_net);
+          y_net = fmaf(hidf<ACT>(t24[4 * c4 + 2]), w.z, y_net);
+          y_net = fmaf(hidf<ACT>(t24[4 * c4 + 3]), w.w, y_net);
         }
       }
       tc::tc_fence_before();

@@ -30,6 +30,18 @@ static __device__ __noinline__ float jump_size_rare(uint32_t u, uint32_t t0, uin
   return dn * muJ + sigJ * sqrtf(dn) * (which ? e1 : e0);
 }
 
+// MUFU.LG2 without the denormal-input rescaling __log2f adds (three instructions): the arguments here are >= 2^-33 or exactly 0
+__device__ __forceinline__ float lg2_raw(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_raw(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // Branch-free common case for the two Poisson draws (u0, u1) of one Philox block.  count = 0: J = 0.  count = 1
 // (thr[0] <= u < thr[1]): v = (u - thr[0] + 1/2) / (thr[1] - thr[0]) is uniform on (0, 1) with ~28 bits;
 // z = Phi^{-1}(v) = sqrt(2) erfinv(2v - 1) by Giles' single-precision polynomial in w = -ln(4 v (1 - v)) (central branch
@@ -41,7 +53,7 @@ __device__ __forceinline__ void jump_sizes_fast(uint32_t u0, uint32_t u1, uint32
   const uint32_t u = one1 ? u1 : u0;
   const float v = ((float)(u - t0) + 0.5f) * inv_w1;
   const float x = fmaf(2.0f, v, -1.0f);
-  float w = -0.6931471805599453f * __log2f(fmaf(-x, x, 1.0f));
+  float w = -0.6931471805599453f * lg2_raw(fmaf(-x, x, 1.0f));
   const bool tail = (one0 || one1) && !(w < 5.0f);
   rare = ((u0 >= t1) || (one0 && (one1 || tail)) ? 1u : 0u) | ((u1 >= t1) || (one1 && (one0 || tail)) ? 2u : 0u);
   w -= 2.5f;
@@ -63,7 +75,7 @@ __device__ __forceinline__ void jump_sizes_fast(uint32_t u0, uint32_t u1, uint32
 __device__ __forceinline__ void box_muller_fast(uint32_t a, uint32_t b, float scale, float& n0, float& n1) {
   const float u = fmaf(__uint2float_rz(a), 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // (0, 1)
   float r;
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * __log2f(u)));           // sqrt(-2 ln u)
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * lg2_raw(u)));           // sqrt(-2 ln u)
   r *= scale;
   float sn, cs;
   __sincosf(__uint2float_rz(b) * 1.4629180792671596e-09f, &sn, &cs);                               // 2 pi b / 2^32
