@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfbsdej.so")
+LIB_PATH = os.environ.get("FBSDEJ_LIB") or os.path.join(_HERE, "libfbsdej.so")   # FBSDEJ_LIB: another build of the same library
 
 MODEL_MERTON, MODEL_VG, MODEL_MFG = 0, 1, 2
 GLOBAL, MULTISTEP1, MULTISTEP2, SUMLOCAL1, SUMLOCAL2, SUMLOCALREG, MULTISTEPREG = range(7)

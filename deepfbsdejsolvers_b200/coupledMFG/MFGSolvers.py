@@ -46,6 +46,9 @@ class SolverBase:
         n_y0 = 2 if self.SCHEME == L.GLOBAL else 0
         sh, si = hat.spec(), ind.spec()
         tc_ok = sh.H <= 22 and si.H <= 22 and sh.L == 2 and si.L == 2 and sh.activation == si.activation
+        if self.tensor_cores and not tc_ok:
+            raise ValueError(f"{type(self).__name__}: tensor_cores=True, but the tcgen05 MFG kernels need two hidden layers of width "
+                             f"<= 22 and one activation for both networks; got {sh} and {si}")
         use_tc = tc_ok if self.tensor_cores is None else bool(self.tensor_cores)
         self.native = self.mathModel.make_solver(self.SCHEME, [sh, si], n_y0, ctx=self.ctx, tensor_cores=use_tc)
         parts = [hat.params, ind.params]
@@ -102,6 +105,20 @@ class SolverBase:
         _, _, tx, _ = self._replay(nbSimul)
         return (list(tx[:, 0].mean(axis=1)), list(tx[:, 0].std(axis=1)), list(tx[:, 1].mean(axis=1)), list(tx[:, 1].std(axis=1)))
 
+    # checkpoint / resume: parameters | Adam m, v, t | Philox iteration; the reference keeps nothing on disk
+    def save(self, path: str) -> None:
+        self.build().save_checkpoint(path, seed=self.seed, listY0_hat=getattr(self, "listY0_hat", []),
+                                     listY0=getattr(self, "listY0", []), lossList=getattr(self, "lossList", []))
+
+    def load(self, path: str) -> None:
+        sd = self.build().load_checkpoint(path)
+        self.seed = int(sd.get("seed", self.seed))
+        self.listY0_hat = [np.float32(x) for x in sd.get("listY0_hat", [])]
+        self.listY0 = [np.float32(x) for x in sd.get("listY0", [])]
+        self.lossList = [float(x) for x in sd.get("lossList", [])]
+        self._resumed = True               # the next train() keeps the restored optimizer state
+        self.pull_params()
+
     def _mask(self, which: str) -> torch.Tensor:
         s = self.native
         m = np.zeros(s.P, dtype=np.float32)
@@ -119,10 +136,12 @@ class SolverBase:
     def train(self, batchSize, batchSizeVal, num_epoch, num_epochExt):
         s = self.build()
         loop = TrainLoop(s, self.lRate, self.seed)
-        s.reset_optimizer()
-        self.listY0_hat: List[float] = []
-        self.listY0: List[float] = []
-        self.lossList: List[float] = []
+        resumed, self._resumed = getattr(self, "_resumed", False), False
+        if not resumed:                    # one optimizer object per train() call (MFGSolvers.py:75) unless load() restored one
+            s.reset_optimizer()
+            self.listY0_hat: List[float] = []
+            self.listY0: List[float] = []
+            self.lossList: List[float] = []
         _, rank, _ = dist_info()
         draw = 0
 

@@ -51,7 +51,18 @@ struct Philox {
 };
 
 // stream ids of the counter's 4th word
-enum : uint32_t { STREAM_PATH = 0, STREAM_JMC = 1, STREAM_JUMPN = 2, STREAM_JMC_JUMPN = 3, STREAM_GAMMA = 4, STREAM_MFG = 5 };
+// Primary streams: the per-path increments, the compensator samples (word 0 = sample index), the MFG increments.  Every
+// secondary draw (a retry of a rejection sampler, the second block of a rare Merton jump) has its OWN named stream.
+enum : uint32_t {
+  STREAM_PATH = 0, STREAM_JMC = 1,
+  STREAM_PATH_RARE_JUMP = 2, STREAM_JMC_RARE_JUMP = 3,       // Merton: count >= 2 (sim_device.cuh: jump_size_rare)
+  STREAM_PATH_GAMMA_RETRY = 4, STREAM_JMC_GAMMA_RETRY = 5,   // VG: Marsaglia-Tsang rejections (sim_vg_kernel)
+  STREAM_MFG = 6, STREAM_MFG_POISSON_RETRY = 7               // MFG: PTRS rejections (poisson_any)
+};
+__host__ __device__ constexpr uint32_t rare_jump_stream(uint32_t s) { return s == STREAM_PATH ? STREAM_PATH_RARE_JUMP : STREAM_JMC_RARE_JUMP; }
+__host__ __device__ constexpr uint32_t gamma_retry_stream(uint32_t s) { return s == STREAM_PATH ? STREAM_PATH_GAMMA_RETRY : STREAM_JMC_GAMMA_RETRY; }
+static_assert(rare_jump_stream(STREAM_PATH) != rare_jump_stream(STREAM_JMC) && gamma_retry_stream(STREAM_PATH) != gamma_retry_stream(STREAM_JMC) &&
+              STREAM_MFG_POISSON_RETRY != STREAM_MFG && STREAM_MFG > STREAM_JMC_GAMMA_RETRY, "Philox stream ids must be distinct");
 
 __device__ __forceinline__ float u01_open(uint32_t x) {  // (0,1]
   return (float)((x >> 8) + 1u) * (1.0f / 16777216.0f);

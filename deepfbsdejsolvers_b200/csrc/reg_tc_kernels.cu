@@ -28,6 +28,9 @@
 //
 // Per path-step inputs come from the tile-major record written by the forward sweep (pricing.cuh: RecLayout): one base
 // pointer, immediate offsets, one bulk L2 prefetch per (tile, step).
+#ifndef FBSDEJ_ABLATE
+#define FBSDEJ_ABLATE 0   // timing experiments only (scripts/ablate_forward.sh): 1 no RNG math, 2 no coupling, 3 no tanh, 4 no MMA, 5 no X stores
+#endif
 #include "pricing.cuh"
 #include "sim_device.cuh"
 #include "tc.cuh"
@@ -325,15 +328,15 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
     if (started && pass == 0) {                        // lanes: D1 hi j, D1 lo 24 + j; columns: X hi i, X lo 16 + i
       for (int e = row; e < (nin + 1) * H; e += kThreads) {
         const int i = e / H, j = e % H;                // i = nin: b1
-        g[e] = S[j * SW + i] + S[j * SW + 16 + i] + S[(24 + j) * SW + i];
+        g[e] = (S[j * SW + i] + S[j * SW + 16 + i]) + (S[(24 + j) * SW + i] + S[(24 + j) * SW + 16 + i]);   // hi.hi + hi.lo + lo.hi + lo.lo
       }
     } else if (started) {                              // lanes: H1 hi 0..23, H2 hi 24..47, H1 lo 48..71, H2 lo 72..95
       for (int e = row; e < (H + 1) * H; e += kThreads) {
         const int k = e / H, j = e % H;                // k = H: b2
-        g[o2 + e] = S[k * SW + j] + S[k * SW + 24 + j] + S[(48 + k) * SW + j];
+        g[o2 + e] = (S[k * SW + j] + S[k * SW + 24 + j]) + (S[(48 + k) * SW + j] + S[(48 + k) * SW + 24 + j]);
       }
       if (row <= H)                                    // dW3[k] (k = H: b3) rides in column COL_DOUT of D2
-        g[o3 + row] = S[(24 + row) * SW + COL_DOUT] + S[(24 + row) * SW + 24 + COL_DOUT] + S[(72 + row) * SW + COL_DOUT];
+        g[o3 + row] = (S[(24 + row) * SW + COL_DOUT] + S[(24 + row) * SW + 24 + COL_DOUT]) + (S[(72 + row) * SW + COL_DOUT] + S[(72 + row) * SW + 24 + COL_DOUT]);
     }
   }
   tc::tc_fence_before();
@@ -376,6 +379,9 @@ constexpr int REGS_NET = 80, REGS_INC = 48;   // (80 + 48) * 128 threads = 64 * 
 template <int ACT>
 __device__ __forceinline__ float hidf(float x) {
   if (ACT != ACT_TANH) return fmaxf(x, 0.0f);
+#if FBSDEJ_ABLATE == 3
+  return 0.5f - 0.1f * x;
+#endif
   float t, r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + 1.0f));
@@ -487,7 +493,11 @@ __global__ void __launch_bounds__(2 * kThreads, 4) reg_forward_tc(const PricingA
       for (int i = 0; i < a.N; ++i, ++it) {
         const uint32_t s = it % NST;
         float E[D];
+#if FBSDEJ_ABLATE == 1
+        if constexpr (false) {
+#else
         if constexpr (RNG) {
+#endif
           // one Philox block per asset pair; the rare cells (a count >= 2, both draws jumping, a far-tail size: ~0.4 %) are
           // redone on the exact path after the branch-free common case of every pair, so that the pairs interleave
           constexpr int KP = (D + 1) / 2;
@@ -519,6 +529,11 @@ __global__ void __launch_bounds__(2 * kThreads, 4) reg_forward_tc(const PricingA
           }
 #pragma unroll
           for (int k = 0; k < D; ++k) E[k] = ex2_raw(E[k] + jj[k]);
+#if FBSDEJ_ABLATE == 1
+        } else if (true) {
+#pragma unroll
+          for (int k = 0; k < D; ++k) E[k] = 1.0f + 1e-3f * (float)k;
+#endif
         } else {
           const float* __restrict__ pw = a.dW + (size_t)i * D * sB + p;
           const float* __restrict__ pj = a.J + (size_t)i * D * sB + p;
@@ -586,16 +601,26 @@ __global__ void __launch_bounds__(2 * kThreads, 4) reg_forward_tc(const PricingA
       publish_net(hrows);
       if (warp == 0 && issuer) {
         tc::tc_fence_after();
+#if FBSDEJ_ABLATE != 4
         gemm_k_tf32<2>(tmem, tmem_a, sa(W1B_HI), sa(W1B_LO));
+#endif
         tc::mma_commit(bar);
       }
       // ---- independent of the network: closed-form coupling, record stores (in the shadow of the first MMA) ------------
+#if FBSDEJ_ABLATE == 2
+      float Ai = 0.2f, dAb = 0.5f;
+#else
       typename Model::AEval ae;
       Model::eval_A_begin(a, i, X, ae);                  // table loads in flight while the stores issue
+#endif
+#if FBSDEJ_ABLATE != 5
 #pragma unroll
       for (int k = 0; k < D; ++k) rs[(RL::P_X + k) * TR] = X[k];
+#endif
+#if FBSDEJ_ABLATE != 2
       float Ai, dAb;
       Model::eval_A_finish(a, i, ae, Ai, dAb);
+#endif
       rs[RL::P_DA * TR] = dAb;
       wait_mma();
       {
@@ -613,7 +638,9 @@ __global__ void __launch_bounds__(2 * kThreads, 4) reg_forward_tc(const PricingA
       publish_net(hrows);
       if (warp == 1 && issuer) {
         tc::tc_fence_after();
+#if FBSDEJ_ABLATE != 4
         gemm_k_tf32<3>(tmem, tmem_a, sa(W2B_HI), sa(W2B_LO));
+#endif
         tc::mma_commit(bar);
       }
       // ---- this step's exponentials from the ring (in the shadow of the second MMA) -------------------------------------

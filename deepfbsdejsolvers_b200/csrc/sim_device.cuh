@@ -23,7 +23,7 @@ static __device__ __noinline__ float jump_size_rare(uint32_t u, uint32_t t0, uin
     if (u < thr[k]) break;
     ++c;
   }
-  const uint4 s = Philox::rand4(gid, c1, iter, stream + 2u, k0, k1);
+  const uint4 s = Philox::rand4(gid, c1, iter, rare_jump_stream(stream), k0, k1);
   float e0, e1;
   box_muller(s.x, s.y, e0, e1);
   const float dn = (float)c;

@@ -17,7 +17,7 @@ namespace fbsdej {
 // the two Poisson counts by table inversion.  A count of 1 (the only frequent non-zero case: P = lam dt e^{-lam dt})
 // takes its jump size from the SAME uniform: conditional on thr[0] <= u < thr[1], (u - thr[0]) / (thr[1] - thr[0]) is
 // uniform with ~28 bits, mapped through the inverse normal CDF (branch-free polynomial, evaluated for every draw).
-// Only counts >= 2 (P ~ (lam dt)^2 / 2) and far-tail sizes go through jump_size_rare (a second Philox block, stream + 2).
+// Only counts >= 2 (P ~ (lam dt)^2 / 2) and far-tail sizes go through jump_size_rare (a second Philox block on its own stream, common.cuh).
 // Work split: a work unit = (step, asset pair, chunk of 256 groups of 4 consecutive paths); a persistent grid (4 CTAs per
 // SM) strides over the units, so the per-CTA set-up is paid once and the only integer divisions are per unit and uniform.
 // 128-bit stores.
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) sim_vg_kernel(const SimVGArgs a) {
       }
       if (have2) { x = x2; ua = ua2; have2 = false; }
       else {
-        const uint4 s = Philox::rand4(gid, (uint32_t)i | ((att / 2u + 1u) << 24), iter, a.stream + 4u, a.seed_lo, a.seed_hi);
+        const uint4 s = Philox::rand4(gid, (uint32_t)i | ((att / 2u + 1u) << 24), iter, gamma_retry_stream(a.stream), a.seed_lo, a.seed_hi);
         box_muller(s.x, s.y, x, x2);
         ua = u01_open(s.z); ua2 = u01_open(s.w);
         have2 = true;
@@ -146,7 +146,7 @@ __device__ float poisson_any(float mean, uint32_t u32a, uint32_t u32b, uint32_t 
     if (!(kf < 0.0f || (us < 0.013f && V > us))) {
       if (__logf(V) + __logf(invalpha) - __logf(aa / (us * us) + b) <= -mean + kf * loglam - lgammaf(kf + 1.0f)) return kf;
     }
-    const uint4 s = Philox::rand4(gid, c1 | ((att + 1u) << 24), iter, stream + 6u, k0, k1);
+    const uint4 s = Philox::rand4(gid, c1 | ((att + 1u) << 24), iter, STREAM_MFG_POISSON_RETRY, k0, k1);
     ua = s.x; ub = s.y;
   }
   return floorf(mean + 0.5f);

@@ -173,11 +173,18 @@ class NativeSolver:
             self.iteration.copy_(torch.from_numpy(np.asarray(sd["iteration"], dtype=np.int32)))
         self.ctx.sync()
 
+    @staticmethod
+    def checkpoint_path(path) -> str:
+        """np.savez appends '.npz' to a name without that suffix; save and load agree on the file actually written."""
+        path = str(path)
+        return path if path.endswith(".npz") else path + ".npz"
+
     def save_checkpoint(self, path: str, **extra) -> None:
-        np.savez(path, **self.state_dict(), **{k: np.asarray(v) for k, v in extra.items()})
+        with open(self.checkpoint_path(path), "wb") as f:
+            np.savez(f, **self.state_dict(), **{k: np.asarray(v) for k, v in extra.items()})
 
     def load_checkpoint(self, path: str) -> dict:
-        with np.load(path) as z:
+        with np.load(self.checkpoint_path(path)) as z:
             sd = {k: z[k] for k in z.files}
         self.load_state_dict(sd)
         return sd

@@ -157,7 +157,10 @@ class PricingSolverBase:
             sb = self.netB.spec() if self.TWO_NET else spec
             jtc_ok = sb.H <= 22 and spec.H <= 23 and sb.L == 2 and sb.activation == "tanh"
         auto = tc_ok or jtc_ok
-        use_tc = auto if self.tensor_cores is None else (bool(self.tensor_cores) and (tc_ok or jtc_ok))
+        if self.tensor_cores and not auto:
+            raise ValueError(f"{type(self).__name__}: tensor_cores=True, but the tcgen05 kernels cover two hidden layers of width <= 22 "
+                             f"(tanh for the jump schemes) at d in (1, 10); got d={d}, first network {spec}")
+        use_tc = auto if self.tensor_cores is None else bool(self.tensor_cores)
         self.native = mm.make_solver(self.SCHEME, [n.spec() for n in nets], n_y0, M, ctx=self.ctx,
                                      stale_time=self.stale_time, tensor_cores=use_tc)
         self.push_params()
@@ -196,9 +199,11 @@ class PricingSolverBase:
     def train(self, batchSize, batchSizeVal, num_epoch, num_epochExt):
         s = self.build()
         loop = TrainLoop(s, self.lRate, self.seed)
-        s.reset_optimizer()
-        self.listY0: List[float] = []
-        self.lossList: List[float] = []
+        resumed, self._resumed = getattr(self, "_resumed", False), False
+        if not resumed:                    # a fresh optimizer per train() call (SolversJumpDiff.py:55) - unless load() just
+            s.reset_optimizer()            # restored Adam's m, v, t and the Philox iteration: then training continues bit-exactly
+            self.listY0: List[float] = []
+            self.lossList: List[float] = []
         self.duration = 0
         self.durationList: List[float] = []
         B, Bval = self.TRAIN_MULT * batchSize, self.VAL_MULT * batchSizeVal
@@ -226,6 +231,7 @@ class PricingSolverBase:
         self.seed = int(sd.get("seed", self.seed))
         self.listY0 = [np.float32(x) for x in sd.get("listY0", [])]
         self.lossList = [float(x) for x in sd.get("lossList", [])]
+        self._resumed = True               # the next train() keeps the restored optimizer state
         self.pull_params()
 
     def _result(self):

@@ -16,6 +16,7 @@ from __future__ import annotations
 import importlib.util
 import os
 import sys
+import zlib
 
 import numpy as np
 import torch
@@ -102,7 +103,7 @@ class Recorder:
 
 def pricing_case(kind, scheme):
     torch.manual_seed(0)
-    tf.random.seed(1000 + hash((kind, scheme)) % 1000)
+    tf.random.seed(1000 + zlib.crc32(f"{kind}/{scheme}".encode()) % 1000)   # (hash() of a str is salted per process)
     tf.keras.initializers.GEN.manual_seed(7 + len(scheme))
     tf.GradientTape.LOG.clear()
     merton = kind == "merton"
@@ -218,6 +219,25 @@ def mfg_case(scheme, couplage="ON"):
     tf.random.normal, model.dN = normal, dN
     solver.train(B, 1, 1, 1)
     tf.random.normal = orig_normal
+    if couplage == "OFF":
+        # MFGSolvers.py:92-115: one Adam step on the projected player's loss (variables of model_hat), a validation pass,
+        # then one step on the individual player's loss (variables of model) with the SAME optimizer object (t = 2)
+        N, sq = model.N, np.float32(np.sqrt(model.dt))
+        out = dict(kind="mfg", scheme=scheme, couplage="OFF", B=B, N=N, lr=lr, QAver=Q, theta0=theta0, theta2=theta(),
+                   Y0_hat_report=np.float32(solver.listY0_hat[0]), Y0_report=np.float32(solver.listY0[0]),
+                   **{k: np.float64(v) for k, v in par.items()})
+        for ph, call in ((1, 0), (2, 2)):            # optimizeBSDE calls: train-hat, validation, train-ind, validation
+            loss, grads, trained = tf.GradientTape.LOG[ph - 1]
+            lookup = {id(v): g for v, g in zip(trained, grads)}
+            g = [flat_grads(km.model_hat, trained, grads), flat_grads(km.model, trained, grads)]
+            if scheme == "Global":
+                gy = [lookup.get(id(km.model_hat.Y0_hat)), lookup.get(id(km.model.Y0))]
+                g.append(np.array([0.0 if x is None else float(x.numpy()) for x in gy], dtype=np.float32))
+            gs, ds = gauss[2 * N * call:2 * N * (call + 1)], dNs[N * call:N * (call + 1)]
+            out.update({f"p{ph}_loss": np.float64(loss), f"p{ph}_grad": np.concatenate(g).astype(np.float32),
+                        f"p{ph}_dW0": (sq * torch.stack(gs[0::2], 0)).numpy(), f"p{ph}_dW": (sq * torch.stack(gs[1::2], 0)).numpy(),
+                        f"p{ph}_dN": torch.stack(ds, 0).numpy()})
+        return out
     loss, grads, trained = tf.GradientTape.LOG[0]
     lookup = {id(v): g for v, g in zip(trained, grads)}
     g = [flat_grads(km.model_hat, trained, grads), flat_grads(km.model, trained, grads)]
@@ -246,6 +266,11 @@ def main():
             d = mfg_case(scheme)
         np.savez_compressed(os.path.join(HERE, f"mfg_{scheme}.npz"), **d)
         print("mfg", scheme, "loss", float(d["loss"]), "Y0_hat", float(d["Y0_hat_report"]), "Y0", float(d["Y0_report"]))
+    for scheme in ("Global", "SumLocalReg"):      # couplage OFF (the other OFF variants crash in the reference: MFGSolvers.py:291,431)
+        with contextlib.redirect_stdout(io.StringIO()):
+            d = mfg_case(scheme, couplage="OFF")
+        np.savez_compressed(os.path.join(HERE, "off", f"mfg_{scheme}_OFF.npz"), **d)
+        print("mfg OFF", scheme, "losses", float(d["p1_loss"]), float(d["p2_loss"]), "Y0_hat", float(d["Y0_hat_report"]), "Y0", float(d["Y0_report"]))
 
 
 if __name__ == "__main__":

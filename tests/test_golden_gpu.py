@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import helpers as H
-from test_oracle_golden import load_case, CASES
+from test_oracle_golden import load_case, CASES, OFF_CASES, off_masks
 
 pytestmark = pytest.mark.gpu
 
@@ -19,15 +19,51 @@ def planes(a):
     return np.ascontiguousarray(a[:, None, :])
 
 
+MFG_KEYS = ("T", "R0", "jumpFactor", "alpha", "beta", "coeffOU", "A", "K", "pi", "p0", "p1", "f0", "f1", "theta", "C", "S0", "h1",
+            "h2", "sig0", "sig", "alphaTarget", "coeffEqui")
+
+
+@pytest.mark.parametrize("tensor_cores", (False, True), ids=("ffma", "tcgen05"))
+@pytest.mark.parametrize("path", OFF_CASES, ids=[os.path.basename(p)[:-4] for p in OFF_CASES])
+def test_cuda_reproduces_reference_couplage_off(ctx, path, tensor_cores):
+    """couplage = 'OFF' two-phase training (MFGSolvers.py:92-115) against the reference's own outputs: objective weights (1, 0)
+    then (0, 1), masked Keras-form Adam with the step counter carried over."""
+    c = load_case(path)
+    scheme, B = str(c["scheme"]), int(c["B"])
+    layout = H.mfg_layout(scheme)
+    s = H.native_mfg(ctx, dict(QAver=c["QAver"], jumpModel="stochastic", **{k: c[k] for k in MFG_KEYS}), scheme, layout,
+                     tensor_cores=tensor_cores)
+    s.set_theta(c["theta0"])
+    s.reset_optimizer()
+    hat, ind = off_masks(layout, scheme)
+    for ph, mask, w in ((1, hat, (1.0, 0.0)), (2, ind, (0.0, 1.0))):
+        s.set_weights(*w)
+        s.set_noise(B, c[f"p{ph}_dW0"], c[f"p{ph}_dW"], c[f"p{ph}_dN"])
+        out = s.grad(B)
+        ref = c[f"p{ph}_loss"]
+        assert abs(out[0] - ref) <= 2e-5 * abs(ref), (ph, out[0], ref)
+        g_ref = c[f"p{ph}_grad"].astype(np.float64)
+        err = np.abs(out[4:] * mask - g_ref).max() / np.abs(g_ref).max()
+        assert err < (5e-5 if tensor_cores else 2e-5), f"phase {ph} gradient: rel-to-max error {err:.2e}"
+        s.adam_step(float(c["lr"]), mask=ctx.to_device(mask))
+    th = s.get_theta()
+    solid = (np.abs(c["p1_grad"]) > 1e-3 * np.abs(c["p1_grad"]).max()) | (np.abs(c["p2_grad"]) > 1e-3 * np.abs(c["p2_grad"]).max())
+    np.testing.assert_allclose(th[solid], c["theta2"][solid], rtol=0, atol=float(c["lr"]) * 2e-2)
+    frozen = (hat + ind) == 0
+    assert np.array_equal(th[frozen], c["theta0"][frozen])
+
+
+@pytest.mark.parametrize("tensor_cores", (False, True), ids=("ffma", "tcgen05"))
 @pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
-def test_cuda_reproduces_reference_step(ctx, path):
+def test_cuda_reproduces_reference_step(ctx, path, tensor_cores):
     c = load_case(path)
     kind, scheme, B = str(c["kind"]), str(c["scheme"]), int(c["B"])
     if kind == "mfg":
         keys = ("T", "R0", "jumpFactor", "alpha", "beta", "coeffOU", "A", "K", "pi", "p0", "p1", "f0", "f1", "theta", "C", "S0", "h1",
                 "h2", "sig0", "sig", "alphaTarget", "coeffEqui")
         layout = H.mfg_layout(scheme)
-        s = H.native_mfg(ctx, dict(QAver=c["QAver"], jumpModel="stochastic", **{k: c[k] for k in keys}), scheme, layout)
+        s = H.native_mfg(ctx, dict(QAver=c["QAver"], jumpModel="stochastic", **{k: c[k] for k in keys}), scheme, layout,
+                         tensor_cores=tensor_cores)
         s.set_theta(c["theta0"])
         s.set_noise(B, c["dW0"], c["dW"], c["dN"])
     else:
@@ -36,14 +72,19 @@ def test_cuda_reproduces_reference_step(ctx, path):
                                  ("T", "r", "theta", "kappa", "sigmaJ", "K", "x0"))}
         par["N"] = int(c["N"])
         M = 0 if scheme.endswith("Reg") else c["JMC"].shape[1]
-        s = H.native_pricing(ctx, kind, par, scheme, layout, d=1, M=M)
+        s = H.native_pricing(ctx, kind, par, scheme, layout, d=1, M=M, tensor_cores=tensor_cores)
         s.set_theta(c["theta0"])
         s.set_noise(B, planes(c["dW"]) if "dW" in c else None, planes(c["J"]), planes(c["JMC"]) if "JMC" in c else None)
     out = s.grad(B)
     assert abs(out[0] - c["loss"]) <= 2e-5 * abs(c["loss"]), (out[0], c["loss"])
     g_ref = c["grad"].astype(np.float64)
     err = np.abs(out[4:] - g_ref).max() / np.abs(g_ref).max()
-    assert err < 1e-4, f"gradient: rel-to-max error {err:.2e}"
+    print(f"{kind} {scheme} {'tcgen05' if tensor_cores else 'ffma'}: loss rel {abs(out[0] - c['loss']) / abs(c['loss']):.1e}, "
+          f"gradient {err:.1e} of max")
+    # tcgen05: 5e-5 for the compensator-free and MFG kernels; the jump schemes carry the cancellation between the own-jump row and
+    # the compensator rows through bf16x3 products (tests/test_tc_gpu.py: JUMP_TC_GRAD_TOL)
+    jump = kind != "mfg" and not scheme.endswith("Reg")
+    assert err < ((3e-4 if jump else 5e-5) if tensor_cores else 2e-5), f"gradient: rel-to-max error {err:.2e}"
     s.adam_step(float(c["lr"]))
     th = s.get_theta()
     solid = np.abs(g_ref) > 1e-3 * np.abs(g_ref).max()

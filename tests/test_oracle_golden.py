@@ -109,6 +109,51 @@ def test_oracle_reproduces_reference_step(path):
         assert abs(y0 - case["Y0_report"]) < 2e-6
 
 
+OFF_CASES = sorted(glob.glob(os.path.join(GOLD, "off", "*.npz")))
+
+
+def off_masks(layout, scheme):
+    """Variables handed to apply_gradients in the two phases of couplage 'OFF' (MFGSolvers.py:50-64)."""
+    n0 = layout.offsets[1]
+    hat, ind = np.zeros(layout.total, np.float32), np.zeros(layout.total, np.float32)
+    hat[:n0] = 1
+    ind[n0:layout.y0_offset] = 1
+    if scheme == "Global":
+        hat[layout.y0_offset] = 1
+        ind[layout.y0_offset + 1] = 1
+    return hat, ind
+
+
+@pytest.mark.parametrize("path", OFF_CASES, ids=[os.path.basename(p)[:-4] for p in OFF_CASES])
+def test_oracle_reproduces_reference_couplage_off(path):
+    """couplage = 'OFF' (MFGSolvers.py:92-115): a step on the projected player's loss over model_hat's variables, then a step on
+    the individual player's loss over model's variables with the SAME optimizer object - the step counter carries over (t = 2
+    in the second bias correction) while the slots of the second group start from zero."""
+    c = load_case(path)
+    assert len(OFF_CASES) == 2
+    scheme, B = str(c["scheme"]), int(c["B"])
+    om, layout = oracle_of(c)
+    hat, ind = off_masks(layout, scheme)
+    th = torch.tensor(c["theta0"].copy())
+    opt = KerasAdam(layout.total, float(c["lr"]))
+    for ph, mask, pick in ((1, hat, 0), (2, ind, 1)):
+        t = th.clone().requires_grad_(True)
+        nz = {k: torch.tensor(c[f"p{ph}_{k}"]) for k in ("dW0", "dW", "dN")}
+        loss = mfg_loss(om, scheme, layout, t, nz, B)[pick]
+        loss.backward()
+        assert abs(float(loss.detach()) - c[f"p{ph}_loss"]) <= 2e-5 * abs(c[f"p{ph}_loss"])
+        g_ref = c[f"p{ph}_grad"].astype(np.float64)
+        err = np.abs(t.grad.numpy() * mask - g_ref).max() / np.abs(g_ref).max()
+        assert err < 5e-5, f"phase {ph} gradient: rel-to-max error {err:.2e}"
+        opt.step(th, torch.tensor(c[f"p{ph}_grad"]), torch.tensor(mask))
+    np.testing.assert_allclose(th.numpy(), c["theta2"], rtol=0, atol=2e-7)
+    # with a fresh optimizer for the second phase (t = 1 instead of 2) the second group's update differs: the carry-over matters
+    th_bad = torch.tensor(c["theta0"].copy())
+    KerasAdam(layout.total, float(c["lr"])).step(th_bad, torch.tensor(c["p1_grad"]), torch.tensor(hat))
+    KerasAdam(layout.total, float(c["lr"])).step(th_bad, torch.tensor(c["p2_grad"]), torch.tensor(ind))
+    assert np.abs(th_bad.numpy() - c["theta2"]).max() > 1e-5
+
+
 def test_merton_closed_form_known_answers():
     om = MertonOracle(aLin=0.1, limit=30, d=1, dtype=torch.float64, **H.MERTON)
     assert abs(float(om.A(0, om.init(1))[0]) - 0.2714569268) < 1e-9

@@ -50,17 +50,17 @@ from oracle import MertonOracle, VGOracle
 
 def _check(s, B, l64, g64, g32, aux64, d):
     out, tx, ty, _ = s.loss(B, traj=True)
-    assert abs(out[0] - l64) <= 2e-5 * abs(l64), (out[0], l64)
+    assert abs(out[0] - l64) <= 1e-5 * abs(l64), (out[0], l64)
     X = aux64["X"].transpose(0, 2, 1)
     assert np.abs(tx - X).max() <= 2e-6 + 1e-5 * np.abs(X).max()
     Y = aux64["Y"]
     assert np.abs(ty[:Y.shape[0]] - Y).max() <= 4e-6 + 1e-5 * np.abs(Y).max()
     g = s.grad(B)
-    assert abs(g[0] - l64) <= 2e-5 * abs(l64)
+    assert abs(g[0] - l64) <= 1e-5 * abs(l64)
     scale = np.abs(g64).max()
     e_gpu, e_32 = np.abs(g[4:] - g64).max() / scale, np.abs(g32 - g64).max() / scale
     print("loss rel", abs(out[0] - l64) / abs(l64), "grad rel-to-max", e_gpu, "(fp32 oracle", e_32, ")")
-    assert e_gpu <= 2e-4, f"gradient error {e_gpu:.3e}"
+    assert e_gpu <= 5e-5, f"gradient error {e_gpu:.3e}"
 
 
 @pytest.mark.parametrize("scheme", ["SumLocalReg", "MultiStepReg"])
@@ -132,28 +132,35 @@ def test_mfg_tensor_core_path_matches_oracle(ctx, scheme, jumpModel, B):
     s.set_theta(theta)
     s.set_noise(B, noise["dW0"].numpy(), noise["dW"].numpy(), noise["dN"].numpy())
     out, tx, ty, _ = s.loss(B, traj=True)
-    assert abs(out[1] - lh64) <= 3e-5 * abs(lh64) and abs(out[2] - li64) <= 3e-5 * abs(li64), (out, lh64, li64)
+    assert abs(out[1] - lh64) <= 1e-5 * abs(lh64) and abs(out[2] - li64) <= 1e-5 * abs(li64), (out, lh64, li64)
     assert np.abs(tx[:, 0, :] - aux64["hS"]).max() <= 2e-5 and np.abs(tx[:, 1, :] - aux64["S"]).max() <= 2e-5
     g = s.grad(B)
     scale = np.abs(g64).max()
     e_gpu, e_32 = np.abs(g[4:] - g64).max() / scale, np.abs(g32 - g64).max() / scale
     print(scheme, jumpModel, "loss rel", abs(out[0] - lh64 - li64) / abs(lh64 + li64), "grad rel-to-max", e_gpu, "(fp32 oracle", e_32, ")")
-    assert e_gpu <= 3e-4, f"gradient error {e_gpu:.3e}"
+    assert e_gpu <= 5e-5, f"gradient error {e_gpu:.3e}"
+
+
+# Gradient bound of the jump schemes on tcgen05: the parameter gradient of the jump network is Ybar (dG(own jump) - mean_m dG(sample m)),
+# a difference of two nearly equal sums (VG: |h_own - mean h| ~ 0.05 |h|), so the 2^-17 relative rounding of the bf16x3 products
+# is amplified ~20x: measured up to 2.3e-4 of the largest component (VG Global, 24 paths x 300 samples), 1e-6 on the fp32 FFMA
+# kernels (mma_mode = 0).  Losses and trajectories keep 1e-5.
+JUMP_TC_GRAD_TOL = 3e-4
 
 
 def _check_jump(s, B, l64, g64, g32, aux64, has_z):
     out, tx, ty, tz = s.loss(B, traj=True)
-    assert abs(out[0] - l64) <= 2e-5 * abs(l64), (out[0], l64)
+    assert abs(out[0] - l64) <= 1e-5 * abs(l64), (out[0], l64)
     X = aux64["X"][:, :, 0]
     assert np.abs(tx[:, 0, :] - X).max() <= 2e-6 + 1e-5 * np.abs(X).max()
     Y = aux64["Y"]
     assert np.abs(ty[:Y.shape[0]] - Y).max() <= 4e-6 + 1e-5 * np.abs(Y).max()
     g = s.grad(B)
-    assert abs(g[0] - l64) <= 2e-5 * abs(l64)
+    assert abs(g[0] - l64) <= 1e-5 * abs(l64)
     scale = np.abs(g64).max()
     e_gpu, e_32 = np.abs(g[4:] - g64).max() / scale, np.abs(g32 - g64).max() / scale
     print("loss rel", abs(out[0] - l64) / abs(l64), "grad rel-to-max", e_gpu, "(fp32 oracle", e_32, ")")
-    assert e_gpu <= 3e-4, f"gradient error {e_gpu:.3e}"
+    assert e_gpu <= JUMP_TC_GRAD_TOL, f"gradient error {e_gpu:.3e}"
 
 
 @pytest.mark.parametrize("scheme", ["Global", "MultiStep1", "MultiStep2", "SumLocal1", "SumLocal2"])
@@ -205,14 +212,14 @@ def test_jump_network_on_tensor_cores_merton_d10(ctx, scheme, B, M):
     s.set_theta(theta)
     s.set_noise(B, H.to_planes(noise["dW"]), H.to_planes(noise["J"]), H.to_planes(noise["JMC"]))
     out, tx, ty, tz = s.loss(B, traj=True)
-    assert abs(out[0] - l64) <= 2e-5 * abs(l64), (out[0], l64)
+    assert abs(out[0] - l64) <= 1e-5 * abs(l64), (out[0], l64)
     X = aux64["X"].transpose(0, 2, 1)
     assert np.abs(tx - X).max() <= 2e-6 + 1e-5 * np.abs(X).max()
     g = s.grad(B)
     scale = np.abs(g64).max()
     e_gpu, e_32 = np.abs(g[4:] - g64).max() / scale, np.abs(g32 - g64).max() / scale
     print("loss rel", abs(out[0] - l64) / abs(l64), "grad rel-to-max", e_gpu, "(fp32 oracle", e_32, ")")
-    assert e_gpu <= 3e-4, f"gradient error {e_gpu:.3e}"
+    assert e_gpu <= JUMP_TC_GRAD_TOL, f"gradient error {e_gpu:.3e}"
 
 
 def test_jump_network_on_tensor_cores_one_path_per_thread(ctx):

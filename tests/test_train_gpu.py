@@ -202,3 +202,88 @@ def test_mfg_graph_replay_equals_stepwise_calls(ctx):
     ta, tb = a.get_theta(), b.get_theta()
     assert np.isfinite(ta).all() and np.abs(ta - theta).max() > 0
     assert np.abs(ta - tb).max() <= 1e-7 * max(1.0, np.abs(tb).max())
+
+
+def _pricing_solver(ctx, seed=5):
+    from deepfbsdejsolvers_b200 import coupledPricing as cp, set_seed
+    set_seed(seed)
+    M = H.MERTON
+    mm = cp.MertonJumpModel(M["T"], 8, M["r"], M["muJ"], M["sigmaJ"], M["sigma"], M["lam"], M["K"], M["x0"], cp.AbsCoupling(H.ALIN), 30)
+    s = cp.SolverGlobalSumLocalReg(mm, cp.Net(0, 1, [21, 21], "tanh"), cp.Net(0, 1, [21, 21], "tanh"), 1e-3, ctx=ctx)
+    s.build()                  # (the networks draw their initial weights here: right after set_seed)
+    return s
+
+
+def _mfg_solver(ctx, couplage="ON", cls="SolverGlobalFBSDE", seed=6):
+    from deepfbsdejsolvers_b200 import coupledMFG as cm, set_seed
+    set_seed(seed)
+    p = H.mfg_params(1)
+    mm = cm.ModelCoupledFBSDE(**p)
+    glob = cls == "SolverGlobalFBSDE"
+    km = cm.kerasModels(cm.Net_hat, cm.Net, "Global" if glob else "SumLocalReg", 2 if glob else 1, 3 if glob else 1, [20, 20], [22, 22],
+                        "tanh", "tanh")
+    s = getattr(cm, cls)(mm, km, 1e-3, couplage, ctx=ctx)
+    s.build()
+    return s
+
+
+@pytest.mark.parametrize("kind", ["pricing", "mfg"])
+def test_class_level_save_load_train_equals_uninterrupted_train(ctx, tmp_path, kind):
+    """Solver.save -> a new Solver.load -> train continues with the restored Adam m, v, t and Philox iteration: the same
+    parameters, bit for bit, as one uninterrupted train() (the reference keeps nothing on disk).  A name without
+    the .npz suffix works on both sides."""
+    make = _pricing_solver if kind == "pricing" else _mfg_solver
+    full, first, second = make(ctx), make(ctx), make(ctx)
+    full.train(1 if kind == "pricing" else 32, 2, 3, 4)
+    first.train(1 if kind == "pricing" else 32, 2, 3, 2)
+    ck = str(tmp_path / "ck")                      # no suffix
+    first.save(ck)
+    second.load(ck)
+    second.train(1 if kind == "pricing" else 32, 2, 3, 2)
+    assert np.array_equal(full.native.get_theta(), second.native.get_theta())
+    assert len(second.listY0) == 4 and np.array_equal(np.array(full.listY0), np.array(second.listY0))
+    # a train() that does NOT follow a load() starts a fresh optimizer, as the reference does (SolversJumpDiff.py:55)
+    second.train(1 if kind == "pricing" else 32, 2, 1, 1)
+    assert int(ctx.to_host(second.native.t).numpy()[0]) == 1
+
+
+@pytest.mark.parametrize("cls", ["SolverGlobalFBSDE", "SolverGlobalSumLocalReg"])
+def test_mfg_couplage_off_class_training(ctx, cls):
+    """couplage = 'OFF' through the drop-in class (MFGSolvers.py:92-115): phase 1 updates only model_hat's variables on the
+    projected player's loss, phase 2 only model's on the individual player's loss, one Adam step counter over both phases -
+    the same parameters as the two phases driven by hand through the C-ABI."""
+    B, ne, next_ = 32, 3, 2
+    s = _mfg_solver(ctx, "OFF", cls)
+    s.build()
+    theta0 = s.native.get_theta().copy()
+    s.train(B, 8, ne, next_)
+    th = s.native.get_theta()
+    assert int(ctx.to_host(s.native.t).numpy()[0]) == 2 * ne * next_          # the counter carried over
+    assert len(s.listY0_hat) == next_ and len(s.listY0) == next_
+    ref = _mfg_solver(ctx, "OFF", cls)
+    n = ref.build()
+    assert np.array_equal(n.get_theta(), theta0)
+    n.reset_optimizer()
+    for w, which in (((1.0, 0.0), "hat"), ((0.0, 1.0), "ind")):
+        n.set_weights(*w)
+        n.train_steps(ref.seed, B, ne * next_, ref.lRate, mask=ref._mask(which))
+        ctx.sync()
+        if which == "hat":
+            mid = n.get_theta()
+            ind = ref._mask("ind").cpu().numpy() > 0
+            assert np.array_equal(mid[ind], theta0[ind]) and np.abs(mid - theta0).max() > 0
+    assert np.array_equal(n.get_theta(), th)
+    hat = ref._mask("hat").cpu().numpy() > 0
+    assert np.array_equal(th[hat], mid[hat])                                   # phase 2 left model_hat alone
+
+
+def test_tensor_cores_true_on_an_unsupported_shape_raises(ctx):
+    from deepfbsdejsolvers_b200 import coupledPricing as cp, coupledMFG as cm
+    M = H.MERTON
+    mm = cp.MertonJumpModel(M["T"], 8, M["r"], M["muJ"], M["sigmaJ"], M["sigma"], M["lam"], M["K"], M["x0"], cp.AbsCoupling(H.ALIN), 30)
+    with pytest.raises(ValueError):
+        cp.SolverGlobalSumLocalReg(mm, cp.Net(0, 1, [40, 40], "tanh"), cp.Net(0, 1, [40, 40], "tanh"), 1e-3, ctx=ctx, tensor_cores=True).build()
+    mfg = cm.ModelCoupledFBSDE(**H.mfg_params(1))
+    km = cm.kerasModels(cm.Net_hat, cm.Net, "SumLocalReg", 1, 1, [30, 30], [30, 30], "tanh", "tanh")
+    with pytest.raises(ValueError):
+        cm.SolverGlobalSumLocalReg(mfg, km, 1e-3, "ON", ctx=ctx, tensor_cores=True).build()
