@@ -5,8 +5,13 @@
     python bench.py --impl reference --gpus N --steps K ...  # reference-equivalent CPU path (torch restatement)
 
 A "step" = one training iteration of the workload: simulate increments -> forward -> adjoint -> reduce ->
-(all-reduce) -> Adam.  Workload (config.workload): Merton d=10 geometric basket, N=100 time steps, H=21 tanh nets,
-SolverGlobalSumLocalReg (B = 2^16 paths on one GPU; config 5: B = 2^20 paths sharded over N>1 GPUs).
+(exchange) -> Adam.  Workloads (config.workload):
+  default     SURVEY 8d config 3 per GPU: Merton d=10 geometric basket, N=100 time steps, H=21 tanh nets, SolverGlobalSumLocalReg,
+              2^16 paths on EVERY GPU (weak scaling: the global batch is N x 2^16; N = 1 is config 3 itself), so that the
+              1 -> 8 GPU curve compares like with like whichever way the N = 1 point is launched
+  --config 5  the same model at a fixed global batch of 2^20 paths sharded over the N GPUs (strong scaling; N = 1 fits: 9.6 GB)
+  --config 1 | 2 | 4   the reference's own defaults (mainMerton.py, mainVG.py, mainMFGComparison.py) through the drop-in classes
+              on one GPU: metric = training iterations/s (path-steps/s beside it); --solver picks the solver class
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -25,6 +30,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "scripts"))
 
 MERTON = dict(T=1.0, N=100, r=0.1, muJ=0.0, sigmaJ=0.2, sigma=0.3, lam=3.0, K=0.9, x0=1.0)
 D, H_WIDTH, LIMIT, ALIN, LR = 10, 21, 100, 0.1, 3e-4
@@ -37,8 +43,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--paths", type=int, default=0, help="global Monte-Carlo batch (default 2^16 on 1 GPU, 2^20 on N>1)")
-    ap.add_argument("--solver", default="SumLocalReg", choices=list(SOLVERS))
+    ap.add_argument("--config", type=int, default=3, choices=[1, 2, 3, 4, 5],
+                    help="SURVEY 8d configuration (default 3: 2^16 paths per GPU; 5: 2^20 paths in total; 1 / 2 / 4: reference defaults)")
+    ap.add_argument("--paths", type=int, default=0, help="global Monte-Carlo batch (default 2^16 per GPU; --config 5: 2^20)")
+    ap.add_argument("--solver", default="", help="configs 3 / 5: SumLocalReg (default), MultiStepReg, Global; configs 1 / 2 / 4: a "
+                                                 "solver class name of the reference (default SolverGlobalFBSDE)")
     ap.add_argument("--M", type=int, default=-1, help="compensator samples for --solver Global (default 256)")
     ap.add_argument("--cpu-paths", type=int, default=0,
                     help="paths of the bounded CPU sample per step (0 = automatic: 16384 for the cpu_baseline leg; for --impl "
@@ -50,12 +59,21 @@ def parse():
     return ap.parse_args()
 
 
+def global_batch(a, world):
+    """Default: 2^16 paths per GPU (config 3 on every GPU, weak scaling); --config 5: 2^20 paths in total (strong scaling)."""
+    if a.paths:
+        return a.paths
+    return 2 ** 20 if a.config == 5 else 2 ** 16 * world
+
+
 def workload_config(a, B, world):
     M = SOLVERS[a.solver] if a.M < 0 else a.M
-    name = ("Merton d=10 geometric basket, N=100, H=21 tanh, Solver%s%s, B=%d paths (SURVEY 8d config %s)"
-            % ("Global" + a.solver if a.solver.endswith("Reg") else a.solver + "FBSDE", "" if M == 0 else " M=%d" % M, B,
-               "3" if world == 1 else "5"))
-    return M, {"workload": name, "paths": B, "time_steps": MERTON["N"], "d": D, "hidden": H_WIDTH, "solver": a.solver,
+    which = ("config 5: fixed global batch, sharded" if a.config == 5 else
+             "config 3" if world == 1 else "config 3 on every GPU: %d x %d paths" % (world, B // world))
+    name = ("Merton d=10 geometric basket, N=100, H=21 tanh, Solver%s%s, B=%d paths (SURVEY 8d %s)"
+            % ("Global" + a.solver if a.solver.endswith("Reg") else a.solver + "FBSDE", "" if M == 0 else " M=%d" % M, B, which))
+    return M, {"workload": name, "paths": B, "paths_per_gpu": B // world, "time_steps": MERTON["N"], "d": D, "hidden": H_WIDTH,
+               "solver": a.solver,
                "compensator_M": M, "mma": a.mma, "parallelism": "dp%d" % world,
                "l2_policy": "working set exceeds L2: %.0f MB of per-path-step records per rank are written by the forward sweep and "
                             "read back by the adjoint every step (126 MB L2); no flush needed"
@@ -136,19 +154,13 @@ def run_reference(a):
     if rank != 0:
         return
     import torch
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm uses every host core whichever way it is launched
+    torch.set_num_threads(os.cpu_count() or 1)
     world = int(os.environ.get("WORLD_SIZE", str(a.gpus)))
-    B = a.paths or (2 ** 16 if world == 1 else 2 ** 20)
+    B = global_batch(a, world)
     M, cfg = workload_config(a, B, world)
-    cpu_paths = a.cpu_paths
-    if cpu_paths <= 0:                       # size the sample from one probe iteration: ~120 s for warm-up + K steps
-        probe = cpu_iteration_factory(a, M, 2048)
-        probe()
-        t0 = time.perf_counter()
-        probe()
-        t_probe = time.perf_counter() - t0
-        cpu_paths = 2048
-        while cpu_paths * 2 <= min(B, 65536) and (a.steps + 1) * t_probe * (cpu_paths * 2 / 2048) <= 120.0:
-            cpu_paths *= 2
+    # the same bounded sample at every N (the restatement's throughput depends on the sample size, not on the batch it stands for)
+    cpu_paths = a.cpu_paths if a.cpu_paths > 0 else 16384
     it = cpu_iteration_factory(a, M, cpu_paths)
     for _ in range(max(1, min(a.warmup, 1))):
         it()
@@ -161,7 +173,7 @@ def run_reference(a):
     print(json.dumps({
         "impl": "reference", "metric": "path-steps/s", "value": val, "unit": "path-steps/s", "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": dt * 1e3, "iters_per_s_equiv": val / (B * MERTON["N"]), "higher_is_better": True,
-        "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+        "scaling": "strong" if a.config == 5 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": val, "unit": "path-steps/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "path-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference-equivalent CPU restatement (torch eager), not TensorFlow"}))
@@ -182,7 +194,7 @@ def run_native(a):
     from deepfbsdejsolvers_b200.solver_base import shard, attach_peers
     import deepfbsdejsolvers_b200._lib as L
 
-    B = a.paths or (2 ** 16 if world == 1 else 2 ** 20)
+    B = global_batch(a, world)
     M, cfg = workload_config(a, B, world)
     off, Bl = shard(B, rank, world)
     ctx = Context.default(local)
@@ -259,7 +271,8 @@ def run_native(a):
     # The step's Brownian / jump increments live in pinned host memory; a copy stream uploads step k+1 into the other
     # device buffer while step k computes (both inside the timed region), the loss comes back to the host every step.
     e2e, e2e_rng = None, None
-    if not a.no_e2e:
+    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+    if not a.no_e2e and world == 1:
         nfl = N * D * Bl
         # one step's increments in pinned host memory (synthetic; the same block is uploaded for every step): Brownian planes
         # dense, compound-Poisson jump planes as their non-zero entries - exactly 0 wherever no jump fell into the step
@@ -272,7 +285,6 @@ def run_native(a):
         jval_h = (torch.randn(nnz, dtype=torch.float32, generator=gen) * MERTON["sigmaJ"] + MERTON["muJ"]).pin_memory()
         del hit
         dev = [[ctx.empty(nfl), ctx.empty(max(nnz, 1), dtype=torch.int32), ctx.empty(max(nnz, 1))] for _ in range(2)]
-        loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
         jmc = ctx.zeros(N * D * max(M, 1)) if M > 0 else None
         copy_stream = torch.cuda.Stream(ctx.device)
         up = [torch.cuda.Event(), torch.cuda.Event()]        # upload of buffer b finished
@@ -320,6 +332,7 @@ def run_native(a):
                        "every step; bounded by the PCIe upload of 4*d bytes per path-step"}
         del dev
 
+    if not a.no_e2e:
         # the production call: Solver.train_steps draws the increments on the device (Philox), so its per-step host input is
         # (seed, step count, learning rate) and its per-step host output the loss
         loss_dev = ctx.zeros(1)
@@ -330,13 +343,29 @@ def run_native(a):
                 loss_host.copy_(loss_dev, non_blocking=True)
             ctx.sync()
 
-        if world == 1:
-            for _ in range(2):
-                rng_step()
-            ms_r = timed(rng_step, a.steps) / a.steps
-            e2e_rng = {"value": B * N / (ms_r * 1e-3), "unit": "path-steps/s", "ms_per_step": ms_r, "h2d_bytes_per_step": 0,
-                       "d2h_bytes_per_step": 4, "what": "fbsdej_solver_train_steps(n_steps=1) + loss D2H + host sync every step; "
-                       "increments drawn on the device, as the reference draws them inside its graph"}
+        def rng_step_dp():
+            if p2p:
+                s.train_steps_dp(0, Bl, B, off, 1, LR, loss_out=loss_dev)
+            else:
+                out = s.grad_step(0, Bl, B, off)
+                with torch.cuda.stream(ctx.stream):
+                    dist.all_reduce(out)
+                    loss_dev.copy_(out[:1])
+                s.adam_step(LR)
+                s.bump_iteration()
+            with torch.cuda.stream(ctx.stream):
+                loss_host.copy_(loss_dev, non_blocking=True)
+            ctx.sync()
+
+        one = rng_step if world == 1 else rng_step_dp
+        for _ in range(2):
+            one()
+        ms_r = timed(one, a.steps) / a.steps
+        e2e_rng = {"value": B * N / (ms_r * 1e-3), "unit": "path-steps/s", "ms_per_step": ms_r, "h2d_bytes_per_step": 0,
+                   "d2h_bytes_per_step": 4 * world,
+                   "what": ("fbsdej_solver_train_steps(n_steps=1)" if world == 1 else "fbsdej_solver_train_steps_dp(n_steps=1) on every rank")
+                   + " + loss D2H + host sync every step; increments drawn on the device, as the reference draws them inside its "
+                     "graph: the per-step host input of the product call is (seed, learning rate)"}
 
     # ---- per-kernel device times + roofline (rank 0) ----------------------------------------------------------------
     roof, kernels = None, None
@@ -416,8 +445,10 @@ def run_native(a):
     if rank == 0:
         line = {"metric": "path-steps/s", "value": value, "unit": "path-steps/s", "n_gpus": world, "steps": a.steps,
                 "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "iters_per_s": 1e3 / ms_step, "higher_is_better": True,
-                "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": cfg, "clocks": clk, "e2e": e2e, "e2e_device_rng": e2e_rng, "gpu_launches": int(launches), "roofline": roof,
+                "scaling": "strong" if a.config == 5 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                # N > 1: the end-to-end number is the product call (device-drawn increments); the host-increment pipeline of the
+                # N = 1 line would measure N ranks sharing the host's PCIe, not the library
+                "config": cfg, "clocks": clk, "e2e": e2e if e2e is not None else e2e_rng, "e2e_device_rng": e2e_rng, "gpu_launches": int(launches), "roofline": roof,
                 "kernels": kernels, "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:
@@ -426,6 +457,13 @@ def run_native(a):
 
 if __name__ == "__main__":
     args = parse()
+    if args.config in (1, 2, 4):
+        from bench_reference_defaults import run_config       # scripts/: configs 1 / 2 / 4
+        run_config(args)
+        sys.exit(0)
+    args.solver = args.solver or "SumLocalReg"
+    if args.solver not in SOLVERS:
+        sys.exit("--solver must be one of %s for configs 3 / 5" % list(SOLVERS))
     if args.impl == "reference":
         run_reference(args)
     else:

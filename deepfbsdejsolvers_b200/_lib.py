@@ -82,6 +82,7 @@ def _load():
         "fbsdej_solver_dp_init": (i32, [vp, i32, i32, vp]),
         "fbsdej_solver_dp_buffer": (i32, [vp, vp]),
         "fbsdej_solver_dp_connect": (i32, [vp, vp, vp]),
+        "fbsdej_solver_dp_check": (i32, [vp]),
         "fbsdej_solver_train_steps_dp": (i32, [vp, vp, vp, vp, vp, vp, vp, u64, i32, i32, u32, i32, f32, f32, f32, f32, vp]),
         "fbsdej_solver_profile": (i32, [vp, vp, u64, i32, i32, C.POINTER(C.c_float)]),
         "fbsdej_solver_net_forward": (i32, [vp, vp, i32, vp, i32, vp]),
@@ -89,7 +90,6 @@ def _load():
         "fbsdej_solver_price": (i32, [vp, i32, vp, i32, vp]),
         "fbsdej_transpose_nbd_to_ndb": (i32, [vp, vp, vp, i32, i32, i32]),
         "fbsdej_transpose_ndb_to_nbd": (i32, [vp, vp, vp, i32, i32, i32]),
-        "fbsdej_selftest_tc": (i32, [vp, vp, vp, vp, vp, vp, vp]),
         "fbsdej_ctx_launch_count": (C.c_longlong, [vp]),
     }
     for name, (res, args) in sig.items():

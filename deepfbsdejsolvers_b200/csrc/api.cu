@@ -21,7 +21,6 @@ void set_error(const std::string& msg) { g_err = msg; }
 }  // namespace fbsdej
 
 namespace fbsdej {
-int launch_tc_selftest(const float*, const float*, const float*, const float*, float*, float*, cudaStream_t);
 }
 using namespace fbsdej;
 
@@ -372,6 +371,8 @@ int run_pass(fbsdej_solver* s, const float* theta, int B, int B_global, float* o
       x.peer_data = s->dp.d_data; x.peer_flags = s->dp.d_flags;
       x.xctr = reinterpret_cast<uint32_t*>(s->dp.buf + data_bytes) + (size_t)s->dp.world * xchg_nblk(s->P);
       x.rank = s->dp.rank; x.world = s->dp.world; x.nstride = xchg_nstride(s->P); x.nblk = xchg_nblk(s->P);
+      const char* to = getenv("FBSDEJ_DP_TIMEOUT_MS");              // default 30 s
+      x.timeout_ns = (to && atof(to) > 0 ? (unsigned long long)(atof(to) * 1e6) : 30000000000ull);
     }
     if (launch_reduce_adam(s->lpart, grid_f, s->gpart, grid_b, s->P, out, f.theta, f.m, f.v, f.mask, f.lr, f.b1, f.b2, f.eps,
                            f.t_dev, f.iter_dev, f.loss_dst, s->step_ctr, s->step_ctr + 1, st, s->dp_step ? &x : nullptr))
@@ -1026,6 +1027,23 @@ int fbsdej_solver_dp_connect(fbsdej_solver* s, const unsigned char* handles, voi
   s->dp.connected = true;
   return 0;
 }
+// Synchronises the ctx stream and reads this rank's error word: 0, or the stamp of the first exchange that timed out (the
+// step was void on this rank: no parameter / Adam / counter update).  Returns -3 with a message in that case.
+int fbsdej_solver_dp_check(fbsdej_solver* s) {
+  FB_REQUIRE(s && s->dp.buf, "dp_check: dp_init first");
+  FB_CUDA(cudaSetDevice(s->ctx->device));
+  FB_CUDA(cudaStreamSynchronize(s->ctx->stream));
+  const size_t data_bytes = sizeof(float) * 2 * (size_t)s->dp.world * xchg_nstride(s->P);
+  const uint32_t* ctr = reinterpret_cast<const uint32_t*>(s->dp.buf + data_bytes) + (size_t)s->dp.world * xchg_nblk(s->P);
+  uint32_t w[2] = {0, 0};
+  FB_CUDA(cudaMemcpy(w, ctr, sizeof(w), cudaMemcpyDeviceToHost));
+  if (w[1] != 0u) {
+    set_error("data-parallel exchange timed out at step stamp " + std::to_string(w[1]) + " on rank " + std::to_string(s->dp.rank) +
+              " of " + std::to_string(s->dp.world) + ": a peer did not deliver its [loss | gradient] vector; the step was not applied");
+    return -3;
+  }
+  return 0;
+}
 int fbsdej_solver_train_steps_dp(fbsdej_solver* s, float* theta, float* m, float* v, const float* mask, int* t_dev,
                                  uint32_t* iter_dev, uint64_t seed, int B, int B_global, uint32_t path_offset, int n_steps,
                                  float lr, float beta1, float beta2, float eps, float* loss_out) {
@@ -1090,13 +1108,6 @@ int fbsdej_solver_price(fbsdej_solver* s, int iStep, const float* X, int n, floa
   return 0;
 }
 
-int fbsdej_selftest_tc(fbsdej_ctx* ctx, const float* A, const float* B, const float* P, const float* Q, float* out0, float* out1) {
-  FB_REQUIRE(ctx && A && B && P && Q && out0 && out1, "selftest_tc: NULL argument");
-  FB_CUDA(cudaSetDevice(ctx->device));
-  if (fbsdej::launch_tc_selftest(A, B, P, Q, out0, out1, ctx->stream)) return -2;
-  ctx->launches += 1;
-  return 0;
-}
 
 int fbsdej_transpose_nbd_to_ndb(fbsdej_ctx* ctx, const float* src, float* dst, int N, int B, int d) {
   FB_REQUIRE(ctx && src && dst, "transpose: NULL argument");

@@ -360,3 +360,15 @@ int launch_tc_selftest(const float* A, const float* B, const float* P, const flo
 }
 
 }  // namespace fbsdej
+
+// This file is linked into libfbsdej_selftest.so (test infrastructure), NOT into the product library.
+namespace fbsdej {
+static thread_local std::string g_selftest_err;
+void set_error(const std::string& msg) { g_selftest_err = msg; }
+}  // namespace fbsdej
+extern "C" __attribute__((visibility("default"))) int fbsdej_selftest_tc(void* stream, const float* A, const float* B, const float* P,
+                                                                        const float* Q, float* out0, float* out1) {
+  if (!A || !B || !P || !Q || !out0 || !out1) return -1;
+  return fbsdej::launch_tc_selftest(A, B, P, Q, out0, out1, (cudaStream_t)stream);
+}
+extern "C" __attribute__((visibility("default"))) const char* fbsdej_selftest_last_error(void) { return fbsdej::g_selftest_err.c_str(); }

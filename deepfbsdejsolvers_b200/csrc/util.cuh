@@ -11,8 +11,9 @@ namespace fbsdej {
 struct XchgArgs {
   float* const* peer_data;       // device array [world]: data block of every rank (own included)
   uint32_t* const* peer_flags;   // device array [world]: flag block of every rank
-  uint32_t* xctr;                // this rank's step stamp (monotonic)
+  uint32_t* xctr;                // this rank's step stamp (monotonic); xctr[1] = error word: stamp of the first step that timed out
   int rank, world, nstride, nblk;
+  unsigned long long timeout_ns; // how long a block waits for a peer's flag before it voids the step
 };
 __host__ __device__ inline int xchg_nblk(int P) { return (kHeader + P + 31) / 32; }
 __host__ __device__ inline int xchg_nstride(int P) { return xchg_nblk(P) * 32; }

@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
   red[ty][tx] = s;
   __syncthreads();
   float t = 0.0f;
+  bool late = false;
   if (ty == 0) {
     t = red[0][tx];
 #pragma unroll
@@ -68,25 +69,31 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
       __threadfence_system();
       __syncwarp();
       if (tx < x.world) st_release_sys(x.peer_flags[tx] + (size_t)x.rank * x.nblk + blockIdx.x, stamp);
-      bool late = false;
       if (tx < x.world) {
         // a peer that never arrives (a rank died, or the ranks disagree on the number of steps) must not hang the device:
-        // after 30 s the step is poisoned with NaN instead
+        // after x.timeout_ns the step is VOID - no parameter, Adam-slot or counter update on this rank - and the failed
+        // stamp is written into the error word of every rank's buffer; fbsdej_solver_dp_check reports it to the host
         const uint32_t* fl = x.peer_flags[x.rank] + (size_t)tx * x.nblk + blockIdx.x;
         const unsigned long long t0 = globaltimer_ns();
         while ((int32_t)(ld_acquire_sys(fl) - stamp) < 0) {
-          if (globaltimer_ns() - t0 > 30000000000ull) { late = true; break; }
+          if (globaltimer_ns() - t0 > x.timeout_ns) { late = true; break; }
         }
       }
       late = __any_sync(0xffffffffu, late);
+      if (late && tx < x.world) atomicCAS_system(x.peer_flags[tx] + (size_t)x.world * x.nblk + 1, 0u, stamp);
+      // an error raised by ANY block of ANY rank voids the step here too (best effort: a rank that already passed this point
+      // has updated; the host-side check still fails on every rank)
+      late = late || ld_acquire_sys(x.xctr + 1) != 0u;
       const float* mine = x.peer_data[x.rank];
-      t = late ? __int_as_float(0x7fc00000) : 0.0f;
+      t = 0.0f;
       for (int r = 0; r < x.world; ++r) t += __ldcv(mine + (slot + r) * x.nstride + e);
+      if (late) t = __int_as_float(0x7fc00000);       // the loss / gradient record of a void step reads NaN
     }
   }
+  late = __shfl_sync(0xffffffffu, late ? 1 : 0, 0) != 0;
   if (ty == 0 && e < n) {
     out[e] = t;
-    if (f.theta && e >= kHeader) {                    // oracle/adam.py, SURVEY fact 9
+    if (f.theta && e >= kHeader && !late) {           // oracle/adam.py, SURVEY fact 9
       const int i = e - kHeader;
       if (!(f.mask && f.mask[i] == 0.0f)) {
         const int step = *f.t_dev + 1;
@@ -106,8 +113,11 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
       const unsigned int prev = atomicAdd(f.done_ctr, 1u);
       if (prev == gridDim.x - 1) {
         __threadfence();
-        *f.t_dev += 1;
-        *f.iter_dev += 1u;
+        const bool failed = f.x.world > 1 && ld_acquire_sys(f.x.xctr + 1) != 0u;   // void step: counters stay
+        if (!failed) {
+          *f.t_dev += 1;
+          *f.iter_dev += 1u;
+        }
         if (f.loss_dst) f.loss_dst[*f.step_ctr] = __ldcg(out);
         *f.step_ctr += 1u;
         if (f.x.world > 1) *f.x.xctr += 1u;

@@ -274,6 +274,10 @@ class NativeSolver:
         check(lib.fbsdej_solver_dp_connect(self.handle, hb, rp))
         self.dp_connected = True
 
+    def dp_check(self) -> None:
+        """Syncs the stream and raises FbsdejError if a data-parallel exchange timed out (the step was not applied)."""
+        check(lib.fbsdej_solver_dp_check(self.handle))
+
     def train_steps_dp(self, seed: int, B: int, B_global: int, path_offset: int, n_steps: int, lr: float,
                        mask: Optional[torch.Tensor] = None, loss_out: Optional[torch.Tensor] = None, beta1: float = 0.9,
                        beta2: float = 0.999, eps: float = 1e-7) -> None:

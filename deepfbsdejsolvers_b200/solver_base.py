@@ -86,7 +86,7 @@ class TrainLoop:
                 # the step's [loss | gradient] exchange runs inside the finishing kernel over peer memory: one CUDA graph
                 # per step on every rank, no collective call (FBSDEJ_DP=nccl keeps the all_reduce loop below)
                 s.train_steps_dp(self.seed, cnt, B, off, n, self.lr, mask=mask)
-                s.ctx.sync()
+                s.dp_check()       # syncs; raises if a peer never delivered its vector (the step is void, not NaN-poisoned)
                 return
             for _ in range(n):
                 out = s.grad_step(self.seed, cnt, B, off)

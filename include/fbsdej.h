@@ -182,10 +182,15 @@ FBSDEJ_API int fbsdej_solver_train_steps(fbsdej_solver* s, float* theta, float* 
  *   train_steps_dp  n_steps training steps on the shard [path_offset, path_offset + B) of a global batch of B_global paths:
  *               the kernel that finishes a step writes its [loss | gradient] vector into every peer's buffer (NVLink peer
  *               stores), waits for the peers' vectors, adds them in rank order and applies the same Adam update on every
- *               rank.  Same CUDA graph replay as train_steps; all ranks must call it with the same n_steps. */
+ *               rank.  Same CUDA graph replay as train_steps; all ranks must call it with the same n_steps.
+ *   dp_check    synchronises the ctx stream; 0, or -3 (message in fbsdej_last_error) if an exchange timed out: a peer did not
+ *               arrive within FBSDEJ_DP_TIMEOUT_MS (default 30 s).  The step that timed out - and every later one - is VOID on
+ *               this rank (parameters, Adam slots and counters untouched; the recorded loss reads NaN), and the error word is
+ *               raised in every reachable rank's buffer, so all ranks fail the check instead of diverging silently. */
 FBSDEJ_API int fbsdej_solver_dp_init(fbsdej_solver* s, int rank, int world, unsigned char* handle64);
 FBSDEJ_API int fbsdej_solver_dp_buffer(fbsdej_solver* s, void** ptr);
 FBSDEJ_API int fbsdej_solver_dp_connect(fbsdej_solver* s, const unsigned char* handles, void* const* raw_ptrs);
+FBSDEJ_API int fbsdej_solver_dp_check(fbsdej_solver* s);
 FBSDEJ_API int fbsdej_solver_train_steps_dp(fbsdej_solver* s, float* theta, float* m, float* v, const float* mask, int* t_dev,
                                  uint32_t* iter_dev, uint64_t seed, int B, int B_global, uint32_t path_offset, int n_steps,
                                  float lr, float beta1, float beta2, float eps, float* loss_out);
@@ -208,11 +213,6 @@ FBSDEJ_API int fbsdej_solver_price(fbsdej_solver* s, int iStep, const float* X, 
 /* Layout helpers: [N][B][d] (reference-style, d innermost) <-> [N][d][B]. */
 FBSDEJ_API int fbsdej_transpose_nbd_to_ndb(fbsdej_ctx* ctx, const float* src, float* dst, int N, int B, int d);
 FBSDEJ_API int fbsdej_transpose_ndb_to_nbd(fbsdej_ctx* ctx, const float* src, float* dst, int N, int B, int d);
-
-/* Self-test of the tcgen05 / TMEM plumbing: out0[128][32] = A[128][24] * B[24][32] (K-major operands),
- * out1[m][n] = sum_r P[r][m] Q[r][n] for r < 128 (MN-major operands; rows m >= 24 and columns n >= 24 are unspecified).
- * Device pointers; 3xTF32 split, fp32-grade results. */
-FBSDEJ_API int fbsdej_selftest_tc(fbsdej_ctx* ctx, const float* A, const float* B, const float* P, const float* Q, float* out0, float* out1);
 
 /* Number of kernels this library has launched on ctx since creation (bench.py's gpu_launches). */
 FBSDEJ_API long long fbsdej_ctx_launch_count(const fbsdej_ctx* ctx);

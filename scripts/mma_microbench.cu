@@ -144,10 +144,80 @@ static void run_mt(long long* d) {
   printf("multi-thread %s,%d,128,%d threads,1,%.1f\n", names[KIND], N, NT, (double)h / (NM * NT));
 }
 
+// One "layer evaluation" round trip as the fused kernels do it: every thread writes its row of the A operand to tensor memory
+// (tcgen05.st), wait::st + fences + CTA barrier, ONE thread issues NMMA tf32 MMAs (A from TMEM) and commits, all threads wait on
+// the mbarrier and read 24 accumulator columns back.  Cycles per round trip = the latency floor of one network layer of a
+// lone CTA (configs 1 / 2 / 4 walk N time steps of 2 (forward) + 4 (adjoint) such round trips on a handful of CTAs).
+template <int NMMA>
+__global__ void __launch_bounds__(128) bench_roundtrip(long long* out, float* sink) {
+  extern __shared__ __align__(1024) float sm[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tslot;
+  for (int i = threadIdx.x; i < 16384; i += 128) sm[i] = 0.0f;
+  if (threadIdx.x < 32) tc::tmem_alloc(&tslot, 128);
+  if (threadIdx.x == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tm = tslot, lane = tm + ((uint32_t)(threadIdx.x & ~31) << 16);
+  const uint32_t sb = tc::smem_u32(sm);
+  constexpr uint32_t idk = tc::idesc_tf32(128, 32, false, false);
+  constexpr int R = 256;
+  float acc = 0.0f;
+  uint32_t phase = 0;
+  const long long t0 = clock64();
+  for (int r = 0; r < R; ++r) {
+    uint32_t v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = __float_as_uint(acc + (float)q);
+    tc::tmem_st8(lane + 64, v);
+    tc::tmem_st_wait();
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc::tc_fence_after();
+      const uint64_t db = tc::smem_desc(sb + 32768, 32 * 16, 128);
+#pragma unroll
+      for (int i = 0; i < NMMA; ++i) tc::mma_tf32_ts(tm, tm + 64, db, idk, i ? 1u : 0u);
+      tc::mma_commit(&bar);
+    }
+    tc::mbar_wait(&bar, phase); phase ^= 1;
+    tc::tc_fence_after();
+    float a8[8], b8[8], c8[8];
+    tc::tmem_ld8(lane, a8); tc::tmem_ld8(lane + 8, b8); tc::tmem_ld8(lane + 16, c8);
+    tc::tmem_ld_wait();
+    acc = a8[0] + b8[1] + c8[2];
+    tc::tc_fence_before();
+  }
+  const long long t1 = clock64();
+  if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = (t1 - t0) / R;
+  sink[blockIdx.x * 128 + threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) tc::tmem_dealloc(tm, 128);
+}
+template <int NMMA>
+static void run_rt(long long* d, float* sink) {
+  const int smem = 65536 + 2048;
+  cudaFuncSetAttribute(bench_roundtrip<NMMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  for (int grid : {1, 148 * 3}) {
+    bench_roundtrip<NMMA><<<grid, 128, smem>>>(d, sink);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("roundtrip NMMA=%d: %s\n", NMMA, cudaGetErrorString(e)); exit(1); }
+    long long h;
+    cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+    printf("round trip (st + barrier + %d tf32 TS MMAs + commit + wait + ld),32,128,1,%d,%lld\n", NMMA, grid, h);
+  }
+}
+
 int main() {
   long long* d;
   cudaMalloc(&d, 8);
   printf("kind,N,M,nacc,grid,cycles_per_mma\n");
+  float* sink;
+  cudaMalloc(&sink, 148 * 3 * 128 * 4);
+  run_rt<1>(d, sink); run_rt<6>(d, sink); run_rt<9>(d, sink);
   run_mt<0, 32, 1>(d); run_mt<0, 32, 2>(d); run_mt<0, 32, 4>(d); run_mt<2, 32, 1>(d); run_mt<2, 32, 2>(d); run_mt<2, 32, 4>(d);
   run_mt<0, 64, 2>(d); run_mt<2, 64, 2>(d);
   for (int grid : {1, 148 * 3}) {

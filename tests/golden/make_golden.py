@@ -166,6 +166,47 @@ def pricing_case(kind, scheme):
     return out
 
 
+def trajectory_case(nsteps=25):
+    """A multi-step training trajectory of the reference's own code: SolverGlobalFBSDE (Merton) for `nsteps` Adam steps.  The fixture
+    holds the increments of every step and, per step, the reference's loss and its trainable Y0 after the update - what the
+    north star calls "the reference's own price" on the way."""
+    torch.manual_seed(0)
+    tf.random.seed(4242)
+    tf.keras.initializers.GEN.manual_seed(31)
+    tf.GradientTape.LOG.clear()
+    B, N = 8, 4
+    par = dict(T=1.0, N=N, r=0.1, muJ=0.0, sigmaJ=0.2, sigma=0.3, lam=3.0, K=0.9, x0=1.0)
+    model = PM.MertonJumpModel(par["T"], N, par["r"], par["muJ"], par["sigmaJ"], par["sigma"], par["lam"], par["K"], par["x0"], func, 30)
+    layer = 21 * np.ones((2,), dtype=np.int32)
+    netA, netB = NETP.Net(1, 1, layer, "tanh"), NETP.Net(0, 1, layer, "tanh")
+    build_net(netA, tf.zeros([1, 2]))
+    build_net(netB, tf.zeros([1, 3]))
+    lr = 4e-4                                           # mainMerton.py:18
+    solver = SJD.SolverGlobalFBSDE(model, netA, netB, lr)
+    theta0 = np.concatenate([flat_net(netA), flat_net(netB), np.array([netA.Y0.detach().numpy()], dtype=np.float32)]).astype(np.float32)
+    y0_after = []
+    orig_apply = tf.keras.optimizers.Adam.apply_gradients
+
+    def apply(self, gv):
+        orig_apply(self, gv)
+        y0_after.append(float(netA.Y0.detach()))
+    tf.keras.optimizers.Adam.apply_gradients = apply
+    rec = Recorder(model, B)
+    solver.train(B, 1, nsteps, 1)
+    rec.close()
+    tf.keras.optimizers.Adam.apply_gradients = orig_apply
+    losses = np.array([tf.GradientTape.LOG[k][0] for k in range(nsteps)], dtype=np.float64)
+    theta1 = np.concatenate([flat_net(netA), flat_net(netB), np.array([netA.Y0.detach().numpy()], dtype=np.float32)]).astype(np.float32)
+    sq = np.float32(np.sqrt(model.dt))
+    k = nsteps * N
+    return dict(kind="merton", scheme="Global", B=B, N=N, lr=lr, nsteps=nsteps, theta0=theta0, theta_final=theta1, losses=losses,
+                Y0_after_step=np.array(y0_after[:nsteps], dtype=np.float32),
+                dW=(sq * torch.stack(rec.gauss[:k], 0)).numpy().reshape(nsteps, N, B),
+                J=torch.stack(rec.J[:k], 0).numpy().reshape(nsteps, N, B),
+                JMC=torch.stack(rec.JMC[:k], 0).numpy().reshape(nsteps, N, MCOMP),
+                **{kk: np.float64(v) for kk, v in par.items() if kk != "N"})
+
+
 def qaver_curve():
     t = np.arange(48) / 48.0
     return (0.35 + 0.2 * np.sin(2 * np.pi * (t - 0.3)) + 0.05 * np.sin(4 * np.pi * t))[:13]    # N = 12 steps
@@ -266,6 +307,11 @@ def main():
             d = mfg_case(scheme)
         np.savez_compressed(os.path.join(HERE, f"mfg_{scheme}.npz"), **d)
         print("mfg", scheme, "loss", float(d["loss"]), "Y0_hat", float(d["Y0_hat_report"]), "Y0", float(d["Y0_report"]))
+    with contextlib.redirect_stdout(io.StringIO()):
+        d = trajectory_case()
+    np.savez_compressed(os.path.join(HERE, "traj", "merton_Global_25steps.npz"), **d)
+    print("trajectory: merton Global", int(d["nsteps"]), "steps, loss", float(d["losses"][0]), "->", float(d["losses"][-1]),
+          "Y0", float(d["Y0_after_step"][0]), "->", float(d["Y0_after_step"][-1]))
     for scheme in ("Global", "SumLocalReg"):      # couplage OFF (the other OFF variants crash in the reference: MFGSolvers.py:291,431)
         with contextlib.redirect_stdout(io.StringIO()):
             d = mfg_case(scheme, couplage="OFF")

@@ -134,3 +134,36 @@ def test_exchange_inside_the_finishing_kernel_mfg(ctx):
     layout = H.mfg_layout("MultiStep")
     _two_ranks_through_the_fused_exchange(ctx, lambda c: H.native_mfg(c, p, "MultiStep", layout, tensor_cores=True),
                                           H.random_theta(layout, 6), 256, 7, 5, 1e-3, 2)
+
+
+def test_missing_peer_voids_the_step_and_raises(ctx, monkeypatch):
+    """A rank whose peer never delivers its vector must neither hang nor poison its parameters: after FBSDEJ_DP_TIMEOUT_MS the
+    step is void (parameters, Adam slots and counters untouched), the error word is raised in BOTH ranks' buffers and
+    fbsdej_solver_dp_check fails on both."""
+    from deepfbsdejsolvers_b200 import Context, FbsdejError
+    monkeypatch.setenv("FBSDEJ_DP_TIMEOUT_MS", "200")
+    p = dict(H.MERTON, N=6)
+    layout = H.pricing_layout("merton", "SumLocalReg", 10)
+    theta = H.random_theta(layout, 5)
+    B, ranks, bufs = 400, [], []
+    for r in range(2):
+        c = Context(ctx.index)
+        s = H.native_pricing(c, "merton", p, "SumLocalReg", layout, d=10, limit=100, tensor_cores=True)
+        s.set_theta(theta); s.reset_optimizer()
+        s.grad_step(3, B // 2, B, r * (B // 2))
+        c.sync()
+        s.dp_init(r, 2)
+        bufs.append(s.dp_buffer())
+        ranks.append((c, s))
+    for c, s in ranks:
+        s.dp_connect(raw_ptrs=bufs)
+    c0, s0 = ranks[0]
+    loss = c0.zeros(2)
+    s0.train_steps_dp(3, B // 2, B, 0, 2, 1e-3, loss_out=loss)     # rank 1 never steps
+    with pytest.raises(FbsdejError, match="timed out"):
+        s0.dp_check()
+    assert np.array_equal(s0.get_theta(), theta)                     # not updated, not NaN
+    assert int(c0.to_host(s0.t).numpy()[0]) == 0 and not np.abs(c0.to_host(s0.m).numpy()).any()
+    assert np.isnan(c0.to_host(loss).numpy()).all()                  # the record says the steps were void
+    with pytest.raises(FbsdejError, match="timed out"):
+        ranks[1][1].dp_check()                                       # the peer sees the failure too

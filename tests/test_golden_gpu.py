@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import helpers as H
-from test_oracle_golden import load_case, CASES, OFF_CASES, off_masks
+from test_oracle_golden import load_case, CASES, OFF_CASES, TRAJ, off_masks
 
 pytestmark = pytest.mark.gpu
 
@@ -102,3 +102,31 @@ def test_cuda_reproduces_reference_step(ctx, path, tensor_cores):
     elif scheme != "Global":
         y0 = s.net_forward(0, np.array([[0.0, c["x0"]]], dtype=np.float32))[0, 0]
         assert abs(y0 - c["Y0_report"]) < 2e-6
+
+
+@pytest.mark.parametrize("tensor_cores", (False, True), ids=("ffma", "tcgen05"))
+def test_cuda_follows_the_reference_training_trajectory(ctx, tensor_cores):
+    """25 consecutive training steps of the reference's own SolverGlobalFBSDE (Merton, 5000 compensator samples per step) on the
+    increments it drew: the CUDA path's loss at every step and its trainable Y0 after every Keras-form Adam update against the
+    reference's - "the reference's own price" on the way (north star), step by step."""
+    c = load_case(TRAJ)
+    B, n, N = int(c["B"]), int(c["nsteps"]), int(c["N"])
+    layout = H.pricing_layout("merton", "Global", 1)
+    par = {k: c[k] for k in ("T", "r", "muJ", "sigmaJ", "sigma", "lam", "K", "x0")}
+    par["N"] = N
+    s = H.native_pricing(ctx, "merton", par, "Global", layout, d=1, M=c["JMC"].shape[2], tensor_cores=tensor_cores)
+    s.set_theta(c["theta0"])
+    s.reset_optimizer()
+    worst_l = worst_y = 0.0
+    for k in range(n):
+        s.set_noise(B, planes(c["dW"][k]), planes(c["J"][k]), planes(c["JMC"][k]))
+        out = s.grad(B)
+        worst_l = max(worst_l, abs(out[0] - c["losses"][k]) / abs(c["losses"][k]))
+        s.adam_step(float(c["lr"]))
+        y0 = float(s.get_theta()[s.y0_offset])
+        worst_y = max(worst_y, abs(y0 - float(c["Y0_after_step"][k])))
+    print(f"trajectory ({'tcgen05' if tensor_cores else 'ffma'}): worst loss rel {worst_l:.1e}, worst |Y0 - Y0_ref| {worst_y:.1e} over {n} steps")
+    assert worst_l <= 3e-5 and worst_y <= 5e-6
+    th = s.get_theta()
+    solid = np.abs(c["theta_final"] - c["theta0"]) > 0.2 * n * float(c["lr"])
+    np.testing.assert_allclose(th[solid], c["theta_final"][solid], rtol=0, atol=0.03 * n * float(c["lr"]))

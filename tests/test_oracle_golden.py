@@ -154,6 +154,29 @@ def test_oracle_reproduces_reference_couplage_off(path):
     assert np.abs(th_bad.numpy() - c["theta2"]).max() > 1e-5
 
 
+TRAJ = os.path.join(GOLD, "traj", "merton_Global_25steps.npz")
+
+
+def test_oracle_follows_the_reference_training_trajectory():
+    """25 consecutive Adam steps of the reference's own SolverGlobalFBSDE (Merton, its 5000 compensator samples) on the recorded
+    increments: the oracle's loss and the trainable Y0 after every step against what the reference computed on the way."""
+    c = load_case(TRAJ)
+    om, layout = oracle_of(c)
+    B, n = int(c["B"]), int(c["nsteps"])
+    th = torch.tensor(c["theta0"].copy())
+    opt = KerasAdam(layout.total, float(c["lr"]))
+    for k in range(n):
+        t = th.clone().requires_grad_(True)
+        nz = {key: torch.tensor(c[key][k])[..., None] for key in ("dW", "J", "JMC")}
+        loss = pricing_loss(om, "Global", layout, t, nz, B)
+        loss.backward()
+        assert abs(float(loss.detach()) - c["losses"][k]) <= 3e-5 * abs(c["losses"][k]), (k, float(loss.detach()), c["losses"][k])
+        opt.step(th, t.grad)
+        assert abs(float(th[layout.y0_offset]) - c["Y0_after_step"][k]) <= 3e-6, (k, float(th[layout.y0_offset]), c["Y0_after_step"][k])
+    solid = np.abs(c["theta_final"] - c["theta0"]) > 0.2 * n * float(c["lr"])       # entries whose gradient kept its sign
+    np.testing.assert_allclose(th.numpy()[solid], c["theta_final"][solid], rtol=0, atol=0.03 * n * float(c["lr"]))
+
+
 def test_merton_closed_form_known_answers():
     om = MertonOracle(aLin=0.1, limit=30, d=1, dtype=torch.float64, **H.MERTON)
     assert abs(float(om.A(0, om.init(1))[0]) - 0.2714569268) < 1e-9

@@ -10,14 +10,18 @@ pytestmark = pytest.mark.gpu
 
 
 def test_tcgen05_selftest(ctx):
+    import os
     from deepfbsdejsolvers_b200 import _lib as L
+    st = C.CDLL(os.path.join(os.path.dirname(L.LIB_PATH), "libfbsdej_selftest.so"))   # test-only kernels live outside the product library
+    st.fbsdej_selftest_tc.restype = C.c_int
+    st.fbsdej_selftest_tc.argtypes = [C.c_void_p] * 7
     rng = np.random.default_rng(0)
     A, B = rng.standard_normal((128, 24)).astype(np.float32), rng.standard_normal((24, 32)).astype(np.float32)
     P, Q = rng.standard_normal((128, 24)).astype(np.float32), rng.standard_normal((128, 24)).astype(np.float32)
     d = [ctx.to_device(x) for x in (A, B, P, Q)]
     o0, o1 = ctx.zeros(4, 128, 32), ctx.zeros(4, 128, 32)
-    L.check(L.lib.fbsdej_selftest_tc(ctx.handle, *[C.c_void_p(t.data_ptr()) for t in d], C.c_void_p(o0.data_ptr()),
-                                     C.c_void_p(o1.data_ptr())))
+    assert st.fbsdej_selftest_tc(C.c_void_p(ctx.stream.cuda_stream), *[C.c_void_p(t.data_ptr()) for t in d], C.c_void_p(o0.data_ptr()),
+                                 C.c_void_p(o1.data_ptr())) == 0
     r0, r1 = ctx.to_host(o0).numpy(), ctx.to_host(o1).numpy()
     ref0 = A.astype(np.float64) @ B.astype(np.float64)
     ref1 = P.astype(np.float64).T @ Q.astype(np.float64)
