@@ -167,6 +167,7 @@ struct fbsdej_solver {
   // work buffers
   float *trajE = nullptr, *trajX = nullptr, *aux_s = nullptr, *aux_dA = nullptr, *sch1 = nullptr, *fin = nullptr;
   float *rec = nullptr, *recN = nullptr;   // tcgen05 path: tile-major records (pricing.cuh: RecLayout)
+  float* wimg = nullptr;                   // tcgen05 compensator-free kernels: weight operand images (reg_tc_kernels.cu)
   float *lpart = nullptr, *gpart = nullptr; int cap_grid = 0;
   float* out_dev = nullptr;       // [4 + P] scratch for train_steps
   uint32_t* step_ctr = nullptr;   // device: [0] step index inside train_steps, [1] finished-block counter of the fused finish
@@ -345,6 +346,11 @@ int run_pass(fbsdej_solver* s, const float* theta, int B, int B_global, float* o
     if (with_grad)
       grid_b = a.C * std::min(ntiles, std::max(1, s->ctx->sms * pricing_blocks_per_sm(s->model, s->D, s->HP, a, true) / a.C));
     if (a.mma_mode == 1 && !a.has_jump) {   // tcgen05 compensator-free kernels: four CTAs per SM, tiles of 4 or 3 warps
+      if (!s->wimg && dev_alloc(&s->wimg, reg_tc_wimg_floats())) return -2;   // (first pass: never inside a graph capture)
+      a.theta = theta;
+      if (launch_reg_stage_operands(a, s->wimg, st)) return -1;             // theta -> TMA-ready operand images
+      s->ctx->launches += 1;
+      a.wimg_fwd = s->wimg; a.wimg_bwd = s->wimg + reg_tc_wimg_fwd_floats();
       a.tmap = make_tile_map(B, 4 * s->ctx->sms);
       grid_f = std::min(a.tmap.ntiles, 4 * s->ctx->sms);
       if (with_grad) grid_b = grid_f;
@@ -654,7 +660,7 @@ int fbsdej_solver_destroy(fbsdej_solver* s) {
   dev_free(s->atab); dev_free(s->atab_meta); dev_free(s->atab_off);
   dev_free(s->vg_coef); dev_free(s->vg_scale); dev_free(s->pois_thr); dev_free(s->qaver); dev_free(s->meanhq);
   dev_free(s->jmc_raw); dev_free(s->jmc); dev_free(s->jmc_nnz); dev_free(s->jmc_n0);
-  dev_free(s->lpart); dev_free(s->gpart); dev_free(s->out_dev); dev_free(s->step_ctr);
+  dev_free(s->lpart); dev_free(s->gpart); dev_free(s->out_dev); dev_free(s->step_ctr); dev_free(s->wimg);
   for (size_t r = 0; r < s->dp.peers.size(); ++r)
     if (s->dp.opened[r] && s->dp.peers[r]) cudaIpcCloseMemHandle(s->dp.peers[r]);
   dev_free(s->dp.buf); dev_free(s->dp.d_data); dev_free(s->dp.d_flags);

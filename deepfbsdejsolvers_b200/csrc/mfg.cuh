@@ -35,5 +35,8 @@ int pricing_blocks_per_sm(int model, int D, int HP, const PricingArgs& a, bool b
 int mfg_blocks_per_sm(int HP, const MFGArgs& a, bool backward);
 int launch_price(int model, int D, const PricingArgs& a, int iStep, const float* X, int n, float* out, cudaStream_t st);
 int launch_untile_traj(int D, const float* rec, const float* recN, TileMap map, int B, int N, float* out, cudaStream_t st);
+size_t reg_tc_wimg_floats();
+size_t reg_tc_wimg_fwd_floats();
+int launch_reg_stage_operands(const PricingArgs& a, float* img, cudaStream_t st);
 
 }  // namespace fbsdej

@@ -88,6 +88,10 @@ struct PricingArgs {
   float* rec;
   float* recN;
   TileMap tmap;
+  // weight operand images of the tcgen05 compensator-free kernels, built from theta by reg_stage_operands_kernel once per pass
+  // and bulk-copied (TMA) into shared memory by every CTA: forward (TF32 hi / lo, r-form scales), adjoint (bf16 hi / lo)
+  const float* wimg_fwd;
+  const float* wimg_bwd;
   float* trajY;               // optional [N+1][B]
   float* trajZ;               // optional [N][D][B]
   float* lpart;               // [grid][4]

@@ -50,6 +50,8 @@ constexpr int OFF_W3 = U4_END * 4;            // float offsets after the uint4 r
 constexpr int OFF_BAR = OFF_W3 + 24;          // two mbarriers (8-byte aligned) + the TMEM base slot
 constexpr int SMEM_FLOATS = OFF_BAR + 8;
 static_assert((OFF_BAR % 2) == 0, "mbarrier alignment");
+constexpr uint32_t WIMG_BYTES = (uint32_t)(OFF_W3 + 24 - W_BASE * 4) * 4;   // weight operand image: the uint4 B operands + W3
+static_assert(WIMG_BYTES % 16 == 0, "bulk copy size");
 constexpr uint32_t C_ACC = 0, C_W1 = 48, C_W2 = 80, NCOLS = 128;   // ACC 48 | WG1 32 | WG2 48 columns
 constexpr int COL_DOUT = 23;                  // spare column of D2 that carries dL/dy through WG2 (needs H <= 22)
 }  // namespace bwd
@@ -70,45 +72,19 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
   const bool issuer = (row & 31) == 0;
   const int H = a.netA.H, nin = a.netA.nin;
 
-  // ---- one-time set-up: zero the tiles, stage the weights as bf16 hi/lo B operands, TMEM, barriers ---------------
-  for (int i = row; i < SMEM_FLOATS; i += kThreads) smem[i] = 0.0f;
+  // ---- one-time set-up: zero the tiles, TMA bulk copy of the weight operand image (bf16 hi / lo B operands + W3; built from
+  // theta by reg_stage_operands_kernel), TMEM, barriers ------------------------------------------------------------------
+  for (int i = row; i < SMEM_FLOATS; i += kThreads)
+    if (i < W_BASE * 4 || i >= OFF_W3 + 24) smem[i] = 0.0f;
   __syncthreads();
-  {
-    const float* __restrict__ th = a.theta + a.netA.ext_off;
-    const int n1 = nin * H, n2 = n1 + H, n3 = n2 + H * H, n4 = n3 + H, n5 = n4 + H;
-    unsigned short* const w1 = reinterpret_cast<unsigned short*>(u4 + W1B);
-    unsigned short* const w2 = reinterpret_cast<unsigned short*>(u4 + W2B);
-    unsigned short* const wt = reinterpret_cast<unsigned short*>(u4 + WTB);
-    unsigned short* const w1t = reinterpret_cast<unsigned short*>(u4 + W1T);
-    // element (n, k) of a stacked B operand with NH n-rows per copy: hi at n, lo at NH + n
-    auto put = [](unsigned short* w, int NH, int n, int k, uint32_t hi, uint32_t lo) {
-      w[((k >> 3) * 2 * NH + n) * 8 + (k & 7)] = (unsigned short)hi;
-      w[((k >> 3) * 2 * NH + NH + n) * 8 + (k & 7)] = (unsigned short)lo;
-    };
-    const float one_in = ACT == ACT_TANH ? 20.0f : 1.0f;   // act(one_in) == 1 exactly: the constant-1 unit of H1 / H2
-    for (int e = row; e < n5 + 2; e += kThreads) {
-      uint32_t hi, lo;
-      if (e < n2) {                                   // W1[i][j]: layer-1 B operand [n = j][k = i]; the time row (i = 0) and
-        const int i = e < n1 ? e / H : nin, j = e < n1 ? e % H : e - n1;   // b1 (i = nin) live in the per-step effective bias
-        tc::split_bf16(th[e], hi, lo);
-        if (i >= 1 && i < nin) put(w1, NB, j, i, hi, lo);
-        if (i < nin) put(w1t, 16, i, j, hi, lo);      // input-gradient B operand [n = i][k = j]
-      } else if (e < n4) {                            // W2[k][j], b2[j] (k = H): layer-2 B operand [n = j][k]
-        const int k = e < n3 ? (e - n2) / H : H, j = e < n3 ? (e - n2) % H : e - n3;
-        tc::split_bf16(th[e], hi, lo);
-        put(w2, NB, j, k, hi, lo);
-        if (k < H) put(wt, NB, k, j, hi, lo);         // W2^T: B operand [n = k][k' = j]
-      } else if (e < n5) {
-        w3s[e - n4] = th[e];                          // W3[k][0], k < H  (entries >= H stay 0: no delta for the constant unit)
-      } else if (e == n5) {                           // (the constant-1 unit of H1 is written with the effective bias)
-      } else {                                        // the constant-1 unit of H2: act(one_in * 1) == 1
-        tc::split_bf16(one_in, hi, lo);
-        put(w2, NB, H, H, hi, lo);
-      }
-    }
-  }
-  if (warp == 0) tc::tmem_alloc(tslot, NCOLS);
   if (row == 0) { tc::mbar_init(bar_f, 1); tc::mbar_init(bar_w, 1); tc::fence_mbar_init(); }
+  __syncthreads();
+  if (row == 0) {
+    tc::mbar_arrive_expect_tx(bar_w, WIMG_BYTES);
+    tc::bulk_g2s(u4 + W_BASE, a.wimg_bwd, WIMG_BYTES, bar_w);
+  }
+  tc::mbar_wait(bar_w, 0);                              // (phase 0 of bar_w; the WG1 commits use the following phases)
+  if (warp == 0) tc::tmem_alloc(tslot, NCOLS);
   tc::fence_async_smem();
   tc::tc_fence_before();
   __syncthreads();
@@ -121,7 +97,7 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
   const int bias_idx = ((nin >> 3) * 2 * NB + row) * 8 + (nin & 7);   // hi copy; the lo copy is NB n-rows further
   const uint32_t sbase = tc::smem_u32(u4);
   auto sa = [&](int off_u4) { return sbase + (uint32_t)off_u4 * 16u; };
-  uint32_t phase_f = 0, phase_w = 0, pending_w = 0, started = 0;
+  uint32_t phase_f = 0, phase_w = 1, pending_w = 0, started = 0;
   auto wait_f = [&]() { tc::mbar_wait(bar_f, phase_f); phase_f ^= 1; tc::tc_fence_after(); };
 
   const float invB = a.inv_B, invBN = a.inv_B / (float)a.N, rdt = a.r * a.dt;
@@ -369,7 +345,7 @@ constexpr int W1B_HI = 0, W1B_LO = W1B_HI + 4 * NB * 4, W2B_HI = W1B_LO + 4 * NB
               OFF_W3 = W2B_LO + 6 * NB * 4 + 32 /* N = 32 reads 8 n-rows past the last chunk */, OFF_RED = OFF_W3 + 32,
               OFF_BAR = OFF_RED + 8 /* mbarriers: mma, full[NST], empty[NST] */, OFF_TS = OFF_BAR + 2 * (1 + 2 * NST),
               OFF_THR = OFF_TS + 2 /* 64 Poisson thresholds (fused RNG) */, OFF_RING = OFF_THR + 64;
-static_assert((OFF_BAR % 2) == 0 && (OFF_RING % 4) == 0, "mbarrier / ring alignment");
+static_assert((OFF_BAR % 2) == 0 && (OFF_RING % 4) == 0 && (OFF_RED % 4) == 0, "mbarrier / ring / image alignment");
 template <int D> constexpr int smem_floats() { return OFF_RING + NST * D * TR; }
 // tensor memory: two allocations (32 + 64 = 96 columns): the accumulator, and the A operand hi (X: 16, H1: 24 columns) | lo
 constexpr uint32_t NCOLS_ACC = 32, NCOLS_A = 64;
@@ -412,57 +388,23 @@ __global__ void __launch_bounds__(2 * kThreads, 4) reg_forward_tc(const PricingA
   const int tid = threadIdx.x, row = tid & (kThreads - 1), wg = tid >> 7, warp = (tid >> 5) & 3, lane = tid & 31;
   const int H = a.netA.H, nin = a.netA.nin;
   constexpr float CS = ACT == ACT_TANH ? 2.885390081777927f : 1.0f;        // pre-activation scale 2 log2(e)
-  constexpr float W2S = ACT == ACT_TANH ? -2.0f * CS : 1.0f, W3S = ACT == ACT_TANH ? -2.0f : 1.0f;
   constexpr float one_in = ACT == ACT_TANH ? -200.0f : 1.0f;               // constant-1 unit: r(-200) = 1, relu(1) = 1
 
-  for (int i = tid; i < OFF_RING; i += 2 * kThreads) smem[i] = 0.0f;
+  // weight operand image (TF32 hi / lo B operands in r form + W3; reg_stage_operands_kernel) by one TMA bulk copy
+  for (int i = tid + OFF_RED; i < OFF_RING; i += 2 * kThreads) smem[i] = 0.0f;
   __syncthreads();
-  {
-    // tanh layers run in "r form": the MMA delivers x' = 2 log2(e) x (scale folded into the weights), the thread forms
-    // r = 1 / (2^x' + 1) (two MUFU + one add) and hands r - not h = 1 - 2 r - to the next layer, whose weights carry the
-    // factor -2 and whose bias row carries b + sum_k W[k][.]; the constant-1 unit is r = 1 exactly (2^-200 flushes to 0).
-    const float* __restrict__ th = a.theta + a.netA.ext_off;
-    const int n1 = nin * H, n2 = n1 + H, n3 = n2 + H * H, n4 = n3 + H, n5 = n4 + H;
-    for (int e = tid; e < n5; e += 2 * kThreads) {
-      float hi, lo;
-      if (e < n1) {                                     // W1[i][j], i >= 1 (the time row lives in the effective bias)
-        const int i = e / H, j = e % H;
-        if (i >= 1) {
-          tc::split_tf32(CS * th[e], hi, lo);
-          smem[W1B_HI + ((i >> 2) * NB + j) * 4 + (i & 3)] = hi;
-          smem[W1B_LO + ((i >> 2) * NB + j) * 4 + (i & 3)] = lo;
-        }
-      } else if (e < n2) {
-      } else if (e < n3) {                              // W2[k][j]
-        const int k = (e - n2) / H, j = (e - n2) % H;
-        tc::split_tf32(W2S * th[e], hi, lo);
-        smem[W2B_HI + ((k >> 2) * NB + j) * 4 + (k & 3)] = hi;
-        smem[W2B_LO + ((k >> 2) * NB + j) * 4 + (k & 3)] = lo;
-      } else if (e < n4) {
-      } else {
-        w3s[e - n4] = W3S * th[e];                      // W3[k], k < H
-      }
-    }
-    if (tid < H) {                                      // bias row of layer 2 (k = H)
-      float b = th[n3 + tid];
-      if (ACT == ACT_TANH) for (int k = 0; k < H; ++k) b += th[n2 + k * H + tid];
-      float hi, lo;
-      tc::split_tf32(CS * b, hi, lo);
-      smem[W2B_HI + ((H >> 2) * NB + tid) * 4 + (H & 3)] = hi;
-      smem[W2B_LO + ((H >> 2) * NB + tid) * 4 + (H & 3)] = lo;
-    }
-    if (tid == 2 * kThreads - 1) {                      // output bias at index 24
-      float b = th[n5];
-      if (ACT == ACT_TANH) for (int k = 0; k < H; ++k) b += th[n4 + k];
-      w3s[24] = b;
-    }
+  if (tid == 0) { tc::mbar_init(bar, 1); tc::fence_mbar_init(); }
+  __syncthreads();
+  if (tid == 0) {
+    tc::mbar_arrive_expect_tx(bar, OFF_RED * 4);
+    tc::bulk_g2s(smem, a.wimg_fwd, OFF_RED * 4, bar);
   }
+  tc::mbar_wait(bar, 0);                                 // (phase 0 of the MMA barrier; the commits use the following phases)
   uint32_t* const sthr = reinterpret_cast<uint32_t*>(smem + OFF_THR);
   if (RNG && tid < 64) sthr[tid] = tid < a.npois ? a.pois_thr[tid] : 0xffffffffu;
   if (tid < 32) { tc::tmem_alloc(tslot, NCOLS_ACC, false); tc::tmem_alloc(tslot + 1, NCOLS_A); }
   const int hrows = tile_height(a.tmap, blockIdx.x);    // rows (= threads per warpgroup) of this CTA's tiles: 128 or 96
   if (tid == 0) {
-    tc::mbar_init(bar, 1);
     for (int s = 0; s < NST; ++s) { tc::mbar_init(bar + 1 + s, hrows / 32); tc::mbar_init(bar + 1 + NST + s, hrows / 32); }
     tc::fence_mbar_init();
   }
@@ -562,7 +504,7 @@ __global__ void __launch_bounds__(2 * kThreads, 4) reg_forward_tc(const PricingA
   const uint32_t lane_base = tmem + ((uint32_t)(row & ~31) << 16), lane_a = tmem_a + ((uint32_t)(row & ~31) << 16);
   const uint32_t sbase = tc::smem_u32(smem);
   auto sa = [&](int off_f) { return sbase + (uint32_t)off_f * 4u; };
-  uint32_t phase = 0;
+  uint32_t phase = 1;
   auto wait_mma = [&]() { tc::mbar_wait(bar, phase); phase ^= 1; tc::tc_fence_after(); };
   const int bias_idx = ((nin >> 2) * NB + row) * 4 + (nin & 3);   // W1B[n = row][k = nin]
   const float rdt = a.r * a.dt;
@@ -731,6 +673,101 @@ __global__ void __launch_bounds__(2 * kThreads, 4) reg_forward_tc(const PricingA
   if (warp == 0) { tc::tmem_dealloc(tmem, NCOLS_ACC); tc::tmem_dealloc(tmem_a, NCOLS_A); }
 }
 
+// ---- weight operand images ------------------------------------------------------------------------------------------------
+// One small launch per pass turns theta (flat fp32) into the operand images the two sweeps want - forward: TF32 hi / lo B
+// operands in r form + W3 (fwd::OFF_RED floats, the head of the forward kernel's shared memory); adjoint: bf16 hi / lo B
+// operands stacked along N + W3 (bwd::WIMG_BYTES, the region [W_BASE, OFF_W3 + 24) of the adjoint kernel's shared memory).  Every
+// CTA of the sweeps then fetches its image with ONE TMA bulk copy (cp.async.bulk + mbarrier) instead of ~2000 scalar loads,
+// splits and scattered shared-memory stores.
+template <int ACT>
+__global__ void __launch_bounds__(256) reg_stage_operands_kernel(const PricingArgs a, float* __restrict__ img_f, float* __restrict__ img_b) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int H = a.netA.H, nin = a.netA.nin;
+  const float* __restrict__ th = a.theta + a.netA.ext_off;
+  const int n1 = nin * H, n2 = n1 + H, n3 = n2 + H * H, n4 = n3 + H, n5 = n4 + H;
+  if (blockIdx.x == 0) {
+    using namespace fwd;
+    float* const smem = img_f;
+    float* const w3s = smem + OFF_W3;
+    constexpr float CS = ACT == ACT_TANH ? 2.885390081777927f : 1.0f;        // pre-activation scale 2 log2(e)
+    constexpr float W2S = ACT == ACT_TANH ? -2.0f * CS : 1.0f, W3S = ACT == ACT_TANH ? -2.0f : 1.0f;
+    for (int i = tid; i < OFF_RED; i += nthr) smem[i] = 0.0f;
+    __syncthreads();
+    // tanh layers run in "r form": the MMA delivers x' = 2 log2(e) x (scale folded into the weights), the thread forms
+    // r = 1 / (2^x' + 1) (two MUFU + one add) and hands r - not h = 1 - 2 r - to the next layer, whose weights carry the
+    // factor -2 and whose bias row carries b + sum_k W[k][.]; the constant-1 unit is r = 1 exactly (2^-200 flushes to 0).
+    for (int e = tid; e < n5; e += nthr) {
+      float hi, lo;
+      if (e < n1) {                                     // W1[i][j], i >= 1 (the time row lives in the effective bias)
+        const int i = e / H, j = e % H;
+        if (i >= 1) {
+          tc::split_tf32(CS * th[e], hi, lo);
+          smem[W1B_HI + ((i >> 2) * NB + j) * 4 + (i & 3)] = hi;
+          smem[W1B_LO + ((i >> 2) * NB + j) * 4 + (i & 3)] = lo;
+        }
+      } else if (e < n2) {
+      } else if (e < n3) {                              // W2[k][j]
+        const int k = (e - n2) / H, j = (e - n2) % H;
+        tc::split_tf32(W2S * th[e], hi, lo);
+        smem[W2B_HI + ((k >> 2) * NB + j) * 4 + (k & 3)] = hi;
+        smem[W2B_LO + ((k >> 2) * NB + j) * 4 + (k & 3)] = lo;
+      } else if (e < n4) {
+      } else {
+        w3s[e - n4] = W3S * th[e];                      // W3[k], k < H
+      }
+    }
+    if (tid < H) {                                      // bias row of layer 2 (k = H)
+      float b = th[n3 + tid];
+      if (ACT == ACT_TANH) for (int k = 0; k < H; ++k) b += th[n2 + k * H + tid];
+      float hi, lo;
+      tc::split_tf32(CS * b, hi, lo);
+      smem[W2B_HI + ((H >> 2) * NB + tid) * 4 + (H & 3)] = hi;
+      smem[W2B_LO + ((H >> 2) * NB + tid) * 4 + (H & 3)] = lo;
+    }
+    if (tid == nthr - 1) {                              // output bias at index 24
+      float b = th[n5];
+      if (ACT == ACT_TANH) for (int k = 0; k < H; ++k) b += th[n4 + k];
+      w3s[24] = b;
+    }
+  } else {
+    using namespace bwd;
+    uint4* const u4 = reinterpret_cast<uint4*>(img_b) - W_BASE;         // the image starts at the adjoint's W_BASE
+    float* const w3s = img_b + (OFF_W3 - W_BASE * 4);
+    for (int i = tid; i < (int)(WIMG_BYTES / 4); i += nthr) img_b[i] = 0.0f;
+    __syncthreads();
+    unsigned short* const w1 = reinterpret_cast<unsigned short*>(u4 + W1B);
+    unsigned short* const w2 = reinterpret_cast<unsigned short*>(u4 + W2B);
+    unsigned short* const wt = reinterpret_cast<unsigned short*>(u4 + WTB);
+    unsigned short* const w1t = reinterpret_cast<unsigned short*>(u4 + W1T);
+    // element (n, k) of a stacked B operand with NH n-rows per copy: hi at n, lo at NH + n
+    auto put = [](unsigned short* w, int NH, int n, int k, uint32_t hi, uint32_t lo) {
+      w[((k >> 3) * 2 * NH + n) * 8 + (k & 7)] = (unsigned short)hi;
+      w[((k >> 3) * 2 * NH + NH + n) * 8 + (k & 7)] = (unsigned short)lo;
+    };
+    const float one_in = ACT == ACT_TANH ? 20.0f : 1.0f;   // act(one_in) == 1 exactly: the constant-1 unit of H1 / H2
+    for (int e = tid; e < n5 + 2; e += nthr) {
+      uint32_t hi, lo;
+      if (e < n2) {                                   // W1[i][j]: layer-1 B operand [n = j][k = i]; the time row (i = 0) and
+        const int i = e < n1 ? e / H : nin, j = e < n1 ? e % H : e - n1;   // b1 (i = nin) live in the per-step effective bias
+        tc::split_bf16(th[e], hi, lo);
+        if (i >= 1 && i < nin) put(w1, NB, j, i, hi, lo);
+        if (i < nin) put(w1t, 16, i, j, hi, lo);      // input-gradient B operand [n = i][k = j]
+      } else if (e < n4) {                            // W2[k][j], b2[j] (k = H): layer-2 B operand [n = j][k]
+        const int k = e < n3 ? (e - n2) / H : H, j = e < n3 ? (e - n2) % H : e - n3;
+        tc::split_bf16(th[e], hi, lo);
+        put(w2, NB, j, k, hi, lo);
+        if (k < H) put(wt, NB, k, j, hi, lo);         // W2^T: B operand [n = k][k' = j]
+      } else if (e < n5) {
+        w3s[e - n4] = th[e];                          // W3[k][0], k < H  (entries >= H stay 0: no delta for the constant unit)
+      } else if (e == n5) {                           // (the constant-1 unit of H1 is written with the effective bias)
+      } else {                                        // the constant-1 unit of H2: act(one_in * 1) == 1
+        tc::split_bf16(one_in, hi, lo);
+        put(w2, NB, H, H, hi, lo);
+      }
+    }
+  }
+}
+
 // Tile-major record -> the plane layout of fbsdej_solver_loss' trajectory output: X [N+1][D][B].
 template <int D>
 __global__ void untile_traj_kernel(const float* __restrict__ rec, const float* __restrict__ recN, TileMap map, int B, int N,
@@ -749,6 +786,16 @@ __global__ void untile_traj_kernel(const float* __restrict__ rec, const float* _
 
 }  // namespace rtc
 
+size_t reg_tc_wimg_fwd_floats() { return (size_t)rtc::fwd::OFF_RED; }
+size_t reg_tc_wimg_floats() { return (size_t)rtc::fwd::OFF_RED + rtc::bwd::WIMG_BYTES / 4; }
+// builds both operand images (forward image first, adjoint image behind it) from a.theta
+int launch_reg_stage_operands(const PricingArgs& a, float* img, cudaStream_t st) {
+  float* img_b = img + rtc::fwd::OFF_RED;
+  if (a.netA.act == ACT_TANH) rtc::reg_stage_operands_kernel<ACT_TANH><<<2, 256, 0, st>>>(a, img, img_b);
+  else rtc::reg_stage_operands_kernel<ACT_RELU><<<2, 256, 0, st>>>(a, img, img_b);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
 size_t reg_tc_backward_smem() { return sizeof(float) * (size_t)rtc::bwd::SMEM_FLOATS; }
 size_t reg_tc_forward_smem(int D) { return sizeof(float) * (size_t)(D == 10 ? rtc::fwd::smem_floats<10>() : rtc::fwd::smem_floats<1>()); }
 
