@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
         tc::tc_fence_after();
         gemm_k<2, 16>(tmem + C_ACC, sa(D1_HI), sa(D1_LO), sa(W1T));
         tc::mma_commit(bar_f);
-        gemm_rows_stacked<32>(tmem + C_W1, sa(D1_HI), sa(XA_HI), started ? 1u : 0u);   // [D1 hi | D1 lo]^T [X hi | X lo] = dW1^T
+        gemm_rows_stacked<32, 64>(tmem + C_W1, sa(D1_HI), sa(XA_HI), started ? 1u : 0u);   // [D1 hi | D1 lo]^T [X hi | X lo] = dW1^T (M = 64)
         tc::mma_commit(bar_w);
       }
       started = 1;
@@ -301,10 +301,11 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
       }
     }
     __syncthreads();
-    if (started && pass == 0) {                        // lanes: D1 hi j, D1 lo 24 + j; columns: X hi i, X lo 16 + i
+    if (started && pass == 0) {                        // rows (M = 64 lane map): D1 hi j, D1 lo 24 + j; columns: X hi i, X lo 16 + i
       for (int e = row; e < (nin + 1) * H; e += kThreads) {
         const int i = e / H, j = e % H;                // i = nin: b1
-        g[e] = (S[j * SW + i] + S[j * SW + 16 + i]) + (S[(24 + j) * SW + i] + S[(24 + j) * SW + 16 + i]);   // hi.hi + hi.lo + lo.hi + lo.lo
+        const int lh = lane_of_row_m64(j), ll = lane_of_row_m64(24 + j);
+        g[e] = (S[lh * SW + i] + S[lh * SW + 16 + i]) + (S[ll * SW + i] + S[ll * SW + 16 + i]);   // hi.hi + hi.lo + lo.hi + lo.lo
       }
     } else if (started) {                              // lanes: H1 hi 0..23, H2 hi 24..47, H1 lo 48..71, H2 lo 72..95
       for (int e = row; e < (H + 1) * H; e += kThreads) {

@@ -51,9 +51,12 @@ __device__ __forceinline__ void load_acc(uint32_t lane_base, float (&v)[NJ]) {
 // are contiguous along M and those of B along N, so ONE MMA per 16-row slice forms all four hi/lo cross products in
 // separate accumulator blocks:  D[m][n], m in [A_hi features | A_lo features], n in [B_hi | B_lo] (24 columns each).
 // The three blocks that matter (hi.hi, hi.lo, lo.hi) are added when the accumulators are read at the end of the kernel.
-template <int NN>
+// MM = 64 when the stacked A features fit 64 rows: the MMA then reads half the A bytes from shared memory (these small MMAs are
+// bound by their operand reads: scripts/mma_microbench.cu), and accumulator row m lands in lane (m / 16) * 32 + m % 16.
+__host__ __device__ constexpr int lane_of_row_m64(int m) { return (m >> 4) * 32 + (m & 15); }
+template <int NN, int MM = 128>
 __device__ __forceinline__ void gemm_rows_stacked(uint32_t tmem_d, uint32_t a, uint32_t b, uint32_t acc0) {
-  constexpr uint32_t id = tc::idesc_bf16(128, NN, true, true);
+  constexpr uint32_t id = tc::idesc_bf16(MM, NN, true, true);
 #pragma unroll
   for (int s = 0; s < 8; ++s)                       // 128 rows = 8 x 16
     tc::mma_bf16(tmem_d, tc::smem_desc(a + s * 256, 128, 2048), tc::smem_desc(b + s * 256, 128, 2048), id, (s > 0) ? 1u : acc0);
