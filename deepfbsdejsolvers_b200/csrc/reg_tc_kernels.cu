@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
   float* const w3s = smem + OFF_W3;
   uint64_t* const bar_f = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* const bar_w = bar_f + 1;
+  uint64_t* const bar_g = bar_f + 3;                    // (slot 2 holds the TMEM base)
   uint32_t* const tslot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 4);
   const int row = threadIdx.x, warp = row >> 5;
   const bool issuer = (row & 31) == 0;
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
   for (int i = row; i < SMEM_FLOATS; i += kThreads)
     if (i < W_BASE * 4 || i >= OFF_W3 + 24) smem[i] = 0.0f;
   __syncthreads();
-  if (row == 0) { tc::mbar_init(bar_f, 1); tc::mbar_init(bar_w, 1); tc::fence_mbar_init(); }
+  if (row == 0) { tc::mbar_init(bar_f, 1); tc::mbar_init(bar_w, 1); tc::mbar_init(bar_g, 1); tc::fence_mbar_init(); }
   __syncthreads();
   if (row == 0) {
     tc::mbar_arrive_expect_tx(bar_w, WIMG_BYTES);
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
   const int bias_idx = ((nin >> 3) * 2 * NB + row) * 8 + (nin & 7);   // hi copy; the lo copy is NB n-rows further
   const uint32_t sbase = tc::smem_u32(u4);
   auto sa = [&](int off_u4) { return sbase + (uint32_t)off_u4 * 16u; };
-  uint32_t phase_f = 0, phase_w = 1, pending_w = 0, started = 0;
+  uint32_t phase_f = 0, phase_w = 1, phase_g = 0, pending_w = 0, started = 0;
   auto wait_f = [&]() { tc::mbar_wait(bar_f, phase_f); phase_f ^= 1; tc::tc_fence_after(); };
 
   const float invB = a.inv_B, invBN = a.inv_B / (float)a.N, rdt = a.r * a.dt;
@@ -241,21 +242,29 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
       publish();
       if (warp == 2 && issuer) {
         tc::tc_fence_after();
-        gemm_rows_stacked<48>(tmem + C_W2, sa(H1_HI), sa(D2_HI), started ? 1u : 0u);   // [H1 | H2 (hi) | H1 | H2 (lo)]^T [D2 hi | lo]
+        // the input-gradient GEMM first: its result is on the step's critical chain, the weight-gradient GEMM is not (the
+        // tensor pipe is in order); the weight-gradient GEMM gets its own barrier because D1 overwrites tiles it reads
         gemm_k<2, NB>(tmem + C_ACC, sa(D2_HI), sa(D2_LO), sa(WTB));
         tc::mma_commit(bar_f);
+        gemm_rows_stacked<48>(tmem + C_W2, sa(H1_HI), sa(D2_HI), started ? 1u : 0u);   // [H1 | H2 (hi) | H1 | H2 (lo)]^T [D2 hi | lo]
+        tc::mma_commit(bar_g);
       }
       wait_f();
       // ---- delta 1 -> DX, WG1 ---------------------------------------------------------------------------------
+      {
+        float d1[24];
 #pragma unroll
-      for (int c8 = 0; c8 < 3; ++c8) {
-        float t8[8], q8[8];
-        tc::tmem_ld8(lane_base + C_ACC + 8 * c8, t8);
-        tc::tmem_ld8(lane_base + C_ACC + NB + 8 * c8, q8);
-        tc::tmem_ld_wait();
+        for (int c8 = 0; c8 < 3; ++c8) {
+          float q8[8];
+          tc::tmem_ld8(lane_base + C_ACC + 8 * c8, reinterpret_cast<float (&)[8]>(d1[8 * c8]));
+          tc::tmem_ld8(lane_base + C_ACC + NB + 8 * c8, q8);
+          tc::tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 8; ++q) t8[q] = (t8[q] + q8[q]) * dactf<ACT>(h1[8 * c8 + q]);
-        tc::store_bf16x8(u4 + D1_HI, u4 + D1_LO, c8, row, t8);
+          for (int q = 0; q < 8; ++q) d1[8 * c8 + q] = (d1[8 * c8 + q] + q8[q]) * dactf<ACT>(h1[8 * c8 + q]);
+        }
+        tc::mbar_wait(bar_g, phase_g); phase_g ^= 1;     // WG2 has read H2 / H1_lo: their tiles may become D1
+#pragma unroll
+        for (int c8 = 0; c8 < 3; ++c8) tc::store_bf16x8(u4 + D1_HI, u4 + D1_LO, c8, row, d1 + 8 * c8);
       }
       publish();
       if (warp == 3 && issuer) {
