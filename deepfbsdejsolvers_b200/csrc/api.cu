@@ -55,7 +55,7 @@ void dev_free(T*& p) {
   p = nullptr;
 }
 
-int padded_width(int H) { return H <= 23 ? 24 : (H <= 31 ? 32 : -1); }
+int padded_width(int H) { return H <= 23 ? 24 : (H <= 31 ? 32 : (H <= 35 ? 36 : -1)); }
 
 // ---- VG: Lewis-FFT integral table + local not-a-knot cubic spline (pricingModels.py:156-179) -------------
 void fft_inplace(std::vector<std::complex<double>>& x, bool inverse) {
@@ -731,7 +731,8 @@ int fbsdej_solver_create(fbsdej_ctx* ctx, const fbsdej_solver_desc* desc, const 
     FB_REQUIRE(nd.nout == expect_out[k], "net " + std::to_string(k) + ": nout must be " + std::to_string(expect_out[k]));
     FB_REQUIRE(nd.act == FBSDEJ_ACT_TANH || nd.act == FBSDEJ_ACT_RELU, "unknown activation");
     const int hp = padded_width(nd.H);
-    FB_REQUIRE(nd.H >= 1 && hp > 0, "hidden width must be in [1, 31]");
+    FB_REQUIRE(nd.H >= 1 && hp > 0, "hidden width must be in [1, 35]");
+    FB_REQUIRE(hp <= 32 || (reg && model != FBSDEJ_MODEL_MFG), "hidden width 32..35 is compiled for the compensator-free pricing solvers only (else <= 31)");
     HP = std::max(HP, hp);
     FB_REQUIRE(nd.nin + 1 <= hp && nd.nout <= NOP, "network too wide for the compiled tiles");
     nets[k]->nin = nd.nin; nets[k]->H = nd.H; nets[k]->nout = nd.nout; nets[k]->act = nd.act; nets[k]->ext_off = off;

@@ -320,7 +320,7 @@ size_t mfg_smem_bytes(int HP, const MFGArgs& a, bool backward) {
 }
 
 int mfg_blocks_per_sm(int HP, const MFGArgs& a, bool backward) {
-  if (HP != 24) return 1;
+  if (HP != 24) return 1;                   // (HP = 32: 199 KB of shared memory, one CTA per SM)
   const size_t smem = mfg_smem<24>(a, backward);
   int nb = 0;
   if (!backward) {
@@ -335,23 +335,28 @@ int mfg_blocks_per_sm(int HP, const MFGArgs& a, bool backward) {
   return nb < 1 ? 1 : nb;
 }
 
-int launch_mfg(int HP, const MFGArgs& a, int grid, bool backward, cudaStream_t st) {
-  if (HP != 24) {
-    set_error("mfg kernels: padded hidden width " + std::to_string(HP) + " not compiled (H <= 23)");
-    return -1;
-  }
-  const size_t smem = mfg_smem<24>(a, backward);
+template <int HP>
+static int launch_mfg_hp(const MFGArgs& a, int grid, bool backward, cudaStream_t st) {
+  const size_t smem = mfg_smem<HP>(a, backward);
+  if (smem > 227 * 1024) { set_error("mfg kernels: shared-memory footprint exceeds 227 KB"); return -1; }
   if (!backward) {
-    auto kern = mfg_forward<24>;
+    auto kern = mfg_forward<HP>;
     FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kMfgThreads, smem, st>>>(a);
   } else {
-    auto kern = mfg_backward<24>;
+    auto kern = mfg_backward<HP>;
     FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kMfgThreads, smem, st>>>(a);
   }
   FB_CUDA(cudaGetLastError());
   return 0;
+}
+// compiled widths: HP = 24 (H <= 23), HP = 32 (H <= 31)
+int launch_mfg(int HP, const MFGArgs& a, int grid, bool backward, cudaStream_t st) {
+  if (HP == 24) return launch_mfg_hp<24>(a, grid, backward, st);
+  if (HP == 32) return launch_mfg_hp<32>(a, grid, backward, st);
+  set_error("mfg kernels: padded hidden width " + std::to_string(HP) + " not compiled (H <= 31)");
+  return -1;
 }
 
 }  // namespace fbsdej

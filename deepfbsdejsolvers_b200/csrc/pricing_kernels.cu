@@ -608,12 +608,22 @@ static int launch_one(const PricingArgs& a, int grid, bool backward, cudaStream_
   FB_CUDA(cudaGetLastError());
   return 0;
 }
+// Compiled widths: HP = 24 (H <= 23: every kernel incl. the tcgen05 variants), HP = 32 (H <= 31: fp32 FFMA kernels), HP = 36
+// (H <= 35, e.g. the H = 32 variant of SURVEY 8d config 3: the compensator-free solvers only - the 4 x 4 weight-gradient blocks
+// of a d = 10 jump network would outnumber the 128 threads of a CTA).
 template <class Model, int HP>
 static int launch_pair(const PricingArgs& a, int grid, bool backward, cudaStream_t st) {
-  if (a.has_jump && a.mma_mode == 1) {   // jump network on tcgen05 (jump_tc.cuh): two-network schemes, d = 1
-    return launch_one<Model, HP, true, true>(a, grid, backward, st);
+  if constexpr (HP == 24) {
+    if (a.has_jump && a.mma_mode == 1) {   // jump network on tcgen05 (jump_tc.cuh): two-network schemes, d = 1
+      return launch_one<Model, HP, true, true>(a, grid, backward, st);
+    }
   }
-  if (a.has_jump) return launch_one<Model, HP, true>(a, grid, backward, st);
+  if (a.mma_mode == 1 && (HP != 24 || a.has_jump)) { set_error("tcgen05 kernels: hidden width <= 22 only"); return -1; }
+  if constexpr (HP == 36) {
+    if (a.has_jump) { set_error("pricing kernels: hidden width 32..35 is compiled for the compensator-free (Reg) solvers only"); return -1; }
+  } else {
+    if (a.has_jump) return launch_one<Model, HP, true>(a, grid, backward, st);
+  }
   if (a.mma_mode == 1) {   // compensator-free solvers on tcgen05 (reg_tc_kernels.cu)
     const int model = std::is_same<Model, VGModel>::value ? 1 : 0;
     return backward ? launch_reg_tc_backward(model, Model::D, a, grid, st) : launch_reg_tc_forward(model, Model::D, a, grid, st);
@@ -683,8 +693,20 @@ static int occ_one(const PricingArgs& a, bool backward) {
   if (getenv("FBSDEJ_DEBUG")) fprintf(stderr, "[fbsdej] occupancy(%s, jtc=%d): %d CTAs/SM, smem %zu\n", backward ? "backward" : "forward", (int)JTC, nb, smem);
   return nb;
 }
+template <class Model>
+static int occ_pair24(const PricingArgs& a, bool backward);
 template <class Model, int HP>
 static int occ_pair(const PricingArgs& a, bool backward) {
+  if constexpr (HP != 24) {
+    if (a.has_jump) { if constexpr (HP == 36) return 1; else return occ_one<Model, HP, true>(a, backward); }
+    return occ_one<Model, HP, false>(a, backward);
+  } else {
+    return occ_pair24<Model>(a, backward);
+  }
+}
+template <class Model>
+static int occ_pair24(const PricingArgs& a, bool backward) {
+  constexpr int HP = 24;
   // tcgen05 kernels, by construction: adjoint 4 CTAs per SM (<= 128 registers, 54.9 KB shared memory, 128 TMEM columns),
   // forward 5 (<= 102 registers, 8 KB, 96 columns); the occupancy calculator does not know about TMEM
   if (a.mma_mode == 1 && !a.has_jump) {
@@ -700,28 +722,36 @@ static int occ_pair(const PricingArgs& a, bool backward) {
   return occ_one<Model, HP, false>(a, backward);
 }
 // resident CTAs per SM of the kernel that launch_pricing would run
-int pricing_blocks_per_sm(int model, int D, int HP, const PricingArgs& a, bool backward) {
-  if (HP == 24) {
-    if (model == 0 && D == 1) return occ_pair<MertonModel<1>, 24>(a, backward);
-    if (model == 0 && D == 10) return occ_pair<MertonModel<10>, 24>(a, backward);
-    if (model == 1 && D == 1) return occ_pair<VGModel, 24>(a, backward);
-  }
+template <int HP>
+static int blocks_per_sm_hp(int model, int D, const PricingArgs& a, bool backward) {
+  if (model == 0 && D == 1) return occ_pair<MertonModel<1>, HP>(a, backward);
+  if (model == 0 && D == 10) return occ_pair<MertonModel<10>, HP>(a, backward);
+  if (model == 1 && D == 1) return occ_pair<VGModel, HP>(a, backward);
   return 1;
+}
+int pricing_blocks_per_sm(int model, int D, int HP, const PricingArgs& a, bool backward) {
+  return HP == 24 ? blocks_per_sm_hp<24>(model, D, a, backward) : HP == 32 ? blocks_per_sm_hp<32>(model, D, a, backward)
+                                                                            : blocks_per_sm_hp<36>(model, D, a, backward);
 }
 
 size_t pricing_smem_bytes(int HP, const PricingArgs& a, bool backward) {
-  return HP == 24 ? pricing_smem<24>(a, backward) : pricing_smem<32>(a, backward);
+  return HP == 24 ? pricing_smem<24>(a, backward) : HP == 32 ? pricing_smem<32>(a, backward) : pricing_smem<36>(a, backward);
 }
 
 // model: 0 = Merton, 1 = VG.  Returns -1 (with message) for shapes that were not compiled in.
+template <int HP>
+static int launch_hp(int model, int D, const PricingArgs& a, int grid, bool backward, cudaStream_t st) {
+  if (model == 0 && D == 1) return launch_pair<MertonModel<1>, HP>(a, grid, backward, st);
+  if (model == 0 && D == 10) return launch_pair<MertonModel<10>, HP>(a, grid, backward, st);
+  if (model == 1 && D == 1) return launch_pair<VGModel, HP>(a, grid, backward, st);
+  return 1;
+}
 int launch_pricing(int model, int D, int HP, const PricingArgs& a, int grid, bool backward, cudaStream_t st) {
-  if (HP == 24) {
-    if (model == 0 && D == 1) return launch_pair<MertonModel<1>, 24>(a, grid, backward, st);
-    if (model == 0 && D == 10) return launch_pair<MertonModel<10>, 24>(a, grid, backward, st);
-    if (model == 1 && D == 1) return launch_pair<VGModel, 24>(a, grid, backward, st);
-  }
+  const int rc = HP == 24 ? launch_hp<24>(model, D, a, grid, backward, st) : HP == 32 ? launch_hp<32>(model, D, a, grid, backward, st)
+               : HP == 36 ? launch_hp<36>(model, D, a, grid, backward, st) : 1;
+  if (rc <= 0) return rc;
   set_error("pricing kernels: unsupported (model, d, padded width) = (" + std::to_string(model) + ", " +
-            std::to_string(D) + ", " + std::to_string(HP) + "); compiled: Merton d in {1,10}, VG d=1, H<=23");
+            std::to_string(D) + ", " + std::to_string(HP) + "); compiled: Merton d in {1,10}, VG d=1, H<=31 (Reg solvers: H<=35)");
   return -1;
 }
 

@@ -195,7 +195,9 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
       publish();
       if (warp == 0 && issuer) {
         tc::tc_fence_after();
+#if FBSDEJ_ABLATE != 12
         gemm_k<1, NB>(tmem + C_ACC, sa(XA_HI), sa(XA_LO), sa(W1B));
+#endif
         tc::mma_commit(bar_f);
       }
       wait_f();
@@ -211,7 +213,9 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
       publish();
       if (warp == 1 && issuer) {
         tc::tc_fence_after();
+#if FBSDEJ_ABLATE != 12
         gemm_k<2, NB>(tmem + C_ACC, sa(H1_HI), sa(H1_LO), sa(W2B));
+#endif
         tc::mma_commit(bar_f);
       }
       wait_f();
@@ -244,9 +248,13 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
         tc::tc_fence_after();
         // the input-gradient GEMM first: its result is on the step's critical chain, the weight-gradient GEMM is not (the
         // tensor pipe is in order); the weight-gradient GEMM gets its own barrier because D1 overwrites tiles it reads
+#if FBSDEJ_ABLATE != 12
         gemm_k<2, NB>(tmem + C_ACC, sa(D2_HI), sa(D2_LO), sa(WTB));
+#endif
         tc::mma_commit(bar_f);
+#if FBSDEJ_ABLATE != 11
         gemm_rows_stacked<48>(tmem + C_W2, sa(H1_HI), sa(D2_HI), started ? 1u : 0u);   // [H1 | H2 (hi) | H1 | H2 (lo)]^T [D2 hi | lo]
+#endif
         tc::mma_commit(bar_g);
       }
       wait_f();
@@ -269,9 +277,13 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
       publish();
       if (warp == 3 && issuer) {
         tc::tc_fence_after();
+#if FBSDEJ_ABLATE != 12
         gemm_k<2, 16>(tmem + C_ACC, sa(D1_HI), sa(D1_LO), sa(W1T));
+#endif
         tc::mma_commit(bar_f);
+#if FBSDEJ_ABLATE != 11
         gemm_rows_stacked<32, 64>(tmem + C_W1, sa(D1_HI), sa(XA_HI), started ? 1u : 0u);   // [D1 hi | D1 lo]^T [X hi | X lo] = dW1^T (M = 64)
+#endif
         tc::mma_commit(bar_w);
       }
       started = 1;

@@ -190,7 +190,9 @@ __device__ __forceinline__ void store_bf16x8(uint4* __restrict__ hi_tile, uint4*
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l[i]) : "f"(r1), "f"(r0));   // upper half <- first source
   }
   hi_tile[chunk * 128 + row] = make_uint4(h[0], h[1], h[2], h[3]);
+#if !(defined(FBSDEJ_ABLATE) && FBSDEJ_ABLATE == 14)
   lo_tile[chunk * 128 + row] = make_uint4(l[0], l[1], l[2], l[3]);
+#endif
 }
 
 }  // namespace tc

@@ -68,7 +68,12 @@ __device__ __forceinline__ float rcp_fast(float x) {
   return r;
 }
 template <int ACT>
-__device__ __forceinline__ float actf(float x) { return ACT == ACT_TANH ? tanh_fast(x) : fmaxf(x, 0.0f); }
+__device__ __forceinline__ float actf(float x) {
+#if defined(FBSDEJ_ABLATE) && FBSDEJ_ABLATE == 13
+  return 0.3f * x;
+#endif
+  return ACT == ACT_TANH ? tanh_fast(x) : fmaxf(x, 0.0f);
+}
 template <int ACT>
 __device__ __forceinline__ float dactf(float h) { return ACT == ACT_TANH ? fmaf(-h, h, 1.0f) : (h > 0.0f ? 1.0f : 0.0f); }
 

@@ -51,7 +51,8 @@ class DenseNet:
     def __init__(self, ndimOut: int, nbNeurons, activation="tanh"):
         self.nbNeurons = [int(h) for h in np.asarray(nbNeurons).reshape(-1)]
         if len(self.nbNeurons) != 2 or self.nbNeurons[0] != self.nbNeurons[1]:
-            raise ValueError("the sm_100a kernels are compiled for two equal hidden layers (reference default nbLayer=2)")
+            raise ValueError("the sm_100a kernels are compiled for two equal hidden layers (the reference's default nbLayer = 2) of "
+                             "width <= 35 for the compensator-free solvers, <= 31 otherwise (tcgen05: <= 22)")
         self.ndimOut = int(ndimOut)
         self.activation = activation_name(activation)
         self.params: Optional[np.ndarray] = None

@@ -214,3 +214,58 @@ def test_sparse_jump_injection_equals_dense(ctx):
                 s.set_noise(B, dW, J, None)
             outs.append(s.grad(B).copy())
     assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[1], outs[3])
+
+
+# ---- wider networks (mainMerton.py:13-14 / mainMFGComparison.py:14-17 expose nbNeuron; SURVEY 8d names an H = 32 variant of
+# config 3): fp32 FFMA kernels compiled for padded widths 32 (H <= 31) and 36 (H <= 35, compensator-free solvers) -----------------
+@pytest.mark.parametrize("scheme,d,Hn,B,M", [("SumLocalReg", 10, 32, 200, 0), ("MultiStepReg", 1, 35, 150, 0), ("SumLocalReg", 10, 27, 140, 0),
+                                              ("Global", 1, 30, 12, 90), ("SumLocal1", 1, 28, 20, 60), ("MultiStep2", 10, 26, 40, 48)])
+def test_wider_hidden_layers(ctx, scheme, d, Hn, B, M):
+    p = dict(H.MERTON, N=6)
+    om = MertonOracle(aLin=H.ALIN, limit=30 if d == 1 else 100, d=d, **p)
+    layout = H.pricing_layout("merton", scheme, d, H=Hn)
+    theta = H.random_theta(layout, 71)
+    noise = H.merton_noise(om, B, max(M, 1), seed=72, with_jmc=M > 0)
+    l32, g32, _ = H.oracle_pricing(om, scheme, layout, theta, noise, B)
+    l64, g64, aux64 = H.oracle_pricing(om, scheme, layout, theta, noise, B, dtype=torch.float64)
+    s = H.native_pricing(ctx, "merton", p, scheme, layout, d=d, M=M, limit=30 if d == 1 else 100)
+    s.set_theta(theta)
+    s.set_noise(B, H.to_planes(noise["dW"]), H.to_planes(noise["J"]), H.to_planes(noise["JMC"]) if M > 0 else None)
+    out, tx, ty, tz = s.loss(B, traj=True)
+    _close(out[0], l64)
+    _close(tx, aux64["X"].transpose(0, 2, 1))
+    g = s.grad(B)
+    _close(g[0], l64)
+    _grad_check(g[4:], g64, g32)
+    # three training steps through the CUDA graph run and move the parameters
+    s.train_steps(1, B, 3, 1e-3)
+    ctx.sync()
+    assert np.isfinite(s.get_theta()).all() and np.abs(s.get_theta() - theta).max() > 0
+
+
+def test_wider_hidden_layers_mfg(ctx):
+    from oracle.mfg import sample_mfg_noise
+    p = H.mfg_params(1, "stochastic")
+    om = MFGOracle(**p)
+    layout = H.mfg_layout("SumLocal", Hh=28, H=31)
+    theta = H.random_theta(layout, 73)
+    B = 70
+    noise = sample_mfg_noise(om, B, torch.Generator().manual_seed(74))
+    (lh32, li32), g32, _ = H.oracle_mfg(om, "SumLocal", layout, theta, noise, B)
+    (lh64, li64), g64, aux64 = H.oracle_mfg(om, "SumLocal", layout, theta, noise, B, dtype=torch.float64)
+    s = H.native_mfg(ctx, p, "SumLocal", layout)
+    s.set_theta(theta)
+    s.set_noise(B, noise["dW0"].numpy(), noise["dW"].numpy(), noise["dN"].numpy())
+    g = s.grad(B)
+    _close(g[1], lh64)
+    _close(g[2], li64)
+    _grad_check(g[4:], g64, g32)
+
+
+def test_unsupported_widths_fail_loudly(ctx):
+    from deepfbsdejsolvers_b200 import FbsdejError
+    p = dict(H.MERTON, N=4)
+    with pytest.raises(FbsdejError):       # H = 36 is not compiled
+        H.native_pricing(ctx, "merton", p, "SumLocalReg", H.pricing_layout("merton", "SumLocalReg", 1, H=36), d=1)
+    with pytest.raises(FbsdejError):       # jump schemes stop at H = 31
+        H.native_pricing(ctx, "merton", p, "Global", H.pricing_layout("merton", "Global", 1, H=33), d=1, M=8)
