@@ -54,6 +54,8 @@ def parse():
                          "reference the largest power of two <= the batch that keeps the run near two minutes - the CPU "
                          "restatement is more efficient on larger samples)")
     ap.add_argument("--mma", default="tcgen05", choices=["ffma", "tcgen05"], help="layer arithmetic of the fused kernels")
+    ap.add_argument("--hidden", type=int, default=21, help="hidden width of the networks (configs 3 / 5; 21 = the reference's; > 22 "
+                                                           "runs the fp32 FFMA kernels: SURVEY 8d's H = 32 variant)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -70,8 +72,8 @@ def workload_config(a, B, world):
     M = SOLVERS[a.solver] if a.M < 0 else a.M
     which = ("config 5: fixed global batch, sharded" if a.config == 5 else
              "config 3" if world == 1 else "config 3 on every GPU: %d x %d paths" % (world, B // world))
-    name = ("Merton d=10 geometric basket, N=100, H=21 tanh, Solver%s%s, B=%d paths (SURVEY 8d %s)"
-            % ("Global" + a.solver if a.solver.endswith("Reg") else a.solver + "FBSDE", "" if M == 0 else " M=%d" % M, B, which))
+    name = ("Merton d=10 geometric basket, N=100, H=%d tanh, Solver%s%s, B=%d paths (SURVEY 8d %s)"
+            % (H_WIDTH, "Global" + a.solver if a.solver.endswith("Reg") else a.solver + "FBSDE", "" if M == 0 else " M=%d" % M, B, which))
     return M, {"workload": name, "paths": B, "paths_per_gpu": B // world, "time_steps": MERTON["N"], "d": D, "hidden": H_WIDTH,
                "solver": a.solver,
                "compensator_M": M, "mma": a.mma, "parallelism": "dp%d" % world,
@@ -457,6 +459,9 @@ def run_native(a):
 
 if __name__ == "__main__":
     args = parse()
+    H_WIDTH = args.hidden
+    if H_WIDTH > 22:
+        args.mma = "ffma"
     if args.config in (1, 2, 4):
         from bench_reference_defaults import run_config       # scripts/: configs 1 / 2 / 4
         run_config(args)

@@ -80,17 +80,22 @@ class SolverBase:
     # networks on fresh increments; the sweep itself is the forward kernel with its trajectory dump -----------------------
     SEED_DIAG = 0x64696167
 
-    def _replay(self, nbSimul: int):
+    def _replay(self, nbSimul: int, noise=None):
+        """noise = (dW0, dW, dN), each [N, nbSimul]: replay on given increments (extension: the reference always draws fresh
+        ones); None: fresh device draws."""
         s = self.build()
-        self._ndiag = getattr(self, "_ndiag", 0) + 1
-        s.simulate(self.seed ^ self.SEED_DIAG, self._ndiag, nbSimul)
+        if noise is not None:
+            s.set_noise(nbSimul, *[np.ascontiguousarray(x, dtype=np.float32) for x in noise])
+        else:
+            self._ndiag = getattr(self, "_ndiag", 0) + 1
+            s.simulate(self.seed ^ self.SEED_DIAG, self._ndiag, nbSimul)
         out, tx, ty, _ = s.loss(nbSimul, traj=True)          # tx: (hS, S) [N+1, 2, B]; ty: (hY, Y) [N+1, 2, B]
         return s, out, tx.astype(np.float64), ty.astype(np.float64)
 
-    def simulateGlobalErr(self, nbSimul):
+    def simulateGlobalErr(self, nbSimul, noise=None):
         """(mean cost of the projected player, mean cost of the individual player, terminal mismatch): cost =
         sum_i dt f(S_i) + g(S_N) with f(U) = C U, g(X) = h1 + h2 X (MFGModel.py:92-98)."""
-        s, out, tx, ty = self._replay(nbSimul)
+        s, out, tx, ty = self._replay(nbSimul, noise)
         mm = self.mathModel
         N, dt = s.N, float(mm.T) / s.N
         run = dt * float(mm.C) * tx[:N].sum(axis=0)                                   # [2, B]
@@ -100,9 +105,9 @@ class SolverBase:
         mismatch = float(((last - gN) ** 2).mean(axis=1).sum())
         return float(cost[0]), float(cost[1]), mismatch
 
-    def followS(self, nbSimul):
+    def followS(self, nbSimul, noise=None):
         """Mean and (population) standard deviation of hS and S at every time step (MFGSolvers.py:148-178)."""
-        _, _, tx, _ = self._replay(nbSimul)
+        _, _, tx, _ = self._replay(nbSimul, noise)
         return (list(tx[:, 0].mean(axis=1)), list(tx[:, 0].std(axis=1)), list(tx[:, 1].mean(axis=1)), list(tx[:, 1].std(axis=1)))
 
     # checkpoint / resume (SURVEY 8f N4): parameters | Adam m, v, t | Philox iteration; the reference keeps nothing on disk

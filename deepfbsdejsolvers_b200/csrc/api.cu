@@ -9,6 +9,19 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges are no-ops unless a profiler injects its library
+
+// NVTX range around the launches of one phase of the training path (visible in Nsight Systems / ncu --nvtx); enabled with
+// FBSDEJ_NVTX=1 so that the default path pays nothing (tracing).
+struct NvtxRange {
+  bool on;
+  explicit NvtxRange(const char* name) {
+    static const bool enabled = getenv("FBSDEJ_NVTX") != nullptr;
+    on = enabled;
+    if (on) nvtxRangePushA(name);
+  }
+  ~NvtxRange() { if (on) nvtxRangePop(); }
+};
 
 #include "../../include/fbsdej.h"
 #include "mfg.cuh"
@@ -332,9 +345,9 @@ int run_pass(fbsdej_solver* s, const float* theta, int B, int B_global, float* o
     if (with_grad) grid_b = std::min(ntiles, s->ctx->sms * (tc ? 1 : mfg_blocks_per_sm(s->HP, a, true)));
     if (ensure_grid(s, std::max(grid_f, grid_b))) return -2;
     a.lpart = s->lpart; a.gpart = s->gpart; a.trajY = trajY;
-    if (tc ? launch_mfg_tc(a, grid_f, false, st) : launch_mfg(s->HP, a, grid_f, false, st)) return -1;
+    { NvtxRange r("fbsdej:forward"); if (tc ? launch_mfg_tc(a, grid_f, false, st) : launch_mfg(s->HP, a, grid_f, false, st)) return -1; }
     if (ev) cudaEventRecord(ev[0], st);
-    if (with_grad && (tc ? launch_mfg_tc(a, grid_b, true, st) : launch_mfg(s->HP, a, grid_b, true, st))) return -1;
+    { NvtxRange r("fbsdej:adjoint"); if (with_grad && (tc ? launch_mfg_tc(a, grid_b, true, st) : launch_mfg(s->HP, a, grid_b, true, st))) return -1; }
     if (ev) cudaEventRecord(ev[1], st);
   } else {
     PricingArgs a;
@@ -363,12 +376,13 @@ int run_pass(fbsdej_solver* s, const float* theta, int B, int B_global, float* o
       a.pois_thr = s->pois_thr; a.npois = s->npois;
       a.sqdt = (float)std::sqrt(s->mer.T / s->mer.N); a.muJ = (float)s->mer.muJ; a.sigJ = (float)s->mer.sigJ;
     }
-    if (launch_pricing(s->model, s->D, s->HP, a, grid_f, false, st)) return -1;
+    { NvtxRange r("fbsdej:forward"); if (launch_pricing(s->model, s->D, s->HP, a, grid_f, false, st)) return -1; }
     if (ev) cudaEventRecord(ev[0], st);
-    if (with_grad && launch_pricing(s->model, s->D, s->HP, a, grid_b, true, st)) return -1;
+    { NvtxRange r("fbsdej:adjoint"); if (with_grad && launch_pricing(s->model, s->D, s->HP, a, grid_b, true, st)) return -1; }
     if (ev) cudaEventRecord(ev[1], st);
   }
   // loss partials come from the forward grid, gradient partials from the backward grid
+  NvtxRange r_fin("fbsdej:reduce+adam");
   if (s->finish && with_grad) {
     const fbsdej_solver::Finish& f = *s->finish;
     XchgArgs x{};
@@ -393,6 +407,7 @@ int run_pass(fbsdej_solver* s, const float* theta, int B, int B_global, float* o
 int do_simulate(fbsdej_solver* s, uint64_t seed, uint32_t iteration, const uint32_t* iter_ptr, uint32_t path_offset,
                 int B, cudaEvent_t* ev = nullptr) {
   if (ensure_capacity(s, B)) return -2;
+  NvtxRange r_sim("fbsdej:simulate");
   cudaStream_t st = s->ctx->stream;
   const uint32_t lo = (uint32_t)seed, hi = (uint32_t)(seed >> 32);
   if (s->model == FBSDEJ_MODEL_MERTON) {

@@ -293,6 +293,61 @@ def mfg_case(scheme, couplage="ON"):
                 dN=torch.stack(dNs[:N], 0).numpy(), **{k: np.float64(v) for k, v in par.items()})
 
 
+def diag_case(scheme, nb=48):
+    """The reference's own MFG diagnostics (MFGSolvers.py:118-178, 436-459) on fresh networks: simulateGlobalErr and followS, with
+    the increments they drew."""
+    tf.random.seed(3000 + len(scheme))
+    tf.keras.initializers.GEN.manual_seed(23 + len(scheme))
+    Q = qaver_curve()
+    par = dict(T=0.25, R0=0.24, jumpFactor=8.0, alpha=30.0, beta=float(np.exp(-15.0)), coeffOU=5.0, A=150.0, K=50.0, pi=0.1,
+               p0=6.159423723, p1=87.4286117, f0=0.0, f1=1e4, theta=0.12, C=80.0, S0=0.0, h1=0.0, h2=600.0, sig0=0.1, sig=0.3,
+               alphaTarget=-0.2, coeffEqui=1.0)
+    Qt = torch.tensor(Q, dtype=torch.float32)
+    MFGM.QAver = Qt
+    model = MFGM.ModelCoupledFBSDE(par["T"], Qt, par["R0"], par["jumpFactor"], par["alpha"], par["beta"], par["coeffOU"], par["A"],
+                                   par["K"], par["pi"], par["p0"], par["p1"], par["f0"], par["f1"], par["theta"], par["C"], par["S0"],
+                                   par["h1"], par["h2"], par["sig0"], par["sig"], par["alphaTarget"], "stochastic", par["coeffEqui"])
+    method = {"Global": "Global", "SumLocal": "SumLocal"}[scheme]
+    wh, wi = (2, 3) if scheme == "Global" else (3, 4)
+    km = NETM.kerasModels(NETM.Net_hat, NETM.Net, method, wh, wi, 20 * np.ones((2,), dtype=np.int32), 22 * np.ones((2,), dtype=np.int32),
+                          "tanh", "tanh")
+    model.init(1)
+    build_net(km.model_hat, model.getProjectedStates())
+    build_net(km.model, model.getAllStates())
+    cls = {"Global": "SolverGlobalFBSDE", "SumLocal": "SolverSumLocalFBSDE"}[scheme]
+    solver = getattr(MFGS, cls)(model, km, 1e-3, "ON")
+    parts = [flat_net(km.model_hat), flat_net(km.model)]
+    if scheme == "Global":
+        parts.append(np.array([km.model_hat.Y0_hat.detach().numpy(), km.model.Y0.detach().numpy()], dtype=np.float32))
+    theta0 = np.concatenate(parts).astype(np.float32)
+    out = dict(kind="mfg", scheme=scheme, nb=nb, N=model.N, QAver=Q, theta0=theta0, **{k: np.float64(v) for k, v in par.items()})
+    N, sq = model.N, np.float32(np.sqrt(model.dt))
+    for which in (("err", "follow") if hasattr(solver, "followS") else ("err",)):     # followS exists on SolverGlobalFBSDE only
+        gauss, dNs = [], []
+        orig_normal, orig_dN = tf.random.normal, model.dN
+
+        def normal(shape, *a, **k):
+            x = orig_normal(shape, *a, **k)
+            gauss.append(x.detach().clone())
+            return x
+
+        def dN():
+            n, c = orig_dN()
+            dNs.append(n.detach().clone())
+            return n, c
+        tf.random.normal, model.dN = normal, dN
+        res = solver.simulateGlobalErr(nb) if which == "err" else solver.followS(nb)
+        tf.random.normal, model.dN = orig_normal, orig_dN
+        out[which + "_dW0"] = (sq * torch.stack(gauss[0:2 * N:2], 0)).numpy()
+        out[which + "_dW"] = (sq * torch.stack(gauss[1:2 * N:2], 0)).numpy()
+        out[which + "_dN"] = torch.stack(dNs[:N], 0).numpy()
+        if which == "err":
+            out["err_result"] = np.array([float(x) for x in res], dtype=np.float64)
+        else:
+            out["follow_result"] = np.array([[float(v) for v in col] for col in res], dtype=np.float64)     # [4][N+1]
+    return out
+
+
 def main():
     import contextlib
     import io
@@ -312,6 +367,11 @@ def main():
     np.savez_compressed(os.path.join(HERE, "traj", "merton_Global_25steps.npz"), **d)
     print("trajectory: merton Global", int(d["nsteps"]), "steps, loss", float(d["losses"][0]), "->", float(d["losses"][-1]),
           "Y0", float(d["Y0_after_step"][0]), "->", float(d["Y0_after_step"][-1]))
+    for scheme in ("Global", "SumLocal"):
+        with contextlib.redirect_stdout(io.StringIO()):
+            d = diag_case(scheme)
+        np.savez_compressed(os.path.join(HERE, "diag", f"mfg_{scheme}_diagnostics.npz"), **d)
+        print("mfg diagnostics", scheme, "simulateGlobalErr", d["err_result"])
     for scheme in ("Global", "SumLocalReg"):      # couplage OFF (the other OFF variants crash in the reference: MFGSolvers.py:291,431)
         with contextlib.redirect_stdout(io.StringIO()):
             d = mfg_case(scheme, couplage="OFF")

@@ -130,3 +130,29 @@ def test_cuda_follows_the_reference_training_trajectory(ctx, tensor_cores):
     th = s.get_theta()
     solid = np.abs(c["theta_final"] - c["theta0"]) > 0.2 * n * float(c["lr"])
     np.testing.assert_allclose(th[solid], c["theta_final"][solid], rtol=0, atol=0.03 * n * float(c["lr"]))
+
+
+DIAG_CASES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "diag", "*.npz")))
+
+
+@pytest.mark.parametrize("path", DIAG_CASES, ids=[os.path.basename(p)[:-4] for p in DIAG_CASES])
+def test_mfg_diagnostics_reproduce_the_reference(ctx, path):
+    """simulateGlobalErr / followS of the drop-in MFG solver classes against the outputs of the reference's own
+    methods (MFGSolvers.py:118-178, 436-459, executed through the TensorFlow stand-in) on the increments the reference drew."""
+    from deepfbsdejsolvers_b200 import coupledMFG as cm
+    c = load_case(path)
+    assert len(DIAG_CASES) == 2
+    scheme, nb = str(c["scheme"]), int(c["nb"])
+    mm = cm.ModelCoupledFBSDE(QAver=c["QAver"], jumpModel="stochastic", **{k: c[k] for k in MFG_KEYS})
+    wh, wi, method, cls = ((2, 3, "Global", "SolverGlobalFBSDE") if scheme == "Global" else (3, 4, "SumLocal", "SolverSumLocalFBSDE"))
+    km = cm.kerasModels(cm.Net_hat, cm.Net, method, wh, wi, [20, 20], [22, 22], "tanh", "tanh")
+    solver = getattr(cm, cls)(mm, km, 1e-3, "ON", ctx=ctx)
+    solver.build().set_theta(c["theta0"])
+    got = np.array(solver.simulateGlobalErr(nb, noise=(c["err_dW0"], c["err_dW"], c["err_dN"])))
+    ref = c["err_result"]
+    print(scheme, "simulateGlobalErr", got, "reference", ref)
+    assert np.all(np.abs(got - ref) <= 2e-5 * np.abs(ref) + 1e-5), (got, ref)
+    if "follow_result" in c:
+        f = np.array(solver.followS(nb, noise=(c["follow_dW0"], c["follow_dW"], c["follow_dN"])))
+        assert f.shape == c["follow_result"].shape
+        assert np.abs(f - c["follow_result"]).max() <= 2e-6 + 2e-5 * np.abs(c["follow_result"]).max()
