@@ -462,22 +462,54 @@ __global__ void __launch_bounds__(2 * kThreads, 4) reg_forward_tc(const PricingA
 #else
         if constexpr (RNG) {
 #endif
-          // one Philox block per asset pair; the rare cells (a count >= 2, both draws jumping, a far-tail size: ~0.4 %) are
-          // redone on the exact path after the branch-free common case of every pair, so that the pairs interleave
+          // one Philox block per asset pair.  Jump sizes: a draw with exactly one jump takes its size from the residual of the
+          // Poisson inversion through the inverse-normal polynomial (sim_device.cuh: jump_sizes_fast - same classification, same
+          // arithmetic, hence the same bits as sim_merton_kernel).  At lam dt = 0.03 a path-step has such a draw with probability
+          // 0.26 and two of them with 0.03, so the polynomial is evaluated ONCE per step, on the pending candidate, instead of
+          // once per pair; a second candidate flushes the pending one first (divergent, rare).  Rare cells (a count >= 2, both
+          // draws of a pair jumping, a far-tail size: ~0.4 %) are redone on the exact path below.
           constexpr int KP = (D + 1) / 2;
           float jj[2 * KP];
-          uint32_t rare_any = 0;
+#pragma unroll
+          for (int k = 0; k < 2 * KP; ++k) jj[k] = 0.0f;
+          uint32_t rare_any = 0, cand_u = t0, cand_k = 255u;
+          auto flush_candidate = [&]() {
+            const float v = ((float)(cand_u - t0) + 0.5f) * inv_w1;
+            const float x = fmaf(2.0f, v, -1.0f);
+            float w = -0.6931471805599453f * lg2_raw(fmaf(-x, x, 1.0f));
+            const bool tail = !(w < 5.0f);
+            w -= 2.5f;
+            float q = 2.81022636e-08f;
+            q = fmaf(q, w, 3.43273939e-07f);
+            q = fmaf(q, w, -3.5233877e-06f);
+            q = fmaf(q, w, -4.39150654e-06f);
+            q = fmaf(q, w, 0.00021858087f);
+            q = fmaf(q, w, -0.00125372503f);
+            q = fmaf(q, w, -0.00417768164f);
+            q = fmaf(q, w, 0.246640727f);
+            q = fmaf(q, w, 1.50140941f);
+            const float jump = fmaf(sigJL, 1.4142135623730951f * q * x, muJL);
+            if (tail && cand_k != 255u) rare_any |= 1u << cand_k;       // far tail: exact path
+#pragma unroll
+            for (int k = 0; k < 2 * KP; ++k) jj[k] = (cand_k == (uint32_t)k) ? jump : jj[k];
+          };
 #pragma unroll
           for (int kp = 0; kp < KP; ++kp) {
             const uint4 r = Philox::rand4(gid, ((uint32_t)i << 8) | (uint32_t)kp, rng_iter, STREAM_PATH, a.seed_lo, a.seed_hi);
             float w0, w1;
             box_muller_fast(r.x, r.y, a.sqdt, w0, w1);
-            uint32_t rare;
-            jump_sizes_fast(r.z, r.w, t0, t1, inv_w1, muJL, sigJL, jj[2 * kp], jj[2 * kp + 1], rare);
-            rare_any |= rare << (2 * kp);
+            const bool one0 = (r.z >= t0) && (r.z < t1), one1 = (r.w >= t0) && (r.w < t1);
+            const bool both = one0 && one1;
+            rare_any |= (((r.z >= t1) || both) ? 1u : 0u) << (2 * kp) | (((r.w >= t1) || both) ? 2u : 0u) << (2 * kp);
+            if (one0 != one1) {                            // exactly one single jump in this pair
+              if (cand_k != 255u) flush_candidate();
+              cand_u = one1 ? r.w : r.z;
+              cand_k = (uint32_t)(2 * kp) + (one1 ? 1u : 0u);
+            }
             E[2 * kp] = fmaf(sigL, w0, driftL);
             if (2 * kp + 1 < D) E[2 * kp + 1] = fmaf(sigL, w1, driftL);
           }
+          flush_candidate();
           if (rare_any) {
 #pragma unroll
             for (int kp = 0; kp < KP; ++kp) {
