@@ -80,7 +80,7 @@ def test_merton_d1_price_table(ctx, scheme, tensor_cores):
     assert e_gpu <= (3e-4 if tensor_cores else 1e-4), f"gradient error {e_gpu:.3e}"
 
 
-@pytest.mark.parametrize("scheme", ["Global", "MultiStep2", "SumLocal1", "SumLocalReg", "MultiStepReg"])
+@pytest.mark.parametrize("scheme", ["Global", "MultiStep1", "MultiStep2", "SumLocal1", "SumLocal2", "SumLocalReg", "MultiStepReg"])
 @pytest.mark.parametrize("price_table", [False, True])
 def test_merton_d10(ctx, scheme, price_table):
     B, M, d = 64, 96, 10

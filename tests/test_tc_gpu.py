@@ -199,7 +199,7 @@ def test_jump_network_on_tensor_cores_vg(ctx, scheme):
     _check_jump(s, B, l64, g64, g32, aux64, False)
 
 
-@pytest.mark.parametrize("scheme", ["Global", "MultiStep2", "SumLocal1"])
+@pytest.mark.parametrize("scheme", ["Global", "MultiStep1", "MultiStep2", "SumLocal1", "SumLocal2"])
 @pytest.mark.parametrize("B,M", [(64, 400), (1500, 96)])
 def test_jump_network_on_tensor_cores_merton_d10(ctx, scheme, B, M):
     """d = 10: the jump rows have 22 input features (three 8-feature chunks of the operand tile); one path per CTA with a
@@ -240,3 +240,36 @@ def test_jump_network_on_tensor_cores_one_path_per_thread(ctx):
     s.set_theta(theta)
     s.set_noise(B, H.to_planes(noise["dW"]), H.to_planes(noise["J"]), H.to_planes(noise["JMC"]))
     _check_jump(s, B, l64, g64, g32, aux64, True)
+
+
+@pytest.mark.parametrize("kind", ["reg", "jump", "mfg"])
+def test_tensor_core_kernels_are_bitwise_repeatable(ctx, kind):
+    """compute-sanitizer is closed on this GPU pool (profiles/r2_sanitizer_unavailable.txt), so the hand-written synchronisation of
+    the tcgen05 kernels (operand-tile reuse behind mbarriers, the warp-specialised ring, the DSMEM cluster sums) is exercised the
+    other way round: a race shows up as run-to-run differences, and eight repetitions of the same call must agree bit for bit."""
+    from oracle.mfg import sample_mfg_noise
+    if kind == "mfg":
+        p = H.mfg_params(1, "stochastic")
+        layout = H.mfg_layout("MultiStep")
+        s = H.native_mfg(ctx, p, "MultiStep", layout, tensor_cores=True)
+        s.set_theta(H.random_theta(layout, 4))
+        nz = sample_mfg_noise(MFGOracle(**p), 300, torch.Generator().manual_seed(8))
+        s.set_noise(300, nz["dW0"].numpy(), nz["dW"].numpy(), nz["dN"].numpy())
+        run = lambda: s.grad(300)
+    elif kind == "reg":
+        p = dict(H.MERTON, N=25)
+        layout = H.pricing_layout("merton", "SumLocalReg", 10)
+        s = H.native_pricing(ctx, "merton", p, "SumLocalReg", layout, d=10, limit=100, tensor_cores=True, price_table=True)
+        s.set_theta(H.random_theta(layout, 5))
+        run = lambda: ctx.to_host(s.grad_step(77, 70001, 70001, 0)).numpy().copy()     # mixed 128 / 96-row tiles, in-kernel increments
+    else:
+        p = dict(H.MERTON, N=10)
+        layout = H.pricing_layout("merton", "Global", 1)
+        s = H.native_pricing(ctx, "merton", p, "Global", layout, d=1, M=500, tensor_cores=True)
+        s.set_theta(H.random_theta(layout, 6))
+        s.simulate(5, 0, 12)                                                           # clusters of CTAs per path
+        run = lambda: s.grad(12)
+    first = run()
+    assert np.isfinite(first).all()
+    for _ in range(7):
+        assert np.array_equal(run(), first)
