@@ -153,16 +153,18 @@ struct JumpTcBwd {
   uint4* w4;
   uint64_t* bar_f;
   uint64_t* bar_w;
-  uint32_t tmem, lane_base, sbase, wbase, phase_f, phase_w, pending_w, started;
+  uint64_t* bar_g;
+  uint32_t tmem, lane_base, sbase, wbase, phase_f, phase_w, phase_g, pending_w, started;
   float w0, b1v;
   int H, nin, nout, bias_idx;
 
   // wts: FLOATS floats; tiles: TILE_FLOATS floats; both 16-byte aligned
   __device__ void init(float* wts, float* tiles, const float* __restrict__ theta, const NetRt& rt) {
     sm = wts; w4 = reinterpret_cast<uint4*>(wts); u4 = reinterpret_cast<uint4*>(tiles); H = rt.H; nin = rt.nin;
-    phase_f = phase_w = pending_w = started = 0;
+    phase_f = phase_w = phase_g = pending_w = started = 0;
     bar_f = reinterpret_cast<uint64_t*>(sm + OFF_BAR);
     bar_w = bar_f + 1;
+    bar_g = bar_f + 3;                                  // (slot 2 holds the TMEM base)
     uint32_t* tslot = reinterpret_cast<uint32_t*>(sm + OFF_BAR + 4);
     const int row = threadIdx.x;
     for (int i = row; i < FLOATS; i += kThreads) sm[i] = 0.0f;
@@ -199,7 +201,7 @@ struct JumpTcBwd {
     w0 = 0.0f; b1v = 0.0f;
     if (row < H) { w0 = th[row]; b1v = th[n1 + row]; }
     if (row < 32) tc::tmem_alloc(tslot, NCOLS);
-    if (row == 0) { tc::mbar_init(bar_f, 1); tc::mbar_init(bar_w, 1); tc::fence_mbar_init(); }
+    if (row == 0) { tc::mbar_init(bar_f, 1); tc::mbar_init(bar_w, 1); tc::mbar_init(bar_g, 1); tc::fence_mbar_init(); }
     tc::fence_async_smem();
     tc::tc_fence_before();
     __syncthreads();
@@ -242,7 +244,7 @@ struct JumpTcBwd {
     publish();
     if (warp == 0 && issuer) {
       tc::tc_fence_after();
-      gemm_k<KS1, NBR>(tmem + C_ACC, sa(XA_HI), sa(XA_LO), sw(W1B));
+      gemm_k<KS1, NBR, true>(tmem + C_ACC, sa(XA_HI), sa(XA_LO), sw(W1B));
       tc::mma_commit(bar_f);
     }
     wait_f();
@@ -257,7 +259,7 @@ struct JumpTcBwd {
     publish();
     if (warp == 1 && issuer) {
       tc::tc_fence_after();
-      gemm_k<2, NBR>(tmem + C_ACC, sa(H1_HI), sa(H1_LO), sw(W2B));
+      gemm_k<2, NBR, true>(tmem + C_ACC, sa(H1_HI), sa(H1_LO), sw(W2B));
       tc::mma_commit(bar_f);
     }
     wait_f();
@@ -287,27 +289,35 @@ struct JumpTcBwd {
     publish();
     if (warp == 2 && issuer) {
       tc::tc_fence_after();
-      gemm_rows_stacked<48>(tmem + C_W2, sa(H1_HI), sa(D2_HI), started ? 1u : 0u);
-      gemm_k<2, NBR>(tmem + C_ACC, sa(D2_HI), sa(D2_LO), sw(WTB));
+      // the input-gradient GEMM first (it is on the tile's chain; the tensor pipe is in order), the weight-gradient GEMM behind
+      // it on its own barrier (D1 overwrites tiles it reads)
+      gemm_k<2, NBR, true>(tmem + C_ACC, sa(D2_HI), sa(D2_LO), sw(WTB));
       tc::mma_commit(bar_f);
+      gemm_rows_stacked<48>(tmem + C_W2, sa(H1_HI), sa(D2_HI), started ? 1u : 0u);
+      tc::mma_commit(bar_g);
     }
     wait_f();
+    {
+      float d1[24];
 #pragma unroll
-    for (int c8 = 0; c8 < 3; ++c8) {
-      float t8[8], q8[8];
-      tc::tmem_ld8(lane_base + C_ACC + 8 * c8, t8);
-      tc::tmem_ld8(lane_base + C_ACC + NBR + 8 * c8, q8);
-      tc::tmem_ld_wait();
+      for (int c8 = 0; c8 < 3; ++c8) {
+        float q8[8];
+        tc::tmem_ld8(lane_base + C_ACC + 8 * c8, reinterpret_cast<float (&)[8]>(d1[8 * c8]));
+        tc::tmem_ld8(lane_base + C_ACC + NBR + 8 * c8, q8);
+        tc::tmem_ld_wait();
 #pragma unroll
-      for (int q = 0; q < 8; ++q) t8[q] = (t8[q] + q8[q]) * dactf<ACT>(h1[8 * c8 + q]);
-      tc::store_bf16x8(u4 + D1_HI, u4 + D1_LO, c8, row, t8);
+        for (int q = 0; q < 8; ++q) d1[8 * c8 + q] = (d1[8 * c8 + q] + q8[q]) * dactf<ACT>(h1[8 * c8 + q]);
+      }
+      tc::mbar_wait(bar_g, phase_g); phase_g ^= 1;
+#pragma unroll
+      for (int c8 = 0; c8 < 3; ++c8) tc::store_bf16x8(u4 + D1_HI, u4 + D1_LO, c8, row, d1 + 8 * c8);
     }
     publish();
     if (warp == 3 && issuer) {
       tc::tc_fence_after();
-      gemm_k<2, NI>(tmem + C_ACC, sa(D1_HI), sa(D1_LO), sw(W1T));
+      gemm_k<2, NI, true>(tmem + C_ACC, sa(D1_HI), sa(D1_LO), sw(W1T));
       tc::mma_commit(bar_f);
-      gemm_rows_stacked<2 * NI>(tmem + C_W1, sa(D1_HI), sa(XA_HI), started ? 1u : 0u);
+      gemm_rows_stacked<2 * NI, 64>(tmem + C_W1, sa(D1_HI), sa(XA_HI), started ? 1u : 0u);   // M = 64: 48 rows [D1 hi; D1 lo]
       tc::mma_commit(bar_w);
     }
     started = 1;
@@ -342,14 +352,17 @@ struct JumpTcBwd {
       if (started && pass == 0) {
         for (int e = row; e < (nin + 1) * H; e += kThreads) {
           const int i = e / H, j = e % H;
-          g[e] += S[j * SW + i] + S[j * SW + NI + i] + S[(24 + j) * SW + i];
+          const int lh = rtc::lane_of_row_m64(j), ll = rtc::lane_of_row_m64(24 + j);     // dW1^T accumulates with M = 64
+          g[e] += (S[lh * SW + i] + S[lh * SW + NI + i]) + (S[ll * SW + i] + S[ll * SW + NI + i]);   // hi.hi + hi.lo + lo.hi + lo.lo
         }
       } else if (started) {
         for (int e = row; e < (H + 1) * H; e += kThreads) {
           const int k = e / H, j = e % H;
-          g[o2 + e] += S[k * SW + j] + S[k * SW + 24 + j] + S[(48 + k) * SW + j];
+          g[o2 + e] += (S[k * SW + j] + S[k * SW + 24 + j]) + (S[(48 + k) * SW + j] + S[(48 + k) * SW + 24 + j]);
         }
-        if (row <= H) g[o3 + row * nout] += S[(24 + row) * SW + COL_DOUT] + S[(24 + row) * SW + 24 + COL_DOUT] + S[(72 + row) * SW + COL_DOUT];
+        if (row <= H)
+          g[o3 + row * nout] += (S[(24 + row) * SW + COL_DOUT] + S[(24 + row) * SW + 24 + COL_DOUT]) +
+                                (S[(72 + row) * SW + COL_DOUT] + S[(72 + row) * SW + 24 + COL_DOUT]);
       }
     }
     tc::tc_fence_before();

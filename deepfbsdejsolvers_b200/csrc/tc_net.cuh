@@ -23,9 +23,12 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) 
 // D[:, 0 .. N2) += A_lo [B_hi | ..] (N2 = NH rounded up to 16; the columns beyond NH pick up lo.lo terms, which belong to
 // the exact product).  The caller adds the column blocks [0, NH) and [NH, 2 NH) when it reads the accumulator.
 // A: K-major tile (128 rows); B: [k / 8][2 NH n-rows][8 bf16].
-template <int KS, int NH>
+// FULL: the second MMA spans both column blocks as well, D[:, 0 .. 2 NH) += A_lo [B_hi | B_lo]: all four hi / lo cross products
+// (the jump schemes, whose gradients are differences of nearly equal sums, want the lo.lo term: 2^-17 instead of 2^-16).
+template <int KS, int NH, bool FULL = false>
 __device__ __forceinline__ void gemm_k(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b) {
-  constexpr uint32_t id1 = tc::idesc_bf16(128, 2 * NH, false, false), id2 = tc::idesc_bf16(128, (NH + 15) / 16 * 16, false, false);
+  constexpr uint32_t id1 = tc::idesc_bf16(128, 2 * NH, false, false),
+                     id2 = tc::idesc_bf16(128, FULL ? 2 * NH : (NH + 15) / 16 * 16, false, false);
   constexpr uint32_t chunk = 2 * NH * 16;
 #pragma unroll
   for (int s = 0; s < KS; ++s) {
