@@ -603,21 +603,14 @@ __global__ void __launch_bounds__(2 * kThreads, 4) reg_forward_tc(const PricingA
         tc::mma_commit(bar);
       }
       // ---- independent of the network: closed-form coupling, record stores (in the shadow of the first MMA) ------------
-#if FBSDEJ_ABLATE == 2
-      float Ai = 0.2f, dAb = 0.5f;
-#else
+#if FBSDEJ_ABLATE != 2
       typename Model::AEval ae;
-      Model::eval_A_begin(a, i, X, ae);                  // table loads in flight while the stores issue
-#endif
+      Model::eval_A_begin(a, i, X, ae);                  // table loads in flight until the shadow of the SECOND MMA (an L2 round
+#endif                                                   // trip is longer than the first MMA: consuming them here stalled the chain)
 #if FBSDEJ_ABLATE != 5
 #pragma unroll
       for (int k = 0; k < D; ++k) rs[(RL::P_X + k) * TR] = X[k];
 #endif
-#if FBSDEJ_ABLATE != 2
-      float Ai, dAb;
-      Model::eval_A_finish(a, i, ae, Ai, dAb);
-#endif
-      rs[RL::P_DA * TR] = dAb;
       wait_mma();
       {
         float t24[24];
@@ -639,7 +632,14 @@ __global__ void __launch_bounds__(2 * kThreads, 4) reg_forward_tc(const PricingA
 #endif
         tc::mma_commit(bar);
       }
-      // ---- this step's exponentials from the ring (in the shadow of the second MMA) -------------------------------------
+      // ---- closed-form coupling, this step's exponentials from the ring (in the shadow of the second MMA) -----------------
+#if FBSDEJ_ABLATE == 2
+      float Ai = 0.2f, dAb = 0.5f;
+#else
+      float Ai, dAb;
+      Model::eval_A_finish(a, i, ae, Ai, dAb);
+#endif
+      rs[RL::P_DA * TR] = dAb;
       float E[D];
       {
         const uint32_t s = it % NST;

@@ -67,3 +67,25 @@ def test_training_reduces_the_validation_loss(ctx, theta):
     s.simulate(SEED ^ 0x55, 0, B)
     after = float(s.loss(B)[0])
     assert np.isfinite(after) and after < 0.7 * before, (before, after)
+
+
+@pytest.mark.parametrize("Bt", [56831, 56832, 56833, 60000, 75776, 75777, 113664, 131073])
+def test_tile_map_edges(ctx, theta, Bt):
+    """Batch sizes around the switches of the tile map (pricing.cuh: make_tile_map - uniform 128-row tiles below 3 warps per CTA
+    slot, mixed 128 / 96-row tiles above, a second wave beyond 4 warps per slot): the tcgen05 kernels on in-kernel increments against
+    the fp32 FFMA kernels on the same (materialised) increments, three time steps."""
+    p = dict(P, N=3)
+    layout = H.pricing_layout("merton", "SumLocalReg", D)
+    tc = H.native_pricing(ctx, "merton", p, "SumLocalReg", layout, d=D, limit=100, tensor_cores=True)
+    ff = H.native_pricing(ctx, "merton", p, "SumLocalReg", layout, d=D, limit=100, tensor_cores=False)
+    tc.set_theta(theta); ff.set_theta(theta)
+    fused = ctx.to_host(tc.grad_step(SEED, Bt, Bt, 0)).numpy().copy()
+    ff.simulate(SEED, 0, Bt)
+    ref = ff.grad(Bt)
+    assert abs(fused[0] - ref[0]) <= 1e-5 * abs(ref[0]), (fused[0], ref[0])
+    assert np.abs(fused[4:] - ref[4:]).max() <= 1e-4 * np.abs(ref[4:]).max()
+    # and the trajectory dump finds every path again (untile through the same map)
+    tc.simulate(SEED, 0, Bt)
+    _, tx, _, _ = tc.loss(Bt, traj=True)
+    _, fx, _, _ = ff.loss(Bt, traj=True)
+    assert np.abs(tx - fx).max() <= 2e-6 + 1e-5 * np.abs(fx).max()
