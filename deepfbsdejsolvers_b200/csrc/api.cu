@@ -741,7 +741,7 @@ int fbsdej_solver_create(fbsdej_ctx* ctx, const fbsdej_solver_desc* desc, const 
   NetRt* nets[2] = {&s->netA, &s->netB};
   for (int k = 0; k < nn; ++k) {
     const fbsdej_net_desc& nd = desc->nets[k];
-    FB_REQUIRE(nd.L == 2, "fused kernels are compiled for L = 2 hidden layers (reference default nbLayer = 2)");
+    FB_REQUIRE(nd.L >= 1 && nd.L <= kMaxL, "the fused kernels support 1, 2 or 3 hidden layers (the reference's nbLayer; default 2)");
     FB_REQUIRE(nd.nin == expect_in[k], "net " + std::to_string(k) + ": nin must be " + std::to_string(expect_in[k]));
     FB_REQUIRE(nd.nout == expect_out[k], "net " + std::to_string(k) + ": nout must be " + std::to_string(expect_out[k]));
     FB_REQUIRE(nd.act == FBSDEJ_ACT_TANH || nd.act == FBSDEJ_ACT_RELU, "unknown activation");
@@ -750,7 +750,8 @@ int fbsdej_solver_create(fbsdej_ctx* ctx, const fbsdej_solver_desc* desc, const 
     FB_REQUIRE(hp <= 32 || (reg && model != FBSDEJ_MODEL_MFG), "hidden width 32..35 is compiled for the compensator-free pricing solvers only (else <= 31)");
     HP = std::max(HP, hp);
     FB_REQUIRE(nd.nin + 1 <= hp && nd.nout <= NOP, "network too wide for the compiled tiles");
-    nets[k]->nin = nd.nin; nets[k]->H = nd.H; nets[k]->nout = nd.nout; nets[k]->act = nd.act; nets[k]->ext_off = off;
+    FB_REQUIRE(nd.L < 3 || hp == 24, "three hidden layers need a hidden width <= 23 (weight-gradient blocks per CTA)");
+    nets[k]->nin = nd.nin; nets[k]->H = nd.H; nets[k]->nout = nd.nout; nets[k]->act = nd.act; nets[k]->ext_off = off; nets[k]->L = nd.L;
     off += net_ext_params(*nets[k]);
   }
   if (one_net) s->netB = s->netA;
@@ -760,6 +761,9 @@ int fbsdej_solver_create(fbsdej_ctx* ctx, const fbsdej_solver_desc* desc, const 
   s->M = s->has_jump ? desc->M : 0;
   FB_REQUIRE(!s->has_jump || desc->M >= 1, "this scheme needs M >= 1 compensator samples");
   FB_REQUIRE(desc->mma_mode == 0 || desc->mma_mode == 1, "mma_mode must be 0 (FFMA) or 1 (tcgen05)");
+  bool all_two = true;
+  for (int k = 0; k < nn; ++k) all_two = all_two && desc->nets[k].L == 2;
+  FB_REQUIRE(desc->mma_mode == 0 || all_two, "mma_mode = 1 (tcgen05) needs two hidden layers");
   // tcgen05 coverage: the compensator-free pricing solvers, the MFG solvers, and the jump evaluations (own jump + Monte-Carlo
   // compensator) of the jump schemes with a tanh network
   const fbsdej_net_desc& jn = desc->nets[one_net ? 0 : 1];
@@ -1105,7 +1109,7 @@ int fbsdej_solver_net_forward(fbsdej_solver* s, const float* theta, int net_inde
   FB_REQUIRE(net_index == 0 || (net_index == 1 && !s->one_net), "net_forward: no such net");
   FB_CUDA(cudaSetDevice(s->ctx->device));
   const NetRt& n = net_index == 0 ? s->netA : s->netB;
-  if (launch_net_forward(theta + n.ext_off, n.nin, n.H, 2, n.nout, n.act, x, rows, y, s->ctx->stream)) return -2;
+  if (launch_net_forward(theta + n.ext_off, n.nin, n.H, n.L, n.nout, n.act, x, rows, y, s->ctx->stream)) return -2;
   s->ctx->launches += 1;
   return 0;
 }

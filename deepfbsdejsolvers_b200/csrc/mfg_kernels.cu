@@ -51,11 +51,12 @@ __global__ void __launch_bounds__(kMfgThreads) mfg_forward(const MFGArgs a) {
   float* tb = outx + 2 * 2 * 4 * TR;
   const int role = threadIdx.x >> 7, row = threadIdx.x & (TR - 1);
   TL t;
-  t.carve(tb + role * TL::fwd_floats(), false);
+  const int Lmax = a.netA.L > a.netB.L ? a.netA.L : a.netB.L;
+  t.carve(tb + role * TL::fwd_floats(Lmax), false, Lmax);
   const NetView<HP> nvA = load_net<HP>(swA, a.theta, a.netA, false);
   const NetView<HP> nvB = load_net<HP>(swB, a.theta, a.netB, false);
   const NetView<HP>& nv = role == 0 ? nvA : nvB;
-  zero_tiles(tb, 2 * TL::fwd_floats());
+  zero_tiles(tb, 2 * TL::fwd_floats(Lmax));
   const size_t sB = (size_t)a.B;
   const int c0 = a.has_y ? 1 : 0;
   float lh_sum = 0.0f, li_sum = 0.0f;
@@ -183,12 +184,13 @@ __global__ void __launch_bounds__(kMfgThreads) mfg_backward(const MFGArgs a) {
   float* tb = dxx + 2 * 3 * TR;
   const int role = threadIdx.x >> 7, row = threadIdx.x & (TR - 1);
   TL t;
-  float* const tbr = tb + role * TL::bwd_floats();
-  t.carve(tbr, true);
+  const int Lmax = a.netA.L > a.netB.L ? a.netA.L : a.netB.L;
+  float* const tbr = tb + role * TL::bwd_floats(Lmax);
+  t.carve(tbr, true, Lmax);
   const NetView<HP> nvA = load_net<HP>(swA, a.theta, a.netA, true);
   const NetView<HP> nvB = load_net<HP>(swB, a.theta, a.netB, true);
   const NetView<HP>& nv = role == 0 ? nvA : nvB;
-  zero_tiles(tb, 2 * TL::bwd_floats());
+  zero_tiles(tb, 2 * TL::bwd_floats(Lmax));
   WGrad<HP> wg;
   wg.init(nv, t, row);
   const size_t sB = (size_t)a.B;
@@ -312,7 +314,8 @@ __global__ void __launch_bounds__(kMfgThreads) mfg_backward(const MFGArgs a) {
 template <int HP>
 static size_t mfg_smem(const MFGArgs& a, bool backward) {
   const int w = net_smem_floats(a.netA, HP, backward) + net_smem_floats(a.netB, HP, backward);
-  const int tl = backward ? 2 * Tiles<HP, 4>::bwd_floats() + 2 * 3 * TR : 2 * Tiles<HP, 4>::fwd_floats() + 2 * 2 * 4 * TR;
+  const int L = a.netA.L > a.netB.L ? a.netA.L : a.netB.L;
+  const int tl = backward ? 2 * Tiles<HP, 4>::bwd_floats(L) + 2 * 3 * TR : 2 * Tiles<HP, 4>::fwd_floats(L) + 2 * 2 * 4 * TR;
   return sizeof(float) * (size_t)(w + 8 + tl);
 }
 size_t mfg_smem_bytes(int HP, const MFGArgs& a, bool backward) {

@@ -49,10 +49,11 @@ __global__ void __launch_bounds__(kThreads, JTC ? 4 : 0) pricing_forward(const P
   using TL = Tiles<HP, JUMP ? NOP : 4>;
   TL t;
   NetView<HP> nvA, nvJ;
-  t.carve(tb, false);
+  const int Lmax = a.netA.L > a.netB.L ? a.netA.L : a.netB.L;
+  t.carve(tb, false, Lmax);
   nvA = load_net<HP>(swA, a.theta, a.netA, false);
   nvJ = (two && !JTC) ? load_net<HP>(swB, a.theta, a.netB, false) : nvA;
-  zero_tiles(tb, TL::fwd_floats());
+  zero_tiles(tb, TL::fwd_floats(Lmax));
   JumpTcFwd<ACT_TANH, NXC> jf;
   if constexpr (JTC) jf.init(smem, a.theta, a.netB);
 
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(kThreads, JTC ? 4 : 0) pricing_forward(const P
           store_row<HP>(t.xt, row, in);
           mlp_fwd<HP, false, TL>(nvA, t, row);
         }
-        auto outA = [&](int j) { return rowmode ? rv[6 * HP + j] : t.out[tix(j, row)]; };
+        auto outA = [&](int j) { return rowmode ? rv[rv_out<HP>() + j] : t.out[tix(j, row)]; };
         if (a.has_y) y_net = outA(0);
         if (JUMP && a.has_z) {
 #pragma unroll
@@ -302,10 +303,11 @@ __global__ void __launch_bounds__(kThreads, JTC ? 2 : 0) pricing_backward(const 
   TL t;
   NetView<HP> nvA, nvJ;
   WGrad<HP> wgA, wgB;
-  t.carve(tb, true);
+  const int Lmax = a.netA.L > a.netB.L ? a.netA.L : a.netB.L;
+  t.carve(tb, true, Lmax);
   nvA = load_net<HP>(swA, a.theta, a.netA, true);
   nvJ = (two && !JTC) ? load_net<HP>(swB, a.theta, a.netB, true) : nvA;
-  zero_tiles(tb, TL::bwd_floats());
+  zero_tiles(tb, TL::bwd_floats(Lmax));
   wgA.init(nvA, t);
   if (JUMP && !JTC) wgB.init(nvJ, t);
   // JTC: the operand tiles of the tensor-core block live in the h1 .. d2 tiles of the FFMA network (every tile is rewritten
@@ -316,7 +318,7 @@ __global__ void __launch_bounds__(kThreads, JTC ? 2 : 0) pricing_backward(const 
   static_assert(JB::TILE_FLOATS <= TL::bwd_floats() - (HP + (JUMP ? NOP : 4)) * TR, "operand tiles fit between the input and dout tiles");
   static_assert(!JTC || 1 + D <= JB::NDX, "input gradients of the state come back in one read");
   JB jb;
-  if constexpr (JTC) jb.init(smem, t.h1, a.theta, a.netB);
+  if constexpr (JTC) jb.init(smem, t.h[0], a.theta, a.netB);
 
   const int row = threadIdx.x;
   const int G = JUMP ? a.G : 1, ppb = kThreads / G, g = threadIdx.x % G;
@@ -576,8 +578,9 @@ static size_t pricing_smem(const PricingArgs& a, bool backward) {
   const bool jtc = a.mma_mode == 1 && a.has_jump;
   const int w = net_smem_floats(a.netA, HP, backward) +
                 (jtc ? (backward ? kJtcBwdFloats : kJtcFwdFloats) : two ? net_smem_floats(a.netB, HP, backward) : 0);
-  const int tl = a.has_jump ? (backward ? Tiles<HP, NOP>::bwd_floats() : Tiles<HP, NOP>::fwd_floats())
-                            : (backward ? Tiles<HP, 4>::bwd_floats() : Tiles<HP, 4>::fwd_floats());
+  const int L = a.netA.L > a.netB.L ? a.netA.L : a.netB.L;
+  const int tl = a.has_jump ? (backward ? Tiles<HP, NOP>::bwd_floats(L) : Tiles<HP, NOP>::fwd_floats(L))
+                            : (backward ? Tiles<HP, 4>::bwd_floats(L) : Tiles<HP, 4>::fwd_floats(L));
   return sizeof(float) * (size_t)(w + kRedFloats + (a.has_jump ? row_floats<HP>() : 0) + tl);
 }
 

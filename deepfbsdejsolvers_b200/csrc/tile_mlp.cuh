@@ -1,8 +1,8 @@
 // Tile MLP primitives: one CTA = 128 rows; thread r owns row r.
 //
 // Replaces the Keras `Dense` stacks of the reference (coupledPricing/Networks.py:6-23,
-// coupledMFG/Networks.py:6-46: nin -> H (act) -> H (act) -> nout) and the tf.GradientTape pass through them
-// (SolversJumpDiff.py:47-53).
+// coupledMFG/Networks.py:6-46: nin -> H (act) -> ... -> H (act) -> nout with L = 1, 2 or 3 equal hidden layers - the
+// reference's `--nbLayer`, default 2) and the tf.GradientTape pass through them (SolversJumpDiff.py:47-53).
 //
 // Data layout (shared memory)
 //   * activation tiles use the UMMA canonical K-major (no-swizzle) layout of sm_100: feature f of row r lives at
@@ -12,8 +12,8 @@
 //   * the constant-1 trick folds biases into the GEMVs: tile XT has a ones column at col nin, H1/H2 have a ones
 //     column at col H (< HP), and the weight blocks carry the bias as one more row / column.
 //   * per net, rows HP floats wide, row counts padded to a multiple of 4 with zero rows:
-//       W1  [(nin+1)][HP]  row nin = b1         W2  [(H+1)][HP]  row H = b2        W3T [nout][HP]  col H = b3
-//       W2T [H][HP]  (W2T[j][k] = W2[k][j])     W1T [H][HP]  (W1T[j][i] = W1[i][j])      (backward only)
+//       W1  [(nin+1)][HP]  row nin = b1         Wh[l] [(H+1)][HP]  row H = bias (l < L-1)   W3T [nout][HP]  col H = b3
+//       WhT[l] [H][HP]  (transposes)            W1T [H][HP]  (W1T[j][i] = W1[i][j])      (backward only)
 //   * the weight gradient is an outer-product GEMM over the rows of the tile.  Every thread owns one fixed 4x4
 //     block (x one row chunk) of one of the three weight matrices and keeps its 16 partial sums IN REGISTERS for
 //     the whole kernel (all time steps, all tiles); they are flushed once at the end.
@@ -27,18 +27,21 @@ constexpr int NOP = 12;   // largest supported nout (width of the out / dout til
 
 enum { ACT_TANH = 0, ACT_RELU = 1 };
 
+constexpr int kMaxL = 3;   // hidden layers supported by the fp32 tile MLP (the tcgen05 kernels: 2)
+
 struct NetRt {     // runtime description of a network
   int nin, H, nout, act;
   int ext_off;     // offset of this net in the external flat parameter vector
+  int L;           // hidden layers (1 .. kMaxL), all H wide
 };
 
 __host__ __device__ inline int pad4(int x) { return (x + 3) & ~3; }
 __host__ __device__ inline int net_ext_params(const NetRt& n) {
-  return n.nin * n.H + n.H + n.H * n.H + n.H + n.H * n.nout + n.nout;
+  return n.nin * n.H + n.H + (n.L - 1) * (n.H * n.H + n.H) + n.H * n.nout + n.nout;
 }
 // smem floats of one net's weight block
 __host__ __device__ inline int net_smem_floats(const NetRt& n, int HP, bool bwd) {
-  return (pad4(n.nin + 1) + pad4(n.H + 1) + n.nout + (bwd ? 2 * pad4(n.H) : 0)) * HP;
+  return (pad4(n.nin + 1) + (n.L - 1) * pad4(n.H + 1) + n.nout + (bwd ? n.L * pad4(n.H) : 0)) * HP;
 }
 
 // float index of (feature f, row r) in a tile
@@ -46,8 +49,8 @@ __device__ __forceinline__ int tix(int f, int r) { return (((f >> 2) * TR + r) <
 
 template <int HP>
 struct NetView {   // smem views of one net
-  const float* W1; const float* W2; const float* W3T; const float* W2T; const float* W1T;
-  int nin, H, nout, act;
+  const float* W1; const float* Wh[kMaxL - 1]; const float* W3T; const float* WhT[kMaxL - 1]; const float* W1T;
+  int nin, H, nout, act, L;
 };
 
 // tanh(x) = 1 - 2 / (2^(2 log2(e) x) + 1): two MUFU ops (ex2, rcp) + three FP32 ops, branch-free, saturates correctly;
@@ -64,13 +67,14 @@ __device__ __forceinline__ float dact_fn(float h, int act) { return act == ACT_T
 // Cooperative load of one net from the external flat vector (W[in][out] row-major, then b) into smem.
 template <int HP>
 __device__ __forceinline__ NetView<HP> load_net(float* sw, const float* __restrict__ theta, const NetRt& rt, bool bwd) {
-  const int nin = rt.nin, H = rt.H, nout = rt.nout;
-  const int o1 = 0, o2 = pad4(nin + 1) * HP, o3 = o2 + pad4(H + 1) * HP, o2t = o3 + nout * HP, o1t = o2t + pad4(H) * HP;
+  const int nin = rt.nin, H = rt.H, nout = rt.nout, L = rt.L;
+  const int o1 = 0, oh = pad4(nin + 1) * HP, szh = pad4(H + 1) * HP, o3 = oh + (L - 1) * szh, oht = o3 + nout * HP,
+            szt = pad4(H) * HP, o1t = oht + (L - 1) * szt;
   const int total = net_smem_floats(rt, HP, bwd);
   for (int i = threadIdx.x; i < total; i += blockDim.x) sw[i] = 0.0f;
   __syncthreads();
   const float* __restrict__ th = theta + rt.ext_off;
-  const int n1 = nin * H, n2 = n1 + H, n3 = n2 + H * H, n4 = n3 + H, n5 = n4 + H * nout, n6 = n5 + nout;
+  const int n1 = nin * H, n2 = n1 + H, blk = H * H + H, n4 = n2 + (L - 1) * blk, n5 = n4 + H * nout, n6 = n5 + nout;
   for (int e = threadIdx.x; e < n6; e += blockDim.x) {
     const float v = th[e];
     if (e < n1) {
@@ -79,12 +83,15 @@ __device__ __forceinline__ NetView<HP> load_net(float* sw, const float* __restri
       if (bwd) sw[o1t + j * HP + i] = v;
     } else if (e < n2) {
       sw[o1 + nin * HP + (e - n1)] = v;
-    } else if (e < n3) {
-      const int k = (e - n2) / H, j = (e - n2) % H;
-      sw[o2 + k * HP + j] = v;
-      if (bwd) sw[o2t + j * HP + k] = v;
-    } else if (e < n4) {
-      sw[o2 + H * HP + (e - n3)] = v;
+    } else if (e < n4) {                                  // hidden-to-hidden layer l: W[k][j] then b[j]
+      const int l = (e - n2) / blk, r = (e - n2) % blk;
+      if (r < H * H) {
+        const int k = r / H, j = r % H;
+        sw[oh + l * szh + k * HP + j] = v;
+        if (bwd) sw[oht + l * szt + j * HP + k] = v;
+      } else {
+        sw[oh + l * szh + H * HP + (r - H * H)] = v;
+      }
     } else if (e < n5) {
       const int k = (e - n4) / nout, j = (e - n4) % nout;
       sw[o3 + j * HP + k] = v;
@@ -94,8 +101,10 @@ __device__ __forceinline__ NetView<HP> load_net(float* sw, const float* __restri
   }
   __syncthreads();
   NetView<HP> nv;
-  nv.W1 = sw + o1; nv.W2 = sw + o2; nv.W3T = sw + o3; nv.W2T = sw + o2t; nv.W1T = sw + o1t;
-  nv.nin = nin; nv.H = H; nv.nout = nout; nv.act = rt.act;
+  nv.W1 = sw + o1; nv.W3T = sw + o3; nv.W1T = sw + o1t;
+#pragma unroll
+  for (int l = 0; l < kMaxL - 1; ++l) { nv.Wh[l] = sw + oh + l * szh; nv.WhT[l] = sw + oht + l * szt; }
+  nv.nin = nin; nv.H = H; nv.nout = nout; nv.act = rt.act; nv.L = L;
   return nv;
 }
 
@@ -136,16 +145,27 @@ __device__ __forceinline__ void store_row(float* __restrict__ tile, int row, con
   for (int c = 0; c < HP / 4; ++c) st4(tile + (c * TR + row) * 4, make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
 }
 
-// Tiles of one CTA.  xt/h1/h2/d1/d2 are HP features wide, dout/out are NW wide (NW = 4 or 12, >= nout).
+// Tiles of one CTA.  xt / h[l] / d[l] are HP features wide, dout / out are NW wide (NW = 4 or 12, >= nout).  Order in memory:
+// xt | h[0] | out | h[1 .. L-1] | d[0 .. L-1] | dout  (forward-only: xt | h[0] | out | h[1] when L = 3).
 template <int HP, int NW>
 struct Tiles {
-  float* xt; float* h1; float* h2; float* d1; float* d2; float* dout; float* out;
-  __host__ __device__ static constexpr int fwd_floats() { return (2 * HP + NW) * TR; }           // xt, h1, out
-  __host__ __device__ static constexpr int bwd_floats() { return (5 * HP + 2 * NW) * TR; }
-  __device__ void carve(float* base, bool bwd) {
-    xt = base; h1 = xt + HP * TR; out = h1 + HP * TR;
-    if (bwd) { h2 = out + NW * TR; d1 = h2 + HP * TR; d2 = d1 + HP * TR; dout = d2 + HP * TR; }
-    else { h2 = d1 = d2 = dout = nullptr; }
+  float* xt; float* h[kMaxL]; float* d[kMaxL]; float* dout; float* out;
+  __host__ __device__ static constexpr int fwd_floats(int L = 2) { return ((L > 2 ? 3 : 2) * HP + NW) * TR; }     // xt, h[0] (, h[1]), out
+  __host__ __device__ static constexpr int bwd_floats(int L = 2) { return ((1 + 2 * L) * HP + 2 * NW) * TR; }
+  __device__ void carve(float* base, bool bwd, int L = 2) {
+    xt = base; h[0] = xt + HP * TR; out = h[0] + HP * TR;
+    float* p = out + NW * TR;
+#pragma unroll
+    for (int l = 1; l < kMaxL; ++l) {
+      h[l] = nullptr;
+      if (l < L && (bwd || l < 2)) { h[l] = p; p += HP * TR; }
+    }
+#pragma unroll
+    for (int l = 0; l < kMaxL; ++l) {
+      d[l] = nullptr;
+      if (bwd && l < L) { d[l] = p; p += HP * TR; }
+    }
+    dout = bwd ? p : nullptr;
   }
 };
 
@@ -155,18 +175,23 @@ __device__ __forceinline__ void zero_tiles(float* base, int nfloats) {
 }
 
 // Forward of this thread's row.  Inputs: xt features [0, nin] written by the caller (feature nin = 1.0).
-// Outputs: t.out features [0, nout).  KEEP_H2: also store the second hidden layer (needed by the backward sweep).
-template <int HP, bool KEEP_H2, class TL>
+// Outputs: t.out features [0, nout).  KEEP: also store the last hidden layer (needed by the backward sweep).
+template <int HP, bool KEEP, class TL>
 __device__ __forceinline__ void mlp_fwd(const NetView<HP>& nv, const TL& t, int row) {
   float a[HP];
   gemv<HP>(a, nv.W1, (nv.nin + 4) >> 2, t.xt, row);
 #pragma unroll
   for (int j = 0; j < HP; ++j) a[j] = (j < nv.H) ? act_fn(a[j], nv.act) : ((j == nv.H) ? 1.0f : 0.0f);
-  store_row<HP>(t.h1, row, a);
-  gemv<HP>(a, nv.W2, (nv.H + 4) >> 2, t.h1, row);
 #pragma unroll
-  for (int j = 0; j < HP; ++j) a[j] = (j < nv.H) ? act_fn(a[j], nv.act) : ((j == nv.H) ? 1.0f : 0.0f);
-  if (KEEP_H2) store_row<HP>(t.h2, row, a);
+  for (int l = 0; l < kMaxL - 1; ++l) {
+    if (l < nv.L - 1) {                                  // a = h[l] -> h[l + 1]
+      store_row<HP>(t.h[l], row, a);
+      gemv<HP>(a, nv.Wh[l], (nv.H + 4) >> 2, t.h[l], row);
+#pragma unroll
+      for (int j = 0; j < HP; ++j) a[j] = (j < nv.H) ? act_fn(a[j], nv.act) : ((j == nv.H) ? 1.0f : 0.0f);
+    }
+  }
+  if (KEEP) store_row<HP>(t.h[nv.L - 1], row, a);
   for (int j = 0; j < nv.nout; ++j) {
     const float* __restrict__ w = nv.W3T + j * HP;
     float acc0 = 0.0f, acc1 = 0.0f;
@@ -180,48 +205,56 @@ __device__ __forceinline__ void mlp_fwd(const NetView<HP>& nv, const TL& t, int 
   }
 }
 
+// a[j] *= act'(h[j]) for j < H, 0 beyond (h = this row of a hidden tile)
+template <int HP>
+__device__ __forceinline__ void times_dact(float (&a)[HP], const float* __restrict__ htile, int row, int H, int act) {
+#pragma unroll
+  for (int c = 0; c < HP / 4; ++c) {
+    const float4 h = ld4(htile + (c * TR + row) * 4);
+    a[4 * c] = (4 * c < H) ? a[4 * c] * dact_fn(h.x, act) : 0.0f;
+    a[4 * c + 1] = (4 * c + 1 < H) ? a[4 * c + 1] * dact_fn(h.y, act) : 0.0f;
+    a[4 * c + 2] = (4 * c + 2 < H) ? a[4 * c + 2] * dact_fn(h.z, act) : 0.0f;
+    a[4 * c + 3] = (4 * c + 3 < H) ? a[4 * c + 3] * dact_fn(h.w, act) : 0.0f;
+  }
+}
+
 // Delta pass of this thread's row (after mlp_fwd<HP,true> on the same inputs).  Inputs: t.dout features [0, nout)
-// (features up to the next multiple of 4 must be finite).  Leaves d2/d1 in the tiles (for the weight gradient) and
+// (features up to the next multiple of 4 must be finite).  Leaves d[l] in the tiles (for the weight gradient) and
 // returns dx[i] = dL/dx_i in a[i], i < nin.
 template <int HP, class TL>
 __device__ __forceinline__ void mlp_delta(const NetView<HP>& nv, const TL& t, int row, float (&a)[HP]) {
-  // d2 = (W3 dout) .* act'(h2)   -- W3T rows beyond nout belong to the next weight block: mask the inputs instead
+  // top delta = (W3 dout) .* act'(h[L-1])   -- W3T rows beyond nout belong to the next weight block: mask the inputs instead
   {
 #pragma unroll
     for (int j = 0; j < HP; ++j) a[j] = 0.0f;
     for (int j = 0; j < nv.nout; ++j) axpy_row<HP>(a, t.dout[tix(j, row)], nv.W3T + j * HP);
   }
+  times_dact<HP>(a, t.h[nv.L - 1], row, nv.H, nv.act);
+  store_row<HP>(t.d[nv.L - 1], row, a);
 #pragma unroll
-  for (int c = 0; c < HP / 4; ++c) {
-    const float4 h = ld4(t.h2 + (c * TR + row) * 4);
-    a[4 * c] = (4 * c < nv.H) ? a[4 * c] * dact_fn(h.x, nv.act) : 0.0f;
-    a[4 * c + 1] = (4 * c + 1 < nv.H) ? a[4 * c + 1] * dact_fn(h.y, nv.act) : 0.0f;
-    a[4 * c + 2] = (4 * c + 2 < nv.H) ? a[4 * c + 2] * dact_fn(h.z, nv.act) : 0.0f;
-    a[4 * c + 3] = (4 * c + 3 < nv.H) ? a[4 * c + 3] * dact_fn(h.w, nv.act) : 0.0f;
+  for (int l = kMaxL - 2; l >= 0; --l) {
+    if (l < nv.L - 1) {                                  // delta of hidden layer l from the one above
+      gemv<HP>(a, nv.WhT[l], (nv.H + 3) >> 2, t.d[l + 1], row);
+      times_dact<HP>(a, t.h[l], row, nv.H, nv.act);
+      store_row<HP>(t.d[l], row, a);
+    }
   }
-  store_row<HP>(t.d2, row, a);
-  gemv<HP>(a, nv.W2T, (nv.H + 3) >> 2, t.d2, row);
-#pragma unroll
-  for (int c = 0; c < HP / 4; ++c) {
-    const float4 h = ld4(t.h1 + (c * TR + row) * 4);
-    a[4 * c] = (4 * c < nv.H) ? a[4 * c] * dact_fn(h.x, nv.act) : 0.0f;
-    a[4 * c + 1] = (4 * c + 1 < nv.H) ? a[4 * c + 1] * dact_fn(h.y, nv.act) : 0.0f;
-    a[4 * c + 2] = (4 * c + 2 < nv.H) ? a[4 * c + 2] * dact_fn(h.z, nv.act) : 0.0f;
-    a[4 * c + 3] = (4 * c + 3 < nv.H) ? a[4 * c + 3] * dact_fn(h.w, nv.act) : 0.0f;
-  }
-  store_row<HP>(t.d1, row, a);
-  gemv<HP>(a, nv.W1T, (nv.H + 3) >> 2, t.d1, row);
+  gemv<HP>(a, nv.W1T, (nv.H + 3) >> 2, t.d[0], row);
 }
 
 // ---- one row shared by the whole CTA ------------------------------------------------------------------------------
 // Jump schemes at small batch: the CTA (G == kThreads) works on ONE path, so the network at the path's state has a single
 // row.  Thread j owns hidden unit j; the layer vectors live in a small shared-memory block
-//   rv: xs[HP] | h1s[HP] | h2s[HP] | d2s[HP] | d1s[HP] | dos[HP] | outs[16]
-// Two barriers per forward, two more per delta pass - instead of every thread walking the same row through the tile MLP.
+//   rv: xs[HP] | hs[kMaxL][HP] | ds[kMaxL][HP] | dos[HP] | outs[16]
+// L + 1 barriers per forward, L + 1 more per delta pass - instead of every thread walking the same row through the tile MLP.
 template <int HP>
-__host__ __device__ constexpr int row_floats() { return 6 * HP + 16; }
+__host__ __device__ constexpr int row_floats() { return (2 + 2 * kMaxL) * HP + 16; }
+template <int HP> __host__ __device__ constexpr int rv_h(int l) { return (1 + l) * HP; }
+template <int HP> __host__ __device__ constexpr int rv_d(int l) { return (1 + kMaxL + l) * HP; }
+template <int HP> __host__ __device__ constexpr int rv_do() { return (1 + 2 * kMaxL) * HP; }
+template <int HP> __host__ __device__ constexpr int rv_out() { return (2 + 2 * kMaxL) * HP; }
 
-// x: CTA-uniform inputs (x[nin] = 1).  Outputs in rv[6 HP + o], o < nout, valid after the call.
+// x: CTA-uniform inputs (x[nin] = 1).  Outputs in rv[rv_out<HP>() + o], o < nout, valid after the call.
 template <int HP>
 __device__ __forceinline__ void row_fwd(const NetView<HP>& nv, float* __restrict__ rv, const float (&x)[HP]) {
   const int j = threadIdx.x;
@@ -235,50 +268,59 @@ __device__ __forceinline__ void row_fwd(const NetView<HP>& nv, float* __restrict
 #pragma unroll
     for (int i = 0; i < HP; ++i)
       if (i <= nv.nin) acc = fmaf(x[i], nv.W1[i * HP + j], acc);
-    rv[HP + j] = (j < nv.H) ? act_fn(acc, nv.act) : ((j == nv.H) ? 1.0f : 0.0f);
+    rv[rv_h<HP>(0) + j] = (j < nv.H) ? act_fn(acc, nv.act) : ((j == nv.H) ? 1.0f : 0.0f);
   }
   __syncthreads();
-  if (j < HP) {
-    float acc = 0.0f;
+  for (int l = 0; l < nv.L - 1; ++l) {
+    if (j < HP) {
+      float acc = 0.0f;
+      const float* __restrict__ hin = rv + rv_h<HP>(l);
+      const float* __restrict__ W = nv.Wh[l];
 #pragma unroll 8
-    for (int k = 0; k <= nv.H; ++k) acc = fmaf(rv[HP + k], nv.W2[k * HP + j], acc);
-    rv[2 * HP + j] = (j < nv.H) ? act_fn(acc, nv.act) : ((j == nv.H) ? 1.0f : 0.0f);
+      for (int k = 0; k <= nv.H; ++k) acc = fmaf(hin[k], W[k * HP + j], acc);
+      rv[rv_h<HP>(l + 1) + j] = (j < nv.H) ? act_fn(acc, nv.act) : ((j == nv.H) ? 1.0f : 0.0f);
+    }
+    __syncthreads();
   }
-  __syncthreads();
   if (j < nv.nout) {
     const float* __restrict__ w = nv.W3T + j * HP;
+    const float* __restrict__ hin = rv + rv_h<HP>(nv.L - 1);
     float acc = 0.0f;
 #pragma unroll 8
-    for (int k = 0; k <= nv.H; ++k) acc = fmaf(rv[2 * HP + k], w[k], acc);
-    rv[6 * HP + j] = acc;
+    for (int k = 0; k <= nv.H; ++k) acc = fmaf(hin[k], w[k], acc);
+    rv[rv_out<HP>() + j] = acc;
   }
   __syncthreads();
 }
-// dout_j: this thread's entry of dL/dout (thread j < nout; anything elsewhere).  Leaves d2s / d1s / dos for the weight
+// dout_j: this thread's entry of dL/dout (thread j < nout; anything elsewhere).  Leaves ds[l] / dos for the weight
 // gradient and returns dx[i] = dL/dx_i for i < NDX in every thread.
 template <int HP, int NDX>
 __device__ __forceinline__ void row_delta(const NetView<HP>& nv, float* __restrict__ rv, float dout_j, float (&dx)[NDX]) {
   const int j = threadIdx.x;
-  if (j < HP) rv[5 * HP + j] = (j < nv.nout) ? dout_j : 0.0f;
+  if (j < HP) rv[rv_do<HP>() + j] = (j < nv.nout) ? dout_j : 0.0f;
   __syncthreads();
   if (j < HP) {
     float acc = 0.0f;
-    for (int o = 0; o < nv.nout; ++o) acc = fmaf(rv[5 * HP + o], nv.W3T[o * HP + j], acc);
-    rv[3 * HP + j] = (j < nv.H) ? acc * dact_fn(rv[2 * HP + j], nv.act) : 0.0f;
+    for (int o = 0; o < nv.nout; ++o) acc = fmaf(rv[rv_do<HP>() + o], nv.W3T[o * HP + j], acc);
+    rv[rv_d<HP>(nv.L - 1) + j] = (j < nv.H) ? acc * dact_fn(rv[rv_h<HP>(nv.L - 1) + j], nv.act) : 0.0f;
   }
   __syncthreads();
-  if (j < HP) {
-    float acc = 0.0f;
+  for (int l = nv.L - 2; l >= 0; --l) {
+    if (j < HP) {
+      float acc = 0.0f;
+      const float* __restrict__ din = rv + rv_d<HP>(l + 1);
+      const float* __restrict__ WT = nv.WhT[l];
 #pragma unroll 8
-    for (int k = 0; k < nv.H; ++k) acc = fmaf(rv[3 * HP + k], nv.W2T[k * HP + j], acc);
-    rv[4 * HP + j] = (j < nv.H) ? acc * dact_fn(rv[HP + j], nv.act) : 0.0f;
+      for (int k = 0; k < nv.H; ++k) acc = fmaf(din[k], WT[k * HP + j], acc);
+      rv[rv_d<HP>(l) + j] = (j < nv.H) ? acc * dact_fn(rv[rv_h<HP>(l) + j], nv.act) : 0.0f;
+    }
+    __syncthreads();
   }
-  __syncthreads();
 #pragma unroll
   for (int i = 0; i < NDX; ++i) dx[i] = 0.0f;
 #pragma unroll 8
   for (int k = 0; k < nv.H; ++k) {
-    const float d = rv[4 * HP + k];
+    const float d = rv[rv_d<HP>(0) + k];
 #pragma unroll
     for (int i = 0; i < NDX; ++i) dx[i] = fmaf(d, nv.W1T[k * HP + i], dx[i]);
   }
@@ -286,7 +328,8 @@ __device__ __forceinline__ void row_delta(const NetView<HP>& nv, float* __restri
 
 // ---- weight gradient ----------------------------------------------------------------------------------------
 // Thread u of the CTA owns block `blk = u % NB` and row chunk `u / NB` of the block list
-//   [ dW1: ceil((nin+1)/4) x HP/4 | dW2: HP/4 x HP/4 | dW3T: ceil(nout/4) x HP/4 ].
+//   [ dW1: ceil((nin+1)/4) x HP/4 | dWh[l]: HP/4 x HP/4 for each hidden-to-hidden layer | dW3T: ceil(nout/4) x HP/4 ]
+// (at most kThreads blocks: three hidden layers need HP = 24).
 // A block is (feature chunk ca of tile A) x (feature chunk cb of tile B): p[a][b] += sum_rows A[4ca+a][r] B[4cb+b][r];
 // one float4 per (chunk, row).  The 8 threads of a quarter-warp start at different rows (row rotation), so their
 // 128-bit loads fall into different banks although they walk the same row range.
@@ -295,7 +338,8 @@ struct WGrad {
   float p[4][4];
   int a_off, b_off;         // float offsets of the two chunks from the tile base (xt), row 0
   int r0, nr;               // first row and number of rows of this thread's chunk
-  int type, k0, j0;         // 0: dW1[k][j]  1: dW2[k][j]  2: dW3T[j][k];  -1: idle
+  int type, k0, j0;         // 0: dW1[k][j]  1 .. L-1: dWh[type-1][k][j]  L: dW3T[j][k];  -1: idle
+  int L;
   int chunk, S;
 
   // u: index of the calling thread among the kThreads threads that share the tile set (threadIdx.x unless a CTA hosts
@@ -303,8 +347,9 @@ struct WGrad {
   template <class TL>
   __device__ void init(const NetView<HP>& nv, const TL& t, int u = -1) {
     constexpr int JB = HP / 4;
+    L = nv.L;
     const int nb1 = ((nv.nin + 1 + 3) / 4) * JB, nb2 = JB * JB, nb3 = ((nv.nout + 3) / 4) * JB;
-    const int NB = nb1 + nb2 + nb3;
+    const int NB = nb1 + (L - 1) * nb2 + nb3;
     S = kThreads / NB;
     S = S < 1 ? 1 : (S > 4 ? 4 : S);
 #pragma unroll
@@ -321,15 +366,15 @@ struct WGrad {
     int ta, tb;
     if (blk < nb1) {
       type = 0; k0 = 4 * (blk / JB); j0 = 4 * (blk % JB);
-      ta = (int)(t.xt - t.xt) + (k0 >> 2) * (4 * TR); tb = (int)(t.d1 - t.xt) + (j0 >> 2) * (4 * TR);
-    } else if (blk < nb1 + nb2) {
-      const int b2 = blk - nb1;
-      type = 1; k0 = 4 * (b2 / JB); j0 = 4 * (b2 % JB);
-      ta = (int)(t.h1 - t.xt) + (k0 >> 2) * (4 * TR); tb = (int)(t.d2 - t.xt) + (j0 >> 2) * (4 * TR);
+      ta = (int)(t.xt - t.xt) + (k0 >> 2) * (4 * TR); tb = (int)(t.d[0] - t.xt) + (j0 >> 2) * (4 * TR);
+    } else if (blk < nb1 + (L - 1) * nb2) {
+      const int l = (blk - nb1) / nb2, b2 = (blk - nb1) % nb2;
+      type = 1 + l; k0 = 4 * (b2 / JB); j0 = 4 * (b2 % JB);
+      ta = (int)(t.h[l] - t.xt) + (k0 >> 2) * (4 * TR); tb = (int)(t.d[l + 1] - t.xt) + (j0 >> 2) * (4 * TR);
     } else {
-      const int b3 = blk - nb1 - nb2;
-      type = 2; j0 = 4 * (b3 / JB); k0 = 4 * (b3 % JB);
-      ta = (int)(t.dout - t.xt) + (j0 >> 2) * (4 * TR); tb = (int)(t.h2 - t.xt) + (k0 >> 2) * (4 * TR);
+      const int b3 = blk - nb1 - (L - 1) * nb2;
+      type = L; j0 = 4 * (b3 / JB); k0 = 4 * (b3 % JB);
+      ta = (int)(t.dout - t.xt) + (j0 >> 2) * (4 * TR); tb = (int)(t.h[L - 1] - t.xt) + (k0 >> 2) * (4 * TR);
     }
     a_off = ta; b_off = tb;
   }
@@ -358,8 +403,8 @@ struct WGrad {
   // single-row variant (row_fwd / row_delta above): only the first row chunk's owner of a block accumulates
   __device__ __forceinline__ void accumulate_row(const float* __restrict__ rv) {
     if (type < 0 || chunk != 0) return;
-    const float4 av = ld4(rv + (type == 0 ? k0 : type == 1 ? HP + k0 : 5 * HP + j0));
-    const float4 bv = ld4(rv + (type == 0 ? 4 * HP + j0 : type == 1 ? 3 * HP + j0 : 2 * HP + k0));
+    const float4 av = ld4(rv + (type == 0 ? k0 : type < L ? rv_h<HP>(type - 1) + k0 : rv_do<HP>() + j0));
+    const float4 bv = ld4(rv + (type == 0 ? rv_d<HP>(0) + j0 : type < L ? rv_d<HP>(type) + j0 : rv_h<HP>(L - 1) + k0));
     p[0][0] = fmaf(av.x, bv.x, p[0][0]); p[0][1] = fmaf(av.x, bv.y, p[0][1]);
     p[0][2] = fmaf(av.x, bv.z, p[0][2]); p[0][3] = fmaf(av.x, bv.w, p[0][3]);
     p[1][0] = fmaf(av.y, bv.x, p[1][0]); p[1][1] = fmaf(av.y, bv.y, p[1][1]);
@@ -378,16 +423,16 @@ struct WGrad {
       if (j >= H || k > nin) return -1;
       return k < nin ? k * H + j : nin * H + j;
     }
-    if (type == 1) {
+    if (type < L) {                                   // hidden-to-hidden layer type - 1
       const int k = k0 + a, j = j0 + b;
       if (j >= H || k > H) return -1;
-      const int base = nin * H + H;
+      const int base = nin * H + H + (type - 1) * (H * H + H);
       return k < H ? base + k * H + j : base + H * H + j;
     }
-    if (type == 2) {
+    if (type == L) {
       const int j = j0 + a, k = k0 + b;
       if (j >= nout || k > H) return -1;
-      const int base = nin * H + H + H * H + H;
+      const int base = nin * H + H + (L - 1) * (H * H + H);
       return k < H ? base + k * nout + j : base + H * nout + j;
     }
     return -1;

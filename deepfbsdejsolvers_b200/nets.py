@@ -50,9 +50,10 @@ class Scalar:
 class DenseNet:
     def __init__(self, ndimOut: int, nbNeurons, activation="tanh"):
         self.nbNeurons = [int(h) for h in np.asarray(nbNeurons).reshape(-1)]
-        if len(self.nbNeurons) != 2 or self.nbNeurons[0] != self.nbNeurons[1]:
-            raise ValueError("the sm_100a kernels are compiled for two equal hidden layers (the reference's default nbLayer = 2) of "
-                             "width <= 35 for the compensator-free solvers, <= 31 otherwise (tcgen05: <= 22)")
+        if not 1 <= len(self.nbNeurons) <= 3 or len(set(self.nbNeurons)) != 1:
+            raise ValueError("the sm_100a kernels take 1, 2 or 3 EQUAL hidden layers (the reference's nbLayer / nbNeuron; default 2 x 21) "
+                             "of width <= 35 for the compensator-free solvers, <= 31 otherwise (three layers: <= 23); the tcgen05 "
+                             "kernels cover two layers of width <= 22")
         self.ndimOut = int(ndimOut)
         self.activation = activation_name(activation)
         self.params: Optional[np.ndarray] = None
@@ -62,9 +63,13 @@ class DenseNet:
     def H(self) -> int:
         return self.nbNeurons[0]
 
+    @property
+    def L(self) -> int:
+        return len(self.nbNeurons)
+
     def spec(self) -> NetSpec:
         assert self.nin is not None, "network not built yet"
-        return NetSpec(self.nin, self.H, self.ndimOut, self.activation, 2)
+        return NetSpec(self.nin, self.H, self.ndimOut, self.activation, self.L)
 
     def build(self, nin: int) -> None:
         """Create the variables (kernels Glorot-normal, biases zero) for input width nin; no-op if already built."""
@@ -73,7 +78,7 @@ class DenseNet:
                 raise ValueError(f"network was built for {self.nin} inputs, got {nin}")
             return
         self.nin = int(nin)
-        dims = [self.nin, self.H, self.H, self.ndimOut]
+        dims = [self.nin] + [self.H] * self.L + [self.ndimOut]
         parts = []
         for a, b in zip(dims[:-1], dims[1:]):
             parts += [_init.glorot_normal((a, b)).reshape(-1), np.zeros(b, dtype=np.float32)]
@@ -91,7 +96,7 @@ class DenseNet:
 
     def layer_arrays(self):
         """[(W, b), ...] views of the flat parameter vector."""
-        dims = [self.nin, self.H, self.H, self.ndimOut]
+        dims = [self.nin] + [self.H] * self.L + [self.ndimOut]
         out, off = [], 0
         for a, b in zip(dims[:-1], dims[1:]):
             W = self.params[off:off + a * b].reshape(a, b); off += a * b

@@ -155,7 +155,7 @@ class PricingSolverBase:
         jtc_ok = False
         if not self.REG and d in (1, 10):
             sb = self.netB.spec() if self.TWO_NET else spec
-            jtc_ok = sb.H <= 22 and spec.H <= 23 and sb.L == 2 and sb.activation == "tanh"
+            jtc_ok = sb.H <= 22 and spec.H <= 23 and sb.L == 2 and spec.L == 2 and sb.activation == "tanh"
         auto = tc_ok or jtc_ok
         if self.tensor_cores and not auto:
             raise ValueError(f"{type(self).__name__}: tensor_cores=True, but the tcgen05 kernels cover two hidden layers of width <= 22 "

@@ -29,7 +29,7 @@ def mfg_params(nbDays=2, jumpModel="stochastic"):
                 sig0=0.1, sig=0.3, alphaTarget=-0.2, jumpModel=jumpModel, coeffEqui=1.0)
 
 
-def pricing_layout(kind, scheme, d, H=21, act="tanh"):
+def pricing_layout(kind, scheme, d, H=21, act="tanh", L=2):
     brown = kind == "merton"
     one = scheme.endswith("1")
     reg = scheme.endswith("Reg")
@@ -39,13 +39,13 @@ def pricing_layout(kind, scheme, d, H=21, act="tanh"):
         noutA = 1
     else:
         noutA = 1 + d if brown else 1
-    nets = [MLPSpec(1 + d, [H, H], noutA, act)]
+    nets = [MLPSpec(1 + d, [H] * L, noutA, act)]
     if not one:
-        nets.append(MLPSpec(1 + 2 * d, [H, H], 1, act))
+        nets.append(MLPSpec(1 + 2 * d, [H] * L, 1, act))
     return ParamLayout(nets, n_y0=1 if scheme == "Global" else 0)
 
 
-def mfg_layout(scheme, Hh=20, H=22, act="tanh"):
+def mfg_layout(scheme, Hh=20, H=22, act="tanh", L=2):
     reg = scheme.endswith("Reg")
     if scheme == "Global":
         a, b = 2, 3
@@ -53,7 +53,7 @@ def mfg_layout(scheme, Hh=20, H=22, act="tanh"):
         a, b = 1, 1
     else:
         a, b = 3, 4
-    return ParamLayout([MLPSpec(4, [Hh, Hh], a, act), MLPSpec(6, [H, H], b, act)], n_y0=2 if scheme == "Global" else 0)
+    return ParamLayout([MLPSpec(4, [Hh] * L, a, act), MLPSpec(6, [H] * L, b, act)], n_y0=2 if scheme == "Global" else 0)
 
 
 def random_theta(layout, seed, scale_bias=0.1):
@@ -127,7 +127,7 @@ def native_pricing(ctx, kind, params, scheme, layout, d=1, M=0, limit=30, stale_
     else:
         mm = VGmodel(params["T"], params["N"], params["r"], params["theta"], params["kappa"], params["sigmaJ"], params["K"],
                      params["x0"], AbsCoupling(ALIN))
-    nets = [NetSpec(n.nin, n.hidden[0], n.nout, n.activation) for n in layout.nets]
+    nets = [NetSpec(n.nin, n.hidden[0], n.nout, n.activation, len(n.hidden)) for n in layout.nets]
     return mm.make_solver(PRICING_SCHEME_ID[scheme], nets, layout.n_y0, M, ctx=ctx, stale_time=stale_time, tensor_cores=tensor_cores)
 
 
@@ -135,5 +135,5 @@ def native_mfg(ctx, params, scheme, layout, tensor_cores=False):
     from deepfbsdejsolvers_b200 import NetSpec
     from deepfbsdejsolvers_b200.coupledMFG import ModelCoupledFBSDE
     mm = ModelCoupledFBSDE(**params)
-    nets = [NetSpec(n.nin, n.hidden[0], n.nout, n.activation) for n in layout.nets]
+    nets = [NetSpec(n.nin, n.hidden[0], n.nout, n.activation, len(n.hidden)) for n in layout.nets]
     return mm.make_solver(MFG_SCHEME_ID[scheme], nets, layout.n_y0, ctx=ctx, tensor_cores=tensor_cores)

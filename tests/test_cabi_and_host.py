@@ -71,8 +71,14 @@ def test_net_lazy_build_and_layout():
     km = kerasModels(Net_hat, NetM, "Global", 2, 3, [20, 20], [22, 22], "tanh", "tanh")
     assert hasattr(km.model_hat, "Y0_hat") and hasattr(km.model, "Y0")
     assert not hasattr(kerasModels(Net_hat, NetM, "SumLocal", 3, 4, [20, 20], [22, 22], "tanh", "tanh").model, "Y0")
+    n3 = Net(0, 1, [21, 21, 21], "tanh")             # nbLayer = 3 (mainMerton.py:13): three equal hidden layers
+    n3.build(2)
+    assert n3.spec().L == 3 and n3.params.size == 2 * 21 + 21 + 2 * (21 * 21 + 21) + 21 + 1 and len(n3.layer_arrays()) == 4
+    assert Net(0, 1, [16], "relu").L == 1
     with pytest.raises(ValueError):
-        Net(0, 1, [21, 21, 21], "tanh")
+        Net(0, 1, [21, 21, 21, 21], "tanh")
+    with pytest.raises(ValueError):
+        Net(0, 1, [21, 16], "tanh")
 
 
 def test_coupling_recognition():

@@ -269,3 +269,76 @@ def test_unsupported_widths_fail_loudly(ctx):
         H.native_pricing(ctx, "merton", p, "SumLocalReg", H.pricing_layout("merton", "SumLocalReg", 1, H=36), d=1)
     with pytest.raises(FbsdejError):       # jump schemes stop at H = 31
         H.native_pricing(ctx, "merton", p, "Global", H.pricing_layout("merton", "Global", 1, H=33), d=1, M=8)
+
+
+# ---- other depths (the reference's --nbLayer, mainMerton.py:13 / mainVG.py:13 / mainMFGComparison.py:14-15): 1 or 3 equal hidden
+# layers on the fp32 FFMA kernels ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("L", [1, 3])
+@pytest.mark.parametrize("kind,scheme,d,B,M", [("merton", "Global", 1, 10, 150), ("merton", "Global", 1, 37, 60), ("merton", "SumLocal1", 1, 24, 80),
+                                               ("merton", "MultiStep2", 10, 40, 48), ("merton", "SumLocalReg", 10, 300, 0),
+                                               ("merton", "MultiStepReg", 1, 200, 0), ("vg", "MultiStep2", 1, 24, 100), ("vg", "SumLocal2", 1, 12, 130)])
+def test_other_network_depths(ctx, L, kind, scheme, d, B, M):
+    if kind == "merton":
+        p = dict(H.MERTON, N=7)
+        om = MertonOracle(aLin=H.ALIN, limit=30 if d == 1 else 100, d=d, **p)
+        noise = H.merton_noise(om, B, max(M, 1), seed=82, with_jmc=M > 0)
+    else:
+        p = dict(H.VG, N=7)
+        om = VGOracle(aLin=H.ALIN, **p)
+        noise = H.vg_noise(om, B, max(M, 1), seed=82, with_jmc=M > 0)
+    layout = H.pricing_layout(kind, scheme, d, L=L)
+    theta = H.random_theta(layout, 81)
+    l32, g32, _ = H.oracle_pricing(om, scheme, layout, theta, noise, B)
+    l64, g64, aux64 = H.oracle_pricing(om, scheme, layout, theta, noise, B, dtype=torch.float64)
+    s = H.native_pricing(ctx, kind, p, scheme, layout, d=d, M=M, limit=30 if d == 1 else 100)
+    s.set_theta(theta)
+    s.set_noise(B, H.to_planes(noise["dW"]) if "dW" in noise else None, H.to_planes(noise["J"]), H.to_planes(noise["JMC"]) if M > 0 else None)
+    out, tx, ty, tz = s.loss(B, traj=True)
+    _close(out[0], l64)
+    _close(tx, aux64["X"].transpose(0, 2, 1))
+    _close(ty[:aux64["Y"].shape[0]], aux64["Y"])
+    g = s.grad(B)
+    _close(g[0], l64)
+    _grad_check(g[4:], g64, g32)
+    y = s.net_forward(0, np.array([[0.0] + [1.0] * d], dtype=np.float32))          # Y0 report path: Net.call with the same depth
+    from oracle import mlp_forward
+    y_ref = mlp_forward(torch.tensor(theta, dtype=torch.float64), layout, 0, torch.tensor([[0.0] + [1.0] * d], dtype=torch.float64))
+    assert np.abs(y - y_ref.numpy()).max() < 5e-6
+    s.train_steps(1, B, 3, 1e-3)
+    ctx.sync()
+    assert np.isfinite(s.get_theta()).all() and np.abs(s.get_theta() - theta).max() > 0
+
+
+@pytest.mark.parametrize("L", [1, 3])
+@pytest.mark.parametrize("scheme", ["Global", "SumLocal", "MultiStepReg"])
+def test_other_network_depths_mfg(ctx, L, scheme):
+    from oracle.mfg import sample_mfg_noise
+    p = H.mfg_params(1, "stochastic")
+    om = MFGOracle(**p)
+    layout = H.mfg_layout(scheme, L=L)
+    theta = H.random_theta(layout, 83)
+    B = 70
+    noise = sample_mfg_noise(om, B, torch.Generator().manual_seed(84))
+    (lh32, li32), g32, _ = H.oracle_mfg(om, scheme, layout, theta, noise, B)
+    (lh64, li64), g64, aux64 = H.oracle_mfg(om, scheme, layout, theta, noise, B, dtype=torch.float64)
+    s = H.native_mfg(ctx, p, scheme, layout)
+    s.set_theta(theta)
+    s.set_noise(B, noise["dW0"].numpy(), noise["dW"].numpy(), noise["dN"].numpy())
+    g = s.grad(B)
+    _close(g[1], lh64)
+    _close(g[2], li64)
+    _grad_check(g[4:], g64, g32)
+
+
+def test_drop_in_classes_take_nbLayer(ctx):
+    """Net(bY0, ndimOut, layerSize * np.ones(nbLayer), activation) as mainMerton.py:88,101 builds it, for nbLayer = 1 and 3."""
+    from deepfbsdejsolvers_b200 import coupledPricing as cp, set_seed
+    set_seed(3)
+    M = H.MERTON
+    for nbLayer in (1, 3):
+        mm = cp.MertonJumpModel(M["T"], 6, M["r"], M["muJ"], M["sigmaJ"], M["sigma"], M["lam"], M["K"], M["x0"], cp.AbsCoupling(H.ALIN), 30)
+        layer = 21 * np.ones((nbLayer,), dtype=np.int32)
+        solver = cp.SolverSumLocalFBSDE2(mm, cp.Net(0, 2, layer, "tanh"), cp.Net(0, 1, layer, "tanh"), 3e-4, M=64, ctx=ctx)
+        listY0, _ = solver.train(8, 16, 4, 2)
+        assert len(listY0) == 2 and np.isfinite(listY0).all() and np.isfinite(solver.lossList).all()
+        assert solver.native.nets[0].L == nbLayer
