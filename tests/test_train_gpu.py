@@ -89,6 +89,13 @@ def test_driver_scripts_run(ctx, tmp_path, monkeypatch):
     hY0, Y0 = mainMFGComparison.main(["--nEpochExt", "2", "--nEpoch", "3", "--batchSize", "16", "--methods", "Global,SumLocalReg"])
     assert len(hY0) == 2 and len(Y0[0]) == 2 and np.isfinite(np.array(Y0)).all()
     assert (tmp_path / "merton_Y0.csv").exists() and (tmp_path / "Y0List.csv").exists()
+    # the network-shape flags of the reference's command lines (mainMerton.py:13-14, mainMFGComparison.py:14-17)
+    cols = mainMerton.main(["--nEpochExt", "1", "--nEpoch", "2", "--batchSize", "4", "--nbLayer", "3", "--nbNeuron", "16",
+                            "--methods", "Global,SumLocalReg"])
+    assert np.isfinite(cols["Y0_Global"]).all() and np.isfinite(cols["Y0_SumLocalReg"]).all()
+    hY0, Y0 = mainMFGComparison.main(["--nEpochExt", "1", "--nEpoch", "2", "--batchSize", "16", "--nbLayer_hat", "1", "--nbNeuron", "30",
+                                      "--methods", "SumLocal"])
+    assert np.isfinite(np.array(Y0)).all()
 
 
 @pytest.mark.parametrize("name", ["SolverGlobalFBSDE", "SolverSumLocalFBSDE"])
