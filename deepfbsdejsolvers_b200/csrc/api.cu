@@ -287,6 +287,7 @@ void fill_pricing_args(const fbsdej_solver* s, const float* theta, int B, int B_
   a.has_y = s->has_y; a.zoff = s->zoff; a.has_z = s->has_z; a.feat_mode = s->feat_mode;
   a.stale_time = s->desc.stale_time;
   a.mma_mode = s->desc.mma_mode;
+  a.jump_sep = getenv("FBSDEJ_NO_JUMP_SEP") ? 0 : 1;
   a.inv_B = 1.0f / (float)B_global;
   if (s->model == FBSDEJ_MODEL_MERTON) {
     a.dt = (float)(s->mer.T / s->mer.N); a.r = (float)s->mer.r; a.K = (float)s->mer.K; a.x0 = (float)s->mer.x0;

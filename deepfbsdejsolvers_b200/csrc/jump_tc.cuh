@@ -123,12 +123,92 @@ struct JumpTcFwd {
     tc::tc_fence_before();
     return y;
   }
+  // ---- separable first layer (one path per thread, two-network schemes) ------------------------------------------------
+  // The input row is (t, state, jump features, 1) and the jump features are the same for every row of a tile (all 128 paths meet
+  // the same compensator sample), so the layer-1 pre-activation splits into a row part a_b (ONE GEMM per path-step: preact) and
+  // a sample part c_m (24 numbers per sample, computed by the caller, uniform over the tile): h1 = act(a_b + scale_b c_m).
+  // An evaluation is then one MMA round trip instead of two and needs no input operand.
+  // xin: the row's inputs with the jump-feature slots ZEROED; pre: the layer-1 pre-activations (incl. the constant-1 unit).
+  __device__ __forceinline__ void preact(const float (&xin)[NI], float (&pre)[24]) {
+    using namespace rtc;
+    const int row = threadIdx.x;
+#pragma unroll
+    for (int c8 = 0; c8 < NXC; ++c8) fwd::store_tf32x8(lane_a, c8, xin + 8 * c8);
+    fwd::publish_tmem();
+    if (row == 0) {
+      tc::tc_fence_after();
+      fwd::gemm_k_tf32<NXC>(tmem, tmem_a, sbase + W1B_HI * 4, sbase + W1B_LO * 4);
+      tc::mma_commit(bar);
+    }
+    tc::mbar_wait(bar, phase); phase ^= 1; tc::tc_fence_after();
+    tc::tmem_ld8(lane_base, reinterpret_cast<float (&)[8]>(pre[0]));
+    tc::tmem_ld8(lane_base + 8, reinterpret_cast<float (&)[8]>(pre[8]));
+    tc::tmem_ld8(lane_base + 16, reinterpret_cast<float (&)[8]>(pre[16]));
+    tc::tmem_ld_wait();
+    tc::tc_fence_before();
+  }
+  // c: the sample part (24 floats in shared memory, the same address for every thread), scale: the row's factor on it
+  __device__ __forceinline__ float eval_sep(const float (&pre)[24], const float* __restrict__ c, float scale) {
+    using namespace rtc;
+    const int row = threadIdx.x, warp = row >> 5;
+#pragma unroll
+    for (int c8 = 0; c8 < 3; ++c8) {
+      const float4 ca = ld4(c + 8 * c8), cb = ld4(c + 8 * c8 + 4);
+      const float cv[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+      float t8[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t8[q] = actf<ACT>(fmaf(scale, cv[q], pre[8 * c8 + q]));
+      fwd::store_tf32x8(lane_a, c8, t8);
+    }
+    fwd::publish_tmem();
+    if (warp == 1 && (row & 31) == 0) {
+      tc::tc_fence_after();
+      fwd::gemm_k_tf32<3>(tmem, tmem_a, sbase + W2B_HI * 4, sbase + W2B_LO * 4);
+      tc::mma_commit(bar);
+    }
+    tc::mbar_wait(bar, phase); phase ^= 1; tc::tc_fence_after();
+    float y = sm[OFF_W3 + 24];
+#pragma unroll
+    for (int c8 = 0; c8 < 3; ++c8) {
+      float t8[8];
+      tc::tmem_ld8(lane_base + 8 * c8, t8);
+      tc::tmem_ld_wait();
+      const float4 wa = ld4(sm + OFF_W3 + 8 * c8), wb = ld4(sm + OFF_W3 + 8 * c8 + 4);
+      const float w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+      for (int q = 0; q < 8; ++q) y = fmaf(actf<ACT>(t8[q]), w8[q], y);
+    }
+    tc::tc_fence_before();
+    return y;
+  }
   __device__ void finish() {
     tc::tc_fence_before();
     __syncthreads();
     if (threadIdx.x < 32) { tc::tmem_dealloc(tmem, 32); tc::tmem_dealloc(tmem_a, 64); }
   }
 };
+
+// Sample parts of the separable first layer for the samples [m0, m0 + kThreads) of step i: thread t fills ctab[t][0..24) with
+// c_m[j] = sum_k W1[slot0 + k][j] feature(J_m[k]) (sample index nnz = the de-duplicated zero sample; beyond it zeros).
+template <class Model>
+__device__ __forceinline__ void jump_sample_parts(const PricingArgs& a, int i, int m0, int nnz, float* __restrict__ ctab) {
+  constexpr int D = Model::D;
+  const int m = m0 + (int)threadIdx.x, H = a.netB.H;
+  const float* __restrict__ W = a.theta + a.netB.ext_off + Model::jump_slot0() * H;    // rows slot0 .. of W1 [in][out]
+  float f[Model::kJumpSlots];
+#pragma unroll
+  for (int k = 0; k < Model::kJumpSlots; ++k)
+    f[k] = m <= nnz ? Model::jump_feature(a, m < nnz ? a.JMC[((size_t)i * D + k) * a.Mcap + m] : 0.0f) : 0.0f;
+  float* __restrict__ out = ctab + (size_t)threadIdx.x * 24;
+  for (int j = 0; j < 24; ++j) {
+    float acc = 0.0f;
+    if (j < H) {
+#pragma unroll
+      for (int k = 0; k < Model::kJumpSlots; ++k) acc = fmaf(__ldg(W + k * H + j), f[k], acc);
+    }
+    out[j] = acc;
+  }
+}
 
 template <int ACT, int NXC>
 struct JumpTcBwd {

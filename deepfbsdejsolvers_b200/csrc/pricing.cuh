@@ -40,6 +40,7 @@ struct PricingArgs {
   int feat_mode;              // Merton two-net: 0 -> J (Global), 1 -> e^J
   int stale_time;             // SumLocal*: time feature of step k >= 1 is k-1
   int mma_mode;               // 0 = fp32 FFMA layers, 1 = tcgen05 (compensator-free solvers only)
+  int jump_sep;               // tcgen05 jump rows, one path per thread: separable first layer (jump_tc.cuh; FBSDEJ_NO_JUMP_SEP=1 turns it off)
   float inv_B;                // 1 / GLOBAL batch (data-parallel ranks sum their partial means)
   float dt, r, K, x0, aLin, sig, drift_dt;
   NetRt netA, netB;
@@ -286,6 +287,12 @@ struct MertonModel {
 #pragma unroll
     for (int k = 0; k < D; ++k) dX[k] += a.one_net ? dx[1 + k] * expf(Jv[k]) : dx[1 + k];
   }
+  // Two-network schemes: the first layer of the jump network is SEPARABLE, W1 in = (time, state, 1 part) + scale * (sample part):
+  // the D jump features sit in the input slots [kJumpSlot0, + D), feature k = jump_feature(J_k); scale = 1.
+  static constexpr int kJumpSlots = D;
+  __device__ static __forceinline__ int jump_slot0() { return 1 + D; }
+  __device__ static __forceinline__ float jump_feature(const PricingArgs& a, float J) { return a.feat_mode == 0 ? J : expf(J); }
+  __device__ static __forceinline__ float jump_scale(const float (&)[D]) { return 1.0f; }
 };
 
 struct VGModel {
@@ -342,6 +349,11 @@ struct VGModel {
     if (a.one_net) dX[0] += dx[1] * (1.0f + Jv[0]);
     else dX[0] += dx[1] + dx[2] * Jv[0];
   }
+  // separable first layer (two-network schemes): the jump feature X J = scale * J with scale = X (slot 2)
+  static constexpr int kJumpSlots = 1;
+  __device__ static __forceinline__ int jump_slot0() { return 2; }
+  __device__ static __forceinline__ float jump_feature(const PricingArgs&, float J) { return J; }
+  __device__ static __forceinline__ float jump_scale(const float (&X)[1]) { return X[0]; }
 };
 
 }  // namespace fbsdej

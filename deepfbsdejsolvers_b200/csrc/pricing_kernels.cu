@@ -138,6 +138,29 @@ __global__ void __launch_bounds__(kThreads, JTC ? 4 : 0) pricing_forward(const P
         const int iters = (nnz + 2 + G * C - 1) / (G * C);
         float gc[2] = {0.0f, 0.0f};
         jf.set_time(tf);
+        if (G == 1 && !a.one_net && a.jump_sep) {
+          // one path per thread: every row of the tile meets the same compensator sample, and the first layer is separable
+          // (jump_tc.cuh: preact / eval_sep) - one GEMM for the state part of the step, then one MMA round trip per sample
+          float in[HP], pre[24];
+          Model::template jump_input<HP>(a, tf, X, Jv, in);
+#pragma unroll
+          for (int k = 0; k < Model::kJumpSlots; ++k) in[Model::jump_slot0() + k] = 0.0f;
+          jf.preact(reinterpret_cast<const float (&)[8 * NXC]>(in), pre);
+          const float scale = Model::jump_scale(X);
+          float* const ctab = t.h[0];                      // (the (U, Z) network is done with its tiles for this step)
+          for (int m0 = 0; m0 <= nnz; m0 += kThreads) {
+            __syncthreads();
+            jump_sample_parts<Model>(a, i, m0, nnz, ctab);
+            __syncthreads();
+            const int mend = (nnz + 1 - m0 < kThreads) ? nnz + 1 - m0 : kThreads;
+            for (int mm = 0; mm < mend; ++mm) {
+              const float y = jf.eval_sep(pre, ctab + mm * 24, scale);
+              gc[1] = fmaf(m0 + mm < nnz ? 1.0f : (float)n0, y, gc[1]);
+            }
+          }
+          Model::template jump_input<HP>(a, tf, X, Jv, in);                  // the path's own jump: a full row
+          gc[0] = jf.eval(reinterpret_cast<const float (&)[8 * NXC]>(in));
+        } else {
         for (int it = 0; it < iters; ++it) {
           const int m = (it * C + crank) * G + g;
           float Jm[D];
@@ -160,6 +183,7 @@ __global__ void __launch_bounds__(kThreads, JTC ? 4 : 0) pricing_forward(const P
           const float y = jf.eval(reinterpret_cast<const float (&)[8 * NXC]>(in));
           gc[1] = fmaf(w, y, gc[1]);
           if (m == nnz + 1) gc[0] = y;
+        }
         }
         group_allsum2(gc[0], gc[1], G, red);
         if (C > 1) cluster_allsum<2>(gc, red, cpar, C);

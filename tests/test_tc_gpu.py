@@ -273,3 +273,36 @@ def test_tensor_core_kernels_are_bitwise_repeatable(ctx, kind):
     assert np.isfinite(first).all()
     for _ in range(7):
         assert np.array_equal(run(), first)
+
+
+@pytest.mark.parametrize("kind,scheme,d,M", [("merton", "Global", 1, 24), ("merton", "MultiStep2", 1, 300), ("merton", "SumLocal2", 10, 40),
+                                             ("merton", "Global", 10, 150), ("vg", "Global", 1, 40), ("vg", "SumLocal2", 1, 200)])
+def test_jump_network_separable_first_layer(ctx, kind, scheme, d, M):
+    """One path per thread (large batch, two-network schemes): the jump rows of a tile share their compensator sample, and the first
+    layer splits into a path part and a sample part (jump_tc.cuh: preact / eval_sep and their adjoint) - against the float64 oracle,
+    and against the same kernels with the split turned off."""
+    B = 38000
+    if kind == "merton":
+        p = dict(H.MERTON, N=3)
+        om = MertonOracle(aLin=H.ALIN, limit=30 if d == 1 else 100, d=d, **p)
+        noise = H.merton_noise(om, B, M, seed=92, with_jmc=True)
+    else:
+        p = dict(H.VG, N=3)
+        om = VGOracle(aLin=H.ALIN, **p)
+        noise = H.vg_noise(om, B, M, seed=92, with_jmc=True)
+    layout = H.pricing_layout(kind, scheme, d)
+    theta = H.random_theta(layout, 91)
+    l32, g32, _ = H.oracle_pricing(om, scheme, layout, theta, noise, B)
+    l64, g64, aux64 = H.oracle_pricing(om, scheme, layout, theta, noise, B, dtype=torch.float64)
+    s = H.native_pricing(ctx, kind, p, scheme, layout, d=d, M=M, limit=30 if d == 1 else 100, tensor_cores=True)
+    s.set_theta(theta)
+    s.set_noise(B, H.to_planes(noise["dW"]) if "dW" in noise else None, H.to_planes(noise["J"]), H.to_planes(noise["JMC"]))
+    out, tx, ty, tz = s.loss(B, traj=True)
+    assert abs(out[0] - l64) <= 1e-5 * abs(l64), (out[0], l64)
+    X = aux64["X"].transpose(0, 2, 1)
+    assert np.abs(tx - X).max() <= 2e-6 + 1e-5 * np.abs(X).max()
+    g = s.grad(B)
+    scale = np.abs(g64).max()
+    e_gpu = np.abs(g[4:] - g64).max() / scale
+    print(kind, scheme, d, "loss rel", abs(out[0] - l64) / abs(l64), "grad rel-to-max", e_gpu)
+    assert e_gpu <= JUMP_TC_GRAD_TOL, f"gradient error {e_gpu:.3e}"
