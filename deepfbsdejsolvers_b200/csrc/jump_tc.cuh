@@ -406,6 +406,141 @@ struct JumpTcBwd {
     load_acc<NI, NDX>(lane_base + C_ACC, dx);
     tc::tc_fence_before();
   }
+  // ---- separable first layer (JumpTcFwd: preact / eval_sep), adjoint ------------------------------------------------------
+  // preact: the state part of the layer-1 pre-activation of this row, ONE GEMM per path-step (xin: inputs with the jump slots
+  // zeroed, xin[0] = time, xin[nin] = 1).
+  __device__ __forceinline__ void preact(const float (&xin)[NI], float (&pre)[24]) {
+    using namespace rtc;
+    const int row = threadIdx.x, warp = row >> 5;
+    drain_w();
+#pragma unroll
+    for (int c8 = 0; c8 < NXC; ++c8) tc::store_bf16x8(u4 + XA_HI, u4 + XA_LO, c8, row, xin + 8 * c8);
+    publish();
+    if (warp == 0 && (row & 31) == 0) {
+      tc::tc_fence_after();
+      gemm_k<KS1, NBR, true>(tmem + C_ACC, sa(XA_HI), sa(XA_LO), sw(W1B));
+      tc::mma_commit(bar_f);
+    }
+    wait_f();
+    load_acc<NBR, 24>(lane_base + C_ACC, pre);
+    tc::tc_fence_before();
+  }
+  // One compensator sample: h1 = act(pre + scale c) (no layer-1 GEMM), layer 2, deltas; the layer-1 delta d1 is ADDED to sumd1
+  // (its input gradient and the weight gradient of the state rows are taken once per path-step, finish_state) and d1 . c to
+  // dscale; the weight gradient of the jump-feature rows, (sum_b d1_b) (x) feature, is this sample's own: WG1 on the X tile
+  // xj = the row's jump-only inputs (zeros outside the jump slots).  Two MMA round trips instead of four.
+  __device__ __forceinline__ void step_sep(const float (&pre)[24], const float* __restrict__ c, float scale, const float (&xj)[NI], float dout,
+                                           float (&sumd1)[24], float& dscale) {
+    using namespace rtc;
+    const int row = threadIdx.x, warp = row >> 5;
+    const bool issuer = (row & 31) == 0;
+    drain_w();                                         // WG1 of the previous sample read X, D1 (= the H2_hi / H1_lo tiles)
+#pragma unroll
+    for (int c8 = 0; c8 < NXC; ++c8) tc::store_bf16x8(u4 + XA_HI, u4 + XA_LO, c8, row, xj + 8 * c8);
+    float h1[24];
+#pragma unroll
+    for (int c8 = 0; c8 < 3; ++c8) {
+      const float4 ca = ld4(c + 8 * c8), cb = ld4(c + 8 * c8 + 4);
+      const float cv[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+#pragma unroll
+      for (int q = 0; q < 8; ++q) h1[8 * c8 + q] = actf<ACT>(fmaf(scale, cv[q], pre[8 * c8 + q]));
+      tc::store_bf16x8(u4 + H1_HI, u4 + H1_LO, c8, row, h1 + 8 * c8);
+    }
+    publish();
+    if (warp == 1 && issuer) {
+      tc::tc_fence_after();
+      gemm_k<2, NBR, true>(tmem + C_ACC, sa(H1_HI), sa(H1_LO), sw(W2B));
+      tc::mma_commit(bar_f);
+    }
+    wait_f();
+#pragma unroll
+    for (int c8 = 0; c8 < 3; ++c8) {
+      float t8[8], d2[8];
+      {
+        float q8[8];
+        tc::tmem_ld8(lane_base + C_ACC + 8 * c8, t8);
+        tc::tmem_ld8(lane_base + C_ACC + NBR + 8 * c8, q8);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t8[q] += q8[q];
+      }
+      const float4 wa = ld4(sm + OFF_W3 + 8 * c8), wb = ld4(sm + OFF_W3 + 8 * c8 + 4);
+      const float w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float h = actf<ACT>(t8[q]);
+        t8[q] = h;
+        d2[q] = dout * w8[q] * dactf<ACT>(h);
+      }
+      if (c8 == 2) d2[COL_DOUT - 16] = dout;
+      tc::store_bf16x8(u4 + H2_HI, u4 + H2_LO, c8, row, t8);
+      tc::store_bf16x8(u4 + D2_HI, u4 + D2_LO, c8, row, d2);
+    }
+    publish();
+    if (warp == 2 && issuer) {
+      tc::tc_fence_after();
+      gemm_k<2, NBR, true>(tmem + C_ACC, sa(D2_HI), sa(D2_LO), sw(WTB));
+      tc::mma_commit(bar_f);
+      gemm_rows_stacked<48>(tmem + C_W2, sa(H1_HI), sa(D2_HI), started ? 1u : 0u);
+      tc::mma_commit(bar_g);
+    }
+    wait_f();
+    {
+      float d1[24];
+#pragma unroll
+      for (int c8 = 0; c8 < 3; ++c8) {
+        float q8[8];
+        tc::tmem_ld8(lane_base + C_ACC + 8 * c8, reinterpret_cast<float (&)[8]>(d1[8 * c8]));
+        tc::tmem_ld8(lane_base + C_ACC + NBR + 8 * c8, q8);
+        tc::tmem_ld_wait();
+        const float4 ca = ld4(c + 8 * c8), cb = ld4(c + 8 * c8 + 4);
+        const float cv[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float v = (d1[8 * c8 + q] + q8[q]) * dactf<ACT>(h1[8 * c8 + q]);
+          d1[8 * c8 + q] = v;
+          sumd1[8 * c8 + q] += v;
+          dscale = fmaf(v, cv[q], dscale);
+        }
+      }
+      tc::mbar_wait(bar_g, phase_g); phase_g ^= 1;
+#pragma unroll
+      for (int c8 = 0; c8 < 3; ++c8) tc::store_bf16x8(u4 + D1_HI, u4 + D1_LO, c8, row, d1 + 8 * c8);
+    }
+    tc::tc_fence_before();
+    publish();
+    if (warp == 3 && issuer) {
+      tc::tc_fence_after();
+      gemm_rows_stacked<2 * NI, 64>(tmem + C_W1, sa(D1_HI), sa(XA_HI), started ? 1u : 0u);
+      tc::mma_commit(bar_w);
+    }
+    started = 1;
+    pending_w = 1;
+  }
+  // Once per path-step after its samples: the summed layer-1 delta against the state inputs - input gradient dx and the weight
+  // gradient of the time / state / bias rows of W1.
+  __device__ __forceinline__ void finish_state(const float (&xin)[NI], const float (&sumd1)[24], float (&dx)[NDX]) {
+    using namespace rtc;
+    const int row = threadIdx.x, warp = row >> 5;
+    drain_w();
+#pragma unroll
+    for (int c8 = 0; c8 < NXC; ++c8) tc::store_bf16x8(u4 + XA_HI, u4 + XA_LO, c8, row, xin + 8 * c8);
+#pragma unroll
+    for (int c8 = 0; c8 < 3; ++c8) tc::store_bf16x8(u4 + D1_HI, u4 + D1_LO, c8, row, sumd1 + 8 * c8);
+    publish();
+    if (warp == 3 && (row & 31) == 0) {
+      tc::tc_fence_after();
+      gemm_k<2, NI, true>(tmem + C_ACC, sa(D1_HI), sa(D1_LO), sw(W1T));
+      tc::mma_commit(bar_f);
+      gemm_rows_stacked<2 * NI, 64>(tmem + C_W1, sa(D1_HI), sa(XA_HI), started ? 1u : 0u);
+      tc::mma_commit(bar_w);
+    }
+    started = 1;
+    pending_w = 1;
+    wait_f();
+    load_acc<NI, NDX>(lane_base + C_ACC, dx);
+    tc::tc_fence_before();
+  }
   // TMEM weight gradients, added to g[...] (external flat layout of this network; first output column of W3 / b3).  All
   // threads call; the operand tiles are dead and serve as scratch (128 x SW floats).
   __device__ void flush(float* __restrict__ g) {

@@ -293,6 +293,7 @@ struct MertonModel {
   __device__ static __forceinline__ int jump_slot0() { return 1 + D; }
   __device__ static __forceinline__ float jump_feature(const PricingArgs& a, float J) { return a.feat_mode == 0 ? J : expf(J); }
   __device__ static __forceinline__ float jump_scale(const float (&)[D]) { return 1.0f; }
+  static constexpr bool kScaleIsState = false;
 };
 
 struct VGModel {
@@ -354,6 +355,7 @@ struct VGModel {
   __device__ static __forceinline__ int jump_slot0() { return 2; }
   __device__ static __forceinline__ float jump_feature(const PricingArgs&, float J) { return J; }
   __device__ static __forceinline__ float jump_scale(const float (&X)[1]) { return X[0]; }
+  static constexpr bool kScaleIsState = true;      // d(scale c)/dX = c: the adjoint adds sum_m d1_m . c_m to dL/dX
 };
 
 }  // namespace fbsdej

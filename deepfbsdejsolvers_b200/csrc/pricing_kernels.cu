@@ -343,6 +343,7 @@ __global__ void __launch_bounds__(kThreads, JTC ? 2 : 0) pricing_backward(const 
   static_assert(!JTC || 1 + D <= JB::NDX, "input gradients of the state come back in one read");
   JB jb;
   if constexpr (JTC) jb.init(smem, t.h[0], a.theta, a.netB);
+  float* const ctab = tb + TL::bwd_floats(Lmax);        // JTC: sample parts of the separable first layer (128 x 24)
 
   const int row = threadIdx.x;
   const int G = JUMP ? a.G : 1, ppb = kThreads / G, g = threadIdx.x % G;
@@ -500,6 +501,49 @@ __global__ void __launch_bounds__(kThreads, JTC ? 2 : 0) pricing_backward(const 
         const float cscale = -abar / (float)a.M * vmsk;
         const int iters = (nnz + 2 + G * C - 1) / (G * C);
         jb.set_time(tf);
+        if (G == 1 && !a.one_net && a.jump_sep) {
+          // one path per thread, separable first layer (jump_tc.cuh: preact / step_sep / finish_state)
+          float pre[24], sumd1[24], dscale = 0.0f;
+#pragma unroll
+          for (int j = 0; j < 24; ++j) sumd1[j] = 0.0f;
+          Model::template jump_input<HP>(a, tf, X, Jv, dx);
+#pragma unroll
+          for (int k = 0; k < Model::kJumpSlots; ++k) dx[Model::jump_slot0() + k] = 0.0f;
+          jb.preact(reinterpret_cast<const float (&)[8 * NXC]>(dx), pre);
+          const float scale = Model::jump_scale(X);
+          for (int m0 = 0; m0 <= nnz; m0 += kThreads) {
+            __syncthreads();
+            jump_sample_parts<Model>(a, i, m0, nnz, ctab);
+            __syncthreads();
+            const int mend = (nnz + 1 - m0 < kThreads) ? nnz + 1 - m0 : kThreads;
+            for (int mm = 0; mm < mend; ++mm) {
+              const int m = m0 + mm;
+              float xj[8 * NXC];
+#pragma unroll
+              for (int j = 0; j < 8 * NXC; ++j) xj[j] = 0.0f;
+#pragma unroll
+              for (int k = 0; k < Model::kJumpSlots; ++k)
+                xj[Model::jump_slot0() + k] = scale * Model::jump_feature(a, m < nnz ? a.JMC[((size_t)i * D + k) * a.Mcap + m] : 0.0f);
+              jb.step_sep(pre, ctab + mm * 24, scale, xj, cscale * (m < nnz ? 1.0f : (float)n0), sumd1, dscale);
+            }
+          }
+          float dn[JB::NDX];
+          jb.finish_state(reinterpret_cast<const float (&)[8 * NXC]>(dx), sumd1, dn);
+          {
+            float Jz[D];
+#pragma unroll
+            for (int k = 0; k < D; ++k) Jz[k] = 0.0f;
+#pragma unroll
+            for (int j = 0; j < JB::NDX; ++j) dx[j] = dn[j];
+            Model::template jump_input_grad<HP>(a, Jz, dx, dXj);
+            if (Model::kScaleIsState) dXj[0] += dscale;
+          }
+          Model::template jump_input<HP>(a, tf, X, Jv, dx);                    // the path's own jump: a full row
+          jb.step(reinterpret_cast<const float (&)[8 * NXC]>(dx), abar * vmsk, dn);
+#pragma unroll
+          for (int j = 0; j < JB::NDX; ++j) dx[j] = dn[j];
+          Model::template jump_input_grad<HP>(a, Jv, dx, dXj);
+        } else {
         for (int it = 0; it < iters; ++it) {
           const int m = (it * C + crank) * G + g;
           float Jm[D];
@@ -524,6 +568,7 @@ __global__ void __launch_bounds__(kThreads, JTC ? 2 : 0) pricing_backward(const 
 #pragma unroll
           for (int j = 0; j < JB::NDX; ++j) dx[j] = dn[j];
           Model::template jump_input_grad<HP>(a, Jm, dx, dXj);
+        }
         }
 #pragma unroll
         for (int k = 0; k < D; ++k) dXj[k] = (G == 1) ? dXj[k] : group_allsum(dXj[k], G, red);
@@ -605,7 +650,7 @@ static size_t pricing_smem(const PricingArgs& a, bool backward) {
   const int L = a.netA.L > a.netB.L ? a.netA.L : a.netB.L;
   const int tl = a.has_jump ? (backward ? Tiles<HP, NOP>::bwd_floats(L) : Tiles<HP, NOP>::fwd_floats(L))
                             : (backward ? Tiles<HP, 4>::bwd_floats(L) : Tiles<HP, 4>::fwd_floats(L));
-  return sizeof(float) * (size_t)(w + kRedFloats + (a.has_jump ? row_floats<HP>() : 0) + tl);
+  return sizeof(float) * (size_t)(w + kRedFloats + (a.has_jump ? row_floats<HP>() : 0) + tl + (jtc && backward ? 24 * kThreads : 0));
 }
 
 template <class Model, int HP, bool JUMP, bool JTC = false>
