@@ -207,6 +207,68 @@ def trajectory_case(nsteps=25):
                 **{kk: np.float64(v) for kk, v in par.items() if kk != "N"})
 
 
+def reg_trajectory_case(nsteps=300, seed=20261018):
+    """A LONG training trajectory of the reference's own SolverGlobalSumLocalReg (the headline scheme; Merton d = 1, 1000 paths per
+    step as its train() draws them - SolversJumpDiff.py:435): `nsteps` consecutive Adam steps.  The increments are INJECTED at the
+    reference's draw sites (tf.random.normal([nbSimul]) and mathModel.jumps(nbSimul), SolversJumpDiff.py:402-405) from NumPy's
+    frozen RandomState stream (tests/golden/noise_streams.py), so the fixture holds the seed, the reference's loss at every
+    step and its reported Y0 = U(0, x0) after every update - not the arrays."""
+    import noise_streams as TH
+    torch.manual_seed(0)
+    tf.random.seed(777)
+    tf.keras.initializers.GEN.manual_seed(41)
+    tf.GradientTape.LOG.clear()
+    N, B = 6, 1000
+    par = dict(T=1.0, N=N, r=0.1, muJ=0.0, sigmaJ=0.2, sigma=0.3, lam=3.0, K=0.9, x0=1.0)
+    model = PM.MertonJumpModel(par["T"], N, par["r"], par["muJ"], par["sigmaJ"], par["sigma"], par["lam"], par["K"], par["x0"], func, 30)
+    layer = 21 * np.ones((2,), dtype=np.int32)
+    netA, netB = NETP.Net(0, 1, layer, "tanh"), NETP.Net(0, 1, layer, "tanh")
+    build_net(netA, tf.zeros([1, 2]))
+    build_net(netB, tf.zeros([1, 3]))
+    lr = 3e-4                                           # mainMerton.py:20
+    solver = SJD.SolverGlobalSumLocalReg(model, netA, netB, lr)
+    theta0 = np.concatenate([flat_net(netA), flat_net(netB)]).astype(np.float32)
+    dW, J = TH.reg_trajectory_noise(seed, nsteps, N, B, model.dt, par["lam"], par["muJ"], par["sigmaJ"])
+    sq = np.float32(np.sqrt(model.dt))
+    cnt = {"g": 0, "j": 0}
+    orig_jumps, orig_normal = model.jumps, tf.random.normal
+
+    def jumps(n):
+        if n != B:
+            return orig_jumps(n)                        # the validation pass (100 paths)
+        k = cnt["j"]
+        cnt["j"] += 1
+        return torch.tensor(J[k // N, k % N])
+
+    def normal(shape, *a, **kw):
+        if list(shape) != [B]:
+            return orig_normal(shape, *a, **kw)
+        k = cnt["g"]
+        cnt["g"] += 1
+        return torch.tensor(dW[k // N, k % N] / sq)     # the reference multiplies by sqrt(dt) itself
+    model.jumps, tf.random.normal = jumps, normal
+    y0_after = []
+    orig_apply = tf.keras.optimizers.Adam.apply_gradients
+
+    def apply(self, gv):
+        orig_apply(self, gv)
+        with torch.no_grad():
+            y0_after.append(float(netA(torch.tensor([[0.0, par["x0"]]], dtype=torch.float32))[0].reshape(-1)[0]))
+    tf.keras.optimizers.Adam.apply_gradients = apply
+    try:
+        solver.train(1, 1, nsteps, 1)
+    finally:
+        tf.keras.optimizers.Adam.apply_gradients = orig_apply
+        tf.random.normal = orig_normal
+    assert cnt["g"] == nsteps * N and cnt["j"] == nsteps * N, cnt
+    losses = np.array([tf.GradientTape.LOG[k][0] for k in range(nsteps)], dtype=np.float64)
+    theta1 = np.concatenate([flat_net(netA), flat_net(netB)]).astype(np.float32)
+    return dict(kind="merton", scheme="SumLocalReg", B=B, N=N, lr=lr, nsteps=nsteps, seed=seed, theta0=theta0, theta_final=theta1,
+                losses=losses, Y0_after_step=np.array(y0_after[:nsteps], dtype=np.float32), Y0_report=np.float32(solver.listY0[0]),
+                dW_checksum=np.float64(dW.astype(np.float64).sum()), J_checksum=np.float64(J.astype(np.float64).sum()),
+                **{kk: np.float64(v) for kk, v in par.items() if kk != "N"})
+
+
 def qaver_curve():
     t = np.arange(48) / 48.0
     return (0.35 + 0.2 * np.sin(2 * np.pi * (t - 0.3)) + 0.05 * np.sin(4 * np.pi * t))[:13]    # N = 12 steps
@@ -366,6 +428,11 @@ def main():
         d = trajectory_case()
     np.savez_compressed(os.path.join(HERE, "traj", "merton_Global_25steps.npz"), **d)
     print("trajectory: merton Global", int(d["nsteps"]), "steps, loss", float(d["losses"][0]), "->", float(d["losses"][-1]),
+          "Y0", float(d["Y0_after_step"][0]), "->", float(d["Y0_after_step"][-1]))
+    with contextlib.redirect_stdout(io.StringIO()):
+        d = reg_trajectory_case()
+    np.savez_compressed(os.path.join(HERE, "traj", "merton_SumLocalReg_300steps.npz"), **d)
+    print("trajectory: merton SumLocalReg", int(d["nsteps"]), "steps, loss", float(d["losses"][0]), "->", float(d["losses"][-1]),
           "Y0", float(d["Y0_after_step"][0]), "->", float(d["Y0_after_step"][-1]))
     for scheme in ("Global", "SumLocal"):
         with contextlib.redirect_stdout(io.StringIO()):

@@ -1,0 +1,15 @@
+"""Seeded increment streams shared by tests/golden/make_golden.py (which hands them to the reference) and the tests (which hand
+them to the oracle and to the CUDA path).  No imports beyond NumPy: the generator must not depend on the oracle."""
+def reg_trajectory_noise(seed, nsteps, N, B, dt, lam, muJ, sigmaJ):
+    """Increments of the long Reg-scheme training trajectory (traj/merton_SumLocalReg_300steps.npz): drawn from NumPy's
+    frozen MT19937 RandomState stream, so the fixture carries the seed instead of the arrays.  Returns float32 (dW, J), each
+    [nsteps, N, B] - the same arrays tests/golden/make_golden.py handed to the reference at its own draw sites."""
+    import numpy as np
+    rs = np.random.RandomState(int(seed))
+    dW = np.empty((nsteps, N, B), dtype=np.float32)
+    J = np.empty((nsteps, N, B), dtype=np.float32)
+    for k in range(nsteps):
+        dW[k] = (np.sqrt(dt) * rs.standard_normal((N, B))).astype(np.float32)
+        dN = rs.poisson(lam * dt, (N, B)).astype(np.float64)
+        J[k] = (muJ * dN + sigmaJ * np.sqrt(dN) * rs.standard_normal((N, B))).astype(np.float32)
+    return dW, J

@@ -137,3 +137,4 @@ def native_mfg(ctx, params, scheme, layout, tensor_cores=False):
     mm = ModelCoupledFBSDE(**params)
     nets = [NetSpec(n.nin, n.hidden[0], n.nout, n.activation, len(n.hidden)) for n in layout.nets]
     return mm.make_solver(MFG_SCHEME_ID[scheme], nets, layout.n_y0, ctx=ctx, tensor_cores=tensor_cores)
+

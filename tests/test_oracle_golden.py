@@ -5,6 +5,7 @@
   (b) the closed-form known answers embedded in the reference."""
 import glob
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -175,6 +176,44 @@ def test_oracle_follows_the_reference_training_trajectory():
         assert abs(float(th[layout.y0_offset]) - c["Y0_after_step"][k]) <= 3e-6, (k, float(th[layout.y0_offset]), c["Y0_after_step"][k])
     solid = np.abs(c["theta_final"] - c["theta0"]) > 0.2 * n * float(c["lr"])       # entries whose gradient kept its sign
     np.testing.assert_allclose(th.numpy()[solid], c["theta_final"][solid], rtol=0, atol=0.03 * n * float(c["lr"]))
+
+
+TRAJ_REG = os.path.join(GOLD, "traj", "merton_SumLocalReg_300steps.npz")
+
+
+def reg_trajectory_inputs(c):
+    """The seeded increments of the long Reg trajectory (golden/noise_streams.py), checked against the fixture's checksums."""
+    sys.path.insert(0, GOLD)
+    import noise_streams
+    dW, J = noise_streams.reg_trajectory_noise(int(c["seed"]), int(c["nsteps"]), int(c["N"]), int(c["B"]), float(c["T"]) / int(c["N"]),
+                                               float(c["lam"]), float(c["muJ"]), float(c["sigmaJ"]))
+    assert abs(dW.astype(np.float64).sum() - c["dW_checksum"]) < 1e-9 and abs(J.astype(np.float64).sum() - c["J_checksum"]) < 1e-9
+    return dW, J
+
+
+def test_oracle_follows_the_reference_reg_trajectory():
+    """300 consecutive Adam steps of the reference's own SolverGlobalSumLocalReg (the headline scheme, 1000 paths per step) on
+    injected increments: the oracle's loss at every step and U(0, x0) after every update against the reference's."""
+    c = load_case(TRAJ_REG)
+    dW, J = reg_trajectory_inputs(c)
+    om, layout = oracle_of(c)
+    B, n = int(c["B"]), int(c["nsteps"])
+    th = torch.tensor(c["theta0"].copy())
+    opt = KerasAdam(layout.total, float(c["lr"]))
+    x0 = torch.tensor([[0.0, float(c["x0"])]], dtype=torch.float32)
+    worst_l = worst_y = 0.0
+    for k in range(n):
+        t = th.clone().requires_grad_(True)
+        nz = {"dW": torch.tensor(dW[k])[..., None], "J": torch.tensor(J[k])[..., None]}
+        loss = pricing_loss(om, "SumLocalReg", layout, t, nz, B)
+        loss.backward()
+        worst_l = max(worst_l, abs(float(loss.detach()) - c["losses"][k]) / abs(c["losses"][k]))
+        opt.step(th, t.grad)
+        y0 = float(mlp_forward(th, layout, 0, x0)[0, 0])
+        worst_y = max(worst_y, abs(y0 - float(c["Y0_after_step"][k])))
+    print(f"oracle vs reference over {n} Reg steps: worst loss rel {worst_l:.1e}, worst |Y0 - Y0_ref| {worst_y:.1e}")
+    assert worst_l <= 2e-5 and worst_y <= 5e-6
+    assert abs(float(c["Y0_after_step"][-1]) - float(c["Y0_report"])) < 1e-6
 
 
 def test_merton_closed_form_known_answers():
