@@ -207,28 +207,37 @@ def trajectory_case(nsteps=25):
                 **{kk: np.float64(v) for kk, v in par.items() if kk != "N"})
 
 
-def reg_trajectory_case(nsteps=300, seed=20261018):
-    """A LONG training trajectory of the reference's own SolverGlobalSumLocalReg (the headline scheme; Merton d = 1, 1000 paths per
-    step as its train() draws them - SolversJumpDiff.py:435): `nsteps` consecutive Adam steps.  The increments are INJECTED at the
-    reference's draw sites (tf.random.normal([nbSimul]) and mathModel.jumps(nbSimul), SolversJumpDiff.py:402-405) from NumPy's
-    frozen RandomState stream (tests/golden/noise_streams.py), so the fixture holds the seed, the reference's loss at every
-    step and its reported Y0 = U(0, x0) after every update - not the arrays."""
+def reg_trajectory_case(kind="merton", nsteps=300, seed=20261018):
+    """A LONG training trajectory of the reference's own SolverGlobalSumLocalReg (the headline scheme; d = 1, 1000 paths per step as
+    its train() draws them - SolversJumpDiff.py:435, SolversPureJump.py:403): `nsteps` consecutive Adam steps.  The increments are
+    INJECTED at the reference's draw sites (tf.random.normal([nbSimul]) and mathModel.jumps(nbSimul), SolversJumpDiff.py:402-405,
+    SolversPureJump.py:372) from NumPy's frozen RandomState stream (tests/golden/noise_streams.py), so the fixture holds the seed,
+    the reference's loss at every step and its reported Y0 = U(0, x0) after every update - not the arrays."""
     import noise_streams as TH
+    merton = kind == "merton"
     torch.manual_seed(0)
     tf.random.seed(777)
-    tf.keras.initializers.GEN.manual_seed(41)
+    tf.keras.initializers.GEN.manual_seed(41 if merton else 43)
     tf.GradientTape.LOG.clear()
-    N, B = 6, 1000
-    par = dict(T=1.0, N=N, r=0.1, muJ=0.0, sigmaJ=0.2, sigma=0.3, lam=3.0, K=0.9, x0=1.0)
-    model = PM.MertonJumpModel(par["T"], N, par["r"], par["muJ"], par["sigmaJ"], par["sigma"], par["lam"], par["K"], par["x0"], func, 30)
+    B = 1000
+    if merton:
+        N = 6
+        par = dict(T=1.0, N=N, r=0.1, muJ=0.0, sigmaJ=0.2, sigma=0.3, lam=3.0, K=0.9, x0=1.0)
+        model = PM.MertonJumpModel(par["T"], N, par["r"], par["muJ"], par["sigmaJ"], par["sigma"], par["lam"], par["K"], par["x0"], func, 30)
+        S, lr = SJD, 3e-4                               # mainMerton.py:20
+        dW, J = TH.reg_trajectory_noise(seed, nsteps, N, B, model.dt, par["lam"], par["muJ"], par["sigmaJ"])
+    else:
+        N = 5
+        par = dict(T=1.0, N=N, r=0.1, theta=-0.1, kappa=0.1, sigmaJ=0.2, K=1.0, x0=1.0)
+        model = PM.VGmodel(par["T"], N, par["r"], par["theta"], par["kappa"], par["sigmaJ"], par["K"], par["x0"], func)
+        S, lr = SPJ, 1.5e-4                             # mainVG.py:20
+        dW, J = None, TH.vg_trajectory_noise(seed + 1, nsteps, N, B, model.dt, par["theta"], par["kappa"], par["sigmaJ"])
     layer = 21 * np.ones((2,), dtype=np.int32)
     netA, netB = NETP.Net(0, 1, layer, "tanh"), NETP.Net(0, 1, layer, "tanh")
     build_net(netA, tf.zeros([1, 2]))
     build_net(netB, tf.zeros([1, 3]))
-    lr = 3e-4                                           # mainMerton.py:20
-    solver = SJD.SolverGlobalSumLocalReg(model, netA, netB, lr)
+    solver = S.SolverGlobalSumLocalReg(model, netA, netB, lr)
     theta0 = np.concatenate([flat_net(netA), flat_net(netB)]).astype(np.float32)
-    dW, J = TH.reg_trajectory_noise(seed, nsteps, N, B, model.dt, par["lam"], par["muJ"], par["sigmaJ"])
     sq = np.float32(np.sqrt(model.dt))
     cnt = {"g": 0, "j": 0}
     orig_jumps, orig_normal = model.jumps, tf.random.normal
@@ -241,7 +250,7 @@ def reg_trajectory_case(nsteps=300, seed=20261018):
         return torch.tensor(J[k // N, k % N])
 
     def normal(shape, *a, **kw):
-        if list(shape) != [B]:
+        if dW is None or list(shape) != [B]:
             return orig_normal(shape, *a, **kw)
         k = cnt["g"]
         cnt["g"] += 1
@@ -260,13 +269,15 @@ def reg_trajectory_case(nsteps=300, seed=20261018):
     finally:
         tf.keras.optimizers.Adam.apply_gradients = orig_apply
         tf.random.normal = orig_normal
-    assert cnt["g"] == nsteps * N and cnt["j"] == nsteps * N, cnt
+    assert cnt["j"] == nsteps * N and cnt["g"] == (nsteps * N if merton else 0), cnt
     losses = np.array([tf.GradientTape.LOG[k][0] for k in range(nsteps)], dtype=np.float64)
     theta1 = np.concatenate([flat_net(netA), flat_net(netB)]).astype(np.float32)
-    return dict(kind="merton", scheme="SumLocalReg", B=B, N=N, lr=lr, nsteps=nsteps, seed=seed, theta0=theta0, theta_final=theta1,
-                losses=losses, Y0_after_step=np.array(y0_after[:nsteps], dtype=np.float32), Y0_report=np.float32(solver.listY0[0]),
-                dW_checksum=np.float64(dW.astype(np.float64).sum()), J_checksum=np.float64(J.astype(np.float64).sum()),
-                **{kk: np.float64(v) for kk, v in par.items() if kk != "N"})
+    out = dict(kind=kind, scheme="SumLocalReg", B=B, N=N, lr=lr, nsteps=nsteps, seed=seed, theta0=theta0, theta_final=theta1,
+               losses=losses, Y0_after_step=np.array(y0_after[:nsteps], dtype=np.float32), Y0_report=np.float32(solver.listY0[0]),
+               J_checksum=np.float64(J.astype(np.float64).sum()), **{kk: np.float64(v) for kk, v in par.items() if kk != "N"})
+    if merton:
+        out["dW_checksum"] = np.float64(dW.astype(np.float64).sum())
+    return out
 
 
 def qaver_curve():
@@ -429,11 +440,12 @@ def main():
     np.savez_compressed(os.path.join(HERE, "traj", "merton_Global_25steps.npz"), **d)
     print("trajectory: merton Global", int(d["nsteps"]), "steps, loss", float(d["losses"][0]), "->", float(d["losses"][-1]),
           "Y0", float(d["Y0_after_step"][0]), "->", float(d["Y0_after_step"][-1]))
-    with contextlib.redirect_stdout(io.StringIO()):
-        d = reg_trajectory_case()
-    np.savez_compressed(os.path.join(HERE, "traj", "merton_SumLocalReg_300steps.npz"), **d)
-    print("trajectory: merton SumLocalReg", int(d["nsteps"]), "steps, loss", float(d["losses"][0]), "->", float(d["losses"][-1]),
-          "Y0", float(d["Y0_after_step"][0]), "->", float(d["Y0_after_step"][-1]))
+    for kind in ("merton", "vg"):
+        with contextlib.redirect_stdout(io.StringIO()):
+            d = reg_trajectory_case(kind)
+        np.savez_compressed(os.path.join(HERE, "traj", f"{kind}_SumLocalReg_300steps.npz"), **d)
+        print("trajectory:", kind, "SumLocalReg", int(d["nsteps"]), "steps, loss", float(d["losses"][0]), "->", float(d["losses"][-1]),
+              "Y0", float(d["Y0_after_step"][0]), "->", float(d["Y0_after_step"][-1]))
     for scheme in ("Global", "SumLocal"):
         with contextlib.redirect_stdout(io.StringIO()):
             d = diag_case(scheme)

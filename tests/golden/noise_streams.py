@@ -13,3 +13,15 @@ def reg_trajectory_noise(seed, nsteps, N, B, dt, lam, muJ, sigmaJ):
         dN = rs.poisson(lam * dt, (N, B)).astype(np.float64)
         J[k] = (muJ * dN + sigmaJ * np.sqrt(dN) * rs.standard_normal((N, B))).astype(np.float32)
     return dW, J
+
+
+def vg_trajectory_noise(seed, nsteps, N, B, dt, theta, kappa, sigmaJ):
+    """Variance-gamma increments of the long VG Reg trajectory (traj/vg_SumLocalReg_300steps.npz): gamma(shape dt/kappa, scale kappa)
+    subordinator steps and the Brownian part on them (pricingModels.py:188-191), float32 [nsteps, N, B], RandomState stream."""
+    import numpy as np
+    rs = np.random.RandomState(int(seed))
+    J = np.empty((nsteps, N, B), dtype=np.float32)
+    for k in range(nsteps):
+        g = rs.gamma(dt / kappa, kappa, (N, B))
+        J[k] = (theta * g + sigmaJ * np.sqrt(g) * rs.standard_normal((N, B))).astype(np.float32)
+    return J

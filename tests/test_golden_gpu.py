@@ -132,32 +132,34 @@ def test_cuda_follows_the_reference_training_trajectory(ctx, tensor_cores):
     np.testing.assert_allclose(th[solid], c["theta_final"][solid], rtol=0, atol=0.03 * n * float(c["lr"]))
 
 
+@pytest.mark.parametrize("kind", ("merton", "vg"))
 @pytest.mark.parametrize("tensor_cores", (False, True), ids=("ffma", "tcgen05"))
-def test_cuda_follows_the_reference_reg_trajectory(ctx, tensor_cores):
+def test_cuda_follows_the_reference_reg_trajectory(ctx, tensor_cores, kind):
     """300 consecutive training steps of the reference's own SolverGlobalSumLocalReg - the headline scheme, 1000 paths per step as its
     train() draws them - on injected increments (seeded stream, golden/noise_streams.py): the CUDA path's loss at every step and its
     U(0, x0) after every Keras-form Adam update against the reference's, and the final parameters."""
     from test_oracle_golden import TRAJ_REG, reg_trajectory_inputs
-    c = load_case(TRAJ_REG)
+    c = load_case(TRAJ_REG[kind])
     dW, J = reg_trajectory_inputs(c)
     B, n, N = int(c["B"]), int(c["nsteps"]), int(c["N"])
-    layout = H.pricing_layout("merton", "SumLocalReg", 1)
-    par = {k: c[k] for k in ("T", "r", "muJ", "sigmaJ", "sigma", "lam", "K", "x0")}
+    layout = H.pricing_layout(kind, "SumLocalReg", 1)
+    keys = ("T", "r", "muJ", "sigmaJ", "sigma", "lam", "K", "x0") if kind == "merton" else ("T", "r", "theta", "kappa", "sigmaJ", "K", "x0")
+    par = {k: c[k] for k in keys}
     par["N"] = N
-    s = H.native_pricing(ctx, "merton", par, "SumLocalReg", layout, d=1, M=0, tensor_cores=tensor_cores)
+    s = H.native_pricing(ctx, kind, par, "SumLocalReg", layout, d=1, M=0, tensor_cores=tensor_cores)
     s.set_theta(c["theta0"])
     s.reset_optimizer()
     x0 = np.array([[0.0, c["x0"]]], dtype=np.float32)
     worst_l = worst_y = 0.0
     for k in range(n):
-        s.set_noise(B, planes(dW[k]), planes(J[k]))
+        s.set_noise(B, None if dW is None else planes(dW[k]), planes(J[k]))
         out = s.grad(B)
         worst_l = max(worst_l, abs(out[0] - c["losses"][k]) / abs(c["losses"][k]))
         s.adam_step(float(c["lr"]))
         worst_y = max(worst_y, abs(float(s.net_forward(0, x0)[0, 0]) - float(c["Y0_after_step"][k])))
     th = s.get_theta()
     dth = float(np.abs(th - c["theta_final"]).max())
-    print(f"Reg trajectory ({'tcgen05' if tensor_cores else 'ffma'}): worst loss rel {worst_l:.1e}, worst |Y0 - Y0_ref| {worst_y:.1e}, "
+    print(f"{kind} Reg trajectory ({'tcgen05' if tensor_cores else 'ffma'}): worst loss rel {worst_l:.1e}, worst |Y0 - Y0_ref| {worst_y:.1e}, "
           f"max |theta - theta_ref| {dth:.1e} over {n} steps")
     # measured: ffma 6.7e-7 / 2.7e-7 / 8.9e-8, tcgen05 1.8e-6 / 9.8e-7 / 5.7e-7
     assert worst_l <= 1e-5 and worst_y <= 5e-6 and dth <= 5e-6

@@ -178,23 +178,29 @@ def test_oracle_follows_the_reference_training_trajectory():
     np.testing.assert_allclose(th.numpy()[solid], c["theta_final"][solid], rtol=0, atol=0.03 * n * float(c["lr"]))
 
 
-TRAJ_REG = os.path.join(GOLD, "traj", "merton_SumLocalReg_300steps.npz")
+TRAJ_REG = {k: os.path.join(GOLD, "traj", f"{k}_SumLocalReg_300steps.npz") for k in ("merton", "vg")}
 
 
 def reg_trajectory_inputs(c):
-    """The seeded increments of the long Reg trajectory (golden/noise_streams.py), checked against the fixture's checksums."""
+    """The seeded increments of a long Reg trajectory (golden/noise_streams.py), checked against the fixture's checksums:
+    (dW or None, J), float32 [nsteps, N, B]."""
     sys.path.insert(0, GOLD)
     import noise_streams
-    dW, J = noise_streams.reg_trajectory_noise(int(c["seed"]), int(c["nsteps"]), int(c["N"]), int(c["B"]), float(c["T"]) / int(c["N"]),
-                                               float(c["lam"]), float(c["muJ"]), float(c["sigmaJ"]))
-    assert abs(dW.astype(np.float64).sum() - c["dW_checksum"]) < 1e-9 and abs(J.astype(np.float64).sum() - c["J_checksum"]) < 1e-9
+    n, N, B, dt = int(c["nsteps"]), int(c["N"]), int(c["B"]), float(c["T"]) / int(c["N"])
+    if str(c["kind"]) == "merton":
+        dW, J = noise_streams.reg_trajectory_noise(int(c["seed"]), n, N, B, dt, float(c["lam"]), float(c["muJ"]), float(c["sigmaJ"]))
+        assert abs(dW.astype(np.float64).sum() - c["dW_checksum"]) < 1e-9
+    else:
+        dW, J = None, noise_streams.vg_trajectory_noise(int(c["seed"]) + 1, n, N, B, dt, float(c["theta"]), float(c["kappa"]), float(c["sigmaJ"]))
+    assert abs(J.astype(np.float64).sum() - c["J_checksum"]) < 1e-9
     return dW, J
 
 
-def test_oracle_follows_the_reference_reg_trajectory():
+@pytest.mark.parametrize("kind", ("merton", "vg"))
+def test_oracle_follows_the_reference_reg_trajectory(kind):
     """300 consecutive Adam steps of the reference's own SolverGlobalSumLocalReg (the headline scheme, 1000 paths per step) on
     injected increments: the oracle's loss at every step and U(0, x0) after every update against the reference's."""
-    c = load_case(TRAJ_REG)
+    c = load_case(TRAJ_REG[kind])
     dW, J = reg_trajectory_inputs(c)
     om, layout = oracle_of(c)
     B, n = int(c["B"]), int(c["nsteps"])
@@ -204,14 +210,16 @@ def test_oracle_follows_the_reference_reg_trajectory():
     worst_l = worst_y = 0.0
     for k in range(n):
         t = th.clone().requires_grad_(True)
-        nz = {"dW": torch.tensor(dW[k])[..., None], "J": torch.tensor(J[k])[..., None]}
+        nz = {"J": torch.tensor(J[k])[..., None]}
+        if dW is not None:
+            nz["dW"] = torch.tensor(dW[k])[..., None]
         loss = pricing_loss(om, "SumLocalReg", layout, t, nz, B)
         loss.backward()
         worst_l = max(worst_l, abs(float(loss.detach()) - c["losses"][k]) / abs(c["losses"][k]))
         opt.step(th, t.grad)
         y0 = float(mlp_forward(th, layout, 0, x0)[0, 0])
         worst_y = max(worst_y, abs(y0 - float(c["Y0_after_step"][k])))
-    print(f"oracle vs reference over {n} Reg steps: worst loss rel {worst_l:.1e}, worst |Y0 - Y0_ref| {worst_y:.1e}")
+    print(f"oracle vs reference over {n} {kind} Reg steps: worst loss rel {worst_l:.1e}, worst |Y0 - Y0_ref| {worst_y:.1e}")
     assert worst_l <= 2e-5 and worst_y <= 5e-6
     assert abs(float(c["Y0_after_step"][-1]) - float(c["Y0_report"])) < 1e-6
 
