@@ -366,6 +366,66 @@ def mfg_case(scheme, couplage="ON"):
                 dN=torch.stack(dNs[:N], 0).numpy(), **{k: np.float64(v) for k, v in par.items()})
 
 
+def mfg_trajectory_case(scheme="Global", nsteps=200):
+    """A LONG training trajectory of the reference's own MFG SolverGlobalFBSDE (couplage ON, stochastic jumps): `nsteps` consecutive
+    Adam steps over both networks and the two trainable initial values.  The increments the reference drew are recorded at its
+    call sites (the Cox jump counts depend on the state, so they cannot be pre-drawn); per step the fixture holds the reference's
+    loss and (Y0_hat, Y0) after the update."""
+    tf.random.seed(3100)
+    tf.keras.initializers.GEN.manual_seed(29)
+    tf.GradientTape.LOG.clear()
+    Q = qaver_curve()
+    par = dict(T=0.25, R0=0.24, jumpFactor=8.0, alpha=30.0, beta=float(np.exp(-15.0)), coeffOU=5.0, A=150.0, K=50.0, pi=0.1,
+               p0=6.159423723, p1=87.4286117, f0=0.0, f1=1e4, theta=0.12, C=80.0, S0=0.0, h1=0.0, h2=600.0, sig0=0.1, sig=0.3,
+               alphaTarget=-0.2, coeffEqui=1.0)
+    Qt = torch.tensor(Q, dtype=torch.float32)
+    MFGM.QAver = Qt
+    model = MFGM.ModelCoupledFBSDE(par["T"], Qt, par["R0"], par["jumpFactor"], par["alpha"], par["beta"], par["coeffOU"], par["A"],
+                                   par["K"], par["pi"], par["p0"], par["p1"], par["f0"], par["f1"], par["theta"], par["C"], par["S0"],
+                                   par["h1"], par["h2"], par["sig0"], par["sig"], par["alphaTarget"], "stochastic", par["coeffEqui"])
+    km = NETM.kerasModels(NETM.Net_hat, NETM.Net, "Global", 2, 3, 20 * np.ones((2,), dtype=np.int32), 22 * np.ones((2,), dtype=np.int32),
+                          "tanh", "tanh")
+    model.init(1)
+    build_net(km.model_hat, model.getProjectedStates())
+    build_net(km.model, model.getAllStates())
+    B, lr = 16, 1e-3                                    # mainMFGComparison.py:24
+    solver = MFGS.SolverGlobalFBSDE(model, km, lr, "ON")
+
+    def theta():
+        return np.concatenate([flat_net(km.model_hat), flat_net(km.model),
+                               np.array([km.model_hat.Y0_hat.detach().numpy(), km.model.Y0.detach().numpy()], dtype=np.float32)]).astype(np.float32)
+    theta0 = theta()
+    gauss, dNs, y0s = [], [], []
+    orig_normal, orig_dN, orig_apply = tf.random.normal, model.dN, tf.keras.optimizers.Adam.apply_gradients
+
+    def normal(shape, *a, **k):
+        x = orig_normal(shape, *a, **k)
+        gauss.append(x.detach().clone())
+        return x
+
+    def dN():
+        n, c = orig_dN()
+        dNs.append(n.detach().clone())
+        return n, c
+
+    def apply(self, gv):
+        orig_apply(self, gv)
+        y0s.append([float(km.model_hat.Y0_hat.detach()), float(km.model.Y0.detach())])
+    tf.random.normal, model.dN, tf.keras.optimizers.Adam.apply_gradients = normal, dN, apply
+    try:
+        solver.train(B, 1, nsteps, 1)
+    finally:
+        tf.random.normal, tf.keras.optimizers.Adam.apply_gradients = orig_normal, orig_apply
+    N, sq = model.N, np.float32(np.sqrt(model.dt))
+    k = nsteps * N
+    losses = np.array([tf.GradientTape.LOG[i][0] for i in range(nsteps)], dtype=np.float64)
+    return dict(kind="mfg", scheme=scheme, B=B, N=N, lr=lr, nsteps=nsteps, QAver=Q, theta0=theta0, theta_final=theta(), losses=losses,
+                Y0_after_step=np.array(y0s[:nsteps], dtype=np.float32),
+                dW0=(sq * torch.stack(gauss[0:2 * k:2], 0)).numpy().reshape(nsteps, N, B),
+                dW=(sq * torch.stack(gauss[1:2 * k:2], 0)).numpy().reshape(nsteps, N, B),
+                dN=torch.stack(dNs[:k], 0).numpy().reshape(nsteps, N, B), **{kk: np.float64(v) for kk, v in par.items()})
+
+
 def diag_case(scheme, nb=48):
     """The reference's own MFG diagnostics (MFGSolvers.py:118-178, 436-459) on fresh networks: simulateGlobalErr and followS, with
     the increments they drew."""
@@ -446,6 +506,11 @@ def main():
         np.savez_compressed(os.path.join(HERE, "traj", f"{kind}_SumLocalReg_300steps.npz"), **d)
         print("trajectory:", kind, "SumLocalReg", int(d["nsteps"]), "steps, loss", float(d["losses"][0]), "->", float(d["losses"][-1]),
               "Y0", float(d["Y0_after_step"][0]), "->", float(d["Y0_after_step"][-1]))
+    with contextlib.redirect_stdout(io.StringIO()):
+        d = mfg_trajectory_case()
+    np.savez_compressed(os.path.join(HERE, "traj", "mfg_Global_200steps.npz"), **d)
+    print("trajectory: mfg Global", int(d["nsteps"]), "steps, loss", float(d["losses"][0]), "->", float(d["losses"][-1]),
+          "Y0_hat, Y0", d["Y0_after_step"][0], "->", d["Y0_after_step"][-1])
     for scheme in ("Global", "SumLocal"):
         with contextlib.redirect_stdout(io.StringIO()):
             d = diag_case(scheme)

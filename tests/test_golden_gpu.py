@@ -165,6 +165,35 @@ def test_cuda_follows_the_reference_reg_trajectory(ctx, tensor_cores, kind):
     assert worst_l <= 1e-5 and worst_y <= 5e-6 and dth <= 5e-6
 
 
+@pytest.mark.parametrize("tensor_cores", (False, True), ids=("ffma", "tcgen05"))
+def test_cuda_follows_the_reference_mfg_trajectory(ctx, tensor_cores):
+    """200 consecutive training steps of the reference's own MFG SolverGlobalFBSDE (couplage ON; Net_hat, Net and both trainable
+    initial values in one Adam update) on the increments it drew: loss at every step, (Y0_hat, Y0) after every update, and the
+    final parameters."""
+    from test_oracle_golden import TRAJ_MFG
+    c = load_case(TRAJ_MFG)
+    B, n = int(c["B"]), int(c["nsteps"])
+    layout = H.mfg_layout("Global")
+    s = H.native_mfg(ctx, dict(QAver=c["QAver"], jumpModel="stochastic", **{k: c[k] for k in MFG_KEYS}), "Global", layout,
+                     tensor_cores=tensor_cores)
+    s.set_theta(c["theta0"])
+    s.reset_optimizer()
+    worst_l = worst_y = 0.0
+    for k in range(n):
+        s.set_noise(B, c["dW0"][k], c["dW"][k], c["dN"][k])
+        out = s.grad(B)
+        worst_l = max(worst_l, abs(out[0] - c["losses"][k]) / abs(c["losses"][k]))
+        s.adam_step(float(c["lr"]))
+        y = s.get_theta()[layout.y0_offset:layout.y0_offset + 2]
+        worst_y = max(worst_y, float(np.abs(y - c["Y0_after_step"][k]).max()))
+    th = s.get_theta()
+    dth = float(np.abs(th - c["theta_final"]).max())
+    print(f"MFG trajectory ({'tcgen05' if tensor_cores else 'ffma'}): worst loss rel {worst_l:.1e}, worst |Y0 - Y0_ref| {worst_y:.1e}, "
+          f"max |theta - theta_ref| {dth:.1e} over {n} steps")
+    # measured: ffma 2.1e-7 / 1.2e-7 / 2.4e-7, tcgen05 2.2e-7 / 1.2e-7 / 6.5e-6
+    assert worst_l <= 5e-6 and worst_y <= 2e-6 and dth <= 3e-5
+
+
 DIAG_CASES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "diag", "*.npz")))
 
 

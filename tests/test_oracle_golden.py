@@ -224,6 +224,32 @@ def test_oracle_follows_the_reference_reg_trajectory(kind):
     assert abs(float(c["Y0_after_step"][-1]) - float(c["Y0_report"])) < 1e-6
 
 
+TRAJ_MFG = os.path.join(GOLD, "traj", "mfg_Global_200steps.npz")
+
+
+def test_oracle_follows_the_reference_mfg_trajectory():
+    """200 consecutive Adam steps of the reference's own MFG SolverGlobalFBSDE (couplage ON, both networks and both initial values
+    trained together) on the increments it drew: the oracle's loss at every step and (Y0_hat, Y0) after every update."""
+    c = load_case(TRAJ_MFG)
+    om, layout = oracle_of(c)
+    B, n = int(c["B"]), int(c["nsteps"])
+    th = torch.tensor(c["theta0"].copy())
+    opt = KerasAdam(layout.total, float(c["lr"]))
+    worst_l = worst_y = 0.0
+    for k in range(n):
+        t = th.clone().requires_grad_(True)
+        nz = {key: torch.tensor(c[key][k]) for key in ("dW0", "dW", "dN")}
+        lh, li = mfg_loss(om, "Global", layout, t, nz, B)
+        loss = lh + li
+        loss.backward()
+        worst_l = max(worst_l, abs(float(loss.detach()) - c["losses"][k]) / abs(c["losses"][k]))
+        opt.step(th, t.grad)
+        y = th[layout.y0_offset:layout.y0_offset + 2].numpy()
+        worst_y = max(worst_y, float(np.abs(y - c["Y0_after_step"][k]).max()))
+    print(f"oracle vs reference over {n} MFG Global steps: worst loss rel {worst_l:.1e}, worst |Y0 - Y0_ref| {worst_y:.1e}")
+    assert worst_l <= 1e-5 and worst_y <= 5e-6
+
+
 def test_merton_closed_form_known_answers():
     om = MertonOracle(aLin=0.1, limit=30, d=1, dtype=torch.float64, **H.MERTON)
     assert abs(float(om.A(0, om.init(1))[0]) - 0.2714569268) < 1e-9
