@@ -216,28 +216,6 @@ struct MertonModel {
       }
     }
   }
-  // the same, from the two partial products pa * pb = prod_k X_k held by the two threads of a path (reg_forward_tc)
-  __device__ static __forceinline__ void eval_A_begin_prod(const PricingArgs& a, int i, float pa, float pb, AEval& e) {
-    if (D == 1) {
-      e.k = __logf(pa / a.K);
-      e.Ge = pa;
-    } else {
-      e.k = (__logf(pa) + __logf(pb)) * (1.0f / D) + __logf(a.qdisc[i] / a.K);
-      e.Ge = a.K * __expf(e.k);
-    }
-    e.tab = false;
-    if (a.use_atab) {
-      e.m = __ldg(a.atab_meta + i);
-      const float u = (e.k - e.m.x) * e.m.y;
-      if (u >= 0.0f && u < e.m.w) {
-        const int j = (int)u;
-        e.t = u - (float)j;
-        const float4* __restrict__ nd = a.atab + a.atab_off[i] + j;
-        e.p0 = __ldg(nd); e.p1 = __ldg(nd + 1);
-        e.tab = true;
-      }
-    }
-  }
   __device__ static __forceinline__ void eval_A_finish(const PricingArgs& a, int i, const AEval& e, float& A, float& dAb) {
     float sD = 0.0f, sK = 0.0f;
     if (e.tab) {
@@ -319,10 +297,6 @@ struct VGModel {
   __device__ static __forceinline__ float dA_k(float dAb, float) { return dAb; }
   struct AEval { float A, dAb; };
   __device__ static __forceinline__ void eval_A_begin(const PricingArgs& a, int i, const float (&X)[1], AEval& e) {
-    eval_A(a, i, X, e.A, e.dAb);
-  }
-  __device__ static __forceinline__ void eval_A_begin_prod(const PricingArgs& a, int i, float pa, float, AEval& e) {
-    const float X[1] = {pa};
     eval_A(a, i, X, e.A, e.dAb);
   }
   __device__ static __forceinline__ void eval_A_finish(const PricingArgs&, int, const AEval& e, float& A, float& dAb) {

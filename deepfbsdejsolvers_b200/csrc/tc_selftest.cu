@@ -20,11 +20,10 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const float* __restric
   float* q_lo = q_hi + 3072;
   float* b_hi = q_lo + 3072;        // [6 chunks][32 n][4]
   float* b_lo = b_hi + 768;
-  float* pad = b_lo + 768;          // >= 64 KB of slack follows (dynamic smem size chosen by the launcher)
+  // (>= 64 KB of slack follows b_lo: dynamic smem size chosen by the launcher)
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base;
   const int r = threadIdx.x, warp = r >> 5;
-  (void)pad;
   if (warp == 0) tc::tmem_alloc(&tmem_base, 64);
   if (r == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
   tc::tc_fence_before();

@@ -280,6 +280,80 @@ def reg_trajectory_case(kind="merton", nsteps=300, seed=20261018):
     return out
 
 
+def jump_trajectory_case(kind="merton", nsteps=100, seed=20261019):
+    """A long training trajectory of the reference's own SolverGlobalFBSDE at the DEFAULT shapes of mainMerton.py / mainVG.py
+    (10 paths, N = 50 / 30 time steps, 5000 compensator samples redrawn at every time step, lr 4e-4 / 5e-4): `nsteps` consecutive
+    Adam steps on increments injected at the reference's draw sites (SolversJumpDiff.py:30-34, SolversPureJump.py:31-32) from the
+    frozen RandomState stream; the fixture holds the seed, the reference's losses and its trainable Y0 after every update."""
+    import noise_streams as TH
+    merton = kind == "merton"
+    torch.manual_seed(0)
+    tf.random.seed(555)
+    tf.keras.initializers.GEN.manual_seed(53 if merton else 59)
+    tf.GradientTape.LOG.clear()
+    B = 10
+    if merton:
+        N = 50
+        par = dict(T=1.0, N=N, r=0.1, muJ=0.0, sigmaJ=0.2, sigma=0.3, lam=3.0, K=0.9, x0=1.0)
+        model = PM.MertonJumpModel(par["T"], N, par["r"], par["muJ"], par["sigmaJ"], par["sigma"], par["lam"], par["K"], par["x0"], func, 30)
+        S, lr, y0_on = SJD, 4e-4, "UZ"                  # mainMerton.py:18
+    else:
+        N = 30
+        par = dict(T=1.0, N=N, r=0.1, theta=-0.1, kappa=0.1, sigmaJ=0.2, K=1.0, x0=1.0)
+        model = PM.VGmodel(par["T"], N, par["r"], par["theta"], par["kappa"], par["sigmaJ"], par["K"], par["x0"], func)
+        S, lr, y0_on = SPJ, 5e-4, "Gam"                 # mainVG.py:18
+    dW, J, JMC = TH.jump_trajectory_noise(kind, seed, nsteps, N, B, MCOMP, model.dt, par)
+    layer = 21 * np.ones((2,), dtype=np.int32)
+    netA = NETP.Net(1 if y0_on == "UZ" else 0, 1, layer, "tanh")
+    netB = NETP.Net(1 if y0_on == "Gam" else 0, 1, layer, "tanh")
+    build_net(netA, tf.zeros([1, 2]))
+    build_net(netB, tf.zeros([1, 3]))
+    holder = netA if y0_on == "UZ" else netB
+    solver = S.SolverGlobalFBSDE(model, netA, netB, lr)
+
+    def theta():
+        return np.concatenate([flat_net(netA), flat_net(netB), np.array([holder.Y0.detach().numpy()], dtype=np.float32)]).astype(np.float32)
+    theta0 = theta()
+    sq = np.float32(np.sqrt(model.dt))
+    cnt = {"g": 0, "j": 0, "m": 0}
+    tot = nsteps * N
+    orig_jumps, orig_normal, orig_apply = model.jumps, tf.random.normal, tf.keras.optimizers.Adam.apply_gradients
+
+    def jumps(n):
+        key, arr = ("j", J) if n == B else ("m", JMC)
+        k = cnt[key]
+        if (n != B and n != MCOMP) or k >= tot:
+            return orig_jumps(n)                        # the validation pass
+        cnt[key] += 1
+        return torch.tensor(arr[k // N, k % N])
+
+    def normal(shape, *a, **kw):
+        if dW is None or list(shape) != [B] or cnt["g"] >= tot:
+            return orig_normal(shape, *a, **kw)
+        k = cnt["g"]
+        cnt["g"] += 1
+        return torch.tensor(dW[k // N, k % N] / sq)
+    y0_after = []
+
+    def apply(self, gv):
+        orig_apply(self, gv)
+        y0_after.append(float(holder.Y0.detach()))
+    model.jumps, tf.random.normal, tf.keras.optimizers.Adam.apply_gradients = jumps, normal, apply
+    try:
+        solver.train(B, 1, nsteps, 1)
+    finally:
+        tf.random.normal, tf.keras.optimizers.Adam.apply_gradients = orig_normal, orig_apply
+    assert cnt["j"] == tot and cnt["m"] == tot and cnt["g"] == (tot if merton else 0), cnt
+    losses = np.array([tf.GradientTape.LOG[k][0] for k in range(nsteps)], dtype=np.float64)
+    out = dict(kind=kind, scheme="Global", B=B, N=N, M=MCOMP, lr=lr, nsteps=nsteps, seed=seed, theta0=theta0, theta_final=theta(),
+               losses=losses, Y0_after_step=np.array(y0_after[:nsteps], dtype=np.float32),
+               J_checksum=np.float64(J.astype(np.float64).sum()), JMC_checksum=np.float64(JMC.astype(np.float64).sum()),
+               **{kk: np.float64(v) for kk, v in par.items() if kk != "N"})
+    if merton:
+        out["dW_checksum"] = np.float64(dW.astype(np.float64).sum())
+    return out
+
+
 def qaver_curve():
     t = np.arange(48) / 48.0
     return (0.35 + 0.2 * np.sin(2 * np.pi * (t - 0.3)) + 0.05 * np.sin(4 * np.pi * t))[:13]    # N = 12 steps
@@ -506,6 +580,12 @@ def main():
         np.savez_compressed(os.path.join(HERE, "traj", f"{kind}_SumLocalReg_300steps.npz"), **d)
         print("trajectory:", kind, "SumLocalReg", int(d["nsteps"]), "steps, loss", float(d["losses"][0]), "->", float(d["losses"][-1]),
               "Y0", float(d["Y0_after_step"][0]), "->", float(d["Y0_after_step"][-1]))
+    for kind in ("merton", "vg"):
+        with contextlib.redirect_stdout(io.StringIO()):
+            d = jump_trajectory_case(kind)
+        np.savez_compressed(os.path.join(HERE, "traj", f"{kind}_Global_defaults_100steps.npz"), **d)
+        print("trajectory:", kind, "Global at the reference's default shapes,", int(d["nsteps"]), "steps, loss", float(d["losses"][0]), "->",
+              float(d["losses"][-1]), "Y0", float(d["Y0_after_step"][0]), "->", float(d["Y0_after_step"][-1]))
     with contextlib.redirect_stdout(io.StringIO()):
         d = mfg_trajectory_case()
     np.savez_compressed(os.path.join(HERE, "traj", "mfg_Global_200steps.npz"), **d)

@@ -25,3 +25,28 @@ def vg_trajectory_noise(seed, nsteps, N, B, dt, theta, kappa, sigmaJ):
         g = rs.gamma(dt / kappa, kappa, (N, B))
         J[k] = (theta * g + sigmaJ * np.sqrt(g) * rs.standard_normal((N, B))).astype(np.float32)
     return J
+
+
+def jump_trajectory_noise(kind, seed, nsteps, N, B, M, dt, par):
+    """Increments of the long jump-scheme trajectories (traj/*_Global_defaults_*steps.npz; the reference's default shapes: B paths,
+    M = 5000 compensator samples redrawn at every time step): float32 (dW or None [nsteps, N, B], J [nsteps, N, B],
+    JMC [nsteps, N, M]) from the frozen RandomState stream, drawn step by step in the order dW, J, JMC."""
+    import numpy as np
+    rs = np.random.RandomState(int(seed))
+    merton = kind == "merton"
+    dW = np.empty((nsteps, N, B), dtype=np.float32) if merton else None
+    J = np.empty((nsteps, N, B), dtype=np.float32)
+    JMC = np.empty((nsteps, N, M), dtype=np.float32)
+
+    def jumps(shape):
+        if merton:
+            dN = rs.poisson(par["lam"] * dt, shape).astype(np.float64)
+            return (par["muJ"] * dN + par["sigmaJ"] * np.sqrt(dN) * rs.standard_normal(shape)).astype(np.float32)
+        g = rs.gamma(dt / par["kappa"], par["kappa"], shape)
+        return (par["theta"] * g + par["sigmaJ"] * np.sqrt(g) * rs.standard_normal(shape)).astype(np.float32)
+    for k in range(nsteps):
+        if merton:
+            dW[k] = (np.sqrt(dt) * rs.standard_normal((N, B))).astype(np.float32)
+        J[k] = jumps((N, B))
+        JMC[k] = jumps((N, M))
+    return dW, J, JMC

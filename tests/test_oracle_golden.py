@@ -250,6 +250,49 @@ def test_oracle_follows_the_reference_mfg_trajectory():
     assert worst_l <= 1e-5 and worst_y <= 5e-6
 
 
+TRAJ_JUMP = {k: os.path.join(GOLD, "traj", f"{k}_Global_defaults_100steps.npz") for k in ("merton", "vg")}
+
+
+def jump_trajectory_inputs(c):
+    """The seeded increments of a default-shape Global trajectory (golden/noise_streams.py), checked against the fixture's checksums."""
+    sys.path.insert(0, GOLD)
+    import noise_streams
+    kind = str(c["kind"])
+    keys = ("lam", "muJ", "sigmaJ") if kind == "merton" else ("theta", "kappa", "sigmaJ")
+    dW, J, JMC = noise_streams.jump_trajectory_noise(kind, int(c["seed"]), int(c["nsteps"]), int(c["N"]), int(c["B"]), int(c["M"]),
+                                                     float(c["T"]) / int(c["N"]), {k: float(c[k]) for k in keys})
+    assert abs(J.astype(np.float64).sum() - c["J_checksum"]) < 1e-9 and abs(JMC.astype(np.float64).sum() - c["JMC_checksum"]) < 1e-6
+    if dW is not None:
+        assert abs(dW.astype(np.float64).sum() - c["dW_checksum"]) < 1e-9
+    return dW, J, JMC
+
+
+@pytest.mark.parametrize("kind", ("merton", "vg"))
+def test_oracle_follows_the_reference_default_shape_trajectory(kind):
+    """The first 25 of 100 consecutive Adam steps of the reference's own SolverGlobalFBSDE at the default shapes of mainMerton.py /
+    mainVG.py (10 paths, N = 50 / 30, 5000 compensator samples per time step): loss at every step and the trainable Y0 after every
+    update.  (The GPU test follows all 100 steps.)"""
+    c = load_case(TRAJ_JUMP[kind])
+    dW, J, JMC = jump_trajectory_inputs(c)
+    om, layout = oracle_of(c)
+    B, n = int(c["B"]), 25
+    th = torch.tensor(c["theta0"].copy())
+    opt = KerasAdam(layout.total, float(c["lr"]))
+    worst_l = worst_y = 0.0
+    for k in range(n):
+        t = th.clone().requires_grad_(True)
+        nz = {"J": torch.tensor(J[k])[..., None], "JMC": torch.tensor(JMC[k])[..., None]}
+        if dW is not None:
+            nz["dW"] = torch.tensor(dW[k])[..., None]
+        loss = pricing_loss(om, "Global", layout, t, nz, B)
+        loss.backward()
+        worst_l = max(worst_l, abs(float(loss.detach()) - c["losses"][k]) / abs(c["losses"][k]))
+        opt.step(th, t.grad)
+        worst_y = max(worst_y, abs(float(th[layout.y0_offset]) - float(c["Y0_after_step"][k])))
+    print(f"oracle vs reference over {n} {kind} Global steps at the default shapes: worst loss rel {worst_l:.1e}, worst |Y0 - Y0_ref| {worst_y:.1e}")
+    assert worst_l <= 3e-5 and worst_y <= 5e-6
+
+
 def test_merton_closed_form_known_answers():
     om = MertonOracle(aLin=0.1, limit=30, d=1, dtype=torch.float64, **H.MERTON)
     assert abs(float(om.A(0, om.init(1))[0]) - 0.2714569268) < 1e-9
