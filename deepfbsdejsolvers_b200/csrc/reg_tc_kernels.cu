@@ -97,7 +97,8 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
   if (row < H) { w0 = a.theta[a.netA.ext_off + row]; b1v = a.theta[a.netA.ext_off + nin * H + row]; }
   const int bias_idx = ((nin >> 3) * 2 * NB + row) * 8 + (nin & 7);   // hi copy; the lo copy is NB n-rows further
   const uint32_t sbase = tc::smem_u32(u4);
-  auto sa = [&](int off_u4) { return sbase + (uint32_t)off_u4 * 16u; };
+  const uint32_t sbase16 = sbase >> 4;                  // operand addresses in units of 16 bytes (tc::smem_desc16)
+  auto sa = [&](int off_u4) { return sbase16 + (uint32_t)off_u4; };
   uint32_t phase_f = 0, phase_w = 1, phase_g = 0, pending_w = 0, started = 0;
   auto wait_f = [&]() { tc::mbar_wait(bar_f, phase_f); phase_f ^= 1; tc::tc_fence_after(); };
 
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
       if (warp == 0 && issuer) {
         tc::tc_fence_after();
 #if FBSDEJ_ABLATE != 12
-        gemm_k<1, NB>(tmem + C_ACC, sa(XA_HI), sa(XA_LO), sa(W1B));
+        gemm_k16<1, NB>(tmem + C_ACC, sa(XA_HI), sa(XA_LO), sa(W1B));
 #endif
         tc::mma_commit(bar_f);
       }
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
       if (warp == 1 && issuer) {
         tc::tc_fence_after();
 #if FBSDEJ_ABLATE != 12
-        gemm_k<2, NB>(tmem + C_ACC, sa(H1_HI), sa(H1_LO), sa(W2B));
+        gemm_k16<2, NB>(tmem + C_ACC, sa(H1_HI), sa(H1_LO), sa(W2B));
 #endif
         tc::mma_commit(bar_f);
       }
@@ -249,11 +250,11 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
         // the input-gradient GEMM first: its result is on the step's critical chain, the weight-gradient GEMM is not (the
         // tensor pipe is in order); the weight-gradient GEMM gets its own barrier because D1 overwrites tiles it reads
 #if FBSDEJ_ABLATE != 12
-        gemm_k<2, NB>(tmem + C_ACC, sa(D2_HI), sa(D2_LO), sa(WTB));
+        gemm_k16<2, NB>(tmem + C_ACC, sa(D2_HI), sa(D2_LO), sa(WTB));
 #endif
         tc::mma_commit(bar_f);
 #if FBSDEJ_ABLATE != 11
-        gemm_rows_stacked<48>(tmem + C_W2, sa(H1_HI), sa(D2_HI), started ? 1u : 0u);   // [H1 | H2 (hi) | H1 | H2 (lo)]^T [D2 hi | lo]
+        gemm_rows_stacked16<48>(tmem + C_W2, sa(H1_HI), sa(D2_HI), started ? 1u : 0u);   // [H1 | H2 (hi) | H1 | H2 (lo)]^T [D2 hi | lo]
 #endif
         tc::mma_commit(bar_g);
       }
@@ -278,11 +279,11 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
       if (warp == 3 && issuer) {
         tc::tc_fence_after();
 #if FBSDEJ_ABLATE != 12
-        gemm_k<2, 16>(tmem + C_ACC, sa(D1_HI), sa(D1_LO), sa(W1T));
+        gemm_k16<2, 16>(tmem + C_ACC, sa(D1_HI), sa(D1_LO), sa(W1T));
 #endif
         tc::mma_commit(bar_f);
 #if FBSDEJ_ABLATE != 11
-        gemm_rows_stacked<32, 64>(tmem + C_W1, sa(D1_HI), sa(XA_HI), started ? 1u : 0u);   // [D1 hi | D1 lo]^T [X hi | X lo] = dW1^T (M = 64)
+        gemm_rows_stacked16<32, 64>(tmem + C_W1, sa(D1_HI), sa(XA_HI), started ? 1u : 0u);   // [D1 hi | D1 lo]^T [X hi | X lo] = dW1^T (M = 64)
 #endif
         tc::mma_commit(bar_w);
       }
@@ -557,7 +558,8 @@ __global__ void __launch_bounds__(2 * kThreads, 4) reg_forward_tc(const PricingA
   const uint32_t tmem = tslot[0], tmem_a = tslot[1];
   const uint32_t lane_base = tmem + ((uint32_t)(row & ~31) << 16), lane_a = tmem_a + ((uint32_t)(row & ~31) << 16);
   const uint32_t sbase = tc::smem_u32(smem);
-  auto sa = [&](int off_f) { return sbase + (uint32_t)off_f * 4u; };
+  const uint32_t sbase16 = sbase >> 4;                  // operand addresses in units of 16 bytes (tc::smem_desc16)
+  auto sa = [&](int off_f) { return sbase16 + (uint32_t)(off_f >> 2); };
   uint32_t phase = 1;
   auto wait_mma = [&]() { tc::mbar_wait(bar, phase); phase ^= 1; tc::tc_fence_after(); };
   const int bias_idx = ((nin >> 2) * NB + row) * 4 + (nin & 3);   // W1B[n = row][k = nin]
@@ -598,7 +600,7 @@ __global__ void __launch_bounds__(2 * kThreads, 4) reg_forward_tc(const PricingA
       if (warp == 0 && issuer) {
         tc::tc_fence_after();
 #if FBSDEJ_ABLATE != 4
-        gemm_k_tf32<2>(tmem, tmem_a, sa(W1B_HI), sa(W1B_LO));
+        gemm_k_tf32_16<2>(tmem, tmem_a, sa(W1B_HI), sa(W1B_LO));
 #endif
         tc::mma_commit(bar);
       }
@@ -628,7 +630,7 @@ __global__ void __launch_bounds__(2 * kThreads, 4) reg_forward_tc(const PricingA
       if (warp == 1 && issuer) {
         tc::tc_fence_after();
 #if FBSDEJ_ABLATE != 4
-        gemm_k_tf32<3>(tmem, tmem_a, sa(W2B_HI), sa(W2B_LO));
+        gemm_k_tf32_16<3>(tmem, tmem_a, sa(W2B_HI), sa(W2B_LO));
 #endif
         tc::mma_commit(bar);
       }

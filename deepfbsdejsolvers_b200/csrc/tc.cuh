@@ -77,6 +77,14 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
   const uint32_t hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14);
   return ((uint64_t)hi << 32) | lo;
 }
+// The same descriptor from the operand's shared-memory address IN UNITS OF 16 BYTES (addr16 = address >> 4 < 2^14): with addr16 =
+// (loop-invariant base >> 4) + compile-time offset the low word is ONE add and the high word a constant - the byte-address form
+// above costs a shift, a mask and an or per descriptor, twice per MMA, on the issuing thread's critical path.
+__device__ __forceinline__ uint64_t smem_desc16(uint32_t addr16, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  const uint32_t lo = addr16 + (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+  const uint32_t hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14);
+  return ((uint64_t)hi << 32) | lo;
+}
 // 32-bit instruction descriptor, kind::tf32, fp32 accumulate.  a_mn / b_mn: operand is MN-major.
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, bool a_mn, bool b_mn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |

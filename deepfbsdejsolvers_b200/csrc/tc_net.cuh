@@ -37,6 +37,19 @@ __device__ __forceinline__ void gemm_k(uint32_t tmem_d, uint32_t a_hi, uint32_t 
     tc::mma_bf16(tmem_d, tc::smem_desc(a_lo + s * 4096, 2048, 128), db, id2, 1u);
   }
 }
+// (addresses in units of 16 bytes: tc::smem_desc16)
+template <int KS, int NH, bool FULL = false>
+__device__ __forceinline__ void gemm_k16(uint32_t tmem_d, uint32_t a_hi16, uint32_t a_lo16, uint32_t b16) {
+  constexpr uint32_t id1 = tc::idesc_bf16(128, 2 * NH, false, false),
+                     id2 = tc::idesc_bf16(128, FULL ? 2 * NH : (NH + 15) / 16 * 16, false, false);
+  constexpr uint32_t chunk = 2 * NH * 16;
+#pragma unroll
+  for (int s = 0; s < KS; ++s) {
+    const uint64_t db = tc::smem_desc16(b16 + s * (2 * chunk / 16), chunk, 128);
+    tc::mma_bf16(tmem_d, tc::smem_desc16(a_hi16 + s * 256, 2048, 128), db, id1, s > 0 ? 1u : 0u);
+    tc::mma_bf16(tmem_d, tc::smem_desc16(a_lo16 + s * 256, 2048, 128), db, id2, 1u);
+  }
+}
 // this thread's row of a layer GEMM result: v[j] = D[j] + D[NH + j], j < NJ (NJ a multiple of 8)
 template <int NH, int NJ>
 __device__ __forceinline__ void load_acc(uint32_t lane_base, float (&v)[NJ]) {
@@ -63,6 +76,14 @@ __device__ __forceinline__ void gemm_rows_stacked(uint32_t tmem_d, uint32_t a, u
 #pragma unroll
   for (int s = 0; s < 8; ++s)                       // 128 rows = 8 x 16
     tc::mma_bf16(tmem_d, tc::smem_desc(a + s * 256, 128, 2048), tc::smem_desc(b + s * 256, 128, 2048), id, (s > 0) ? 1u : acc0);
+}
+
+template <int NN, int MM = 128>
+__device__ __forceinline__ void gemm_rows_stacked16(uint32_t tmem_d, uint32_t a16, uint32_t b16, uint32_t acc0) {
+  constexpr uint32_t id = tc::idesc_bf16(MM, NN, true, true);
+#pragma unroll
+  for (int s = 0; s < 8; ++s)                       // 128 rows = 8 x 16
+    tc::mma_bf16(tmem_d, tc::smem_desc16(a16 + s * 16, 128, 2048), tc::smem_desc16(b16 + s * 16, 128, 2048), id, (s > 0) ? 1u : acc0);
 }
 
 __device__ __forceinline__ float rcp_fast(float x) {
@@ -92,6 +113,17 @@ __device__ __forceinline__ void gemm_k_tf32(uint32_t tmem_acc, uint32_t tmem_a, 
 #pragma unroll
   for (int s = 0; s < KS; ++s) {
     const uint64_t dbh = tc::smem_desc(b_hi + s * (2 * NB * 16), NB * 16, 128), dbl = tc::smem_desc(b_lo + s * (2 * NB * 16), NB * 16, 128);
+    tc::mma_tf32_ts(tmem_acc, tmem_a + C_AHI + 8 * s, dbh, id, s > 0 ? 1u : 0u);
+    tc::mma_tf32_ts(tmem_acc, tmem_a + C_ALO + 8 * s, dbh, id, 1u);
+    tc::mma_tf32_ts(tmem_acc, tmem_a + C_AHI + 8 * s, dbl, id, 1u);
+  }
+}
+template <int KS>
+__device__ __forceinline__ void gemm_k_tf32_16(uint32_t tmem_acc, uint32_t tmem_a, uint32_t b_hi16, uint32_t b_lo16) {
+  constexpr uint32_t id = tc::idesc_tf32(128, 32, false, false);
+#pragma unroll
+  for (int s = 0; s < KS; ++s) {
+    const uint64_t dbh = tc::smem_desc16(b_hi16 + s * (2 * NB), NB * 16, 128), dbl = tc::smem_desc16(b_lo16 + s * (2 * NB), NB * 16, 128);
     tc::mma_tf32_ts(tmem_acc, tmem_a + C_AHI + 8 * s, dbh, id, s > 0 ? 1u : 0u);
     tc::mma_tf32_ts(tmem_acc, tmem_a + C_ALO + 8 * s, dbh, id, 1u);
     tc::mma_tf32_ts(tmem_acc, tmem_a + C_AHI + 8 * s, dbl, id, 1u);
