@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
         }
       }
       publish();
-      if (warp == 0 && issuer) {
+      if (warp == 0 && tc::elect_one()) {
         tc::tc_fence_after();
 #if FBSDEJ_ABLATE != 12
         gemm_k16<1, NB>(tmem + C_ACC, sa(XA_HI), sa(XA_LO), sa(W1B));
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
         tc::store_bf16x8(u4 + H1_HI, u4 + H1_LO, c8, row, h1 + 8 * c8);
       }
       publish();
-      if (warp == 1 && issuer) {
+      if (warp == 1 && tc::elect_one()) {
         tc::tc_fence_after();
 #if FBSDEJ_ABLATE != 12
         gemm_k16<2, NB>(tmem + C_ACC, sa(H1_HI), sa(H1_LO), sa(W2B));
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
         tc::store_bf16x8(u4 + D2_HI, u4 + D2_LO, c8, row, d2);
       }
       publish();
-      if (warp == 2 && issuer) {
+      if (warp == 2 && tc::elect_one()) {
         tc::tc_fence_after();
         // the input-gradient GEMM first: its result is on the step's critical chain, the weight-gradient GEMM is not (the
         // tensor pipe is in order); the weight-gradient GEMM gets its own barrier because D1 overwrites tiles it reads
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
         for (int c8 = 0; c8 < 3; ++c8) tc::store_bf16x8(u4 + D1_HI, u4 + D1_LO, c8, row, d1 + 8 * c8);
       }
       publish();
-      if (warp == 3 && issuer) {
+      if (warp == 3 && tc::elect_one()) {
         tc::tc_fence_after();
 #if FBSDEJ_ABLATE != 12
         gemm_k16<2, 16>(tmem + C_ACC, sa(D1_HI), sa(D1_LO), sa(W1T));
@@ -597,7 +597,7 @@ __global__ void __launch_bounds__(2 * kThreads, 4) reg_forward_tc(const PricingA
         store_tf32x8(lane_a, 1, xin + 8);
       }
       publish_net(hrows);
-      if (warp == 0 && issuer) {
+      if (warp == 0 && tc::elect_one()) {
         tc::tc_fence_after();
 #if FBSDEJ_ABLATE != 4
         gemm_k_tf32_16<2>(tmem, tmem_a, sa(W1B_HI), sa(W1B_LO));
@@ -627,7 +627,7 @@ __global__ void __launch_bounds__(2 * kThreads, 4) reg_forward_tc(const PricingA
         store_tf32x8(lane_a, 2, t24 + 16);
       }
       publish_net(hrows);
-      if (warp == 1 && issuer) {
+      if (warp == 1 && tc::elect_one()) {
         tc::tc_fence_after();
 #if FBSDEJ_ABLATE != 4
         gemm_k_tf32_16<3>(tmem, tmem_a, sa(W2B_HI), sa(W2B_LO));

@@ -97,6 +97,13 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, bool a_mn, bool 
          ((uint32_t)(M >> 4) << 24);
 }
 
+// One lane of a converged warp (elect.sync): the issuing-thread predicate ptxas recognises - a `lane == 0` test makes it wrap every
+// tcgen05 instruction of the branch in an elect / retry loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(p));
+  return p != 0;
+}
 // D[tmem] (+)= A[smem] * B[smem], issued by ONE thread.
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(

@@ -37,17 +37,37 @@ __device__ __forceinline__ void gemm_k(uint32_t tmem_d, uint32_t a_hi, uint32_t 
     tc::mma_bf16(tmem_d, tc::smem_desc(a_lo + s * 4096, 2048, 128), db, id2, 1u);
   }
 }
-// (addresses in units of 16 bytes: tc::smem_desc16)
+// (addresses in units of 16 bytes: tc::smem_desc16).  All MMAs of the GEMM sit in ONE asm statement: the compiler wraps every asm
+// statement that uses uniform registers inside a divergent branch (the single issuing lane) in an elect / retry loop of five
+// instructions, and these MMAs are on the critical path between a barrier and the next wait.
 template <int KS, int NH, bool FULL = false>
 __device__ __forceinline__ void gemm_k16(uint32_t tmem_d, uint32_t a_hi16, uint32_t a_lo16, uint32_t b16) {
+  static_assert(KS == 1 || KS == 2, "one or two 16-wide K slices");
   constexpr uint32_t id1 = tc::idesc_bf16(128, 2 * NH, false, false),
                      id2 = tc::idesc_bf16(128, FULL ? 2 * NH : (NH + 15) / 16 * 16, false, false);
   constexpr uint32_t chunk = 2 * NH * 16;
-#pragma unroll
-  for (int s = 0; s < KS; ++s) {
-    const uint64_t db = tc::smem_desc16(b16 + s * (2 * chunk / 16), chunk, 128);
-    tc::mma_bf16(tmem_d, tc::smem_desc16(a_hi16 + s * 256, 2048, 128), db, id1, s > 0 ? 1u : 0u);
-    tc::mma_bf16(tmem_d, tc::smem_desc16(a_lo16 + s * 256, 2048, 128), db, id2, 1u);
+  const uint64_t dah = tc::smem_desc16(a_hi16, 2048, 128), dal = tc::smem_desc16(a_lo16, 2048, 128), db = tc::smem_desc16(b16, chunk, 128);
+  if constexpr (KS == 1) {
+    asm volatile(
+        "{\n\t.reg .pred pf, pt;\n\t"
+        "setp.ne.u32 pf, 0, 0;\n\tsetp.eq.u32 pt, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %3, %4, pf;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %2, %3, %5, pt;\n\t}"
+        :
+        : "r"(tmem_d), "l"(dah), "l"(dal), "l"(db), "r"(id1), "r"(id2)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred pf, pt;\n\t.reg .b64 ah1, al1, b1;\n\t"
+        "setp.ne.u32 pf, 0, 0;\n\tsetp.eq.u32 pt, 0, 0;\n\t"
+        "add.s64 ah1, %1, 256;\n\tadd.s64 al1, %2, 256;\n\tadd.s64 b1, %3, %6;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %3, %4, pf;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %2, %3, %5, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], ah1, b1, %4, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], al1, b1, %5, pt;\n\t}"
+        :
+        : "r"(tmem_d), "l"(dah), "l"(dal), "l"(db), "r"(id1), "r"(id2), "n"(2 * chunk / 16)
+        : "memory");
   }
 }
 // this thread's row of a layer GEMM result: v[j] = D[j] + D[NH + j], j < NJ (NJ a multiple of 8)
@@ -81,9 +101,22 @@ __device__ __forceinline__ void gemm_rows_stacked(uint32_t tmem_d, uint32_t a, u
 template <int NN, int MM = 128>
 __device__ __forceinline__ void gemm_rows_stacked16(uint32_t tmem_d, uint32_t a16, uint32_t b16, uint32_t acc0) {
   constexpr uint32_t id = tc::idesc_bf16(MM, NN, true, true);
-#pragma unroll
-  for (int s = 0; s < 8; ++s)                       // 128 rows = 8 x 16
-    tc::mma_bf16(tmem_d, tc::smem_desc16(a16 + s * 16, 128, 2048), tc::smem_desc16(b16 + s * 16, 128, 2048), id, (s > 0) ? 1u : acc0);
+  const uint64_t da = tc::smem_desc16(a16, 128, 2048), db = tc::smem_desc16(b16, 128, 2048);
+  asm volatile(                                     // 128 rows = 8 x 16: operand s is 256 bytes (16 units) after operand s - 1
+      "{\n\t.reg .pred p, pt;\n\t.reg .b64 a, b;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\tsetp.eq.u32 pt, 0, 0;\n\t"
+      "mov.b64 a, %1;\n\tmov.b64 b, %2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, p;\n\t"
+      "add.s64 a, a, 16;\n\tadd.s64 b, b, 16;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, pt;\n\t"
+      "add.s64 a, a, 16;\n\tadd.s64 b, b, 16;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, pt;\n\t"
+      "add.s64 a, a, 16;\n\tadd.s64 b, b, 16;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, pt;\n\t"
+      "add.s64 a, a, 16;\n\tadd.s64 b, b, 16;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, pt;\n\t"
+      "add.s64 a, a, 16;\n\tadd.s64 b, b, 16;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, pt;\n\t"
+      "add.s64 a, a, 16;\n\tadd.s64 b, b, 16;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, pt;\n\t"
+      "add.s64 a, a, 16;\n\tadd.s64 b, b, 16;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, pt;\n\t}"
+      :
+      : "r"(tmem_d), "l"(da), "l"(db), "r"(id), "r"(acc0)
+      : "memory");
 }
 
 __device__ __forceinline__ float rcp_fast(float x) {
@@ -120,14 +153,36 @@ __device__ __forceinline__ void gemm_k_tf32(uint32_t tmem_acc, uint32_t tmem_a, 
 }
 template <int KS>
 __device__ __forceinline__ void gemm_k_tf32_16(uint32_t tmem_acc, uint32_t tmem_a, uint32_t b_hi16, uint32_t b_lo16) {
+  static_assert(KS == 2 || KS == 3, "two or three 8-wide K slices");
   constexpr uint32_t id = tc::idesc_tf32(128, 32, false, false);
-#pragma unroll
-  for (int s = 0; s < KS; ++s) {
-    const uint64_t dbh = tc::smem_desc16(b_hi16 + s * (2 * NB), NB * 16, 128), dbl = tc::smem_desc16(b_lo16 + s * (2 * NB), NB * 16, 128);
-    tc::mma_tf32_ts(tmem_acc, tmem_a + C_AHI + 8 * s, dbh, id, s > 0 ? 1u : 0u);
-    tc::mma_tf32_ts(tmem_acc, tmem_a + C_ALO + 8 * s, dbh, id, 1u);
-    tc::mma_tf32_ts(tmem_acc, tmem_a + C_AHI + 8 * s, dbl, id, 1u);
+  const uint64_t dbh = tc::smem_desc16(b_hi16, NB * 16, 128), dbl = tc::smem_desc16(b_lo16, NB * 16, 128);
+  const uint32_t ahi = tmem_a + C_AHI, alo = tmem_a + C_ALO;
+#define FBSDEJ_TF32_SLICE(P0)                                                           \
+  "tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah], bh, %5, " P0 ";\n\t"                  \
+  "tcgen05.mma.cta_group::1.kind::tf32 [%0], [al], bh, %5, pt;\n\t"                      \
+  "tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah], bl, %5, pt;\n\t"
+#define FBSDEJ_TF32_NEXT "add.u32 ah, ah, 8;\n\tadd.u32 al, al, 8;\n\tadd.s64 bh, bh, %6;\n\tadd.s64 bl, bl, %6;\n\t"
+  if constexpr (KS == 2) {
+    asm volatile(
+        "{\n\t.reg .pred pf, pt;\n\t.reg .b32 ah, al;\n\t.reg .b64 bh, bl;\n\t"
+        "setp.ne.u32 pf, 0, 0;\n\tsetp.eq.u32 pt, 0, 0;\n\t"
+        "mov.b32 ah, %1;\n\tmov.b32 al, %2;\n\tmov.b64 bh, %3;\n\tmov.b64 bl, %4;\n\t"
+        FBSDEJ_TF32_SLICE("pf") FBSDEJ_TF32_NEXT FBSDEJ_TF32_SLICE("pt") "}"
+        :
+        : "r"(tmem_acc), "r"(ahi), "r"(alo), "l"(dbh), "l"(dbl), "r"(id), "n"(2 * NB)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred pf, pt;\n\t.reg .b32 ah, al;\n\t.reg .b64 bh, bl;\n\t"
+        "setp.ne.u32 pf, 0, 0;\n\tsetp.eq.u32 pt, 0, 0;\n\t"
+        "mov.b32 ah, %1;\n\tmov.b32 al, %2;\n\tmov.b64 bh, %3;\n\tmov.b64 bl, %4;\n\t"
+        FBSDEJ_TF32_SLICE("pf") FBSDEJ_TF32_NEXT FBSDEJ_TF32_SLICE("pt") FBSDEJ_TF32_NEXT FBSDEJ_TF32_SLICE("pt") "}"
+        :
+        : "r"(tmem_acc), "r"(ahi), "r"(alo), "l"(dbh), "l"(dbl), "r"(id), "n"(2 * NB)
+        : "memory");
   }
+#undef FBSDEJ_TF32_SLICE
+#undef FBSDEJ_TF32_NEXT
 }
 // 8 consecutive features of this thread's row -> TF32 hi / lo columns of the A operand in tensor memory
 __device__ __forceinline__ void store_tf32x8(uint32_t lane_base /* of the A allocation */, int c8, const float* v) {
