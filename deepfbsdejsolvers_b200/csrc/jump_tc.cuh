@@ -87,7 +87,7 @@ struct JumpTcFwd {
 #pragma unroll
     for (int c8 = 0; c8 < NXC; ++c8) fwd::store_tf32x8(lane_a, c8, xin + 8 * c8);
     fwd::publish_tmem();
-    if (row == 0) {
+    if (warp == 0 && tc::elect_one()) {
       tc::tc_fence_after();
       fwd::gemm_k_tf32<NXC>(tmem, tmem_a, sbase + W1B_HI * 4, sbase + W1B_LO * 4);
       tc::mma_commit(bar);
@@ -103,7 +103,7 @@ struct JumpTcFwd {
       fwd::store_tf32x8(lane_a, c8, t8);
     }
     fwd::publish_tmem();
-    if (warp == 1 && (row & 31) == 0) {
+    if (warp == 1 && tc::elect_one()) {
       tc::tc_fence_after();
       fwd::gemm_k_tf32<3>(tmem, tmem_a, sbase + W2B_HI * 4, sbase + W2B_LO * 4);
       tc::mma_commit(bar);
@@ -131,11 +131,11 @@ struct JumpTcFwd {
   // xin: the row's inputs with the jump-feature slots ZEROED; pre: the layer-1 pre-activations (incl. the constant-1 unit).
   __device__ __forceinline__ void preact(const float (&xin)[NI], float (&pre)[24]) {
     using namespace rtc;
-    const int row = threadIdx.x;
+    const int warp = threadIdx.x >> 5;
 #pragma unroll
     for (int c8 = 0; c8 < NXC; ++c8) fwd::store_tf32x8(lane_a, c8, xin + 8 * c8);
     fwd::publish_tmem();
-    if (row == 0) {
+    if (warp == 0 && tc::elect_one()) {
       tc::tc_fence_after();
       fwd::gemm_k_tf32<NXC>(tmem, tmem_a, sbase + W1B_HI * 4, sbase + W1B_LO * 4);
       tc::mma_commit(bar);
@@ -161,7 +161,7 @@ struct JumpTcFwd {
       fwd::store_tf32x8(lane_a, c8, t8);
     }
     fwd::publish_tmem();
-    if (warp == 1 && (row & 31) == 0) {
+    if (warp == 1 && tc::elect_one()) {
       tc::tc_fence_after();
       fwd::gemm_k_tf32<3>(tmem, tmem_a, sbase + W2B_HI * 4, sbase + W2B_LO * 4);
       tc::mma_commit(bar);
@@ -317,12 +317,11 @@ struct JumpTcBwd {
   __device__ __forceinline__ void step(const float (&xin)[NI], float dout, float (&dx)[NDX]) {
     using namespace rtc;
     const int row = threadIdx.x, warp = row >> 5;
-    const bool issuer = (row & 31) == 0;
     drain_w();                                         // WG1 of the previous tile read X, D1
 #pragma unroll
     for (int c8 = 0; c8 < NXC; ++c8) tc::store_bf16x8(u4 + XA_HI, u4 + XA_LO, c8, row, xin + 8 * c8);
     publish();
-    if (warp == 0 && issuer) {
+    if (warp == 0 && tc::elect_one()) {
       tc::tc_fence_after();
       gemm_k<KS1, NBR, true>(tmem + C_ACC, sa(XA_HI), sa(XA_LO), sw(W1B));
       tc::mma_commit(bar_f);
@@ -337,7 +336,7 @@ struct JumpTcBwd {
       tc::store_bf16x8(u4 + H1_HI, u4 + H1_LO, c8, row, h1 + 8 * c8);
     }
     publish();
-    if (warp == 1 && issuer) {
+    if (warp == 1 && tc::elect_one()) {
       tc::tc_fence_after();
       gemm_k<2, NBR, true>(tmem + C_ACC, sa(H1_HI), sa(H1_LO), sw(W2B));
       tc::mma_commit(bar_f);
@@ -367,7 +366,7 @@ struct JumpTcBwd {
       tc::store_bf16x8(u4 + D2_HI, u4 + D2_LO, c8, row, d2);
     }
     publish();
-    if (warp == 2 && issuer) {
+    if (warp == 2 && tc::elect_one()) {
       tc::tc_fence_after();
       // the input-gradient GEMM first (it is on the tile's chain; the tensor pipe is in order), the weight-gradient GEMM behind
       // it on its own barrier (D1 overwrites tiles it reads)
@@ -393,7 +392,7 @@ struct JumpTcBwd {
       for (int c8 = 0; c8 < 3; ++c8) tc::store_bf16x8(u4 + D1_HI, u4 + D1_LO, c8, row, d1 + 8 * c8);
     }
     publish();
-    if (warp == 3 && issuer) {
+    if (warp == 3 && tc::elect_one()) {
       tc::tc_fence_after();
       gemm_k<2, NI, true>(tmem + C_ACC, sa(D1_HI), sa(D1_LO), sw(W1T));
       tc::mma_commit(bar_f);
@@ -416,7 +415,7 @@ struct JumpTcBwd {
 #pragma unroll
     for (int c8 = 0; c8 < NXC; ++c8) tc::store_bf16x8(u4 + XA_HI, u4 + XA_LO, c8, row, xin + 8 * c8);
     publish();
-    if (warp == 0 && (row & 31) == 0) {
+    if (warp == 0 && tc::elect_one()) {
       tc::tc_fence_after();
       gemm_k<KS1, NBR, true>(tmem + C_ACC, sa(XA_HI), sa(XA_LO), sw(W1B));
       tc::mma_commit(bar_f);
@@ -433,7 +432,6 @@ struct JumpTcBwd {
                                            float (&sumd1)[24], float& dscale) {
     using namespace rtc;
     const int row = threadIdx.x, warp = row >> 5;
-    const bool issuer = (row & 31) == 0;
     drain_w();                                         // WG1 of the previous sample read X, D1 (= the H2_hi / H1_lo tiles)
 #pragma unroll
     for (int c8 = 0; c8 < NXC; ++c8) tc::store_bf16x8(u4 + XA_HI, u4 + XA_LO, c8, row, xj + 8 * c8);
@@ -447,7 +445,7 @@ struct JumpTcBwd {
       tc::store_bf16x8(u4 + H1_HI, u4 + H1_LO, c8, row, h1 + 8 * c8);
     }
     publish();
-    if (warp == 1 && issuer) {
+    if (warp == 1 && tc::elect_one()) {
       tc::tc_fence_after();
       gemm_k<2, NBR, true>(tmem + C_ACC, sa(H1_HI), sa(H1_LO), sw(W2B));
       tc::mma_commit(bar_f);
@@ -477,7 +475,7 @@ struct JumpTcBwd {
       tc::store_bf16x8(u4 + D2_HI, u4 + D2_LO, c8, row, d2);
     }
     publish();
-    if (warp == 2 && issuer) {
+    if (warp == 2 && tc::elect_one()) {
       tc::tc_fence_after();
       gemm_k<2, NBR, true>(tmem + C_ACC, sa(D2_HI), sa(D2_LO), sw(WTB));
       tc::mma_commit(bar_f);
@@ -509,7 +507,7 @@ struct JumpTcBwd {
     }
     tc::tc_fence_before();
     publish();
-    if (warp == 3 && issuer) {
+    if (warp == 3 && tc::elect_one()) {
       tc::tc_fence_after();
       gemm_rows_stacked<2 * NI, 64>(tmem + C_W1, sa(D1_HI), sa(XA_HI), started ? 1u : 0u);
       tc::mma_commit(bar_w);
@@ -528,7 +526,7 @@ struct JumpTcBwd {
 #pragma unroll
     for (int c8 = 0; c8 < 3; ++c8) tc::store_bf16x8(u4 + D1_HI, u4 + D1_LO, c8, row, sumd1 + 8 * c8);
     publish();
-    if (warp == 3 && (row & 31) == 0) {
+    if (warp == 3 && tc::elect_one()) {
       tc::tc_fence_after();
       gemm_k<2, NI, true>(tmem + C_ACC, sa(D1_HI), sa(D1_LO), sw(W1T));
       tc::mma_commit(bar_f);

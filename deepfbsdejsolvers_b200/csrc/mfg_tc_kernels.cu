@@ -60,7 +60,6 @@ __global__ void __launch_bounds__(kT, 1) mfg_forward_tc(const MFGArgs a) {
   using namespace f;
   extern __shared__ __align__(1024) float smem[];
   const int role = threadIdx.x >> 7, row = threadIdx.x & (TR - 1), warp = row >> 5;
-  const bool issuer = (row & 31) == 0;
   const NetRt& net = role == 0 ? a.netA : a.netB;
   const int H = net.H, nin = net.nin, nout = net.nout;
   float* const rw = smem + role * ROLE_FLOATS;
@@ -146,7 +145,7 @@ __global__ void __launch_bounds__(kT, 1) mfg_forward_tc(const MFGArgs a) {
         fwd::store_tf32x8(lane_a, 1, xin + 8);
       }
       fwd::publish_tmem();
-      if (warp == 0 && issuer) {
+      if (warp == 0 && tc::elect_one()) {
         tc::tc_fence_after();
         fwd::gemm_k_tf32<2>(tmem, tmem_a, sa(W1B_HI), sa(W1B_LO));
         tc::mma_commit(bar);
@@ -162,7 +161,7 @@ __global__ void __launch_bounds__(kT, 1) mfg_forward_tc(const MFGArgs a) {
         fwd::store_tf32x8(lane_a, c8, t8);
       }
       fwd::publish_tmem();
-      if (warp == 1 && issuer) {
+      if (warp == 1 && tc::elect_one()) {
         tc::tc_fence_after();
         fwd::gemm_k_tf32<3>(tmem, tmem_a, sa(W2B_HI), sa(W2B_LO));
         tc::mma_commit(bar);
@@ -297,7 +296,6 @@ __global__ void __launch_bounds__(kT, 1) mfg_backward_tc(const MFGArgs a) {
   using namespace b;
   extern __shared__ __align__(1024) float smem[];
   const int role = threadIdx.x >> 7, row = threadIdx.x & (TR - 1), warp = row >> 5;
-  const bool issuer = (row & 31) == 0;
   const NetRt& net = role == 0 ? a.netA : a.netB;
   const int H = net.H, nin = net.nin, nout = net.nout;
   float* const rf = smem + role * ROLE_FLOATS;
@@ -459,7 +457,7 @@ __global__ void __launch_bounds__(kT, 1) mfg_backward_tc(const MFGArgs a) {
         reinterpret_cast<unsigned short*>(u4 + W1B)[bias_idx + NB * 8] = (unsigned short)lo;
       }
       publish();
-      if (warp == 0 && issuer) {
+      if (warp == 0 && tc::elect_one()) {
         tc::tc_fence_after();
         gemm_k<1, NB>(tmem + C_ACC, sa(XA_HI), sa(XA_LO), sa(W1B));
         tc::mma_commit(bar_f);
@@ -475,7 +473,7 @@ __global__ void __launch_bounds__(kT, 1) mfg_backward_tc(const MFGArgs a) {
         tc::store_bf16x8(u4 + H1_HI, u4 + H1_LO, c8, row, h1 + 8 * c8);
       }
       publish();
-      if (warp == 1 && issuer) {
+      if (warp == 1 && tc::elect_one()) {
         tc::tc_fence_after();
         gemm_k<2, NB>(tmem + C_ACC, sa(H1_HI), sa(H1_LO), sa(W2B));
         tc::mma_commit(bar_f);
@@ -505,7 +503,7 @@ __global__ void __launch_bounds__(kT, 1) mfg_backward_tc(const MFGArgs a) {
       }
       tc::store_bf16x8(u4 + DO_HI, u4 + DO_LO, 0, row, dd);
       publish();
-      if (warp == 2 && issuer) {
+      if (warp == 2 && tc::elect_one()) {
         tc::tc_fence_after();
         gemm_rows_stacked<64>(tmem + C_W2, sa(H1_HI), sa(D2_HI), started ? 1u : 0u);   // [H1|H2 hi, lo]^T [D2 hi|lo | dout hi|lo]
         gemm_k<2, NB>(tmem + C_ACC, sa(D2_HI), sa(D2_LO), sa(WTB));
@@ -524,7 +522,7 @@ __global__ void __launch_bounds__(kT, 1) mfg_backward_tc(const MFGArgs a) {
         tc::store_bf16x8(u4 + D1_HI, u4 + D1_LO, c8, row, t8);
       }
       publish();
-      if (warp == 3 && issuer) {
+      if (warp == 3 && tc::elect_one()) {
         tc::tc_fence_after();
         gemm_k<2, 16>(tmem + C_ACC, sa(D1_HI), sa(D1_LO), sa(W1T));
         tc::mma_commit(bar_f);

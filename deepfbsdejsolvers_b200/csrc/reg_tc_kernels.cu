@@ -70,7 +70,6 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
   uint64_t* const bar_g = bar_f + 3;                    // (slot 2 holds the TMEM base)
   uint32_t* const tslot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 4);
   const int row = threadIdx.x, warp = row >> 5;
-  const bool issuer = (row & 31) == 0;
   const int H = a.netA.H, nin = a.netA.nin;
 
   // ---- one-time set-up: zero the tiles, TMA bulk copy of the weight operand image (bf16 hi / lo B operands + W3; built from
@@ -97,7 +96,7 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
   if (row < H) { w0 = a.theta[a.netA.ext_off + row]; b1v = a.theta[a.netA.ext_off + nin * H + row]; }
   const int bias_idx = ((nin >> 3) * 2 * NB + row) * 8 + (nin & 7);   // hi copy; the lo copy is NB n-rows further
   const uint32_t sbase = tc::smem_u32(u4);
-  const uint32_t sbase16 = sbase >> 4;                  // operand addresses in units of 16 bytes (tc::smem_desc16)
+  const uint32_t sbase16 = tc::addr16(sbase);                 // operand addresses in units of 16 bytes (tc::smem_desc16)
   auto sa = [&](int off_u4) { return sbase16 + (uint32_t)off_u4; };
   uint32_t phase_f = 0, phase_w = 1, phase_g = 0, pending_w = 0, started = 0;
   auto wait_f = [&]() { tc::mbar_wait(bar_f, phase_f); phase_f ^= 1; tc::tc_fence_after(); };
@@ -558,7 +557,7 @@ __global__ void __launch_bounds__(2 * kThreads, 4) reg_forward_tc(const PricingA
   const uint32_t tmem = tslot[0], tmem_a = tslot[1];
   const uint32_t lane_base = tmem + ((uint32_t)(row & ~31) << 16), lane_a = tmem_a + ((uint32_t)(row & ~31) << 16);
   const uint32_t sbase = tc::smem_u32(smem);
-  const uint32_t sbase16 = sbase >> 4;                  // operand addresses in units of 16 bytes (tc::smem_desc16)
+  const uint32_t sbase16 = tc::addr16(sbase);                 // operand addresses in units of 16 bytes (tc::smem_desc16)
   auto sa = [&](int off_f) { return sbase16 + (uint32_t)(off_f >> 2); };
   uint32_t phase = 1;
   auto wait_mma = [&]() { tc::mbar_wait(bar, phase); phase ^= 1; tc::tc_fence_after(); };

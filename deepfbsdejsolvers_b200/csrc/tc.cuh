@@ -77,7 +77,10 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
   const uint32_t hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14);
   return ((uint64_t)hi << 32) | lo;
 }
-// The same descriptor from the operand's shared-memory address IN UNITS OF 16 BYTES (addr16 = address >> 4 < 2^14): with addr16 =
+// shared-memory address in units of 16 bytes, as the 14-bit descriptor field wants it.  The mask matters: in a thread-block
+// cluster the shared::cta window of a CTA does not start at 0, and the unmasked high bits would run into the LBO field.
+__device__ __forceinline__ uint32_t addr16(uint32_t smem_addr) { return (smem_addr >> 4) & 0x3FFFu; }
+// The same descriptor from the operand's shared-memory address IN UNITS OF 16 BYTES (addr16 = tc::addr16(address)): with addr16 =
 // (loop-invariant base >> 4) + compile-time offset the low word is ONE add and the high word a constant - the byte-address form
 // above costs a shift, a mask and an or per descriptor, twice per MMA, on the issuing thread's critical path.
 __device__ __forceinline__ uint64_t smem_desc16(uint32_t addr16, uint32_t lbo_bytes, uint32_t sbo_bytes) {

@@ -25,19 +25,9 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) 
 // A: K-major tile (128 rows); B: [k / 8][2 NH n-rows][8 bf16].
 // FULL: the second MMA spans both column blocks as well, D[:, 0 .. 2 NH) += A_lo [B_hi | B_lo]: all four hi / lo cross products
 // (the jump schemes, whose gradients are differences of nearly equal sums, want the lo.lo term: 2^-17 instead of 2^-16).
-template <int KS, int NH, bool FULL = false>
-__device__ __forceinline__ void gemm_k(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b) {
-  constexpr uint32_t id1 = tc::idesc_bf16(128, 2 * NH, false, false),
-                     id2 = tc::idesc_bf16(128, FULL ? 2 * NH : (NH + 15) / 16 * 16, false, false);
-  constexpr uint32_t chunk = 2 * NH * 16;
-#pragma unroll
-  for (int s = 0; s < KS; ++s) {
-    const uint64_t db = tc::smem_desc(b + s * 2 * chunk, chunk, 128);
-    tc::mma_bf16(tmem_d, tc::smem_desc(a_hi + s * 4096, 2048, 128), db, id1, s > 0 ? 1u : 0u);
-    tc::mma_bf16(tmem_d, tc::smem_desc(a_lo + s * 4096, 2048, 128), db, id2, 1u);
-  }
-}
-// (addresses in units of 16 bytes: tc::smem_desc16).  All MMAs of the GEMM sit in ONE asm statement: the compiler wraps every asm
+// (addresses in units of 16 bytes: tc::smem_desc16).  CALL UNDER `warp == k && tc::elect_one()`, not under a `lane == 0` test: in
+// a lane-divergent branch ptxas wraps every tcgen05 instruction in an elect / retry loop of five instructions.
+// All MMAs of the GEMM sit in ONE asm statement: the compiler wraps every asm
 // statement that uses uniform registers inside a divergent branch (the single issuing lane) in an elect / retry loop of five
 // instructions, and these MMAs are on the critical path between a barrier and the next wait.
 template <int KS, int NH, bool FULL = false>
@@ -70,6 +60,11 @@ __device__ __forceinline__ void gemm_k16(uint32_t tmem_d, uint32_t a_hi16, uint3
         : "memory");
   }
 }
+// byte-address form (16-byte aligned operands)
+template <int KS, int NH, bool FULL = false>
+__device__ __forceinline__ void gemm_k(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b) {
+  gemm_k16<KS, NH, FULL>(tmem_d, tc::addr16(a_hi), tc::addr16(a_lo), tc::addr16(b));
+}
 // this thread's row of a layer GEMM result: v[j] = D[j] + D[NH + j], j < NJ (NJ a multiple of 8)
 template <int NH, int NJ>
 __device__ __forceinline__ void load_acc(uint32_t lane_base, float (&v)[NJ]) {
@@ -91,14 +86,6 @@ __device__ __forceinline__ void load_acc(uint32_t lane_base, float (&v)[NJ]) {
 // bound by their operand reads: scripts/mma_microbench.cu), and accumulator row m lands in lane (m / 16) * 32 + m % 16.
 __host__ __device__ constexpr int lane_of_row_m64(int m) { return (m >> 4) * 32 + (m & 15); }
 template <int NN, int MM = 128>
-__device__ __forceinline__ void gemm_rows_stacked(uint32_t tmem_d, uint32_t a, uint32_t b, uint32_t acc0) {
-  constexpr uint32_t id = tc::idesc_bf16(MM, NN, true, true);
-#pragma unroll
-  for (int s = 0; s < 8; ++s)                       // 128 rows = 8 x 16
-    tc::mma_bf16(tmem_d, tc::smem_desc(a + s * 256, 128, 2048), tc::smem_desc(b + s * 256, 128, 2048), id, (s > 0) ? 1u : acc0);
-}
-
-template <int NN, int MM = 128>
 __device__ __forceinline__ void gemm_rows_stacked16(uint32_t tmem_d, uint32_t a16, uint32_t b16, uint32_t acc0) {
   constexpr uint32_t id = tc::idesc_bf16(MM, NN, true, true);
   const uint64_t da = tc::smem_desc16(a16, 128, 2048), db = tc::smem_desc16(b16, 128, 2048);
@@ -117,6 +104,11 @@ __device__ __forceinline__ void gemm_rows_stacked16(uint32_t tmem_d, uint32_t a1
       :
       : "r"(tmem_d), "l"(da), "l"(db), "r"(id), "r"(acc0)
       : "memory");
+}
+
+template <int NN, int MM = 128>
+__device__ __forceinline__ void gemm_rows_stacked(uint32_t tmem_d, uint32_t a, uint32_t b, uint32_t acc0) {
+  gemm_rows_stacked16<NN, MM>(tmem_d, tc::addr16(a), tc::addr16(b), acc0);
 }
 
 __device__ __forceinline__ float rcp_fast(float x) {
@@ -140,17 +132,6 @@ namespace fwd {
 constexpr uint32_t C_AHI = 0, C_ALO = 32;     // columns of the A allocation: hi copy (X: 16, H1: 24 columns) | lo copy
 // D[ACC] = A (tensor memory: lane = row, one TF32 element per column, KS slices of 8 columns; hi and lo copies)
 //          * B (shared memory [k/4][n][4], NB n-rows per chunk), N = 32, 3xTF32
-template <int KS>
-__device__ __forceinline__ void gemm_k_tf32(uint32_t tmem_acc, uint32_t tmem_a, uint32_t b_hi, uint32_t b_lo) {
-  constexpr uint32_t id = tc::idesc_tf32(128, 32, false, false);
-#pragma unroll
-  for (int s = 0; s < KS; ++s) {
-    const uint64_t dbh = tc::smem_desc(b_hi + s * (2 * NB * 16), NB * 16, 128), dbl = tc::smem_desc(b_lo + s * (2 * NB * 16), NB * 16, 128);
-    tc::mma_tf32_ts(tmem_acc, tmem_a + C_AHI + 8 * s, dbh, id, s > 0 ? 1u : 0u);
-    tc::mma_tf32_ts(tmem_acc, tmem_a + C_ALO + 8 * s, dbh, id, 1u);
-    tc::mma_tf32_ts(tmem_acc, tmem_a + C_AHI + 8 * s, dbl, id, 1u);
-  }
-}
 template <int KS>
 __device__ __forceinline__ void gemm_k_tf32_16(uint32_t tmem_acc, uint32_t tmem_a, uint32_t b_hi16, uint32_t b_lo16) {
   static_assert(KS == 2 || KS == 3, "two or three 8-wide K slices");
@@ -183,6 +164,10 @@ __device__ __forceinline__ void gemm_k_tf32_16(uint32_t tmem_acc, uint32_t tmem_
   }
 #undef FBSDEJ_TF32_SLICE
 #undef FBSDEJ_TF32_NEXT
+}
+template <int KS>
+__device__ __forceinline__ void gemm_k_tf32(uint32_t tmem_acc, uint32_t tmem_a, uint32_t b_hi, uint32_t b_lo) {
+  gemm_k_tf32_16<KS>(tmem_acc, tmem_a, tc::addr16(b_hi), tc::addr16(b_lo));
 }
 // 8 consecutive features of this thread's row -> TF32 hi / lo columns of the A operand in tensor memory
 __device__ __forceinline__ void store_tf32x8(uint32_t lane_base /* of the A allocation */, int c8, const float* v) {
