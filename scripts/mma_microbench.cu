@@ -7,6 +7,8 @@
 //   M         128 or 64
 // with one CTA on the device and with 4 CTAs on every SM (the training kernels' residency).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scripts/build/mma_microbench scripts/mma_microbench.cu
+//        add -DMB_ELECT to pick the issuing lane with elect.sync (tc::elect_one) instead of a lane test: ptxas then emits the
+//        tcgen05 instructions without an elect / retry loop around each (profiles/r2_mma_microbench_elect.csv)
 #include <cstdio>
 #include <cstdint>
 #include <vector>
@@ -16,6 +18,14 @@
 using namespace fbsdej;
 
 constexpr int NM = 64;
+#ifdef MB_ELECT
+#define MB_ISSUER0 ((threadIdx.x >> 5) == 0 && tc::elect_one())
+#define MB_ISSUERW(w, NT) ((w) < (NT) && tc::elect_one())
+#else
+#define MB_ISSUER0 (threadIdx.x == 0)
+#define MB_ISSUERW(w, NT) ((threadIdx.x & 31) == 0 && (w) < (NT))
+#endif
+
 template <int KIND, int N, int NACC, int M>
 __global__ void __launch_bounds__(128) bench(int ncols, long long* out) {
   extern __shared__ __align__(1024) float sm[];
@@ -35,7 +45,7 @@ __global__ void __launch_bounds__(128) bench(int ncols, long long* out) {
   constexpr uint32_t idk = KIND == 2 ? tc::idesc_tf32(M, N, false, false) : tc::idesc_bf16(M, N, KIND == 1, KIND == 1);
   for (int rep = 0; rep < 3; ++rep) {
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (MB_ISSUER0) {
       tc::tc_fence_after();
       uint64_t da[8], db[8];
 #pragma unroll
@@ -112,7 +122,7 @@ __global__ void __launch_bounds__(128) bench_mt(long long* out) {
   for (int rep = 0; rep < 3; ++rep) {
     __syncthreads();
     t0 = clock64();
-    if ((threadIdx.x & 31) == 0 && w < NT) {
+    if (MB_ISSUERW(w, NT)) {
       tc::tc_fence_after();
       const uint64_t da = tc::smem_desc(sb + w * 4096, 2048, 128), db = tc::smem_desc(sb + 32768, N * 16, 128);
       const uint32_t d = tm + 32 + (uint32_t)(w * N);
@@ -176,7 +186,7 @@ __global__ void __launch_bounds__(128) bench_roundtrip(long long* out, float* si
     tc::fence_async_smem();
     tc::tc_fence_before();
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (MB_ISSUER0) {
       tc::tc_fence_after();
       const uint64_t db = tc::smem_desc(sb + 32768, 32 * 16, 128);
 #pragma unroll
