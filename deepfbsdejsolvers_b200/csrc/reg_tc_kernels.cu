@@ -54,6 +54,20 @@ constexpr uint32_t WIMG_BYTES = (uint32_t)(OFF_W3 + 24 - W_BASE * 4) * 4;   // w
 static_assert(WIMG_BYTES % 16 == 0, "bulk copy size");
 constexpr uint32_t C_ACC = 0, C_W1 = 48, C_W2 = 80, NCOLS = 128;   // ACC 48 | WG1 32 | WG2 48 columns
 constexpr int COL_DOUT = 23;                  // spare column of D2 that carries dL/dy through WG2 (needs H <= 22)
+// tanh layers in "r form" (as the forward sweep): the GEMM delivers x' = 2 log2(e) x (scale in the staged weights), the thread forms
+// r = 1 / (2^x' + 1) and stores r - not h = 1 - 2 r - in the operand tiles; the next layer's weights carry the factor -2 and its
+// bias row b + sum_k W[k][.]; 1 - h^2 = 4 (r - r^2) with the 4 in the staged W3 / W2^T.  Two instructions per hidden unit less
+// than tanh_fast + dact.  The weight gradients come out against r: dW[k][j] = db[j] - 2 sum_rows r[k] d[j] (flush).
+template <int ACT>
+__device__ __forceinline__ float hid_r(float x) {
+  if (ACT != ACT_TANH) return fmaxf(x, 0.0f);
+  float t, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + 1.0f));
+  return r;
+}
+template <int ACT>
+__device__ __forceinline__ float dact_r(float r) { return ACT == ACT_TANH ? fmaf(-r, r, r) : (r > 0.0f ? 1.0f : 0.0f); }
 }  // namespace bwd
 
 template <class Model, int ACT>
@@ -93,7 +107,8 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
   const uint32_t lane_base = tmem + ((uint32_t)(row & ~31) << 16);
   // thread j <= H owns the effective layer-1 bias of hidden unit j: c_j(t) = t W1[0][j] + b1[j] (fp32, then split)
   float w0 = 0.0f, b1v = 0.0f;
-  if (row < H) { w0 = a.theta[a.netA.ext_off + row]; b1v = a.theta[a.netA.ext_off + nin * H + row]; }
+  constexpr float CS = ACT == ACT_TANH ? 2.885390081777927f : 1.0f;        // pre-activation scale 2 log2(e) (r form)
+  if (row < H) { w0 = CS * a.theta[a.netA.ext_off + row]; b1v = CS * a.theta[a.netA.ext_off + nin * H + row]; }
   const int bias_idx = ((nin >> 3) * 2 * NB + row) * 8 + (nin & 7);   // hi copy; the lo copy is NB n-rows further
   const uint32_t sbase = tc::smem_u32(u4);
   const uint32_t sbase16 = tc::addr16(sbase);                 // operand addresses in units of 16 bytes (tc::smem_desc16)
@@ -187,7 +202,7 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
         tc::store_bf16x8(u4 + XA_HI, u4 + XA_LO, 1, row, xin + 8);
         if (row <= H) {
           uint32_t hi, lo;
-          tc::split_bf16(row < H ? fmaf(tf, w0, b1v) : (ACT == ACT_TANH ? 20.0f : 1.0f), hi, lo);
+          tc::split_bf16(row < H ? fmaf(tf, w0, b1v) : (ACT == ACT_TANH ? -200.0f : 1.0f), hi, lo);   // constant unit: r(-200) = 1
           reinterpret_cast<unsigned short*>(u4 + W1B)[bias_idx] = (unsigned short)hi;
           reinterpret_cast<unsigned short*>(u4 + W1B)[bias_idx + NB * 8] = (unsigned short)lo;
         }
@@ -207,7 +222,7 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
 #pragma unroll
       for (int c8 = 0; c8 < 3; ++c8) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) h1[8 * c8 + q] = actf<ACT>(h1[8 * c8 + q]);
+        for (int q = 0; q < 8; ++q) h1[8 * c8 + q] = hid_r<ACT>(h1[8 * c8 + q]);
         tc::store_bf16x8(u4 + H1_HI, u4 + H1_LO, c8, row, h1 + 8 * c8);
       }
       publish();
@@ -235,9 +250,9 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
         const float w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const float h = actf<ACT>(t8[q]);
+          const float h = hid_r<ACT>(t8[q]);
           t8[q] = h;
-          d2[q] = dout * w8[q] * dactf<ACT>(h);
+          d2[q] = dout * w8[q] * dact_r<ACT>(h);
         }
         if (c8 == 2) d2[COL_DOUT - 16] = dout;
         tc::store_bf16x8(u4 + H2_HI, u4 + H2_LO, c8, row, t8);
@@ -268,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
           tc::tmem_ld8(lane_base + C_ACC + NB + 8 * c8, q8);
           tc::tmem_ld_wait();
 #pragma unroll
-          for (int q = 0; q < 8; ++q) d1[8 * c8 + q] = (d1[8 * c8 + q] + q8[q]) * dactf<ACT>(h1[8 * c8 + q]);
+          for (int q = 0; q < 8; ++q) d1[8 * c8 + q] = (d1[8 * c8 + q] + q8[q]) * dact_r<ACT>(h1[8 * c8 + q]);
         }
         tc::mbar_wait(bar_g, phase_g); phase_g ^= 1;     // WG2 has read H2 / H1_lo: their tiles may become D1
 #pragma unroll
@@ -329,12 +344,17 @@ __global__ void __launch_bounds__(kThreads, 4) reg_backward_tc(const PricingArgs
         g[e] = (S[lh * SW + i] + S[lh * SW + 16 + i]) + (S[ll * SW + i] + S[ll * SW + 16 + i]);   // hi.hi + hi.lo + lo.hi + lo.lo
       }
     } else if (started) {                              // lanes: H1 hi 0..23, H2 hi 24..47, H1 lo 48..71, H2 lo 72..95
+      auto w2sum = [&](int k, int j) { return (S[k * SW + j] + S[k * SW + 24 + j]) + (S[(48 + k) * SW + j] + S[(48 + k) * SW + 24 + j]); };
+      auto w3sum = [&](int k) {
+        return (S[(24 + k) * SW + COL_DOUT] + S[(24 + k) * SW + 24 + COL_DOUT]) + (S[(72 + k) * SW + COL_DOUT] + S[(72 + k) * SW + 24 + COL_DOUT]);
+      };
+      // tanh: the tiles hold r = (1 - h) / 2, so sum_rows h[k] d[j] = db[j] - 2 sum_rows r[k] d[j] (the constant unit, k = H, is r = 1)
       for (int e = row; e < (H + 1) * H; e += kThreads) {
         const int k = e / H, j = e % H;                // k = H: b2
-        g[o2 + e] = (S[k * SW + j] + S[k * SW + 24 + j]) + (S[(48 + k) * SW + j] + S[(48 + k) * SW + 24 + j]);
+        g[o2 + e] = (ACT == ACT_TANH && k < H) ? fmaf(-2.0f, w2sum(k, j), w2sum(H, j)) : w2sum(k, j);
       }
       if (row <= H)                                    // dW3[k] (k = H: b3) rides in column COL_DOUT of D2
-        g[o3 + row] = (S[(24 + row) * SW + COL_DOUT] + S[(24 + row) * SW + 24 + COL_DOUT]) + (S[(72 + row) * SW + COL_DOUT] + S[(72 + row) * SW + 24 + COL_DOUT]);
+        g[o3 + row] = (ACT == ACT_TANH && row < H) ? fmaf(-2.0f, w3sum(row), w3sum(H)) : w3sum(row);
     }
   }
   tc::tc_fence_before();
@@ -799,21 +819,33 @@ __global__ void __launch_bounds__(256) reg_stage_operands_kernel(const PricingAr
       w[((k >> 3) * 2 * NH + n) * 8 + (k & 7)] = (unsigned short)hi;
       w[((k >> 3) * 2 * NH + NH + n) * 8 + (k & 7)] = (unsigned short)lo;
     };
-    const float one_in = ACT == ACT_TANH ? 20.0f : 1.0f;   // act(one_in) == 1 exactly: the constant-1 unit of H1 / H2
+    // tanh: r form (bwd::hid_r) - W1 and the layer-2 bias row carry 2 log2(e), W2 carries -4 log2(e), the bias row adds sum_k W2[k][.],
+    // W2^T and W3 (which only meet 1 - h^2 = 4 (r - r^2)) carry the 4
+    constexpr float CS = ACT == ACT_TANH ? 2.885390081777927f : 1.0f, W2S = ACT == ACT_TANH ? -2.0f * CS : 1.0f,
+                    DS = ACT == ACT_TANH ? 4.0f : 1.0f;
+    const float one_in = ACT == ACT_TANH ? -200.0f : 1.0f;   // hid_r(one_in) == 1 exactly: the constant-1 unit of H1 / H2
     for (int e = tid; e < n5 + 2; e += nthr) {
       uint32_t hi, lo;
       if (e < n2) {                                   // W1[i][j]: layer-1 B operand [n = j][k = i]; the time row (i = 0) and
         const int i = e < n1 ? e / H : nin, j = e < n1 ? e % H : e - n1;   // b1 (i = nin) live in the per-step effective bias
         tc::split_bf16(th[e], hi, lo);
-        if (i >= 1 && i < nin) put(w1, NB, j, i, hi, lo);
         if (i < nin) put(w1t, 16, i, j, hi, lo);      // input-gradient B operand [n = i][k = j]
+        tc::split_bf16(CS * th[e], hi, lo);
+        if (i >= 1 && i < nin) put(w1, NB, j, i, hi, lo);
       } else if (e < n4) {                            // W2[k][j], b2[j] (k = H): layer-2 B operand [n = j][k]
         const int k = e < n3 ? (e - n2) / H : H, j = e < n3 ? (e - n2) % H : e - n3;
-        tc::split_bf16(th[e], hi, lo);
+        if (k < H) {
+          tc::split_bf16(DS * th[e], hi, lo);
+          put(wt, NB, k, j, hi, lo);                  // W2^T: B operand [n = k][k' = j]
+          tc::split_bf16(W2S * th[e], hi, lo);
+        } else {                                      // bias row: b2[j] (+ sum_k W2[k][j] in r form)
+          float b = th[e];
+          if (ACT == ACT_TANH) for (int kk = 0; kk < H; ++kk) b += th[n2 + kk * H + j];
+          tc::split_bf16(CS * b, hi, lo);
+        }
         put(w2, NB, j, k, hi, lo);
-        if (k < H) put(wt, NB, k, j, hi, lo);         // W2^T: B operand [n = k][k' = j]
       } else if (e < n5) {
-        w3s[e - n4] = th[e];                          // W3[k][0], k < H  (entries >= H stay 0: no delta for the constant unit)
+        w3s[e - n4] = DS * th[e];                     // W3[k][0], k < H  (entries >= H stay 0: no delta for the constant unit)
       } else if (e == n5) {                           // (the constant-1 unit of H1 is written with the effective bias)
       } else {                                        // the constant-1 unit of H2: act(one_in * 1) == 1
         tc::split_bf16(one_in, hi, lo);
