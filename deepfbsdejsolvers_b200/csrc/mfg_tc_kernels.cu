@@ -55,6 +55,25 @@ static_assert((OFF_BAR % 2) == 0 && (ROLE_FLOATS % 4) == 0, "alignment");
 constexpr uint32_t ROLE_COLS = 128, C_A = 32, NCOLS = 256;
 }  // namespace f
 
+// Forward sweep: tanh layers in "r form" (as reg_tc_kernels.cu): the GEMM delivers x' = 2 log2(e) x (scale in the staged weights),
+// the thread forms r = 1 / (2^x' + 1) and hands r - not h = 1 - 2 r - to the next layer, whose weights carry the factor -2 and
+// whose bias row b + sum_k W[k][.]; the constant-1 unit is r(-200) = 1.  Two instructions per hidden unit less.  (The adjoint
+// sweep keeps h: with r in its tiles the weight gradients become db - 2 sum r d, and that difference costs a factor ~3 in
+// accuracy - 5.7e-5 of the largest component against the 5e-5 bound of tests/test_tc_gpu.py.)
+template <int ACT>
+__device__ __forceinline__ float hid_r(float x) {
+  if (ACT != ACT_TANH) return fmaxf(x, 0.0f);
+  float t, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + 1.0f));
+  return r;
+}
+template <int ACT> struct RForm {
+  static constexpr float CS = ACT == ACT_TANH ? 2.885390081777927f : 1.0f;     // layer inputs: 2 log2(e)
+  static constexpr float WS = ACT == ACT_TANH ? -2.0f : 1.0f;                  // weights that meet r instead of h
+  static constexpr float ONE_IN = ACT == ACT_TANH ? -200.0f : 1.0f;            // hid_r(ONE_IN) == 1 exactly
+};
+
 template <int ACT>
 __global__ void __launch_bounds__(kT, 1) mfg_forward_tc(const MFGArgs a) {
   using namespace f;
@@ -67,7 +86,8 @@ __global__ void __launch_bounds__(kT, 1) mfg_forward_tc(const MFGArgs a) {
   float* const outx = smem + OFF_OUT;
   uint64_t* const bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR) + role;
   uint32_t* const tslot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 4);
-  const float one_in = ACT == ACT_TANH ? 20.0f : 1.0f;
+  using RF = RForm<ACT>;
+  const float one_in = RF::ONE_IN;
 
   for (int i = threadIdx.x; i < SMEM_FLOATS; i += kT) smem[i] = 0.0f;
   __syncthreads();
@@ -75,26 +95,34 @@ __global__ void __launch_bounds__(kT, 1) mfg_forward_tc(const MFGArgs a) {
   {
     const float* __restrict__ th = a.theta + net.ext_off;
     const int n1 = nin * H, n2 = n1 + H, n3 = n2 + H * H, n4 = n3 + H, n5 = n4 + H * nout, n6 = n5 + nout;
-    if (row < H) { w0 = th[row]; b1v = th[n1 + row]; }
+    if (row < H) { w0 = RF::CS * th[row]; b1v = RF::CS * th[n1 + row]; }
     for (int e = row; e < n6; e += TR) {
       float hi, lo;
       if (e < n1) {                                  // W1[i][j], i >= 1 (the time row lives in the effective bias)
         const int i = e / H, j = e % H;
         if (i >= 1) {
-          tc::split_tf32(th[e], hi, lo);
+          tc::split_tf32(RF::CS * th[e], hi, lo);
           rw[W1B_HI + ((i >> 2) * NB + j) * 4 + (i & 3)] = hi;
           rw[W1B_LO + ((i >> 2) * NB + j) * 4 + (i & 3)] = lo;
         }
       } else if (e < n2) {
-      } else if (e < n4) {                           // W2[k][j], b2[j] (k = H)
+      } else if (e < n4) {                           // W2[k][j], b2[j] (k = H; r form: + sum_k W2[k][j])
         const int k = e < n3 ? (e - n2) / H : H, j = e < n3 ? (e - n2) % H : e - n3;
-        tc::split_tf32(th[e], hi, lo);
+        float v = RF::CS * RF::WS * th[e];
+        if (k == H) {
+          v = th[e];
+          if (ACT == ACT_TANH) for (int kk = 0; kk < H; ++kk) v += th[n2 + kk * H + j];
+          v *= RF::CS;
+        }
+        tc::split_tf32(v, hi, lo);
         rw[W2B_HI + ((k >> 2) * NB + j) * 4 + (k & 3)] = hi;
         rw[W2B_LO + ((k >> 2) * NB + j) * 4 + (k & 3)] = lo;
       } else if (e < n5) {                           // W3[k][o] -> [k][4]
-        rw[OFF_W3 + ((e - n4) / nout) * 4 + (e - n4) % nout] = th[e];
-      } else {
-        rw[OFF_B3 + (e - n5)] = th[e];
+        rw[OFF_W3 + ((e - n4) / nout) * 4 + (e - n4) % nout] = RF::WS * th[e];
+      } else {                                       // b3[o] (r form: + sum_k W3[k][o])
+        float v = th[e];
+        if (ACT == ACT_TANH) for (int kk = 0; kk < H; ++kk) v += th[n4 + kk * nout + (e - n5)];
+        rw[OFF_B3 + (e - n5)] = v;
       }
     }
   }
@@ -157,7 +185,7 @@ __global__ void __launch_bounds__(kT, 1) mfg_forward_tc(const MFGArgs a) {
         tc::tmem_ld8(lane_base + 8 * c8, t8);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 8; ++q) t8[q] = actf<ACT>(t8[q]);
+        for (int q = 0; q < 8; ++q) t8[q] = hid_r<ACT>(t8[q]);
         fwd::store_tf32x8(lane_a, c8, t8);
       }
       fwd::publish_tmem();
@@ -175,7 +203,7 @@ __global__ void __launch_bounds__(kT, 1) mfg_forward_tc(const MFGArgs a) {
         tc::tmem_ld_wait();
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const float h = actf<ACT>(t8[q]);
+          const float h = hid_r<ACT>(t8[q]);
           const float4 w = ld4(rw + OFF_W3 + (8 * c8 + q) * 4);     // rows >= H are zero
           o.x = fmaf(h, w.x, o.x); o.y = fmaf(h, w.y, o.y); o.z = fmaf(h, w.z, o.z); o.w = fmaf(h, w.w, o.w);
         }
