@@ -16,8 +16,25 @@
 namespace fbsdej {
 
 // NXC: 8-feature chunks of the input row (2: up to 15 inputs + the constant 1, d = 1; 3: up to 23, d = 10)
+// Forward evaluations: tanh layers in "r form" (as reg_forward_tc): the GEMM delivers x' = 2 log2(e) x (scale in the staged
+// weights), the thread forms r = 1 / (2^x' + 1) and hands r - not h = 1 - 2 r - to the next layer, whose weights carry the factor
+// -2 and whose bias b + sum_k W[k][.]; the constant-1 unit is r(-200) = 1.  Two instructions per hidden unit less.  (The adjoint
+// block keeps h: r in its tiles would turn the weight gradients into db - 2 sum r d, a difference the jump schemes' accuracy
+// cannot afford.)
+template <int ACT>
+__device__ __forceinline__ float jump_hid_r(float x) {
+  if (ACT != ACT_TANH) return fmaxf(x, 0.0f);
+  float t, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + 1.0f));
+  return r;
+}
+
 template <int ACT, int NXC>
 struct JumpTcFwd {
+  static constexpr float CS = ACT == ACT_TANH ? 2.885390081777927f : 1.0f;   // layer inputs: 2 log2(e)
+  static constexpr float WS = ACT == ACT_TANH ? -2.0f : 1.0f;                // weights that meet r instead of h
+  static constexpr float ONE_IN = ACT == ACT_TANH ? -200.0f : 1.0f;          // jump_hid_r(ONE_IN) == 1 exactly
   static_assert(NXC == 2 || NXC == 3, "input row of 16 or 24 features");
   // shared memory (floats): B operands of the two layers (TF32 hi / lo), W3 + b3, the mbarrier, the TMEM slots
   static constexpr int NBR = rtc::NB, NI = 8 * NXC;
@@ -39,21 +56,32 @@ struct JumpTcFwd {
     const float* __restrict__ th = theta + rt.ext_off;
     const int n1 = nin * H, n2 = n1 + H, n3 = n2 + H * H, n4 = n3 + H, nout = rt.nout;
     w0 = 0.0f; b1v = 0.0f;
-    if (row < H) { w0 = th[row]; b1v = th[n1 + row]; }
-    if (row <= H) sm[OFF_W3 + (row < H ? row : 24)] = th[n4 + row * nout];   // W3[k][0], k < H; b3[0] at index 24
+    if (row < H) { w0 = CS * th[row]; b1v = CS * th[n1 + row]; }
+    if (row < H) sm[OFF_W3 + row] = WS * th[n4 + row * nout];                // W3[k][0], k < H
+    if (row == H) {                                                          // b3[0] at index 24 (r form: + sum_k W3[k][0])
+      float b = th[n4 + H * nout];
+      if (ACT == ACT_TANH) for (int k = 0; k < H; ++k) b += th[n4 + k * nout];
+      sm[OFF_W3 + 24] = b;
+    }
     for (int e = row; e < n4; e += kThreads) {
       float hi, lo;
       if (e < n1) {
         const int i = e / H, j = e % H;
         if (i >= 1) {
-          tc::split_tf32(th[e], hi, lo);
+          tc::split_tf32(CS * th[e], hi, lo);
           sm[W1B_HI + ((i >> 2) * NBR + j) * 4 + (i & 3)] = hi;
           sm[W1B_LO + ((i >> 2) * NBR + j) * 4 + (i & 3)] = lo;
         }
       } else if (e < n2) {
       } else {
         const int k = e < n3 ? (e - n2) / H : H, j = e < n3 ? (e - n2) % H : e - n3;
-        tc::split_tf32(th[e], hi, lo);
+        float v = CS * WS * th[e];
+        if (k == H) {                                                        // bias row (r form: + sum_k W2[k][j])
+          v = th[e];
+          if (ACT == ACT_TANH) for (int kk = 0; kk < H; ++kk) v += th[n2 + kk * H + j];
+          v *= CS;
+        }
+        tc::split_tf32(v, hi, lo);
         sm[W2B_HI + ((k >> 2) * NBR + j) * 4 + (k & 3)] = hi;
         sm[W2B_LO + ((k >> 2) * NBR + j) * 4 + (k & 3)] = lo;
       }
@@ -75,7 +103,7 @@ struct JumpTcFwd {
     const int row = threadIdx.x;
     if (row <= H) {
       float hi, lo;
-      tc::split_tf32(row < H ? fmaf(t, w0, b1v) : (ACT == ACT_TANH ? 20.0f : 1.0f), hi, lo);
+      tc::split_tf32(row < H ? fmaf(t, w0, b1v) : ONE_IN, hi, lo);
       sm[W1B_HI + bias_idx] = hi;
       sm[W1B_LO + bias_idx] = lo;
     }
@@ -99,7 +127,7 @@ struct JumpTcFwd {
       tc::tmem_ld8(lane_base + 8 * c8, t8);
       tc::tmem_ld_wait();
 #pragma unroll
-      for (int q = 0; q < 8; ++q) t8[q] = actf<ACT>(t8[q]);
+      for (int q = 0; q < 8; ++q) t8[q] = jump_hid_r<ACT>(t8[q]);
       fwd::store_tf32x8(lane_a, c8, t8);
     }
     fwd::publish_tmem();
@@ -118,7 +146,7 @@ struct JumpTcFwd {
       const float4 wa = ld4(sm + OFF_W3 + 8 * c8), wb = ld4(sm + OFF_W3 + 8 * c8 + 4);
       const float w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
-      for (int q = 0; q < 8; ++q) y = fmaf(actf<ACT>(t8[q]), w8[q], y);
+      for (int q = 0; q < 8; ++q) y = fmaf(jump_hid_r<ACT>(t8[q]), w8[q], y);
     }
     tc::tc_fence_before();
     return y;
@@ -157,7 +185,7 @@ struct JumpTcFwd {
       const float cv[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
       float t8[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) t8[q] = actf<ACT>(fmaf(scale, cv[q], pre[8 * c8 + q]));
+      for (int q = 0; q < 8; ++q) t8[q] = jump_hid_r<ACT>(fmaf(CS * scale, cv[q], pre[8 * c8 + q]));
       fwd::store_tf32x8(lane_a, c8, t8);
     }
     fwd::publish_tmem();
@@ -176,7 +204,7 @@ struct JumpTcFwd {
       const float4 wa = ld4(sm + OFF_W3 + 8 * c8), wb = ld4(sm + OFF_W3 + 8 * c8 + 4);
       const float w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
-      for (int q = 0; q < 8; ++q) y = fmaf(actf<ACT>(t8[q]), w8[q], y);
+      for (int q = 0; q < 8; ++q) y = fmaf(jump_hid_r<ACT>(t8[q]), w8[q], y);
     }
     tc::tc_fence_before();
     return y;
